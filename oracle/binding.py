@@ -1,0 +1,294 @@
+"""ctypes bindings for the two CPU checkers -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+  * ``Oracle("port")``  -> oracle/liboracle.so        (plain-C restatement, oracle/dmz_oracle.c)
+  * ``Oracle("ref")``   -> oracle/_ref/libdmz_ref.so  (the reference's own sources + cvshim)
+
+Both expose the same stage taps (prefix ``orc_`` / ``ref_``), so a test can run either.  Only
+tests/, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference`` legs may
+import this module; the product path never does.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+WEIGHTS_DIR = os.path.join(ROOT, "card.io-dmz_b200", "weights")
+
+
+class VSeg(C.Structure):
+    _fields_ = [("score", C.c_float), ("y_offset", C.c_uint16), ("pattern_type", C.c_uint8),
+                ("number_pattern", C.c_uint8 * 19), ("number_pattern_length", C.c_uint8),
+                ("number_length", C.c_uint8)]
+
+
+class HSeg(C.Structure):
+    _fields_ = [("n_offsets", C.c_uint8), ("offsets", C.c_uint16 * 16), ("score", C.c_float),
+                ("number_width", C.c_float), ("pattern_offset", C.c_uint16)]
+
+
+class Line(C.Structure):
+    _fields_ = [("found", C.c_int32), ("r", C.c_int32), ("n", C.c_int32), ("max_votes", C.c_int32),
+                ("low", C.c_int32), ("high", C.c_int32), ("n_edge_px", C.c_int32),
+                ("rho", C.c_float), ("theta", C.c_float)]
+
+
+class Detect(C.Structure):
+    _fields_ = [("found", C.c_int32 * 4), ("rho", C.c_float * 4), ("theta", C.c_float * 4),
+                ("corners", C.c_float * 8), ("all_found", C.c_int32)]
+
+
+class Scan(C.Structure):
+    _fields_ = [("scores", C.c_float * 160), ("hseg", HSeg), ("vseg", VSeg),
+                ("usable", C.c_uint8), ("upside_down", C.c_uint8), ("pad", C.c_uint8 * 2)]
+
+
+class FrameRecord(C.Structure):
+    _fields_ = [("detect", Detect), ("scan", Scan), ("card_crc", C.c_uint32)]
+
+
+assert C.sizeof(VSeg) == 28 and C.sizeof(HSeg) == 48 and C.sizeof(Scan) == 720, (
+    C.sizeof(VSeg), C.sizeof(HSeg), C.sizeof(Scan))
+
+RECORD_DTYPE = np.dtype([
+    ("found", "<i4", 4), ("rho", "<f4", 4), ("theta", "<f4", 4), ("corners", "<f4", 8), ("all_found", "<i4"),
+    ("scores", "<f4", 160),
+    ("h_n_offsets", "u1"), ("_p0", "u1"), ("h_offsets", "<u2", 16), ("_p1", "u1", 2), ("h_score", "<f4"),
+    ("h_number_width", "<f4"), ("h_pattern_offset", "<u2"), ("_p2", "u1", 2),
+    ("v_score", "<f4"), ("v_y_offset", "<u2"), ("v_pattern_type", "u1"), ("v_number_pattern", "u1", 19),
+    ("v_number_pattern_length", "u1"), ("v_number_length", "u1"),
+    ("usable", "u1"), ("upside_down", "u1"), ("_p4", "u1", 2),
+    ("card_crc", "<u4"),
+])
+assert RECORD_DTYPE.itemsize == C.sizeof(FrameRecord), (RECORD_DTYPE.itemsize, C.sizeof(FrameRecord))
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def lib_path(kind):
+    return os.path.join(HERE, "liboracle.so") if kind == "port" else os.path.join(HERE, "_ref", "libdmz_ref.so")
+
+
+def available(kind):
+    return os.path.exists(lib_path(kind))
+
+
+class Oracle:
+    """Uniform front-end over either checker library."""
+
+    def __init__(self, kind="port"):
+        assert kind in ("port", "ref")
+        self.kind = kind
+        self.prefix = "orc_" if kind == "port" else "ref_"
+        self.lib = C.CDLL(lib_path(kind))
+        if kind == "port":
+            self.lib.orc_load_weights.argtypes = [C.c_char_p]
+            rc = self.lib.orc_load_weights(WEIGHTS_DIR.encode())
+            if rc != 0:
+                raise RuntimeError("oracle: cannot load weights from " + WEIGHTS_DIR)
+        f = self._f
+        vp, i, fp = C.c_void_p, C.c_int, C.POINTER(C.c_float)
+        f("detection_boxes", [i, i, i, vp])
+        f("sobel7", [vp, i, i, i, vp, vp])
+        f("adaptive_canny", [vp, i, i, i, vp, vp, vp, vp, vp])
+        f("best_line", [vp, i, i, i, i, C.POINTER(Line)])
+        f("detect_edges", [vp, i, i, i, vp, vp, i, i, C.POINTER(Detect)], i)
+        f("calc_persp_transform", [vp, vp, vp])
+        f("transform_card", [vp, i, i, i, vp, i, vp])
+        f("vseg_row", [vp, i, vp])
+        f("vseg_model", [vp, vp])
+        f("best_n_vseg", [vp, C.POINTER(VSeg)])
+        f("best_n_hseg", [vp, C.POINTER(VSeg), C.POINTER(HSeg)])
+        f("number_scores", [vp, i, C.POINTER(HSeg), vp])
+        f("digit_patch_prep", [vp, i, vp])
+        f("digit_models", [vp, vp])
+        f("scan_card_image", [vp, C.POINTER(Scan)])
+        f("process_frame", [vp, i, i, i, vp, vp, i, i, vp, vp])
+        f("scanner_new", [], vp)
+        f("scanner_free", [vp])
+        f("scanner_reset", [vp])
+        f("scanner_add_frame", [vp, vp, C.POINTER(Scan)])
+        f("scanner_peek", [vp, vp, vp, vp])
+        f("scanner_result", [vp, vp, C.POINTER(C.c_int32)], i)
+        f("luhn", [vp, i], i)
+        f("card_type", [vp, i], i)
+        f("bench_frames", [vp, i, i, i, vp, vp, i, i, vp], C.c_double)
+        if kind == "ref":
+            self.lib.ref_run_kats.restype = i
+            self.lib.ref_sizeof.argtypes = [i]
+        else:
+            self.lib.orc_scanner_add_scan.argtypes = [vp, C.POINTER(Scan)]
+            self.lib.orc_crc32.argtypes = [vp, C.c_size_t]
+            self.lib.orc_crc32.restype = C.c_uint32
+
+    def _f(self, name, argtypes, restype=None):
+        fn = getattr(self.lib, self.prefix + name)
+        fn.argtypes = argtypes
+        fn.restype = restype
+        setattr(self, "_" + name, fn)
+
+    # ---- stage taps -------------------------------------------------------------------------
+    def detection_boxes(self, w, h, orientation=3):
+        out = np.zeros(16, np.int32)
+        self._detection_boxes(w, h, orientation, _p(out))
+        return out.reshape(4, 4)  # top, bottom, left, right  x  (x, y, w, h)
+
+    def sobel7(self, img):
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w = img.shape
+        dx = np.zeros((h, w), np.int16)
+        dy = np.zeros((h, w), np.int16)
+        self._sobel7(_p(img), w, w, h, _p(dx), _p(dy))
+        return dx, dy
+
+    def adaptive_canny(self, img, dx, dy):
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w = img.shape
+        dx = np.ascontiguousarray(dx, np.int16)
+        dy = np.ascontiguousarray(dy, np.int16)
+        edges = np.zeros((h, w), np.uint8)
+        lo, hi = C.c_int32(), C.c_int32()
+        self._adaptive_canny(_p(img), w, w, h, _p(dx), _p(dy), _p(edges), C.addressof(lo), C.addressof(hi))
+        return edges, lo.value, hi.value
+
+    def best_line(self, img, vertical):
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w = img.shape
+        out = Line()
+        self._best_line(_p(img), w, w, h, int(vertical), C.byref(out))
+        return out
+
+    def detect_edges(self, y, cb=None, cr=None, orientation=3):
+        y = np.ascontiguousarray(y, np.uint8)
+        h, w = y.shape
+        if cb is None:
+            cb = np.full((h // 2, w // 2), 128, np.uint8)
+        if cr is None:
+            cr = np.full((h // 2, w // 2), 128, np.uint8)
+        cb = np.ascontiguousarray(cb, np.uint8)
+        cr = np.ascontiguousarray(cr, np.uint8)
+        out = Detect()
+        self._detect_edges(_p(y), w, h, w, _p(cb), _p(cr), w // 2, orientation, C.byref(out))
+        return out
+
+    def calc_persp_transform(self, src, dst):
+        src = np.ascontiguousarray(src, np.float32).reshape(8)
+        dst = np.ascontiguousarray(dst, np.float32).reshape(8)
+        m = np.zeros(9, np.float32)
+        self._calc_persp_transform(_p(src), _p(dst), _p(m))
+        return m.reshape(3, 3)
+
+    def transform_card(self, y, corners, orientation=3):
+        y = np.ascontiguousarray(y, np.uint8)
+        h, w = y.shape
+        corners = np.ascontiguousarray(corners, np.float32).reshape(8)
+        card = np.zeros((270, 428), np.uint8)
+        self._transform_card(_p(y), w, h, w, _p(corners), orientation, _p(card))
+        return card
+
+    def vseg_row(self, card, row):
+        card = np.ascontiguousarray(card, np.uint8)
+        out = np.zeros(3, np.float32)
+        self._vseg_row(_p(card), int(row), _p(out))
+        return out
+
+    def vseg_model(self, x204):
+        x = np.ascontiguousarray(x204, np.float32)
+        out = np.zeros(3, np.float32)
+        self._vseg_model(_p(x), _p(out))
+        return out
+
+    def best_n_vseg(self, card):
+        card = np.ascontiguousarray(card, np.uint8)
+        out = VSeg()
+        self._best_n_vseg(_p(card), C.byref(out))
+        return out
+
+    def best_n_hseg(self, card, vseg):
+        card = np.ascontiguousarray(card, np.uint8)
+        out = HSeg()
+        self._best_n_hseg(_p(card), C.byref(vseg), C.byref(out))
+        return out
+
+    def number_scores(self, card, y_offset, hseg):
+        card = np.ascontiguousarray(card, np.uint8)
+        out = np.zeros((16, 10), np.float32)
+        self._number_scores(_p(card), int(y_offset), C.byref(hseg), _p(out))
+        return out
+
+    def digit_patch_prep(self, img27x19):
+        img = np.ascontiguousarray(img27x19, np.uint8)
+        assert img.shape == (27, 19)
+        out = np.zeros((27, 19), np.float32)
+        self._digit_patch_prep(_p(img), 19, _p(out))
+        return out
+
+    def digit_models(self, patch):
+        patch = np.ascontiguousarray(patch, np.float32).reshape(27 * 19)
+        out = np.zeros(40, np.float32)
+        self._digit_models(_p(patch), _p(out))
+        return out[:10].copy(), out[10:].reshape(3, 10).copy()
+
+    def scan_card_image(self, card):
+        card = np.ascontiguousarray(card, np.uint8)
+        out = Scan()
+        self._scan_card_image(_p(card), C.byref(out))
+        return out
+
+    def process_frames(self, frames, orientation=3, want_cards=False):
+        """frames: (n, h, w) u8. Returns a RECORD_DTYPE array (and the cards if asked)."""
+        frames = np.ascontiguousarray(frames, np.uint8)
+        n, h, w = frames.shape
+        cb = np.full((h // 2, w // 2), 128, np.uint8)
+        recs = np.zeros(n, RECORD_DTYPE)
+        cards = np.zeros((n, 270, 428), np.uint8) if want_cards else None
+        for k in range(n):
+            self._process_frame(_p(frames[k]), w, h, w, _p(cb), _p(cb), w // 2, orientation,
+                                recs[k:k + 1].ctypes.data_as(C.c_void_p),
+                                _p(cards[k]) if want_cards else None)
+        return (recs, cards) if want_cards else recs
+
+    def bench_frames(self, frames, nthreads, orientation=3):
+        frames = np.ascontiguousarray(frames, np.uint8)
+        n, h, w = frames.shape
+        cb = np.full((h // 2, w // 2), 128, np.uint8)
+        recs = np.zeros(n, RECORD_DTYPE)
+        secs = self._bench_frames(_p(frames), n, w, h, _p(cb), _p(cb), orientation, int(nthreads), _p(recs))
+        return secs, recs
+
+    # ---- scanner session --------------------------------------------------------------------
+    def scanner_new(self):
+        return self._scanner_new()
+
+    def scanner_free(self, s):
+        self._scanner_free(s)
+
+    def scanner_add_frame(self, s, card):
+        card = np.ascontiguousarray(card, np.uint8)
+        out = Scan()
+        self._scanner_add_frame(s, _p(card), C.byref(out))
+        return out
+
+    def scanner_peek(self, s):
+        a15 = np.zeros((16, 10), np.float32)
+        a16 = np.zeros((16, 10), np.float32)
+        cnt = np.zeros(2, np.int32)
+        self._scanner_peek(s, _p(a15), _p(a16), _p(cnt))
+        return a15, a16, cnt
+
+    def scanner_result(self, s):
+        digits = np.zeros(16, np.uint8)
+        n = C.c_int32()
+        complete = self._scanner_result(s, _p(digits), C.byref(n))
+        return bool(complete), digits[: n.value].copy()
+
+    def luhn(self, digits):
+        d = np.ascontiguousarray(digits, np.uint8)
+        return bool(self._luhn(_p(d), len(d)))
+
+    def card_type(self, digits):
+        d = np.ascontiguousarray(digits, np.uint8)
+        return int(self._card_type(_p(d), len(d)))
