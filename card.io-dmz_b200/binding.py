@@ -1,0 +1,283 @@
+"""ctypes mirror of include/b200_dmz.h.  Raises if the CUDA extension is missing or fails: there is no
+CPU fallback on the product path."""
+import ctypes as C
+import os
+
+import numpy as np
+
+__all__ = ["Dmz", "Scanner", "B200Error", "lib_path", "Edges", "CornerPoints", "VSeg", "HSeg", "Scan", "Line",
+           "FrameRecord", "RECORD_DTYPE", "SCAN_DTYPE", "LINE_DTYPE", "MEM_HOST", "MEM_DEVICE", "CARD_W", "CARD_H"]
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+MEM_HOST, MEM_DEVICE = 0, 1
+CARD_W, CARD_H = 428, 270
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+def lib_path():
+    return os.path.join(HERE, "libb200dmz.so")
+
+
+class FoundEdge(C.Structure):
+    _fields_ = [("found", C.c_int32), ("rho", C.c_float), ("theta", C.c_float)]
+
+
+class Edges(C.Structure):
+    _fields_ = [("top", FoundEdge), ("left", FoundEdge), ("bottom", FoundEdge), ("right", FoundEdge)]
+
+
+class CornerPoints(C.Structure):
+    _fields_ = [("top_left", C.c_float * 2), ("bottom_left", C.c_float * 2), ("top_right", C.c_float * 2),
+                ("bottom_right", C.c_float * 2)]
+
+
+class VSeg(C.Structure):
+    _fields_ = [("score", C.c_float), ("y_offset", C.c_uint16), ("pattern_type", C.c_uint8),
+                ("number_pattern", C.c_uint8 * 19), ("number_pattern_length", C.c_uint8), ("number_length", C.c_uint8)]
+
+
+class HSeg(C.Structure):
+    _fields_ = [("n_offsets", C.c_uint8), ("offsets", C.c_uint16 * 16), ("score", C.c_float),
+                ("number_width", C.c_float), ("pattern_offset", C.c_uint16)]
+
+
+class Scan(C.Structure):
+    _fields_ = [("scores", C.c_float * 160), ("hseg", HSeg), ("vseg", VSeg), ("usable", C.c_uint8),
+                ("upside_down", C.c_uint8), ("pad", C.c_uint8 * 2)]
+
+
+class Line(C.Structure):
+    _fields_ = [("found", C.c_int32), ("r", C.c_int32), ("n", C.c_int32), ("max_votes", C.c_int32), ("low", C.c_int32),
+                ("high", C.c_int32), ("n_edge_px", C.c_int32), ("rho", C.c_float), ("theta", C.c_float)]
+
+
+class FrameRecord(C.Structure):
+    _fields_ = [("found", C.c_int32 * 4), ("rho", C.c_float * 4), ("theta", C.c_float * 4), ("corners", C.c_float * 8),
+                ("all_found", C.c_int32), ("scan", Scan), ("card_check", C.c_uint32)]
+
+
+_SCAN_FIELDS = [
+    ("scores", "<f4", 160),
+    ("h_n_offsets", "u1"), ("_p0", "u1"), ("h_offsets", "<u2", 16), ("_p1", "u1", 2), ("h_score", "<f4"),
+    ("h_number_width", "<f4"), ("h_pattern_offset", "<u2"), ("_p2", "u1", 2),
+    ("v_score", "<f4"), ("v_y_offset", "<u2"), ("v_pattern_type", "u1"), ("v_number_pattern", "u1", 19),
+    ("v_number_pattern_length", "u1"), ("v_number_length", "u1"),
+    ("usable", "u1"), ("upside_down", "u1"), ("_p4", "u1", 2),
+]
+SCAN_DTYPE = np.dtype(_SCAN_FIELDS)
+RECORD_DTYPE = np.dtype([("found", "<i4", 4), ("rho", "<f4", 4), ("theta", "<f4", 4), ("corners", "<f4", 8),
+                         ("all_found", "<i4")] + _SCAN_FIELDS + [("card_check", "<u4")])
+LINE_DTYPE = np.dtype([("found", "<i4"), ("r", "<i4"), ("n", "<i4"), ("max_votes", "<i4"), ("low", "<i4"),
+                       ("high", "<i4"), ("n_edge_px", "<i4"), ("rho", "<f4"), ("theta", "<f4")])
+assert SCAN_DTYPE.itemsize == C.sizeof(Scan) == 720
+assert RECORD_DTYPE.itemsize == C.sizeof(FrameRecord) == 808
+assert LINE_DTYPE.itemsize == C.sizeof(Line) == 36
+
+_lib = None
+
+
+def _load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise B200Error("CUDA extension %s is not built (run __graft_entry__.build()); there is no CPU fallback" % path)
+    lib = C.CDLL(path)
+    vp, i, sz = C.c_void_p, C.c_int, C.c_size_t
+    lib.b200_ctx_create.argtypes = [C.POINTER(vp), i, C.c_char_p]
+    lib.b200_ctx_destroy.argtypes = [vp]
+    lib.b200_last_error.argtypes = [vp]
+    lib.b200_last_error.restype = C.c_char_p
+    lib.b200_ctx_reserve.argtypes = [vp, i, i, i]
+    lib.b200_launch_count.argtypes = [vp]
+    lib.b200_launch_count.restype = C.c_uint64
+    lib.b200_ctx_stream.argtypes = [vp]
+    lib.b200_ctx_stream.restype = vp
+    lib.b200_detect_edges_batch.argtypes = [vp, vp, i, sz, vp, vp, i, sz, i, i, i, i, i, vp, vp, vp, vp]
+    lib.b200_transform_card_batch.argtypes = [vp, vp, i, sz, i, i, i, vp, vp, i, i, i, vp]
+    lib.b200_scan_cards_batch.argtypes = [vp, vp, i, vp, i, vp]
+    lib.b200_process_frames_batch.argtypes = [vp, vp, i, sz, i, i, i, i, i, vp, vp]
+    lib.b200_calc_persp_transform_batch.argtypes = [vp, vp, vp, i, vp]
+    lib.b200_categorize_patches_batch.argtypes = [vp, vp, i, i, vp]
+    lib.b200_vseg_model_batch.argtypes = [vp, vp, i, i, vp]
+    lib.b200_scanner_new.restype = vp
+    lib.b200_scanner_free.argtypes = [vp]
+    lib.b200_scanner_reset.argtypes = [vp]
+    lib.b200_scanner_add_scan.argtypes = [vp, vp]
+    lib.b200_scanner_result.argtypes = [vp, vp, C.POINTER(C.c_int32)]
+    lib.b200_scanner_peek.argtypes = [vp, vp, vp, vp]
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Dmz:
+    """One b200_ctx (device, stream, weights, scratch).  NumPy arrays = host buffers (B200_MEM_HOST);
+    integer addresses = device pointers (B200_MEM_DEVICE)."""
+
+    def __init__(self, device=0, weights_dir=None):
+        self.lib = _load()
+        self.ctx = C.c_void_p()
+        rc = self.lib.b200_ctx_create(C.byref(self.ctx), device, weights_dir.encode() if weights_dir else None)
+        if rc != 0:
+            msg = self.lib.b200_last_error(self.ctx).decode() if self.ctx else "context allocation failed"
+            if self.ctx:
+                self.lib.b200_ctx_destroy(self.ctx)
+                self.ctx = None
+            raise B200Error("b200_ctx_create failed (%d): %s" % (rc, msg))
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.b200_ctx_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise B200Error("b200 call failed (%d): %s" % (rc, self.lib.b200_last_error(self.ctx).decode()))
+
+    @property
+    def launches(self):
+        return int(self.lib.b200_launch_count(self.ctx))
+
+    @property
+    def stream(self):
+        return self.lib.b200_ctx_stream(self.ctx)
+
+    def reserve(self, n, w, h):
+        self._check(self.lib.b200_ctx_reserve(self.ctx, n, w, h))
+
+    # ---- host-buffer API (numpy) -----------------------------------------------------------------
+    def detect_edges(self, y, cb=None, cr=None, orientation=3, want_lines=False):
+        """y: (n,h,w) u8.  Returns (edges[n] as structured array view, corners (n,8), all_found (n,), lines (n,4))."""
+        y = np.ascontiguousarray(y, np.uint8)
+        n, h, w = y.shape
+        if cb is not None:
+            cb = np.ascontiguousarray(cb, np.uint8)
+            cr = np.ascontiguousarray(cr, np.uint8)
+        edges = np.zeros((n, 4, 3), np.float32)  # placeholder raw view: (found:int32, rho, theta) per edge
+        edges_raw = np.zeros(n * 12, np.int32)
+        corners = np.zeros((n, 8), np.float32)
+        found = np.zeros(n, np.uint8)
+        lines = np.zeros((n, 4), LINE_DTYPE) if want_lines else None
+        self._check(self.lib.b200_detect_edges_batch(self.ctx, _ptr(y), w, w * h, _ptr(cb), _ptr(cr), w // 2,
+                                                     (w // 2) * (h // 2), w, h, n, orientation, MEM_HOST,
+                                                     _ptr(edges_raw), _ptr(corners), _ptr(found), _ptr(lines)))
+        er = edges_raw.reshape(n, 4, 3)
+        out = {"found": er[:, :, 0].copy(), "rho": er[:, :, 1].copy().view(np.float32), "theta": er[:, :, 2].copy().view(np.float32)}
+        return out, corners, found, lines
+
+    def transform_card(self, frames, corners, valid=None, orientation=3, upsample=False):
+        frames = np.ascontiguousarray(frames, np.uint8)
+        n, h, w = frames.shape
+        corners = np.ascontiguousarray(corners, np.float32).reshape(n, 8)
+        if valid is not None:
+            valid = np.ascontiguousarray(valid, np.uint8)
+        cards = np.zeros((n, CARD_H, CARD_W), np.uint8)
+        self._check(self.lib.b200_transform_card_batch(self.ctx, _ptr(frames), w, w * h, w, h, n, _ptr(corners), _ptr(valid),
+                                                       orientation, int(upsample), MEM_HOST, _ptr(cards)))
+        return cards
+
+    def scan_cards(self, cards, valid=None):
+        cards = np.ascontiguousarray(cards, np.uint8)
+        n = cards.shape[0]
+        assert cards.shape[1:] == (CARD_H, CARD_W)
+        if valid is not None:
+            valid = np.ascontiguousarray(valid, np.uint8)
+        scans = np.zeros(n, SCAN_DTYPE)
+        self._check(self.lib.b200_scan_cards_batch(self.ctx, _ptr(cards), n, _ptr(valid), MEM_HOST, _ptr(scans)))
+        return scans
+
+    def process_frames(self, frames, orientation=3, want_cards=False):
+        frames = np.ascontiguousarray(frames, np.uint8)
+        n, h, w = frames.shape
+        recs = np.zeros(n, RECORD_DTYPE)
+        cards = np.zeros((n, CARD_H, CARD_W), np.uint8) if want_cards else None
+        self._check(self.lib.b200_process_frames_batch(self.ctx, _ptr(frames), w, w * h, w, h, n, orientation, MEM_HOST,
+                                                       _ptr(recs), _ptr(cards)))
+        return (recs, cards) if want_cards else recs
+
+    def calc_persp_transform(self, src, dst):
+        src = np.ascontiguousarray(src, np.float32).reshape(-1, 8)
+        dst = np.ascontiguousarray(dst, np.float32).reshape(-1, 8)
+        n = src.shape[0]
+        m = np.zeros((n, 9), np.float32)
+        self._check(self.lib.b200_calc_persp_transform_batch(self.ctx, _ptr(src), _ptr(dst), n, _ptr(m)))
+        return m.reshape(n, 3, 3)
+
+    def categorize_patches(self, patches):
+        patches = np.ascontiguousarray(patches, np.uint8).reshape(-1, 27, 19)
+        n = patches.shape[0]
+        out = np.zeros((n, 40), np.float32)
+        self._check(self.lib.b200_categorize_patches_batch(self.ctx, _ptr(patches), n, MEM_HOST, _ptr(out)))
+        return out[:, :10].copy(), out[:, 10:].reshape(n, 3, 10).copy()
+
+    def vseg_model(self, rows):
+        rows = np.ascontiguousarray(rows, np.float32).reshape(-1, 204)
+        n = rows.shape[0]
+        out = np.zeros((n, 3), np.float32)
+        self._check(self.lib.b200_vseg_model_batch(self.ctx, _ptr(rows), n, MEM_HOST, _ptr(out)))
+        return out
+
+    # ---- device-pointer API (bench: inputs resident in HBM) ----------------------------------------
+    def process_frames_device(self, d_frames, n, w, h, d_records, d_cards=None, orientation=3, row_stride=None, frame_stride=None):
+        self._check(self.lib.b200_process_frames_batch(self.ctx, C.c_void_p(d_frames), row_stride or w, frame_stride or w * h,
+                                                       w, h, n, orientation, MEM_DEVICE, C.c_void_p(d_records),
+                                                       C.c_void_p(d_cards) if d_cards else None))
+
+    def process_frames_host_ptr(self, h_frames, n, w, h, h_records, orientation=3):
+        """Host pointers given as integers (e.g. pinned torch tensors): the e2e path, copies inside the call."""
+        self._check(self.lib.b200_process_frames_batch(self.ctx, C.c_void_p(h_frames), w, w * h, w, h, n, orientation,
+                                                       MEM_HOST, C.c_void_p(h_records), None))
+
+
+class Scanner:
+    """scanner_* session (scan/scan.h:50-72) over b200_scan records."""
+
+    def __init__(self):
+        self.lib = _load()
+        self.s = self.lib.b200_scanner_new()
+
+    def close(self):
+        if self.s:
+            self.lib.b200_scanner_free(self.s)
+            self.s = None
+
+    def reset(self):
+        self.lib.b200_scanner_reset(self.s)
+
+    def add_scan(self, scan_record):
+        """scan_record: one element of a SCAN_DTYPE array, or the scan part of a RECORD_DTYPE element."""
+        buf = np.zeros(1, SCAN_DTYPE)
+        for name in SCAN_DTYPE.names:
+            buf[0][name] = scan_record[name]
+        self.lib.b200_scanner_add_scan(self.s, _ptr(buf))
+
+    def peek(self):
+        a15 = np.zeros((16, 10), np.float32)
+        a16 = np.zeros((16, 10), np.float32)
+        cnt = np.zeros(2, np.int32)
+        self.lib.b200_scanner_peek(self.s, _ptr(a15), _ptr(a16), _ptr(cnt))
+        return a15, a16, cnt
+
+    def result(self):
+        digits = np.zeros(16, np.uint8)
+        n = C.c_int32()
+        complete = self.lib.b200_scanner_result(self.s, _ptr(digits), C.byref(n))
+        return bool(complete), digits[: n.value].copy()

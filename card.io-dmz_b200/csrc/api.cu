@@ -1,0 +1,471 @@
+// card.io-dmz_b200/csrc/api.cu -- the extern "C" boundary (include/b200_dmz.h): context, device memory,
+// host<->device staging and the per-call kernel sequences.  No CPU fallback exists: if CUDA is
+// unavailable every entry point fails with B200_ECUDA.
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "b200_internal.h"
+
+namespace {
+constexpr int kDetectThreads = 416;  // must match detect.cu
+constexpr size_t kCardBytes = (size_t)B200_CARD_W * B200_CARD_H;
+}  // namespace
+
+struct b200_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string error;
+  uint64_t launches = 0;
+
+  // weights
+  float *d_vseg = nullptr;
+  float *d_cnn[3] = {nullptr, nullptr, nullptr};
+  float *d_hwT = nullptr;
+  NetWeights wts{};
+
+  // geometry cache
+  int cfg_w = 0, cfg_h = 0, cfg_orient = 0, cfg_planes = 0;
+  DetectParams dp[2];  // Y, chroma
+  GeomParams gp;
+
+  // device scratch, sized for `cap` frames of cap_w x cap_h
+  int cap = 0, cap_w = 0, cap_h = 0;
+  uint8_t *d_frames = nullptr, *d_cb = nullptr, *d_cr = nullptr;
+  b200_line *d_lines = nullptr;  // 3 * cap * 4
+  FrameGeom *d_geom = nullptr;
+  uint8_t *d_cards = nullptr;
+  float *d_vprob = nullptr;
+  b200_scan *d_scan = nullptr;
+  b200_frame_record *d_records = nullptr;
+  int16_t *d_grad = nullptr;
+  size_t grad_elems = 0;
+  // small staging buffers for host-mode outputs
+  void *d_misc = nullptr;
+  size_t misc_bytes = 0;
+  void *h_pinned = nullptr;
+  size_t pinned_bytes = 0;
+};
+
+namespace {
+
+int fail(b200_ctx *c, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (c) c->error = buf;
+  return code;
+}
+
+#define CU(call)                                                                                     \
+  do {                                                                                               \
+    cudaError_t e_ = (call);                                                                         \
+    if (e_ != cudaSuccess) return fail(ctx, B200_ECUDA, "%s: %s", #call, cudaGetErrorString(e_));    \
+  } while (0)
+
+#define LAUNCH(call)                                                                                  \
+  do {                                                                                                \
+    int rc_ = (call);                                                                                 \
+    if (rc_ < 0) return fail(ctx, B200_ECUDA, "%s: %s", #call, cudaGetErrorString(cudaGetLastError())); \
+    ctx->launches += (uint64_t)rc_;                                                                   \
+  } while (0)
+
+bool read_blob(const std::string &path, std::vector<float> *out, size_t floats) {
+  FILE *f = fopen(path.c_str(), "rb");
+  if (!f) return false;
+  out->resize(floats);
+  size_t got = fread(out->data(), sizeof(float), floats, f);
+  fclose(f);
+  return got == floats;
+}
+
+std::string default_weights_dir() {
+  const char *env = getenv("B200_DMZ_WEIGHTS");
+  if (env && *env) return env;
+  Dl_info info;
+  if (dladdr((void *)&default_weights_dir, &info) && info.dli_fname) {
+    std::string p = info.dli_fname;
+    size_t slash = p.find_last_of('/');
+    std::string dir = slash == std::string::npos ? "." : p.substr(0, slash);
+    return dir + "/weights";
+  }
+  return "weights";
+}
+
+void free_scratch(b200_ctx *c) {
+  cudaFree(c->d_frames), cudaFree(c->d_cb), cudaFree(c->d_cr), cudaFree(c->d_lines), cudaFree(c->d_geom);
+  cudaFree(c->d_cards), cudaFree(c->d_vprob), cudaFree(c->d_scan), cudaFree(c->d_records), cudaFree(c->d_grad);
+  c->d_frames = c->d_cb = c->d_cr = nullptr;
+  c->d_lines = nullptr, c->d_geom = nullptr, c->d_cards = nullptr, c->d_vprob = nullptr, c->d_scan = nullptr;
+  c->d_records = nullptr, c->d_grad = nullptr;
+  c->grad_elems = 0;
+  c->cap = 0;
+}
+
+int ensure_config(b200_ctx *ctx, int w, int h, int orientation, int planes) {
+  if (w < 32 || h < 32 || orientation < 1 || orientation > 4) return fail(ctx, B200_EINVAL, "bad frame size / orientation");
+  if (ctx->cfg_w == w && ctx->cfg_h == h && ctx->cfg_orient == orientation && ctx->cfg_planes == planes) return B200_OK;
+  b200_build_detect_params(w, h, orientation, kDetectThreads, &ctx->dp[0]);
+  b200_build_detect_params(w / 2, h / 2, orientation, kDetectThreads, &ctx->dp[1]);
+  b200_build_geom_params(w, h, orientation, planes, &ctx->gp);
+  int max_smem = 0;
+  cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
+  for (int p = 0; p < 2; p++) {
+    ctx->dp[p].use_global_grad = 0;
+    if (detect_smem_bytes(ctx->dp[p]) > (size_t)max_smem - 1024) {
+      ctx->dp[p].use_global_grad = 1;
+      if (detect_smem_bytes(ctx->dp[p]) > (size_t)max_smem - 1024)
+        return fail(ctx, B200_EUNSUPPORTED, "detection strips of a %dx%d frame do not fit in shared memory", w, h);
+    }
+  }
+  for (int s = 0; s < 4; s++)
+    if (ctx->dp[0].strip[s].w < 1 || ctx->dp[0].strip[s].h < 1) return fail(ctx, B200_EINVAL, "degenerate detection strip");
+  ctx->cfg_w = w, ctx->cfg_h = h, ctx->cfg_orient = orientation, ctx->cfg_planes = planes;
+  return B200_OK;
+}
+
+int ensure_capacity(b200_ctx *ctx, int n, int w, int h, bool need_frames) {
+  if (n <= ctx->cap && w * h <= ctx->cap_w * ctx->cap_h && (!need_frames || ctx->d_frames)) return B200_OK;
+  int cap = n > ctx->cap ? n : ctx->cap;
+  int cw = w, chh = h;
+  if ((size_t)ctx->cap_w * ctx->cap_h > (size_t)w * h) cw = ctx->cap_w, chh = ctx->cap_h;
+  bool had_frames = ctx->d_frames != nullptr;
+  free_scratch(ctx);
+  if (need_frames || had_frames) {
+    CU(cudaMalloc(&ctx->d_frames, (size_t)cap * cw * chh));
+    CU(cudaMalloc(&ctx->d_cb, (size_t)cap * (cw / 2) * (chh / 2)));
+    CU(cudaMalloc(&ctx->d_cr, (size_t)cap * (cw / 2) * (chh / 2)));
+  }
+  CU(cudaMalloc(&ctx->d_lines, sizeof(b200_line) * 3 * (size_t)cap * 4));
+  CU(cudaMalloc(&ctx->d_geom, sizeof(FrameGeom) * (size_t)cap));
+  CU(cudaMalloc(&ctx->d_cards, kCardBytes * (size_t)cap));
+  CU(cudaMalloc(&ctx->d_vprob, (size_t)cap * (540 * sizeof(float) + 16)));
+  CU(cudaMalloc(&ctx->d_scan, sizeof(b200_scan) * (size_t)cap));
+  CU(cudaMalloc(&ctx->d_records, sizeof(b200_frame_record) * (size_t)cap));
+  ctx->cap = cap, ctx->cap_w = cw, ctx->cap_h = chh;
+  return B200_OK;
+}
+
+int ensure_grad(b200_ctx *ctx, int n) {
+  size_t need = 0;
+  for (int p = 0; p < 2; p++) {
+    if (!ctx->dp[p].use_global_grad) continue;
+    size_t mx = 0;
+    for (int s = 0; s < 4; s++) {
+      size_t v = (size_t)ctx->dp[p].strip[s].w * ctx->dp[p].strip[s].h;
+      mx = v > mx ? v : mx;
+    }
+    size_t e = (size_t)n * 4 * mx * 2;
+    need = e > need ? e : need;
+  }
+  if (need > ctx->grad_elems) {
+    cudaFree(ctx->d_grad);
+    ctx->d_grad = nullptr;
+    ctx->grad_elems = 0;
+    CU(cudaMalloc(&ctx->d_grad, need * sizeof(int16_t)));
+    ctx->grad_elems = need;
+  }
+  return B200_OK;
+}
+
+int ensure_misc(b200_ctx *ctx, size_t bytes) {
+  if (bytes <= ctx->misc_bytes) return B200_OK;
+  cudaFree(ctx->d_misc);
+  ctx->d_misc = nullptr, ctx->misc_bytes = 0;
+  CU(cudaMalloc(&ctx->d_misc, bytes));
+  ctx->misc_bytes = bytes;
+  return B200_OK;
+}
+
+// Copy n strided host planes into a dense device buffer (or hand back the caller's device pointer).
+int stage_planes(b200_ctx *ctx, const uint8_t *src, int row_stride, size_t frame_stride, int w, int h, int n, int mem,
+                 uint8_t *d_dense, const uint8_t **out_ptr, int *out_row_stride, size_t *out_frame_stride) {
+  if (mem == B200_MEM_DEVICE) {
+    *out_ptr = src, *out_row_stride = row_stride, *out_frame_stride = frame_stride;
+    return B200_OK;
+  }
+  if (row_stride == w && frame_stride == (size_t)w * h) {
+    CU(cudaMemcpyAsync(d_dense, src, (size_t)n * w * h, cudaMemcpyHostToDevice, ctx->stream));
+  } else if (frame_stride == (size_t)row_stride * h) {
+    CU(cudaMemcpy2DAsync(d_dense, w, src, row_stride, w, (size_t)h * n, cudaMemcpyHostToDevice, ctx->stream));
+  } else {
+    for (int i = 0; i < n; i++)
+      CU(cudaMemcpy2DAsync(d_dense + (size_t)i * w * h, w, src + (size_t)i * frame_stride, row_stride, w, h,
+                           cudaMemcpyHostToDevice, ctx->stream));
+  }
+  *out_ptr = d_dense, *out_row_stride = w, *out_frame_stride = (size_t)w * h;
+  return B200_OK;
+}
+
+int detect_sequence(b200_ctx *ctx, const uint8_t *y, int yrs, size_t yfs, const uint8_t *cb, const uint8_t *cr, int crs,
+                    size_t cfs, int n) {
+  const size_t plane_stride = (size_t)ctx->cap * 4;
+  int rc = ensure_grad(ctx, n);
+  if (rc) return rc;
+  LAUNCH(launch_detect(ctx->dp[0], y, yrs, yfs, n, nullptr, nullptr, ctx->d_lines, ctx->d_grad, ctx->stream));
+  if (cb && cr) {
+    // Cb is searched only where Y produced no line, Cr only where neither Y nor Cb did (dmz.cpp:351)
+    LAUNCH(launch_detect(ctx->dp[1], cb, crs, cfs, n, ctx->d_lines, nullptr, ctx->d_lines + plane_stride, ctx->d_grad, ctx->stream));
+    LAUNCH(launch_detect(ctx->dp[1], cr, crs, cfs, n, ctx->d_lines, ctx->d_lines + plane_stride, ctx->d_lines + 2 * plane_stride,
+                         ctx->d_grad, ctx->stream));
+  }
+  LAUNCH(launch_geometry(ctx->gp, ctx->d_lines, plane_stride, n, ctx->d_geom, ctx->stream));
+  return B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200_ctx_create(b200_ctx **out, int device_ordinal, const char *weights_dir) {
+  if (!out) return B200_EINVAL;
+  *out = nullptr;
+  b200_ctx *ctx = new b200_ctx();
+  ctx->device = device_ordinal;
+  *out = ctx;  // returned even on failure so the caller can read b200_last_error, then destroy
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(ctx, B200_ECUDA, "no CUDA device available (%s); this library has no CPU fallback", cudaGetErrorString(e));
+  CU(cudaSetDevice(device_ordinal));
+  CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+
+  const std::string dir = weights_dir && *weights_dir ? weights_dir : default_weights_dir();
+  std::vector<float> blob;
+  if (!read_blob(dir + "/modelm_befe75da.bin", &blob, 10403)) return fail(ctx, B200_EINVAL, "cannot read %s/modelm_befe75da.bin", dir.c_str());
+  CU(cudaMalloc(&ctx->d_vseg, blob.size() * sizeof(float)));
+  CU(cudaMemcpy(ctx->d_vseg, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice));
+  static const char *names[3] = {"modelc_5c241121.bin", "modelc_01266c1b.bin", "modelc_b00bf70c.bin"};
+  std::vector<float> cnn[3], hwT(3 * 320 * 32);
+  const float *ptrs[3];
+  for (int m = 0; m < 3; m++) {
+    if (!read_blob(dir + "/" + names[m], &cnn[m], 10682)) return fail(ctx, B200_EINVAL, "cannot read %s/%s", dir.c_str(), names[m]);
+    CU(cudaMalloc(&ctx->d_cnn[m], cnn[m].size() * sizeof(float)));
+    CU(cudaMemcpy(ctx->d_cnn[m], cnn[m].data(), cnn[m].size() * sizeof(float), cudaMemcpyHostToDevice));
+    for (int u = 0; u < 32; u++)
+      for (int j = 0; j < 320; j++) hwT[((size_t)m * 320 + j) * 32 + u] = cnn[m][80 + (size_t)u * 320 + j];
+    ptrs[m] = cnn[m].data();
+  }
+  CU(cudaMalloc(&ctx->d_hwT, hwT.size() * sizeof(float)));
+  CU(cudaMemcpy(ctx->d_hwT, hwT.data(), hwT.size() * sizeof(float), cudaMemcpyHostToDevice));
+  if (upload_conv_constants(ptrs) != 0) return fail(ctx, B200_ECUDA, "cudaMemcpyToSymbol: %s", cudaGetErrorString(cudaGetLastError()));
+  ctx->wts.vseg = ctx->d_vseg;
+  for (int m = 0; m < 3; m++) ctx->wts.cnn[m] = ctx->d_cnn[m];
+  ctx->wts.cnn_hwT = ctx->d_hwT;
+  return B200_OK;
+}
+
+void b200_ctx_destroy(b200_ctx *ctx) {
+  if (!ctx) return;
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  free_scratch(ctx);
+  cudaFree(ctx->d_misc);
+  if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  cudaFree(ctx->d_vseg), cudaFree(ctx->d_hwT);
+  for (int m = 0; m < 3; m++) cudaFree(ctx->d_cnn[m]);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char *b200_last_error(const b200_ctx *ctx) { return ctx ? ctx->error.c_str() : "null context"; }
+uint64_t b200_launch_count(const b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+void *b200_ctx_stream(const b200_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+int b200_ctx_reserve(b200_ctx *ctx, int max_frames, int width, int height) {
+  if (!ctx || max_frames < 1) return B200_EINVAL;
+  CU(cudaSetDevice(ctx->device));
+  return ensure_capacity(ctx, max_frames, width, height, true);
+}
+
+int b200_detect_edges_batch(b200_ctx *ctx, const uint8_t *y, int yrs, size_t yfs, const uint8_t *cb, const uint8_t *cr,
+                            int crs, size_t cfs, int width, int height, int n, int orientation, int mem, b200_edges *edges,
+                            b200_corner_points *corners, uint8_t *all_found, b200_line *lines) {
+  if (!ctx || !y || n < 1 || (!cb) != (!cr)) return fail(ctx, B200_EINVAL, "b200_detect_edges_batch: bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  int rc = ensure_config(ctx, width, height, orientation, cb ? 3 : 1);
+  if (rc) return rc;
+  rc = ensure_capacity(ctx, n, width, height, mem == B200_MEM_HOST);
+  if (rc) return rc;
+  const uint8_t *dy, *dcb = nullptr, *dcr = nullptr;
+  int drs, dcrs = 0;
+  size_t dfs, dcfs = 0;
+  rc = stage_planes(ctx, y, yrs, yfs, width, height, n, mem, ctx->d_frames, &dy, &drs, &dfs);
+  if (rc) return rc;
+  if (cb) {
+    rc = stage_planes(ctx, cb, crs, cfs, width / 2, height / 2, n, mem, ctx->d_cb, &dcb, &dcrs, &dcfs);
+    if (rc) return rc;
+    rc = stage_planes(ctx, cr, crs, cfs, width / 2, height / 2, n, mem, ctx->d_cr, &dcr, &dcrs, &dcfs);
+    if (rc) return rc;
+  }
+  rc = detect_sequence(ctx, dy, drs, dfs, dcb, dcr, dcrs, dcfs, n);
+  if (rc) return rc;
+  // unpack FrameGeom into the caller's structs (host side; geometry records are small)
+  std::vector<FrameGeom> hg(n);
+  CU(cudaMemcpyAsync(hg.data(), ctx->d_geom, sizeof(FrameGeom) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  std::vector<b200_line> hl;
+  if (lines) {
+    hl.resize((size_t)n * 4);
+    CU(cudaMemcpyAsync(hl.data(), ctx->d_lines, sizeof(b200_line) * n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  std::vector<b200_edges> he(n);
+  std::vector<b200_corner_points> hc(n);
+  std::vector<uint8_t> hf(n);
+  for (int i = 0; i < n; i++) {
+    b200_found_edge *fe[4] = {&he[i].top, &he[i].left, &he[i].bottom, &he[i].right};
+    for (int s = 0; s < 4; s++) fe[s]->found = hg[i].found[s], fe[s]->rho = hg[i].rho[s], fe[s]->theta = hg[i].theta[s];
+    memcpy(&hc[i], hg[i].corners, sizeof(float) * 8);
+    hf[i] = (uint8_t)hg[i].all_found;
+  }
+  const cudaMemcpyKind kind = mem == B200_MEM_DEVICE ? cudaMemcpyHostToDevice : cudaMemcpyHostToHost;
+  if (edges) CU(cudaMemcpy(edges, he.data(), sizeof(b200_edges) * n, kind));
+  if (corners) CU(cudaMemcpy(corners, hc.data(), sizeof(b200_corner_points) * n, kind));
+  if (all_found) CU(cudaMemcpy(all_found, hf.data(), n, kind));
+  if (lines) CU(cudaMemcpy(lines, hl.data(), sizeof(b200_line) * n * 4, kind));
+  return B200_OK;
+}
+
+int b200_transform_card_batch(b200_ctx *ctx, const uint8_t *sample, int row_stride, size_t frame_stride, int width,
+                              int height, int n, const b200_corner_points *corners, const uint8_t *valid, int orientation,
+                              int upsample, int mem, uint8_t *cards) {
+  if (!ctx || !sample || !corners || !cards || n < 1) return fail(ctx, B200_EINVAL, "b200_transform_card_batch: bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  int rc = ensure_capacity(ctx, n, width, height, mem == B200_MEM_HOST);
+  if (rc) return rc;
+  const uint8_t *ds;
+  int drs;
+  size_t dfs;
+  rc = stage_planes(ctx, sample, row_stride, frame_stride, width, height, n, mem, ctx->d_frames, &ds, &drs, &dfs);
+  if (rc) return rc;
+  const b200_corner_points *dc = corners;
+  const uint8_t *dv = valid;
+  if (mem == B200_MEM_HOST) {
+    rc = ensure_misc(ctx, (sizeof(b200_corner_points) + 1) * (size_t)n);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(ctx->d_misc, corners, sizeof(b200_corner_points) * n, cudaMemcpyHostToDevice, ctx->stream));
+    dc = (const b200_corner_points *)ctx->d_misc;
+    if (valid) {
+      uint8_t *p = (uint8_t *)ctx->d_misc + sizeof(b200_corner_points) * (size_t)n;
+      CU(cudaMemcpyAsync(p, valid, n, cudaMemcpyHostToDevice, ctx->stream));
+      dv = p;
+    }
+  }
+  LAUNCH(launch_corners_to_geom(dc, dv, n, orientation, upsample, ctx->d_geom, ctx->stream));
+  uint8_t *dcards = mem == B200_MEM_DEVICE ? cards : ctx->d_cards;
+  LAUNCH(launch_warp(ds, drs, dfs, width, height, n, ctx->d_geom, dcards, ctx->stream));
+  if (mem == B200_MEM_HOST) CU(cudaMemcpyAsync(cards, ctx->d_cards, kCardBytes * n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}
+
+int b200_scan_cards_batch(b200_ctx *ctx, const uint8_t *cards, int n, const uint8_t *valid, int mem, b200_scan *scans) {
+  if (!ctx || !cards || !scans || n < 1) return fail(ctx, B200_EINVAL, "b200_scan_cards_batch: bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  int rc = ensure_capacity(ctx, n, ctx->cap_w ? ctx->cap_w : 32, ctx->cap_h ? ctx->cap_h : 32, false);
+  if (rc) return rc;
+  const uint8_t *dc = cards, *dv = valid;
+  if (mem == B200_MEM_HOST) {
+    CU(cudaMemcpyAsync(ctx->d_cards, cards, kCardBytes * n, cudaMemcpyHostToDevice, ctx->stream));
+    dc = ctx->d_cards;
+    if (valid) {
+      rc = ensure_misc(ctx, n);
+      if (rc) return rc;
+      CU(cudaMemcpyAsync(ctx->d_misc, valid, n, cudaMemcpyHostToDevice, ctx->stream));
+      dv = (const uint8_t *)ctx->d_misc;
+    }
+  }
+  b200_scan *ds = mem == B200_MEM_DEVICE ? scans : ctx->d_scan;
+  LAUNCH(launch_scan(ctx->wts, dc, n, nullptr, dv, ctx->d_vprob, ds, ctx->stream));
+  if (mem == B200_MEM_HOST) CU(cudaMemcpyAsync(scans, ctx->d_scan, sizeof(b200_scan) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}
+
+int b200_process_frames_batch(b200_ctx *ctx, const uint8_t *y, int yrs, size_t yfs, int width, int height, int n,
+                              int orientation, int mem, b200_frame_record *records, uint8_t *cards_out) {
+  if (!ctx || !y || !records || n < 1) return fail(ctx, B200_EINVAL, "b200_process_frames_batch: bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  int rc = ensure_config(ctx, width, height, orientation, 1);
+  if (rc) return rc;
+  rc = ensure_capacity(ctx, n, width, height, mem == B200_MEM_HOST);
+  if (rc) return rc;
+  const uint8_t *dy;
+  int drs;
+  size_t dfs;
+  rc = stage_planes(ctx, y, yrs, yfs, width, height, n, mem, ctx->d_frames, &dy, &drs, &dfs);
+  if (rc) return rc;
+  rc = detect_sequence(ctx, dy, drs, dfs, nullptr, nullptr, 0, 0, n);
+  if (rc) return rc;
+  uint8_t *dcards = (mem == B200_MEM_DEVICE && cards_out) ? cards_out : ctx->d_cards;
+  LAUNCH(launch_warp(dy, drs, dfs, width, height, n, ctx->d_geom, dcards, ctx->stream));
+  LAUNCH(launch_scan(ctx->wts, dcards, n, ctx->d_geom, nullptr, ctx->d_vprob, ctx->d_scan, ctx->stream));
+  b200_frame_record *drec = mem == B200_MEM_DEVICE ? records : ctx->d_records;
+  LAUNCH(launch_finalize_records(ctx->d_geom, ctx->d_scan, dcards, n, drec, ctx->stream));
+  if (mem == B200_MEM_HOST) {
+    CU(cudaMemcpyAsync(records, ctx->d_records, sizeof(b200_frame_record) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (cards_out) CU(cudaMemcpyAsync(cards_out, ctx->d_cards, kCardBytes * n, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}
+
+int b200_calc_persp_transform_batch(b200_ctx *ctx, const float *src_pts, const float *dst_pts, int n, float *M) {
+  if (!ctx || !src_pts || !dst_pts || !M || n < 1) return fail(ctx, B200_EINVAL, "b200_calc_persp_transform_batch: bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  int rc = ensure_misc(ctx, sizeof(float) * 25 * (size_t)n);
+  if (rc) return rc;
+  float *ds = (float *)ctx->d_misc, *dd = ds + (size_t)n * 8, *dm = dd + (size_t)n * 8;
+  CU(cudaMemcpyAsync(ds, src_pts, sizeof(float) * 8 * n, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(dd, dst_pts, sizeof(float) * 8 * n, cudaMemcpyHostToDevice, ctx->stream));
+  LAUNCH(launch_homography_only(ds, dd, n, dm, ctx->stream));
+  CU(cudaMemcpyAsync(M, dm, sizeof(float) * 9 * n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}
+
+int b200_categorize_patches_batch(b200_ctx *ctx, const uint8_t *patches, int n, int mem, float *out) {
+  if (!ctx || !patches || !out || n < 1) return fail(ctx, B200_EINVAL, "b200_categorize_patches_batch: bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  const uint8_t *dp = patches;
+  float *dout = out;
+  if (mem == B200_MEM_HOST) {
+    int rc = ensure_misc(ctx, (size_t)n * (513 + 160) + 64);
+    if (rc) return rc;
+    dout = (float *)ctx->d_misc;
+    uint8_t *p = (uint8_t *)ctx->d_misc + (size_t)n * 160;
+    CU(cudaMemcpyAsync(p, patches, (size_t)n * 513, cudaMemcpyHostToDevice, ctx->stream));
+    dp = p;
+  }
+  LAUNCH(launch_categorize_patches(ctx->wts, dp, n, dout, ctx->stream));
+  if (mem == B200_MEM_HOST) CU(cudaMemcpyAsync(out, dout, (size_t)n * 160, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}
+
+int b200_vseg_model_batch(b200_ctx *ctx, const float *rows, int n, int mem, float *out) {
+  if (!ctx || !rows || !out || n < 1) return fail(ctx, B200_EINVAL, "b200_vseg_model_batch: bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  const float *dr = rows;
+  float *dout = out;
+  if (mem == B200_MEM_HOST) {
+    int rc = ensure_misc(ctx, (size_t)n * (204 + 3) * sizeof(float));
+    if (rc) return rc;
+    float *p = (float *)ctx->d_misc;
+    CU(cudaMemcpyAsync(p, rows, (size_t)n * 204 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    dr = p;
+    dout = p + (size_t)n * 204;
+  }
+  LAUNCH(launch_vseg_model(ctx->wts, dr, n, dout, ctx->stream));
+  if (mem == B200_MEM_HOST) CU(cudaMemcpyAsync(out, dout, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}
+
+}  // extern "C"

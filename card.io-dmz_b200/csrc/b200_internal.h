@@ -1,0 +1,100 @@
+// card.io-dmz_b200/csrc/b200_internal.h -- shared declarations of the B200-native hot path.
+//
+// Layout of the per-batch device state (all in HBM, owned by b200_ctx, sized for `cap` frames):
+//   d_frames   cap x (H x W) u8        staging copy of the caller's Y planes (B200_MEM_HOST only)
+//   d_lines    3 planes x cap x 4      b200_line   strip taps (Y, Cb, Cr)
+//   d_geom     cap                      FrameGeom   edges, corners, float M, double inverse M
+//   d_cards    cap x (270 x 428) u8    warped cards
+//   d_vprob    cap x 270 x 2 f32       per-row (visa-like, amex-like) probabilities, 0 = not computed
+//   d_scan     cap                      b200_scan
+//   d_records  cap                      b200_frame_record
+#ifndef B200_INTERNAL_H
+#define B200_INTERNAL_H
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "b200_dmz.h"
+
+#define B200_NUMANGLE 10  // cvRound((theta_max - theta_min) / theta) for the +-5 degree window, hough.cpp:98
+
+// One detection strip of one plane (dmz.cpp:279-341 geometry + hough.cpp:98-150 constants).  All float /
+// trig derived values are computed on the HOST with the C library (b200_tables.cpp) so that libm
+// differences between host and device can never leak into the integer results.
+struct StripDesc {
+  int x, y, w, h;
+  int vertical;    // expected line orientation (LineOrientationVertical == 0 in the reference; here 1 = vertical)
+  int numrho;      // 2 (w + h) + 1
+  int half;        // (numrho - 1) / 2
+  int threshold;   // max(w, h) / 6, dmz.cpp:246
+  int ncells;      // compacted accumulator size
+  int chunk_rows;  // Sobel work split: rows per work item
+  int nchunks;
+  int tab_sin[B200_NUMANGLE];
+  int tab_cos[B200_NUMANGLE];
+  int rlo[B200_NUMANGLE];        // smallest accumulator rho index reachable for angle n
+  int rcount[B200_NUMANGLE];     // number of reachable rho indices
+  int cell_base[B200_NUMANGLE];  // start of angle n's cells in the compacted accumulator
+  float slope_a, slope_b;        // tanf bounds of the gradient gate, hough.cpp:117-124
+  float theta[B200_NUMANGLE];    // n * theta + theta_min
+};
+
+struct DetectParams {
+  StripDesc strip[4];  // detection order: top, bottom, left, right
+  int use_global_grad; // dx/dy live in a global scratch slab instead of shared memory (very large strips)
+};
+
+// Geometry constants for one (resolution, orientation): everything lineByShiftingOrigin / parametricIntersect
+// need that involves libm (geometry.cpp:14-43).
+struct GeomParams {
+  double delta_rho[3][4][B200_NUMANGLE];  // [plane][strip in detection order][n]
+  float cos_t[2][B200_NUMANGLE];          // [0 = horizontal line, 1 = vertical line][n]
+  float sin_t[2][B200_NUMANGLE];
+  float theta[2][B200_NUMANGLE];
+  int orientation;
+  int n_planes;
+};
+
+struct FrameGeom {
+  int32_t found[4];  // top, left, bottom, right
+  float rho[4];
+  float theta[4];
+  int32_t n_idx[4];  // Hough angle index of the accepted line per edge
+  float corners[8];  // tl, bl, tr, br
+  int32_t all_found;
+  float M[9];        // llcv_calc_persp_transform output (src -> dst)
+  int32_t pad;
+  double Minv[9];    // cv::invert of M promoted to double (dst -> src), used by the warp
+};
+
+struct NetWeights {  // device pointers
+  const float *vseg;     // modelm_befe75da blob: hidden W 50x204, hidden b 50, logistic W 3x50, logistic b 3
+  const float *cnn[3];   // modelc blobs: conv W 8x9, conv b 8, hidden W 32x320, hidden b 32, logistic W 10x32, b 10
+  const float *cnn_hwT;  // 3 x [320][32] transposed hidden weights (built on the host)
+};
+
+// launchers (each returns the number of kernels it launched, or -1 after setting a CUDA error)
+int launch_detect(const DetectParams &p, const uint8_t *plane, int row_stride, size_t frame_stride, int n,
+                  const b200_line *prev_lines, const b200_line *prev_lines2, b200_line *lines, int16_t *grad_scratch,
+                  cudaStream_t s);
+int launch_geometry(const GeomParams &g, const b200_line *lines, size_t plane_stride, int n, FrameGeom *geom, cudaStream_t s);
+int launch_homography_only(const float *src_pts, const float *dst_pts, int n, float *M, cudaStream_t s);
+int launch_corners_to_geom(const b200_corner_points *corners, const uint8_t *valid, int n, int orientation, int upsample,
+                           FrameGeom *geom, cudaStream_t s);
+int launch_warp(const uint8_t *src, int row_stride, size_t frame_stride, int w, int h, int n, const FrameGeom *geom,
+                uint8_t *cards, cudaStream_t s);
+int launch_scan(const NetWeights &wts, const uint8_t *cards, int n, const FrameGeom *geom_or_null, const uint8_t *valid,
+                float *vprob, b200_scan *scans, cudaStream_t s);
+int launch_finalize_records(const FrameGeom *geom, const b200_scan *scans, const uint8_t *cards, int n,
+                            b200_frame_record *recs, cudaStream_t s);
+int launch_categorize_patches(const NetWeights &wts, const uint8_t *patches, int n, float *out, cudaStream_t s);
+int launch_vseg_model(const NetWeights &wts, const float *rows, int n, float *out, cudaStream_t s);
+int upload_conv_constants(const float *cnn_blobs[3]);  // __constant__ conv kernels / biases (nets.cu)
+
+size_t detect_smem_bytes(const DetectParams &p);
+
+// host tables (b200_tables.cpp, compiled WITHOUT fp contraction)
+void b200_build_detect_params(int width, int height, int orientation, int block_threads, DetectParams *out);
+void b200_build_geom_params(int width, int height, int orientation, int n_planes, GeomParams *out);
+
+#endif

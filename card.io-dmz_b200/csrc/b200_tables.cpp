@@ -1,0 +1,162 @@
+// card.io-dmz_b200/csrc/b200_tables.cpp -- host-side constant tables of the detect stage.
+//
+// Everything in the reference's edge detection that touches libm (sinf/cosf/tanf/atanf/cos/sqrt) or
+// float rounding of constants takes only a handful of distinct values per (resolution, orientation):
+// 10 Hough angles per line orientation and 4 strip origins per plane.  They are evaluated here ONCE on
+// the host, with the same C library and float/double expressions as the reference, and handed to the
+// kernels as constants; the device code then needs integer arithmetic and IEEE +,-,*,/ only.
+// Compiled with -ffp-contract=off (no FMA), x86-64 baseline.
+//
+//   detection_boxes_for_sample   dmz.cpp:279-341
+//   best_line_for_sample         dmz.cpp:224-271   (theta window, threshold)
+//   llcv_hough tables            cv/hough.cpp:98-124
+//   lineByShiftingOrigin         geometry.cpp:34-43
+//   parametricIntersect          geometry.cpp:14-32 (cosf / sinf of the 10 + 10 possible thetas)
+#include <float.h>
+#include <math.h>
+#include <string.h>
+
+#include "b200_internal.h"
+
+#define CV_PI 3.1415926535897932384626433832795
+
+namespace {
+
+struct Rect {
+  int x, y, w, h;
+};
+
+Rect inset(Rect r, int hi, int vi) { return Rect{r.x + hi, r.y + vi, r.w - 2 * hi, r.h - 2 * vi}; }
+
+// dmz_constants.h:16-27 (integer division inside the macros is intentional)
+const float kPortraitVerticalPercentInset = (float)((640 - 270) / 2) / (float)640;
+const float kPortraitHorizontalPercentInset = (float)((480 - 428) / 2) / (float)480;
+const float kLandscapeVerticalPercentInset = (float)((480 - 270) / 2) / (float)480;
+const float kLandscapeHorizontalPercentInset = (float)((640 - 428) / 2) / (float)640;
+
+void detection_boxes(int img_w, int img_h, int orientation, Rect boxes[4]) {
+  int inset_v = 0, slop_v = 0, inset_h = 0, slop_h = 0;
+  int width = (img_h * 4) / 3;  // central 4:3 region
+  int left_margin = (img_w - width) / 2;
+  switch (orientation) {
+    case B200_ORIENT_PORTRAIT:
+    case B200_ORIENT_PORTRAIT_UPSIDE_DOWN:
+      inset_v = (int)roundf(kPortraitHorizontalPercentInset * img_h);
+      slop_v = (int)roundf(0.03f * img_h);
+      inset_h = (int)roundf(kPortraitVerticalPercentInset * width);
+      slop_h = (int)roundf(0.03f * width);
+      break;
+    case B200_ORIENT_LANDSCAPE_RIGHT:
+    case B200_ORIENT_LANDSCAPE_LEFT:
+      inset_v = (int)roundf(kLandscapeVerticalPercentInset * img_h);
+      slop_v = (int)roundf(0.03f * img_h);
+      inset_h = (int)roundf(kLandscapeHorizontalPercentInset * width);
+      slop_h = (int)roundf(0.03f * width);
+      break;
+    default: break;
+  }
+  Rect image_rect{left_margin, 0, width - 1, img_h - 1};
+  Rect outer = inset(image_rect, inset_h - slop_h, inset_v - slop_v);
+  Rect inner = inset(image_rect, inset_h + slop_h, inset_v + slop_v);
+  boxes[0] = Rect{inner.x, outer.y, inner.w, 2 * slop_v};            // top
+  boxes[1] = Rect{inner.x, inner.y + inner.h, inner.w, 2 * slop_v};  // bottom
+  boxes[2] = Rect{outer.x, inner.y, 2 * slop_h, inner.h};            // left
+  boxes[3] = Rect{inner.x + inner.w, inner.y, 2 * slop_h, inner.h};  // right
+}
+
+int cv_round(double v) { return (int)lrint(v); }
+
+const float kHorizontalAngle = (float)(CV_PI / 2.0f);
+const float kVerticalAngle = (float)CV_PI;
+const float kMaxAngleDeviationAllowed = (float)(5.0f * (CV_PI / 180.0f));
+
+void hough_tables(int vertical, int tab_sin[], int tab_cos[], float theta_out[], float *slope_a, float *slope_b) {
+  float base_angle = vertical ? kVerticalAngle : kHorizontalAngle;
+  float theta_min = base_angle - kMaxAngleDeviationAllowed;
+  float theta_max = base_angle + kMaxAngleDeviationAllowed;
+  float theta = (float)CV_PI / 180.0f, irho = 1 / 1.0f, ang;
+  float gat = 10;  // kHoughGradientAngleThreshold
+  int numangle = cv_round((theta_max - theta_min) / theta), n;
+  if (numangle != B200_NUMANGLE) numangle = B200_NUMANGLE;  // 9.999998f rounds to 10 on every IEEE platform
+  for (ang = theta_min, n = 0; n < numangle; ang += theta, n++) {
+    tab_sin[n] = (int)floorf(1024 * sinf(ang) * irho);
+    tab_cos[n] = (int)floorf(1024 * cosf(ang) * irho);
+    theta_out[n] = n * theta + theta_min;  // line.angle = n * theta + theta_min, hough.cpp:190
+  }
+  if (vertical) {
+    *slope_a = tanf((float)(CV_PI * (180 - gat) / 180.0f));
+    *slope_b = tanf((float)(CV_PI * (180 + gat) / 180.0f));
+  } else {
+    *slope_a = tanf((float)(CV_PI * (90 - gat) / 180.0f));
+    *slope_b = tanf((float)(CV_PI * (90 + gat) / 180.0f));
+  }
+}
+
+double delta_rho_for(float theta, int x_off, int y_off) {  // geometry.cpp:34-43, everything but the final add
+  double offset_angle = x_off == 0 ? CV_PI / 2.0f : (double)atanf((float)y_off / (float)x_off);
+  double delta_angle = theta - offset_angle + CV_PI / 2.0f;
+  double offset_magnitude = sqrt((double)(x_off * x_off + y_off * y_off));
+  return offset_magnitude * cos(CV_PI / 2 - delta_angle);
+}
+
+}  // namespace
+
+void b200_build_detect_params(int width, int height, int orientation, int block_threads, DetectParams *out) {
+  Rect boxes[4];
+  memset(out, 0, sizeof(*out));
+  detection_boxes(width, height, orientation, boxes);
+  for (int s = 0; s < 4; s++) {
+    StripDesc &d = out->strip[s];
+    d.x = boxes[s].x, d.y = boxes[s].y, d.w = boxes[s].w, d.h = boxes[s].h;
+    d.vertical = s >= 2;
+    d.numrho = cv_round(((d.w + d.h) * 2 + 1) / 1.0f);
+    d.half = (d.numrho - 1) / 2;
+    d.threshold = (d.w > d.h ? d.w : d.h) / 6;
+    hough_tables(d.vertical, d.tab_sin, d.tab_cos, d.theta, &d.slope_a, &d.slope_b);
+    // compact accumulator: r = ((j cos + i sin) >> 10) + half is monotone in j and in i, so its extremes
+    // over the strip are attained at the four corner pixels
+    int base = 0;
+    for (int n = 0; n < B200_NUMANGLE; n++) {
+      int lo = 1 << 30, hi = -(1 << 30);
+      for (int c = 0; c < 4; c++) {
+        int j = (c & 1) ? d.w - 1 : 0, i = (c & 2) ? d.h - 1 : 0;
+        int r = ((j * d.tab_cos[n] + i * d.tab_sin[n]) >> 10) + d.half;
+        lo = r < lo ? r : lo;
+        hi = r > hi ? r : hi;
+      }
+      d.rlo[n] = lo;
+      d.rcount[n] = hi - lo + 1;
+      d.cell_base[n] = base;
+      base += d.rcount[n];
+    }
+    d.ncells = base;
+    d.nchunks = d.w > 0 ? block_threads / d.w : 1;
+    if (d.nchunks < 1) d.nchunks = 1;
+    if (d.nchunks > d.h) d.nchunks = d.h > 0 ? d.h : 1;
+    d.chunk_rows = (d.h + d.nchunks - 1) / d.nchunks;
+    d.nchunks = d.chunk_rows > 0 ? (d.h + d.chunk_rows - 1) / d.chunk_rows : 1;
+  }
+}
+
+void b200_build_geom_params(int width, int height, int orientation, int n_planes, GeomParams *out) {
+  memset(out, 0, sizeof(*out));
+  out->orientation = orientation;
+  out->n_planes = n_planes;
+  for (int v = 0; v < 2; v++) {
+    int ts[B200_NUMANGLE], tc[B200_NUMANGLE];
+    float sa, sb;
+    hough_tables(v, ts, tc, out->theta[v], &sa, &sb);
+    for (int n = 0; n < B200_NUMANGLE; n++) {
+      out->cos_t[v][n] = cosf(out->theta[v][n]);
+      out->sin_t[v][n] = sinf(out->theta[v][n]);
+    }
+  }
+  for (int p = 0; p < 3; p++) {
+    Rect boxes[4];
+    int pw = p == 0 ? width : width / 2, ph = p == 0 ? height : height / 2;
+    detection_boxes(pw, ph, orientation, boxes);
+    for (int s = 0; s < 4; s++)
+      for (int n = 0; n < B200_NUMANGLE; n++)
+        out->delta_rho[p][s][n] = delta_rho_for(out->theta[s >= 2][n], boxes[s].x, boxes[s].y);
+  }
+}

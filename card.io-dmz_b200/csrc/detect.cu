@@ -1,0 +1,358 @@
+// card.io-dmz_b200/csrc/detect.cu -- best_line_for_sample for every (frame, strip): one CTA per strip.
+//
+// Replaces, for one detection strip (dmz.cpp:224-271):
+//   llcv_sobel7 x2                         cv/sobel.cpp:476-530   (7x7 separable, replicate border, s16 saturation)
+//   llcv_adaptive_canny7_precomputed_sobel cv/canny.cpp:555-580   (thresholds) + canny.cpp:58-336 (NMS, hysteresis)
+//   llcv_hough                             cv/hough.cpp:52-196    (gradient-gated votes, first-max argmax)
+//
+// Data flow inside the CTA (everything after the first load stays in shared memory):
+//   global u8 strip --(32-bit coalesced loads)--> s_src[h][w]
+//   Sobel: one work item per (column, row chunk) walks down its rows keeping the last seven row-filter
+//          results for both kernels in registers (no intermediate image) --> s_dx, s_dy (s16)
+//   thresholds: block reduction (warp shuffles) of the saturated |dx| + |dy| sums, 64-bit exact
+//   NMS: per pixel from s_dx / s_dy --> s_map {0 candidate, 1 no edge, 2 edge}
+//   hysteresis: in-place propagation sweeps to the unique fixed point (= the reference's stack walk)
+//   Hough: shared-memory atomics into a compacted accumulator (only the reachable rho range per angle)
+//   argmax: packed (votes, -(r, n)) 64-bit keys reduced with warp shuffles -> reference scan order r outer,
+//           n inner, strict '>'
+// All integer; the two float comparisons of the gradient gate are IEEE divisions (-fmad=false file).
+#include <float.h>
+
+#include "b200_internal.h"
+
+namespace {
+
+constexpr int kThreads = 416;  // 13 warps: one Sobel work item per thread for the 389-wide strips
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long t = __shfl_xor_sync(0xffffffffu, v, o);
+    v = t > v ? t : v;
+  }
+  return v;
+}
+
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+struct SmemLayout {
+  uint8_t *src;
+  int16_t *dx, *dy;
+  uint8_t *map;
+  unsigned int *acc;
+};
+
+__device__ __forceinline__ size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
+
+__global__ void __launch_bounds__(kThreads, 1)
+detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__restrict__ plane, int row_stride,
+                     size_t frame_stride, const b200_line *__restrict__ prev_lines, const b200_line *__restrict__ prev_lines2,
+                     b200_line *__restrict__ lines,
+                     int16_t *__restrict__ grad_scratch, size_t grad_scratch_stride) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __shared__ unsigned long long s_red[kThreads / 32];
+  __shared__ int s_low, s_high, s_flag;
+
+  const int strip = blockIdx.x;
+  const int frame = blockIdx.y;
+  const int tid = threadIdx.x;
+  const StripDesc &S = P.strip[strip];
+  const int w = S.w, h = S.h, npx = w * h;
+  const size_t out_idx = (size_t)frame * 4 + strip;
+
+  // Fallback planes: skip strips whose edge was already found on an earlier plane (dmz.cpp:351).
+  if ((prev_lines != nullptr && prev_lines[out_idx].found) || (prev_lines2 != nullptr && prev_lines2[out_idx].found)) {
+    if (tid == 0) {
+      b200_line l;
+      l.found = 0, l.r = 0, l.n = 0, l.max_votes = 0, l.low = 0, l.high = 0, l.n_edge_px = 0;
+      l.rho = FLT_MAX, l.theta = FLT_MAX;
+      lines[out_idx] = l;
+    }
+    return;
+  }
+
+  // ---- carve shared memory
+  SmemLayout L;
+  size_t off = 0;
+  L.src = smem_raw + off;
+  off = align16(off + (size_t)npx);
+  if (P.use_global_grad) {
+    L.dx = grad_scratch + ((size_t)frame * 4 + strip) * grad_scratch_stride;
+    L.dy = L.dx + grad_scratch_stride / 2;
+  } else {
+    L.dx = reinterpret_cast<int16_t *>(smem_raw + off);
+    off = align16(off + (size_t)npx * 2);
+    L.dy = reinterpret_cast<int16_t *>(smem_raw + off);
+    off = align16(off + (size_t)npx * 2);
+  }
+  L.map = smem_raw + off;
+  off = align16(off + (size_t)npx);
+  L.acc = reinterpret_cast<unsigned int *>(smem_raw + off);
+
+  // ---- 1. load the strip: 32-bit coalesced loads of the covering aligned words
+  {
+    const uint8_t *base = plane + (size_t)frame * frame_stride + (size_t)S.y * row_stride + S.x;
+    const bool word_ok = ((reinterpret_cast<uintptr_t>(plane) | (uintptr_t)row_stride | (uintptr_t)frame_stride) & 3u) == 0;
+    if (word_ok) {
+      const int shift = S.x & 3;                      // bytes of the first word that precede the strip
+      const int words = (shift + w + 3) >> 2;         // words per row
+      for (int i = tid; i < words * h; i += kThreads) {
+        const int row = i / words, k = i - row * words;
+        const unsigned int v = __ldg(reinterpret_cast<const unsigned int *>(base + (size_t)row * row_stride - shift) + k);
+        const int c0 = k * 4 - shift;
+        uint8_t *dst = L.src + row * w;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+          const int c = c0 + b;
+          if (c >= 0 && c < w) dst[c] = (uint8_t)(v >> (8 * b));
+        }
+      }
+    } else {
+      for (int i = tid; i < npx; i += kThreads) {
+        const int row = i / w, c = i - row * w;
+        L.src[i] = __ldg(base + (size_t)row * row_stride + c);
+      }
+    }
+  }
+  for (int i = tid; i < S.ncells; i += kThreads) L.acc[i] = 0u;
+  __syncthreads();
+
+  // ---- 2. Sobel-7 dx, dy with a register sliding window; accumulate the saturated |.| sums on the fly
+  unsigned long long abs_sum = 0;
+  {
+    const int items = w * S.nchunks;
+    for (int it = tid; it < items; it += kThreads) {
+      const int chunk = it / w, x = it - chunk * w;
+      const int y0 = chunk * S.chunk_rows;
+      const int y1 = min(h, y0 + S.chunk_rows);
+      // column offsets with BORDER_REPLICATE at the ROI edge
+      int xo[7];
+#pragma unroll
+      for (int k = 0; k < 7; k++) xo[k] = clampi(x + k - 3, 0, w - 1);
+      int hx[7], sx[7];  // row-filter results of the last seven rows: derivative taps, smoothing taps
+      // prime with rows y0-3 .. y0+2 (clamped)
+#pragma unroll
+      for (int k = 0; k < 6; k++) {
+        const uint8_t *r = L.src + clampi(y0 + k - 3, 0, h - 1) * w;
+        const int p0 = r[xo[0]], p1 = r[xo[1]], p2 = r[xo[2]], p3 = r[xo[3]], p4 = r[xo[4]], p5 = r[xo[5]], p6 = r[xo[6]];
+        hx[k + 1] = (p6 - p0) + 4 * (p5 - p1) + 5 * (p4 - p2);                       // [-1,-4,-5,0,5,4,1]
+        sx[k + 1] = (p0 + p6) + 6 * (p1 + p5) + 15 * (p2 + p4) + 20 * p3;            // [1,6,15,20,15,6,1]
+      }
+      for (int y = y0; y < y1; y++) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) hx[k] = hx[k + 1], sx[k] = sx[k + 1];
+        {
+          const uint8_t *r = L.src + clampi(y + 3, 0, h - 1) * w;
+          const int p0 = r[xo[0]], p1 = r[xo[1]], p2 = r[xo[2]], p3 = r[xo[3]], p4 = r[xo[4]], p5 = r[xo[5]], p6 = r[xo[6]];
+          hx[6] = (p6 - p0) + 4 * (p5 - p1) + 5 * (p4 - p2);
+          sx[6] = (p0 + p6) + 6 * (p1 + p5) + 15 * (p2 + p4) + 20 * p3;
+        }
+        int gx = (hx[0] + hx[6]) + 6 * (hx[1] + hx[5]) + 15 * (hx[2] + hx[4]) + 20 * hx[3];  // smooth down the column
+        int gy = (sx[6] - sx[0]) + 4 * (sx[5] - sx[1]) + 5 * (sx[4] - sx[2]);               // derivative down the column
+        gx = clampi(gx, -32768, 32767);  // saturate_cast<short>
+        gy = clampi(gy, -32768, 32767);
+        L.dx[y * w + x] = (int16_t)gx;
+        L.dy[y * w + x] = (int16_t)gy;
+        abs_sum += (unsigned)min(abs(gx), 32767) + (unsigned)min(abs(gy), 32767);  // cvAbs saturates, canny.cpp:355-361
+      }
+    }
+  }
+  // ---- 3. adaptive thresholds: low = floor(mean), high = floor(3 * mean), canny.cpp:568-580
+  abs_sum = warp_sum_u64(abs_sum);
+  if ((tid & 31) == 0) s_red[tid >> 5] = abs_sum;
+  __syncthreads();
+  if (tid == 0) {
+    unsigned long long tot = 0;
+    for (int i = 0; i < kThreads / 32; i++) tot += s_red[i];
+    const double mean = (double)tot / (double)npx;
+    s_low = (int)floor(mean);
+    s_high = (int)floor(3.0 * mean);  // 3.0f * low_threshold evaluated in double
+  }
+  __syncthreads();
+  const int low = s_low, high = s_high;
+
+  // ---- 4. non-maxima suppression, canny.cpp:220-285 (zero magnitude outside the ROI)
+  for (int i = tid; i < npx; i += kThreads) {
+    const int y = i / w, x = i - y * w;
+    const int gx = L.dx[i], gy = L.dy[i];
+    const int m = abs(gx) + abs(gy);
+    uint8_t out = 1;
+    if (m > low) {
+      auto mag = [&](int yy, int xx) -> int {
+        if (xx < 0 || xx >= w || yy < 0 || yy >= h) return 0;
+        const int j = yy * w + xx;
+        return abs((int)L.dx[j]) + abs((int)L.dy[j]);
+      };
+      const long long ax = abs(gx), ay = abs(gy);
+      const long long tg22x = ax * 13573;  // TG22 = (int)(0.41421356 * 2^15 + 0.5)
+      const long long tg67x = tg22x + ((ax + ax) << 15);
+      const long long ys = ay << 15;
+      bool is_max;
+      if (ys < tg22x) {
+        is_max = m > mag(y, x - 1) && m >= mag(y, x + 1);
+      } else if (ys > tg67x) {
+        is_max = m > mag(y - 1, x) && m >= mag(y + 1, x);
+      } else {
+        const int s = ((gx ^ gy) < 0) ? -1 : 1;
+        is_max = m > mag(y - 1, x - s) && m > mag(y + 1, x + s);
+      }
+      if (is_max) out = (m > high) ? 2 : 0;
+    }
+    L.map[i] = out;
+  }
+  __syncthreads();
+
+  // ---- 5. hysteresis: candidates 8-connected to an edge pixel become edge pixels; sweep to the fixed point.
+  // Each thread owns a run of consecutive pixels along the strip's long axis and sweeps it forwards and
+  // backwards, so a chain crossing a run is absorbed in one iteration.
+  {
+    const int run = (npx + kThreads - 1) / kThreads;
+    const int k0 = tid * run, k1 = min(npx, k0 + run);
+    const bool colmajor = h > w;
+    auto touch = [&](int k) -> bool {
+      int x, y;
+      if (colmajor) {
+        x = k / h;
+        y = k - x * h;
+      } else {
+        y = k / w;
+        x = k - y * w;
+      }
+      const int i = y * w + x;
+      if (L.map[i] != 0) return false;
+      bool hit = false;
+#pragma unroll
+      for (int dyy = -1; dyy <= 1; dyy++) {
+        const int yy = y + dyy;
+        if (yy < 0 || yy >= h) continue;
+#pragma unroll
+        for (int dxx = -1; dxx <= 1; dxx++) {
+          const int xx = x + dxx;
+          if (xx < 0 || xx >= w) continue;
+          hit |= (L.map[yy * w + xx] == 2);
+        }
+      }
+      if (hit) L.map[i] = 2;
+      return hit;
+    };
+    while (true) {
+      int changed = 0;
+      for (int k = k0; k < k1; k++) changed |= touch(k);
+      for (int k = k1 - 1; k >= k0; k--) changed |= touch(k);
+      if (!__syncthreads_or(changed)) break;
+    }
+  }
+
+  // ---- 6. gradient-gated Hough votes, hough.cpp:126-160
+  int n_edge = 0;
+  for (int i = tid; i < npx; i += kThreads) {
+    if (L.map[i] != 2) continue;
+    n_edge++;
+    const int y = i / w, x = i - y * w;
+    const int del_x = L.dx[i], del_y = L.dy[i];
+    bool use;
+    if (del_x != 0) {
+      const float slope = (float)del_y / (float)del_x;
+      use = S.vertical ? (slope >= S.slope_a && slope <= S.slope_b) : (slope >= S.slope_a || slope <= S.slope_b);
+    } else {
+      use = !S.vertical;
+    }
+    if (use) {
+#pragma unroll
+      for (int n = 0; n < B200_NUMANGLE; n++) {
+        const int r = ((x * S.tab_cos[n] + y * S.tab_sin[n]) >> 10) + S.half;
+        atomicAdd(&L.acc[S.cell_base[n] + (r - S.rlo[n])], 1u);
+      }
+    }
+  }
+  {
+    unsigned long long ne = warp_sum_u64((unsigned long long)n_edge);
+    __syncthreads();  // votes complete; s_red free again
+    if ((tid & 31) == 0) s_red[tid >> 5] = ne;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    unsigned long long tot = 0;
+    for (int i = 0; i < kThreads / 32; i++) tot += s_red[i];
+    s_flag = (int)tot;
+  }
+
+  // ---- 7. argmax in the reference's scan order (r outer, n inner, first strict maximum), hough.cpp:165-176
+  unsigned long long best = 0;
+  for (int n = 0; n < B200_NUMANGLE; n++) {
+    for (int c = tid; c < S.rcount[n]; c += kThreads) {
+      const unsigned int v = L.acc[S.cell_base[n] + c];
+      if (v == 0) continue;
+      const unsigned int r = (unsigned)(S.rlo[n] + c);
+      const unsigned long long key = ((unsigned long long)v << 32) | (0xFFFFFFFFu - (r * 16u + (unsigned)n));
+      best = key > best ? key : best;
+    }
+  }
+  best = warp_max_u64(best);
+  __syncthreads();  // s_flag written, s_red reads done
+  if ((tid & 31) == 0) s_red[tid >> 5] = best;
+  __syncthreads();
+  if (tid == 0) {
+    unsigned long long b = 0;
+    for (int i = 0; i < kThreads / 32; i++) b = s_red[i] > b ? s_red[i] : b;
+    b200_line l;
+    l.max_votes = (int)(b >> 32);
+    l.low = low, l.high = high, l.n_edge_px = s_flag;
+    l.found = 0, l.r = 0, l.n = 0, l.rho = FLT_MAX, l.theta = FLT_MAX;
+    if (l.max_votes > S.threshold) {
+      const unsigned int rn = 0xFFFFFFFFu - (unsigned int)(b & 0xFFFFFFFFu);
+      l.found = 1;
+      l.r = (int)(rn >> 4);
+      l.n = (int)(rn & 15u);
+      l.rho = ((float)l.r - (float)(S.numrho - 1) * 0.5f) * 1.0f;  // hough.cpp:189
+      l.theta = S.theta[l.n];
+    }
+    lines[out_idx] = l;
+  }
+}
+
+}  // namespace
+
+size_t detect_smem_bytes(const DetectParams &p) {
+  size_t worst = 0;
+  for (int s = 0; s < 4; s++) {
+    const StripDesc &d = p.strip[s];
+    size_t npx = (size_t)d.w * d.h;
+    size_t b = ((npx + 15) & ~(size_t)15) * 2;  // src + map
+    if (!p.use_global_grad) b += (((npx * 2) + 15) & ~(size_t)15) * 2;
+    b += (size_t)d.ncells * 4 + 64;
+    worst = b > worst ? b : worst;
+  }
+  return worst;
+}
+
+int launch_detect(const DetectParams &p, const uint8_t *plane, int row_stride, size_t frame_stride, int n,
+                  const b200_line *prev_lines, const b200_line *prev_lines2, b200_line *lines, int16_t *grad_scratch, cudaStream_t s) {
+  size_t smem = detect_smem_bytes(p);
+  static size_t configured = 0;
+  if (smem > configured) {
+    if (cudaFuncSetAttribute(detect_strips_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    configured = smem;
+  }
+  size_t max_npx = 0;
+  for (int i = 0; i < 4; i++) {
+    size_t v = (size_t)p.strip[i].w * p.strip[i].h;
+    max_npx = v > max_npx ? v : max_npx;
+  }
+  // y is limited to 65535 blocks: split very large batches
+  int launches = 0;
+  for (int f0 = 0; f0 < n; f0 += 65535) {
+    int cnt = n - f0 < 65535 ? n - f0 : 65535;
+    detect_strips_kernel<<<dim3(4, cnt), kThreads, smem, s>>>(
+        p, plane + (size_t)f0 * frame_stride, row_stride, frame_stride, prev_lines ? prev_lines + (size_t)f0 * 4 : nullptr, prev_lines2 ? prev_lines2 + (size_t)f0 * 4 : nullptr,
+        lines + (size_t)f0 * 4, grad_scratch ? grad_scratch + (size_t)f0 * 4 * max_npx * 2 : nullptr, max_npx * 2);
+    launches++;
+  }
+  return cudaGetLastError() == cudaSuccess ? launches : -1;
+}

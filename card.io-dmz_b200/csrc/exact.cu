@@ -1,0 +1,711 @@
+// card.io-dmz_b200/csrc/exact.cu -- the bit-exact float / fixed-point stages.  Compiled with -fmad=false:
+// every float and double operation below is a single IEEE-754 round-to-nearest op in exactly the order
+// the reference's x86-64 SSE2 build performs it (SURVEY section 7 "hard parts").
+//
+//   geometry_kernel        find_line_in_detection_rects tail + corner intersections   dmz.cpp:346-438, geometry.cpp
+//   householder_qr_solve8  llcv_calc_persp_transform = Eigen 3.2.4 householderQr().solve cv/warp.cpp:34-125
+//   warp_kernel            cvWarpPerspective(INTER_LINEAR + FILL_OUTLIERS, 0)          cv/warp.cpp:153-166
+//   vseg_select_kernel     best_segmentation_for_vseg_scores + gating                  scan/n_vseg.cpp:49-92, frame.cpp:38-47
+//   hseg_kernel            best_n_hseg / best_n_hseg_constrained                        scan/n_hseg.cpp:39-152
+//   scan_finish_kernel     number_score gate                                            scan/frame.cpp:63-64
+//   finalize_records_kernel  flat per-frame record + card checksum
+#include <float.h>
+
+#include "b200_internal.h"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// Eigen 3.2.4 vectorised redux order (Core/Redux.h:192-246, Packet4f, SSE2 predux (a0+a2)+(a1+a3)),
+// alignedStart == 0.  v(i) yields the i-th coefficient of the reduced expression.
+// ------------------------------------------------------------------------------------------------
+template <typename F>
+__device__ __forceinline__ float eig_redux_sum(F v, int n) {
+  if (n == 0) return 0.0f;
+  const int aligned2 = (n / 8) * 8, aligned = (n / 4) * 4;
+  float res;
+  if (aligned) {
+    float p0[4], p1[4];
+#pragma unroll
+    for (int l = 0; l < 4; l++) p0[l] = v(l);
+    if (aligned > 4) {
+#pragma unroll
+      for (int l = 0; l < 4; l++) p1[l] = v(4 + l);
+      for (int i = 8; i < aligned2; i += 8) {
+#pragma unroll
+        for (int l = 0; l < 4; l++) {
+          p0[l] = p0[l] + v(i + l);
+          p1[l] = p1[l] + v(i + 4 + l);
+        }
+      }
+#pragma unroll
+      for (int l = 0; l < 4; l++) p0[l] = p0[l] + p1[l];
+      if (aligned > aligned2) {
+#pragma unroll
+        for (int l = 0; l < 4; l++) p0[l] = p0[l] + v(aligned2 + l);
+      }
+    }
+    res = (p0[0] + p0[2]) + (p0[1] + p0[3]);
+    for (int i = aligned; i < n; i++) res = res + v(i);
+  } else {
+    res = v(0);
+    for (int i = 1; i < n; i++) res = res + v(i);
+  }
+  return res;
+}
+
+// ------------------------------------------------------------------------------------------------
+// W1: x = A.householderQr().solve(b) for the 8x8 float system (column-major a[i + 8 j]).
+// Householder/HouseholderQR.h (unblocked; block size 8 covers the matrix), Householder.h,
+// HouseholderSequence.h, products/TriangularSolverVector.h -- operation by operation.
+// ------------------------------------------------------------------------------------------------
+#define A_(i, j) a[(i) + 8 * (j)]
+
+__device__ void householder_qr_solve8(float *a, const float *bvec, float *xout) {
+  float hcoef[8], tmp[8], c[8];
+  for (int k = 0; k < 8; k++) {
+    const int rem_rows = 8 - k, n = rem_rows - 1;
+    const float c0 = A_(k, k);
+    float tail_sq = 0.0f, beta, tau;
+    if (rem_rows != 1) tail_sq = eig_redux_sum([&](int i) { return A_(k + 1 + i, k) * A_(k + 1 + i, k); }, n);
+    if (tail_sq == 0.0f) {
+      tau = 0.0f;
+      beta = c0;
+      for (int i = 0; i < n; i++) A_(k + 1 + i, k) = 0.0f;
+    } else {
+      beta = sqrtf(c0 * c0 + tail_sq);
+      if (c0 >= 0.0f) beta = -beta;
+      const float denom = c0 - beta;
+      for (int i = 0; i < n; i++) A_(k + 1 + i, k) = A_(k + 1 + i, k) / denom;
+      tau = (beta - c0) / beta;
+    }
+    hcoef[k] = tau;
+    A_(k, k) = beta;
+    if (rem_rows != 1) {
+      for (int j = k + 1; j < 8; j++) tmp[j] = eig_redux_sum([&](int i) { return A_(k + 1 + i, k) * A_(k + 1 + i, j); }, n);
+      for (int j = k + 1; j < 8; j++) tmp[j] = tmp[j] + A_(k, j);
+      for (int j = k + 1; j < 8; j++) A_(k, j) = A_(k, j) - tau * tmp[j];
+      for (int j = k + 1; j < 8; j++)
+        for (int i = 0; i < n; i++) A_(k + 1 + i, j) = A_(k + 1 + i, j) - (A_(k + 1 + i, k) * tau) * tmp[j];
+    }
+  }
+  for (int i = 0; i < 8; i++) c[i] = bvec[i];
+  for (int k = 0; k < 8; k++) {
+    const int n = 7 - k;
+    const float tau = hcoef[k];
+    if (n == 0) {
+      c[k] = c[k] * (1.0f - tau);
+    } else {
+      float t = eig_redux_sum([&](int i) { return A_(k + 1 + i, k) * c[k + 1 + i]; }, n);
+      t = t + c[k];
+      c[k] = c[k] - tau * t;
+      for (int i = 0; i < n; i++) c[k + 1 + i] = c[k + 1 + i] - (A_(k + 1 + i, k) * tau) * t;
+    }
+  }
+  for (int k = 0; k < 8; k++) {
+    const int i = 7 - k;
+    c[i] = c[i] / A_(i, i);
+    for (int j = 0; j < i; j++) c[j] = c[j] - c[i] * A_(j, i);
+  }
+  for (int i = 0; i < 8; i++) xout[i] = c[i];
+}
+
+__device__ void calc_persp_transform(const float *s, const float *d, float *M) {
+  float a[64], b[8], x[8];
+  for (int i = 0; i < 64; i++) a[i] = 0.0f;
+  for (int i = 0; i < 4; i++) {
+    const float sx = s[2 * i], sy = s[2 * i + 1], dx = d[2 * i], dy = d[2 * i + 1];
+    A_(i, 0) = sx, A_(i, 1) = sy, A_(i, 2) = 1.0f;
+    A_(i, 6) = -sx * dx;
+    A_(i, 7) = -sy * dx;
+    A_(i + 4, 3) = sx, A_(i + 4, 4) = sy, A_(i + 4, 5) = 1.0f;
+    A_(i + 4, 6) = -sx * dy;
+    A_(i + 4, 7) = -sy * dy;
+    b[i] = dx;
+    b[i + 4] = dy;
+  }
+  householder_qr_solve8(a, b, x);
+  for (int i = 0; i < 8; i++) M[i] = x[i];
+  M[8] = 1.0f;
+}
+#undef A_
+
+// cv::invert of the 3x3 matrix promoted to double (closed-form adjugate path of lapack.cpp, 2.4.x)
+__device__ void invert3x3(const float *Mf, double *t) {
+  double m[9];
+  for (int i = 0; i < 9; i++) m[i] = (double)Mf[i];
+#define S(i, j) m[(i)*3 + (j)]
+  double d = S(0, 0) * (S(1, 1) * S(2, 2) - S(1, 2) * S(2, 1)) - S(0, 1) * (S(1, 0) * S(2, 2) - S(1, 2) * S(2, 0)) +
+             S(0, 2) * (S(1, 0) * S(2, 1) - S(1, 1) * S(2, 0));
+  if (d == 0.) {
+    for (int i = 0; i < 9; i++) t[i] = 0.0;
+    return;
+  }
+  d = 1. / d;
+  t[0] = (S(1, 1) * S(2, 2) - S(1, 2) * S(2, 1)) * d;
+  t[1] = (S(0, 2) * S(2, 1) - S(0, 1) * S(2, 2)) * d;
+  t[2] = (S(0, 1) * S(1, 2) - S(0, 2) * S(1, 1)) * d;
+  t[3] = (S(1, 2) * S(2, 0) - S(1, 0) * S(2, 2)) * d;
+  t[4] = (S(0, 0) * S(2, 2) - S(0, 2) * S(2, 0)) * d;
+  t[5] = (S(0, 2) * S(1, 0) - S(0, 0) * S(1, 2)) * d;
+  t[6] = (S(1, 0) * S(2, 1) - S(1, 1) * S(2, 0)) * d;
+  t[7] = (S(0, 1) * S(2, 0) - S(0, 0) * S(2, 1)) * d;
+  t[8] = (S(0, 0) * S(1, 1) - S(0, 1) * S(1, 0)) * d;
+#undef S
+}
+
+// dmz_transform_card corner permutation (dmz.cpp:446-481) + homography + inverse
+__device__ void corners_to_transform(const float *c /* tl, bl, tr, br */, int orientation, int upsample, FrameGeom *g) {
+  const float *tl = c, *bl = c + 2, *tr = c + 4, *br = c + 6;
+  const float *sp[4];
+  switch (orientation) {
+    case B200_ORIENT_PORTRAIT: sp[0] = bl, sp[1] = tl, sp[2] = br, sp[3] = tr; break;
+    case B200_ORIENT_LANDSCAPE_LEFT: sp[0] = br, sp[1] = bl, sp[2] = tr, sp[3] = tl; break;
+    case B200_ORIENT_PORTRAIT_UPSIDE_DOWN: sp[0] = tr, sp[1] = br, sp[2] = tl, sp[3] = bl; break;
+    default: sp[0] = tl, sp[1] = tr, sp[2] = bl, sp[3] = br; break;
+  }
+  float src[8];
+  const float dst[8] = {0.0f, 0.0f, 427.0f, 0.0f, 0.0f, 269.0f, 427.0f, 269.0f};
+  for (int i = 0; i < 4; i++) {
+    src[2 * i] = sp[i][0];
+    src[2 * i + 1] = sp[i][1];
+    if (upsample) {
+      src[2 * i] = src[2 * i] / 2.0f;
+      src[2 * i + 1] = src[2 * i + 1] / 2.0f;
+    }
+  }
+  calc_persp_transform(src, dst, g->M);
+  invert3x3(g->M, g->Minv);
+}
+
+// parametricIntersect (geometry.cpp:14-32): Eigen Matrix2f determinant / inverse (LU/Inverse.h:70-89)
+__device__ bool parametric_intersect(float rho1, float c1, float s1, float rho2, float c2, float s2, float *x, float *y) {
+  const float det = c1 * s2 - c2 * s1;
+  if ((double)det < 1e-10) return false;
+  const float invdet = 1.0f / det;
+  const float i00 = s2 * invdet, i10 = -c2 * invdet, i01 = -s1 * invdet, i11 = c1 * invdet;
+  *x = i00 * rho1 + i01 * rho2;
+  *y = i10 * rho1 + i11 * rho2;
+  return true;
+}
+
+__global__ void geometry_kernel(const __grid_constant__ GeomParams G, const b200_line *__restrict__ lines,
+                                size_t plane_stride, int n, FrameGeom *__restrict__ geom) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n) return;
+  FrameGeom g;
+  // dmz_edges slot order top, left, bottom, right; strips are stored top, bottom, left, right
+  const int box_of_slot[4] = {0, 2, 1, 3};
+  const float mult[3] = {1.0f, 2.0f, 2.0f};
+  for (int slot = 0; slot < 4; slot++) {
+    const int box = box_of_slot[slot];
+    g.found[slot] = 0, g.rho[slot] = 0.0f, g.theta[slot] = 0.0f, g.n_idx[slot] = 0;
+    for (int p = 0; p < G.n_planes && !g.found[slot]; p++) {
+      const b200_line l = lines[(size_t)p * plane_stride + (size_t)f * 4 + box];
+      if (l.found) {
+        float rho = (float)((double)l.rho + G.delta_rho[p][box][l.n]);  // lineByShiftingOrigin
+        rho = rho * mult[p];
+        g.found[slot] = 1;
+        g.rho[slot] = rho;
+        g.theta[slot] = G.theta[box >= 2][l.n];
+        g.n_idx[slot] = l.n;
+      }
+    }
+  }
+  g.all_found = 0;
+  for (int i = 0; i < 8; i++) g.corners[i] = 0.0f;
+  for (int i = 0; i < 9; i++) g.M[i] = 0.0f, g.Minv[i] = 0.0;
+  g.pad = 0;
+  if (g.found[0] && g.found[1] && g.found[2] && g.found[3]) {
+    // slots: 0 top (horizontal), 1 left (vertical), 2 bottom, 3 right
+    const float ct = G.cos_t[0][g.n_idx[0]], st = G.sin_t[0][g.n_idx[0]];
+    const float cl = G.cos_t[1][g.n_idx[1]], sl = G.sin_t[1][g.n_idx[1]];
+    const float cb = G.cos_t[0][g.n_idx[2]], sb = G.sin_t[0][g.n_idx[2]];
+    const float cr = G.cos_t[1][g.n_idx[3]], sr = G.sin_t[1][g.n_idx[3]];
+    float c[8];
+    const bool tl = parametric_intersect(g.rho[0], ct, st, g.rho[1], cl, sl, &c[0], &c[1]);
+    const bool bl = parametric_intersect(g.rho[2], cb, sb, g.rho[1], cl, sl, &c[2], &c[3]);
+    const bool tr = parametric_intersect(g.rho[0], ct, st, g.rho[3], cr, sr, &c[4], &c[5]);
+    const bool br = parametric_intersect(g.rho[2], cb, sb, g.rho[3], cr, sr, &c[6], &c[7]);
+    if (tl && bl && tr && br) {
+      for (int i = 0; i < 8; i++) g.corners[i] = c[i];
+      g.all_found = 1;
+      corners_to_transform(g.corners, G.orientation, 0, &g);
+    }
+  }
+  geom[f] = g;
+}
+
+__global__ void corners_to_geom_kernel(const b200_corner_points *__restrict__ corners, const uint8_t *__restrict__ valid,
+                                       int n, int orientation, int upsample, FrameGeom *__restrict__ geom) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n) return;
+  FrameGeom g;
+  for (int i = 0; i < 4; i++) g.found[i] = 1, g.rho[i] = 0.0f, g.theta[i] = 0.0f, g.n_idx[i] = 0;
+  const float *c = reinterpret_cast<const float *>(corners + f);
+  for (int i = 0; i < 8; i++) g.corners[i] = c[i];
+  g.all_found = valid ? (valid[f] != 0) : 1;
+  g.pad = 0;
+  for (int i = 0; i < 9; i++) g.M[i] = 0.0f, g.Minv[i] = 0.0;
+  if (g.all_found) corners_to_transform(g.corners, orientation, upsample, &g);
+  geom[f] = g;
+}
+
+__global__ void homography_only_kernel(const float *__restrict__ src, const float *__restrict__ dst, int n, float *__restrict__ M) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n) return;
+  float s[8], d[8], m[9];
+  for (int i = 0; i < 8; i++) s[i] = src[(size_t)f * 8 + i], d[i] = dst[(size_t)f * 8 + i];
+  calc_persp_transform(s, d, m);
+  for (int i = 0; i < 9; i++) M[(size_t)f * 9 + i] = m[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// W2: fixed-point perspective warp.  cv::warpPerspective traverses the destination in 64 x 16 blocks and
+// evaluates X0 = M0*x_block + M1*y + M2 once per block row, then (X0 + M0*x1) * (32 / W) per pixel; the
+// coordinates are rounded (half-to-even) to 1/32 px and the four taps are blended with 15-bit integer
+// weights, out-of-image taps being 0.  Each thread produces four horizontally adjacent pixels (one
+// 32-bit store); a CTA covers kWarpRows destination rows of one frame.
+// ------------------------------------------------------------------------------------------------
+constexpr int kWarpRows = 8;
+constexpr int kQuadsPerRow = B200_CARD_W / 4;  // 107
+
+__device__ __forceinline__ int warp_sample(const uint8_t *__restrict__ src, int row_stride, int sw, int sh, const double *M,
+                                           double X0, double Y0, double W0, int x1) {
+  double W = W0 + M[6] * x1;
+  W = W != 0.0 ? 32. / W : 0.0;
+  double fX = (X0 + M[0] * x1) * W;
+  double fY = (Y0 + M[3] * x1) * W;
+  fX = fX < -2147483648.0 ? -2147483648.0 : (fX > 2147483647.0 ? 2147483647.0 : fX);
+  fY = fY < -2147483648.0 ? -2147483648.0 : (fY > 2147483647.0 ? 2147483647.0 : fY);
+  const int X = __double2int_rn(fX), Y = __double2int_rn(fY);
+  int sx = X >> 5, sy = Y >> 5;
+  sx = sx < -32768 ? -32768 : (sx > 32767 ? 32767 : sx);  // saturate_cast<short>
+  sy = sy < -32768 ? -32768 : (sy > 32767 ? 32767 : sy);
+  const int fx = X & 31, fy = Y & 31;
+  int w00 = (32 - fx) * (32 - fy) * 32, w01 = fx * (32 - fy) * 32, w10 = (32 - fx) * fy * 32, w11 = fx * fy * 32;
+  if ((fx | fy) == 0) w00 = 32767, w11 = 1;  // initInterTab2D saturate/compensate quirk at (0,0)
+  int v0, v1, v2, v3;
+  if ((unsigned)sx < (unsigned)(sw - 1) && (unsigned)sy < (unsigned)(sh - 1)) {
+    const uint8_t *p = src + (size_t)sy * row_stride + sx;
+    v0 = __ldg(p), v1 = __ldg(p + 1), v2 = __ldg(p + row_stride), v3 = __ldg(p + row_stride + 1);
+  } else if (sx >= sw || sx + 1 < 0 || sy >= sh || sy + 1 < 0) {
+    return 0;
+  } else {
+    const bool x0ok = sx >= 0 && sx < sw, x1ok = sx + 1 >= 0 && sx + 1 < sw;
+    const bool y0ok = sy >= 0 && sy < sh, y1ok = sy + 1 >= 0 && sy + 1 < sh;
+    v0 = (x0ok && y0ok) ? __ldg(src + (size_t)sy * row_stride + sx) : 0;
+    v1 = (x1ok && y0ok) ? __ldg(src + (size_t)sy * row_stride + sx + 1) : 0;
+    v2 = (x0ok && y1ok) ? __ldg(src + (size_t)(sy + 1) * row_stride + sx) : 0;
+    v3 = (x1ok && y1ok) ? __ldg(src + (size_t)(sy + 1) * row_stride + sx + 1) : 0;
+  }
+  const int v = (v0 * w00 + v1 * w01 + v2 * w10 + v3 * w11 + (1 << 14)) >> 15;
+  return v < 0 ? 0 : (v > 255 ? 255 : v);
+}
+
+__global__ void __launch_bounds__(256)
+warp_kernel(const uint8_t *__restrict__ src, int row_stride, size_t frame_stride, int sw, int sh,
+            const FrameGeom *__restrict__ geom, uint8_t *__restrict__ cards) {
+  const int frame = blockIdx.y;
+  const int row0 = blockIdx.x * kWarpRows;
+  __shared__ double sM[9];
+  __shared__ int s_ok;
+  if (threadIdx.x < 9) sM[threadIdx.x] = geom[frame].Minv[threadIdx.x];
+  if (threadIdx.x == 0) s_ok = geom[frame].all_found;
+  __syncthreads();
+  uint8_t *dst = cards + (size_t)frame * (B200_CARD_W * B200_CARD_H);
+  const uint8_t *s = src + (size_t)frame * frame_stride;
+  const int nrows = min(kWarpRows, B200_CARD_H - row0);
+  for (int i = threadIdx.x; i < nrows * kQuadsPerRow; i += blockDim.x) {
+    const int r = i / kQuadsPerRow, q = i - r * kQuadsPerRow;
+    const int y = row0 + r, x = q * 4;
+    unsigned int packed = 0;
+    if (s_ok) {
+      const int xb = x & ~63;  // block origin: bw0 = 64
+      const double X0 = sM[0] * xb + sM[1] * y + sM[2];
+      const double Y0 = sM[3] * xb + sM[4] * y + sM[5];
+      const double W0 = sM[6] * xb + sM[7] * y + sM[8];
+#pragma unroll
+      for (int k = 0; k < 4; k++) packed |= (unsigned)warp_sample(s, row_stride, sw, sh, sM, X0, Y0, W0, x + k - xb) << (8 * k);
+    }
+    *reinterpret_cast<unsigned int *>(dst + (size_t)y * B200_CARD_W + x) = packed;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// V0 tail: best_segmentation_for_vseg_scores (n_vseg.cpp:49-92), sequential float running sums.
+// pass 0: coarse best -> window for the fine rows.  pass 1: final vseg + gating (frame.cpp:38-47).
+// ------------------------------------------------------------------------------------------------
+__device__ void best_segmentation(const float *__restrict__ vp /* [270][2] visa, amex */, float *score, int *ptype, int *yoff) {
+  float vsum = 0.0f, asum = 0.0f, best = 0.0f;
+  int bt = 0, by = 0;
+  for (int y = 0; y < 270; y++) {
+    vsum = vsum + vp[2 * y];
+    asum = asum + vp[2 * y + 1];
+    if (y >= 26) {
+      if (vsum > best) best = vsum, bt = 1, by = y - 26;
+      if (asum > best) best = asum, bt = 2, by = y - 26;
+      // ring_buffer[(y + 1) % 27] holds the score of row y - 26
+      vsum = vsum - vp[2 * (y - 26)];
+      asum = asum - vp[2 * (y - 26) + 1];
+    }
+  }
+  *score = best, *ptype = bt, *yoff = by;
+}
+
+__global__ void vseg_select_kernel(const float *__restrict__ vprob, const uint8_t *__restrict__ gate, int n, int pass,
+                                   b200_scan *__restrict__ scans) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n) return;
+  b200_scan *sc = scans + f;
+  if (gate && !gate[f]) {
+    if (pass == 1) {
+      b200_scan z;
+      memset(&z, 0, sizeof(z));
+      *sc = z;
+    } else {
+      sc->vseg.y_offset = 0xFFFF;  // no fine rows
+    }
+    return;
+  }
+  float score;
+  int pt, yo;
+  best_segmentation(vprob + (size_t)f * 540, &score, &pt, &yo);
+  if (pass == 0) {
+    sc->vseg.y_offset = (uint16_t)yo;
+    return;
+  }
+  const uint8_t pat[3][19] = {{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0},
+                              {1, 1, 1, 1, 0, 1, 1, 1, 1, 0, 1, 1, 1, 1, 0, 1, 1, 1, 1},
+                              {1, 1, 1, 1, 0, 1, 1, 1, 1, 1, 1, 0, 1, 1, 1, 1, 1, 0, 0}};
+  const uint8_t pat_len[3] = {0, 19, 17}, num_len[3] = {0, 16, 15};
+  b200_scan out;
+  memset(&out, 0, sizeof(out));
+  out.vseg.score = score;
+  out.vseg.y_offset = (uint16_t)yo;
+  out.vseg.pattern_type = (uint8_t)pt;
+  for (int i = 0; i < 19; i++) out.vseg.number_pattern[i] = pat[pt][i];
+  out.vseg.number_pattern_length = pat_len[pt];
+  out.vseg.number_length = num_len[pt];
+  if (yo < (B200_CARD_H - 27) / 2) out.upside_down = 1;  // kFlipVSegYOffsetCutoff
+  else out.usable = score > 15.0f;                       // kMinVSegScore
+  *sc = out;
+}
+
+// ------------------------------------------------------------------------------------------------
+// H0 / H1: best_n_hseg.  One CTA per frame.
+// ------------------------------------------------------------------------------------------------
+constexpr int kHsegThreads = 256;
+constexpr int kMaxWidths = 16;
+constexpr int kMaxCands = 1024;
+
+__device__ __constant__ float kNumberGradSumPattern[19] = {
+    0.26228655f, 0.30289554f, 0.34632607f, 0.38725636f, 0.42745813f, 0.45875135f, 0.46498017f,
+    0.45258447f, 0.43045216f, 0.42430462f, 0.44796554f, 0.47726529f, 0.48471646f, 0.46457738f,
+    0.42799847f, 0.38851183f, 0.33966308f, 0.28802608f, 0.25377602f};
+
+struct HsegPass {
+  int nwidths;
+  float width[kMaxWidths];
+  int omin[kMaxWidths], count[kMaxWidths], start[kMaxWidths + 1];
+  int ostep;
+};
+
+__global__ void __launch_bounds__(kHsegThreads)
+hseg_kernel(const uint8_t *__restrict__ cards, int n, b200_scan *__restrict__ scans) {
+  const int f = blockIdx.x;
+  const int tid = threadIdx.x;
+  b200_scan *sc = scans + f;
+  if (!sc->usable) return;  // upside_down / vseg gate (block-uniform)
+
+  __shared__ uint8_t s_strip[27][B200_CARD_W];
+  __shared__ float s_g[B200_CARD_W];
+  __shared__ int s_isum[B200_CARD_W];
+  __shared__ int s_mn, s_mx;
+  __shared__ HsegPass s_pass;
+  __shared__ unsigned long long s_red[kHsegThreads / 32];
+  __shared__ b200_hseg s_best;
+  __shared__ uint8_t s_pat[19];
+  __shared__ int s_npl;
+
+  const int y_off = sc->vseg.y_offset;
+  const uint8_t *card = cards + (size_t)f * (B200_CARD_W * B200_CARD_H) + (size_t)y_off * B200_CARD_W;
+  for (int i = tid; i < 27 * B200_CARD_W / 4; i += kHsegThreads)
+    reinterpret_cast<unsigned int *>(&s_strip[0][0])[i] = __ldg(reinterpret_cast<const unsigned int *>(card) + i);
+  if (tid < 19) s_pat[tid] = sc->vseg.number_pattern[tid];
+  if (tid == 0) {
+    s_npl = sc->vseg.number_pattern_length;
+    s_mn = 0x7fffffff, s_mx = 0;
+    b200_hseg b;
+    memset(&b, 0, sizeof(b));
+    b.n_offsets = sc->vseg.number_length;
+    b.score = 428.0f;
+    b.number_width = 0.0f;
+    s_best = b;
+  }
+  __syncthreads();
+
+  // llcv_morph_grad3_2d_cross_u8 on the isolated 428 x 27 strip (cv/morph.cpp:177-255), then cvReduce column sums
+  for (int x = tid; x < B200_CARD_W; x += kHsegThreads) {
+    const int xl = x > 0 ? x - 1 : x, xr = x < B200_CARD_W - 1 ? x + 1 : x;
+    int acc = 0;
+    for (int y = 0; y < 27; y++) {
+      const int yu = y > 0 ? y - 1 : y, yd = y < 26 ? y + 1 : y;
+      const int a = s_strip[yu][x], b = s_strip[y][xl], c = s_strip[y][x], d = s_strip[y][xr], e = s_strip[yd][x];
+      const int mx = max(a, max(b, max(c, max(d, e)))), mn = min(a, min(b, min(c, min(d, e))));
+      acc += mx - mn;
+    }
+    s_isum[x] = acc;
+    atomicMin(&s_mn, acc);
+    atomicMax(&s_mx, acc);
+  }
+  __syncthreads();
+  {
+    // cvNormalize(MINMAX, 0, 1): scale / shift in double, applied as float multiply then float add
+    const double smin = (double)(float)s_mn, smax = (double)(float)s_mx;
+    const double scale = (1.0 - 0.0) * (smax - smin > DBL_EPSILON ? 1. / (smax - smin) : 0.0);
+    const double shift = 0.0 - smin * scale;
+    const float fs = (float)scale, fb = (float)shift;
+    for (int x = tid; x < B200_CARD_W; x += kHsegThreads) s_g[x] = (float)s_isum[x] * fs + fb;
+  }
+  __syncthreads();
+
+  for (int pass = 0; pass < 4; pass++) {
+    if (tid == 0) {
+      float wmin, wmax, wstep;
+      unsigned omin, omax, ostep;
+      const b200_hseg &b = s_best;
+      if (pass == 0) {
+        wmin = 17.1f, wmax = 19.7f, wstep = 0.5f, omin = 0, omax = 0xFFFF, ostep = 10;
+      } else if (pass == 1) {
+        wmin = b.number_width - 0.5f, wmax = b.number_width + 0.5f, wstep = 0.2f;
+        omin = b.pattern_offset < 10 ? 0 : b.pattern_offset - 10, omax = (uint16_t)(b.pattern_offset + 10), ostep = 1;
+      } else if (pass == 2) {
+        wmin = b.number_width - 0.2f, wmax = b.number_width + 0.2f, wstep = 0.1f;
+        omin = b.pattern_offset < 3 ? 0 : b.pattern_offset - 3, omax = (uint16_t)(b.pattern_offset + 3), ostep = 1;
+      } else {
+        wmin = b.number_width - 0.1f, wmax = b.number_width + 0.1f, wstep = 0.05f;
+        omin = b.pattern_offset < 3 ? 0 : b.pattern_offset - 3, omax = (uint16_t)(b.pattern_offset + 3), ostep = 1;
+      }
+      int nw = 0, total = 0;
+      for (float width = wmin; width < wmax && nw < kMaxWidths; width += wstep) {
+        const float pattern_width = (float)s_npl * width;
+        unsigned pom = omax;
+        const unsigned maximum = (uint16_t)(428 - (long)__float2int_rn(pattern_width));  // lrintf: current rounding mode = nearest-even
+        if (pom == 0xFFFFu || pom > maximum) pom = maximum;
+        int cnt = pom > omin ? (int)((pom - omin + ostep - 1) / ostep) : 0;
+        if (total + cnt > kMaxCands) cnt = kMaxCands - total;
+        s_pass.width[nw] = width;
+        s_pass.omin[nw] = (int)omin;
+        s_pass.count[nw] = cnt;
+        s_pass.start[nw] = total;
+        total += cnt;
+        nw++;
+      }
+      s_pass.start[nw] = total;
+      s_pass.nwidths = nw;
+      s_pass.ostep = (int)ostep;
+    }
+    __syncthreads();
+    const int total = s_pass.start[s_pass.nwidths];
+    unsigned long long best_key = ~0ull;
+    // eight lanes per candidate reproduce Eigen's two 4-lane packet accumulators over the 428 coefficients
+    const int lane8 = tid & 7;
+    for (int c0 = 0; c0 < total; c0 += kHsegThreads / 8) {
+      const int c = c0 + (tid >> 3);
+      float score = 0.0f;
+      bool valid = c < total;
+      int centers[16];
+      int nd = 0;
+      if (valid) {
+        int wi = 0;
+        while (c >= s_pass.start[wi + 1]) wi++;
+        const float width = s_pass.width[wi];
+        const int offset = s_pass.omin[wi] + (c - s_pass.start[wi]) * s_pass.ostep;
+        for (int pi = 0; pi < s_npl; pi++) {
+          if (s_pat[pi]) {
+            const int center = (uint16_t)(offset + __float2int_rn((float)pi * width));
+            if (!(center + 19 < 428)) valid = false;
+            if (nd < 16) centers[nd] = center;
+            nd++;
+          }
+        }
+      }
+      if (nd > 16) nd = 16;
+      // (valid is uniform across the eight lanes of a candidate; the shuffles stay outside any branch)
+      int d = -1;  // last digit whose template starts at or before i
+      auto coeff = [&](int i) -> float {
+        while (d + 1 < nd && centers[d + 1] <= i) d++;
+        float p = 0.0f;
+        if (d >= 0 && i - centers[d] < 19) p = kNumberGradSumPattern[i - centers[d]];
+        return fabsf(s_g[i] - p);
+      };
+      float acc = 0.0f;
+      if (valid) {
+        acc = coeff(lane8);
+        for (int k = 1; k < 53; k++) acc = acc + coeff(8 * k + lane8);
+      }
+      const float hi = __shfl_down_sync(0xffffffffu, acc, 4, 8);
+      float r = acc + hi;                                         // packet_res0 + packet_res1
+      if (valid && lane8 < 4) r = r + coeff(424 + lane8);         // the 107th packet
+      const float r2 = __shfl_down_sync(0xffffffffu, r, 2, 8);
+      const float t = r + r2;                                     // lanes 0,1: (r0 + r2), (r1 + r3)
+      const float t1 = __shfl_down_sync(0xffffffffu, t, 1, 8);
+      score = t + t1;                                             // lane 0: (r0 + r2) + (r1 + r3)
+      if (valid && lane8 == 0) {
+        const unsigned long long key = ((unsigned long long)__float_as_uint(score) << 32) | (unsigned)c;
+        best_key = key < best_key ? key : best_key;
+      }
+    }
+    // block argmin (smallest score, then smallest candidate index = first in the reference's loop order)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long t = __shfl_xor_sync(0xffffffffu, best_key, o);
+      best_key = t < best_key ? t : best_key;
+    }
+    if ((tid & 31) == 0) s_red[tid >> 5] = best_key;
+    __syncthreads();
+    if (tid == 0) {
+      unsigned long long k = ~0ull;
+      for (int i = 0; i < kHsegThreads / 32; i++) k = s_red[i] < k ? s_red[i] : k;
+      if (k != ~0ull) {
+        const float score = __uint_as_float((unsigned)(k >> 32));
+        const int c = (int)(k & 0xFFFFFFFFu);
+        if (score < s_best.score) {
+          int wi = 0;
+          while (c >= s_pass.start[wi + 1]) wi++;
+          const float width = s_pass.width[wi];
+          const int offset = s_pass.omin[wi] + (c - s_pass.start[wi]) * s_pass.ostep;
+          int oi = 0;
+          for (int i = 0; i < 16; i++) s_best.offsets[i] = 0;
+          for (int pi = 0; pi < s_npl; pi++)
+            if (s_pat[pi]) {
+              if (oi < 16) s_best.offsets[oi] = (uint16_t)(offset + __float2int_rn((float)pi * width));
+              oi++;
+            }
+          s_best.score = score;
+          s_best.number_width = width;
+          s_best.pattern_offset = (uint16_t)offset;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0) sc->hseg = s_best;
+}
+
+// S0 tail: usable = (n_offsets - scores.sum()) < kMaxNumberScoreDelta, frame.cpp:63-64.  scores.sum() on the
+// 16x10 fixed matrix is the vectorised linear redux.
+__global__ void scan_finish_kernel(int n, b200_scan *__restrict__ scans) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n) return;
+  b200_scan *sc = scans + f;
+  if (!sc->usable) return;
+  const float *s = sc->scores;
+  const float sum = eig_redux_sum([&](int i) { return s[i]; }, 160);
+  const float number_score = (float)sc->hseg.n_offsets - sum;
+  sc->usable = number_score < 3.0f;
+}
+
+// Flat per-frame record + card checksum sum_i (i+1) * card[i] (mod 2^32).  One CTA per frame.
+__global__ void __launch_bounds__(256)
+finalize_records_kernel(const FrameGeom *__restrict__ geom, const b200_scan *__restrict__ scans,
+                        const uint8_t *__restrict__ cards, b200_frame_record *__restrict__ recs) {
+  const int f = blockIdx.x;
+  const int tid = threadIdx.x;
+  __shared__ unsigned int s_red[8];
+  const FrameGeom &g = geom[f];
+  unsigned int sum = 0;
+  if (g.all_found) {
+    const unsigned int *c = reinterpret_cast<const unsigned int *>(cards + (size_t)f * (B200_CARD_W * B200_CARD_H));
+    for (int i = tid; i < B200_CARD_W * B200_CARD_H / 4; i += 256) {
+      const unsigned int v = __ldg(c + i);
+      const unsigned int base = 4u * (unsigned)i + 1u;
+      sum += base * (v & 255u) + (base + 1u) * ((v >> 8) & 255u) + (base + 2u) * ((v >> 16) & 255u) + (base + 3u) * (v >> 24);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((tid & 31) == 0) s_red[tid >> 5] = sum;
+  __syncthreads();
+  if (tid == 0) {
+    unsigned int tot = 0;
+    for (int i = 0; i < 8; i++) tot += s_red[i];
+    b200_frame_record r;
+    memset(&r, 0, sizeof(r));
+    for (int i = 0; i < 4; i++) r.found[i] = g.found[i], r.rho[i] = g.rho[i], r.theta[i] = g.theta[i];
+    for (int i = 0; i < 8; i++) r.corners[i] = g.corners[i];
+    r.all_found = g.all_found;
+    if (g.all_found) {
+      r.scan = scans[f];
+      r.card_check = tot;
+    }
+    recs[f] = r;
+  }
+}
+
+__global__ void scan_gate_kernel(const FrameGeom *__restrict__ geom, const uint8_t *__restrict__ valid, int n, uint8_t *__restrict__ gate) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n) return;
+  uint8_t g = 1;
+  if (geom) g = geom[f].all_found != 0;
+  if (valid) g = g && valid[f];
+  gate[f] = g;
+}
+
+}  // namespace
+
+static int blocks_for(int n, int t) { return (n + t - 1) / t; }
+
+int launch_geometry(const GeomParams &g, const b200_line *lines, size_t plane_stride, int n, FrameGeom *geom, cudaStream_t s) {
+  geometry_kernel<<<blocks_for(n, 64), 64, 0, s>>>(g, lines, plane_stride, n, geom);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int launch_homography_only(const float *src_pts, const float *dst_pts, int n, float *M, cudaStream_t s) {
+  homography_only_kernel<<<blocks_for(n, 64), 64, 0, s>>>(src_pts, dst_pts, n, M);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int launch_corners_to_geom(const b200_corner_points *corners, const uint8_t *valid, int n, int orientation, int upsample,
+                           FrameGeom *geom, cudaStream_t s) {
+  corners_to_geom_kernel<<<blocks_for(n, 64), 64, 0, s>>>(corners, valid, n, orientation, upsample, geom);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int launch_warp(const uint8_t *src, int row_stride, size_t frame_stride, int w, int h, int n, const FrameGeom *geom,
+                uint8_t *cards, cudaStream_t s) {
+  int launches = 0;
+  const int row_blocks = (B200_CARD_H + kWarpRows - 1) / kWarpRows;
+  for (int f0 = 0; f0 < n; f0 += 65535) {
+    const int cnt = n - f0 < 65535 ? n - f0 : 65535;
+    warp_kernel<<<dim3(row_blocks, cnt), 256, 0, s>>>(src + (size_t)f0 * frame_stride, row_stride, frame_stride, w, h, geom + f0,
+                                                      cards + (size_t)f0 * (B200_CARD_W * B200_CARD_H));
+    launches++;
+  }
+  return cudaGetLastError() == cudaSuccess ? launches : -1;
+}
+
+int launch_finalize_records(const FrameGeom *geom, const b200_scan *scans, const uint8_t *cards, int n,
+                            b200_frame_record *recs, cudaStream_t s) {
+  finalize_records_kernel<<<n, 256, 0, s>>>(geom, scans, cards, recs);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// exported to nets.cu's launch_scan through these thin wrappers
+int launch_scan_gate(const FrameGeom *geom, const uint8_t *valid, int n, uint8_t *gate, cudaStream_t s) {
+  scan_gate_kernel<<<blocks_for(n, 256), 256, 0, s>>>(geom, valid, n, gate);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+int launch_vseg_select(const float *vprob, const uint8_t *gate, int n, int pass, b200_scan *scans, cudaStream_t s) {
+  vseg_select_kernel<<<blocks_for(n, 64), 64, 0, s>>>(vprob, gate, n, pass, scans);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+int launch_hseg(const uint8_t *cards, int n, b200_scan *scans, cudaStream_t s) {
+  hseg_kernel<<<n, kHsegThreads, 0, s>>>(cards, n, scans);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+int launch_scan_finish(int n, b200_scan *scans, cudaStream_t s) {
+  scan_finish_kernel<<<blocks_for(n, 128), 128, 0, s>>>(n, scans);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}

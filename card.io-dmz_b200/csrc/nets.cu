@@ -1,0 +1,479 @@
+// card.io-dmz_b200/csrc/nets.cu -- the two generated networks of the number path, as direct small-filter
+// CUDA-core kernels (FP32 FMA; contract: <= 1e-4 on the probabilities, scan/../models KATs at 1e-5).
+//
+//   vseg_rows_kernel    vseg_probabilities_for_hstrip = llcv_morph_grad3_1d_u8 -> llcv_lineardown2_1d_u8 ->
+//                       llcv_norm_convert_1d_u8_to_f32 -> applym_befe75da      scan/n_vseg.cpp:39-47,
+//                                                                               models/generated/modelm_befe75da.cpp:1770-1786
+//   categorize_kernel   number_scores: per digit ROI -> llcv_morph_grad3_2d_cross_u8 -> llcv_equalize_hist -> /255 ->
+//                       applyc_{5c241121,01266c1b,b00bf70c} -> (r0+r1+r2-max)/2 scan/n_categorize.cpp:45-108,
+//                                                                               models/generated/modelc_*.cpp:1844-1937
+//
+// Neither contraction is large enough to fill a tcgen05 MMA tile at FP32-equivalent accuracy (the 3x3
+// convolutions have K = 9; the FC layers are 320x32 and 204x50 and would need a 3xTF32 split to hold 1e-4),
+// so they run on the FP32 pipe: convolution weights are warp-uniform operands served from __constant__
+// memory, FC weights sit in shared memory for the lifetime of a persistent CTA.
+#include <float.h>
+
+#include "b200_internal.h"
+
+// exact.cu
+int launch_scan_gate(const FrameGeom *geom, const uint8_t *valid, int n, uint8_t *gate, cudaStream_t s);
+int launch_vseg_select(const float *vprob, const uint8_t *gate, int n, int pass, b200_scan *scans, cudaStream_t s);
+int launch_hseg(const uint8_t *cards, int n, b200_scan *scans, cudaStream_t s);
+int launch_scan_finish(int n, b200_scan *scans, cudaStream_t s);
+
+namespace {
+
+constexpr int kCardBytes = B200_CARD_W * B200_CARD_H;
+
+// conv kernels and post-pool biases of the three digit CNNs: [model][kernel][9] and [model][kernel]
+__constant__ float c_conv_w[3][8][9];
+__constant__ float c_conv_b[3][8];
+
+// ------------------------------------------------------------------------------------------------
+// V1 + V2.  A CTA owns a tile of kVRows (frame,row) work items; W1 (50 x 204, padded rows) stays in shared
+// memory across the persistent tile loop.
+// ------------------------------------------------------------------------------------------------
+constexpr int kVThreads = 256;
+constexpr int kVRows = 32;
+constexpr int kVStride = 205;  // odd stride: conflict-free column walks
+constexpr int kFineSlots = 43; // rows [y0 - 8, y0 + 35)
+
+struct VsegSmem {
+  float w1[50 * kVStride];
+  float b1[50];
+  float w2[3 * 50];
+  float b2[3];
+  float x[kVRows][204];
+  float h[kVRows][52];
+  int item_frame[kVRows];
+  int item_row[kVRows];
+};
+
+// mode 0: coarse rows 0,4,..,268 of every gated frame.  mode 1: fine rows around the coarse best.
+// mode 2: raw prepared rows (stage tap): in = n x 204 floats, out = n x 3.
+__global__ void __launch_bounds__(kVThreads)
+vseg_rows_kernel(const float *__restrict__ wts, const uint8_t *__restrict__ cards, const uint8_t *__restrict__ gate,
+                 const b200_scan *__restrict__ scans, int n, int mode, float *__restrict__ vprob,
+                 const float *__restrict__ raw_rows, float *__restrict__ raw_out) {
+  extern __shared__ __align__(16) uint8_t vs_raw[];
+  VsegSmem &S = *reinterpret_cast<VsegSmem *>(vs_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  for (int i = tid; i < 50 * 204; i += kVThreads) S.w1[(i / 204) * kVStride + (i % 204)] = __ldg(wts + i);
+  for (int i = tid; i < 50; i += kVThreads) S.b1[i] = __ldg(wts + 10200 + i);
+  for (int i = tid; i < 150; i += kVThreads) S.w2[i] = __ldg(wts + 10250 + i);
+  if (tid < 3) S.b2[tid] = __ldg(wts + 10400 + tid);
+
+  const int per_frame = mode == 0 ? 68 : (mode == 1 ? kFineSlots : 1);
+  const long long total = (long long)n * per_frame;
+  const long long ntiles = (total + kVRows - 1) / kVRows;
+
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    __syncthreads();  // weights visible / previous tile consumed
+    // ---- resolve the work items of this tile
+    if (tid < kVRows) {
+      const long long item = tile * kVRows + tid;
+      int fr = -1, row = -1;
+      if (item < total) {
+        const int f = (int)(item / per_frame), j = (int)(item % per_frame);
+        if (mode == 2) {
+          fr = f, row = 0;
+        } else if (!gate || gate[f]) {
+          if (mode == 0) {
+            fr = f, row = 4 * j;
+          } else {
+            const int y0 = scans[f].vseg.y_offset;  // coarse best (vseg_select pass 0)
+            const int lo = y0 < 8 ? 0 : y0 - 8;     // n_vseg.cpp:140-142
+            const int hi = min(270, y0 + 27 + 8);
+            const int r = lo + j;
+            if (y0 != 0xFFFF && r < hi && (r & 3) != 0) fr = f, row = r;  // rows r % 4 == 0 were scored by the coarse pass
+          }
+        }
+      }
+      S.item_frame[tid] = fr;
+      S.item_row[tid] = row;
+    }
+    __syncthreads();
+    // ---- V1: row preparation, one warp per row (4 rows per warp)
+    for (int r = warp; r < kVRows; r += kVThreads / 32) {
+      const int fr = S.item_frame[r];
+      if (fr < 0) continue;  // warp-uniform
+      if (mode == 2) {
+        for (int k = lane; k < 204; k += 32) S.x[r][k] = __ldg(raw_rows + (size_t)fr * 204 + k);
+        continue;
+      }
+      const uint8_t *src = cards + (size_t)fr * kCardBytes + (size_t)S.item_row[r] * B200_CARD_W + 10;
+      // ROI (10, row, 408, 1): 3-tap max - min with replicate at the ROI edge, then (a + b + 1) >> 1
+      int vals[7];
+      int mn = 255, mx = 0;
+#pragma unroll
+      for (int q = 0; q < 7; q++) {
+        const int k = lane + 32 * q;  // output index 0..203
+        int v = 0;
+        if (k < 204) {
+          const int j0 = 2 * k, j1 = 2 * k + 1;
+          const int a = __ldg(src + (j0 > 0 ? j0 - 1 : 0)), b = __ldg(src + j0), c = __ldg(src + j1), d = __ldg(src + (j1 < 407 ? j1 + 1 : 407));
+          const int g0 = max(a, max(b, c)) - min(a, min(b, c));
+          const int g1 = max(b, max(c, d)) - min(b, min(c, d));
+          v = (g0 + g1 + 1) >> 1;
+          mn = min(mn, v);
+          mx = max(mx, v);
+        }
+        vals[q] = v;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      }
+      // cvConvertScale(1/255) then cvNormalize(MINMAX 0..1): float multiply, then float multiply + float add
+      const float k255 = 1.0f / 255.0f;
+      const float fmn = __fmul_rn((float)mn, k255), fmx = __fmul_rn((float)mx, k255);
+      const double smin = (double)fmn, smax = (double)fmx;
+      const double scale = (smax - smin > DBL_EPSILON) ? 1. / (smax - smin) : 0.0;
+      const double shift = 0.0 - smin * scale;
+      const float fs = (float)scale, fb = (float)shift;
+#pragma unroll
+      for (int q = 0; q < 7; q++) {
+        const int k = lane + 32 * q;
+        if (k < 204) S.x[r][k] = __fadd_rn(__fmul_rn(__fmul_rn((float)vals[q], k255), fs), fb);
+      }
+    }
+    __syncthreads();
+    // ---- V2 hidden layer: thread -> (unit i, row group g); rows g, g+5, ...
+    if (tid < 250) {
+      const int i = tid % 50, g = tid / 50;
+      float acc[7];
+#pragma unroll
+      for (int q = 0; q < 7; q++) acc[q] = 0.0f;
+      const float *w = S.w1 + i * kVStride;
+      for (int k = 0; k < 204; k++) {
+        const float wk = w[k];
+#pragma unroll
+        for (int q = 0; q < 7; q++) {
+          const int r = g + 5 * q;
+          if (r < kVRows) acc[q] = fmaf(wk, S.x[r][k], acc[q]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 7; q++) {
+        const int r = g + 5 * q;
+        if (r < kVRows) S.h[r][i] = tanhf(acc[q] + S.b1[i]);
+      }
+    }
+    __syncthreads();
+    // ---- logistic layer + softmax (expf / sum, no max shift -- as the generated model does)
+    if (tid < kVRows) {
+      const int fr = S.item_frame[tid];
+      if (fr >= 0) {
+        float o[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          float acc = 0.0f;
+          for (int k = 0; k < 50; k++) acc = fmaf(S.w2[c * 50 + k], S.h[tid][k], acc);
+          o[c] = expf(acc + S.b2[c]);
+        }
+        const float sum = (o[0] + o[1]) + o[2];
+        if (mode == 2) {
+          raw_out[(size_t)fr * 3 + 0] = o[0] / sum;
+          raw_out[(size_t)fr * 3 + 1] = o[1] / sum;
+          raw_out[(size_t)fr * 3 + 2] = o[2] / sum;
+        } else {
+          float *dst = vprob + ((size_t)fr * 270 + S.item_row[tid]) * 2;
+          dst[0] = o[1] / sum;  // visa-like
+          dst[1] = o[2] / sum;  // amex-like
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// C0..C2.  One CTA (8 warps) processes the 16 digit slots of a "group" (= one frame, or 16 raw patches);
+// persistent over groups so the 123 KB of transposed hidden weights are staged once per CTA.
+// ------------------------------------------------------------------------------------------------
+constexpr int kCThreads = 256;
+
+struct CatSmem {
+  float hwT[3][320][32];   // hidden W transposed: [model][feature][unit]
+  float hb[3][32];
+  float lw[3][10][32];
+  float lb[3][10];
+  float patch[16][27 * 19 + 3];  // normalised digit images
+  float feat[16][320];           // tanh(pool + bias) of the current model
+  float hid[16][3][32];
+  float prob[16][3][10];
+  unsigned int hist[8][256];
+  uint8_t g8[8][27 * 20];
+  uint8_t lut[8][256];
+};
+
+template <bool kRaw>
+__global__ void __launch_bounds__(kCThreads, 1)
+categorize_kernel(NetWeights W, const uint8_t *__restrict__ cards, b200_scan *__restrict__ scans,
+                  const uint8_t *__restrict__ raw_patches, int n_items /* frames, or raw patches */, float *__restrict__ raw_out) {
+  extern __shared__ __align__(16) uint8_t cs_raw[];
+  CatSmem &S = *reinterpret_cast<CatSmem *>(cs_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  for (int i = tid; i < 3 * 320 * 32; i += kCThreads) (&S.hwT[0][0][0])[i] = __ldg(W.cnn_hwT + i);
+  for (int m = 0; m < 3; m++) {
+    const float *b = W.cnn[m];
+    for (int i = tid; i < 32; i += kCThreads) S.hb[m][i] = __ldg(b + 80 + 10240 + i);
+    for (int i = tid; i < 320; i += kCThreads) S.lw[m][i / 32][i % 32] = __ldg(b + 80 + 10240 + 32 + i);
+    for (int i = tid; i < 10; i += kCThreads) S.lb[m][i] = __ldg(b + 80 + 10240 + 32 + 320 + i);
+  }
+
+  const int n_groups = kRaw ? (n_items + 15) / 16 : n_items;
+  for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+    __syncthreads();
+    int nd;
+    const uint8_t *src_base = nullptr;
+    const b200_scan *sc = nullptr;
+    if (kRaw) {
+      nd = min(16, n_items - grp * 16);
+    } else {
+      sc = scans + grp;
+      if (!sc->usable) continue;  // block-uniform: upside-down / vseg gate (frame.cpp:38-47)
+      nd = min(16, (int)sc->hseg.n_offsets);
+      src_base = cards + (size_t)grp * kCardBytes + (size_t)sc->vseg.y_offset * B200_CARD_W;
+    }
+    // ---- C0 + C1: patch preparation, one warp per digit (two rounds of eight)
+    for (int d = warp; d < nd; d += 8) {
+      const uint8_t *src;
+      int stride;
+      if (kRaw) {
+        src = raw_patches + (size_t)(grp * 16 + d) * (27 * 19);
+        stride = 19;
+      } else {
+        src = src_base + sc->hseg.offsets[d];
+        stride = B200_CARD_W;
+      }
+      uint8_t *g8 = S.g8[warp];
+      unsigned int *hist = S.hist[warp];
+      for (int i = lane; i < 256; i += 32) hist[i] = 0;
+      __syncwarp();
+      // 5-point cross max - min with replicate at the PATCH edge (cv/morph.cpp:177-255 on the 19x27 ROI)
+      for (int i = lane; i < 27 * 19; i += 32) {
+        const int y = i / 19, x = i - y * 19;
+        const int yu = y > 0 ? y - 1 : y, yd = y < 26 ? y + 1 : y, xl = x > 0 ? x - 1 : x, xr = x < 18 ? x + 1 : x;
+        const int a = __ldg(src + yu * stride + x), b = __ldg(src + y * stride + xl), c = __ldg(src + y * stride + x);
+        const int e = __ldg(src + y * stride + xr), f = __ldg(src + yd * stride + x);
+        const int v = max(a, max(b, max(c, max(e, f)))) - min(a, min(b, min(c, min(e, f))));
+        g8[y * 20 + x] = (uint8_t)v;
+        atomicAdd(&hist[v], 1u);
+      }
+      __syncwarp();
+      // llcv_equalize_hist (cv/stats.cpp:116-159): lut[i] = sat8(cvRound(cum(i) * (255.f / 513))), lut[0] = 0
+      {
+        unsigned int local[8], run = 0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+          run += hist[lane * 8 + q];
+          local[q] = run;
+        }
+        unsigned int incl = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += t;
+        }
+        const unsigned int excl = incl - run;
+        const float scale = 255.f / (19 * 27);
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+          const int val = __float2int_rn(__fmul_rn((float)(int)(excl + local[q]), scale));
+          S.lut[warp][lane * 8 + q] = (uint8_t)(val < 0 ? 0 : (val > 255 ? 255 : val));
+        }
+        __syncwarp();
+        if (lane == 0) S.lut[warp][0] = 0;
+        __syncwarp();
+      }
+      for (int i = lane; i < 27 * 19; i += 32) {
+        const int y = i / 19, x = i - y * 19;
+        S.patch[d][i] = __fmul_rn((float)S.lut[warp][g8[y * 20 + x]], 1.0f / 255.0f);  // cvConvertScale
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+    // ---- C2, model by model
+    for (int m = 0; m < 3; m++) {
+      // conv 3x3 (valid, 24 x 15 computed) -> 3x3/3 max pool (8 x 5) -> + bias -> tanh.  Work item = (digit, pooled
+      // cell); the 5x5 input window of a cell is loaded once and feeds all eight kernels.
+      for (int it = tid; it < nd * 40; it += kCThreads) {
+        const int d = it / 40, cell = it - d * 40;
+        const int pr = cell / 5, pc = cell - pr * 5;
+        const float *p = &S.patch[d][(pr * 3) * 19 + pc * 3];
+        float win[5][5];
+#pragma unroll
+        for (int i = 0; i < 5; i++)
+#pragma unroll
+          for (int j = 0; j < 5; j++) win[i][j] = p[i * 19 + j];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          float best = -FLT_MAX;
+#pragma unroll
+          for (int r = 0; r < 3; r++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+              float acc = 0.0f;
+#pragma unroll
+              for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int j = 0; j < 3; j++) acc = fmaf(c_conv_w[m][k][i * 3 + j], win[r + i][c + j], acc);
+              best = fmaxf(best, acc);
+            }
+          S.feat[d][k * 40 + cell] = tanhf(best + c_conv_b[m][k]);
+        }
+      }
+      __syncthreads();
+      // hidden layer 320 -> 32: thread -> (unit, digit pair)
+      {
+        const int u = tid & 31, dg = tid >> 5;  // digits dg and dg + 8
+        float a0 = 0.0f, a1 = 0.0f;
+        const bool v0 = dg < nd, v1 = dg + 8 < nd;
+        if (v0) {
+          for (int j = 0; j < 320; j++) {
+            const float wv = S.hwT[m][j][u];
+            a0 = fmaf(wv, S.feat[dg][j], a0);
+            if (v1) a1 = fmaf(wv, S.feat[dg + 8][j], a1);
+          }
+          S.hid[dg][m][u] = tanhf(a0 + S.hb[m][u]);
+          if (v1) S.hid[dg + 8][m][u] = tanhf(a1 + S.hb[m][u]);
+        }
+      }
+      __syncthreads();
+    }
+    // logistic layer 32 -> 10 and softmax, thread -> (digit, model, class)
+    for (int it = tid; it < nd * 30; it += kCThreads) {
+      const int d = it / 30, r = it - d * 30, m = r / 10, c = r - m * 10;
+      float acc = 0.0f;
+#pragma unroll
+      for (int j = 0; j < 32; j++) acc = fmaf(S.lw[m][c][j], S.hid[d][m][j], acc);
+      S.prob[d][m][c] = expf(acc + S.lb[m][c]);
+    }
+    __syncthreads();
+    for (int it = tid; it < 16 * 10; it += kCThreads) {
+      const int d = it / 10, c = it - d * 10;
+      float e = 0.0f, pm[3] = {0.0f, 0.0f, 0.0f};
+      if (d < nd) {
+#pragma unroll
+        for (int m = 0; m < 3; m++) {
+          float sum = 0.0f;
+#pragma unroll
+          for (int j = 0; j < 10; j++) sum += S.prob[d][m][j];
+          pm[m] = S.prob[d][m][c] / sum;
+        }
+        const float mx = fmaxf(pm[0], fmaxf(pm[1], pm[2]));
+        e = (((pm[0] + pm[1]) + pm[2]) - mx) / 2.0f;  // n_categorize.cpp:69-70
+      }
+      if (kRaw) {
+        if (d < nd) {
+          float *o = raw_out + (size_t)(grp * 16 + d) * 40;
+          o[c] = e;
+          o[10 + c] = pm[0];
+          o[20 + c] = pm[1];
+          o[30 + c] = pm[2];
+        }
+      } else {
+        scans[grp].scores[d * 10 + c] = e;  // rows >= n_offsets stay 0 (NumberScores::Zero())
+      }
+    }
+  }
+}
+
+int g_num_sms = 0;
+
+int num_sms() {
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <typename K>
+bool ensure_smem(K kernel, size_t bytes) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) == cudaSuccess;
+}
+
+}  // namespace
+
+int upload_conv_constants(const float *cnn_blobs[3]) {
+  float w[3][8][9], b[3][8];
+  for (int m = 0; m < 3; m++) {
+    for (int i = 0; i < 72; i++) (&w[m][0][0])[i] = cnn_blobs[m][i];
+    for (int i = 0; i < 8; i++) b[m][i] = cnn_blobs[m][72 + i];
+  }
+  if (cudaMemcpyToSymbol(c_conv_w, w, sizeof(w)) != cudaSuccess) return -1;
+  if (cudaMemcpyToSymbol(c_conv_b, b, sizeof(b)) != cudaSuccess) return -1;
+  return 0;
+}
+
+static int launch_vseg_rows(const NetWeights &wts, const uint8_t *cards, const uint8_t *gate, const b200_scan *scans, int n,
+                            int mode, float *vprob, const float *raw_rows, float *raw_out, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    if (!ensure_smem(vseg_rows_kernel, sizeof(VsegSmem))) return -1;
+    configured = true;
+  }
+  const int per_frame = mode == 0 ? 68 : (mode == 1 ? kFineSlots : 1);
+  const long long tiles = ((long long)n * per_frame + kVRows - 1) / kVRows;
+  const int ctas_per_sm = 2;
+  long long grid = (long long)num_sms() * ctas_per_sm;
+  if (grid > tiles) grid = tiles;
+  if (grid < 1) grid = 1;
+  vseg_rows_kernel<<<(int)grid, kVThreads, sizeof(VsegSmem), s>>>(wts.vseg, cards, gate, scans, n, mode, vprob, raw_rows, raw_out);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int launch_vseg_model(const NetWeights &wts, const float *rows, int n, float *out, cudaStream_t s) {
+  return launch_vseg_rows(wts, nullptr, nullptr, nullptr, n, 2, nullptr, rows, out, s);
+}
+
+static int launch_categorize(const NetWeights &wts, const uint8_t *cards, b200_scan *scans, const uint8_t *raw, int n,
+                             float *raw_out, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    if (!ensure_smem(categorize_kernel<false>, sizeof(CatSmem))) return -1;
+    if (!ensure_smem(categorize_kernel<true>, sizeof(CatSmem))) return -1;
+    configured = true;
+  }
+  const int groups = raw ? (n + 15) / 16 : n;
+  int grid = num_sms();
+  if (grid > groups) grid = groups;
+  if (grid < 1) grid = 1;
+  if (raw) categorize_kernel<true><<<grid, kCThreads, sizeof(CatSmem), s>>>(wts, nullptr, nullptr, raw, n, raw_out);
+  else categorize_kernel<false><<<grid, kCThreads, sizeof(CatSmem), s>>>(wts, cards, scans, nullptr, n, nullptr);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int launch_categorize_patches(const NetWeights &wts, const uint8_t *patches, int n, float *out, cudaStream_t s) {
+  return launch_categorize(wts, nullptr, nullptr, patches, n, out, s);
+}
+
+// scan_card_image for a batch: gate -> vseg (coarse, select, fine, select) -> hseg -> categorize -> finish.
+// vprob doubles as scratch: its tail holds the per-frame gate bytes.
+int launch_scan(const NetWeights &wts, const uint8_t *cards, int n, const FrameGeom *geom, const uint8_t *valid,
+                float *vprob, b200_scan *scans, cudaStream_t s) {
+  int launches = 0, rc;
+  uint8_t *gate = reinterpret_cast<uint8_t *>(vprob + (size_t)n * 540);
+#define STEP(call)          \
+  rc = (call);              \
+  if (rc < 0) return -1;    \
+  launches += rc;
+  STEP(launch_scan_gate(geom, valid, n, gate, s));
+  if (cudaMemsetAsync(vprob, 0, (size_t)n * 540 * sizeof(float), s) != cudaSuccess) return -1;
+  STEP(launch_vseg_rows(wts, cards, gate, scans, n, 0, vprob, nullptr, nullptr, s));
+  STEP(launch_vseg_select(vprob, gate, n, 0, scans, s));
+  STEP(launch_vseg_rows(wts, cards, gate, scans, n, 1, vprob, nullptr, nullptr, s));
+  STEP(launch_vseg_select(vprob, gate, n, 1, scans, s));
+  STEP(launch_hseg(cards, n, scans, s));
+  STEP(launch_categorize(wts, cards, scans, nullptr, n, nullptr, s));
+  STEP(launch_scan_finish(n, scans, s));
+#undef STEP
+  return launches;
+}

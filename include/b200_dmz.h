@@ -1,0 +1,173 @@
+/*
+ * include/b200_dmz.h -- C ABI of the B200-native card.io-dmz hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch/OpenCV types.  The reference's
+ * C++ entry points (dmz.h / scan/scan.h) are re-exported with their original signatures by the thin
+ * C++ layer in include/dmz_b200_compat.h + card.io-dmz_b200/csrc/dmz_compat.cpp, which forwards here
+ * with a batch of one.  Throughput callers use the *_batch functions directly.
+ *
+ * Every image argument is a dense-or-strided 8-bit single-channel plane.  `mem` says where the
+ * caller's buffers (inputs AND outputs) live: B200_MEM_HOST (copies to/from the device are done
+ * inside the call on the context's stream) or B200_MEM_DEVICE (pointers are device pointers on the
+ * context's device; no copies, the call returns after enqueueing and synchronising the stream).
+ *
+ * All functions return 0 on success, a negative B200_E* code on failure (never throw, never abort);
+ * b200_last_error() gives the text.  A context is thread-compatible (one thread at a time), like the
+ * reference (SURVEY 8b "Threading").
+ */
+#ifndef B200_DMZ_H
+#define B200_DMZ_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_MEM_HOST 0
+#define B200_MEM_DEVICE 1
+
+#define B200_OK 0
+#define B200_EINVAL (-1)   /* bad argument */
+#define B200_ECUDA (-2)    /* CUDA runtime error (text in b200_last_error) */
+#define B200_ENOMEM (-3)
+#define B200_EUNSUPPORTED (-4)
+
+/* FrameOrientation, dmz_olm.h:16-22 */
+#define B200_ORIENT_PORTRAIT 1
+#define B200_ORIENT_PORTRAIT_UPSIDE_DOWN 2
+#define B200_ORIENT_LANDSCAPE_RIGHT 3
+#define B200_ORIENT_LANDSCAPE_LEFT 4
+
+#define B200_CARD_W 428 /* kCreditCardTargetWidth,  dmz_constants.h:7 */
+#define B200_CARD_H 270 /* kCreditCardTargetHeight, dmz_constants.h:8 */
+
+typedef struct b200_ctx b200_ctx;
+
+/* == dmz_found_edge / dmz_edges, dmz.h:22-37 (member order top, left, bottom, right) */
+typedef struct {
+  int32_t found;
+  float rho, theta;
+} b200_found_edge;
+typedef struct {
+  b200_found_edge top, left, bottom, right;
+} b200_edges;
+
+/* == dmz_corner_points, dmz_olm.h:37-42 */
+typedef struct {
+  float top_left[2], bottom_left[2], top_right[2], bottom_right[2];
+} b200_corner_points;
+
+/* == NVerticalSegmentation, scan/n_vseg.h:14-21 */
+typedef struct {
+  float score;
+  uint16_t y_offset;
+  uint8_t pattern_type;
+  uint8_t number_pattern[19];
+  uint8_t number_pattern_length;
+  uint8_t number_length;
+} b200_vseg;
+
+/* == NHorizontalSegmentation, scan/n_hseg.h:13-19 */
+typedef struct {
+  uint8_t n_offsets;
+  uint16_t offsets[16];
+  float score;
+  float number_width;
+  uint16_t pattern_offset;
+} b200_hseg;
+
+/* What scan_card_image (scan/frame.cpp:24-81) leaves in a FrameScanResult. */
+typedef struct {
+  float scores[160]; /* NumberScores: 16 x 10 row-major, rows >= hseg.n_offsets are 0 */
+  b200_hseg hseg;
+  b200_vseg vseg;
+  uint8_t usable;
+  uint8_t upside_down;
+  uint8_t pad[2];
+} b200_scan;
+
+/* Per-strip integer taps of best_line_for_sample (dmz.cpp:224-271); used by the parity tests. */
+typedef struct {
+  int32_t found, r, n, max_votes, low, high, n_edge_px;
+  float rho, theta; /* ROI-local; FLT_MAX when !found */
+} b200_line;
+
+/* Per-frame record of the whole path. */
+typedef struct {
+  int32_t found[4]; /* top, left, bottom, right */
+  float rho[4];     /* full-frame (rho, theta) per edge; unspecified where !found */
+  float theta[4];
+  float corners[8]; /* tl, bl, tr, br (x,y) */
+  int32_t all_found;
+  b200_scan scan;      /* valid iff all_found */
+  uint32_t card_check; /* sum_i (i+1)*card[i] mod 2^32 over the 428x270 card; 0 if !all_found */
+} b200_frame_record;
+
+/* ---- life cycle (replaces dmz_context_create / destroy + mz_create, dmz.h:45-51, mz.h:19-25) ---- */
+
+/* weights_dir: directory with the model blobs (card.io-dmz_b200/weights); NULL = $B200_DMZ_WEIGHTS or
+ * the directory next to the shared library. */
+int b200_ctx_create(b200_ctx **ctx, int device_ordinal, const char *weights_dir);
+void b200_ctx_destroy(b200_ctx *ctx);
+const char *b200_last_error(const b200_ctx *ctx);
+/* Optional: pre-size device scratch for batches of up to max_frames frames of width x height. */
+int b200_ctx_reserve(b200_ctx *ctx, int max_frames, int width, int height);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+uint64_t b200_launch_count(const b200_ctx *ctx);
+/* The CUDA stream (cudaStream_t) all work of this context is enqueued on. */
+void *b200_ctx_stream(const b200_ctx *ctx);
+
+/* ---- dmz_detect_edges (dmz.h:86-87, dmz.cpp:371-439), batched ----
+ * y: n planes width x height; cb, cr: n planes (width/2) x (height/2), or both NULL (then only the Y
+ * plane is searched; with real chroma the reference falls back Y -> Cb -> Cr per edge, dmz.cpp:351-367).
+ * edges / corners / all_found: n entries each; lines (optional, may be NULL): 4*n Y-plane strip taps in
+ * detection order top, bottom, left, right. */
+int b200_detect_edges_batch(b200_ctx *ctx, const uint8_t *y, int y_row_stride, size_t y_frame_stride,
+                            const uint8_t *cb, const uint8_t *cr, int c_row_stride, size_t c_frame_stride,
+                            int width, int height, int n, int orientation, int mem,
+                            b200_edges *edges, b200_corner_points *corners, uint8_t *all_found, b200_line *lines);
+
+/* ---- dmz_transform_card (dmz.h:96, dmz.cpp:443-497), batched ----
+ * valid (optional): frames with valid[i] == 0 are skipped (their card is zero-filled).
+ * cards: n dense 428 x 270 planes. */
+int b200_transform_card_batch(b200_ctx *ctx, const uint8_t *sample, int row_stride, size_t frame_stride, int width,
+                              int height, int n, const b200_corner_points *corners, const uint8_t *valid,
+                              int orientation, int upsample, int mem, uint8_t *cards);
+
+/* ---- scan_card_image (scan/frame.cpp:24; the arithmetic inside scanner_add_frame_*), batched ----
+ * cards: n dense 428 x 270 planes.  scans: n entries. */
+int b200_scan_cards_batch(b200_ctx *ctx, const uint8_t *cards, int n, const uint8_t *valid, int mem, b200_scan *scans);
+
+/* ---- whole path, intermediates stay in HBM: detect -> transform -> scan ----
+ * records: n entries.  cards_out (optional): n dense 428 x 270 planes. */
+int b200_process_frames_batch(b200_ctx *ctx, const uint8_t *y, int y_row_stride, size_t y_frame_stride, int width,
+                              int height, int n, int orientation, int mem, b200_frame_record *records,
+                              uint8_t *cards_out);
+
+/* ---- stage taps for the parity tests (device work, host-visible results; mem as above) ---- */
+/* llcv_calc_persp_transform (cv/warp.cpp:34): pts = n x 8 floats (x0,y0..x3,y3) src and dst; M = n x 9. */
+int b200_calc_persp_transform_batch(b200_ctx *ctx, const float *src_pts, const float *dst_pts, int n, float *M);
+/* scores_for_number_image + patch prep (scan/n_categorize.cpp:45-108): patches = n x 27 x 19 u8 taken from a
+ * card; out = n x 40 floats (10 ensemble scores + 3 x 10 model probabilities). */
+int b200_categorize_patches_batch(b200_ctx *ctx, const uint8_t *patches, int n, int mem, float *out);
+/* applym_befe75da on prepared rows: in = n x 204 f32, out = n x 3 f32 */
+int b200_vseg_model_batch(b200_ctx *ctx, const float *rows, int n, int mem, float *out);
+
+/* ---- scanner session (scan/scan.h:50-72): host-side aggregation, no GPU work ---- */
+typedef struct b200_scanner b200_scanner;
+b200_scanner *b200_scanner_new(void);
+void b200_scanner_free(b200_scanner *s);
+void b200_scanner_reset(b200_scanner *s);
+/* scanner_add_frame's bookkeeping given the frame's scan result (scan.cpp:41-86). */
+void b200_scanner_add_scan(b200_scanner *s, const b200_scan *scan);
+/* scanner_result (scan.cpp:88-194): returns complete; digits[16], *n_numbers filled when complete
+ * (and, as in the reference, with the current best guess while checks are still failing). */
+int b200_scanner_result(b200_scanner *s, uint8_t digits[16], int32_t *n_numbers);
+void b200_scanner_peek(const b200_scanner *s, float agg15[160], float agg16[160], int32_t counts[2]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -45,7 +45,7 @@ class Scan(C.Structure):
 
 
 class FrameRecord(C.Structure):
-    _fields_ = [("detect", Detect), ("scan", Scan), ("card_crc", C.c_uint32)]
+    _fields_ = [("detect", Detect), ("scan", Scan), ("card_check", C.c_uint32)]
 
 
 assert C.sizeof(VSeg) == 28 and C.sizeof(HSeg) == 48 and C.sizeof(Scan) == 720, (
@@ -59,7 +59,7 @@ RECORD_DTYPE = np.dtype([
     ("v_score", "<f4"), ("v_y_offset", "<u2"), ("v_pattern_type", "u1"), ("v_number_pattern", "u1", 19),
     ("v_number_pattern_length", "u1"), ("v_number_length", "u1"),
     ("usable", "u1"), ("upside_down", "u1"), ("_p4", "u1", 2),
-    ("card_crc", "<u4"),
+    ("card_check", "<u4"),
 ])
 assert RECORD_DTYPE.itemsize == C.sizeof(FrameRecord), (RECORD_DTYPE.itemsize, C.sizeof(FrameRecord))
 
@@ -121,8 +121,8 @@ class Oracle:
             self.lib.ref_sizeof.argtypes = [i]
         else:
             self.lib.orc_scanner_add_scan.argtypes = [vp, C.POINTER(Scan)]
-            self.lib.orc_crc32.argtypes = [vp, C.c_size_t]
-            self.lib.orc_crc32.restype = C.c_uint32
+            self.lib.orc_card_check.argtypes = [vp, C.c_size_t]
+            self.lib.orc_card_check.restype = C.c_uint32
 
     def _f(self, name, argtypes, restype=None):
         fn = getattr(self.lib, self.prefix + name)

@@ -832,23 +832,11 @@ void orc_scan_card_image(const uint8_t *card, orc_scan *out) {
   out->usable = number_score < 3;
 }
 
-uint32_t orc_crc32(const uint8_t *p, size_t n) {
-  static uint32_t table[256];
-  static int ready = 0;
-  uint32_t c = 0xFFFFFFFFu;
+uint32_t orc_card_check(const uint8_t *p, size_t n) {
+  uint32_t c = 0;
   size_t i;
-  if (!ready) {
-    uint32_t t;
-    int k;
-    for (t = 0; t < 256; t++) {
-      uint32_t v = t;
-      for (k = 0; k < 8; k++) v = (v & 1) ? 0xEDB88320u ^ (v >> 1) : v >> 1;
-      table[t] = v;
-    }
-    ready = 1;
-  }
-  for (i = 0; i < n; i++) c = table[(c ^ p[i]) & 255] ^ (c >> 8);
-  return c ^ 0xFFFFFFFFu;
+  for (i = 0; i < n; i++) c += (uint32_t)(i + 1) * p[i];
+  return c;
 }
 
 void orc_process_frame(const uint8_t *y, int w, int h, int ystep, const uint8_t *cb, const uint8_t *cr, int cstep,
@@ -858,7 +846,7 @@ void orc_process_frame(const uint8_t *y, int w, int h, int ystep, const uint8_t 
   if (!orc_detect_edges(y, w, h, ystep, cb, cr, cstep, orientation, &rec->detect)) return;
   card = card_out ? card_out : (uint8_t *)malloc(kCardW * kCardH);
   orc_transform_card(y, w, h, ystep, rec->detect.corners, orientation, card);
-  rec->card_crc = orc_crc32(card, kCardW * kCardH);
+  rec->card_check = orc_card_check(card, kCardW * kCardH);
   orc_scan_card_image(card, &rec->scan);
   if (!card_out) free(card);
 }

@@ -58,7 +58,7 @@ int orc_scanner_result(void *state, uint8_t digits[16], int32_t *n_numbers);
 int orc_luhn(const uint8_t *digits, int n);
 int orc_card_type(const uint8_t *digits, int n);
 
-uint32_t orc_crc32(const uint8_t *p, size_t n);
+uint32_t orc_card_check(const uint8_t *p, size_t n);
 
 /* multi-threaded timing of the whole path (bench.py cpu_baseline kind "port"); returns wall seconds */
 double orc_bench_frames(const uint8_t *frames, int n, int w, int h, const uint8_t *cb, const uint8_t *cr,

@@ -68,7 +68,7 @@ typedef struct {
 typedef struct {
   orc_detect detect;
   orc_scan scan;      /* valid iff detect.all_found */
-  uint32_t card_crc;  /* CRC-32 (IEEE) of the 428x270 card image, 0 if not detected */
+  uint32_t card_check; /* sum_i (i+1)*card[i] mod 2^32 over the 428x270 card image, 0 if not detected */
 } orc_frame_record;
 
 #ifdef __cplusplus

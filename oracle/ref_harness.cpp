@@ -45,20 +45,10 @@ void wrap(Hdr *h, const void *data, int w, int hgt, int step, int depth) {
   h->img.align = 4;
 }
 
-uint32_t crc32_ieee(const uint8_t *p, size_t n) {
-  static uint32_t table[256];
-  static int ready = 0;
-  if (!ready) {
-    for (uint32_t i = 0; i < 256; i++) {
-      uint32_t c = i;
-      for (int k = 0; k < 8; k++) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
-      table[i] = c;
-    }
-    ready = 1;
-  }
-  uint32_t c = 0xFFFFFFFFu;
-  for (size_t i = 0; i < n; i++) c = table[(c ^ p[i]) & 255] ^ (c >> 8);
-  return c ^ 0xFFFFFFFFu;
+uint32_t card_checksum(const uint8_t *p, size_t n) {
+  uint32_t c = 0;
+  for (size_t i = 0; i < n; i++) c += (uint32_t)(i + 1) * p[i];
+  return c;
 }
 
 void flatten_scan(const FrameScanResult &r, orc_scan *out) {
@@ -331,7 +321,7 @@ void ref_process_frame(const uint8_t *y, int w, int h, int ystep, const uint8_t 
   if (!ref_detect_edges(y, w, h, ystep, cb, cr, cstep, orientation, &rec->detect)) return;
   uint8_t *card = card_out ? card_out : (uint8_t *)malloc(428 * 270);
   ref_transform_card(y, w, h, ystep, rec->detect.corners, orientation, card);
-  rec->card_crc = crc32_ieee(card, 428 * 270);
+  rec->card_check = card_checksum(card, 428 * 270);
   ref_scan_card_image(card, &rec->scan);
   if (!card_out) free(card);
 }
