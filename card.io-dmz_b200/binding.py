@@ -104,6 +104,9 @@ def _load():
     lib.b200_calc_persp_transform_batch.argtypes = [vp, vp, vp, i, vp]
     lib.b200_categorize_patches_batch.argtypes = [vp, vp, i, i, vp]
     lib.b200_vseg_model_batch.argtypes = [vp, vp, i, i, vp]
+    lib.b200_digit_models_batch.argtypes = [vp, vp, i, i, vp]
+    lib.b200_set_profiling.argtypes = [vp, i]
+    lib.b200_stage_times.argtypes = [vp, vp, C.POINTER(C.c_uint64)]
     lib.b200_scanner_new.restype = vp
     lib.b200_scanner_free.argtypes = [vp]
     lib.b200_scanner_reset.argtypes = [vp]
@@ -227,6 +230,26 @@ class Dmz:
         out = np.zeros((n, 40), np.float32)
         self._check(self.lib.b200_categorize_patches_batch(self.ctx, _ptr(patches), n, MEM_HOST, _ptr(out)))
         return out[:, :10].copy(), out[:, 10:].reshape(n, 3, 10).copy()
+
+    def digit_models(self, patches):
+        """patches: (n, 27, 19) float32, already prepared.  Returns (ensemble (n,10), per-model probs (n,3,10))."""
+        patches = np.ascontiguousarray(patches, np.float32).reshape(-1, 27 * 19)
+        n = patches.shape[0]
+        out = np.zeros((n, 40), np.float32)
+        self._check(self.lib.b200_digit_models_batch(self.ctx, _ptr(patches), n, MEM_HOST, _ptr(out)))
+        return out[:, :10].copy(), out[:, 10:].reshape(n, 3, 10).copy()
+
+    STAGES = ("detect", "geometry", "warp", "vseg", "hseg", "categorize", "finalize")
+
+    def set_profiling(self, on=True):
+        self.lib.b200_set_profiling(self.ctx, int(on))
+
+    def stage_times(self):
+        """{stage: accumulated ms}, frames covered (device-pointer process_frames calls while profiling)."""
+        ms = np.zeros(7, np.float64)
+        frames = C.c_uint64()
+        self._check(self.lib.b200_stage_times(self.ctx, _ptr(ms), C.byref(frames)))
+        return dict(zip(self.STAGES, ms.tolist())), int(frames.value)
 
     def vseg_model(self, rows):
         rows = np.ascontiguousarray(rows, np.float32).reshape(-1, 204)

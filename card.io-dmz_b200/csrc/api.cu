@@ -17,11 +17,36 @@ constexpr int kDetectThreads = 416;  // must match detect.cu
 constexpr size_t kCardBytes = (size_t)B200_CARD_W * B200_CARD_H;
 }  // namespace
 
+// Device scratch of one in-flight batch.  A context owns two lanes so that the host-buffer path can overlap
+// the H2D copy of chunk k+1 with the kernels of chunk k (separate streams).
+struct Lane {
+  cudaStream_t stream = nullptr;
+  int cap = 0, cap_w = 0, cap_h = 0;
+  uint8_t *d_frames = nullptr, *d_cb = nullptr, *d_cr = nullptr;
+  b200_line *d_lines = nullptr;  // 3 * cap * 4
+  FrameGeom *d_geom = nullptr;
+  uint8_t *d_cards = nullptr;
+  float *d_vprob = nullptr;
+  b200_scan *d_scan = nullptr;
+  b200_frame_record *d_records = nullptr;
+  int16_t *d_grad = nullptr;
+  size_t grad_elems = 0;
+};
+
+enum { ST_DETECT = 0, ST_GEOMETRY, ST_WARP, ST_VSEG, ST_HSEG, ST_CATEGORIZE, ST_FINALIZE, ST_COUNT };
+
 struct b200_ctx {
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;  // == lane[0].stream
   std::string error;
   uint64_t launches = 0;
+  Lane lane[2];
+  int host_chunk = 2048;  // frames per pipelined chunk on the host-buffer path
+  // per-stage device time (CUDA events on the lane stream), accumulated while profiling is on
+  int profiling = 0;
+  double stage_ms[ST_COUNT] = {0};
+  uint64_t stage_frames = 0;
+  cudaEvent_t ev[ST_COUNT + 1] = {nullptr};
 
   // weights
   float *d_vseg = nullptr;
@@ -34,17 +59,6 @@ struct b200_ctx {
   DetectParams dp[2];  // Y, chroma
   GeomParams gp;
 
-  // device scratch, sized for `cap` frames of cap_w x cap_h
-  int cap = 0, cap_w = 0, cap_h = 0;
-  uint8_t *d_frames = nullptr, *d_cb = nullptr, *d_cr = nullptr;
-  b200_line *d_lines = nullptr;  // 3 * cap * 4
-  FrameGeom *d_geom = nullptr;
-  uint8_t *d_cards = nullptr;
-  float *d_vprob = nullptr;
-  b200_scan *d_scan = nullptr;
-  b200_frame_record *d_records = nullptr;
-  int16_t *d_grad = nullptr;
-  size_t grad_elems = 0;
   // small staging buffers for host-mode outputs
   void *d_misc = nullptr;
   size_t misc_bytes = 0;
@@ -99,14 +113,14 @@ std::string default_weights_dir() {
   return "weights";
 }
 
-void free_scratch(b200_ctx *c) {
-  cudaFree(c->d_frames), cudaFree(c->d_cb), cudaFree(c->d_cr), cudaFree(c->d_lines), cudaFree(c->d_geom);
-  cudaFree(c->d_cards), cudaFree(c->d_vprob), cudaFree(c->d_scan), cudaFree(c->d_records), cudaFree(c->d_grad);
-  c->d_frames = c->d_cb = c->d_cr = nullptr;
-  c->d_lines = nullptr, c->d_geom = nullptr, c->d_cards = nullptr, c->d_vprob = nullptr, c->d_scan = nullptr;
-  c->d_records = nullptr, c->d_grad = nullptr;
-  c->grad_elems = 0;
-  c->cap = 0;
+void free_lane(Lane *l) {
+  cudaFree(l->d_frames), cudaFree(l->d_cb), cudaFree(l->d_cr), cudaFree(l->d_lines), cudaFree(l->d_geom);
+  cudaFree(l->d_cards), cudaFree(l->d_vprob), cudaFree(l->d_scan), cudaFree(l->d_records), cudaFree(l->d_grad);
+  l->d_frames = l->d_cb = l->d_cr = nullptr;
+  l->d_lines = nullptr, l->d_geom = nullptr, l->d_cards = nullptr, l->d_vprob = nullptr, l->d_scan = nullptr;
+  l->d_records = nullptr, l->d_grad = nullptr;
+  l->grad_elems = 0;
+  l->cap = 0;
 }
 
 int ensure_config(b200_ctx *ctx, int w, int h, int orientation, int planes) {
@@ -131,29 +145,29 @@ int ensure_config(b200_ctx *ctx, int w, int h, int orientation, int planes) {
   return B200_OK;
 }
 
-int ensure_capacity(b200_ctx *ctx, int n, int w, int h, bool need_frames) {
-  if (n <= ctx->cap && w * h <= ctx->cap_w * ctx->cap_h && (!need_frames || ctx->d_frames)) return B200_OK;
-  int cap = n > ctx->cap ? n : ctx->cap;
+int ensure_capacity(b200_ctx *ctx, Lane *l, int n, int w, int h, bool need_frames) {
+  if (n <= l->cap && (size_t)w * h <= (size_t)l->cap_w * l->cap_h && (!need_frames || l->d_frames)) return B200_OK;
+  int cap = n > l->cap ? n : l->cap;
   int cw = w, chh = h;
-  if ((size_t)ctx->cap_w * ctx->cap_h > (size_t)w * h) cw = ctx->cap_w, chh = ctx->cap_h;
-  bool had_frames = ctx->d_frames != nullptr;
-  free_scratch(ctx);
+  if ((size_t)l->cap_w * l->cap_h > (size_t)w * h) cw = l->cap_w, chh = l->cap_h;
+  bool had_frames = l->d_frames != nullptr;
+  free_lane(l);
   if (need_frames || had_frames) {
-    CU(cudaMalloc(&ctx->d_frames, (size_t)cap * cw * chh));
-    CU(cudaMalloc(&ctx->d_cb, (size_t)cap * (cw / 2) * (chh / 2)));
-    CU(cudaMalloc(&ctx->d_cr, (size_t)cap * (cw / 2) * (chh / 2)));
+    CU(cudaMalloc(&l->d_frames, (size_t)cap * cw * chh));
+    CU(cudaMalloc(&l->d_cb, (size_t)cap * (cw / 2) * (chh / 2)));
+    CU(cudaMalloc(&l->d_cr, (size_t)cap * (cw / 2) * (chh / 2)));
   }
-  CU(cudaMalloc(&ctx->d_lines, sizeof(b200_line) * 3 * (size_t)cap * 4));
-  CU(cudaMalloc(&ctx->d_geom, sizeof(FrameGeom) * (size_t)cap));
-  CU(cudaMalloc(&ctx->d_cards, kCardBytes * (size_t)cap));
-  CU(cudaMalloc(&ctx->d_vprob, (size_t)cap * (540 * sizeof(float) + 16)));
-  CU(cudaMalloc(&ctx->d_scan, sizeof(b200_scan) * (size_t)cap));
-  CU(cudaMalloc(&ctx->d_records, sizeof(b200_frame_record) * (size_t)cap));
-  ctx->cap = cap, ctx->cap_w = cw, ctx->cap_h = chh;
+  CU(cudaMalloc(&l->d_lines, sizeof(b200_line) * 3 * (size_t)cap * 4));
+  CU(cudaMalloc(&l->d_geom, sizeof(FrameGeom) * (size_t)cap));
+  CU(cudaMalloc(&l->d_cards, kCardBytes * (size_t)cap));
+  CU(cudaMalloc(&l->d_vprob, (size_t)cap * (540 * sizeof(float) + 16)));
+  CU(cudaMalloc(&l->d_scan, sizeof(b200_scan) * (size_t)cap));
+  CU(cudaMalloc(&l->d_records, sizeof(b200_frame_record) * (size_t)cap));
+  l->cap = cap, l->cap_w = cw, l->cap_h = chh;
   return B200_OK;
 }
 
-int ensure_grad(b200_ctx *ctx, int n) {
+int ensure_grad(b200_ctx *ctx, Lane *l, int n) {
   size_t need = 0;
   for (int p = 0; p < 2; p++) {
     if (!ctx->dp[p].use_global_grad) continue;
@@ -165,12 +179,12 @@ int ensure_grad(b200_ctx *ctx, int n) {
     size_t e = (size_t)n * 4 * mx * 2;
     need = e > need ? e : need;
   }
-  if (need > ctx->grad_elems) {
-    cudaFree(ctx->d_grad);
-    ctx->d_grad = nullptr;
-    ctx->grad_elems = 0;
-    CU(cudaMalloc(&ctx->d_grad, need * sizeof(int16_t)));
-    ctx->grad_elems = need;
+  if (need > l->grad_elems) {
+    cudaFree(l->d_grad);
+    l->d_grad = nullptr;
+    l->grad_elems = 0;
+    CU(cudaMalloc(&l->d_grad, need * sizeof(int16_t)));
+    l->grad_elems = need;
   }
   return B200_OK;
 }
@@ -185,38 +199,66 @@ int ensure_misc(b200_ctx *ctx, size_t bytes) {
 }
 
 // Copy n strided host planes into a dense device buffer (or hand back the caller's device pointer).
-int stage_planes(b200_ctx *ctx, const uint8_t *src, int row_stride, size_t frame_stride, int w, int h, int n, int mem,
-                 uint8_t *d_dense, const uint8_t **out_ptr, int *out_row_stride, size_t *out_frame_stride) {
+int stage_planes(b200_ctx *ctx, cudaStream_t stream, const uint8_t *src, int row_stride, size_t frame_stride, int w, int h,
+                 int n, int mem, uint8_t *d_dense, const uint8_t **out_ptr, int *out_row_stride, size_t *out_frame_stride) {
   if (mem == B200_MEM_DEVICE) {
     *out_ptr = src, *out_row_stride = row_stride, *out_frame_stride = frame_stride;
     return B200_OK;
   }
   if (row_stride == w && frame_stride == (size_t)w * h) {
-    CU(cudaMemcpyAsync(d_dense, src, (size_t)n * w * h, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d_dense, src, (size_t)n * w * h, cudaMemcpyHostToDevice, stream));
   } else if (frame_stride == (size_t)row_stride * h) {
-    CU(cudaMemcpy2DAsync(d_dense, w, src, row_stride, w, (size_t)h * n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpy2DAsync(d_dense, w, src, row_stride, w, (size_t)h * n, cudaMemcpyHostToDevice, stream));
   } else {
     for (int i = 0; i < n; i++)
       CU(cudaMemcpy2DAsync(d_dense + (size_t)i * w * h, w, src + (size_t)i * frame_stride, row_stride, w, h,
-                           cudaMemcpyHostToDevice, ctx->stream));
+                           cudaMemcpyHostToDevice, stream));
   }
   *out_ptr = d_dense, *out_row_stride = w, *out_frame_stride = (size_t)w * h;
   return B200_OK;
 }
 
-int detect_sequence(b200_ctx *ctx, const uint8_t *y, int yrs, size_t yfs, const uint8_t *cb, const uint8_t *cr, int crs,
-                    size_t cfs, int n) {
-  const size_t plane_stride = (size_t)ctx->cap * 4;
-  int rc = ensure_grad(ctx, n);
+int detect_sequence(b200_ctx *ctx, Lane *l, const uint8_t *y, int yrs, size_t yfs, const uint8_t *cb, const uint8_t *cr,
+                    int crs, size_t cfs, int n, bool timed) {
+  const size_t plane_stride = (size_t)l->cap * 4;
+  int rc = ensure_grad(ctx, l, n);
   if (rc) return rc;
-  LAUNCH(launch_detect(ctx->dp[0], y, yrs, yfs, n, nullptr, nullptr, ctx->d_lines, ctx->d_grad, ctx->stream));
+  if (timed) CU(cudaEventRecord(ctx->ev[ST_DETECT], l->stream));
+  LAUNCH(launch_detect(ctx->dp[0], y, yrs, yfs, n, nullptr, nullptr, l->d_lines, l->d_grad, l->stream));
   if (cb && cr) {
     // Cb is searched only where Y produced no line, Cr only where neither Y nor Cb did (dmz.cpp:351)
-    LAUNCH(launch_detect(ctx->dp[1], cb, crs, cfs, n, ctx->d_lines, nullptr, ctx->d_lines + plane_stride, ctx->d_grad, ctx->stream));
-    LAUNCH(launch_detect(ctx->dp[1], cr, crs, cfs, n, ctx->d_lines, ctx->d_lines + plane_stride, ctx->d_lines + 2 * plane_stride,
-                         ctx->d_grad, ctx->stream));
+    LAUNCH(launch_detect(ctx->dp[1], cb, crs, cfs, n, l->d_lines, nullptr, l->d_lines + plane_stride, l->d_grad, l->stream));
+    LAUNCH(launch_detect(ctx->dp[1], cr, crs, cfs, n, l->d_lines, l->d_lines + plane_stride, l->d_lines + 2 * plane_stride,
+                         l->d_grad, l->stream));
   }
-  LAUNCH(launch_geometry(ctx->gp, ctx->d_lines, plane_stride, n, ctx->d_geom, ctx->stream));
+  if (timed) CU(cudaEventRecord(ctx->ev[ST_GEOMETRY], l->stream));
+  LAUNCH(launch_geometry(ctx->gp, l->d_lines, plane_stride, n, l->d_geom, l->stream));
+  return B200_OK;
+}
+
+// detect -> warp -> scan -> records for n frames already visible to the device on lane l.
+int pipeline_on_lane(b200_ctx *ctx, Lane *l, const uint8_t *dy, int drs, size_t dfs, int width, int height, int n,
+                     uint8_t *dcards, b200_frame_record *drec, bool timed) {
+  int rc = detect_sequence(ctx, l, dy, drs, dfs, nullptr, nullptr, 0, 0, n, timed);
+  if (rc) return rc;
+  if (timed) CU(cudaEventRecord(ctx->ev[ST_WARP], l->stream));
+  LAUNCH(launch_warp(dy, drs, dfs, width, height, n, l->d_geom, dcards, l->stream));
+  cudaEvent_t *ev = timed ? ctx->ev : nullptr;
+  LAUNCH(launch_scan(ctx->wts, dcards, n, l->d_geom, nullptr, l->d_vprob, l->d_scan, l->stream,
+                     ev ? ev[ST_VSEG] : nullptr, ev ? ev[ST_HSEG] : nullptr, ev ? ev[ST_CATEGORIZE] : nullptr,
+                     ev ? ev[ST_FINALIZE] : nullptr));
+  LAUNCH(launch_finalize_records(l->d_geom, l->d_scan, dcards, n, drec, l->stream));
+  if (timed) CU(cudaEventRecord(ctx->ev[ST_COUNT], l->stream));
+  return B200_OK;
+}
+
+int collect_stage_times(b200_ctx *ctx, int n) {
+  for (int s = 0; s < ST_COUNT; s++) {
+    float ms = 0.0f;
+    CU(cudaEventElapsedTime(&ms, ctx->ev[s], ctx->ev[s + 1]));
+    ctx->stage_ms[s] += ms;
+  }
+  ctx->stage_frames += (uint64_t)n;
   return B200_OK;
 }
 
@@ -235,7 +277,11 @@ int b200_ctx_create(b200_ctx **out, int device_ordinal, const char *weights_dir)
   if (e != cudaSuccess || count == 0)
     return fail(ctx, B200_ECUDA, "no CUDA device available (%s); this library has no CPU fallback", cudaGetErrorString(e));
   CU(cudaSetDevice(device_ordinal));
-  CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; i++) CU(cudaStreamCreateWithFlags(&ctx->lane[i].stream, cudaStreamNonBlocking));
+  ctx->stream = ctx->lane[0].stream;
+  for (int i = 0; i <= ST_COUNT; i++) CU(cudaEventCreate(&ctx->ev[i]));
+  const char *chunk_env = getenv("B200_DMZ_HOST_CHUNK");
+  if (chunk_env && atoi(chunk_env) > 0) ctx->host_chunk = atoi(chunk_env);
 
   const std::string dir = weights_dir && *weights_dir ? weights_dir : default_weights_dir();
   std::vector<float> blob;
@@ -264,13 +310,17 @@ int b200_ctx_create(b200_ctx **out, int device_ordinal, const char *weights_dir)
 
 void b200_ctx_destroy(b200_ctx *ctx) {
   if (!ctx) return;
-  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  free_scratch(ctx);
+  for (int i = 0; i < 2; i++) {
+    if (ctx->lane[i].stream) cudaStreamSynchronize(ctx->lane[i].stream);
+    free_lane(&ctx->lane[i]);
+    if (ctx->lane[i].stream) cudaStreamDestroy(ctx->lane[i].stream);
+  }
+  for (int i = 0; i <= ST_COUNT; i++)
+    if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   cudaFree(ctx->d_misc);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   cudaFree(ctx->d_vseg), cudaFree(ctx->d_hwT);
   for (int m = 0; m < 3; m++) cudaFree(ctx->d_cnn[m]);
-  if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
 
@@ -281,7 +331,21 @@ void *b200_ctx_stream(const b200_ctx *ctx) { return ctx ? (void *)ctx->stream : 
 int b200_ctx_reserve(b200_ctx *ctx, int max_frames, int width, int height) {
   if (!ctx || max_frames < 1) return B200_EINVAL;
   CU(cudaSetDevice(ctx->device));
-  return ensure_capacity(ctx, max_frames, width, height, true);
+  return ensure_capacity(ctx, &ctx->lane[0], max_frames, width, height, false);
+}
+
+void b200_set_profiling(b200_ctx *ctx, int on) {
+  if (!ctx) return;
+  ctx->profiling = on;
+  for (int s = 0; s < ST_COUNT; s++) ctx->stage_ms[s] = 0.0;
+  ctx->stage_frames = 0;
+}
+
+int b200_stage_times(const b200_ctx *ctx, double ms[7], uint64_t *frames) {
+  if (!ctx) return B200_EINVAL;
+  for (int s = 0; s < ST_COUNT; s++) ms[s] = ctx->stage_ms[s];
+  if (frames) *frames = ctx->stage_frames;
+  return B200_OK;
 }
 
 int b200_detect_edges_batch(b200_ctx *ctx, const uint8_t *y, int yrs, size_t yfs, const uint8_t *cb, const uint8_t *cr,
@@ -289,32 +353,33 @@ int b200_detect_edges_batch(b200_ctx *ctx, const uint8_t *y, int yrs, size_t yfs
                             b200_corner_points *corners, uint8_t *all_found, b200_line *lines) {
   if (!ctx || !y || n < 1 || (!cb) != (!cr)) return fail(ctx, B200_EINVAL, "b200_detect_edges_batch: bad arguments");
   CU(cudaSetDevice(ctx->device));
+  Lane *l = &ctx->lane[0];
   int rc = ensure_config(ctx, width, height, orientation, cb ? 3 : 1);
   if (rc) return rc;
-  rc = ensure_capacity(ctx, n, width, height, mem == B200_MEM_HOST);
+  rc = ensure_capacity(ctx, l, n, width, height, mem == B200_MEM_HOST);
   if (rc) return rc;
   const uint8_t *dy, *dcb = nullptr, *dcr = nullptr;
   int drs, dcrs = 0;
   size_t dfs, dcfs = 0;
-  rc = stage_planes(ctx, y, yrs, yfs, width, height, n, mem, ctx->d_frames, &dy, &drs, &dfs);
+  rc = stage_planes(ctx, l->stream, y, yrs, yfs, width, height, n, mem, l->d_frames, &dy, &drs, &dfs);
   if (rc) return rc;
   if (cb) {
-    rc = stage_planes(ctx, cb, crs, cfs, width / 2, height / 2, n, mem, ctx->d_cb, &dcb, &dcrs, &dcfs);
+    rc = stage_planes(ctx, l->stream, cb, crs, cfs, width / 2, height / 2, n, mem, l->d_cb, &dcb, &dcrs, &dcfs);
     if (rc) return rc;
-    rc = stage_planes(ctx, cr, crs, cfs, width / 2, height / 2, n, mem, ctx->d_cr, &dcr, &dcrs, &dcfs);
+    rc = stage_planes(ctx, l->stream, cr, crs, cfs, width / 2, height / 2, n, mem, l->d_cr, &dcr, &dcrs, &dcfs);
     if (rc) return rc;
   }
-  rc = detect_sequence(ctx, dy, drs, dfs, dcb, dcr, dcrs, dcfs, n);
+  rc = detect_sequence(ctx, l, dy, drs, dfs, dcb, dcr, dcrs, dcfs, n, false);
   if (rc) return rc;
   // unpack FrameGeom into the caller's structs (host side; geometry records are small)
   std::vector<FrameGeom> hg(n);
-  CU(cudaMemcpyAsync(hg.data(), ctx->d_geom, sizeof(FrameGeom) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(hg.data(), l->d_geom, sizeof(FrameGeom) * n, cudaMemcpyDeviceToHost, l->stream));
   std::vector<b200_line> hl;
   if (lines) {
     hl.resize((size_t)n * 4);
-    CU(cudaMemcpyAsync(hl.data(), ctx->d_lines, sizeof(b200_line) * n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(hl.data(), l->d_lines, sizeof(b200_line) * n * 4, cudaMemcpyDeviceToHost, l->stream));
   }
-  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaStreamSynchronize(l->stream));
   std::vector<b200_edges> he(n);
   std::vector<b200_corner_points> hc(n);
   std::vector<uint8_t> hf(n);
@@ -337,54 +402,56 @@ int b200_transform_card_batch(b200_ctx *ctx, const uint8_t *sample, int row_stri
                               int upsample, int mem, uint8_t *cards) {
   if (!ctx || !sample || !corners || !cards || n < 1) return fail(ctx, B200_EINVAL, "b200_transform_card_batch: bad arguments");
   CU(cudaSetDevice(ctx->device));
-  int rc = ensure_capacity(ctx, n, width, height, mem == B200_MEM_HOST);
+  Lane *l = &ctx->lane[0];
+  int rc = ensure_capacity(ctx, l, n, width, height, mem == B200_MEM_HOST);
   if (rc) return rc;
   const uint8_t *ds;
   int drs;
   size_t dfs;
-  rc = stage_planes(ctx, sample, row_stride, frame_stride, width, height, n, mem, ctx->d_frames, &ds, &drs, &dfs);
+  rc = stage_planes(ctx, l->stream, sample, row_stride, frame_stride, width, height, n, mem, l->d_frames, &ds, &drs, &dfs);
   if (rc) return rc;
   const b200_corner_points *dc = corners;
   const uint8_t *dv = valid;
   if (mem == B200_MEM_HOST) {
     rc = ensure_misc(ctx, (sizeof(b200_corner_points) + 1) * (size_t)n);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(ctx->d_misc, corners, sizeof(b200_corner_points) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_misc, corners, sizeof(b200_corner_points) * n, cudaMemcpyHostToDevice, l->stream));
     dc = (const b200_corner_points *)ctx->d_misc;
     if (valid) {
       uint8_t *p = (uint8_t *)ctx->d_misc + sizeof(b200_corner_points) * (size_t)n;
-      CU(cudaMemcpyAsync(p, valid, n, cudaMemcpyHostToDevice, ctx->stream));
+      CU(cudaMemcpyAsync(p, valid, n, cudaMemcpyHostToDevice, l->stream));
       dv = p;
     }
   }
-  LAUNCH(launch_corners_to_geom(dc, dv, n, orientation, upsample, ctx->d_geom, ctx->stream));
-  uint8_t *dcards = mem == B200_MEM_DEVICE ? cards : ctx->d_cards;
-  LAUNCH(launch_warp(ds, drs, dfs, width, height, n, ctx->d_geom, dcards, ctx->stream));
-  if (mem == B200_MEM_HOST) CU(cudaMemcpyAsync(cards, ctx->d_cards, kCardBytes * n, cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
+  LAUNCH(launch_corners_to_geom(dc, dv, n, orientation, upsample, l->d_geom, l->stream));
+  uint8_t *dcards = mem == B200_MEM_DEVICE ? cards : l->d_cards;
+  LAUNCH(launch_warp(ds, drs, dfs, width, height, n, l->d_geom, dcards, l->stream));
+  if (mem == B200_MEM_HOST) CU(cudaMemcpyAsync(cards, l->d_cards, kCardBytes * n, cudaMemcpyDeviceToHost, l->stream));
+  CU(cudaStreamSynchronize(l->stream));
   return B200_OK;
 }
 
 int b200_scan_cards_batch(b200_ctx *ctx, const uint8_t *cards, int n, const uint8_t *valid, int mem, b200_scan *scans) {
   if (!ctx || !cards || !scans || n < 1) return fail(ctx, B200_EINVAL, "b200_scan_cards_batch: bad arguments");
   CU(cudaSetDevice(ctx->device));
-  int rc = ensure_capacity(ctx, n, ctx->cap_w ? ctx->cap_w : 32, ctx->cap_h ? ctx->cap_h : 32, false);
+  Lane *l = &ctx->lane[0];
+  int rc = ensure_capacity(ctx, l, n, l->cap_w ? l->cap_w : 32, l->cap_h ? l->cap_h : 32, false);
   if (rc) return rc;
   const uint8_t *dc = cards, *dv = valid;
   if (mem == B200_MEM_HOST) {
-    CU(cudaMemcpyAsync(ctx->d_cards, cards, kCardBytes * n, cudaMemcpyHostToDevice, ctx->stream));
-    dc = ctx->d_cards;
+    CU(cudaMemcpyAsync(l->d_cards, cards, kCardBytes * n, cudaMemcpyHostToDevice, l->stream));
+    dc = l->d_cards;
     if (valid) {
       rc = ensure_misc(ctx, n);
       if (rc) return rc;
-      CU(cudaMemcpyAsync(ctx->d_misc, valid, n, cudaMemcpyHostToDevice, ctx->stream));
+      CU(cudaMemcpyAsync(ctx->d_misc, valid, n, cudaMemcpyHostToDevice, l->stream));
       dv = (const uint8_t *)ctx->d_misc;
     }
   }
-  b200_scan *ds = mem == B200_MEM_DEVICE ? scans : ctx->d_scan;
-  LAUNCH(launch_scan(ctx->wts, dc, n, nullptr, dv, ctx->d_vprob, ds, ctx->stream));
-  if (mem == B200_MEM_HOST) CU(cudaMemcpyAsync(scans, ctx->d_scan, sizeof(b200_scan) * n, cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
+  b200_scan *ds = mem == B200_MEM_DEVICE ? scans : l->d_scan;
+  LAUNCH(launch_scan(ctx->wts, dc, n, nullptr, dv, l->d_vprob, ds, l->stream, nullptr, nullptr, nullptr, nullptr));
+  if (mem == B200_MEM_HOST) CU(cudaMemcpyAsync(scans, l->d_scan, sizeof(b200_scan) * n, cudaMemcpyDeviceToHost, l->stream));
+  CU(cudaStreamSynchronize(l->stream));
   return B200_OK;
 }
 
@@ -394,25 +461,41 @@ int b200_process_frames_batch(b200_ctx *ctx, const uint8_t *y, int yrs, size_t y
   CU(cudaSetDevice(ctx->device));
   int rc = ensure_config(ctx, width, height, orientation, 1);
   if (rc) return rc;
-  rc = ensure_capacity(ctx, n, width, height, mem == B200_MEM_HOST);
-  if (rc) return rc;
-  const uint8_t *dy;
-  int drs;
-  size_t dfs;
-  rc = stage_planes(ctx, y, yrs, yfs, width, height, n, mem, ctx->d_frames, &dy, &drs, &dfs);
-  if (rc) return rc;
-  rc = detect_sequence(ctx, dy, drs, dfs, nullptr, nullptr, 0, 0, n);
-  if (rc) return rc;
-  uint8_t *dcards = (mem == B200_MEM_DEVICE && cards_out) ? cards_out : ctx->d_cards;
-  LAUNCH(launch_warp(dy, drs, dfs, width, height, n, ctx->d_geom, dcards, ctx->stream));
-  LAUNCH(launch_scan(ctx->wts, dcards, n, ctx->d_geom, nullptr, ctx->d_vprob, ctx->d_scan, ctx->stream));
-  b200_frame_record *drec = mem == B200_MEM_DEVICE ? records : ctx->d_records;
-  LAUNCH(launch_finalize_records(ctx->d_geom, ctx->d_scan, dcards, n, drec, ctx->stream));
-  if (mem == B200_MEM_HOST) {
-    CU(cudaMemcpyAsync(records, ctx->d_records, sizeof(b200_frame_record) * n, cudaMemcpyDeviceToHost, ctx->stream));
-    if (cards_out) CU(cudaMemcpyAsync(cards_out, ctx->d_cards, kCardBytes * n, cudaMemcpyDeviceToHost, ctx->stream));
+  if (mem == B200_MEM_DEVICE) {
+    Lane *l = &ctx->lane[0];
+    rc = ensure_capacity(ctx, l, n, width, height, false);
+    if (rc) return rc;
+    uint8_t *dcards = cards_out ? cards_out : l->d_cards;
+    rc = pipeline_on_lane(ctx, l, y, yrs, yfs, width, height, n, dcards, records, ctx->profiling != 0);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(l->stream));
+    if (ctx->profiling) return collect_stage_times(ctx, n);
+    return B200_OK;
   }
-  CU(cudaStreamSynchronize(ctx->stream));
+  // Host buffers: chunked two-lane pipeline.  Lane k%2 takes chunk k: H2D copy, kernels and the D2H of the
+  // records are queued on that lane's stream, so chunk k+1's copy overlaps chunk k's kernels.
+  const int chunk = n < ctx->host_chunk ? n : ctx->host_chunk;
+  for (int i = 0; i < 2; i++) {
+    if (i == 1 && n <= chunk) break;
+    rc = ensure_capacity(ctx, &ctx->lane[i], chunk, width, height, true);
+    if (rc) return rc;
+  }
+  int k = 0;
+  for (int f0 = 0; f0 < n; f0 += chunk, k++) {
+    Lane *l = &ctx->lane[k & 1];
+    const int cnt = n - f0 < chunk ? n - f0 : chunk;
+    const uint8_t *dy;
+    int drs;
+    size_t dfs;
+    rc = stage_planes(ctx, l->stream, y + (size_t)f0 * yfs, yrs, yfs, width, height, cnt, B200_MEM_HOST, l->d_frames, &dy, &drs, &dfs);
+    if (rc) return rc;
+    rc = pipeline_on_lane(ctx, l, dy, drs, dfs, width, height, cnt, l->d_cards, l->d_records, false);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(records + f0, l->d_records, sizeof(b200_frame_record) * cnt, cudaMemcpyDeviceToHost, l->stream));
+    if (cards_out) CU(cudaMemcpyAsync(cards_out + (size_t)f0 * kCardBytes, l->d_cards, kCardBytes * cnt, cudaMemcpyDeviceToHost, l->stream));
+  }
+  CU(cudaStreamSynchronize(ctx->lane[0].stream));
+  if (k > 1) CU(cudaStreamSynchronize(ctx->lane[1].stream));
   return B200_OK;
 }
 
@@ -443,8 +526,27 @@ int b200_categorize_patches_batch(b200_ctx *ctx, const uint8_t *patches, int n, 
     CU(cudaMemcpyAsync(p, patches, (size_t)n * 513, cudaMemcpyHostToDevice, ctx->stream));
     dp = p;
   }
-  LAUNCH(launch_categorize_patches(ctx->wts, dp, n, dout, ctx->stream));
+  LAUNCH(launch_categorize_patches(ctx->wts, dp, nullptr, n, dout, ctx->stream));
   if (mem == B200_MEM_HOST) CU(cudaMemcpyAsync(out, dout, (size_t)n * 160, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}
+
+int b200_digit_models_batch(b200_ctx *ctx, const float *patches, int n, int mem, float *out) {
+  if (!ctx || !patches || !out || n < 1) return fail(ctx, B200_EINVAL, "b200_digit_models_batch: bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  const float *dp = patches;
+  float *dout = out;
+  if (mem == B200_MEM_HOST) {
+    int rc = ensure_misc(ctx, (size_t)n * (513 + 40) * sizeof(float));
+    if (rc) return rc;
+    float *p = (float *)ctx->d_misc;
+    CU(cudaMemcpyAsync(p, patches, (size_t)n * 513 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    dp = p;
+    dout = p + (size_t)n * 513;
+  }
+  LAUNCH(launch_categorize_patches(ctx->wts, nullptr, dp, n, dout, ctx->stream));
+  if (mem == B200_MEM_HOST) CU(cudaMemcpyAsync(out, dout, (size_t)n * 40 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return B200_OK;
 }

@@ -84,10 +84,12 @@ int launch_corners_to_geom(const b200_corner_points *corners, const uint8_t *val
 int launch_warp(const uint8_t *src, int row_stride, size_t frame_stride, int w, int h, int n, const FrameGeom *geom,
                 uint8_t *cards, cudaStream_t s);
 int launch_scan(const NetWeights &wts, const uint8_t *cards, int n, const FrameGeom *geom_or_null, const uint8_t *valid,
-                float *vprob, b200_scan *scans, cudaStream_t s);
+                float *vprob, b200_scan *scans, cudaStream_t s, cudaEvent_t ev_vseg, cudaEvent_t ev_hseg, cudaEvent_t ev_cat,
+                cudaEvent_t ev_fin);
 int launch_finalize_records(const FrameGeom *geom, const b200_scan *scans, const uint8_t *cards, int n,
                             b200_frame_record *recs, cudaStream_t s);
-int launch_categorize_patches(const NetWeights &wts, const uint8_t *patches, int n, float *out, cudaStream_t s);
+int launch_categorize_patches(const NetWeights &wts, const uint8_t *patches, const float *float_patches, int n, float *out,
+                              cudaStream_t s);
 int launch_vseg_model(const NetWeights &wts, const float *rows, int n, float *out, cudaStream_t s);
 int upload_conv_constants(const float *cnn_blobs[3]);  // __constant__ conv kernels / biases (nets.cu)
 

@@ -1,0 +1,260 @@
+// card.io-dmz_b200/csrc/dmz_compat.cpp -- the reference's C++ entry points (dmz.h:45-101, scan/scan.h:50-72) on top
+// of the C ABI, batch of one.  Host-side only: image bookkeeping, the session EMA and scanner_result's checks
+// (scan.cpp:88-194); all image arithmetic happens in the CUDA kernels behind b200_*_batch.
+// If CUDA fails the functions report "nothing found / not usable" (the reference has no error channel either).
+#include <dlfcn.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/time.h>
+
+#include <mutex>
+
+#include "b200_dmz.h"
+#include "dmz_b200_compat.h"
+
+namespace {
+
+std::mutex g_mutex;
+b200_ctx *g_default_ctx = nullptr;  // scanner_* carry no dmz_context: they share one lazily created context
+
+b200_ctx *default_ctx() {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  if (!g_default_ctx) {
+    const char *dev = getenv("B200_DMZ_DEVICE");
+    if (b200_ctx_create(&g_default_ctx, dev ? atoi(dev) : 0, nullptr) != B200_OK) {
+      fprintf(stderr, "b200dmz: %s\n", b200_last_error(g_default_ctx));
+      b200_ctx_destroy(g_default_ctx);
+      g_default_ctx = nullptr;
+    }
+  }
+  return g_default_ctx;
+}
+
+struct PlaneView {
+  const uint8_t *data;
+  int w, h, step;
+};
+
+// cvGetSize / llcv_get_data_origin semantics: an image with a ROI is the ROI (cv/image_util.cpp:30-37)
+PlaneView view_of(const IplImage *img) {
+  PlaneView v;
+  v.step = img->widthStep;
+  if (img->roi) {
+    v.data = (const uint8_t *)img->imageData + (size_t)img->roi->yOffset * img->widthStep + img->roi->xOffset;
+    v.w = img->roi->width, v.h = img->roi->height;
+  } else {
+    v.data = (const uint8_t *)img->imageData;
+    v.w = img->width, v.h = img->height;
+  }
+  return v;
+}
+
+IplImage *create_card_image() {
+  // Prefer the host application's OpenCV allocator so that its cvReleaseImage frees what we hand out.
+  typedef struct { int width, height; } Size2;
+  typedef IplImage *(*create_fn)(Size2, int, int);
+  static create_fn cv_create = (create_fn)dlsym(RTLD_DEFAULT, "cvCreateImage");
+  if (cv_create) {
+    Size2 s = {B200_CARD_W, B200_CARD_H};
+    return cv_create(s, IPL_DEPTH_8U, 1);
+  }
+  IplImage *img = (IplImage *)calloc(1, sizeof(IplImage));
+  img->nSize = sizeof(IplImage);
+  img->nChannels = 1;
+  img->depth = IPL_DEPTH_8U;
+  img->width = B200_CARD_W, img->height = B200_CARD_H;
+  img->align = 4;
+  img->widthStep = B200_CARD_W;
+  img->imageSize = B200_CARD_W * B200_CARD_H;
+  img->imageData = img->imageDataOrigin = (char *)malloc((size_t)img->imageSize);
+  memcpy(img->colorModel, "GRAY", 4);
+  memcpy(img->channelSeq, "GRAY", 4);
+  return img;
+}
+
+float tree_sum(const float *v, int start, int len) {  // Eigen unrolled redux, Core/Redux.h:96-118
+  if (len == 1) return v[start];
+  return tree_sum(v, start, len / 2) + tree_sum(v, start + len / 2, len - len / 2);
+}
+
+bool luhn(const uint8_t *d, int n) {
+  int even = 0, sum = 0;
+  for (int i = n - 1; i >= 0; i--) {
+    int addend = d[i] * (1 << (even++ & 1));
+    sum += addend % 10 + addend / 10;
+  }
+  return sum % 10 == 0;
+}
+
+}  // namespace
+
+// implemented in scanner.cpp's translation unit via the C ABI: reuse its prefix table through a scratch session
+extern "C" int b200_card_type_for_number(const uint8_t *digits, int n);
+
+dmz_context *dmz_context_create(void) {
+  dmz_context *dmz = (dmz_context *)calloc(1, sizeof(dmz_context));
+  b200_ctx *ctx = nullptr;
+  const char *dev = getenv("B200_DMZ_DEVICE");
+  if (b200_ctx_create(&ctx, dev ? atoi(dev) : 0, nullptr) != B200_OK) {
+    fprintf(stderr, "b200dmz: %s\n", b200_last_error(ctx));
+    b200_ctx_destroy(ctx);
+    ctx = nullptr;
+  }
+  dmz->mz = ctx;  // dmz.h:17-20: mz is the designated per-platform hook
+  return dmz;
+}
+
+void dmz_context_destroy(dmz_context *dmz) {
+  if (!dmz) return;
+  b200_ctx_destroy((b200_ctx *)dmz->mz);
+  free(dmz);
+}
+
+void dmz_prepare_for_backgrounding(dmz_context *) {}
+
+bool dmz_found_all_edges(dmz_edges e) { return e.top.found && e.bottom.found && e.left.found && e.right.found; }
+
+bool dmz_detect_edges(IplImage *y, IplImage *cb, IplImage *cr, FrameOrientation orientation, dmz_edges *found_edges,
+                      dmz_corner_points *corner_points) {
+  found_edges->top.found = found_edges->bottom.found = found_edges->left.found = found_edges->right.found = 0;
+  b200_ctx *ctx = default_ctx();
+  if (!ctx || !y || !cb || !cr) return false;
+  PlaneView vy = view_of(y), vb = view_of(cb), vr = view_of(cr);
+  if (vb.w != vy.w / 2 || vb.h != vy.h / 2 || vr.w != vb.w || vr.h != vb.h || vr.step != vb.step) return false;
+  b200_edges e;
+  b200_corner_points c;
+  uint8_t all = 0;
+  int rc = b200_detect_edges_batch(ctx, vy.data, vy.step, (size_t)vy.step * vy.h, vb.data, vr.data, vb.step,
+                                   (size_t)vb.step * vb.h, vy.w, vy.h, 1, orientation, B200_MEM_HOST, &e, &c, &all, nullptr);
+  if (rc != B200_OK) return false;
+  memcpy(found_edges, &e, sizeof(e));  // identical layouts (include/b200_dmz.h)
+  if (all) memcpy(corner_points, &c, sizeof(c));
+  return all != 0;
+}
+
+void dmz_transform_card(dmz_context *dmz, IplImage *sample, dmz_corner_points corner_points, FrameOrientation orientation,
+                        bool upsample, IplImage **transformed) {
+  b200_ctx *ctx = dmz && dmz->mz ? (b200_ctx *)dmz->mz : default_ctx();
+  if (*transformed == NULL) *transformed = create_card_image();  // dmz.cpp:493-495; the caller frees it
+  if (!ctx || !sample) return;
+  PlaneView v = view_of(sample);
+  IplImage *out = *transformed;
+  b200_corner_points c;
+  memcpy(&c, &corner_points, sizeof(c));
+  if (out->widthStep == B200_CARD_W) {
+    b200_transform_card_batch(ctx, v.data, v.step, (size_t)v.step * v.h, v.w, v.h, 1, &c, nullptr, orientation, upsample,
+                              B200_MEM_HOST, (uint8_t *)out->imageData);
+  } else {
+    uint8_t *tmp = (uint8_t *)malloc((size_t)B200_CARD_W * B200_CARD_H);
+    if (b200_transform_card_batch(ctx, v.data, v.step, (size_t)v.step * v.h, v.w, v.h, 1, &c, nullptr, orientation, upsample,
+                                  B200_MEM_HOST, tmp) == B200_OK)
+      for (int r = 0; r < B200_CARD_H; r++) memcpy(out->imageData + (size_t)r * out->widthStep, tmp + (size_t)r * B200_CARD_W, B200_CARD_W);
+    free(tmp);
+  }
+}
+
+void scanner_initialize(ScannerState *state) { scanner_reset(state); }
+
+void scanner_reset(ScannerState *state) {  // scan.cpp:23-35
+  state->count15 = 0;
+  state->count16 = 0;
+  memset(state->aggregated15.v, 0, sizeof(state->aggregated15.v));
+  memset(state->aggregated16.v, 0, sizeof(state->aggregated16.v));
+  state->session_analytics.num_frames_scanned = 0;
+  state->session_analytics.frames_ring_start = 0;
+  state->timeOfCardNumberCompletionInMilliseconds = 0;
+  state->scan_expiry = false;
+  state->expiry_month = 0;
+  state->expiry_year = 0;
+  state->expiry_groups.clear();
+  state->name_groups.clear();
+}
+
+void scanner_add_frame(ScannerState *state, IplImage *y, FrameScanResult *result) {
+  scanner_add_frame_with_expiry(state, y, false, result);
+}
+
+void scanner_add_frame_with_expiry(ScannerState *state, IplImage *y, bool, FrameScanResult *result) {
+  // scan_card_image (frame.cpp:24-81) on the GPU; expiry scanning is outside this build's scope
+  result->upside_down = false;
+  result->usable = false;
+  b200_ctx *ctx = default_ctx();
+  if (!ctx || !y || y->width != B200_CARD_W || y->height != B200_CARD_H) return;
+  const bool need_number = state->timeOfCardNumberCompletionInMilliseconds == 0;
+  b200_scan s;
+  int rc;
+  if (y->widthStep == B200_CARD_W) {
+    rc = b200_scan_cards_batch(ctx, (const uint8_t *)y->imageData, 1, nullptr, B200_MEM_HOST, &s);
+  } else {
+    uint8_t *tmp = (uint8_t *)malloc((size_t)B200_CARD_W * B200_CARD_H);
+    for (int r = 0; r < B200_CARD_H; r++) memcpy(tmp + (size_t)r * B200_CARD_W, y->imageData + (size_t)r * y->widthStep, B200_CARD_W);
+    rc = b200_scan_cards_batch(ctx, tmp, 1, nullptr, B200_MEM_HOST, &s);
+    free(tmp);
+  }
+  if (rc != B200_OK) return;
+  memcpy(&result->vseg, &s.vseg, sizeof(s.vseg));
+  result->upside_down = s.upside_down;
+  if (s.upside_down) return;
+  if (!need_number) {  // collect_card_number == false: only the vseg gate applies (frame.cpp:43-49)
+    result->usable = s.vseg.score > 15;
+    return;
+  }
+  result->usable = s.usable;
+  if (s.vseg.score > 15) {
+    memcpy(&result->hseg, &s.hseg, sizeof(s.hseg));
+    memcpy(result->scores.v, s.scores, sizeof(s.scores));
+  }
+  if (!result->usable) return;
+  state->mostRecentUsableHSeg = result->hseg;
+  state->mostRecentUsableVSeg = result->vseg;
+  NumberScores *agg = nullptr;
+  if (result->hseg.n_offsets == 15) agg = &state->aggregated15, state->count15++;
+  else if (result->hseg.n_offsets == 16) agg = &state->aggregated16, state->count16++;
+  if (!agg) return;
+  for (int i = 0; i < 160; i++) agg->v[i] *= 0.8f;                           // kDecayFactor, scan.cpp:75-83
+  for (int i = 0; i < 160; i++) agg->v[i] += result->scores.v[i] * (1 - 0.8f);
+}
+
+void scanner_result(ScannerState *state, ScannerResult *result) {  // scan.cpp:88-194 with SCAN_EXPIRY off
+  result->complete = false;
+  if (state->timeOfCardNumberCompletionInMilliseconds > 0) {
+    *result = state->successfulCardNumberResult;
+  } else {
+    const uint16_t max_count = state->count15 > state->count16 ? state->count15 : state->count16;
+    const uint16_t min_count = state->count15 < state->count16 ? state->count15 : state->count16;
+    if (max_count - min_count < 3) return;
+    if (min_count * 2 > max_count) return;
+    result->hseg = state->mostRecentUsableHSeg;
+    result->vseg = state->mostRecentUsableVSeg;
+    const NumberScores *agg;
+    if (state->count15 > state->count16) result->n_numbers = 15, agg = &state->aggregated15;
+    else result->n_numbers = 16, agg = &state->aggregated16;
+    uint8_t number[16];
+    for (uint8_t i = 0; i < result->n_numbers; i++) {
+      const float *row = agg->v + i * 10;
+      float mx = row[0];
+      int arg = 0;
+      for (int j = 1; j < 10; j++)
+        if (row[j] > mx) mx = row[j], arg = j;
+      const float sum = tree_sum(row, 0, 10);
+      result->predictions(i) = arg;
+      number[i] = (uint8_t)arg;
+      if (mx / sum < 0.7f) return;  // kMinStability
+    }
+    const int type = b200_card_type_for_number(number, result->n_numbers);
+    if (type != 0 /* unrecognized */ && type != 1 /* ambiguous */ && luhn(number, result->n_numbers)) {
+      struct timeval t;
+      gettimeofday(&t, NULL);
+      state->timeOfCardNumberCompletionInMilliseconds = (long)((t.tv_sec * 1000) + (t.tv_usec / 1000));
+      state->successfulCardNumberResult = *result;
+    }
+  }
+  if (state->timeOfCardNumberCompletionInMilliseconds > 0) {
+    result->expiry_month = 0;
+    result->expiry_year = 0;
+    result->complete = true;
+  }
+}
+
+void scanner_destroy(ScannerState *) {}

@@ -212,7 +212,8 @@ struct CatSmem {
 template <bool kRaw>
 __global__ void __launch_bounds__(kCThreads, 1)
 categorize_kernel(NetWeights W, const uint8_t *__restrict__ cards, b200_scan *__restrict__ scans,
-                  const uint8_t *__restrict__ raw_patches, int n_items /* frames, or raw patches */, float *__restrict__ raw_out) {
+                  const uint8_t *__restrict__ raw_patches, const float *__restrict__ raw_float, int n_items /* frames, or raw patches */,
+                  float *__restrict__ raw_out) {
   extern __shared__ __align__(16) uint8_t cs_raw[];
   CatSmem &S = *reinterpret_cast<CatSmem *>(cs_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -243,6 +244,10 @@ categorize_kernel(NetWeights W, const uint8_t *__restrict__ cards, b200_scan *__
     for (int d = warp; d < nd; d += 8) {
       const uint8_t *src;
       int stride;
+      if (kRaw && raw_float != nullptr) {  // already-prepared float patches (model known-answer tests)
+        for (int i = lane; i < 27 * 19; i += 32) S.patch[d][i] = __ldg(raw_float + (size_t)(grp * 16 + d) * (27 * 19) + i);
+        continue;
+      }
       if (kRaw) {
         src = raw_patches + (size_t)(grp * 16 + d) * (27 * 19);
         stride = 19;
@@ -434,45 +439,52 @@ int launch_vseg_model(const NetWeights &wts, const float *rows, int n, float *ou
   return launch_vseg_rows(wts, nullptr, nullptr, nullptr, n, 2, nullptr, rows, out, s);
 }
 
-static int launch_categorize(const NetWeights &wts, const uint8_t *cards, b200_scan *scans, const uint8_t *raw, int n,
-                             float *raw_out, cudaStream_t s) {
+static int launch_categorize(const NetWeights &wts, const uint8_t *cards, b200_scan *scans, const uint8_t *raw,
+                             const float *raw_float, int n, float *raw_out, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
     if (!ensure_smem(categorize_kernel<false>, sizeof(CatSmem))) return -1;
     if (!ensure_smem(categorize_kernel<true>, sizeof(CatSmem))) return -1;
     configured = true;
   }
-  const int groups = raw ? (n + 15) / 16 : n;
+  const bool is_raw = raw != nullptr || raw_float != nullptr;
+  const int groups = is_raw ? (n + 15) / 16 : n;
   int grid = num_sms();
   if (grid > groups) grid = groups;
   if (grid < 1) grid = 1;
-  if (raw) categorize_kernel<true><<<grid, kCThreads, sizeof(CatSmem), s>>>(wts, nullptr, nullptr, raw, n, raw_out);
-  else categorize_kernel<false><<<grid, kCThreads, sizeof(CatSmem), s>>>(wts, cards, scans, nullptr, n, nullptr);
+  if (is_raw) categorize_kernel<true><<<grid, kCThreads, sizeof(CatSmem), s>>>(wts, nullptr, nullptr, raw, raw_float, n, raw_out);
+  else categorize_kernel<false><<<grid, kCThreads, sizeof(CatSmem), s>>>(wts, cards, scans, nullptr, nullptr, n, nullptr);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
-int launch_categorize_patches(const NetWeights &wts, const uint8_t *patches, int n, float *out, cudaStream_t s) {
-  return launch_categorize(wts, nullptr, nullptr, patches, n, out, s);
+int launch_categorize_patches(const NetWeights &wts, const uint8_t *patches, const float *float_patches, int n, float *out,
+                              cudaStream_t s) {
+  return launch_categorize(wts, nullptr, nullptr, patches, float_patches, n, out, s);
 }
 
 // scan_card_image for a batch: gate -> vseg (coarse, select, fine, select) -> hseg -> categorize -> finish.
 // vprob doubles as scratch: its tail holds the per-frame gate bytes.
 int launch_scan(const NetWeights &wts, const uint8_t *cards, int n, const FrameGeom *geom, const uint8_t *valid,
-                float *vprob, b200_scan *scans, cudaStream_t s) {
+                float *vprob, b200_scan *scans, cudaStream_t s, cudaEvent_t ev_vseg, cudaEvent_t ev_hseg, cudaEvent_t ev_cat,
+                cudaEvent_t ev_fin) {
   int launches = 0, rc;
   uint8_t *gate = reinterpret_cast<uint8_t *>(vprob + (size_t)n * 540);
 #define STEP(call)          \
   rc = (call);              \
   if (rc < 0) return -1;    \
   launches += rc;
+  if (ev_vseg) cudaEventRecord(ev_vseg, s);
   STEP(launch_scan_gate(geom, valid, n, gate, s));
   if (cudaMemsetAsync(vprob, 0, (size_t)n * 540 * sizeof(float), s) != cudaSuccess) return -1;
   STEP(launch_vseg_rows(wts, cards, gate, scans, n, 0, vprob, nullptr, nullptr, s));
   STEP(launch_vseg_select(vprob, gate, n, 0, scans, s));
   STEP(launch_vseg_rows(wts, cards, gate, scans, n, 1, vprob, nullptr, nullptr, s));
   STEP(launch_vseg_select(vprob, gate, n, 1, scans, s));
+  if (ev_hseg) cudaEventRecord(ev_hseg, s);
   STEP(launch_hseg(cards, n, scans, s));
-  STEP(launch_categorize(wts, cards, scans, nullptr, n, nullptr, s));
+  if (ev_cat) cudaEventRecord(ev_cat, s);
+  STEP(launch_categorize(wts, cards, scans, nullptr, nullptr, n, nullptr, s));
+  if (ev_fin) cudaEventRecord(ev_fin, s);
   STEP(launch_scan_finish(n, scans, s));
 #undef STEP
   return launches;

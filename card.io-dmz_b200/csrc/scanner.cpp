@@ -60,6 +60,9 @@ int card_type(const uint8_t *d, int n) {
 
 extern "C" {
 
+/* dmz_card_info_for_prefix_and_length(number, n, false).card_type; 0 = unrecognized, 1 = ambiguous (dmz_olm.h:44-53) */
+int b200_card_type_for_number(const uint8_t *digits, int n) { return card_type(digits, n); }
+
 b200_scanner *b200_scanner_new(void) {
   b200_scanner *s = new b200_scanner();
   memset(s, 0, sizeof(*s));

@@ -118,6 +118,12 @@ int b200_ctx_reserve(b200_ctx *ctx, int max_frames, int width, int height);
 uint64_t b200_launch_count(const b200_ctx *ctx);
 /* The CUDA stream (cudaStream_t) all work of this context is enqueued on. */
 void *b200_ctx_stream(const b200_ctx *ctx);
+/* Per-stage device time of b200_process_frames_batch (B200_MEM_DEVICE calls), measured with CUDA events on the
+ * context's stream.  Stages: 0 detect (Sobel/Canny/Hough), 1 geometry, 2 warp, 3 vseg, 4 hseg, 5 categorize,
+ * 6 finalize.  b200_set_profiling(ctx, 1) zeroes the accumulators; b200_stage_times returns the accumulated
+ * milliseconds and the number of frames they cover. */
+void b200_set_profiling(b200_ctx *ctx, int on);
+int b200_stage_times(const b200_ctx *ctx, double ms[7], uint64_t *frames);
 
 /* ---- dmz_detect_edges (dmz.h:86-87, dmz.cpp:371-439), batched ----
  * y: n planes width x height; cb, cr: n planes (width/2) x (height/2), or both NULL (then only the Y
@@ -152,6 +158,9 @@ int b200_calc_persp_transform_batch(b200_ctx *ctx, const float *src_pts, const f
 /* scores_for_number_image + patch prep (scan/n_categorize.cpp:45-108): patches = n x 27 x 19 u8 taken from a
  * card; out = n x 40 floats (10 ensemble scores + 3 x 10 model probabilities). */
 int b200_categorize_patches_batch(b200_ctx *ctx, const uint8_t *patches, int n, int mem, float *out);
+/* applyc_* ensemble on already-prepared float patches (n x 27 x 19 f32); out as above.  This is the entry the
+ * reference's embedded model known-answer tests (modelc_*.cpp:2039-2051) are replayed through. */
+int b200_digit_models_batch(b200_ctx *ctx, const float *patches, int n, int mem, float *out);
 /* applym_befe75da on prepared rows: in = n x 204 f32, out = n x 3 f32 */
 int b200_vseg_model_batch(b200_ctx *ctx, const float *rows, int n, int mem, float *out);
 

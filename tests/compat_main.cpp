@@ -1,0 +1,77 @@
+// tests/compat_main.cpp -- a caller written against the reference's own API shape (dmz.h / scan/scan.h), compiled
+// against include/dmz_b200_compat.h and linked with libb200dmz.so: the per-frame SDK sequence of SURVEY 3.4.
+// usage: compat_main frames.bin n width height out.bin
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "dmz_b200_compat.h"
+
+static void wrap(IplImage *img, uint8_t *data, int w, int h) {
+  memset(img, 0, sizeof(*img));
+  img->nSize = sizeof(IplImage);
+  img->nChannels = 1;
+  img->depth = IPL_DEPTH_8U;
+  img->width = w, img->height = h, img->widthStep = w;
+  img->imageSize = w * h;
+  img->imageData = img->imageDataOrigin = (char *)data;
+  img->align = 4;
+}
+
+int main(int argc, char **argv) {
+  if (argc < 6) return 2;
+  const int n = atoi(argv[2]), w = atoi(argv[3]), h = atoi(argv[4]);
+  std::vector<uint8_t> frames((size_t)n * w * h), chroma((size_t)(w / 2) * (h / 2), 128);
+  FILE *f = fopen(argv[1], "rb");
+  if (!f || fread(frames.data(), 1, frames.size(), f) != frames.size()) return 3;
+  fclose(f);
+  FILE *out = fopen(argv[5], "wb");
+  dmz_context *dmz = dmz_context_create();
+  ScannerState state;
+  scanner_initialize(&state);
+  for (int k = 0; k < n; k++) {
+    IplImage y, cb, cr;
+    wrap(&y, frames.data() + (size_t)k * w * h, w, h);
+    wrap(&cb, chroma.data(), w / 2, h / 2);
+    wrap(&cr, chroma.data(), w / 2, h / 2);
+    dmz_edges edges;
+    dmz_corner_points corners;
+    memset(&corners, 0, sizeof(corners));
+    bool found = dmz_detect_edges(&y, &cb, &cr, FrameOrientationLandscapeRight, &edges, &corners);
+    int32_t rec[8] = {found, dmz_found_all_edges(edges), 0, 0, 0, 0, 0, 0};
+    uint8_t digits[16] = {0};
+    float scores[160] = {0};
+    uint32_t check = 0;
+    if (found) {
+      IplImage *card = NULL;
+      dmz_transform_card(dmz, &y, corners, FrameOrientationLandscapeRight, false, &card);
+      for (int i = 0; i < 428 * 270; i++) check += (uint32_t)(i + 1) * (uint8_t)card->imageData[(i / 428) * card->widthStep + i % 428];
+      FrameScanResult fr;
+      fr.flipped = false;
+      fr.focus_score = 0;
+      memset(fr.scores.v, 0, sizeof(fr.scores.v));
+      scanner_add_frame_with_expiry(&state, card, false, &fr);
+      rec[2] = fr.usable, rec[3] = fr.upside_down, rec[4] = fr.vseg.y_offset;
+      memcpy(scores, fr.scores.v, sizeof(scores));
+      ScannerResult sr;
+      memset(sr.predictions.v, 0, sizeof(sr.predictions.v));
+      sr.n_numbers = 0;
+      scanner_result(&state, &sr);
+      rec[5] = sr.complete, rec[6] = sr.n_numbers;
+      for (int i = 0; i < 16; i++) digits[i] = (uint8_t)sr.predictions(i);
+      free(card->imageDataOrigin);
+      free(card);
+    }
+    rec[7] = (int32_t)check;
+    fwrite(rec, sizeof(rec), 1, out);
+    fwrite(&corners, sizeof(corners), 1, out);
+    fwrite(scores, sizeof(scores), 1, out);
+    fwrite(digits, 16, 1, out);
+  }
+  scanner_destroy(&state);
+  dmz_context_destroy(dmz);
+  fclose(out);
+  return 0;
+}

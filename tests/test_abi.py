@@ -1,0 +1,91 @@
+"""The drop-in boundary, checked without a GPU: the shared library loads, exports every symbol the C-ABI header
+declares and the reference's C++-mangled entry points; struct layouts equal the reference build's; the host-side
+scanner session logic agrees with the oracle's restatement of scan.cpp."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from util import ROOT, deck_frames
+
+LIB = os.path.join(ROOT, "card.io-dmz_b200", "libb200dmz.so")
+
+# mangled names of the reference's own build (nm -D oracle/_ref/libdmz_ref.so)
+REFERENCE_SYMBOLS = [
+    "_Z18dmz_context_createv", "_Z19dmz_context_destroyP11dmz_context", "_Z19dmz_found_all_edges9dmz_edges",
+    "_Z16dmz_detect_edgesP9_IplImageS0_S0_hP9dmz_edgesP17dmz_corner_points",
+    "_Z18dmz_transform_cardP11dmz_contextP9_IplImage17dmz_corner_pointshbPS2_",
+    "_Z18scanner_initializeP12ScannerState", "_Z13scanner_resetP12ScannerState",
+    "_Z17scanner_add_frameP12ScannerStateP9_IplImageP15FrameScanResult",
+    "_Z29scanner_add_frame_with_expiryP12ScannerStateP9_IplImagebP15FrameScanResult",
+    "_Z14scanner_resultP12ScannerStateP13ScannerResult", "_Z15scanner_destroyP12ScannerState",
+]
+
+
+def exported():
+    out = subprocess.check_output(["nm", "-D", "--defined-only", LIB], text=True)
+    return {line.split()[-1] for line in out.splitlines() if line.strip()}
+
+
+def test_library_loads_without_gpu():
+    assert os.path.exists(LIB), "run __graft_entry__.build() first"
+    C.CDLL(LIB)
+
+
+def test_exports_every_declared_c_symbol():
+    hdr = open(os.path.join(ROOT, "include", "b200_dmz.h")).read()
+    declared = set(re.findall(r"\b(b200_[a-z_0-9]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    missing = declared - exported()
+    assert not missing, missing
+
+
+def test_exports_reference_cxx_entry_points():
+    missing = set(REFERENCE_SYMBOLS) - exported()
+    assert not missing, missing
+
+
+def test_reference_symbol_names_are_current(ref):
+    out = subprocess.check_output(["nm", "-D", "--defined-only", os.path.join(ROOT, "oracle", "_ref", "libdmz_ref.so")], text=True)
+    have = {line.split()[-1] for line in out.splitlines() if line.strip()}
+    assert set(REFERENCE_SYMBOLS) <= have
+
+
+def test_struct_layouts(pkg, ref):
+    # sizes asserted at compile time in include/dmz_b200_compat.h against these reference-build numbers
+    sizes = [ref.lib.ref_sizeof(i) for i in range(10)]
+    assert sizes == [28, 48, 640, 816, 240, 2832, 48, 32, 144, 520]
+    assert C.sizeof(pkg.VSeg) == sizes[0] and C.sizeof(pkg.HSeg) == sizes[1]
+    assert C.sizeof(pkg.Edges) == sizes[6] and C.sizeof(pkg.CornerPoints) == sizes[7]
+
+
+def test_no_context_without_cuda(pkg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(pkg.B200Error, match="no CPU fallback"):
+        pkg.Dmz()
+
+
+def test_scanner_session_matches_oracle(pkg, oracle):
+    """b200_scanner_* (host logic, scan.cpp:41-194) fed with oracle scan records == the oracle's own session."""
+    frames = deck_frames(16, 8)
+    recs, cards = oracle.process_frames(frames, want_cards=True)
+    so = oracle.scanner_new()
+    sb = pkg.Scanner()
+    for k in range(8):
+        oracle.scanner_add_frame(so, cards[k])
+        sb.add_scan(recs[k])
+        a15o, a16o, cnto = oracle.scanner_peek(so)
+        a15b, a16b, cntb = sb.peek()
+        assert np.array_equal(cnto, cntb)
+        assert np.array_equal(a16o.view(np.uint32), a16b.view(np.uint32)) and np.array_equal(a15o.view(np.uint32), a15b.view(np.uint32))
+        do, go = oracle.scanner_result(so)
+        db, gb = sb.result()
+        assert do == db and go.tolist() == gb.tolist()
+    assert db, "the deck session should complete"
+    oracle.scanner_free(so)
+    sb.close()

@@ -1,0 +1,85 @@
+"""BASELINE.json-sized runs (100k frames on one GPU by default; B200_FULLSIZE_FRAMES overrides) checked through
+size-independent properties, plus a random sample against the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+from util import deck_frames_cuda
+
+pytestmark = pytest.mark.gpu
+N = int(os.environ.get("B200_FULLSIZE_FRAMES", "100000"))
+
+
+@pytest.fixture(scope="module")
+def full(dmz, pkg):
+    import torch
+    frames = torch.empty((N, 480, 640), dtype=torch.uint8, device="cuda")
+    for f0 in range(0, N, 8192):
+        cnt = min(8192, N - f0)
+        frames[f0:f0 + cnt] = deck_frames_cuda(f0, cnt)
+    recs = torch.zeros((N, 808), dtype=torch.uint8, device="cuda")
+    dmz.process_frames_device(frames.data_ptr(), N, 640, 480, recs.data_ptr())
+    return frames, recs, recs.cpu().numpy().view(pkg.RECORD_DTYPE).reshape(N)
+
+
+def test_every_frame_of_the_deck_is_detected(full):
+    _, _, r = full
+    assert r["all_found"].all()
+    assert (r["upside_down"] == 0).all()
+    assert (r["usable"] == 1).mean() > 0.6
+
+
+def test_deterministic_and_batch_invariant(dmz, pkg, full):
+    """Running again, and running a slice on its own, give byte-identical records."""
+    import torch
+    frames, recs, r = full
+    again = torch.zeros_like(recs)
+    dmz.process_frames_device(frames.data_ptr(), N, 640, 480, again.data_ptr())
+    assert bool((again == recs).all())
+    lo, cnt = N // 3, min(1000, N - N // 3)
+    part = torch.zeros((cnt, 808), dtype=torch.uint8, device="cuda")
+    dmz.process_frames_device(frames[lo:].data_ptr(), cnt, 640, 480, part.data_ptr())
+    assert bool((part == recs[lo:lo + cnt]).all())
+
+
+def test_sessions_read_the_true_number(pkg, full):
+    """Each 8-frame session shows one card number; the per-session scanner result must complete for most sessions
+    and equal the deck's ground truth (Luhn-valid by construction)."""
+    from util import deck_truth
+    _, _, r = full
+    done = correct = 0
+    n_sessions = min(N // 8, 400)
+    for s in range(n_sessions):
+        sc = pkg.Scanner()
+        for k in range(8):
+            sc.add_scan(r[s * 8 + k])
+        ok, digits = sc.result()
+        sc.close()
+        if ok:
+            done += 1
+            truth, _ = deck_truth(s * 8)
+            correct += digits.tolist() == truth.tolist()
+    assert done >= 0.5 * n_sessions
+    assert correct >= 0.95 * done
+
+
+def test_random_sample_against_oracle(oracle, full):
+    frames, _, r = full
+    idx = np.sort(np.random.default_rng(0).choice(N, size=min(96, N), replace=False))
+    host = frames[idx.tolist()].cpu().numpy()
+    want = oracle.process_frames(host)
+    got = r[idx]
+    for f in ("found", "all_found", "card_check", "v_y_offset", "v_pattern_type", "usable", "upside_down", "h_offsets"):
+        assert np.array_equal(got[f], want[f]), f
+    assert np.array_equal(got["corners"].view(np.uint32), want["corners"].view(np.uint32))
+    assert np.abs(got["scores"] - want["scores"]).max() <= 1e-4
+
+
+def test_host_buffer_path_equals_device_path(dmz, pkg, full):
+    """The chunked two-lane H2D pipeline returns the same bytes as the device-resident path."""
+    frames, recs, r = full
+    n = min(N, 5000)
+    host = frames[:n].cpu().numpy()
+    got = dmz.process_frames(host)
+    assert np.array_equal(got.view(np.uint8).reshape(n, 808), recs[:n].cpu().numpy())

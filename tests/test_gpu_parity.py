@@ -1,0 +1,257 @@
+"""Parity of the CUDA path with the CPU oracle, stage by stage, through the C ABI (include/b200_dmz.h).
+
+Bar (BASELINE.json north_star): bit-exact for the integer edge / Hough / warp / segmentation results (and for the
+float geometry whose evaluation order is mirrored: line parameters, corners, homography, hseg scores); <= 1e-4
+absolute on the CNN / MLP probabilities."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from util import ROOT, deck_frames, synthetic_strip
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+G = os.path.join(ROOT, "tests", "golden")
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+@pytest.fixture(scope="module")
+def deck():
+    return deck_frames(200, 48)
+
+
+@pytest.fixture(scope="module")
+def orecs(oracle, deck):
+    return oracle.process_frames(deck, want_cards=True)
+
+
+def test_extension_is_the_cuda_library(pkg, dmz):
+    assert os.path.basename(pkg.lib_path()) == "libb200dmz.so" and dmz.launches == 0
+
+
+def test_detect_line_taps_exact(dmz, oracle, deck):
+    edges, corners, found, lines = dmz.detect_edges(deck[:16], want_lines=True)
+    boxes = oracle.detection_boxes(640, 480)
+    for k in range(16):
+        for s, (x, y, w, h) in enumerate(boxes):
+            ol = oracle.best_line(deck[k][y:y + h, x:x + w], s >= 2)
+            gl = lines[k, s]
+            for f in ("found", "max_votes", "low", "high", "n_edge_px"):
+                assert int(gl[f]) == getattr(ol, f), (k, s, f)
+            if ol.found:
+                assert (int(gl["r"]), int(gl["n"])) == (ol.r, ol.n)
+                assert bits([gl["rho"], gl["theta"]]).tolist() == bits([ol.rho, ol.theta]).tolist()
+
+
+def test_detect_edges_and_corners_exact(dmz, deck, orecs):
+    rec = orecs[0]
+    edges, corners, found, _ = dmz.detect_edges(deck)
+    assert np.array_equal(found, rec["all_found"].astype(np.uint8))
+    assert np.array_equal(edges["found"], rec["found"])
+    m = rec["found"] == 1
+    assert np.array_equal(bits(edges["rho"])[m], bits(rec["rho"])[m]) and np.array_equal(bits(edges["theta"])[m], bits(rec["theta"])[m])
+    assert np.array_equal(bits(corners), bits(rec["corners"]))
+
+
+def test_detect_edge_cases(dmz, oracle):
+    rng = np.random.default_rng(3)
+    frames = np.stack([
+        np.full((480, 640), 90, np.uint8),                                # flat: no edges at all
+        rng.integers(0, 256, (480, 640)).astype(np.uint8),                # uniform noise: high > any magnitude
+        deck_frames(7, 1)[0][:, ::-1].copy(),                              # mirrored card
+        np.where(np.indices((480, 640))[1] > 320, 200, 20).astype(np.uint8),  # one vertical step through the frame
+    ])
+    want = oracle.process_frames(frames)
+    edges, corners, found, lines = dmz.detect_edges(frames, want_lines=True)
+    assert np.array_equal(found, want["all_found"].astype(np.uint8))
+    assert np.array_equal(edges["found"], want["found"])
+    assert lines["n_edge_px"][1].sum() == 0
+
+
+def test_chroma_fallback_exact(dmz, oracle):
+    f = deck_frames(5, 1)[0]
+    cb = np.ascontiguousarray(f[::2, ::2])
+    cr = np.full((240, 320), 128, np.uint8)
+    y = f.copy()
+    y[:, :160] = 60
+    want = oracle.detect_edges(y, cb, cr)
+    edges, corners, found, _ = dmz.detect_edges(y[None], cb[None], cr[None])
+    assert list(edges["found"][0]) == list(want.found) and int(found[0]) == want.all_found
+    assert bits(edges["rho"][0]).tolist() == bits(list(want.rho)).tolist()
+    if want.all_found:
+        assert bits(corners[0]).tolist() == bits(list(want.corners)).tolist()
+
+
+def test_homography_bits(dmz, oracle, golden):
+    dst = np.array([0, 0, 427, 0, 0, 269, 427, 269], np.float32)
+    src = golden["homog_src"]
+    M = dmz.calc_persp_transform(src, np.tile(dst, (len(src), 1)))
+    assert np.array_equal(M.view(np.uint32), golden["homog_M_bits"])  # reference (Eigen SSE2) bits
+    rng = np.random.default_rng(9)
+    src = (np.array([106, 105, 533, 105, 106, 374, 533, 374], np.float32) + rng.uniform(-30, 30, (4000, 8))).astype(np.float32)
+    Mg = dmz.calc_persp_transform(src, np.tile(dst, (4000, 1)))
+    Mo = np.stack([oracle.calc_persp_transform(s, dst) for s in src])
+    assert np.array_equal(Mg.view(np.uint32), Mo.view(np.uint32))
+
+
+def test_transform_card_exact(dmz, oracle, deck, orecs):
+    rec, ocards = orecs
+    cards = dmz.transform_card(deck, rec["corners"], valid=rec["all_found"].astype(np.uint8))
+    assert np.array_equal(cards, ocards)
+    # all four orientations and the chroma (upsample) variant on one frame
+    for o in (1, 2, 3, 4):
+        assert np.array_equal(dmz.transform_card(deck[:1], rec["corners"][:1], orientation=o)[0], oracle.transform_card(deck[0], rec["corners"][0], o))
+
+
+def test_transform_card_outside_frame(dmz, oracle, deck):
+    """Corners partly outside the image: BORDER_CONSTANT 0 taps (cv/warp.cpp:165 CV_WARP_FILL_OUTLIERS)."""
+    c = np.array([[-40, -30, -20, 300, 500, -10, 700, 520]], np.float32)
+    assert np.array_equal(dmz.transform_card(deck[:1], c)[0], oracle.transform_card(deck[0], c[0]))
+
+
+def test_warp_identity_is_idempotent(dmz):
+    """Size-independent property: warping a 428x270 image with the identity corner set returns it unchanged."""
+    img = np.random.default_rng(1).integers(0, 256, (1, 270, 428)).astype(np.uint8)
+    c = np.array([[0, 0, 0, 269, 427, 0, 427, 269]], np.float32)  # tl, bl, tr, br
+    assert np.array_equal(dmz.transform_card(img, c)[0], img[0])
+
+
+def test_scan_cards(dmz, orecs):
+    rec, ocards = orecs
+    scans = dmz.scan_cards(ocards, valid=rec["all_found"].astype(np.uint8))
+    for f in ("v_y_offset", "v_pattern_type", "usable", "upside_down", "h_n_offsets", "h_pattern_offset", "h_offsets"):
+        assert np.array_equal(scans[f], rec[f]), f
+    assert np.abs(scans["v_score"] - rec["v_score"]).max() <= 1e-3  # sum of 27 probabilities
+    assert np.array_equal(bits(scans["h_score"]), bits(rec["h_score"])) and np.array_equal(bits(scans["h_number_width"]), bits(rec["h_number_width"]))
+    assert np.abs(scans["scores"] - rec["scores"]).max() <= TOL
+    assert (rec["usable"] == 1).sum() >= 24, "the deck should mostly be usable"
+
+
+def test_scan_edge_cases(dmz, oracle):
+    rng = np.random.default_rng(4)
+    good = oracle.process_frames(deck_frames(0, 1), want_cards=True)[1][0]
+    cards = np.stack([np.full((270, 428), 175, np.uint8),              # blank card: vseg gate fails
+                      rng.integers(0, 256, (270, 428)).astype(np.uint8),  # noise
+                      good[::-1, ::-1].copy(),                           # upside-down card
+                      good])
+    scans = dmz.scan_cards(cards)
+    for k in range(4):
+        w = oracle.scan_card_image(cards[k])
+        assert (scans["usable"][k], scans["upside_down"][k]) == (w.usable, w.upside_down), k
+        assert scans["v_y_offset"][k] == w.vseg.y_offset and scans["v_pattern_type"][k] == w.vseg.pattern_type, k
+    assert scans["upside_down"][2] == 1
+
+
+def test_model_known_answer_vectors(dmz):
+    """The reference's embedded KATs (models/generated/*.cpp pass*_()), replayed through the CUDA kernels, at the
+    reference's own tolerance 1e-5."""
+    def kat(name):
+        meta = json.load(open(os.path.join(G, "kat_%s.json" % name)))
+        data = np.fromfile(os.path.join(G, "kat_%s.bin" % name), "<f4")
+        return {v["label"]: data[v["offset"]:v["offset"] + v["count"]] for v in meta["vectors"]}
+    k = kat("modelm_befe75da")
+    assert np.abs(dmz.vseg_model(k["test input"])[0] - k["test output"]).max() <= 1e-5
+    for i, m in enumerate(("5c241121", "01266c1b", "b00bf70c")):
+        k = kat("modelc_" + m)
+        _, per_model = dmz.digit_models(k["test input"])
+        assert np.abs(per_model[0, i] - k["test output"]).max() <= 1e-5, m
+
+
+def test_categorize_patches(dmz, oracle, golden):
+    patches = golden["card0_patches"]
+    ens, mods = dmz.categorize_patches(patches)
+    assert np.abs(ens - golden["card0_ensemble"]).max() <= TOL and np.abs(mods - golden["card0_models"]).max() <= TOL
+    rng = np.random.default_rng(8)
+    noise = rng.integers(0, 256, (100, 27, 19)).astype(np.uint8)
+    noise[0] = 0      # all-equal patch: histogram has one bin, lut[0] = 0
+    noise[1] = 255
+    ens, mods = dmz.categorize_patches(noise)
+    for i in range(100):
+        e, m = oracle.digit_models(oracle.digit_patch_prep(noise[i]))
+        assert np.abs(ens[i] - e).max() <= TOL and np.abs(mods[i] - m).max() <= TOL, i
+
+
+def test_whole_path_records(dmz, deck, orecs):
+    rec, ocards = orecs
+    got, cards = dmz.process_frames(deck, want_cards=True)
+    assert np.array_equal(cards, ocards)
+    for f in ("found", "all_found", "card_check", "v_y_offset", "v_pattern_type", "usable", "upside_down", "h_n_offsets", "h_offsets", "h_pattern_offset"):
+        assert np.array_equal(got[f], rec[f]), f
+    assert np.array_equal(bits(got["corners"]), bits(rec["corners"]))
+    assert np.abs(got["scores"] - rec["scores"]).max() <= TOL
+
+
+def test_whole_path_against_reference_fixture(dmz, golden):
+    """Golden records produced by the reference's own sources (tools/make_ref_golden.py)."""
+    idx = golden["deck_idx"]
+    frames = np.concatenate([deck_frames(int(i), 1) for i in idx])
+    got, cards = dmz.process_frames(frames, want_cards=True)
+    want = golden["deck_records"]
+    assert np.array_equal(cards[0], golden["deck_card0"])
+    for f in ("found", "all_found", "card_check", "v_y_offset", "v_pattern_type", "usable", "upside_down", "h_offsets"):
+        assert np.array_equal(got[f], want[f]), f
+    assert np.array_equal(bits(got["corners"]), bits(want["corners"]))
+    assert np.abs(got["scores"] - want["scores"]).max() <= TOL
+
+
+def test_strided_input_and_ragged_batches(dmz, deck, orecs):
+    """Row / frame strides and batch sizes that are not multiples of anything; records must not depend on batching."""
+    rec = orecs[0]
+    for n in (1, 3, 17):
+        got = dmz.process_frames(deck[:n])
+        assert np.array_equal(got["card_check"], rec["card_check"][:n])
+    padded = np.zeros((5, 500, 704), np.uint8)
+    padded[:, :480, :640] = deck[:5]
+    import ctypes as C
+    recs = np.zeros(5, got.dtype)
+    rc = dmz.lib.b200_process_frames_batch(dmz.ctx, padded.ctypes.data_as(C.c_void_p), 704, 704 * 500, 640, 480, 5, 3, 0,
+                                           recs.ctypes.data_as(C.c_void_p), None)
+    assert rc == 0 and np.array_equal(recs["card_check"], rec["card_check"][:5])
+
+
+def test_720p_frames(dmz, oracle):
+    fr = deck_frames(0, 4, 1280, 720)
+    want = oracle.process_frames(fr)
+    got = dmz.process_frames(fr)
+    for f in ("found", "all_found", "card_check", "v_y_offset", "usable"):
+        assert np.array_equal(got[f], want[f]), f
+    assert want["all_found"].all()
+
+
+def test_bad_arguments_fail_cleanly(dmz, pkg):
+    with pytest.raises(pkg.B200Error):
+        dmz.process_frames(np.zeros((1, 16, 16), np.uint8))  # frame too small for detection strips
+
+
+def test_cxx_dropin_layer(dmz, oracle, tmp_path):
+    """A caller written against the reference's dmz.h / scan.h shape, linked with libb200dmz.so."""
+    exe = str(tmp_path / "compat_main")
+    subprocess.check_call(["g++", "-std=c++14", "-O1", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "compat_main.cpp"),
+                           "-o", exe, "-L" + os.path.join(ROOT, "card.io-dmz_b200"), "-lb200dmz",
+                           "-Wl,-rpath," + os.path.join(ROOT, "card.io-dmz_b200"), "-ldl"])
+    frames = deck_frames(16, 8)
+    fin, fout = str(tmp_path / "frames.bin"), str(tmp_path / "out.bin")
+    frames.tofile(fin)
+    subprocess.check_call([exe, fin, "8", "640", "480", fout])
+    dt = np.dtype([("rec", "<i4", 8), ("corners", "<f4", 8), ("scores", "<f4", 160), ("digits", "u1", 16)])
+    got = np.fromfile(fout, dt)
+    want, cards = oracle.process_frames(frames, want_cards=True)
+    assert np.array_equal(got["rec"][:, 0], want["all_found"])
+    assert np.array_equal(bits(got["corners"]), bits(want["corners"]))
+    assert np.array_equal(got["rec"][:, 7].astype(np.uint32), want["card_check"])
+    assert np.array_equal(got["rec"][:, 2], want["usable"]) and np.array_equal(got["rec"][:, 4], want["v_y_offset"])
+    assert np.abs(got["scores"] - want["scores"]).max() <= TOL
+    s = oracle.scanner_new()
+    for k in range(8):
+        oracle.scanner_add_frame(s, cards[k])
+        done, digits = oracle.scanner_result(s)
+        assert got["rec"][k, 5] == int(done)
+        if done:
+            assert got["digits"][k][: len(digits)].tolist() == digits.tolist()
+    oracle.scanner_free(s)

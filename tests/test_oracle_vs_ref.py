@@ -1,0 +1,77 @@
+"""Live, stage-by-stage comparison of the plain-C oracle with the reference's own sources (oracle/_ref).  Skipped
+where oracle/_ref is not built.  This is what pins the oracle beyond the committed fixtures: fresh random inputs."""
+import numpy as np
+import pytest
+
+from util import deck_frames, synthetic_strip
+
+
+def fields(s):
+    out = {}
+    for n, _ in s._fields_:
+        v = getattr(s, n)
+        out[n] = list(v) if hasattr(v, "__len__") else v
+    return out
+
+
+def test_reference_kats(ref):
+    assert ref.lib.ref_run_kats() == 0b1111  # passm_befe75da, passc_5c241121, passc_01266c1b, passc_b00bf70c
+
+
+def test_struct_sizes(ref):
+    # NVerticalSegmentation, NHorizontalSegmentation, NumberScores, dmz_edges, dmz_corner_points
+    assert [ref.lib.ref_sizeof(i) for i in (0, 1, 2, 6, 7)] == [28, 48, 640, 48, 32]
+
+
+def test_detect_stage_random_strips(ref, oracle):
+    rng = np.random.default_rng(11)
+    for t in range(24):
+        vert = t % 2
+        w, h = ((38, 241) if vert else (389, 28)) if t < 16 else (int(rng.integers(8, 80)), int(rng.integers(8, 80)))
+        img = synthetic_strip(rng, w, h, vert, ["edge", "edge", "noise"][t % 3])
+        dxr, dyr = ref.sobel7(img)
+        dxo, dyo = oracle.sobel7(img)
+        assert np.array_equal(dxr, dxo) and np.array_equal(dyr, dyo)
+        er, eo = ref.adaptive_canny(img, dxr, dyr), oracle.adaptive_canny(img, dxr, dyr)
+        assert er[1:] == eo[1:] and np.array_equal(er[0], eo[0])
+        lr, lo = fields(ref.best_line(img, vert)), fields(oracle.best_line(img, vert))
+        lr.pop("max_votes"); lo.pop("max_votes")
+        if not lr["found"]:
+            lr.pop("r"), lr.pop("n"), lo.pop("r"), lo.pop("n")
+        assert lr == lo
+
+
+def test_homography_bits_random(ref, oracle):
+    rng = np.random.default_rng(12)
+    dst = np.array([0, 0, 427, 0, 0, 269, 427, 269], np.float32)
+    for _ in range(3000):
+        src = (np.array([106, 105, 533, 105, 106, 374, 533, 374], np.float32) + rng.uniform(-30, 30, 8)).astype(np.float32)
+        assert np.array_equal(ref.calc_persp_transform(src, dst).view(np.uint32), oracle.calc_persp_transform(src, dst).view(np.uint32))
+
+
+def test_whole_path_deck(ref, oracle):
+    frames = deck_frames(100, 12)
+    rr, rc = ref.process_frames(frames, want_cards=True)
+    po, pc = oracle.process_frames(frames, want_cards=True)
+    assert np.array_equal(rc, pc)
+    for f in ("found", "all_found", "card_check", "v_y_offset", "v_pattern_type", "usable", "upside_down", "h_n_offsets", "h_offsets", "h_pattern_offset"):
+        assert np.array_equal(rr[f], po[f]), f
+    for f in ("corners", "h_score", "h_number_width"):
+        assert np.array_equal(rr[f].view(np.uint32), po[f].view(np.uint32)), f
+    ok = rr["all_found"] == 1
+    assert np.array_equal(rr["rho"][ok].view(np.uint32), po["rho"][ok].view(np.uint32))
+    assert np.abs(rr["scores"] - po["scores"]).max() <= 1e-5
+
+
+def test_chroma_fallback(ref, oracle):
+    """Y plane flat on the left -> the left edge must come from Cb (rho doubled), dmz.cpp:351-367."""
+    f = deck_frames(5, 1)[0]
+    cb = np.ascontiguousarray(f[::2, ::2])  # half-resolution copy with real structure
+    cr = np.full((240, 320), 128, np.uint8)
+    y = f.copy()
+    y[:, :160] = 60  # wipe the left edge from Y only
+    dr, do = ref.detect_edges(y, cb, cr), oracle.detect_edges(y, cb, cr)
+    assert fields(dr)["found"] == fields(do)["found"]
+    assert dr.all_found == do.all_found
+    if dr.all_found:
+        assert np.array_equal(np.array(dr.corners, np.float32).view(np.uint32), np.array(do.corners, np.float32).view(np.uint32))
