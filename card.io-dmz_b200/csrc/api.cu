@@ -29,6 +29,7 @@ struct Lane {
   float *d_vprob = nullptr;
   b200_scan *d_scan = nullptr;
   b200_frame_record *d_records = nullptr;
+  unsigned int *d_check = nullptr;
   int16_t *d_grad = nullptr;
   size_t grad_elems = 0;
 };
@@ -115,10 +116,10 @@ std::string default_weights_dir() {
 
 void free_lane(Lane *l) {
   cudaFree(l->d_frames), cudaFree(l->d_cb), cudaFree(l->d_cr), cudaFree(l->d_lines), cudaFree(l->d_geom);
-  cudaFree(l->d_cards), cudaFree(l->d_vprob), cudaFree(l->d_scan), cudaFree(l->d_records), cudaFree(l->d_grad);
+  cudaFree(l->d_cards), cudaFree(l->d_vprob), cudaFree(l->d_scan), cudaFree(l->d_records), cudaFree(l->d_grad), cudaFree(l->d_check);
   l->d_frames = l->d_cb = l->d_cr = nullptr;
   l->d_lines = nullptr, l->d_geom = nullptr, l->d_cards = nullptr, l->d_vprob = nullptr, l->d_scan = nullptr;
-  l->d_records = nullptr, l->d_grad = nullptr;
+  l->d_records = nullptr, l->d_grad = nullptr, l->d_check = nullptr;
   l->grad_elems = 0;
   l->cap = 0;
 }
@@ -163,6 +164,7 @@ int ensure_capacity(b200_ctx *ctx, Lane *l, int n, int w, int h, bool need_frame
   CU(cudaMalloc(&l->d_vprob, (size_t)cap * (540 * sizeof(float) + 16)));
   CU(cudaMalloc(&l->d_scan, sizeof(b200_scan) * (size_t)cap));
   CU(cudaMalloc(&l->d_records, sizeof(b200_frame_record) * (size_t)cap));
+  CU(cudaMalloc(&l->d_check, sizeof(unsigned int) * (size_t)cap));
   l->cap = cap, l->cap_w = cw, l->cap_h = chh;
   return B200_OK;
 }
@@ -173,7 +175,7 @@ int ensure_grad(b200_ctx *ctx, Lane *l, int n) {
     if (!ctx->dp[p].use_global_grad) continue;
     size_t mx = 0;
     for (int s = 0; s < 4; s++) {
-      size_t v = (size_t)ctx->dp[p].strip[s].w * ctx->dp[p].strip[s].h;
+      size_t v = (size_t)(ctx->dp[p].strip[s].w + 2) * (ctx->dp[p].strip[s].h + 2);
       mx = v > mx ? v : mx;
     }
     size_t e = (size_t)n * 4 * mx * 2;
@@ -242,12 +244,12 @@ int pipeline_on_lane(b200_ctx *ctx, Lane *l, const uint8_t *dy, int drs, size_t 
   int rc = detect_sequence(ctx, l, dy, drs, dfs, nullptr, nullptr, 0, 0, n, timed);
   if (rc) return rc;
   if (timed) CU(cudaEventRecord(ctx->ev[ST_WARP], l->stream));
-  LAUNCH(launch_warp(dy, drs, dfs, width, height, n, l->d_geom, dcards, l->stream));
+  LAUNCH(launch_warp(dy, drs, dfs, width, height, n, l->d_geom, dcards, l->d_check, l->stream));
   cudaEvent_t *ev = timed ? ctx->ev : nullptr;
   LAUNCH(launch_scan(ctx->wts, dcards, n, l->d_geom, nullptr, l->d_vprob, l->d_scan, l->stream,
                      ev ? ev[ST_VSEG] : nullptr, ev ? ev[ST_HSEG] : nullptr, ev ? ev[ST_CATEGORIZE] : nullptr,
                      ev ? ev[ST_FINALIZE] : nullptr));
-  LAUNCH(launch_finalize_records(l->d_geom, l->d_scan, dcards, n, drec, l->stream));
+  LAUNCH(launch_finalize_records(l->d_geom, l->d_scan, l->d_check, n, drec, l->stream));
   if (timed) CU(cudaEventRecord(ctx->ev[ST_COUNT], l->stream));
   return B200_OK;
 }
@@ -425,7 +427,7 @@ int b200_transform_card_batch(b200_ctx *ctx, const uint8_t *sample, int row_stri
   }
   LAUNCH(launch_corners_to_geom(dc, dv, n, orientation, upsample, l->d_geom, l->stream));
   uint8_t *dcards = mem == B200_MEM_DEVICE ? cards : l->d_cards;
-  LAUNCH(launch_warp(ds, drs, dfs, width, height, n, l->d_geom, dcards, l->stream));
+  LAUNCH(launch_warp(ds, drs, dfs, width, height, n, l->d_geom, dcards, nullptr, l->stream));
   if (mem == B200_MEM_HOST) CU(cudaMemcpyAsync(cards, l->d_cards, kCardBytes * n, cudaMemcpyDeviceToHost, l->stream));
   CU(cudaStreamSynchronize(l->stream));
   return B200_OK;

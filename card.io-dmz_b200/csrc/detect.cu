@@ -8,14 +8,16 @@
 // Data flow inside the CTA (everything after the first load stays in shared memory):
 //   global u8 strip --(32-bit coalesced loads)--> s_src[h][w]
 //   Sobel: one work item per (column, row chunk) walks down its rows keeping the last seven row-filter
-//          results for both kernels in registers (no intermediate image) --> s_dx, s_dy (s16)
+//          results for both kernels in registers (no intermediate image) --> s_dx, s_dy (s16, zero-padded border)
 //   thresholds: block reduction (warp shuffles) of the saturated |dx| + |dy| sums, 64-bit exact
-//   NMS: per pixel from s_dx / s_dy --> s_map {0 candidate, 1 no edge, 2 edge}
-//   hysteresis: in-place propagation sweeps to the unique fixed point (= the reference's stack walk)
-//   Hough: shared-memory atomics into a compacted accumulator (only the reachable rho range per angle)
+//   NMS: per pixel from s_dx / s_dy --> s_map {0 candidate, 1 no edge, 2 edge}; candidates go to a work list
+//   hysteresis: propagation over the candidate list to the unique fixed point (= the reference's stack walk)
+//   Hough: gated edge pixels go to a vote list; shared-memory atomics into a compacted accumulator (only the
+//          reachable rho range per angle)
 //   argmax: packed (votes, -(r, n)) 64-bit keys reduced with warp shuffles -> reference scan order r outer,
 //           n inner, strict '>'
-// All integer; the two float comparisons of the gradient gate are IEEE divisions (-fmad=false file).
+// All integer; the float comparisons of the gradient gate are IEEE divisions (-fmad=false file).  No integer
+// division appears inside any per-pixel loop (2-D walks are set up once per thread).
 #include <float.h>
 
 #include "b200_internal.h"
@@ -42,28 +44,49 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
 }
 
 struct SmemLayout {
-  uint8_t *src;
-  int16_t *dx, *dy;
-  uint8_t *map;
-  unsigned int *acc;
+  uint8_t *src;          // h x w source strip
+  int16_t *dx, *dy;      // (h + 2) x (w + 2), zero border: no bounds checks in the NMS neighbourhood
+  uint8_t *map;          // (h + 2) x (w + 2): 0 candidate, 1 no edge (also the border), 2 edge
+  unsigned short *list;  // candidate list (hysteresis), then vote list (Hough): padded pixel indices
+  unsigned int *acc;     // compacted Hough accumulator
 };
 
-__device__ __forceinline__ size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
+__host__ __device__ __forceinline__ size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 
-__global__ void __launch_bounds__(kThreads, 1)
+// Per-thread 2-D walk over a w x h strip without integer division inside the loop:
+//   w <= T: tx = tid % w, ty = tid / w (computed once), rows advance by T / w;  w > T: tx = tid, columns advance by T.
+struct Walk {
+  int tx, ty, xstep, ystep;
+  bool active;
+};
+__device__ __forceinline__ Walk make_walk(int tid, int w, int T) {
+  Walk k;
+  if (w <= T) {
+    k.ystep = T / w;
+    k.ty = tid / w;
+    k.tx = tid - k.ty * w;
+    k.xstep = w;  // a single column per thread
+    k.active = k.ty < k.ystep;
+  } else {
+    k.ystep = 1, k.ty = 0, k.tx = tid, k.xstep = T, k.active = true;
+  }
+  return k;
+}
+
+__global__ void __launch_bounds__(kThreads, 2)
 detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__restrict__ plane, int row_stride,
                      size_t frame_stride, const b200_line *__restrict__ prev_lines, const b200_line *__restrict__ prev_lines2,
-                     b200_line *__restrict__ lines,
-                     int16_t *__restrict__ grad_scratch, size_t grad_scratch_stride) {
+                     b200_line *__restrict__ lines, int16_t *__restrict__ grad_scratch, size_t grad_scratch_stride) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __shared__ unsigned long long s_red[kThreads / 32];
-  __shared__ int s_low, s_high, s_flag;
+  __shared__ int s_low, s_high, s_ncand, s_nvote, s_nedge;
 
   const int strip = blockIdx.x;
   const int frame = blockIdx.y;
   const int tid = threadIdx.x;
   const StripDesc &S = P.strip[strip];
   const int w = S.w, h = S.h, npx = w * h;
+  const int wp = w + 2, npad = wp * (h + 2);
   const size_t out_idx = (size_t)frame * 4 + strip;
 
   // Fallback planes: skip strips whose edge was already found on an earlier plane (dmz.cpp:351).
@@ -87,40 +110,56 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
     L.dy = L.dx + grad_scratch_stride / 2;
   } else {
     L.dx = reinterpret_cast<int16_t *>(smem_raw + off);
-    off = align16(off + (size_t)npx * 2);
+    off = align16(off + (size_t)npad * 2);
     L.dy = reinterpret_cast<int16_t *>(smem_raw + off);
-    off = align16(off + (size_t)npx * 2);
+    off = align16(off + (size_t)npad * 2);
   }
   L.map = smem_raw + off;
-  off = align16(off + (size_t)npx);
+  off = align16(off + (size_t)npad);
+  L.list = reinterpret_cast<unsigned short *>(smem_raw + off);
+  off = align16(off + (size_t)npx * 2);
   L.acc = reinterpret_cast<unsigned int *>(smem_raw + off);
 
-  // ---- 1. load the strip: 32-bit coalesced loads of the covering aligned words
+  // ---- 1. load the strip (32-bit coalesced loads of the covering aligned words); clear borders / accumulator
   {
     const uint8_t *base = plane + (size_t)frame * frame_stride + (size_t)S.y * row_stride + S.x;
     const bool word_ok = ((reinterpret_cast<uintptr_t>(plane) | (uintptr_t)row_stride | (uintptr_t)frame_stride) & 3u) == 0;
     if (word_ok) {
-      const int shift = S.x & 3;                      // bytes of the first word that precede the strip
-      const int words = (shift + w + 3) >> 2;         // words per row
-      for (int i = tid; i < words * h; i += kThreads) {
-        const int row = i / words, k = i - row * words;
-        const unsigned int v = __ldg(reinterpret_cast<const unsigned int *>(base + (size_t)row * row_stride - shift) + k);
-        const int c0 = k * 4 - shift;
-        uint8_t *dst = L.src + row * w;
+      const int shift = S.x & 3;               // bytes of the first word that precede the strip
+      const int words = (shift + w + 3) >> 2;  // words per row
+      const Walk k = make_walk(tid, words, kThreads);
+      if (k.active)
+        for (int row = k.ty; row < h; row += k.ystep)
+          for (int q = k.tx; q < words; q += k.xstep) {
+            const unsigned int v = __ldg(reinterpret_cast<const unsigned int *>(base + (size_t)row * row_stride - shift) + q);
+            const int c0 = q * 4 - shift;
+            uint8_t *dst = L.src + row * w;
 #pragma unroll
-        for (int b = 0; b < 4; b++) {
-          const int c = c0 + b;
-          if (c >= 0 && c < w) dst[c] = (uint8_t)(v >> (8 * b));
-        }
-      }
+            for (int b = 0; b < 4; b++) {
+              const int c = c0 + b;
+              if (c >= 0 && c < w) dst[c] = (uint8_t)(v >> (8 * b));
+            }
+          }
     } else {
-      for (int i = tid; i < npx; i += kThreads) {
-        const int row = i / w, c = i - row * w;
-        L.src[i] = __ldg(base + (size_t)row * row_stride + c);
-      }
+      const Walk k = make_walk(tid, w, kThreads);
+      if (k.active)
+        for (int row = k.ty; row < h; row += k.ystep)
+          for (int c = k.tx; c < w; c += k.xstep) L.src[row * w + c] = __ldg(base + (size_t)row * row_stride + c);
     }
   }
   for (int i = tid; i < S.ncells; i += kThreads) L.acc[i] = 0u;
+  // zero the one-pixel border of dx / dy, mark the border of the map as "no edge"
+  for (int i = tid; i < wp; i += kThreads) {
+    const int j = (h + 1) * wp + i;
+    L.dx[i] = 0, L.dy[i] = 0, L.map[i] = 1;
+    L.dx[j] = 0, L.dy[j] = 0, L.map[j] = 1;
+  }
+  for (int y = tid; y < h; y += kThreads) {
+    const int a = (y + 1) * wp, b = a + wp - 1;
+    L.dx[a] = 0, L.dy[a] = 0, L.map[a] = 1;
+    L.dx[b] = 0, L.dy[b] = 0, L.map[b] = 1;
+  }
+  if (tid == 0) s_ncand = 0, s_nvote = 0, s_nedge = 0;
   __syncthreads();
 
   // ---- 2. Sobel-7 dx, dy with a register sliding window; accumulate the saturated |.| sums on the fly
@@ -131,24 +170,23 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
       const int chunk = it / w, x = it - chunk * w;
       const int y0 = chunk * S.chunk_rows;
       const int y1 = min(h, y0 + S.chunk_rows);
-      // column offsets with BORDER_REPLICATE at the ROI edge
-      int xo[7];
+      int xo[7];  // column offsets with BORDER_REPLICATE at the ROI edge
 #pragma unroll
       for (int k = 0; k < 7; k++) xo[k] = clampi(x + k - 3, 0, w - 1);
       int hx[7], sx[7];  // row-filter results of the last seven rows: derivative taps, smoothing taps
-      // prime with rows y0-3 .. y0+2 (clamped)
 #pragma unroll
-      for (int k = 0; k < 6; k++) {
+      for (int k = 0; k < 6; k++) {  // prime with rows y0-3 .. y0+2 (clamped)
         const uint8_t *r = L.src + clampi(y0 + k - 3, 0, h - 1) * w;
         const int p0 = r[xo[0]], p1 = r[xo[1]], p2 = r[xo[2]], p3 = r[xo[3]], p4 = r[xo[4]], p5 = r[xo[5]], p6 = r[xo[6]];
-        hx[k + 1] = (p6 - p0) + 4 * (p5 - p1) + 5 * (p4 - p2);                       // [-1,-4,-5,0,5,4,1]
-        sx[k + 1] = (p0 + p6) + 6 * (p1 + p5) + 15 * (p2 + p4) + 20 * p3;            // [1,6,15,20,15,6,1]
+        hx[k + 1] = (p6 - p0) + 4 * (p5 - p1) + 5 * (p4 - p2);             // [-1,-4,-5,0,5,4,1]
+        sx[k + 1] = (p0 + p6) + 6 * (p1 + p5) + 15 * (p2 + p4) + 20 * p3;  // [1,6,15,20,15,6,1]
       }
-      for (int y = y0; y < y1; y++) {
+      int o = (y0 + 1) * wp + x + 1;
+      for (int y = y0; y < y1; y++, o += wp) {
 #pragma unroll
         for (int k = 0; k < 6; k++) hx[k] = hx[k + 1], sx[k] = sx[k + 1];
         {
-          const uint8_t *r = L.src + clampi(y + 3, 0, h - 1) * w;
+          const uint8_t *r = L.src + min(y + 3, h - 1) * w;
           const int p0 = r[xo[0]], p1 = r[xo[1]], p2 = r[xo[2]], p3 = r[xo[3]], p4 = r[xo[4]], p5 = r[xo[5]], p6 = r[xo[6]];
           hx[6] = (p6 - p0) + 4 * (p5 - p1) + 5 * (p4 - p2);
           sx[6] = (p0 + p6) + 6 * (p1 + p5) + 15 * (p2 + p4) + 20 * p3;
@@ -157,8 +195,8 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
         int gy = (sx[6] - sx[0]) + 4 * (sx[5] - sx[1]) + 5 * (sx[4] - sx[2]);               // derivative down the column
         gx = clampi(gx, -32768, 32767);  // saturate_cast<short>
         gy = clampi(gy, -32768, 32767);
-        L.dx[y * w + x] = (int16_t)gx;
-        L.dy[y * w + x] = (int16_t)gy;
+        L.dx[o] = (int16_t)gx;
+        L.dy[o] = (int16_t)gy;
         abs_sum += (unsigned)min(abs(gx), 32767) + (unsigned)min(abs(gy), 32767);  // cvAbs saturates, canny.cpp:355-361
       }
     }
@@ -177,93 +215,99 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
   __syncthreads();
   const int low = s_low, high = s_high;
 
-  // ---- 4. non-maxima suppression, canny.cpp:220-285 (zero magnitude outside the ROI)
-  for (int i = tid; i < npx; i += kThreads) {
-    const int y = i / w, x = i - y * w;
-    const int gx = L.dx[i], gy = L.dy[i];
-    const int m = abs(gx) + abs(gy);
-    uint8_t out = 1;
-    if (m > low) {
-      auto mag = [&](int yy, int xx) -> int {
-        if (xx < 0 || xx >= w || yy < 0 || yy >= h) return 0;
-        const int j = yy * w + xx;
-        return abs((int)L.dx[j]) + abs((int)L.dy[j]);
-      };
-      const long long ax = abs(gx), ay = abs(gy);
-      const long long tg22x = ax * 13573;  // TG22 = (int)(0.41421356 * 2^15 + 0.5)
-      const long long tg67x = tg22x + ((ax + ax) << 15);
-      const long long ys = ay << 15;
-      bool is_max;
-      if (ys < tg22x) {
-        is_max = m > mag(y, x - 1) && m >= mag(y, x + 1);
-      } else if (ys > tg67x) {
-        is_max = m > mag(y - 1, x) && m >= mag(y + 1, x);
-      } else {
-        const int s = ((gx ^ gy) < 0) ? -1 : 1;
-        is_max = m > mag(y - 1, x - s) && m > mag(y + 1, x + s);
-      }
-      if (is_max) out = (m > high) ? 2 : 0;
-    }
-    L.map[i] = out;
+  // ---- 4. non-maxima suppression, canny.cpp:220-285; candidates are appended to the hysteresis work list
+  {
+    const Walk k = make_walk(tid, w, kThreads);
+    if (k.active)
+      for (int y = k.ty; y < h; y += k.ystep)
+        for (int x = k.tx; x < w; x += k.xstep) {
+          const int o = (y + 1) * wp + x + 1;
+          const int gx = L.dx[o], gy = L.dy[o];
+          const int m = abs(gx) + abs(gy);
+          uint8_t out = 1;
+          if (m > low) {
+            auto mag = [&](int j) -> int { return abs((int)L.dx[j]) + abs((int)L.dy[j]); };
+            const long long ax = abs(gx), ay = abs(gy);
+            const long long tg22x = ax * 13573;  // TG22 = (int)(0.41421356 * 2^15 + 0.5)
+            const long long tg67x = tg22x + ((ax + ax) << 15);
+            const long long ys = ay << 15;
+            bool is_max;
+            if (ys < tg22x) {
+              is_max = m > mag(o - 1) && m >= mag(o + 1);
+            } else if (ys > tg67x) {
+              is_max = m > mag(o - wp) && m >= mag(o + wp);
+            } else {
+              const int s = ((gx ^ gy) < 0) ? -1 : 1;
+              is_max = m > mag(o - wp - s) && m > mag(o + wp + s);
+            }
+            if (is_max) {
+              if (m > high) {
+                out = 2;
+              } else {
+                out = 0;
+                L.list[atomicAdd(&s_ncand, 1)] = (unsigned short)o;
+              }
+            }
+          }
+          L.map[o] = out;
+        }
   }
   __syncthreads();
 
-  // ---- 5. hysteresis: candidates 8-connected to an edge pixel become edge pixels; sweep to the fixed point.
-  // Each thread owns a run of consecutive pixels along the strip's long axis and sweeps it forwards and
-  // backwards, so a chain crossing a run is absorbed in one iteration.
+  // ---- 5. hysteresis: a candidate 8-connected to an edge pixel becomes an edge pixel; iterate over the (short)
+  // candidate list to the fixed point, which is the reference's stack-walk result whatever the visiting order.
   {
-    const int run = (npx + kThreads - 1) / kThreads;
-    const int k0 = tid * run, k1 = min(npx, k0 + run);
-    const bool colmajor = h > w;
-    auto touch = [&](int k) -> bool {
-      int x, y;
-      if (colmajor) {
-        x = k / h;
-        y = k - x * h;
-      } else {
-        y = k / w;
-        x = k - y * w;
-      }
-      const int i = y * w + x;
-      if (L.map[i] != 0) return false;
-      bool hit = false;
-#pragma unroll
-      for (int dyy = -1; dyy <= 1; dyy++) {
-        const int yy = y + dyy;
-        if (yy < 0 || yy >= h) continue;
-#pragma unroll
-        for (int dxx = -1; dxx <= 1; dxx++) {
-          const int xx = x + dxx;
-          if (xx < 0 || xx >= w) continue;
-          hit |= (L.map[yy * w + xx] == 2);
-        }
-      }
-      if (hit) L.map[i] = 2;
-      return hit;
-    };
+    const int ncand = s_ncand;
     while (true) {
       int changed = 0;
-      for (int k = k0; k < k1; k++) changed |= touch(k);
-      for (int k = k1 - 1; k >= k0; k--) changed |= touch(k);
+      for (int c = tid; c < ncand; c += kThreads) {
+        const int o = L.list[c];
+        const uint8_t *m = L.map + o;
+        if (*m != 0) continue;
+        const bool hit = m[-wp - 1] == 2 || m[-wp] == 2 || m[-wp + 1] == 2 || m[-1] == 2 || m[1] == 2 || m[wp - 1] == 2 ||
+                         m[wp] == 2 || m[wp + 1] == 2;
+        if (hit) {
+          L.map[o] = 2;
+          changed = 1;
+        }
+      }
       if (!__syncthreads_or(changed)) break;
     }
   }
 
-  // ---- 6. gradient-gated Hough votes, hough.cpp:126-160
-  int n_edge = 0;
-  for (int i = tid; i < npx; i += kThreads) {
-    if (L.map[i] != 2) continue;
-    n_edge++;
-    const int y = i / w, x = i - y * w;
-    const int del_x = L.dx[i], del_y = L.dy[i];
-    bool use;
-    if (del_x != 0) {
-      const float slope = (float)del_y / (float)del_x;
-      use = S.vertical ? (slope >= S.slope_a && slope <= S.slope_b) : (slope >= S.slope_a || slope <= S.slope_b);
-    } else {
-      use = !S.vertical;
-    }
-    if (use) {
+  // ---- 6. vote list: edge pixels that pass the gradient-direction gate, hough.cpp:126-150 (the candidate list is
+  // dead after the fixed point, its storage is reused)
+  {
+    const Walk k = make_walk(tid, w, kThreads);
+    int n_edge = 0;
+    if (k.active)
+      for (int y = k.ty; y < h; y += k.ystep)
+        for (int x = k.tx; x < w; x += k.xstep) {
+          const int o = (y + 1) * wp + x + 1;
+          if (L.map[o] != 2) continue;
+          n_edge++;
+          const int del_x = L.dx[o], del_y = L.dy[o];
+          bool use;
+          if (del_x != 0) {
+            const float slope = (float)del_y / (float)del_x;
+            use = S.vertical ? (slope >= S.slope_a && slope <= S.slope_b) : (slope >= S.slope_a || slope <= S.slope_b);
+          } else {
+            use = !S.vertical;
+          }
+          if (use) L.list[atomicAdd(&s_nvote, 1)] = (unsigned short)o;
+        }
+    n_edge = (int)warp_sum_u64((unsigned long long)n_edge);
+    if ((tid & 31) == 0 && n_edge) atomicAdd(&s_nedge, n_edge);
+  }
+  __syncthreads();
+
+  // ---- 7. votes, hough.cpp:152-158: shared-memory atomics on the compacted accumulator
+  {
+    const int nvote = s_nvote;
+    for (int e = tid; e < nvote; e += kThreads) {
+      const int o = L.list[e];
+      const int yy = o / wp;
+      const int x = o - yy * wp - 1, y = yy - 1;
 #pragma unroll
       for (int n = 0; n < B200_NUMANGLE; n++) {
         const int r = ((x * S.tab_cos[n] + y * S.tab_sin[n]) >> 10) + S.half;
@@ -271,19 +315,9 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
       }
     }
   }
-  {
-    unsigned long long ne = warp_sum_u64((unsigned long long)n_edge);
-    __syncthreads();  // votes complete; s_red free again
-    if ((tid & 31) == 0) s_red[tid >> 5] = ne;
-  }
   __syncthreads();
-  if (tid == 0) {
-    unsigned long long tot = 0;
-    for (int i = 0; i < kThreads / 32; i++) tot += s_red[i];
-    s_flag = (int)tot;
-  }
 
-  // ---- 7. argmax in the reference's scan order (r outer, n inner, first strict maximum), hough.cpp:165-176
+  // ---- 8. argmax in the reference's scan order (r outer, n inner, first strict maximum), hough.cpp:165-176
   unsigned long long best = 0;
   for (int n = 0; n < B200_NUMANGLE; n++) {
     for (int c = tid; c < S.rcount[n]; c += kThreads) {
@@ -295,15 +329,14 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
     }
   }
   best = warp_max_u64(best);
-  __syncthreads();  // s_flag written, s_red reads done
-  if ((tid & 31) == 0) s_red[tid >> 5] = best;
+  if ((tid & 31) == 0) s_red[tid >> 5] = best;  // s_red's threshold use ended several barriers ago
   __syncthreads();
   if (tid == 0) {
     unsigned long long b = 0;
     for (int i = 0; i < kThreads / 32; i++) b = s_red[i] > b ? s_red[i] : b;
     b200_line l;
     l.max_votes = (int)(b >> 32);
-    l.low = low, l.high = high, l.n_edge_px = s_flag;
+    l.low = low, l.high = high, l.n_edge_px = s_nedge;
     l.found = 0, l.r = 0, l.n = 0, l.rho = FLT_MAX, l.theta = FLT_MAX;
     if (l.max_votes > S.threshold) {
       const unsigned int rn = 0xFFFFFFFFu - (unsigned int)(b & 0xFFFFFFFFu);
@@ -323,9 +356,9 @@ size_t detect_smem_bytes(const DetectParams &p) {
   size_t worst = 0;
   for (int s = 0; s < 4; s++) {
     const StripDesc &d = p.strip[s];
-    size_t npx = (size_t)d.w * d.h;
-    size_t b = ((npx + 15) & ~(size_t)15) * 2;  // src + map
-    if (!p.use_global_grad) b += (((npx * 2) + 15) & ~(size_t)15) * 2;
+    const size_t npx = (size_t)d.w * d.h, npad = (size_t)(d.w + 2) * (d.h + 2);
+    size_t b = align16(npx) + align16(npad) + align16(npx * 2);  // src, map, list
+    if (!p.use_global_grad) b += 2 * align16(npad * 2);
     b += (size_t)d.ncells * 4 + 64;
     worst = b > worst ? b : worst;
   }
@@ -333,25 +366,27 @@ size_t detect_smem_bytes(const DetectParams &p) {
 }
 
 int launch_detect(const DetectParams &p, const uint8_t *plane, int row_stride, size_t frame_stride, int n,
-                  const b200_line *prev_lines, const b200_line *prev_lines2, b200_line *lines, int16_t *grad_scratch, cudaStream_t s) {
+                  const b200_line *prev_lines, const b200_line *prev_lines2, b200_line *lines, int16_t *grad_scratch,
+                  cudaStream_t s) {
   size_t smem = detect_smem_bytes(p);
   static size_t configured = 0;
   if (smem > configured) {
     if (cudaFuncSetAttribute(detect_strips_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
     configured = smem;
   }
-  size_t max_npx = 0;
+  size_t max_npad = 0;
   for (int i = 0; i < 4; i++) {
-    size_t v = (size_t)p.strip[i].w * p.strip[i].h;
-    max_npx = v > max_npx ? v : max_npx;
+    size_t v = (size_t)(p.strip[i].w + 2) * (p.strip[i].h + 2);
+    max_npad = v > max_npad ? v : max_npad;
   }
-  // y is limited to 65535 blocks: split very large batches
+  // grid.y is limited to 65535 blocks: split very large batches
   int launches = 0;
   for (int f0 = 0; f0 < n; f0 += 65535) {
     int cnt = n - f0 < 65535 ? n - f0 : 65535;
     detect_strips_kernel<<<dim3(4, cnt), kThreads, smem, s>>>(
-        p, plane + (size_t)f0 * frame_stride, row_stride, frame_stride, prev_lines ? prev_lines + (size_t)f0 * 4 : nullptr, prev_lines2 ? prev_lines2 + (size_t)f0 * 4 : nullptr,
-        lines + (size_t)f0 * 4, grad_scratch ? grad_scratch + (size_t)f0 * 4 * max_npx * 2 : nullptr, max_npx * 2);
+        p, plane + (size_t)f0 * frame_stride, row_stride, frame_stride, prev_lines ? prev_lines + (size_t)f0 * 4 : nullptr,
+        prev_lines2 ? prev_lines2 + (size_t)f0 * 4 : nullptr, lines + (size_t)f0 * 4,
+        grad_scratch ? grad_scratch + (size_t)f0 * 4 * max_npad * 2 : nullptr, max_npad * 2);
     launches++;
   }
   return cudaGetLastError() == cudaSuccess ? launches : -1;

@@ -274,50 +274,52 @@ __device__ __forceinline__ int warp_sample(const uint8_t *__restrict__ src, int 
                                            double X0, double Y0, double W0, int x1) {
   double W = W0 + M[6] * x1;
   W = W != 0.0 ? 32. / W : 0.0;
-  double fX = (X0 + M[0] * x1) * W;
-  double fY = (Y0 + M[3] * x1) * W;
-  fX = fX < -2147483648.0 ? -2147483648.0 : (fX > 2147483647.0 ? 2147483647.0 : fX);
-  fY = fY < -2147483648.0 ? -2147483648.0 : (fY > 2147483647.0 ? 2147483647.0 : fY);
+  const double fX = (X0 + M[0] * x1) * W;
+  const double fY = (Y0 + M[3] * x1) * W;
+  // saturate_cast<int>(clamp(f, INT_MIN, INT_MAX)): cvt.rni.s32.f64 rounds half-to-even and saturates at the int range
   const int X = __double2int_rn(fX), Y = __double2int_rn(fY);
-  int sx = X >> 5, sy = Y >> 5;
-  sx = sx < -32768 ? -32768 : (sx > 32767 ? 32767 : sx);  // saturate_cast<short>
-  sy = sy < -32768 ? -32768 : (sy > 32767 ? 32767 : sy);
+  const int sx = max(-32768, min(32767, X >> 5));  // saturate_cast<short>
+  const int sy = max(-32768, min(32767, Y >> 5));
   const int fx = X & 31, fy = Y & 31;
   int w00 = (32 - fx) * (32 - fy) * 32, w01 = fx * (32 - fy) * 32, w10 = (32 - fx) * fy * 32, w11 = fx * fy * 32;
   if ((fx | fy) == 0) w00 = 32767, w11 = 1;  // initInterTab2D saturate/compensate quirk at (0,0)
   int v0, v1, v2, v3;
   if ((unsigned)sx < (unsigned)(sw - 1) && (unsigned)sy < (unsigned)(sh - 1)) {
-    const uint8_t *p = src + (size_t)sy * row_stride + sx;
+    const uint8_t *p = src + (sy * row_stride + sx);  // 32-bit offset inside one frame
     v0 = __ldg(p), v1 = __ldg(p + 1), v2 = __ldg(p + row_stride), v3 = __ldg(p + row_stride + 1);
   } else if (sx >= sw || sx + 1 < 0 || sy >= sh || sy + 1 < 0) {
     return 0;
   } else {
     const bool x0ok = sx >= 0 && sx < sw, x1ok = sx + 1 >= 0 && sx + 1 < sw;
     const bool y0ok = sy >= 0 && sy < sh, y1ok = sy + 1 >= 0 && sy + 1 < sh;
-    v0 = (x0ok && y0ok) ? __ldg(src + (size_t)sy * row_stride + sx) : 0;
-    v1 = (x1ok && y0ok) ? __ldg(src + (size_t)sy * row_stride + sx + 1) : 0;
-    v2 = (x0ok && y1ok) ? __ldg(src + (size_t)(sy + 1) * row_stride + sx) : 0;
-    v3 = (x1ok && y1ok) ? __ldg(src + (size_t)(sy + 1) * row_stride + sx + 1) : 0;
+    v0 = (x0ok && y0ok) ? __ldg(src + (sy * row_stride + sx)) : 0;
+    v1 = (x1ok && y0ok) ? __ldg(src + (sy * row_stride + sx + 1)) : 0;
+    v2 = (x0ok && y1ok) ? __ldg(src + ((sy + 1) * row_stride + sx)) : 0;
+    v3 = (x1ok && y1ok) ? __ldg(src + ((sy + 1) * row_stride + sx + 1)) : 0;
   }
   const int v = (v0 * w00 + v1 * w01 + v2 * w10 + v3 * w11 + (1 << 14)) >> 15;
-  return v < 0 ? 0 : (v > 255 ? 255 : v);
+  return min(255, max(0, v));
 }
 
+// card_check (optional): per-frame checksum sum_i (i + 1) * card[i] mod 2^32, accumulated while the pixels are
+// still in registers (one global atomic per CTA) so that no later stage has to re-read the card for it.
 __global__ void __launch_bounds__(256)
 warp_kernel(const uint8_t *__restrict__ src, int row_stride, size_t frame_stride, int sw, int sh,
-            const FrameGeom *__restrict__ geom, uint8_t *__restrict__ cards) {
+            const FrameGeom *__restrict__ geom, uint8_t *__restrict__ cards, unsigned int *__restrict__ card_check) {
   const int frame = blockIdx.y;
   const int row0 = blockIdx.x * kWarpRows;
   __shared__ double sM[9];
   __shared__ int s_ok;
+  __shared__ unsigned int s_sum;
   if (threadIdx.x < 9) sM[threadIdx.x] = geom[frame].Minv[threadIdx.x];
-  if (threadIdx.x == 0) s_ok = geom[frame].all_found;
+  if (threadIdx.x == 0) s_ok = geom[frame].all_found, s_sum = 0u;
   __syncthreads();
   uint8_t *dst = cards + (size_t)frame * (B200_CARD_W * B200_CARD_H);
   const uint8_t *s = src + (size_t)frame * frame_stride;
   const int nrows = min(kWarpRows, B200_CARD_H - row0);
-  for (int i = threadIdx.x; i < nrows * kQuadsPerRow; i += blockDim.x) {
-    const int r = i / kQuadsPerRow, q = i - r * kQuadsPerRow;
+  unsigned int sum = 0;
+  int r = threadIdx.x / kQuadsPerRow, q = threadIdx.x - r * kQuadsPerRow;  // 256 = 2 * 107 + 42
+  for (; r < nrows;) {
     const int y = row0 + r, x = q * 4;
     unsigned int packed = 0;
     if (s_ok) {
@@ -325,10 +327,26 @@ warp_kernel(const uint8_t *__restrict__ src, int row_stride, size_t frame_stride
       const double X0 = sM[0] * xb + sM[1] * y + sM[2];
       const double Y0 = sM[3] * xb + sM[4] * y + sM[5];
       const double W0 = sM[6] * xb + sM[7] * y + sM[8];
+      const unsigned int base = (unsigned)(y * B200_CARD_W + x) + 1u;
 #pragma unroll
-      for (int k = 0; k < 4; k++) packed |= (unsigned)warp_sample(s, row_stride, sw, sh, sM, X0, Y0, W0, x + k - xb) << (8 * k);
+      for (int k = 0; k < 4; k++) {
+        const unsigned int v = (unsigned)warp_sample(s, row_stride, sw, sh, sM, X0, Y0, W0, x + k - xb);
+        packed |= v << (8 * k);
+        sum += (base + k) * v;
+      }
     }
-    *reinterpret_cast<unsigned int *>(dst + (size_t)y * B200_CARD_W + x) = packed;
+    *reinterpret_cast<unsigned int *>(dst + y * B200_CARD_W + x) = packed;
+    // advance by blockDim.x = 256 quads = 2 rows + 42 quads, without a division
+    q += 256 - 2 * kQuadsPerRow;
+    r += 2;
+    if (q >= kQuadsPerRow) q -= kQuadsPerRow, r += 1;
+  }
+  if (card_check != nullptr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if ((threadIdx.x & 31) == 0 && sum) atomicAdd(&s_sum, sum);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_sum) atomicAdd(&card_check[frame], s_sum);
   }
 }
 
@@ -427,12 +445,15 @@ hseg_kernel(const uint8_t *__restrict__ cards, int n, b200_scan *__restrict__ sc
   __shared__ b200_hseg s_best;
   __shared__ uint8_t s_pat[19];
   __shared__ int s_npl;
+  __shared__ float s_tpl[64];                           // the 19-tap template followed by zeros
+  __shared__ short s_centers[kHsegThreads / 8][18];     // digit centres of the candidates in flight (+ sentinel)
 
   const int y_off = sc->vseg.y_offset;
   const uint8_t *card = cards + (size_t)f * (B200_CARD_W * B200_CARD_H) + (size_t)y_off * B200_CARD_W;
   for (int i = tid; i < 27 * B200_CARD_W / 4; i += kHsegThreads)
     reinterpret_cast<unsigned int *>(&s_strip[0][0])[i] = __ldg(reinterpret_cast<const unsigned int *>(card) + i);
   if (tid < 19) s_pat[tid] = sc->vseg.number_pattern[tid];
+  if (tid < 64) s_tpl[tid] = tid < 19 ? kNumberGradSumPattern[tid] : 0.0f;
   if (tid == 0) {
     s_npl = sc->vseg.number_pattern_length;
     s_mn = 0x7fffffff, s_mx = 0;
@@ -512,11 +533,12 @@ hseg_kernel(const uint8_t *__restrict__ cards, int n, b200_scan *__restrict__ sc
     // eight lanes per candidate reproduce Eigen's two 4-lane packet accumulators over the 428 coefficients
     const int lane8 = tid & 7;
     for (int c0 = 0; c0 < total; c0 += kHsegThreads / 8) {
-      const int c = c0 + (tid >> 3);
+      const int slot = tid >> 3;
+      const int c = c0 + slot;
       float score = 0.0f;
       bool valid = c < total;
-      int centers[16];
       int nd = 0;
+      __syncthreads();  // previous round's centres consumed
       if (valid) {
         int wi = 0;
         while (c >= s_pass.start[wi + 1]) wi++;
@@ -526,23 +548,31 @@ hseg_kernel(const uint8_t *__restrict__ cards, int n, b200_scan *__restrict__ sc
           if (s_pat[pi]) {
             const int center = (uint16_t)(offset + __float2int_rn((float)pi * width));
             if (!(center + 19 < 428)) valid = false;
-            if (nd < 16) centers[nd] = center;
+            if (nd < 16 && lane8 == 0) s_centers[slot][nd] = (short)center;
             nd++;
           }
         }
+        if (nd > 16) nd = 16;
+        if (lane8 == 0) s_centers[slot][nd] = 32767;  // sentinel: no further digit
       }
-      if (nd > 16) nd = 16;
+      __syncthreads();
       // (valid is uniform across the eight lanes of a candidate; the shuffles stay outside any branch)
-      int d = -1;  // last digit whose template starts at or before i
+      // Walk i = lane8, lane8 + 8, ...: `cur` is the centre of the last digit starting at or before i, `nxt` the
+      // next centre.  Centres are >= 17 apart and i advances by 8, so at most one digit boundary is crossed per step.
+      int d = 0, cur = -1000, nxt = valid ? s_centers[slot][0] : 32767;
       auto coeff = [&](int i) -> float {
-        while (d + 1 < nd && centers[d + 1] <= i) d++;
-        float p = 0.0f;
-        if (d >= 0 && i - centers[d] < 19) p = kNumberGradSumPattern[i - centers[d]];
-        return fabsf(s_g[i] - p);
+        if (i >= nxt) {
+          cur = nxt;
+          d++;
+          nxt = s_centers[slot][d];
+        }
+        const int rel = min(i - cur, 63);  // >= 19 -> zero tail of the table
+        return fabsf(s_g[i] - s_tpl[rel]);
       };
       float acc = 0.0f;
       if (valid) {
         acc = coeff(lane8);
+#pragma unroll 4
         for (int k = 1; k < 53; k++) acc = acc + coeff(8 * k + lane8);
       }
       const float hi = __shfl_down_sync(0xffffffffu, acc, 4, 8);
@@ -607,40 +637,26 @@ __global__ void scan_finish_kernel(int n, b200_scan *__restrict__ scans) {
   sc->usable = number_score < 3.0f;
 }
 
-// Flat per-frame record + card checksum sum_i (i+1) * card[i] (mod 2^32).  One CTA per frame.
-__global__ void __launch_bounds__(256)
-finalize_records_kernel(const FrameGeom *__restrict__ geom, const b200_scan *__restrict__ scans,
-                        const uint8_t *__restrict__ cards, b200_frame_record *__restrict__ recs) {
-  const int f = blockIdx.x;
-  const int tid = threadIdx.x;
-  __shared__ unsigned int s_red[8];
+// Flat per-frame record; the card checksum was accumulated by the warp kernel.  One thread per frame.
+__global__ void finalize_records_kernel(const FrameGeom *__restrict__ geom, const b200_scan *__restrict__ scans,
+                                        const unsigned int *__restrict__ card_check, int n, b200_frame_record *__restrict__ recs) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n) return;
   const FrameGeom &g = geom[f];
-  unsigned int sum = 0;
+  b200_frame_record *r = recs + f;
+  for (int i = 0; i < 4; i++) r->found[i] = g.found[i], r->rho[i] = g.rho[i], r->theta[i] = g.theta[i];
+  for (int i = 0; i < 8; i++) r->corners[i] = g.corners[i];
+  r->all_found = g.all_found;
+  const uint4 *src = reinterpret_cast<const uint4 *>(scans + f);  // sizeof(b200_scan) == 720 == 45 x 16
+  uint4 *dst = reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(r) + 84);  // offsetof(b200_frame_record, scan), 4-aligned only
+  unsigned int *dw = reinterpret_cast<unsigned int *>(dst);
+  const unsigned int *sw_ = reinterpret_cast<const unsigned int *>(src);
   if (g.all_found) {
-    const unsigned int *c = reinterpret_cast<const unsigned int *>(cards + (size_t)f * (B200_CARD_W * B200_CARD_H));
-    for (int i = tid; i < B200_CARD_W * B200_CARD_H / 4; i += 256) {
-      const unsigned int v = __ldg(c + i);
-      const unsigned int base = 4u * (unsigned)i + 1u;
-      sum += base * (v & 255u) + (base + 1u) * ((v >> 8) & 255u) + (base + 2u) * ((v >> 16) & 255u) + (base + 3u) * (v >> 24);
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  if ((tid & 31) == 0) s_red[tid >> 5] = sum;
-  __syncthreads();
-  if (tid == 0) {
-    unsigned int tot = 0;
-    for (int i = 0; i < 8; i++) tot += s_red[i];
-    b200_frame_record r;
-    memset(&r, 0, sizeof(r));
-    for (int i = 0; i < 4; i++) r.found[i] = g.found[i], r.rho[i] = g.rho[i], r.theta[i] = g.theta[i];
-    for (int i = 0; i < 8; i++) r.corners[i] = g.corners[i];
-    r.all_found = g.all_found;
-    if (g.all_found) {
-      r.scan = scans[f];
-      r.card_check = tot;
-    }
-    recs[f] = r;
+    for (int i = 0; i < 180; i++) dw[i] = sw_[i];
+    r->card_check = card_check[f];
+  } else {
+    for (int i = 0; i < 180; i++) dw[i] = 0u;
+    r->card_check = 0u;
   }
 }
 
@@ -674,21 +690,23 @@ int launch_corners_to_geom(const b200_corner_points *corners, const uint8_t *val
 }
 
 int launch_warp(const uint8_t *src, int row_stride, size_t frame_stride, int w, int h, int n, const FrameGeom *geom,
-                uint8_t *cards, cudaStream_t s) {
+                uint8_t *cards, unsigned int *card_check, cudaStream_t s) {
+  if (card_check && cudaMemsetAsync(card_check, 0, sizeof(unsigned int) * (size_t)n, s) != cudaSuccess) return -1;
   int launches = 0;
   const int row_blocks = (B200_CARD_H + kWarpRows - 1) / kWarpRows;
   for (int f0 = 0; f0 < n; f0 += 65535) {
     const int cnt = n - f0 < 65535 ? n - f0 : 65535;
     warp_kernel<<<dim3(row_blocks, cnt), 256, 0, s>>>(src + (size_t)f0 * frame_stride, row_stride, frame_stride, w, h, geom + f0,
-                                                      cards + (size_t)f0 * (B200_CARD_W * B200_CARD_H));
+                                                      cards + (size_t)f0 * (B200_CARD_W * B200_CARD_H),
+                                                      card_check ? card_check + f0 : nullptr);
     launches++;
   }
   return cudaGetLastError() == cudaSuccess ? launches : -1;
 }
 
-int launch_finalize_records(const FrameGeom *geom, const b200_scan *scans, const uint8_t *cards, int n,
+int launch_finalize_records(const FrameGeom *geom, const b200_scan *scans, const unsigned int *card_check, int n,
                             b200_frame_record *recs, cudaStream_t s) {
-  finalize_records_kernel<<<n, 256, 0, s>>>(geom, scans, cards, recs);
+  finalize_records_kernel<<<blocks_for(n, 128), 128, 0, s>>>(geom, scans, card_check, n, recs);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

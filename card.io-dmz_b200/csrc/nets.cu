@@ -36,16 +36,17 @@ __constant__ float c_conv_b[3][8];
 // ------------------------------------------------------------------------------------------------
 constexpr int kVThreads = 256;
 constexpr int kVRows = 32;
-constexpr int kVStride = 205;  // odd stride: conflict-free column walks
+constexpr int kVStride = 212;  // 53 16-byte units per row (odd): conflict-free LDS.128 across hidden units
 constexpr int kFineSlots = 43; // rows [y0 - 8, y0 + 35)
 
 struct VsegSmem {
-  float w1[50 * kVStride];
+  alignas(16) float w1[50 * kVStride];
   float b1[50];
   float w2[3 * 50];
   float b2[3];
-  float x[kVRows][204];
+  alignas(16) float x[kVRows][204];
   float h[kVRows][52];
+  alignas(4) uint8_t raw[kVThreads / 32][412];  // one staged card row (408 px) per warp
   int item_frame[kVRows];
   int item_row[kVRows];
 };
@@ -104,6 +105,15 @@ vseg_rows_kernel(const float *__restrict__ wts, const uint8_t *__restrict__ card
         continue;
       }
       const uint8_t *src = cards + (size_t)fr * kCardBytes + (size_t)S.item_row[r] * B200_CARD_W + 10;
+      // stage the 408-byte row with coalesced 16-bit loads (the row starts at an even, not 4-aligned, offset)
+      uint8_t *raw = S.raw[warp];
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < 7; q++) {
+        const int k = lane + 32 * q;
+        if (k < 204) reinterpret_cast<unsigned short *>(raw)[k] = __ldg(reinterpret_cast<const unsigned short *>(src) + k);
+      }
+      __syncwarp();
       // ROI (10, row, 408, 1): 3-tap max - min with replicate at the ROI edge, then (a + b + 1) >> 1
       int vals[7];
       int mn = 255, mx = 0;
@@ -113,7 +123,7 @@ vseg_rows_kernel(const float *__restrict__ wts, const uint8_t *__restrict__ card
         int v = 0;
         if (k < 204) {
           const int j0 = 2 * k, j1 = 2 * k + 1;
-          const int a = __ldg(src + (j0 > 0 ? j0 - 1 : 0)), b = __ldg(src + j0), c = __ldg(src + j1), d = __ldg(src + (j1 < 407 ? j1 + 1 : 407));
+          const int a = raw[j0 > 0 ? j0 - 1 : 0], b = raw[j0], c = raw[j1], d = raw[j1 < 407 ? j1 + 1 : 407];
           const int g0 = max(a, max(b, c)) - min(a, min(b, c));
           const int g1 = max(b, max(c, d)) - min(b, min(c, d));
           v = (g0 + g1 + 1) >> 1;
@@ -147,13 +157,19 @@ vseg_rows_kernel(const float *__restrict__ wts, const uint8_t *__restrict__ card
       float acc[7];
 #pragma unroll
       for (int q = 0; q < 7; q++) acc[q] = 0.0f;
-      const float *w = S.w1 + i * kVStride;
-      for (int k = 0; k < 204; k++) {
-        const float wk = w[k];
+      const float4 *w4 = reinterpret_cast<const float4 *>(S.w1 + i * kVStride);
+      for (int k4 = 0; k4 < 51; k4++) {
+        const float4 wv = w4[k4];
 #pragma unroll
         for (int q = 0; q < 7; q++) {
           const int r = g + 5 * q;
-          if (r < kVRows) acc[q] = fmaf(wk, S.x[r][k], acc[q]);
+          if (r < kVRows) {
+            const float4 xv = reinterpret_cast<const float4 *>(S.x[r])[k4];  // broadcast within the row group
+            acc[q] = fmaf(wv.x, xv.x, acc[q]);
+            acc[q] = fmaf(wv.y, xv.y, acc[q]);
+            acc[q] = fmaf(wv.z, xv.z, acc[q]);
+            acc[q] = fmaf(wv.w, xv.w, acc[q]);
+          }
         }
       }
 #pragma unroll
@@ -190,24 +206,56 @@ vseg_rows_kernel(const float *__restrict__ wts, const uint8_t *__restrict__ card
 }
 
 // ------------------------------------------------------------------------------------------------
-// C0..C2.  One CTA (8 warps) processes the 16 digit slots of a "group" (= one frame, or 16 raw patches);
+// C0..C2.  One CTA (16 warps) processes the 16 digit slots of a "group" (= one frame, or 16 raw patches);
 // persistent over groups so the 123 KB of transposed hidden weights are staged once per CTA.
 // ------------------------------------------------------------------------------------------------
-constexpr int kCThreads = 256;
+constexpr int kCThreads = 512;
 
+struct CatPrep {  // patch-preparation scratch, one slice per warp; dead once the float patches exist
+  unsigned int hist[16][256];
+  uint8_t raw[16][27 * 24];
+  uint8_t g8[16][27 * 20];
+  uint8_t lut[16][256];
+};
+struct CatWork {  // network activations of the current group
+  alignas(16) float feat[16][320];  // tanh(pool + bias) of the current model
+  float part[4][16][32];            // hidden-layer partial sums over the four K quarters
+  float hid[16][3][32];
+  float prob[16][3][10];
+};
 struct CatSmem {
-  float hwT[3][320][32];   // hidden W transposed: [model][feature][unit]
+  float hwT[3][320][32];  // hidden W transposed: [model][feature][unit]
   float hb[3][32];
   float lw[3][10][32];
   float lb[3][10];
   float patch[16][27 * 19 + 3];  // normalised digit images
-  float feat[16][320];           // tanh(pool + bias) of the current model
-  float hid[16][3][32];
-  float prob[16][3][10];
-  unsigned int hist[8][256];
-  uint8_t g8[8][27 * 20];
-  uint8_t lut[8][256];
+  union {
+    CatPrep prep;
+    CatWork work;
+  } u;
 };
+
+// four of the eight kernels of model m on one pooled cell: conv 3x3 over the 5x5 window, 3x3 max, + bias, tanh
+template <int K0>
+__device__ __forceinline__ void conv_pool_four(int m, const float (&win)[5][5], float *feat_cell /* stride 40 per kernel */) {
+#pragma unroll
+  for (int kk = 0; kk < 4; kk++) {
+    const int k = K0 + kk;
+    float best = -FLT_MAX;
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        float acc = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+          for (int j = 0; j < 3; j++) acc = fmaf(c_conv_w[m][k][i * 3 + j], win[r + i][c + j], acc);
+        best = fmaxf(best, acc);
+      }
+    feat_cell[k * 40] = tanhf(best + c_conv_b[m][k]);
+  }
+}
 
 template <bool kRaw>
 __global__ void __launch_bounds__(kCThreads, 1)
@@ -240,74 +288,86 @@ categorize_kernel(NetWeights W, const uint8_t *__restrict__ cards, b200_scan *__
       nd = min(16, (int)sc->hseg.n_offsets);
       src_base = cards + (size_t)grp * kCardBytes + (size_t)sc->vseg.y_offset * B200_CARD_W;
     }
-    // ---- C0 + C1: patch preparation, one warp per digit (two rounds of eight)
-    for (int d = warp; d < nd; d += 8) {
-      const uint8_t *src;
-      int stride;
+    // ---- C0 + C1: patch preparation, one warp per digit
+    if (warp < nd) {
+      const int d = warp;
       if (kRaw && raw_float != nullptr) {  // already-prepared float patches (model known-answer tests)
         for (int i = lane; i < 27 * 19; i += 32) S.patch[d][i] = __ldg(raw_float + (size_t)(grp * 16 + d) * (27 * 19) + i);
-        continue;
-      }
-      if (kRaw) {
-        src = raw_patches + (size_t)(grp * 16 + d) * (27 * 19);
-        stride = 19;
       } else {
-        src = src_base + sc->hseg.offsets[d];
-        stride = B200_CARD_W;
-      }
-      uint8_t *g8 = S.g8[warp];
-      unsigned int *hist = S.hist[warp];
-      for (int i = lane; i < 256; i += 32) hist[i] = 0;
-      __syncwarp();
-      // 5-point cross max - min with replicate at the PATCH edge (cv/morph.cpp:177-255 on the 19x27 ROI)
-      for (int i = lane; i < 27 * 19; i += 32) {
-        const int y = i / 19, x = i - y * 19;
-        const int yu = y > 0 ? y - 1 : y, yd = y < 26 ? y + 1 : y, xl = x > 0 ? x - 1 : x, xr = x < 18 ? x + 1 : x;
-        const int a = __ldg(src + yu * stride + x), b = __ldg(src + y * stride + xl), c = __ldg(src + y * stride + x);
-        const int e = __ldg(src + y * stride + xr), f = __ldg(src + yd * stride + x);
-        const int v = max(a, max(b, max(c, max(e, f)))) - min(a, min(b, min(c, min(e, f))));
-        g8[y * 20 + x] = (uint8_t)v;
-        atomicAdd(&hist[v], 1u);
-      }
-      __syncwarp();
-      // llcv_equalize_hist (cv/stats.cpp:116-159): lut[i] = sat8(cvRound(cum(i) * (255.f / 513))), lut[0] = 0
-      {
-        unsigned int local[8], run = 0;
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-          run += hist[lane * 8 + q];
-          local[q] = run;
-        }
-        unsigned int incl = run;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += t;
-        }
-        const unsigned int excl = incl - run;
-        const float scale = 255.f / (19 * 27);
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-          const int val = __float2int_rn(__fmul_rn((float)(int)(excl + local[q]), scale));
-          S.lut[warp][lane * 8 + q] = (uint8_t)(val < 0 ? 0 : (val > 255 ? 255 : val));
+        uint8_t *raw = S.u.prep.raw[warp];  // [27][24], patch column c at byte c + a of each row
+        uint8_t *g8 = S.u.prep.g8[warp];
+        unsigned int *hist = S.u.prep.hist[warp];
+        int a = 0;
+        for (int i = lane; i < 256; i += 32) hist[i] = 0;
+        if (kRaw) {
+          const uint8_t *src = raw_patches + (size_t)(grp * 16 + d) * (27 * 19);
+          for (int i = lane; i < 27 * 19; i += 32) raw[(i / 19) * 24 + (i % 19)] = __ldg(src + i);
+        } else {
+          // rows of a card are 428 = 4 * 107 bytes apart, so every row of the patch has the same word alignment:
+          // fetch the <= 6 aligned words covering the 19 bytes of each row
+          const uint8_t *src = src_base + sc->hseg.offsets[d];
+          a = (int)(reinterpret_cast<uintptr_t>(src) & 3u);
+          const unsigned int *wsrc = reinterpret_cast<const unsigned int *>(src - a);
+          const int words = (a + 19 + 3) >> 2;
+          for (int i = lane; i < 27 * 6; i += 32) {
+            const int row = i / 6, q = i - row * 6;
+            if (q < words) reinterpret_cast<unsigned int *>(raw)[row * 6 + q] = __ldg(wsrc + row * (B200_CARD_W / 4) + q);
+          }
         }
         __syncwarp();
-        if (lane == 0) S.lut[warp][0] = 0;
+        // 5-point cross max - min with replicate at the PATCH edge (cv/morph.cpp:177-255 on the 19x27 ROI)
+        for (int i = lane; i < 27 * 19; i += 32) {
+          const int y = i / 19, x = i - y * 19;
+          const int yu = y > 0 ? y - 1 : y, yd = y < 26 ? y + 1 : y, xl = x > 0 ? x - 1 : x, xr = x < 18 ? x + 1 : x;
+          const int p = raw[yu * 24 + x + a], q = raw[y * 24 + xl + a], c = raw[y * 24 + x + a];
+          const int e = raw[y * 24 + xr + a], f = raw[yd * 24 + x + a];
+          const int v = max(p, max(q, max(c, max(e, f)))) - min(p, min(q, min(c, min(e, f))));
+          g8[y * 20 + x] = (uint8_t)v;
+          atomicAdd(&hist[v], 1u);
+        }
         __syncwarp();
+        // llcv_equalize_hist (cv/stats.cpp:116-159): lut[i] = sat8(cvRound(cum(i) * (255.f / 513))), lut[0] = 0
+        {
+          unsigned int local[8], run = 0;
+#pragma unroll
+          for (int q = 0; q < 8; q++) {
+            run += hist[lane * 8 + q];
+            local[q] = run;
+          }
+          unsigned int incl = run;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+          }
+          const unsigned int excl = incl - run;
+          const float scale = 255.f / (19 * 27);
+#pragma unroll
+          for (int q = 0; q < 8; q++) {
+            const int val = __float2int_rn(__fmul_rn((float)(int)(excl + local[q]), scale));
+            S.u.prep.lut[warp][lane * 8 + q] = (uint8_t)(val < 0 ? 0 : (val > 255 ? 255 : val));
+          }
+          __syncwarp();
+          if (lane == 0) S.u.prep.lut[warp][0] = 0;
+          __syncwarp();
+        }
+        for (int i = lane; i < 27 * 19; i += 32) {
+          const int y = i / 19, x = i - y * 19;
+          S.patch[d][i] = __fmul_rn((float)S.u.prep.lut[warp][g8[y * 20 + x]], 1.0f / 255.0f);  // cvConvertScale
+        }
       }
-      for (int i = lane; i < 27 * 19; i += 32) {
-        const int y = i / 19, x = i - y * 19;
-        S.patch[d][i] = __fmul_rn((float)S.lut[warp][g8[y * 20 + x]], 1.0f / 255.0f);  // cvConvertScale
-      }
-      __syncwarp();
     }
-    __syncthreads();
+    __syncthreads();  // patches complete; the prep scratch is dead from here on (aliased by u.work)
     // ---- C2, model by model
     for (int m = 0; m < 3; m++) {
-      // conv 3x3 (valid, 24 x 15 computed) -> 3x3/3 max pool (8 x 5) -> + bias -> tanh.  Work item = (digit, pooled
-      // cell); the 5x5 input window of a cell is loaded once and feeds all eight kernels.
-      for (int it = tid; it < nd * 40; it += kCThreads) {
-        const int d = it / 40, cell = it - d * 40;
+      // conv 3x3 (valid, 24 x 15 computed) -> 3x3/3 max pool (8 x 5) -> + bias -> tanh.  Work item = (kernel half,
+      // digit, pooled cell); the 5x5 input window of a cell is loaded once and feeds four kernels whose weights are
+      // warp-uniform __constant__ operands.
+      const int half_items = nd * 40;
+      for (int it = tid; it < 2 * half_items; it += kCThreads) {
+        const int kh = it >= half_items;
+        const int dc = it - kh * half_items;
+        const int d = dc / 40, cell = dc - d * 40;
         const int pr = cell / 5, pc = cell - pr * 5;
         const float *p = &S.patch[d][(pr * 3) * 19 + pc * 3];
         float win[5][5];
@@ -315,39 +375,40 @@ categorize_kernel(NetWeights W, const uint8_t *__restrict__ cards, b200_scan *__
         for (int i = 0; i < 5; i++)
 #pragma unroll
           for (int j = 0; j < 5; j++) win[i][j] = p[i * 19 + j];
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-          float best = -FLT_MAX;
-#pragma unroll
-          for (int r = 0; r < 3; r++)
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-              float acc = 0.0f;
-#pragma unroll
-              for (int i = 0; i < 3; i++)
-#pragma unroll
-                for (int j = 0; j < 3; j++) acc = fmaf(c_conv_w[m][k][i * 3 + j], win[r + i][c + j], acc);
-              best = fmaxf(best, acc);
-            }
-          S.feat[d][k * 40 + cell] = tanhf(best + c_conv_b[m][k]);
-        }
+        if (kh == 0) conv_pool_four<0>(m, win, &S.u.work.feat[d][cell]);
+        else conv_pool_four<4>(m, win, &S.u.work.feat[d][cell]);
       }
       __syncthreads();
-      // hidden layer 320 -> 32: thread -> (unit, digit pair)
+      // hidden layer 320 -> 32: thread -> (unit u, digit quad dq, K quarter jq); 4 digits x 80 features each
       {
-        const int u = tid & 31, dg = tid >> 5;  // digits dg and dg + 8
-        float a0 = 0.0f, a1 = 0.0f;
-        const bool v0 = dg < nd, v1 = dg + 8 < nd;
-        if (v0) {
-          for (int j = 0; j < 320; j++) {
-            const float wv = S.hwT[m][j][u];
-            a0 = fmaf(wv, S.feat[dg][j], a0);
-            if (v1) a1 = fmaf(wv, S.feat[dg + 8][j], a1);
-          }
-          S.hid[dg][m][u] = tanhf(a0 + S.hb[m][u]);
-          if (v1) S.hid[dg + 8][m][u] = tanhf(a1 + S.hb[m][u]);
+        const int u = tid & 31, dq = (tid >> 5) & 3, jq = tid >> 7;
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+        const float (*wT)[32] = S.hwT[m];
+        for (int j = jq * 80; j < jq * 80 + 80; j += 4) {
+          const float w0 = wT[j][u], w1 = wT[j + 1][u], w2 = wT[j + 2][u], w3 = wT[j + 3][u];
+          const float4 f0 = *reinterpret_cast<const float4 *>(&S.u.work.feat[dq][j]);
+          const float4 f1 = *reinterpret_cast<const float4 *>(&S.u.work.feat[dq + 4][j]);
+          const float4 f2 = *reinterpret_cast<const float4 *>(&S.u.work.feat[dq + 8][j]);
+          const float4 f3 = *reinterpret_cast<const float4 *>(&S.u.work.feat[dq + 12][j]);
+          a0 = fmaf(w0, f0.x, a0), a0 = fmaf(w1, f0.y, a0), a0 = fmaf(w2, f0.z, a0), a0 = fmaf(w3, f0.w, a0);
+          a1 = fmaf(w0, f1.x, a1), a1 = fmaf(w1, f1.y, a1), a1 = fmaf(w2, f1.z, a1), a1 = fmaf(w3, f1.w, a1);
+          a2 = fmaf(w0, f2.x, a2), a2 = fmaf(w1, f2.y, a2), a2 = fmaf(w2, f2.z, a2), a2 = fmaf(w3, f2.w, a2);
+          a3 = fmaf(w0, f3.x, a3), a3 = fmaf(w1, f3.y, a3), a3 = fmaf(w2, f3.z, a3), a3 = fmaf(w3, f3.w, a3);
+        }
+        S.u.work.part[jq][dq][u] = a0;
+        S.u.work.part[jq][dq + 4][u] = a1;
+        S.u.work.part[jq][dq + 8][u] = a2;
+        S.u.work.part[jq][dq + 12][u] = a3;
+      }
+      __syncthreads();
+      {
+        const int u = tid & 31, d = tid >> 5;  // 16 digits x 32 units
+        if (d < nd) {
+          const float sum = ((S.u.work.part[0][d][u] + S.u.work.part[1][d][u]) + S.u.work.part[2][d][u]) + S.u.work.part[3][d][u];
+          S.u.work.hid[d][m][u] = tanhf(sum + S.hb[m][u]);
         }
       }
+      // (feat is rewritten by the next model's conv only after the barrier below; part after the one above)
       __syncthreads();
     }
     // logistic layer 32 -> 10 and softmax, thread -> (digit, model, class)
@@ -355,8 +416,8 @@ categorize_kernel(NetWeights W, const uint8_t *__restrict__ cards, b200_scan *__
       const int d = it / 30, r = it - d * 30, m = r / 10, c = r - m * 10;
       float acc = 0.0f;
 #pragma unroll
-      for (int j = 0; j < 32; j++) acc = fmaf(S.lw[m][c][j], S.hid[d][m][j], acc);
-      S.prob[d][m][c] = expf(acc + S.lb[m][c]);
+      for (int j = 0; j < 32; j++) acc = fmaf(S.lw[m][c][j], S.u.work.hid[d][m][j], acc);
+      S.u.work.prob[d][m][c] = expf(acc + S.lb[m][c]);
     }
     __syncthreads();
     for (int it = tid; it < 16 * 10; it += kCThreads) {
@@ -367,8 +428,8 @@ categorize_kernel(NetWeights W, const uint8_t *__restrict__ cards, b200_scan *__
         for (int m = 0; m < 3; m++) {
           float sum = 0.0f;
 #pragma unroll
-          for (int j = 0; j < 10; j++) sum += S.prob[d][m][j];
-          pm[m] = S.prob[d][m][c] / sum;
+          for (int j = 0; j < 10; j++) sum += S.u.work.prob[d][m][j];
+          pm[m] = S.u.work.prob[d][m][c] / sum;
         }
         const float mx = fmaxf(pm[0], fmaxf(pm[1], pm[2]));
         e = (((pm[0] + pm[1]) + pm[2]) - mx) / 2.0f;  // n_categorize.cpp:69-70

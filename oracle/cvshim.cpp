@@ -107,8 +107,8 @@ CV_IMPL IplImage *cvCreateImageHeader(CvSize size, int depth, int channels) {
 CV_IMPL IplImage *cvCreateImage(CvSize size, int depth, int channels) {
   IplImage *img = cvCreateImageHeader(size, depth, channels);
   void *mem = NULL;
-  if (posix_memalign(&mem, 64, (size_t)img->imageSize + 64) != 0) SHIM_FAIL("alloc");
-  memset(mem, 0xCD, (size_t)img->imageSize + 64); /* uninitialised in OpenCV; poison to catch reads */
+  /* cvCreateImage -> cv::fastMalloc: a 16-byte aligned malloc; contents uninitialised */
+  if (posix_memalign(&mem, 16, (size_t)img->imageSize + 16) != 0) SHIM_FAIL("alloc");
   img->imageData = img->imageDataOrigin = (char *)mem;
   return img;
 }

@@ -13,6 +13,7 @@
  */
 #include "dmz_all.cpp"
 
+#include <malloc.h>
 #include <pthread.h>
 #include <time.h>
 
@@ -398,6 +399,12 @@ static void *bench_worker(void *arg) {
 double ref_bench_frames(const uint8_t *frames, int n, int w, int h, const uint8_t *cb, const uint8_t *cr, int orientation,
                         int nthreads, orc_frame_record *recs) {
   if (nthreads < 1) nthreads = 1;
+  /* The reference allocates and frees ~20 images per frame (cvCreateImage).  With glibc's defaults the larger
+   * ones are mmap()ed and unmapped every time, which serialises the threads in the kernel; keep them on the
+   * per-thread arenas instead so the many-core baseline measures the reference's arithmetic, not mmap. */
+  mallopt(M_MMAP_THRESHOLD, 1 << 30);
+  mallopt(M_TRIM_THRESHOLD, 1 << 30);
+  mallopt(M_ARENA_MAX, 256);
   pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * nthreads);
   BenchJob *jobs = (BenchJob *)malloc(sizeof(BenchJob) * nthreads);
   struct timespec t0, t1;
