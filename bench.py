@@ -47,6 +47,25 @@ ALG_BYTES = {
 }
 
 
+def usable_cpus():
+    """Host threads this process may really use: affinity mask, clipped by a cgroup CPU quota if one is set."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(float(txt[0]) / float(txt[1]) + 0.5)))
+            else:
+                q = int(txt[0])
+                if q > 0:
+                    period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                    n = min(n, max(1, int(q / period + 0.5)))
+        except Exception:
+            pass
+    return n
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -109,7 +128,7 @@ def reference_arm(args, rank, world):
     from util import deck_frames
     kind = "ref" if available("ref") else "port"
     orc = Oracle(kind)
-    cores = os.cpu_count() or 1
+    cores = usable_cpus()
     sample = args.cpu_sample
     frames = deck_frames(0, sample, W, H, JITTER, DECK_SEED, threads=min(cores, 64))
     for _ in range(args.warmup):
@@ -240,6 +259,7 @@ def main():
         for _ in range(max(1, min(args.warmup, 2))):
             dmz.process_frames_host_ptr(h_frames.data_ptr(), Fe, W, H, h_records.data_ptr())
         barrier()
+        h2d0, d2h0 = dmz.transfer_bytes()
         te = time.perf_counter()
         for _ in range(args.steps):
             dmz.process_frames_host_ptr(h_frames.data_ptr(), Fe, W, H, h_records.data_ptr())
@@ -252,8 +272,11 @@ def main():
             dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
         e2e_s = float(t_e.item())
         same = bool((h_records.cuda() == records[:Fe]).all().item())
-        e2e = {"value": Fe * world * args.steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": Fe * FRAME_BYTES,
-               "d2h_bytes_per_step": Fe * RECORD_BYTES, "frames_per_step": Fe, "records_equal_device_path": same,
+        h2d1, d2h1 = dmz.transfer_bytes()
+        e2e = {"value": Fe * world * args.steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": (h2d1 - h2d0) // args.steps,
+               "d2h_bytes_per_step": (d2h1 - d2h0) // args.steps, "frames_per_step": Fe, "records_equal_device_path": same,
+               "host_frame_bytes_per_step": Fe * FRAME_BYTES, "full_frame_redos": dmz.full_frame_redos,
+               "note": "host frames are full 640x480 planes in pinned memory; the library uploads only the detection-region rectangle (+8 px) of each and re-uploads a whole frame if its card quad reaches outside it",
                "timing": "wall clock around the synchronous C-ABI calls, max over ranks"}
 
     # ---- CPU baseline on the host cores (rank 0 only, bounded sample)
@@ -262,7 +285,7 @@ def main():
         from oracle.binding import Oracle, available
         kind = "ref" if available("ref") else "port"
         orc = Oracle(kind)
-        cores = os.cpu_count() or 1
+        cores = usable_cpus()
         S = min(args.cpu_sample, F)
         sample = frames[:S].cpu().numpy()
         orc.bench_frames(sample[: max(cores, 64)], cores)

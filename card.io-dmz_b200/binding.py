@@ -106,6 +106,10 @@ def _load():
     lib.b200_vseg_model_batch.argtypes = [vp, vp, i, i, vp]
     lib.b200_digit_models_batch.argtypes = [vp, vp, i, i, vp]
     lib.b200_set_profiling.argtypes = [vp, i]
+    lib.b200_set_crop_margin.argtypes = [vp, i]
+    lib.b200_full_frame_redos.argtypes = [vp]
+    lib.b200_full_frame_redos.restype = C.c_uint64
+    lib.b200_transfer_bytes.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.b200_stage_times.argtypes = [vp, vp, C.POINTER(C.c_uint64)]
     lib.b200_scanner_new.restype = vp
     lib.b200_scanner_free.argtypes = [vp]
@@ -240,6 +244,18 @@ class Dmz:
         return out[:, :10].copy(), out[:, 10:].reshape(n, 3, 10).copy()
 
     STAGES = ("detect", "geometry", "warp", "vseg", "hseg", "categorize", "finalize")
+
+    def set_crop_margin(self, margin):
+        self.lib.b200_set_crop_margin(self.ctx, int(margin))
+
+    @property
+    def full_frame_redos(self):
+        return int(self.lib.b200_full_frame_redos(self.ctx))
+
+    def transfer_bytes(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        self.lib.b200_transfer_bytes(self.ctx, C.byref(a), C.byref(b))
+        return int(a.value), int(b.value)
 
     def set_profiling(self, on=True):
         self.lib.b200_set_profiling(self.ctx, int(on))

@@ -30,6 +30,7 @@ struct Lane {
   b200_scan *d_scan = nullptr;
   b200_frame_record *d_records = nullptr;
   unsigned int *d_check = nullptr;
+  uint8_t *d_flags = nullptr;
   int16_t *d_grad = nullptr;
   size_t grad_elems = 0;
 };
@@ -41,8 +42,11 @@ struct b200_ctx {
   cudaStream_t stream = nullptr;  // == lane[0].stream
   std::string error;
   uint64_t launches = 0;
+  uint64_t full_frame_redos = 0;
+  uint64_t h2d_bytes = 0, d2h_bytes = 0;  // bytes moved by b200_process_frames_batch(B200_MEM_HOST)  // host-buffer frames that had to be re-uploaded whole (crop too small)
   Lane lane[2];
   int host_chunk = 2048;  // frames per pipelined chunk on the host-buffer path
+  int crop_margin = 8;    // host-buffer path uploads only the detection region + this margin (< 0: whole frames)
   // per-stage device time (CUDA events on the lane stream), accumulated while profiling is on
   int profiling = 0;
   double stage_ms[ST_COUNT] = {0};
@@ -116,10 +120,10 @@ std::string default_weights_dir() {
 
 void free_lane(Lane *l) {
   cudaFree(l->d_frames), cudaFree(l->d_cb), cudaFree(l->d_cr), cudaFree(l->d_lines), cudaFree(l->d_geom);
-  cudaFree(l->d_cards), cudaFree(l->d_vprob), cudaFree(l->d_scan), cudaFree(l->d_records), cudaFree(l->d_grad), cudaFree(l->d_check);
+  cudaFree(l->d_cards), cudaFree(l->d_vprob), cudaFree(l->d_scan), cudaFree(l->d_records), cudaFree(l->d_grad), cudaFree(l->d_check), cudaFree(l->d_flags);
   l->d_frames = l->d_cb = l->d_cr = nullptr;
   l->d_lines = nullptr, l->d_geom = nullptr, l->d_cards = nullptr, l->d_vprob = nullptr, l->d_scan = nullptr;
-  l->d_records = nullptr, l->d_grad = nullptr, l->d_check = nullptr;
+  l->d_records = nullptr, l->d_grad = nullptr, l->d_check = nullptr, l->d_flags = nullptr;
   l->grad_elems = 0;
   l->cap = 0;
 }
@@ -165,6 +169,7 @@ int ensure_capacity(b200_ctx *ctx, Lane *l, int n, int w, int h, bool need_frame
   CU(cudaMalloc(&l->d_scan, sizeof(b200_scan) * (size_t)cap));
   CU(cudaMalloc(&l->d_records, sizeof(b200_frame_record) * (size_t)cap));
   CU(cudaMalloc(&l->d_check, sizeof(unsigned int) * (size_t)cap));
+  CU(cudaMalloc(&l->d_flags, (size_t)cap));
   l->cap = cap, l->cap_w = cw, l->cap_h = chh;
   return B200_OK;
 }
@@ -220,13 +225,18 @@ int stage_planes(b200_ctx *ctx, cudaStream_t stream, const uint8_t *src, int row
   return B200_OK;
 }
 
+struct Crop {  // uploaded sub-rectangle [x0, x1) x [y0, y1) of the frame; x0 == x1 means "whole frame"
+  int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+  bool active() const { return x1 > x0; }
+};
+
 int detect_sequence(b200_ctx *ctx, Lane *l, const uint8_t *y, int yrs, size_t yfs, const uint8_t *cb, const uint8_t *cr,
-                    int crs, size_t cfs, int n, bool timed) {
+                    int crs, size_t cfs, int n, bool timed, Crop crop = Crop()) {
   const size_t plane_stride = (size_t)l->cap * 4;
   int rc = ensure_grad(ctx, l, n);
   if (rc) return rc;
   if (timed) CU(cudaEventRecord(ctx->ev[ST_DETECT], l->stream));
-  LAUNCH(launch_detect(ctx->dp[0], y, yrs, yfs, n, nullptr, nullptr, l->d_lines, l->d_grad, l->stream));
+  LAUNCH(launch_detect(ctx->dp[0], y, yrs, yfs, n, nullptr, nullptr, l->d_lines, l->d_grad, l->stream, crop.x0, crop.y0));
   if (cb && cr) {
     // Cb is searched only where Y produced no line, Cr only where neither Y nor Cb did (dmz.cpp:351)
     LAUNCH(launch_detect(ctx->dp[1], cb, crs, cfs, n, l->d_lines, nullptr, l->d_lines + plane_stride, l->d_grad, l->stream));
@@ -240,16 +250,17 @@ int detect_sequence(b200_ctx *ctx, Lane *l, const uint8_t *y, int yrs, size_t yf
 
 // detect -> warp -> scan -> records for n frames already visible to the device on lane l.
 int pipeline_on_lane(b200_ctx *ctx, Lane *l, const uint8_t *dy, int drs, size_t dfs, int width, int height, int n,
-                     uint8_t *dcards, b200_frame_record *drec, bool timed) {
-  int rc = detect_sequence(ctx, l, dy, drs, dfs, nullptr, nullptr, 0, 0, n, timed);
+                     uint8_t *dcards, b200_frame_record *drec, bool timed, Crop crop = Crop()) {
+  int rc = detect_sequence(ctx, l, dy, drs, dfs, nullptr, nullptr, 0, 0, n, timed, crop);
   if (rc) return rc;
   if (timed) CU(cudaEventRecord(ctx->ev[ST_WARP], l->stream));
-  LAUNCH(launch_warp(dy, drs, dfs, width, height, n, l->d_geom, dcards, l->d_check, l->stream));
+  LAUNCH(launch_warp(dy, drs, dfs, width, height, n, l->d_geom, dcards, l->d_check, l->stream, crop.x0, crop.y0));
   cudaEvent_t *ev = timed ? ctx->ev : nullptr;
   LAUNCH(launch_scan(ctx->wts, dcards, n, l->d_geom, nullptr, l->d_vprob, l->d_scan, l->stream,
                      ev ? ev[ST_VSEG] : nullptr, ev ? ev[ST_HSEG] : nullptr, ev ? ev[ST_CATEGORIZE] : nullptr,
                      ev ? ev[ST_FINALIZE] : nullptr));
-  LAUNCH(launch_finalize_records(l->d_geom, l->d_scan, l->d_check, n, drec, l->stream));
+  LAUNCH(launch_finalize_records(l->d_geom, l->d_scan, l->d_check, n, drec, l->stream, crop.active() ? l->d_flags : nullptr, crop.x0,
+                                 crop.y0, crop.x1, crop.y1));
   if (timed) CU(cudaEventRecord(ctx->ev[ST_COUNT], l->stream));
   return B200_OK;
 }
@@ -284,6 +295,8 @@ int b200_ctx_create(b200_ctx **out, int device_ordinal, const char *weights_dir)
   for (int i = 0; i <= ST_COUNT; i++) CU(cudaEventCreate(&ctx->ev[i]));
   const char *chunk_env = getenv("B200_DMZ_HOST_CHUNK");
   if (chunk_env && atoi(chunk_env) > 0) ctx->host_chunk = atoi(chunk_env);
+  const char *crop_env = getenv("B200_DMZ_CROP_MARGIN");
+  if (crop_env && *crop_env) ctx->crop_margin = atoi(crop_env);
 
   const std::string dir = weights_dir && *weights_dir ? weights_dir : default_weights_dir();
   std::vector<float> blob;
@@ -329,6 +342,14 @@ void b200_ctx_destroy(b200_ctx *ctx) {
 const char *b200_last_error(const b200_ctx *ctx) { return ctx ? ctx->error.c_str() : "null context"; }
 uint64_t b200_launch_count(const b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
 void *b200_ctx_stream(const b200_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+uint64_t b200_full_frame_redos(const b200_ctx *ctx) { return ctx ? ctx->full_frame_redos : 0; }
+void b200_transfer_bytes(const b200_ctx *ctx, uint64_t *h2d, uint64_t *d2h) {
+  if (h2d) *h2d = ctx ? ctx->h2d_bytes : 0;
+  if (d2h) *d2h = ctx ? ctx->d2h_bytes : 0;
+}
+void b200_set_crop_margin(b200_ctx *ctx, int margin) {
+  if (ctx) ctx->crop_margin = margin;
+}
 
 int b200_ctx_reserve(b200_ctx *ctx, int max_frames, int width, int height) {
   if (!ctx || max_frames < 1) return B200_EINVAL;
@@ -476,12 +497,35 @@ int b200_process_frames_batch(b200_ctx *ctx, const uint8_t *y, int yrs, size_t y
   }
   // Host buffers: chunked two-lane pipeline.  Lane k%2 takes chunk k: H2D copy, kernels and the D2H of the
   // records are queued on that lane's stream, so chunk k+1's copy overlaps chunk k's kernels.
+  //
+  // Only the part of each frame the path can touch is uploaded: the bounding rectangle of the four detection
+  // strips plus a margin (PCIe, not the kernels, bounds this path).  The warp's source taps lie inside the hull
+  // of the detected corners; finalize_records_kernel flags the (rare) frames whose hull leaves the uploaded
+  // rectangle and those are redone below from a full-frame upload, so results never depend on the crop.
+  Crop crop;
+  if (ctx->crop_margin >= 0 && yfs % (size_t)yrs == 0) {
+    int x0 = width, y0 = height, x1 = 0, y1 = 0;
+    for (int s = 0; s < 4; s++) {
+      const StripDesc &d = ctx->dp[0].strip[s];
+      x0 = d.x < x0 ? d.x : x0, y0 = d.y < y0 ? d.y : y0;
+      x1 = d.x + d.w > x1 ? d.x + d.w : x1, y1 = d.y + d.h > y1 ? d.y + d.h : y1;
+    }
+    const int m = ctx->crop_margin;
+    crop.x0 = (x0 - m > 0 ? x0 - m : 0) & ~15;
+    crop.x1 = (x1 + m + 15) & ~15;
+    if (crop.x1 > width) crop.x1 = width;
+    crop.y0 = y0 - m > 0 ? y0 - m : 0;
+    crop.y1 = y1 + m < height ? y1 + m : height;
+    if ((crop.x1 - crop.x0) % 4 != 0 || (size_t)(crop.x1 - crop.x0) * (crop.y1 - crop.y0) * 10 > (size_t)width * height * 9) crop = Crop();
+  }
+  const int cw = crop.active() ? crop.x1 - crop.x0 : width, chh = crop.active() ? crop.y1 - crop.y0 : height;
   const int chunk = n < ctx->host_chunk ? n : ctx->host_chunk;
   for (int i = 0; i < 2; i++) {
     if (i == 1 && n <= chunk) break;
     rc = ensure_capacity(ctx, &ctx->lane[i], chunk, width, height, true);
     if (rc) return rc;
   }
+  std::vector<uint8_t> flags(crop.active() ? n : 0);
   int k = 0;
   for (int f0 = 0; f0 < n; f0 += chunk, k++) {
     Lane *l = &ctx->lane[k & 1];
@@ -489,15 +533,49 @@ int b200_process_frames_batch(b200_ctx *ctx, const uint8_t *y, int yrs, size_t y
     const uint8_t *dy;
     int drs;
     size_t dfs;
-    rc = stage_planes(ctx, l->stream, y + (size_t)f0 * yfs, yrs, yfs, width, height, cnt, B200_MEM_HOST, l->d_frames, &dy, &drs, &dfs);
-    if (rc) return rc;
-    rc = pipeline_on_lane(ctx, l, dy, drs, dfs, width, height, cnt, l->d_cards, l->d_records, false);
+    if (crop.active()) {
+      cudaMemcpy3DParms p;
+      memset(&p, 0, sizeof(p));
+      p.srcPtr = make_cudaPitchedPtr((void *)(y + (size_t)f0 * yfs), (size_t)yrs, (size_t)width, yfs / (size_t)yrs);
+      p.srcPos = make_cudaPos((size_t)crop.x0, (size_t)crop.y0, 0);
+      p.dstPtr = make_cudaPitchedPtr(l->d_frames, (size_t)cw, (size_t)cw, (size_t)chh);
+      p.extent = make_cudaExtent((size_t)cw, (size_t)chh, (size_t)cnt);
+      p.kind = cudaMemcpyHostToDevice;
+      CU(cudaMemcpy3DAsync(&p, l->stream));
+      ctx->h2d_bytes += (uint64_t)cw * chh * cnt;
+      dy = l->d_frames, drs = cw, dfs = (size_t)cw * chh;
+    } else {
+      rc = stage_planes(ctx, l->stream, y + (size_t)f0 * yfs, yrs, yfs, width, height, cnt, B200_MEM_HOST, l->d_frames, &dy, &drs, &dfs);
+      if (rc) return rc;
+      ctx->h2d_bytes += (uint64_t)width * height * cnt;
+    }
+    rc = pipeline_on_lane(ctx, l, dy, drs, dfs, width, height, cnt, l->d_cards, l->d_records, false, crop);
     if (rc) return rc;
     CU(cudaMemcpyAsync(records + f0, l->d_records, sizeof(b200_frame_record) * cnt, cudaMemcpyDeviceToHost, l->stream));
+    ctx->d2h_bytes += sizeof(b200_frame_record) * (uint64_t)cnt + (crop.active() ? cnt : 0) + (cards_out ? kCardBytes * cnt : 0);
+    if (crop.active()) CU(cudaMemcpyAsync(flags.data() + f0, l->d_flags, cnt, cudaMemcpyDeviceToHost, l->stream));
     if (cards_out) CU(cudaMemcpyAsync(cards_out + (size_t)f0 * kCardBytes, l->d_cards, kCardBytes * cnt, cudaMemcpyDeviceToHost, l->stream));
   }
   CU(cudaStreamSynchronize(ctx->lane[0].stream));
   if (k > 1) CU(cudaStreamSynchronize(ctx->lane[1].stream));
+  // frames whose card quad reaches outside the uploaded rectangle: redo from the whole frame
+  for (int i = 0; i < (int)flags.size(); i++) {
+    if (!flags[i]) continue;
+    Lane *l = &ctx->lane[0];
+    const uint8_t *dy;
+    int drs;
+    size_t dfs;
+    rc = stage_planes(ctx, l->stream, y + (size_t)i * yfs, yrs, yfs, width, height, 1, B200_MEM_HOST, l->d_frames, &dy, &drs, &dfs);
+    if (rc) return rc;
+    rc = pipeline_on_lane(ctx, l, dy, drs, dfs, width, height, 1, l->d_cards, l->d_records, false);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(records + i, l->d_records, sizeof(b200_frame_record), cudaMemcpyDeviceToHost, l->stream));
+    if (cards_out) CU(cudaMemcpyAsync(cards_out + (size_t)i * kCardBytes, l->d_cards, kCardBytes, cudaMemcpyDeviceToHost, l->stream));
+    CU(cudaStreamSynchronize(l->stream));
+    ctx->full_frame_redos++;
+    ctx->h2d_bytes += (uint64_t)width * height;
+    ctx->d2h_bytes += sizeof(b200_frame_record);
+  }
   return B200_OK;
 }
 

@@ -76,18 +76,19 @@ struct NetWeights {  // device pointers
 // launchers (each returns the number of kernels it launched, or -1 after setting a CUDA error)
 int launch_detect(const DetectParams &p, const uint8_t *plane, int row_stride, size_t frame_stride, int n,
                   const b200_line *prev_lines, const b200_line *prev_lines2, b200_line *lines, int16_t *grad_scratch,
-                  cudaStream_t s);
+                  cudaStream_t s, int ox = 0, int oy = 0);
 int launch_geometry(const GeomParams &g, const b200_line *lines, size_t plane_stride, int n, FrameGeom *geom, cudaStream_t s);
 int launch_homography_only(const float *src_pts, const float *dst_pts, int n, float *M, cudaStream_t s);
 int launch_corners_to_geom(const b200_corner_points *corners, const uint8_t *valid, int n, int orientation, int upsample,
                            FrameGeom *geom, cudaStream_t s);
 int launch_warp(const uint8_t *src, int row_stride, size_t frame_stride, int w, int h, int n, const FrameGeom *geom,
-                uint8_t *cards, unsigned int *card_check, cudaStream_t s);
+                uint8_t *cards, unsigned int *card_check, cudaStream_t s, int ox = 0, int oy = 0);
 int launch_scan(const NetWeights &wts, const uint8_t *cards, int n, const FrameGeom *geom_or_null, const uint8_t *valid,
                 float *vprob, b200_scan *scans, cudaStream_t s, cudaEvent_t ev_vseg, cudaEvent_t ev_hseg, cudaEvent_t ev_cat,
                 cudaEvent_t ev_fin);
 int launch_finalize_records(const FrameGeom *geom, const b200_scan *scans, const unsigned int *card_check, int n,
-                            b200_frame_record *recs, cudaStream_t s);
+                            b200_frame_record *recs, cudaStream_t s, uint8_t *needs_full = nullptr, int cx0 = 0, int cy0 = 0,
+                            int cx1 = 0, int cy1 = 0);
 int launch_categorize_patches(const NetWeights &wts, const uint8_t *patches, const float *float_patches, int n, float *out,
                               cudaStream_t s);
 int launch_vseg_model(const NetWeights &wts, const float *rows, int n, float *out, cudaStream_t s);

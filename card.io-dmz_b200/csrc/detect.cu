@@ -76,7 +76,7 @@ __device__ __forceinline__ Walk make_walk(int tid, int w, int T) {
 __global__ void __launch_bounds__(kThreads, 2)
 detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__restrict__ plane, int row_stride,
                      size_t frame_stride, const b200_line *__restrict__ prev_lines, const b200_line *__restrict__ prev_lines2,
-                     b200_line *__restrict__ lines, int16_t *__restrict__ grad_scratch, size_t grad_scratch_stride) {
+                     b200_line *__restrict__ lines, int16_t *__restrict__ grad_scratch, size_t grad_scratch_stride, int ox, int oy) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __shared__ unsigned long long s_red[kThreads / 32];
   __shared__ int s_low, s_high, s_ncand, s_nvote, s_nedge;
@@ -122,10 +122,10 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
 
   // ---- 1. load the strip (32-bit coalesced loads of the covering aligned words); clear borders / accumulator
   {
-    const uint8_t *base = plane + (size_t)frame * frame_stride + (size_t)S.y * row_stride + S.x;
+    const uint8_t *base = plane + (size_t)frame * frame_stride + (size_t)(S.y - oy) * row_stride + (S.x - ox);  // plane origin = (ox, oy)
     const bool word_ok = ((reinterpret_cast<uintptr_t>(plane) | (uintptr_t)row_stride | (uintptr_t)frame_stride) & 3u) == 0;
     if (word_ok) {
-      const int shift = S.x & 3;               // bytes of the first word that precede the strip
+      const int shift = (S.x - ox) & 3;        // bytes of the first word that precede the strip
       const int words = (shift + w + 3) >> 2;  // words per row
       const Walk k = make_walk(tid, words, kThreads);
       if (k.active)
@@ -367,7 +367,7 @@ size_t detect_smem_bytes(const DetectParams &p) {
 
 int launch_detect(const DetectParams &p, const uint8_t *plane, int row_stride, size_t frame_stride, int n,
                   const b200_line *prev_lines, const b200_line *prev_lines2, b200_line *lines, int16_t *grad_scratch,
-                  cudaStream_t s) {
+                  cudaStream_t s, int ox, int oy) {
   size_t smem = detect_smem_bytes(p);
   static size_t configured = 0;
   if (smem > configured) {
@@ -386,7 +386,7 @@ int launch_detect(const DetectParams &p, const uint8_t *plane, int row_stride, s
     detect_strips_kernel<<<dim3(4, cnt), kThreads, smem, s>>>(
         p, plane + (size_t)f0 * frame_stride, row_stride, frame_stride, prev_lines ? prev_lines + (size_t)f0 * 4 : nullptr,
         prev_lines2 ? prev_lines2 + (size_t)f0 * 4 : nullptr, lines + (size_t)f0 * 4,
-        grad_scratch ? grad_scratch + (size_t)f0 * 4 * max_npad * 2 : nullptr, max_npad * 2);
+        grad_scratch ? grad_scratch + (size_t)f0 * 4 * max_npad * 2 : nullptr, max_npad * 2, ox, oy);
     launches++;
   }
   return cudaGetLastError() == cudaSuccess ? launches : -1;

@@ -270,6 +270,8 @@ __global__ void homography_only_kernel(const float *__restrict__ src, const floa
 constexpr int kWarpRows = 8;
 constexpr int kQuadsPerRow = B200_CARD_W / 4;  // 107
 
+// src points at pixel (ox, oy) of the sw x sh frame (the host-buffer path uploads only a crop); the crop is
+// guaranteed by the caller to contain every in-image tap of this frame's quad.
 __device__ __forceinline__ int warp_sample(const uint8_t *__restrict__ src, int row_stride, int sw, int sh, const double *M,
                                            double X0, double Y0, double W0, int x1) {
   double W = W0 + M[6] * x1;
@@ -305,7 +307,7 @@ __device__ __forceinline__ int warp_sample(const uint8_t *__restrict__ src, int 
 // still in registers (one global atomic per CTA) so that no later stage has to re-read the card for it.
 __global__ void __launch_bounds__(256)
 warp_kernel(const uint8_t *__restrict__ src, int row_stride, size_t frame_stride, int sw, int sh,
-            const FrameGeom *__restrict__ geom, uint8_t *__restrict__ cards, unsigned int *__restrict__ card_check) {
+            const FrameGeom *__restrict__ geom, uint8_t *__restrict__ cards, unsigned int *__restrict__ card_check, int ox, int oy) {
   const int frame = blockIdx.y;
   const int row0 = blockIdx.x * kWarpRows;
   __shared__ double sM[9];
@@ -315,7 +317,8 @@ warp_kernel(const uint8_t *__restrict__ src, int row_stride, size_t frame_stride
   if (threadIdx.x == 0) s_ok = geom[frame].all_found, s_sum = 0u;
   __syncthreads();
   uint8_t *dst = cards + (size_t)frame * (B200_CARD_W * B200_CARD_H);
-  const uint8_t *s = src + (size_t)frame * frame_stride;
+  // pointer to the (virtual) pixel (0, 0) of the frame; only addresses inside the uploaded crop are dereferenced
+  const uint8_t *s = src + (size_t)frame * frame_stride - ((ptrdiff_t)oy * row_stride + ox);
   const int nrows = min(kWarpRows, B200_CARD_H - row0);
   unsigned int sum = 0;
   int r = threadIdx.x / kQuadsPerRow, q = threadIdx.x - r * kQuadsPerRow;  // 256 = 2 * 107 + 42
@@ -376,11 +379,10 @@ __global__ void vseg_select_kernel(const float *__restrict__ vprob, const uint8_
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= n) return;
   b200_scan *sc = scans + f;
+  unsigned int *words = reinterpret_cast<unsigned int *>(sc);  // sizeof(b200_scan) == 720: padding bytes must be 0 too
   if (gate && !gate[f]) {
     if (pass == 1) {
-      b200_scan z;
-      memset(&z, 0, sizeof(z));
-      *sc = z;
+      for (int i = 0; i < 180; i++) words[i] = 0u;
     } else {
       sc->vseg.y_offset = 0xFFFF;  // no fine rows
     }
@@ -397,17 +399,15 @@ __global__ void vseg_select_kernel(const float *__restrict__ vprob, const uint8_
                               {1, 1, 1, 1, 0, 1, 1, 1, 1, 0, 1, 1, 1, 1, 0, 1, 1, 1, 1},
                               {1, 1, 1, 1, 0, 1, 1, 1, 1, 1, 1, 0, 1, 1, 1, 1, 1, 0, 0}};
   const uint8_t pat_len[3] = {0, 19, 17}, num_len[3] = {0, 16, 15};
-  b200_scan out;
-  memset(&out, 0, sizeof(out));
-  out.vseg.score = score;
-  out.vseg.y_offset = (uint16_t)yo;
-  out.vseg.pattern_type = (uint8_t)pt;
-  for (int i = 0; i < 19; i++) out.vseg.number_pattern[i] = pat[pt][i];
-  out.vseg.number_pattern_length = pat_len[pt];
-  out.vseg.number_length = num_len[pt];
-  if (yo < (B200_CARD_H - 27) / 2) out.upside_down = 1;  // kFlipVSegYOffsetCutoff
-  else out.usable = score > 15.0f;                       // kMinVSegScore
-  *sc = out;
+  for (int i = 0; i < 180; i++) words[i] = 0u;
+  sc->vseg.score = score;
+  sc->vseg.y_offset = (uint16_t)yo;
+  sc->vseg.pattern_type = (uint8_t)pt;
+  for (int i = 0; i < 19; i++) sc->vseg.number_pattern[i] = pat[pt][i];
+  sc->vseg.number_pattern_length = pat_len[pt];
+  sc->vseg.number_length = num_len[pt];
+  if (yo < (B200_CARD_H - 27) / 2) sc->upside_down = 1;  // kFlipVSegYOffsetCutoff
+  else sc->usable = score > 15.0f;                       // kMinVSegScore
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -442,7 +442,8 @@ hseg_kernel(const uint8_t *__restrict__ cards, int n, b200_scan *__restrict__ sc
   __shared__ int s_mn, s_mx;
   __shared__ HsegPass s_pass;
   __shared__ unsigned long long s_red[kHsegThreads / 32];
-  __shared__ b200_hseg s_best;
+  __shared__ unsigned int s_best_words[12];  // a b200_hseg whose padding bytes stay zero
+  b200_hseg &s_best = *reinterpret_cast<b200_hseg *>(s_best_words);
   __shared__ uint8_t s_pat[19];
   __shared__ int s_npl;
   __shared__ float s_tpl[64];                           // the 19-tap template followed by zeros
@@ -457,12 +458,10 @@ hseg_kernel(const uint8_t *__restrict__ cards, int n, b200_scan *__restrict__ sc
   if (tid == 0) {
     s_npl = sc->vseg.number_pattern_length;
     s_mn = 0x7fffffff, s_mx = 0;
-    b200_hseg b;
-    memset(&b, 0, sizeof(b));
-    b.n_offsets = sc->vseg.number_length;
-    b.score = 428.0f;
-    b.number_width = 0.0f;
-    s_best = b;
+    for (int i = 0; i < 12; i++) s_best_words[i] = 0u;
+    s_best.n_offsets = sc->vseg.number_length;
+    s_best.score = 428.0f;
+    s_best.number_width = 0.0f;
   }
   __syncthreads();
 
@@ -621,7 +620,7 @@ hseg_kernel(const uint8_t *__restrict__ cards, int n, b200_scan *__restrict__ sc
     }
     __syncthreads();
   }
-  if (tid == 0) sc->hseg = s_best;
+  if (tid < 12) reinterpret_cast<unsigned int *>(&sc->hseg)[tid] = s_best_words[tid];
 }
 
 // S0 tail: usable = (n_offsets - scores.sum()) < kMaxNumberScoreDelta, frame.cpp:63-64.  scores.sum() on the
@@ -639,10 +638,26 @@ __global__ void scan_finish_kernel(int n, b200_scan *__restrict__ scans) {
 
 // Flat per-frame record; the card checksum was accumulated by the warp kernel.  One thread per frame.
 __global__ void finalize_records_kernel(const FrameGeom *__restrict__ geom, const b200_scan *__restrict__ scans,
-                                        const unsigned int *__restrict__ card_check, int n, b200_frame_record *__restrict__ recs) {
+                                        const unsigned int *__restrict__ card_check, int n, b200_frame_record *__restrict__ recs,
+                                        uint8_t *__restrict__ needs_full, int cx0, int cy0, int cx1, int cy1) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= n) return;
   const FrameGeom &g = geom[f];
+  if (needs_full != nullptr) {
+    // Cropped upload: the warp's taps lie in the convex hull of the four source corners (+1 px for the second tap,
+    // +1 for the 1/32-px rounding).  If that box leaves the uploaded crop [cx0, cx1) x [cy0, cy1) the frame is
+    // redone from a full upload by the host (b200_process_frames_batch).
+    uint8_t flag = 0;
+    if (g.all_found) {
+      float lox = g.corners[0], hix = g.corners[0], loy = g.corners[1], hiy = g.corners[1];
+      for (int i = 1; i < 4; i++) {
+        lox = fminf(lox, g.corners[2 * i]), hix = fmaxf(hix, g.corners[2 * i]);
+        loy = fminf(loy, g.corners[2 * i + 1]), hiy = fmaxf(hiy, g.corners[2 * i + 1]);
+      }
+      flag = !(lox - 2.0f >= (float)cx0 && hix + 3.0f < (float)cx1 && loy - 2.0f >= (float)cy0 && hiy + 3.0f < (float)cy1);
+    }
+    needs_full[f] = flag;
+  }
   b200_frame_record *r = recs + f;
   for (int i = 0; i < 4; i++) r->found[i] = g.found[i], r->rho[i] = g.rho[i], r->theta[i] = g.theta[i];
   for (int i = 0; i < 8; i++) r->corners[i] = g.corners[i];
@@ -690,7 +705,7 @@ int launch_corners_to_geom(const b200_corner_points *corners, const uint8_t *val
 }
 
 int launch_warp(const uint8_t *src, int row_stride, size_t frame_stride, int w, int h, int n, const FrameGeom *geom,
-                uint8_t *cards, unsigned int *card_check, cudaStream_t s) {
+                uint8_t *cards, unsigned int *card_check, cudaStream_t s, int ox, int oy) {
   if (card_check && cudaMemsetAsync(card_check, 0, sizeof(unsigned int) * (size_t)n, s) != cudaSuccess) return -1;
   int launches = 0;
   const int row_blocks = (B200_CARD_H + kWarpRows - 1) / kWarpRows;
@@ -698,15 +713,15 @@ int launch_warp(const uint8_t *src, int row_stride, size_t frame_stride, int w, 
     const int cnt = n - f0 < 65535 ? n - f0 : 65535;
     warp_kernel<<<dim3(row_blocks, cnt), 256, 0, s>>>(src + (size_t)f0 * frame_stride, row_stride, frame_stride, w, h, geom + f0,
                                                       cards + (size_t)f0 * (B200_CARD_W * B200_CARD_H),
-                                                      card_check ? card_check + f0 : nullptr);
+                                                      card_check ? card_check + f0 : nullptr, ox, oy);
     launches++;
   }
   return cudaGetLastError() == cudaSuccess ? launches : -1;
 }
 
 int launch_finalize_records(const FrameGeom *geom, const b200_scan *scans, const unsigned int *card_check, int n,
-                            b200_frame_record *recs, cudaStream_t s) {
-  finalize_records_kernel<<<blocks_for(n, 128), 128, 0, s>>>(geom, scans, card_check, n, recs);
+                            b200_frame_record *recs, cudaStream_t s, uint8_t *needs_full, int cx0, int cy0, int cx1, int cy1) {
+  finalize_records_kernel<<<blocks_for(n, 128), 128, 0, s>>>(geom, scans, card_check, n, recs, needs_full, cx0, cy0, cx1, cy1);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

@@ -118,6 +118,14 @@ int b200_ctx_reserve(b200_ctx *ctx, int max_frames, int width, int height);
 uint64_t b200_launch_count(const b200_ctx *ctx);
 /* The CUDA stream (cudaStream_t) all work of this context is enqueued on. */
 void *b200_ctx_stream(const b200_ctx *ctx);
+/* Host-buffer path of b200_process_frames_batch: only the bounding rectangle of the four detection strips plus
+ * `margin` pixels is copied to the device (margin < 0: whole frames; default 8 or $B200_DMZ_CROP_MARGIN).  Frames
+ * whose detected card quad reaches outside that rectangle are transparently redone from a full-frame upload;
+ * b200_full_frame_redos counts them.  Results never depend on the margin. */
+void b200_set_crop_margin(b200_ctx *ctx, int margin);
+uint64_t b200_full_frame_redos(const b200_ctx *ctx);
+/* Bytes copied host->device / device->host so far by b200_process_frames_batch(B200_MEM_HOST) calls. */
+void b200_transfer_bytes(const b200_ctx *ctx, uint64_t *h2d, uint64_t *d2h);
 /* Per-stage device time of b200_process_frames_batch (B200_MEM_DEVICE calls), measured with CUDA events on the
  * context's stream.  Stages: 0 detect (Sobel/Canny/Hough), 1 geometry, 2 warp, 3 vseg, 4 hseg, 5 categorize,
  * 6 finalize.  b200_set_profiling(ctx, 1) zeroes the accumulators; b200_stage_times returns the accumulated

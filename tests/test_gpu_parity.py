@@ -218,6 +218,28 @@ def test_strided_input_and_ragged_batches(dmz, deck, orecs):
     assert rc == 0 and np.array_equal(recs["card_check"], rec["card_check"][:5])
 
 
+def test_cropped_upload_falls_back_to_full_frames(pkg, oracle):
+    """Host-buffer path: with a zero margin some quads of a jitter-14 deck reach outside the uploaded rectangle;
+    those frames must be redone from the whole frame and every record must still equal the oracle's."""
+    frames = deck_frames(300, 24, jitter=14.0)
+    want = oracle.process_frames(frames)
+    d = pkg.Dmz(device=0)
+    try:
+        for margin in (0, 8, -1):
+            d.set_crop_margin(margin)
+            before = d.full_frame_redos
+            got = d.process_frames(frames)
+            for f in ("found", "all_found", "card_check", "v_y_offset", "usable", "h_offsets"):
+                assert np.array_equal(got[f], want[f]), (margin, f)
+            assert np.array_equal(bits(got["corners"]), bits(want["corners"]))
+            if margin == 0:
+                assert d.full_frame_redos > before, "the test deck should exercise the fallback"
+            if margin < 0:
+                assert d.full_frame_redos == before
+    finally:
+        d.close()
+
+
 def test_720p_frames(dmz, oracle):
     fr = deck_frames(0, 4, 1280, 720)
     want = oracle.process_frames(fr)
