@@ -511,9 +511,15 @@ int b200_process_frames_batch(b200_ctx *ctx, const uint8_t *y, int yrs, size_t y
       x1 = d.x + d.w > x1 ? d.x + d.w : x1, y1 = d.y + d.h > y1 ? d.y + d.h : y1;
     }
     const int m = ctx->crop_margin;
-    crop.x0 = (x0 - m > 0 ? x0 - m : 0) & ~15;
-    crop.x1 = (x1 + m + 15) & ~15;
-    if (crop.x1 > width) crop.x1 = width;
+    // Whole rows when the caller's rows are dense: each frame's region is then ONE contiguous host segment
+    // (measured: 496-byte pitched rows reach ~34 GB/s over PCIe Gen5, contiguous 200 KB segments ~53 GB/s).
+    if (yrs == width) {
+      crop.x0 = 0, crop.x1 = width;
+    } else {
+      crop.x0 = (x0 - m > 0 ? x0 - m : 0) & ~15;
+      crop.x1 = (x1 + m + 15) & ~15;
+      if (crop.x1 > width) crop.x1 = width;
+    }
     crop.y0 = y0 - m > 0 ? y0 - m : 0;
     crop.y1 = y1 + m < height ? y1 + m : height;
     if ((crop.x1 - crop.x0) % 4 != 0 || (size_t)(crop.x1 - crop.x0) * (crop.y1 - crop.y0) * 10 > (size_t)width * height * 9) crop = Crop();

@@ -271,12 +271,15 @@ def test_cxx_dropin_layer(dmz, oracle, tmp_path):
     assert np.array_equal(bits(got["corners"]), bits(want["corners"]))
     assert np.array_equal(got["rec"][:, 7].astype(np.uint32), want["card_check"])
     assert np.array_equal(got["rec"][:, 2], want["usable"]) and np.array_equal(got["rec"][:, 4], want["v_y_offset"])
-    assert np.abs(got["scores"] - want["scores"]).max() <= TOL
     s = oracle.scanner_new()
+    done = False
     for k in range(8):
+        if not done:  # once the number is complete the reference stops collecting scores (scan.cpp:43, frame.cpp:49)
+            assert np.abs(got["scores"][k] - want["scores"][k]).max() <= TOL
         oracle.scanner_add_frame(s, cards[k])
         done, digits = oracle.scanner_result(s)
         assert got["rec"][k, 5] == int(done)
         if done:
             assert got["digits"][k][: len(digits)].tolist() == digits.tolist()
+    assert done
     oracle.scanner_free(s)
