@@ -270,21 +270,43 @@ __global__ void homography_only_kernel(const float *__restrict__ src, const floa
 constexpr int kWarpRows = 8;
 constexpr int kQuadsPerRow = B200_CARD_W / 4;  // 107
 
-// src points at pixel (ox, oy) of the sw x sh frame (the host-buffer path uploads only a crop); the crop is
-// guaranteed by the caller to contain every in-image tap of this frame's quad.
+// src points at pixel (0, 0) of the sw x sh frame (the host-buffer path uploads only a crop and passes a
+// correspondingly shifted pointer); the crop is guaranteed by the caller to contain every in-image tap of the quad.
+//
+// Coordinates.  The reference computes W' = 32 / W (IEEE divide), fX = (X0 + M0 x1) W', X = cvRound(fX).  The
+// FP64 divide is the most expensive instruction sequence of this kernel, so X is first computed with a cheap
+// reciprocal (rcp.approx + two Newton steps, relative error ~1e-15): unless that value lies within 1e-6 of a
+// rounding boundary -- where a last-bit difference could change the integer -- it rounds to the same X as the
+// reference's doubly-rounded value; the rare boundary cases (and W ~ 0 / huge coordinates) take the exact
+// sequence.  The result is bit-identical to the reference for every pixel.
+__device__ __forceinline__ void warp_coords(const double *M, double X0, double Y0, double W0, int x1, int *X, int *Y) {
+  const double Wr = W0 + M[6] * x1;
+  const double nx = X0 + M[0] * x1, ny = Y0 + M[3] * x1;
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(Wr));
+  r = __fma_rn(r, __fma_rn(-Wr, r, 1.0), r);
+  r = __fma_rn(r, __fma_rn(-Wr, r, 1.0), r);
+  const double w32 = r * 32.0;
+  const double fx = nx * w32, fy = ny * w32;
+  int xi = __double2int_rn(fx), yi = __double2int_rn(fy);
+  const double ex = fabs(fx - (double)xi), ey = fabs(fy - (double)yi);
+  const double aw = fabs(Wr);
+  if (!(ex < 0.499999 && ey < 0.499999 && aw > 1e-200 && aw < 1e200)) {
+    double W = Wr != 0.0 ? 32. / Wr : 0.0;  // exact reference sequence
+    const double gx = nx * W, gy = ny * W;
+    xi = __double2int_rn(gx);  // cvt.rni.s32.f64: round-half-even, saturating == saturate_cast<int>(clamp(.))
+    yi = __double2int_rn(gy);
+  }
+  *X = xi, *Y = yi;
+}
+
 __device__ __forceinline__ int warp_sample(const uint8_t *__restrict__ src, int row_stride, int sw, int sh, const double *M,
                                            double X0, double Y0, double W0, int x1) {
-  double W = W0 + M[6] * x1;
-  W = W != 0.0 ? 32. / W : 0.0;
-  const double fX = (X0 + M[0] * x1) * W;
-  const double fY = (Y0 + M[3] * x1) * W;
-  // saturate_cast<int>(clamp(f, INT_MIN, INT_MAX)): cvt.rni.s32.f64 rounds half-to-even and saturates at the int range
-  const int X = __double2int_rn(fX), Y = __double2int_rn(fY);
-  const int sx = max(-32768, min(32767, X >> 5));  // saturate_cast<short>
-  const int sy = max(-32768, min(32767, Y >> 5));
+  int X, Y;
+  warp_coords(M, X0, Y0, W0, x1, &X, &Y);
+  // saturate_cast<short>(X >> 5) only matters beyond +-32767 px, where every tap is outside the image anyway
+  const int sx = X >> 5, sy = Y >> 5;
   const int fx = X & 31, fy = Y & 31;
-  int w00 = (32 - fx) * (32 - fy) * 32, w01 = fx * (32 - fy) * 32, w10 = (32 - fx) * fy * 32, w11 = fx * fy * 32;
-  if ((fx | fy) == 0) w00 = 32767, w11 = 1;  // initInterTab2D saturate/compensate quirk at (0,0)
   int v0, v1, v2, v3;
   if ((unsigned)sx < (unsigned)(sw - 1) && (unsigned)sy < (unsigned)(sh - 1)) {
     const uint8_t *p = src + (sy * row_stride + sx);  // 32-bit offset inside one frame
@@ -299,8 +321,13 @@ __device__ __forceinline__ int warp_sample(const uint8_t *__restrict__ src, int 
     v2 = (x0ok && y1ok) ? __ldg(src + ((sy + 1) * row_stride + sx)) : 0;
     v3 = (x1ok && y1ok) ? __ldg(src + ((sy + 1) * row_stride + sx + 1)) : 0;
   }
-  const int v = (v0 * w00 + v1 * w01 + v2 * w10 + v3 * w11 + (1 << 14)) >> 15;
-  return min(255, max(0, v));
+  // The 15-bit weights are (32-fx)(32-fy)*32, fx(32-fy)*32, (32-fx)fy*32, fx*fy*32, so
+  //   (sum w_i v_i + 2^14) >> 15  ==  ((v0 (32-fx) + v1 fx)(32-fy) + (v2 (32-fx) + v3 fx) fy + 2^9) >> 10   exactly.
+  // OpenCV's table holds {32767, 0, 0, 1} at (0,0) (saturate_cast<short>(32768) + compensation); that entry also
+  // evaluates to v0 for every 8-bit v0, v3, as does this formula, so no special case is needed.
+  const int ax = 32 - fx;
+  const int top = v0 * ax + v1 * fx, bot = v2 * ax + v3 * fx;
+  return (top * (32 - fy) + bot * fy + 512) >> 10;  // always in [0, 255]
 }
 
 // card_check (optional): per-frame checksum sum_i (i + 1) * card[i] mod 2^32, accumulated while the pixels are
