@@ -540,14 +540,20 @@ int b200_process_frames_batch(b200_ctx *ctx, const uint8_t *y, int yrs, size_t y
     int drs;
     size_t dfs;
     if (crop.active()) {
-      cudaMemcpy3DParms p;
-      memset(&p, 0, sizeof(p));
-      p.srcPtr = make_cudaPitchedPtr((void *)(y + (size_t)f0 * yfs), (size_t)yrs, (size_t)width, yfs / (size_t)yrs);
-      p.srcPos = make_cudaPos((size_t)crop.x0, (size_t)crop.y0, 0);
-      p.dstPtr = make_cudaPitchedPtr(l->d_frames, (size_t)cw, (size_t)cw, (size_t)chh);
-      p.extent = make_cudaExtent((size_t)cw, (size_t)chh, (size_t)cnt);
-      p.kind = cudaMemcpyHostToDevice;
-      CU(cudaMemcpy3DAsync(&p, l->stream));
+      if (cw == width && yrs == width) {
+        // whole rows of dense frames: one contiguous host segment per frame -> plain 2-D copy (width = the segment)
+        CU(cudaMemcpy2DAsync(l->d_frames, (size_t)cw * chh, y + (size_t)f0 * yfs + (size_t)crop.y0 * yrs, yfs, (size_t)cw * chh,
+                             (size_t)cnt, cudaMemcpyHostToDevice, l->stream));
+      } else {
+        cudaMemcpy3DParms p;
+        memset(&p, 0, sizeof(p));
+        p.srcPtr = make_cudaPitchedPtr((void *)(y + (size_t)f0 * yfs), (size_t)yrs, (size_t)width, yfs / (size_t)yrs);
+        p.srcPos = make_cudaPos((size_t)crop.x0, (size_t)crop.y0, 0);
+        p.dstPtr = make_cudaPitchedPtr(l->d_frames, (size_t)cw, (size_t)cw, (size_t)chh);
+        p.extent = make_cudaExtent((size_t)cw, (size_t)chh, (size_t)cnt);
+        p.kind = cudaMemcpyHostToDevice;
+        CU(cudaMemcpy3DAsync(&p, l->stream));
+      }
       ctx->h2d_bytes += (uint64_t)cw * chh * cnt;
       dy = l->d_frames, drs = cw, dfs = (size_t)cw * chh;
     } else {

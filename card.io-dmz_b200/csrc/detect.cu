@@ -44,10 +44,10 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
 }
 
 struct SmemLayout {
-  uint8_t *src;          // h x w source strip
+  uint8_t *src;          // h x w source strip (dead after Sobel: its storage then holds the work lists)
   int16_t *dx, *dy;      // (h + 2) x (w + 2), zero border: no bounds checks in the NMS neighbourhood
   uint8_t *map;          // (h + 2) x (w + 2): 0 candidate, 1 no edge (also the border), 2 edge
-  unsigned short *list;  // candidate list (hysteresis), then vote list (Hough): padded pixel indices
+  unsigned short *list;  // candidate list (hysteresis), then vote list (Hough): padded pixel indices; aliases src
   unsigned int *acc;     // compacted Hough accumulator
 };
 
@@ -73,7 +73,7 @@ __device__ __forceinline__ Walk make_walk(int tid, int w, int T) {
   return k;
 }
 
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 3)
 detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__restrict__ plane, int row_stride,
                      size_t frame_stride, const b200_line *__restrict__ prev_lines, const b200_line *__restrict__ prev_lines2,
                      b200_line *__restrict__ lines, int16_t *__restrict__ grad_scratch, size_t grad_scratch_stride, int ox, int oy) {
@@ -116,9 +116,9 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
   }
   L.map = smem_raw + off;
   off = align16(off + (size_t)npad);
-  L.list = reinterpret_cast<unsigned short *>(smem_raw + off);
-  off = align16(off + (size_t)npx * 2);
   L.acc = reinterpret_cast<unsigned int *>(smem_raw + off);
+  L.list = reinterpret_cast<unsigned short *>(L.src);  // npx bytes = npx / 2 entries; overflow falls back to full scans
+  const int list_cap = npx >> 1;
 
   // ---- 1. load the strip (32-bit coalesced loads of the covering aligned words); clear borders / accumulator
   {
@@ -245,7 +245,8 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
                 out = 2;
               } else {
                 out = 0;
-                L.list[atomicAdd(&s_ncand, 1)] = (unsigned short)o;
+                const int slot = atomicAdd(&s_ncand, 1);
+                if (slot < list_cap) L.list[slot] = (unsigned short)o;
               }
             }
           }
@@ -258,20 +259,42 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
   // candidate list to the fixed point, which is the reference's stack-walk result whatever the visiting order.
   {
     const int ncand = s_ncand;
-    while (true) {
-      int changed = 0;
-      for (int c = tid; c < ncand; c += kThreads) {
-        const int o = L.list[c];
-        const uint8_t *m = L.map + o;
-        if (*m != 0) continue;
-        const bool hit = m[-wp - 1] == 2 || m[-wp] == 2 || m[-wp + 1] == 2 || m[-1] == 2 || m[1] == 2 || m[wp - 1] == 2 ||
-                         m[wp] == 2 || m[wp + 1] == 2;
-        if (hit) {
-          L.map[o] = 2;
-          changed = 1;
+    if (ncand <= list_cap) {
+      while (true) {
+        int changed = 0;
+        for (int c = tid; c < ncand; c += kThreads) {
+          const int o = L.list[c];
+          const uint8_t *m = L.map + o;
+          if (*m != 0) continue;
+          const bool hit = m[-wp - 1] == 2 || m[-wp] == 2 || m[-wp + 1] == 2 || m[-1] == 2 || m[1] == 2 || m[wp - 1] == 2 ||
+                           m[wp] == 2 || m[wp + 1] == 2;
+          if (hit) {
+            L.map[o] = 2;
+            changed = 1;
+          }
         }
+        if (!__syncthreads_or(changed)) break;
       }
-      if (!__syncthreads_or(changed)) break;
+    } else {
+      // more candidates than list slots (pathological texture): sweep the whole map instead
+      const Walk k = make_walk(tid, w, kThreads);
+      while (true) {
+        int changed = 0;
+        if (k.active)
+          for (int y = k.ty; y < h; y += k.ystep)
+            for (int x = k.tx; x < w; x += k.xstep) {
+              const int o = (y + 1) * wp + x + 1;
+              const uint8_t *m = L.map + o;
+              if (*m != 0) continue;
+              const bool hit = m[-wp - 1] == 2 || m[-wp] == 2 || m[-wp + 1] == 2 || m[-1] == 2 || m[1] == 2 ||
+                               m[wp - 1] == 2 || m[wp] == 2 || m[wp + 1] == 2;
+              if (hit) {
+                L.map[o] = 2;
+                changed = 1;
+              }
+            }
+        if (!__syncthreads_or(changed)) break;
+      }
     }
   }
 
@@ -294,7 +317,18 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
           } else {
             use = !S.vertical;
           }
-          if (use) L.list[atomicAdd(&s_nvote, 1)] = (unsigned short)o;
+          if (use) {
+            const int slot = atomicAdd(&s_nvote, 1);
+            if (slot < list_cap) {
+              L.list[slot] = (unsigned short)o;
+            } else {  // list full: vote directly
+#pragma unroll
+              for (int n = 0; n < B200_NUMANGLE; n++) {
+                const int r = ((x * S.tab_cos[n] + y * S.tab_sin[n]) >> 10) + S.half;
+                atomicAdd(&L.acc[S.cell_base[n] + (r - S.rlo[n])], 1u);
+              }
+            }
+          }
         }
     n_edge = (int)warp_sum_u64((unsigned long long)n_edge);
     if ((tid & 31) == 0 && n_edge) atomicAdd(&s_nedge, n_edge);
@@ -303,7 +337,7 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
 
   // ---- 7. votes, hough.cpp:152-158: shared-memory atomics on the compacted accumulator
   {
-    const int nvote = s_nvote;
+    const int nvote = min(s_nvote, list_cap);
     for (int e = tid; e < nvote; e += kThreads) {
       const int o = L.list[e];
       const int yy = o / wp;
@@ -357,7 +391,7 @@ size_t detect_smem_bytes(const DetectParams &p) {
   for (int s = 0; s < 4; s++) {
     const StripDesc &d = p.strip[s];
     const size_t npx = (size_t)d.w * d.h, npad = (size_t)(d.w + 2) * (d.h + 2);
-    size_t b = align16(npx) + align16(npad) + align16(npx * 2);  // src, map, list
+    size_t b = align16(npx) + align16(npad);  // src (later the work lists), map
     if (!p.use_global_grad) b += 2 * align16(npad * 2);
     b += (size_t)d.ncells * 4 + 64;
     worst = b > worst ? b : worst;

@@ -288,10 +288,17 @@ __device__ __forceinline__ void warp_coords(const double *M, double X0, double Y
   r = __fma_rn(r, __fma_rn(-Wr, r, 1.0), r);
   const double w32 = r * 32.0;
   const double fx = nx * w32, fy = ny * w32;
-  int xi = __double2int_rn(fx), yi = __double2int_rn(fy);
-  const double ex = fabs(fx - (double)xi), ey = fabs(fy - (double)yi);
-  const double aw = fabs(Wr);
-  if (!(ex < 0.499999 && ey < 0.499999 && aw > 1e-200 && aw < 1e200)) {
+  // round-half-even to integer with the 1.5 * 2^52 trick (valid for |f| < 2^31): no FP64<->int conversions
+  const double kMagic = 6755399441055744.0;
+  const double tx = fx + kMagic, ty = fy + kMagic;
+  int xi = __double2loint(tx), yi = __double2loint(ty);
+  const double ex = fx - (tx - kMagic), ey = fy - (ty - kMagic);
+  // "safe" = rounding residual below 0.499999 and |f| < 2^31, tested on the high words (positive doubles order like
+  // their bit patterns; NaN / inf from a degenerate W compare as unsafe)
+  const unsigned hex = (unsigned)__double2hiint(ex) & 0x7fffffffu, hey = (unsigned)__double2hiint(ey) & 0x7fffffffu;
+  const unsigned hfx = (unsigned)__double2hiint(fx) & 0x7fffffffu, hfy = (unsigned)__double2hiint(fy) & 0x7fffffffu;
+  const bool safe = (hex < 0x3FDFFFFBu) & (hey < 0x3FDFFFFBu) & (hfx < 0x41E00000u) & (hfy < 0x41E00000u);
+  if (!safe) {
     double W = Wr != 0.0 ? 32. / Wr : 0.0;  // exact reference sequence
     const double gx = nx * W, gy = ny * W;
     xi = __double2int_rn(gx);  // cvt.rni.s32.f64: round-half-even, saturating == saturate_cast<int>(clamp(.))
@@ -332,7 +339,7 @@ __device__ __forceinline__ int warp_sample(const uint8_t *__restrict__ src, int 
 
 // card_check (optional): per-frame checksum sum_i (i + 1) * card[i] mod 2^32, accumulated while the pixels are
 // still in registers (one global atomic per CTA) so that no later stage has to re-read the card for it.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 warp_kernel(const uint8_t *__restrict__ src, int row_stride, size_t frame_stride, int sw, int sh,
             const FrameGeom *__restrict__ geom, uint8_t *__restrict__ cards, unsigned int *__restrict__ card_check, int ox, int oy) {
   const int frame = blockIdx.y;

@@ -77,7 +77,35 @@ def test_detect_edge_cases(dmz, oracle):
     assert lines["n_edge_px"][1].sum() == 0
 
 
-def test_chroma_fallback_exact(dmz, oracle):
+def test_detect_textured_frames(dmz, oracle):
+    """Dense textures: many NMS candidates / edge pixels per strip (exercises the candidate- and vote-list overflow
+    paths of the detect kernel).  Every per-strip tap must still equal the oracle's."""
+    yy, xx = np.mgrid[0:480, 0:640]
+    rng = np.random.default_rng(21)
+    frames = []
+    for period in (3, 4, 5, 8):
+        frames.append((127 + 120 * np.sin(2 * np.pi * xx / period)).astype(np.uint8))
+        frames.append((127 + 120 * np.sin(2 * np.pi * yy / period)).astype(np.uint8))
+        frames.append((127 + 60 * np.sin(2 * np.pi * xx / period) + 60 * np.sin(2 * np.pi * yy / (period + 1))).astype(np.uint8))
+    frames.append(((xx // 2 + yy // 2) % 2 * 255).astype(np.uint8))
+    frames.append(((xx + yy) % 2 * 200 + 20).astype(np.uint8))
+    n = rng.integers(0, 256, (480, 640)).astype(np.float32)
+    sm = (n + np.roll(n, 1, 0) + np.roll(n, 1, 1) + np.roll(n, -1, 0) + np.roll(n, -1, 1)) / 5
+    frames.append(sm.astype(np.uint8))
+    frames = np.stack(frames)
+    edges, corners, found, lines = dmz.detect_edges(frames, want_lines=True)
+    boxes = oracle.detection_boxes(640, 480)
+    for k in range(len(frames)):
+        for s_, (x, y, w, h) in enumerate(boxes):
+            ol = oracle.best_line(frames[k][y:y + h, x:x + w], s_ >= 2)
+            gl = lines[k, s_]
+            for f in ("found", "max_votes", "low", "high", "n_edge_px"):
+                assert int(gl[f]) == getattr(ol, f), (k, s_, f, int(gl[f]), getattr(ol, f))
+            if ol.found:
+                assert (int(gl["r"]), int(gl["n"])) == (ol.r, ol.n), (k, s_)
+
+
+
     f = deck_frames(5, 1)[0]
     cb = np.ascontiguousarray(f[::2, ::2])
     cr = np.full((240, 320), 128, np.uint8)
