@@ -513,7 +513,7 @@ int b200_process_frames_batch(b200_ctx *ctx, const uint8_t *y, int yrs, size_t y
     const int m = ctx->crop_margin;
     // Whole rows when the caller's rows are dense: each frame's region is then ONE contiguous host segment
     // (measured: 496-byte pitched rows reach ~34 GB/s over PCIe Gen5, contiguous 200 KB segments ~53 GB/s).
-    if (yrs == width) {
+    if (yrs == width && !getenv("B200_DMZ_CROP_COLS")) {
       crop.x0 = 0, crop.x1 = width;
     } else {
       crop.x0 = (x0 - m > 0 ? x0 - m : 0) & ~15;
@@ -531,7 +531,18 @@ int b200_process_frames_batch(b200_ctx *ctx, const uint8_t *y, int yrs, size_t y
     rc = ensure_capacity(ctx, &ctx->lane[i], chunk, width, height, true);
     if (rc) return rc;
   }
-  std::vector<uint8_t> flags(crop.active() ? n : 0);
+  // needs-full-frame flags come back into PINNED memory: an async D2H into pageable memory would block the host
+  // at every chunk and serialise the two lanes
+  uint8_t *flags = nullptr;
+  if (crop.active()) {
+    if (ctx->pinned_bytes < (size_t)n) {
+      if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+      ctx->h_pinned = nullptr, ctx->pinned_bytes = 0;
+      CU(cudaHostAlloc(&ctx->h_pinned, (size_t)n, cudaHostAllocDefault));
+      ctx->pinned_bytes = (size_t)n;
+    }
+    flags = (uint8_t *)ctx->h_pinned;
+  }
   int k = 0;
   for (int f0 = 0; f0 < n; f0 += chunk, k++) {
     Lane *l = &ctx->lane[k & 1];
@@ -565,13 +576,13 @@ int b200_process_frames_batch(b200_ctx *ctx, const uint8_t *y, int yrs, size_t y
     if (rc) return rc;
     CU(cudaMemcpyAsync(records + f0, l->d_records, sizeof(b200_frame_record) * cnt, cudaMemcpyDeviceToHost, l->stream));
     ctx->d2h_bytes += sizeof(b200_frame_record) * (uint64_t)cnt + (crop.active() ? cnt : 0) + (cards_out ? kCardBytes * cnt : 0);
-    if (crop.active()) CU(cudaMemcpyAsync(flags.data() + f0, l->d_flags, cnt, cudaMemcpyDeviceToHost, l->stream));
+    if (crop.active()) CU(cudaMemcpyAsync(flags + f0, l->d_flags, cnt, cudaMemcpyDeviceToHost, l->stream));
     if (cards_out) CU(cudaMemcpyAsync(cards_out + (size_t)f0 * kCardBytes, l->d_cards, kCardBytes * cnt, cudaMemcpyDeviceToHost, l->stream));
   }
   CU(cudaStreamSynchronize(ctx->lane[0].stream));
   if (k > 1) CU(cudaStreamSynchronize(ctx->lane[1].stream));
   // frames whose card quad reaches outside the uploaded rectangle: redo from the whole frame
-  for (int i = 0; i < (int)flags.size(); i++) {
+  for (int i = 0; i < (crop.active() ? n : 0); i++) {
     if (!flags[i]) continue;
     Lane *l = &ctx->lane[0];
     const uint8_t *dy;

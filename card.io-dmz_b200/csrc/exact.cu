@@ -267,8 +267,10 @@ __global__ void homography_only_kernel(const float *__restrict__ src, const floa
 // weights, out-of-image taps being 0.  Each thread produces four horizontally adjacent pixels (one
 // 32-bit store); a CTA covers kWarpRows destination rows of one frame.
 // ------------------------------------------------------------------------------------------------
-constexpr int kWarpRows = 8;
-constexpr int kQuadsPerRow = B200_CARD_W / 4;  // 107
+constexpr int kWarpRows = 10;                   // 270 = 27 x 10: no ragged last block
+constexpr int kQuadsPerRow = B200_CARD_W / 4;  // 107 four-pixel groups per destination row
+constexpr int kWarpThreads = 224;               // 2 x 107 = 214 workers (two rows per pass, five passes, equal work each),
+                                                // padded to whole warps so the final warp-shuffle reduction is well defined
 
 // src points at pixel (0, 0) of the sw x sh frame (the host-buffer path uploads only a crop and passes a
 // correspondingly shifted pointer); the crop is guaranteed by the caller to contain every in-image tap of the quad.
@@ -339,7 +341,7 @@ __device__ __forceinline__ int warp_sample(const uint8_t *__restrict__ src, int 
 
 // card_check (optional): per-frame checksum sum_i (i + 1) * card[i] mod 2^32, accumulated while the pixels are
 // still in registers (one global atomic per CTA) so that no later stage has to re-read the card for it.
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(kWarpThreads, 4)
 warp_kernel(const uint8_t *__restrict__ src, int row_stride, size_t frame_stride, int sw, int sh,
             const FrameGeom *__restrict__ geom, uint8_t *__restrict__ cards, unsigned int *__restrict__ card_check, int ox, int oy) {
   const int frame = blockIdx.y;
@@ -355,8 +357,8 @@ warp_kernel(const uint8_t *__restrict__ src, int row_stride, size_t frame_stride
   const uint8_t *s = src + (size_t)frame * frame_stride - ((ptrdiff_t)oy * row_stride + ox);
   const int nrows = min(kWarpRows, B200_CARD_H - row0);
   unsigned int sum = 0;
-  int r = threadIdx.x / kQuadsPerRow, q = threadIdx.x - r * kQuadsPerRow;  // 256 = 2 * 107 + 42
-  for (; r < nrows;) {
+  const int r0 = threadIdx.x >= kQuadsPerRow ? 1 : 0, q = threadIdx.x - r0 * kQuadsPerRow;
+  for (int r = threadIdx.x < 2 * kQuadsPerRow ? r0 : nrows; r < nrows; r += 2) {
     const int y = row0 + r, x = q * 4;
     unsigned int packed = 0;
     if (s_ok) {
@@ -373,10 +375,6 @@ warp_kernel(const uint8_t *__restrict__ src, int row_stride, size_t frame_stride
       }
     }
     *reinterpret_cast<unsigned int *>(dst + y * B200_CARD_W + x) = packed;
-    // advance by blockDim.x = 256 quads = 2 rows + 42 quads, without a division
-    q += 256 - 2 * kQuadsPerRow;
-    r += 2;
-    if (q >= kQuadsPerRow) q -= kQuadsPerRow, r += 1;
   }
   if (card_check != nullptr) {
 #pragma unroll
@@ -745,7 +743,7 @@ int launch_warp(const uint8_t *src, int row_stride, size_t frame_stride, int w, 
   const int row_blocks = (B200_CARD_H + kWarpRows - 1) / kWarpRows;
   for (int f0 = 0; f0 < n; f0 += 65535) {
     const int cnt = n - f0 < 65535 ? n - f0 : 65535;
-    warp_kernel<<<dim3(row_blocks, cnt), 256, 0, s>>>(src + (size_t)f0 * frame_stride, row_stride, frame_stride, w, h, geom + f0,
+    warp_kernel<<<dim3(row_blocks, cnt), kWarpThreads, 0, s>>>(src + (size_t)f0 * frame_stride, row_stride, frame_stride, w, h, geom + f0,
                                                       cards + (size_t)f0 * (B200_CARD_W * B200_CARD_H),
                                                       card_check ? card_check + f0 : nullptr, ox, oy);
     launches++;
