@@ -511,9 +511,10 @@ int b200_process_frames_batch(b200_ctx *ctx, const uint8_t *y, int yrs, size_t y
       x1 = d.x + d.w > x1 ? d.x + d.w : x1, y1 = d.y + d.h > y1 ? d.y + d.h : y1;
     }
     const int m = ctx->crop_margin;
-    // Whole rows when the caller's rows are dense: each frame's region is then ONE contiguous host segment
-    // (measured: 496-byte pitched rows reach ~34 GB/s over PCIe Gen5, contiguous 200 KB segments ~53 GB/s).
-    if (yrs == width && !getenv("B200_DMZ_CROP_COLS")) {
+    // Measured on B200 / PCIe Gen5 (16384-frame steps): whole frames 307 KB @ 53.7 GB/s = 175 k frames/s; whole-row
+    // band 200 KB @ 52.9 GB/s = 264 k frames/s; row+column rectangle 155 KB @ 46.9 GB/s (pitched 3-D copy) =
+    // 302 k frames/s.  The rectangle wins; B200_DMZ_CROP_ROWS=1 selects the whole-row band instead.
+    if (yrs == width && getenv("B200_DMZ_CROP_ROWS")) {
       crop.x0 = 0, crop.x1 = width;
     } else {
       crop.x0 = (x0 - m > 0 ? x0 - m : 0) & ~15;

@@ -277,6 +277,26 @@ def test_720p_frames(dmz, oracle):
     assert want["all_found"].all()
 
 
+def test_1080p_detect_and_path(dmz, oracle):
+    """BASELINE configs[3] sizes: the 1080p strips (875x64, 86x543) exceed shared memory for dx/dy, so the detect
+    kernel keeps the gradients in a global scratch slab; results must not change."""
+    fr = deck_frames(0, 2, 1920, 1080)
+    edges, corners, found, lines = dmz.detect_edges(fr, want_lines=True)
+    boxes = oracle.detection_boxes(1920, 1080)
+    for k in range(2):
+        for s_, (x, y, w, h) in enumerate(boxes):
+            ol = oracle.best_line(fr[k][y:y + h, x:x + w], s_ >= 2)
+            gl = lines[k, s_]
+            for f in ("found", "max_votes", "low", "high", "n_edge_px"):
+                assert int(gl[f]) == getattr(ol, f), (k, s_, f)
+            if ol.found:
+                assert (int(gl["r"]), int(gl["n"])) == (ol.r, ol.n)
+    want = oracle.process_frames(fr)
+    got = dmz.process_frames(fr)
+    for f in ("found", "all_found", "card_check", "v_y_offset", "usable"):
+        assert np.array_equal(got[f], want[f]), f
+
+
 def test_bad_arguments_fail_cleanly(dmz, pkg):
     with pytest.raises(pkg.B200Error):
         dmz.process_frames(np.zeros((1, 16, 16), np.uint8))  # frame too small for detection strips
