@@ -310,8 +310,14 @@ def main():
         if dom:
             ach = ALG_BYTES[dom] * stage_frames / (stage_ms[dom] * 1e-3) / 1e9
             pipe = ALG_BYTES["pipeline_materialised"] * stage_frames / (sum(stage_ms.values()) * 1e-3) / 1e9
+            traffic = None
+            try:
+                tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+                traffic = {"bytes_per_launch": tj["per_frame"][dom] * F, "bytes_per_frame": tj["per_frame"][dom], "source": tj["source"]}
+            except Exception:
+                pass
             roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": None, "peak_source": peak_src, "alg_bytes_per_frame": ALG_BYTES[dom],
+                    "traffic": traffic, "peak_source": peak_src, "alg_bytes_per_frame": ALG_BYTES[dom],
                     "share_of_step": stage_ms[dom] / sum(stage_ms.values()),
                     "pipeline": {"alg_bytes_per_frame": ALG_BYTES["pipeline_materialised"], "achieved": pipe, "frac": pipe / peak},
                     "note": "per-stage CUDA-event times on the launching stream; stages other than detect/warp are FP32/latency bound (DESIGN.md)"}
