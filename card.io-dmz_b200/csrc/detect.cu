@@ -6,9 +6,10 @@
 //   llcv_hough                             cv/hough.cpp:52-196    (gradient-gated votes, first-max argmax)
 //
 // Data flow inside the CTA (everything after the first load stays in shared memory):
-//   global u8 strip --(32-bit coalesced loads)--> s_src[h][w]
-//   Sobel: one work item per (column, row chunk) walks down its rows keeping the last seven row-filter
-//          results for both kernels in registers (no intermediate image) --> s_dx, s_dy (s16, zero-padded border)
+//   global u8 strip --(32-bit coalesced loads)--> s_src[h][ws] with a 3-pixel replicated halo left and right
+//   Sobel: one work item per (column, row chunk) walks down its rows; each row filter is two dp4a over the eight
+//          bytes around the pixel (3 aligned LDS.32 + funnel shifts), the last seven row results of both kernels
+//          live in a register ring (no intermediate image) --> s_dx, s_dy (s16, zero-padded border)
 //   thresholds: block reduction (warp shuffles) of the saturated |dx| + |dy| sums, 64-bit exact
 //   NMS: per pixel from s_dx / s_dy --> s_map {0 candidate, 1 no edge, 2 edge}; candidates go to a work list
 //   hysteresis: propagation over the candidate list to the unique fixed point (= the reference's stack walk)
@@ -79,7 +80,7 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
                      b200_line *__restrict__ lines, int16_t *__restrict__ grad_scratch, size_t grad_scratch_stride, int ox, int oy) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __shared__ unsigned long long s_red[kThreads / 32];
-  __shared__ int s_low, s_high, s_ncand, s_nvote, s_nedge;
+  __shared__ int s_low, s_high, s_ncand, s_nvote, s_nedge, s_overflow;
 
   const int strip = blockIdx.x;
   const int frame = blockIdx.y;
@@ -87,6 +88,7 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
   const StripDesc &S = P.strip[strip];
   const int w = S.w, h = S.h, npx = w * h;
   const int wp = w + 2, npad = wp * (h + 2);
+  const int ws = ((w + 6 + 3) & ~3) + 4;  // source row stride: 3-px halo each side, 4-byte aligned, room for 12-byte reads
   const size_t out_idx = (size_t)frame * 4 + strip;
 
   // Fallback planes: skip strips whose edge was already found on an earlier plane (dmz.cpp:351).
@@ -104,7 +106,7 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
   SmemLayout L;
   size_t off = 0;
   L.src = smem_raw + off;
-  off = align16(off + (size_t)npx);
+  off = align16(off + (size_t)ws * h);
   if (P.use_global_grad) {
     L.dx = grad_scratch + ((size_t)frame * 4 + strip) * grad_scratch_stride;
     L.dy = L.dx + grad_scratch_stride / 2;
@@ -117,8 +119,10 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
   L.map = smem_raw + off;
   off = align16(off + (size_t)npad);
   L.acc = reinterpret_cast<unsigned int *>(smem_raw + off);
-  L.list = reinterpret_cast<unsigned short *>(L.src);  // npx bytes = npx / 2 entries; overflow falls back to full scans
-  const int list_cap = npx >> 1;
+  // work lists alias the (by then dead) source strip: candidates in the first half, votes in the second
+  L.list = reinterpret_cast<unsigned short *>(L.src);
+  const int list_cap = (ws * h) >> 2;  // entries per list; overflow falls back to full scans
+  unsigned short *vote_list = L.list + list_cap;
 
   // ---- 1. load the strip (32-bit coalesced loads of the covering aligned words); clear borders / accumulator
   {
@@ -133,7 +137,7 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
           for (int q = k.tx; q < words; q += k.xstep) {
             const unsigned int v = __ldg(reinterpret_cast<const unsigned int *>(base + (size_t)row * row_stride - shift) + q);
             const int c0 = q * 4 - shift;
-            uint8_t *dst = L.src + row * w;
+            uint8_t *dst = L.src + row * ws + 3;
 #pragma unroll
             for (int b = 0; b < 4; b++) {
               const int c = c0 + b;
@@ -144,7 +148,7 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
       const Walk k = make_walk(tid, w, kThreads);
       if (k.active)
         for (int row = k.ty; row < h; row += k.ystep)
-          for (int c = k.tx; c < w; c += k.xstep) L.src[row * w + c] = __ldg(base + (size_t)row * row_stride + c);
+          for (int c = k.tx; c < w; c += k.xstep) L.src[row * ws + 3 + c] = __ldg(base + (size_t)row * row_stride + c);
     }
   }
   for (int i = tid; i < S.ncells; i += kThreads) L.acc[i] = 0u;
@@ -159,10 +163,18 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
     L.dx[a] = 0, L.dy[a] = 0, L.map[a] = 1;
     L.dx[b] = 0, L.dy[b] = 0, L.map[b] = 1;
   }
-  if (tid == 0) s_ncand = 0, s_nvote = 0, s_nedge = 0;
+  if (tid == 0) s_ncand = 0, s_nvote = 0, s_nedge = 0, s_overflow = 0;
+  __syncthreads();
+  // BORDER_REPLICATE halo: three copies of the first / last pixel of every row
+  for (int y = tid; y < h; y += kThreads) {
+    uint8_t *r = L.src + y * ws;
+    const uint8_t a = r[3], b = r[3 + w - 1];
+    r[0] = a, r[1] = a, r[2] = a;
+    r[3 + w] = b, r[4 + w] = b, r[5 + w] = b;
+  }
   __syncthreads();
 
-  // ---- 2. Sobel-7 dx, dy with a register sliding window; accumulate the saturated |.| sums on the fly
+  // ---- 2. Sobel-7 dx, dy; accumulate the saturated |.| sums on the fly
   unsigned long long abs_sum = 0;
   {
     const int items = w * S.nchunks;
@@ -170,34 +182,40 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
       const int chunk = it / w, x = it - chunk * w;
       const int y0 = chunk * S.chunk_rows;
       const int y1 = min(h, y0 + S.chunk_rows);
-      int xo[7];  // column offsets with BORDER_REPLICATE at the ROI edge
+      const int word = x >> 2, sh = (x & 3) * 8;  // padded column x holds pixel x - 3: bytes x .. x+6 are the seven taps
+      int hx[7], sx[7];  // ring of row-filter results: derivative taps [-1,-4,-5,0,5,4,1], smoothing taps [1,6,15,20,15,6,1]
+      auto row_filter = [&](int row, int &hxo, int &sxo) {
+        const unsigned int *r32 = reinterpret_cast<const unsigned int *>(L.src + row * ws) + word;
+        const unsigned int w0 = r32[0], w1 = r32[1], w2 = r32[2];
+        const unsigned int lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);  // p0..p3, p4..p7
+        int a, b;
+        asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(a) : "r"(lo), "r"(0x00FBFCFF), "r"(0));   // -1 -4 -5  0
+        asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(a) : "r"(hi), "r"(0x00010405), "r"(a));   //  5  4  1  .
+        asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(b) : "r"(lo), "r"(0x140F0601), "r"(0));   //  1  6 15 20
+        asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(b) : "r"(hi), "r"(0x0001060F), "r"(b));   // 15  6  1  .
+        hxo = a, sxo = b;
+      };
 #pragma unroll
-      for (int k = 0; k < 7; k++) xo[k] = clampi(x + k - 3, 0, w - 1);
-      int hx[7], sx[7];  // row-filter results of the last seven rows: derivative taps, smoothing taps
-#pragma unroll
-      for (int k = 0; k < 6; k++) {  // prime with rows y0-3 .. y0+2 (clamped)
-        const uint8_t *r = L.src + clampi(y0 + k - 3, 0, h - 1) * w;
-        const int p0 = r[xo[0]], p1 = r[xo[1]], p2 = r[xo[2]], p3 = r[xo[3]], p4 = r[xo[4]], p5 = r[xo[5]], p6 = r[xo[6]];
-        hx[k + 1] = (p6 - p0) + 4 * (p5 - p1) + 5 * (p4 - p2);             // [-1,-4,-5,0,5,4,1]
-        sx[k + 1] = (p0 + p6) + 6 * (p1 + p5) + 15 * (p2 + p4) + 20 * p3;  // [1,6,15,20,15,6,1]
-      }
+      for (int k = 0; k < 6; k++) row_filter(clampi(y0 + k - 3, 0, h - 1), hx[k], sx[k]);  // rows y0-3 .. y0+2
       int o = (y0 + 1) * wp + x + 1;
-      for (int y = y0; y < y1; y++, o += wp) {
+      for (int y = y0; y < y1; y += 7) {
+        // seven output rows per trip: the ring slot of every tap is a compile-time constant, no register shuffling
 #pragma unroll
-        for (int k = 0; k < 6; k++) hx[k] = hx[k + 1], sx[k] = sx[k + 1];
-        {
-          const uint8_t *r = L.src + min(y + 3, h - 1) * w;
-          const int p0 = r[xo[0]], p1 = r[xo[1]], p2 = r[xo[2]], p3 = r[xo[3]], p4 = r[xo[4]], p5 = r[xo[5]], p6 = r[xo[6]];
-          hx[6] = (p6 - p0) + 4 * (p5 - p1) + 5 * (p4 - p2);
-          sx[6] = (p0 + p6) + 6 * (p1 + p5) + 15 * (p2 + p4) + 20 * p3;
+        for (int k = 0; k < 7; k++) {
+          if (y + k < y1) {
+            row_filter(min(y + k + 3, h - 1), hx[(k + 6) % 7], sx[(k + 6) % 7]);
+            int gx = (hx[k % 7] + hx[(k + 6) % 7]) + 6 * (hx[(k + 1) % 7] + hx[(k + 5) % 7]) +
+                     15 * (hx[(k + 2) % 7] + hx[(k + 4) % 7]) + 20 * hx[(k + 3) % 7];        // smooth down the column
+            int gy = (sx[(k + 6) % 7] - sx[k % 7]) + 4 * (sx[(k + 5) % 7] - sx[(k + 1) % 7]) +
+                     5 * (sx[(k + 4) % 7] - sx[(k + 2) % 7]);                                  // derivative down the column
+            gx = clampi(gx, -32768, 32767);  // saturate_cast<short>
+            gy = clampi(gy, -32768, 32767);
+            L.dx[o] = (int16_t)gx;
+            L.dy[o] = (int16_t)gy;
+            abs_sum += (unsigned)min(abs(gx), 32767) + (unsigned)min(abs(gy), 32767);  // cvAbs saturates, canny.cpp:355-361
+            o += wp;
+          }
         }
-        int gx = (hx[0] + hx[6]) + 6 * (hx[1] + hx[5]) + 15 * (hx[2] + hx[4]) + 20 * hx[3];  // smooth down the column
-        int gy = (sx[6] - sx[0]) + 4 * (sx[5] - sx[1]) + 5 * (sx[4] - sx[2]);               // derivative down the column
-        gx = clampi(gx, -32768, 32767);  // saturate_cast<short>
-        gy = clampi(gy, -32768, 32767);
-        L.dx[o] = (int16_t)gx;
-        L.dy[o] = (int16_t)gy;
-        abs_sum += (unsigned)min(abs(gx), 32767) + (unsigned)min(abs(gy), 32767);  // cvAbs saturates, canny.cpp:355-361
       }
     }
   }
@@ -215,7 +233,24 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
   __syncthreads();
   const int low = s_low, high = s_high;
 
-  // ---- 4. non-maxima suppression, canny.cpp:220-285; candidates are appended to the hysteresis work list
+  // gradient-direction gate of the Hough stage (hough.cpp:126-150) for the pixel at padded index o
+  auto gate = [&](int o) -> bool {
+    const int del_x = L.dx[o], del_y = L.dy[o];
+    if (del_x != 0) {
+      const float slope = (float)del_y / (float)del_x;
+      return S.vertical ? (slope >= S.slope_a && slope <= S.slope_b) : (slope >= S.slope_a || slope <= S.slope_b);
+    }
+    return !S.vertical;
+  };
+  auto push_vote = [&](int o) {
+    const int slot = atomicAdd(&s_nvote, 1);
+    if (slot < list_cap) vote_list[slot] = (unsigned short)o;
+    else s_overflow = 1;
+  };
+  int n_edge = 0;
+
+  // ---- 4. non-maxima suppression, canny.cpp:220-285.  The source strip is dead now: weak candidates go to the
+  // hysteresis work list, strong pixels (edges for sure) are gated and queued for voting right away.
   {
     const Walk k = make_walk(tid, w, kThreads);
     if (k.active)
@@ -243,10 +278,13 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
             if (is_max) {
               if (m > high) {
                 out = 2;
+                n_edge++;
+                if (gate(o)) push_vote(o);
               } else {
                 out = 0;
                 const int slot = atomicAdd(&s_ncand, 1);
                 if (slot < list_cap) L.list[slot] = (unsigned short)o;
+                else s_overflow = 1;
               }
             }
           }
@@ -257,6 +295,7 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
 
   // ---- 5. hysteresis: a candidate 8-connected to an edge pixel becomes an edge pixel; iterate over the (short)
   // candidate list to the fixed point, which is the reference's stack-walk result whatever the visiting order.
+  // A promoted candidate is gated and queued for voting on the spot (each candidate is promoted exactly once).
   {
     const int ncand = s_ncand;
     if (ncand <= list_cap) {
@@ -271,6 +310,8 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
           if (hit) {
             L.map[o] = 2;
             changed = 1;
+            n_edge++;
+            if (gate(o)) push_vote(o);
           }
         }
         if (!__syncthreads_or(changed)) break;
@@ -297,49 +338,13 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
       }
     }
   }
+  __syncthreads();  // s_overflow / s_nvote final
 
-  // ---- 6. vote list: edge pixels that pass the gradient-direction gate, hough.cpp:126-150 (the candidate list is
-  // dead after the fixed point, its storage is reused)
-  {
-    const Walk k = make_walk(tid, w, kThreads);
-    int n_edge = 0;
-    if (k.active)
-      for (int y = k.ty; y < h; y += k.ystep)
-        for (int x = k.tx; x < w; x += k.xstep) {
-          const int o = (y + 1) * wp + x + 1;
-          if (L.map[o] != 2) continue;
-          n_edge++;
-          const int del_x = L.dx[o], del_y = L.dy[o];
-          bool use;
-          if (del_x != 0) {
-            const float slope = (float)del_y / (float)del_x;
-            use = S.vertical ? (slope >= S.slope_a && slope <= S.slope_b) : (slope >= S.slope_a || slope <= S.slope_b);
-          } else {
-            use = !S.vertical;
-          }
-          if (use) {
-            const int slot = atomicAdd(&s_nvote, 1);
-            if (slot < list_cap) {
-              L.list[slot] = (unsigned short)o;
-            } else {  // list full: vote directly
-#pragma unroll
-              for (int n = 0; n < B200_NUMANGLE; n++) {
-                const int r = ((x * S.tab_cos[n] + y * S.tab_sin[n]) >> 10) + S.half;
-                atomicAdd(&L.acc[S.cell_base[n] + (r - S.rlo[n])], 1u);
-              }
-            }
-          }
-        }
-    n_edge = (int)warp_sum_u64((unsigned long long)n_edge);
-    if ((tid & 31) == 0 && n_edge) atomicAdd(&s_nedge, n_edge);
-  }
-  __syncthreads();
-
-  // ---- 7. votes, hough.cpp:152-158: shared-memory atomics on the compacted accumulator
-  {
-    const int nvote = min(s_nvote, list_cap);
+  // ---- 6/7. votes, hough.cpp:152-158: shared-memory atomics on the compacted accumulator
+  if (!s_overflow) {
+    const int nvote = s_nvote;
     for (int e = tid; e < nvote; e += kThreads) {
-      const int o = L.list[e];
+      const int o = vote_list[e];
       const int yy = o / wp;
       const int x = o - yy * wp - 1, y = yy - 1;
 #pragma unroll
@@ -348,7 +353,27 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
         atomicAdd(&L.acc[S.cell_base[n] + (r - S.rlo[n])], 1u);
       }
     }
+  } else {
+    // a work list overflowed: ignore the lists, recount and vote by scanning the final map
+    n_edge = 0;
+    const Walk k = make_walk(tid, w, kThreads);
+    if (k.active)
+      for (int y = k.ty; y < h; y += k.ystep)
+        for (int x = k.tx; x < w; x += k.xstep) {
+          const int o = (y + 1) * wp + x + 1;
+          if (L.map[o] != 2) continue;
+          n_edge++;
+          if (gate(o)) {
+#pragma unroll
+            for (int n = 0; n < B200_NUMANGLE; n++) {
+              const int r = ((x * S.tab_cos[n] + y * S.tab_sin[n]) >> 10) + S.half;
+              atomicAdd(&L.acc[S.cell_base[n] + (r - S.rlo[n])], 1u);
+            }
+          }
+        }
   }
+  n_edge = (int)warp_sum_u64((unsigned long long)n_edge);
+  if ((tid & 31) == 0 && n_edge) atomicAdd(&s_nedge, n_edge);
   __syncthreads();
 
   // ---- 8. argmax in the reference's scan order (r outer, n inner, first strict maximum), hough.cpp:165-176
@@ -390,8 +415,9 @@ size_t detect_smem_bytes(const DetectParams &p) {
   size_t worst = 0;
   for (int s = 0; s < 4; s++) {
     const StripDesc &d = p.strip[s];
-    const size_t npx = (size_t)d.w * d.h, npad = (size_t)(d.w + 2) * (d.h + 2);
-    size_t b = align16(npx) + align16(npad);  // src (later the work lists), map
+    const size_t npad = (size_t)(d.w + 2) * (d.h + 2);
+    const size_t ws = (((size_t)d.w + 6 + 3) & ~(size_t)3) + 4;
+    size_t b = align16(ws * d.h) + align16(npad);  // padded src (later the work lists), map
     if (!p.use_global_grad) b += 2 * align16(npad * 2);
     b += (size_t)d.ncells * 4 + 64;
     worst = b > worst ? b : worst;
