@@ -22,6 +22,7 @@ constexpr size_t kCardBytes = (size_t)B200_CARD_W * B200_CARD_H;
 struct Lane {
   cudaStream_t stream = nullptr;
   int cap = 0, cap_w = 0, cap_h = 0;
+  size_t frame_bytes = 0;  // size of d_frames (host-buffer staging)
   uint8_t *d_frames = nullptr, *d_cb = nullptr, *d_cr = nullptr;
   b200_line *d_lines = nullptr;  // 3 * cap * 4
   FrameGeom *d_geom = nullptr;
@@ -125,6 +126,7 @@ void free_lane(Lane *l) {
   l->d_lines = nullptr, l->d_geom = nullptr, l->d_cards = nullptr, l->d_vprob = nullptr, l->d_scan = nullptr;
   l->d_records = nullptr, l->d_grad = nullptr, l->d_check = nullptr, l->d_flags = nullptr;
   l->grad_elems = 0;
+  l->frame_bytes = 0;
   l->cap = 0;
 }
 
@@ -151,26 +153,38 @@ int ensure_config(b200_ctx *ctx, int w, int h, int orientation, int planes) {
 }
 
 int ensure_capacity(b200_ctx *ctx, Lane *l, int n, int w, int h, bool need_frames) {
-  if (n <= l->cap && (size_t)w * h <= (size_t)l->cap_w * l->cap_h && (!need_frames || l->d_frames)) return B200_OK;
-  int cap = n > l->cap ? n : l->cap;
-  int cw = w, chh = h;
-  if ((size_t)l->cap_w * l->cap_h > (size_t)w * h) cw = l->cap_w, chh = l->cap_h;
-  bool had_frames = l->d_frames != nullptr;
-  free_lane(l);
-  if (need_frames || had_frames) {
-    CU(cudaMalloc(&l->d_frames, (size_t)cap * cw * chh));
-    CU(cudaMalloc(&l->d_cb, (size_t)cap * (cw / 2) * (chh / 2)));
-    CU(cudaMalloc(&l->d_cr, (size_t)cap * (cw / 2) * (chh / 2)));
+  // per-frame records / cards: sized by frame COUNT
+  if (n > l->cap) {
+    uint8_t *keep_frames = l->d_frames, *keep_cb = l->d_cb, *keep_cr = l->d_cr;
+    const size_t keep_bytes = l->frame_bytes;
+    l->d_frames = l->d_cb = l->d_cr = nullptr;  // staging buffers are managed below
+    free_lane(l);
+    l->d_frames = keep_frames, l->d_cb = keep_cb, l->d_cr = keep_cr;
+    l->frame_bytes = keep_bytes;
+    CU(cudaMalloc(&l->d_lines, sizeof(b200_line) * 3 * (size_t)n * 4));
+    CU(cudaMalloc(&l->d_geom, sizeof(FrameGeom) * (size_t)n));
+    CU(cudaMalloc(&l->d_cards, kCardBytes * (size_t)n));
+    CU(cudaMalloc(&l->d_vprob, (size_t)n * (540 * sizeof(float) + 16)));
+    CU(cudaMalloc(&l->d_scan, sizeof(b200_scan) * (size_t)n));
+    CU(cudaMalloc(&l->d_records, sizeof(b200_frame_record) * (size_t)n));
+    CU(cudaMalloc(&l->d_check, sizeof(unsigned int) * (size_t)n));
+    CU(cudaMalloc(&l->d_flags, (size_t)n));
+    l->cap = n;
   }
-  CU(cudaMalloc(&l->d_lines, sizeof(b200_line) * 3 * (size_t)cap * 4));
-  CU(cudaMalloc(&l->d_geom, sizeof(FrameGeom) * (size_t)cap));
-  CU(cudaMalloc(&l->d_cards, kCardBytes * (size_t)cap));
-  CU(cudaMalloc(&l->d_vprob, (size_t)cap * (540 * sizeof(float) + 16)));
-  CU(cudaMalloc(&l->d_scan, sizeof(b200_scan) * (size_t)cap));
-  CU(cudaMalloc(&l->d_records, sizeof(b200_frame_record) * (size_t)cap));
-  CU(cudaMalloc(&l->d_check, sizeof(unsigned int) * (size_t)cap));
-  CU(cudaMalloc(&l->d_flags, (size_t)cap));
-  l->cap = cap, l->cap_w = cw, l->cap_h = chh;
+  // input staging (host-buffer calls only): sized in BYTES for this call's n x w x h
+  if (need_frames) {
+    const size_t need = (size_t)n * w * h;
+    if (need > l->frame_bytes) {
+      cudaFree(l->d_frames), cudaFree(l->d_cb), cudaFree(l->d_cr);
+      l->d_frames = l->d_cb = l->d_cr = nullptr;
+      l->frame_bytes = 0;
+      CU(cudaMalloc(&l->d_frames, need));
+      CU(cudaMalloc(&l->d_cb, (size_t)n * (w / 2) * (h / 2) + 16));
+      CU(cudaMalloc(&l->d_cr, (size_t)n * (w / 2) * (h / 2) + 16));
+      l->frame_bytes = need;
+    }
+  }
+  if ((size_t)w * h > (size_t)l->cap_w * l->cap_h) l->cap_w = w, l->cap_h = h;
   return B200_OK;
 }
 

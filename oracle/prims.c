@@ -299,6 +299,51 @@ void orc_warp_perspective_u8(const uint8_t *src, int sstep, int sw, int sh, uint
     }
 }
 
+void orc_bilateral_tables(int d, double sigma_color, double sigma_space, float *color_lut, float *space_w) {
+  int radius = d / 2, i, j, k = 0;
+  double gcc, gsc;
+  if (sigma_color <= 0) sigma_color = 1;
+  if (sigma_space <= 0) sigma_space = 1;
+  gcc = -0.5 / (sigma_color * sigma_color);
+  gsc = -0.5 / (sigma_space * sigma_space);
+  if (radius < 1) radius = 1;
+  for (i = 0; i < 256; i++) color_lut[i] = (float)exp(i * i * gcc);
+  for (i = -radius; i <= radius; i++)
+    for (j = -radius; j <= radius; j++, k++) {
+      double r = sqrt((double)i * i + (double)j * j);
+      space_w[k] = r > radius ? 0.0f : (float)exp(r * r * gsc);
+    }
+}
+
+void orc_bilateral_u8(const uint8_t *src, int sstep, int w, int h, uint8_t *dst, int dstep, int d, double sigma_color,
+                      double sigma_space) {
+  float color_lut[256], space_w[81];
+  int radius = d / 2 < 1 ? 1 : d / 2, dd = 2 * radius + 1, x, y, i, j;
+  orc_bilateral_tables(d, sigma_color, sigma_space, color_lut, space_w);
+  for (y = 0; y < h; y++)
+    for (x = 0; x < w; x++) {
+      float sum = 0, wsum = 0;
+      int val0 = src[(size_t)y * sstep + x];
+      for (i = -radius; i <= radius; i++)
+        for (j = -radius; j <= radius; j++) {
+          float sw = space_w[(i + radius) * dd + (j + radius)], wgt;
+          int yy, xx, val;
+          if (sqrt((double)i * i + (double)j * j) > radius) continue;
+          yy = clampi(y + i, 0, h - 1);
+          xx = clampi(x + j, 0, w - 1);
+          val = src[(size_t)yy * sstep + xx];
+          {
+            volatile float wv = sw * color_lut[abs(val - val0)];
+            volatile float pv = val * wv;
+            wgt = wv;
+            sum = sum + pv;
+            wsum = wsum + wgt;
+          }
+        }
+      dst[(size_t)y * dstep + x] = (uint8_t)orc_cv_round(sum / wsum);
+    }
+}
+
 double orc_mean_u8(const uint8_t *src, int sstep, int w, int h) {
   double total = 0;
   int x, y;
