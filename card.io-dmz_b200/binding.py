@@ -105,6 +105,8 @@ def _load():
     lib.b200_categorize_patches_batch.argtypes = [vp, vp, i, i, vp]
     lib.b200_vseg_model_batch.argtypes = [vp, vp, i, i, vp]
     lib.b200_digit_models_batch.argtypes = [vp, vp, i, i, vp]
+    lib.b200_expiry_digits_batch.argtypes = [vp, vp, i, i, vp]
+    lib.b200_expiry_digit_models_batch.argtypes = [vp, vp, i, i, vp]
     lib.b200_set_profiling.argtypes = [vp, i]
     lib.b200_set_crop_margin.argtypes = [vp, i]
     lib.b200_full_frame_redos.argtypes = [vp]
@@ -242,6 +244,19 @@ class Dmz:
         out = np.zeros((n, 40), np.float32)
         self._check(self.lib.b200_digit_models_batch(self.ctx, _ptr(patches), n, MEM_HOST, _ptr(out)))
         return out[:, :10].copy(), out[:, 10:].reshape(n, 3, 10).copy()
+
+    def expiry_digits(self, patches):
+        """patches: (n, 16, 11) u8 character crops.  Returns (n, 10) digit probabilities (E0)."""
+        patches = np.ascontiguousarray(patches, np.uint8).reshape(-1, 176)
+        out = np.zeros((patches.shape[0], 10), np.float32)
+        self._check(self.lib.b200_expiry_digits_batch(self.ctx, _ptr(patches), patches.shape[0], MEM_HOST, _ptr(out)))
+        return out
+
+    def expiry_digit_models(self, prepared):
+        prepared = np.ascontiguousarray(prepared, np.float32).reshape(-1, 176)
+        out = np.zeros((prepared.shape[0], 10), np.float32)
+        self._check(self.lib.b200_expiry_digit_models_batch(self.ctx, _ptr(prepared), prepared.shape[0], MEM_HOST, _ptr(out)))
+        return out
 
     STAGES = ("detect", "geometry", "warp", "vseg", "hseg", "categorize", "finalize")
 

@@ -58,6 +58,7 @@ struct b200_ctx {
   float *d_vseg = nullptr;
   float *d_cnn[3] = {nullptr, nullptr, nullptr};
   float *d_hwT = nullptr;
+  float *d_expiry = nullptr;  // modelc_bf4dd6c8 blob (optional: E0 entry points need it)
   NetWeights wts{};
 
   // geometry cache
@@ -331,6 +332,16 @@ int b200_ctx_create(b200_ctx **out, int device_ordinal, const char *weights_dir)
   CU(cudaMalloc(&ctx->d_hwT, hwT.size() * sizeof(float)));
   CU(cudaMemcpy(ctx->d_hwT, hwT.data(), hwT.size() * sizeof(float), cudaMemcpyHostToDevice));
   if (upload_conv_constants(ptrs) != 0) return fail(ctx, B200_ECUDA, "cudaMemcpyToSymbol: %s", cudaGetErrorString(cudaGetLastError()));
+  {  // E0 (expiry digit): optional weights + bilateral tables
+    std::vector<float> eb;
+    if (read_blob(dir + "/modelc_bf4dd6c8.bin", &eb, 74406)) {
+      CU(cudaMalloc(&ctx->d_expiry, eb.size() * sizeof(float)));
+      CU(cudaMemcpy(ctx->d_expiry, eb.data(), eb.size() * sizeof(float), cudaMemcpyHostToDevice));
+      float color[256], space[5];
+      b200_build_bilateral_tables(color, space);
+      if (upload_bilateral_tables(color, space) != 0) return fail(ctx, B200_ECUDA, "cudaMemcpyToSymbol (bilateral tables)");
+    }
+  }
   ctx->wts.vseg = ctx->d_vseg;
   for (int m = 0; m < 3; m++) ctx->wts.cnn[m] = ctx->d_cnn[m];
   ctx->wts.cnn_hwT = ctx->d_hwT;
@@ -348,7 +359,7 @@ void b200_ctx_destroy(b200_ctx *ctx) {
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   cudaFree(ctx->d_misc);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
-  cudaFree(ctx->d_vseg), cudaFree(ctx->d_hwT);
+  cudaFree(ctx->d_vseg), cudaFree(ctx->d_hwT), cudaFree(ctx->d_expiry);
   for (int m = 0; m < 3; m++) cudaFree(ctx->d_cnn[m]);
   delete ctx;
 }
@@ -667,6 +678,40 @@ int b200_digit_models_batch(b200_ctx *ctx, const float *patches, int n, int mem,
   if (mem == B200_MEM_HOST) CU(cudaMemcpyAsync(out, dout, (size_t)n * 40 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return B200_OK;
+}
+
+static int expiry_call(b200_ctx *ctx, const uint8_t *patches, const float *prepared, int n, int mem, float *out) {
+  if (!ctx || (!patches && !prepared) || !out || n < 1) return fail(ctx, B200_EINVAL, "b200_expiry_*: bad arguments");
+  if (!ctx->d_expiry) return fail(ctx, B200_EUNSUPPORTED, "modelc_bf4dd6c8.bin was not found in the weights directory");
+  CU(cudaSetDevice(ctx->device));
+  const uint8_t *dp = patches;
+  const float *df = prepared;
+  float *dout = out;
+  if (mem == B200_MEM_HOST) {
+    int rc = ensure_misc(ctx, (size_t)n * (176 * sizeof(float) + 10 * sizeof(float)) + 64);
+    if (rc) return rc;
+    dout = (float *)ctx->d_misc;
+    uint8_t *p = (uint8_t *)ctx->d_misc + (size_t)n * 10 * sizeof(float);
+    if (patches) {
+      CU(cudaMemcpyAsync(p, patches, (size_t)n * 176, cudaMemcpyHostToDevice, ctx->stream));
+      dp = p;
+    } else {
+      CU(cudaMemcpyAsync(p, prepared, (size_t)n * 176 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+      df = (const float *)p;
+    }
+  }
+  LAUNCH(launch_expiry_digits(ctx->d_expiry, dp, df, n, dout, ctx->stream));
+  if (mem == B200_MEM_HOST) CU(cudaMemcpyAsync(out, dout, (size_t)n * 10 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}
+
+int b200_expiry_digits_batch(b200_ctx *ctx, const uint8_t *patches, int n, int mem, float *out) {
+  return expiry_call(ctx, patches, nullptr, n, mem, out);
+}
+
+int b200_expiry_digit_models_batch(b200_ctx *ctx, const float *prepared, int n, int mem, float *out) {
+  return expiry_call(ctx, nullptr, prepared, n, mem, out);
 }
 
 int b200_vseg_model_batch(b200_ctx *ctx, const float *rows, int n, int mem, float *out) {

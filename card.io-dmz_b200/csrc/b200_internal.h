@@ -92,7 +92,10 @@ int launch_finalize_records(const FrameGeom *geom, const b200_scan *scans, const
 int launch_categorize_patches(const NetWeights &wts, const uint8_t *patches, const float *float_patches, int n, float *out,
                               cudaStream_t s);
 int launch_vseg_model(const NetWeights &wts, const float *rows, int n, float *out, cudaStream_t s);
-int upload_conv_constants(const float *cnn_blobs[3]);  // __constant__ conv kernels / biases (nets.cu)
+int upload_conv_constants(const float *cnn_blobs[3]);
+int upload_bilateral_tables(const float *color256, const float *space5);  // E0 prep constants (nets.cu)
+int launch_expiry_digits(const float *weights, const uint8_t *patches, const float *prepared, int n, float *out, cudaStream_t s);
+void b200_build_bilateral_tables(float *color256, float *space5);  // b200_tables.cpp  // __constant__ conv kernels / biases (nets.cu)
 
 size_t detect_smem_bytes(const DetectParams &p);
 

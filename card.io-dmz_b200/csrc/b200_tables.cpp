@@ -160,3 +160,17 @@ void b200_build_geom_params(int width, int height, int orientation, int n_planes
         out->delta_rho[p][s][n] = delta_rho_for(out->theta[s >= 2][n], boxes[s].x, boxes[s].y);
   }
 }
+
+// prepare_image_for_cat's bilateral filter (scan/expiry_categorize.cpp:52-60): cvSmooth(CV_BILATERAL, 3, 3,
+// space_sigma, color_sigma) == cv::bilateralFilter(d = 3, sigmaColor = space_sigma, sigmaSpace = color_sigma)
+// -- the reference's variable names are swapped relative to OpenCV's parameter order.  Colour LUT and the
+// five in-circle spatial weights (mask order N, W, C, E, S) as imgproc/smooth.cpp builds them: (float)exp(double).
+void b200_build_bilateral_tables(float *color256, float *space5) {
+  const int aperture = 3;
+  const double sigma_color = (aperture / 2.0 - 1) * 0.3 + 0.8;  // the reference's "space_sigma"
+  const double sigma_space = (aperture - 1) / 3.0;              // the reference's "color_sigma"
+  const double gcc = -0.5 / (sigma_color * sigma_color), gsc = -0.5 / (sigma_space * sigma_space);
+  for (int i = 0; i < 256; i++) color256[i] = (float)exp(i * i * gcc);
+  const double r2[5] = {1.0, 1.0, 0.0, 1.0, 1.0};
+  for (int k = 0; k < 5; k++) space5[k] = (float)exp(r2[k] * gsc);
+}

@@ -449,6 +449,210 @@ categorize_kernel(NetWeights W, const uint8_t *__restrict__ cards, b200_scan *__
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// E0: expiry digit.  prepare_image_for_cat (scan/expiry_categorize.cpp:37-73) + applyc_bf4dd6c8
+// (models/expiry/modelc_bf4dd6c8.cpp:12500-13505).  Secondary path (SCAN_EXPIRY builds only); four digits per CTA
+// iteration, layer-2 weights (200 KB) streamed through shared memory one input map at a time.
+// ------------------------------------------------------------------------------------------------
+constexpr int kEThreads = 288;  // 4 digits x 70 pooled cells = 280 layer-1 items; 4 x 18 x 4 = 288 layer-2 items
+constexpr int kEDigits = 4;
+
+__constant__ float c_bil_color[256];  // bilateral colour LUT / spatial weights, computed on the host (b200_tables.cpp)
+__constant__ float c_bil_space[5];    // mask order N, W, C, E, S
+
+struct ExpirySmem {
+  float c1w[50][25];
+  float c1b[50];
+  float xpad[kEDigits][24][20];   // mean-subtracted input with a 4-pixel zero border (full correlation), row stride 20
+  float l1[kEDigits][50][70];     // ReLU(pool(conv1) + b)
+  float wk[40][25];               // layer-2 kernels of the current input map
+  float c2[kEDigits][40][18];
+  float l2[kEDigits][120];
+  float hid[kEDigits][176];
+  float o[kEDigits][10];
+  float x[kEDigits][176];
+  unsigned int hist[kEDigits][256];
+  uint8_t raw[kEDigits][16 * 12], g8[kEDigits][16 * 12], lut[kEDigits][256];
+};
+
+__global__ void __launch_bounds__(kEThreads, 1)
+expiry_kernel(const float *__restrict__ W /* modelc_bf4dd6c8 blob */, const uint8_t *__restrict__ patches,
+              const float *__restrict__ prepared, int n, float *__restrict__ out) {
+  extern __shared__ __align__(16) uint8_t es_raw[];
+  ExpirySmem &S = *reinterpret_cast<ExpirySmem *>(es_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float *c2w = W + 1300, *c2b = W + 51300, *hw = W + 51340, *hb = W + 72460, *lw = W + 72636, *lb = W + 74396;
+  for (int i = tid; i < 1250; i += kEThreads) (&S.c1w[0][0])[i] = __ldg(W + i);
+  for (int i = tid; i < 50; i += kEThreads) S.c1b[i] = __ldg(W + 1250 + i);
+
+  const int n_groups = (n + kEDigits - 1) / kEDigits;
+  for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+    const int nd = min(kEDigits, n - grp * kEDigits);
+    __syncthreads();
+    for (int i = tid; i < kEDigits * 24 * 20; i += kEThreads) (&S.xpad[0][0][0])[i] = 0.0f;
+    // ---- patch preparation: one warp per digit
+    if (warp < nd) {
+      const int d = warp;
+      const size_t idx = (size_t)grp * kEDigits + d;
+      if (prepared != nullptr) {
+        for (int i = lane; i < 176; i += 32) S.x[d][i] = __ldg(prepared + idx * 176 + i);
+      } else {
+        uint8_t *raw = S.raw[d], *g8 = S.g8[d];
+        unsigned int *hist = S.hist[d];
+        for (int i = lane; i < 256; i += 32) hist[i] = 0;
+        for (int i = lane; i < 176; i += 32) raw[(i / 11) * 12 + (i % 11)] = __ldg(patches + idx * 176 + i);
+        __syncwarp();
+        for (int i = lane; i < 176; i += 32) {  // cvMorphologyEx(GRADIENT, 3x3 cross), replicate at the ROI edge
+          const int y = i / 11, x = i - y * 11;
+          const int yu = y > 0 ? y - 1 : y, yd = y < 15 ? y + 1 : y, xl = x > 0 ? x - 1 : x, xr = x < 10 ? x + 1 : x;
+          const int a = raw[yu * 12 + x], b = raw[y * 12 + xl], c = raw[y * 12 + x], e = raw[y * 12 + xr], f = raw[yd * 12 + x];
+          const int v = max(a, max(b, max(c, max(e, f)))) - min(a, min(b, min(c, min(e, f))));
+          g8[y * 12 + x] = (uint8_t)v;
+          atomicAdd(&hist[v], 1u);
+        }
+        __syncwarp();
+        {  // llcv_equalize_hist: lut[i] = sat8(cvRound(cum(i) * (255.f / 176))), lut[0] = 0
+          unsigned int local[8], run = 0;
+#pragma unroll
+          for (int q = 0; q < 8; q++) {
+            run += hist[lane * 8 + q];
+            local[q] = run;
+          }
+          unsigned int incl = run;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+          }
+          const unsigned int excl = incl - run;
+          const float scale = 255.f / (11 * 16);
+#pragma unroll
+          for (int q = 0; q < 8; q++) {
+            const int val = __float2int_rn(__fmul_rn((float)(int)(excl + local[q]), scale));
+            S.lut[d][lane * 8 + q] = (uint8_t)(val < 0 ? 0 : (val > 255 ? 255 : val));
+          }
+          __syncwarp();
+          if (lane == 0) S.lut[d][0] = 0;
+          __syncwarp();
+        }
+        for (int i = lane; i < 176; i += 32) raw[(i / 11) * 12 + (i % 11)] = S.lut[d][g8[(i / 11) * 12 + (i % 11)]];
+        __syncwarp();
+        for (int i = lane; i < 176; i += 32) {  // cv::bilateralFilter(d = 3): mask N, W, C, E, S; float accumulation in that order
+          const int y = i / 11, x = i - y * 11;
+          const int yu = y > 0 ? y - 1 : y, yd = y < 15 ? y + 1 : y, xl = x > 0 ? x - 1 : x, xr = x < 10 ? x + 1 : x;
+          const int v0 = raw[y * 12 + x];
+          const int vals[5] = {raw[yu * 12 + x], raw[y * 12 + xl], v0, raw[y * 12 + xr], raw[yd * 12 + x]};
+          float sum = 0.0f, wsum = 0.0f;
+#pragma unroll
+          for (int k = 0; k < 5; k++) {
+            const float w = __fmul_rn(c_bil_space[k], c_bil_color[abs(vals[k] - v0)]);
+            sum = __fadd_rn(sum, __fmul_rn((float)vals[k], w));
+            wsum = __fadd_rn(wsum, w);
+          }
+          const int r = __float2int_rn(__fdiv_rn(sum, wsum));
+          S.x[d][i] = __fmul_rn((float)(r < 0 ? 0 : (r > 255 ? 255 : r)), 1.0f / 255.0f);  // cvConvertScale
+        }
+      }
+      __syncwarp();
+      // normalized_input = input - input.mean()
+      float part = 0.0f;
+      for (int i = lane; i < 176; i += 32) part += S.x[d][i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      const float mean = part / 176.0f;
+      __syncwarp();
+      for (int i = lane; i < 176; i += 32) S.xpad[d][4 + i / 11][4 + i % 11] = S.x[d][i] - mean;
+    }
+    __syncthreads();
+    // ---- layer 1: item = (digit, pooled cell); the 6x6 input window feeds all 50 kernels (weights broadcast from smem)
+    if (tid < nd * 70) {
+      const int d = tid / 70, cell = tid - d * 70, pr = cell / 7, pc = cell - pr * 7;
+      float win[6][6];
+#pragma unroll
+      for (int i = 0; i < 6; i++)
+#pragma unroll
+        for (int j = 0; j < 6; j++) win[i][j] = S.xpad[d][2 * pr + i][2 * pc + j];  // conv output (r, c) reads xpad rows r .. r+4
+      for (int f = 0; f < 50; f++) {
+        float a00 = 0.0f, a01 = 0.0f, a10 = 0.0f, a11 = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 5; i++)
+#pragma unroll
+          for (int j = 0; j < 5; j++) {
+            const float w = S.c1w[f][i * 5 + j];
+            a00 = fmaf(w, win[i][j], a00);
+            a01 = fmaf(w, win[i][j + 1], a01);
+            a10 = fmaf(w, win[i + 1][j], a10);
+            a11 = fmaf(w, win[i + 1][j + 1], a11);
+          }
+        S.l1[d][f][cell] = fmaxf(fmaxf(fmaxf(a00, a01), fmaxf(a10, a11)) + S.c1b[f], 0.0f);
+      }
+    }
+    __syncthreads();
+    // ---- layer 2: thread = (digit, position, map group); maps fg, fg+4, ..; K loop over the 50 input maps
+    {
+      const int dp = tid % 72, fg = tid / 72, d = dp / 18, pos = dp - d * 18, r = pos / 3, c = pos - r * 3;
+      float acc[10];
+#pragma unroll
+      for (int q = 0; q < 10; q++) acc[q] = 0.0f;
+      for (int k = 0; k < 50; k++) {
+        __syncthreads();
+        for (int i = tid; i < 1000; i += kEThreads) S.wk[i / 25][i % 25] = __ldg(c2w + (size_t)(i / 25) * 1250 + k * 25 + (i % 25));
+        __syncthreads();
+        if (d < nd) {
+          float win[25];
+#pragma unroll
+          for (int i = 0; i < 5; i++)
+#pragma unroll
+            for (int j = 0; j < 5; j++) win[i * 5 + j] = S.l1[d][k][(r + i) * 7 + c + j];
+#pragma unroll
+          for (int q = 0; q < 10; q++) {
+            const float *w = S.wk[fg + 4 * q];
+            float a = 0.0f;
+#pragma unroll
+            for (int t = 0; t < 25; t++) a = fmaf(w[t], win[t], a);
+            acc[q] += a;
+          }
+        }
+      }
+      if (d < nd) {
+#pragma unroll
+        for (int q = 0; q < 10; q++) S.c2[d][fg + 4 * q][pos] = acc[q];
+      }
+    }
+    __syncthreads();
+    for (int it = tid; it < nd * 120; it += kEThreads) {  // 2x3 max pool -> + bias -> ReLU; feature order [map][3]
+      const int d = it / 120, q = it - d * 120, f = q / 3, r = q - f * 3;
+      const float *p = &S.c2[d][f][2 * r * 3];
+      const float m = fmaxf(fmaxf(fmaxf(p[0], p[1]), fmaxf(p[2], p[3])), fmaxf(p[4], p[5]));
+      S.l2[d][q] = fmaxf(m + __ldg(c2b + f), 0.0f);
+    }
+    __syncthreads();
+    for (int it = tid; it < nd * 176; it += kEThreads) {  // hidden 120 -> 176, ReLU
+      const int d = it / 176, i = it - d * 176;
+      const float *w = hw + (size_t)i * 120;
+      float a = 0.0f;
+      for (int j = 0; j < 120; j++) a = fmaf(__ldg(w + j), S.l2[d][j], a);
+      S.hid[d][i] = fmaxf(a + __ldg(hb + i), 0.0f);
+    }
+    __syncthreads();
+    for (int it = tid; it < nd * 10; it += kEThreads) {  // logistic 176 -> 10
+      const int d = it / 10, i = it - d * 10;
+      const float *w = lw + (size_t)i * 176;
+      float a = 0.0f;
+      for (int j = 0; j < 176; j++) a = fmaf(__ldg(w + j), S.hid[d][j], a);
+      S.o[d][i] = expf(a + __ldg(lb + i));
+    }
+    __syncthreads();
+    for (int it = tid; it < nd * 10; it += kEThreads) {
+      const int d = it / 10, i = it - d * 10;
+      float sum = 0.0f;
+#pragma unroll
+      for (int j = 0; j < 10; j++) sum += S.o[d][j];
+      out[((size_t)grp * kEDigits + d) * 10 + i] = S.o[d][i] / sum;
+    }
+  }
+}
+
 int g_num_sms = 0;
 
 int num_sms() {
@@ -515,6 +719,26 @@ static int launch_categorize(const NetWeights &wts, const uint8_t *cards, b200_s
   if (grid < 1) grid = 1;
   if (is_raw) categorize_kernel<true><<<grid, kCThreads, sizeof(CatSmem), s>>>(wts, nullptr, nullptr, raw, raw_float, n, raw_out);
   else categorize_kernel<false><<<grid, kCThreads, sizeof(CatSmem), s>>>(wts, cards, scans, nullptr, nullptr, n, nullptr);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int upload_bilateral_tables(const float *color256, const float *space5) {
+  if (cudaMemcpyToSymbol(c_bil_color, color256, 256 * sizeof(float)) != cudaSuccess) return -1;
+  if (cudaMemcpyToSymbol(c_bil_space, space5, 5 * sizeof(float)) != cudaSuccess) return -1;
+  return 0;
+}
+
+int launch_expiry_digits(const float *weights, const uint8_t *patches, const float *prepared, int n, float *out, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    if (!ensure_smem(expiry_kernel, sizeof(ExpirySmem))) return -1;
+    configured = true;
+  }
+  int grid = num_sms();
+  const int groups = (n + kEDigits - 1) / kEDigits;
+  if (grid > groups) grid = groups;
+  if (grid < 1) grid = 1;
+  expiry_kernel<<<grid, kEThreads, sizeof(ExpirySmem), s>>>(weights, patches, prepared, n, out);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

@@ -172,6 +172,13 @@ int b200_digit_models_batch(b200_ctx *ctx, const float *patches, int n, int mem,
 /* applym_befe75da on prepared rows: in = n x 204 f32, out = n x 3 f32 */
 int b200_vseg_model_batch(b200_ctx *ctx, const float *rows, int n, int mem, float *out);
 
+/* ---- E0: expiry digit (the SCAN_EXPIRY-only branch of scanner_add_frame_with_expiry) ----
+ * prepare_image_for_cat + applyc_bf4dd6c8 (scan/expiry_categorize.cpp:37-109, models/expiry/modelc_bf4dd6c8.cpp):
+ * patches = n x 16 rows x 11 cols u8 cut from the card at a character rect; out = n x 10 digit probabilities.
+ * The *_models_ variant takes already prepared 16 x 11 float inputs (the reference's embedded KAT entry). */
+int b200_expiry_digits_batch(b200_ctx *ctx, const uint8_t *patches, int n, int mem, float *out);
+int b200_expiry_digit_models_batch(b200_ctx *ctx, const float *prepared, int n, int mem, float *out);
+
 /* ---- scanner session (scan/scan.h:50-72): host-side aggregation, no GPU work ---- */
 typedef struct b200_scanner b200_scanner;
 b200_scanner *b200_scanner_new(void);

@@ -120,6 +120,8 @@ class Oracle:
             self.lib.ref_run_kats.restype = i
             self.lib.ref_sizeof.argtypes = [i]
         else:
+            self.lib.orc_expiry_patch_prep.argtypes = [vp, i, vp]
+            self.lib.orc_expiry_digit_model.argtypes = [vp, vp, vp, vp, vp]
             self.lib.orc_scanner_add_scan.argtypes = [vp, C.POINTER(Scan)]
             self.lib.orc_card_check.argtypes = [vp, C.c_size_t]
             self.lib.orc_card_check.restype = C.c_uint32
@@ -231,6 +233,21 @@ class Oracle:
         out = np.zeros(40, np.float32)
         self._digit_models(_p(patch), _p(out))
         return out[:10].copy(), out[10:].reshape(3, 10).copy()
+
+    # ---- E0: expiry digit (port only; the reference build here has SCAN_EXPIRY off) -----------------------
+    def expiry_patch_prep(self, img16x11):
+        img = np.ascontiguousarray(img16x11, np.uint8)
+        assert img.shape == (16, 11)
+        out = np.zeros((16, 11), np.float32)
+        self.lib.orc_expiry_patch_prep(_p(img), 11, _p(out))
+        return out
+
+    def expiry_digit_model(self, x, taps=False):
+        x = np.ascontiguousarray(x, np.float32).reshape(176)
+        out = np.zeros(10, np.float32)
+        l1, l2, hid = np.zeros(3500, np.float32), np.zeros(120, np.float32), np.zeros(176, np.float32)
+        self.lib.orc_expiry_digit_model(_p(x), _p(out), _p(l1), _p(l2), _p(hid))
+        return (out, l1, l2, hid) if taps else out
 
     def scan_card_image(self, card):
         card = np.ascontiguousarray(card, np.uint8)

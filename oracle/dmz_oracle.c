@@ -531,6 +531,13 @@ static mlp_weights g_vseg;
 static cnn_weights g_cnn[3];
 static int g_weights_loaded = 0;
 
+/* expiry digit CNN, models/expiry/modelc_bf4dd6c8.cpp (blob order = table order in the generated file) */
+typedef struct {
+  float c1w[50][25], c1b[50], c2w[40][50][25], c2b[40], hw[176][120], hb[176], lw[10][176], lb[10];
+} expiry_weights;
+static expiry_weights g_exp;
+static int g_exp_loaded = 0;
+
 static int read_blob(const char *dir, const char *name, void *dst, size_t bytes) {
   char path[1024];
   FILE *f;
@@ -550,6 +557,7 @@ int orc_load_weights(const char *dir) {
   for (i = 0; i < 3; i++)
     if (read_blob(dir, cnn_names[i], &g_cnn[i], sizeof(cnn_weights))) return -1;
   g_weights_loaded = 1;
+  g_exp_loaded = read_blob(dir, "modelc_bf4dd6c8.bin", &g_exp, sizeof(g_exp)) == 0;
   return 0;
 }
 
@@ -811,6 +819,94 @@ void orc_number_scores(const uint8_t *card, int y_offset, const orc_hseg *hseg, 
     orc_digit_models(patch, out);
     memcpy(scores + d * 10, out, 10 * sizeof(float));
   }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * E0  expiry digit: prepare_image_for_cat (scan/expiry_categorize.cpp:37-73) + applyc_bf4dd6c8
+ *     (models/expiry/modelc_bf4dd6c8.cpp:12500-13505)
+ * ------------------------------------------------------------------------------------------------ */
+void orc_expiry_patch_prep(const uint8_t *img, int step, float *out /* 16 x 11 */) {
+  uint8_t g[16 * 12], b[16 * 12];
+  const int aperture = 3;
+  const double space_sigma = (aperture / 2.0 - 1) * 0.3 + 0.8, color_sigma = (aperture - 1) / 3.0;
+  orc_morph_grad_cross3_u8(img, step, 11, 16, g, 12);       /* cvMorphologyEx(GRADIENT, 3x3 cross) on the 11x16 ROI */
+  equalize_hist_u8(g, 12, 11, 16);                           /* llcv_equalize_hist, scale 255.f / 176 */
+  /* cvSmooth(.., CV_BILATERAL, 3, 3, space_sigma, color_sigma): param3 -> sigmaColor, param4 -> sigmaSpace */
+  orc_bilateral_u8(g, 12, 11, 16, b, 12, aperture, space_sigma, color_sigma);
+  orc_convert_scale_u8_f32(b, 12, 11, 16, out, 11 * 4, 1.0f / 255.0f);
+}
+
+static float relu(float v) { return v > 0.0f ? v : 0.0f; }
+
+/* in: 16 x 11 floats.  Optional taps: l1 50 x 70, l2 40 x 3, hid 176 (the layers the reference's KAT checks). */
+void orc_expiry_digit_model(const float *in, float *out10, float *l1_out, float *l2_out, float *hid_out) {
+  float x[16][11], l1[50][10][7], l2[40][3], hid[176], o[10], mean = 0.0f, sum;
+  int f, r, c, i, j, k;
+  if (!g_exp_loaded) {
+    fprintf(stderr, "dmz_oracle: expiry weights (modelc_bf4dd6c8.bin) not loaded\n");
+    abort();
+  }
+  /* normalized_input = input - input.mean(): Eigen's vectorised linear redux over the 176 coefficients, / 176 */
+  mean = eig_redux_sum(in, 176) / 176.0f;
+  for (r = 0; r < 16; r++)
+    for (c = 0; c < 11; c++) x[r][c] = in[r * 11 + c] - mean;
+  /* layer 1: 50 x "full" 5x5 cross-correlation with zero padding (20 x 14), 2x2 max pool (10 x 7), + bias, ReLU */
+  for (f = 0; f < 50; f++) {
+    float conv[20][14];
+    for (r = 0; r < 20; r++)
+      for (c = 0; c < 14; c++) {
+        float prod[25];
+        for (i = 0; i < 5; i++)
+          for (j = 0; j < 5; j++) {
+            int rr = r - 4 + i, cc = c - 4 + j;
+            prod[i * 5 + j] = g_exp.c1w[f][i * 5 + j] * ((rr >= 0 && rr < 16 && cc >= 0 && cc < 11) ? x[rr][cc] : 0.0f);
+          }
+        conv[r][c] = 0.0f + eig_tree_sum(prod, 0, 25); /* kernel.cwiseProduct(sub).sum(): unrolled tree; += onto Zero() */
+      }
+    for (r = 0; r < 10; r++)
+      for (c = 0; c < 7; c++) {
+        float m = conv[2 * r][2 * c];
+        if (conv[2 * r][2 * c + 1] > m) m = conv[2 * r][2 * c + 1];
+        if (conv[2 * r + 1][2 * c] > m) m = conv[2 * r + 1][2 * c];
+        if (conv[2 * r + 1][2 * c + 1] > m) m = conv[2 * r + 1][2 * c + 1];
+        l1[f][r][c] = relu(m + g_exp.c1b[f]);
+      }
+  }
+  /* layer 2: 40 maps, each the sum over 50 input maps of a valid 5x5 correlation (6 x 3), 2x3 max pool (3 x 1) */
+  for (f = 0; f < 40; f++) {
+    float acc[6][3];
+    memset(acc, 0, sizeof(acc));
+    for (k = 0; k < 50; k++)
+      for (r = 0; r < 6; r++)
+        for (c = 0; c < 3; c++) {
+          float prod[25];
+          for (i = 0; i < 5; i++)
+            for (j = 0; j < 5; j++) prod[i * 5 + j] = g_exp.c2w[f][k][i * 5 + j] * l1[k][r + i][c + j];
+          acc[r][c] += eig_tree_sum(prod, 0, 25);
+        }
+    for (r = 0; r < 3; r++) {
+      float m = acc[2 * r][0];
+      for (i = 0; i < 2; i++)
+        for (j = 0; j < 3; j++)
+          if (acc[2 * r + i][j] > m) m = acc[2 * r + i][j];
+      l2[f][r] = relu(m + g_exp.c2b[f]);
+    }
+  }
+  for (i = 0; i < 176; i++) {
+    float a = 0.0f;
+    for (j = 0; j < 120; j++) a += g_exp.hw[i][j] * (&l2[0][0])[j];
+    hid[i] = relu(a + g_exp.hb[i]);
+  }
+  for (i = 0; i < 10; i++) {
+    float a = 0.0f;
+    for (j = 0; j < 176; j++) a += g_exp.lw[i][j] * hid[j];
+    o[i] = expf(a + g_exp.lb[i]);
+  }
+  sum = eig_tree_sum(o, 0, 10);
+  for (i = 0; i < 10; i++) out10[i] = o[i] / sum;
+  if (l1_out) memcpy(l1_out, l1, sizeof(l1));
+  if (l2_out) memcpy(l2_out, l2, sizeof(l2));
+  if (hid_out) memcpy(hid_out, hid, sizeof(hid));
 }
 
 /* ------------------------------------------------------------------------------------------------

@@ -44,6 +44,9 @@ void orc_number_scores(const uint8_t *card, int y_offset, const orc_hseg *hseg, 
 void orc_digit_patch_prep(const uint8_t *img, int step, float *patch);
 void orc_digit_models(const float *patch, float *out40);
 void orc_scan_card_image(const uint8_t *card, orc_scan *out);
+/* E0 (expiry digit): patch = 16 rows x 11 cols */
+void orc_expiry_patch_prep(const uint8_t *img, int step, float *out176);
+void orc_expiry_digit_model(const float *in176, float *out10, float *l1_3500, float *l2_120, float *hid_176);
 void orc_process_frame(const uint8_t *y, int w, int h, int ystep, const uint8_t *cb, const uint8_t *cr, int cstep,
                        int orientation, orc_frame_record *rec, uint8_t *card_out);
 

@@ -208,6 +208,37 @@ def test_categorize_patches(dmz, oracle, golden):
         assert np.abs(ens[i] - e).max() <= TOL and np.abs(mods[i] - m).max() <= TOL, i
 
 
+def test_expiry_digit_known_answer_and_parity(dmz, oracle):
+    """E0: prepare_image_for_cat + applyc_bf4dd6c8 (scan/expiry_categorize.cpp:37-109).  The
+    reference's embedded KAT at its own 1e-5; random / structured character crops against the oracle at 1e-4."""
+    meta = json.load(open(os.path.join(G, "kat_modelc_bf4dd6c8.json")))
+    data = np.fromfile(os.path.join(G, "kat_modelc_bf4dd6c8.bin"), "<f4")
+    k = {v["label"]: data[v["offset"]:v["offset"] + v["count"]] for v in meta["vectors"]}
+    assert np.abs(dmz.expiry_digit_models(k["test input"])[0] - k["test output"]).max() <= 1e-5
+    rng = np.random.default_rng(21)
+    n = 203  # not a multiple of the 4 digits a CTA takes per iteration
+    patches = rng.integers(0, 256, (n, 16, 11)).astype(np.uint8)
+    patches[0] = 0       # flat patch: gradient 0 everywhere, single histogram bin
+    patches[1] = 255
+    patches[2:60] = (patches[2:60] // 32) * 9       # few grey levels: colour weights of the bilateral filter matter
+    yy, xx = np.mgrid[0:16, 0:11]
+    for i in range(60, 120):                         # stroke-like shapes
+        cx, cy, r = rng.uniform(3, 8), rng.uniform(4, 12), rng.uniform(2, 5)
+        ring = np.abs(np.hypot(xx - cx, (yy - cy) * 0.7) - r) < 1.0
+        patches[i] = np.where(ring, 200 + rng.integers(0, 40), 30 + rng.integers(0, 30, (16, 11))).astype(np.uint8)
+    got = dmz.expiry_digits(patches)
+    assert got.shape == (n, 10) and np.abs(got.sum(1) - 1).max() < 1e-5
+    for i in range(n):
+        want = oracle.expiry_digit_model(oracle.expiry_patch_prep(patches[i]))
+        assert np.abs(got[i] - want).max() <= TOL, i
+    # prepared-input entry, batched, against the oracle's model alone
+    prepared = rng.random((37, 176)).astype(np.float32)
+    got = dmz.expiry_digit_models(prepared)
+    for i in range(37):
+        assert np.abs(got[i] - oracle.expiry_digit_model(prepared[i])).max() <= TOL, i
+    assert got.argmax(1).tolist() == [int(oracle.expiry_digit_model(prepared[i]).argmax()) for i in range(37)]
+
+
 def test_whole_path_records(dmz, deck, orecs):
     rec, ocards = orecs
     got, cards = dmz.process_frames(deck, want_cards=True)

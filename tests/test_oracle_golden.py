@@ -30,6 +30,16 @@ def test_kat_digit_cnn(oracle, idx, model):
     assert np.abs(per_model[idx] - k["test output"]).max() <= tol
 
 
+def test_kat_expiry_cnn(oracle):
+    """E0: applyc_bf4dd6c8's embedded per-layer vectors (models/expiry/modelc_bf4dd6c8.cpp:13507-13560)."""
+    k, tol = kat("modelc_bf4dd6c8")
+    out, l1, l2, hid = oracle.expiry_digit_model(k["test input"], taps=True)
+    assert np.abs(l1.ravel() - k["test output layer 1"]).max() <= tol
+    assert np.abs(l2.ravel() - k["test output layer 2"]).max() <= tol
+    assert np.abs(hid.ravel() - k["test output layer 3"]).max() <= tol
+    assert np.abs(out - k["test output"]).max() <= tol
+
+
 def test_detection_boxes(oracle, golden):
     for key in golden.files:
         if key.startswith("boxes_"):

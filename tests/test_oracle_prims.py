@@ -81,3 +81,14 @@ def test_bilinear_table_quirk(lib):
     assert tab[0, 0].tolist() == [32767, 0, 0, 1]  # saturate_cast<short>(32768) compensated on the last tap
     assert (tab.reshape(-1, 4).sum(1) == 32768).all()
     assert tab[16, 16].tolist() == [8192] * 4
+
+
+def test_bilateral(lib, g):
+    """cvSmooth(CV_BILATERAL, 3, 3, 0.95, 2/3) of prepare_image_for_cat (scan/expiry_categorize.cpp:52-60)."""
+    lib.orc_bilateral_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double]
+    for i in range(4):
+        img = np.ascontiguousarray(g["bilateral%d_img" % i])
+        h, w = img.shape
+        out = np.zeros_like(img)
+        lib.orc_bilateral_u8(P(img), w, w, h, P(out), w, 3, (3 / 2.0 - 1) * 0.3 + 0.8, (3 - 1) / 3.0)
+        assert np.array_equal(out, g["bilateral%d_out" % i]), i

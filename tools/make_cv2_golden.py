@@ -40,6 +40,17 @@ out["warp_out"] = np.stack(outs)
 A = rng.normal(size=(8, 3, 3))
 out["invert_in"] = A
 out["invert_out"] = np.stack([cv2.invert(a)[1] for a in A])
+# bilateral filter as prepare_image_for_cat calls it (scan/expiry_categorize.cpp:52-60): d = 3, sigmaColor = 0.95
+# (the reference's "space_sigma"), sigmaSpace = 2/3 (its "color_sigma"), replicate border.  Widths stay below cv2 4.x's
+# SIMD width on purpose: 4.x's vector body accumulates differently from its own scalar tail (and from 2.4.x);
+# the scalar tail is the 2.4.x generic-C summation order the oracle restates, and the path only ever filters
+# 11-pixel-wide patches.
+for i, (w, h) in enumerate([(11, 16), (11, 16), (7, 30), (3, 3)]):
+    img = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    if i == 1:
+        img = (img // 64 * 3).astype(np.uint8)  # small differences: colour weights far from 0
+    out["bilateral%d_img" % i] = img
+    out["bilateral%d_out" % i] = cv2.bilateralFilter(img, 3, (3 / 2.0 - 1) * 0.3 + 0.8, (3 - 1) / 3.0, borderType=cv2.BORDER_REPLICATE)
 path = os.path.join(ROOT, "tests", "golden", "cv2_prims.npz")
 np.savez_compressed(path, **out)
 print("wrote", path, os.path.getsize(path))
