@@ -105,6 +105,7 @@ def _load():
     lib.b200_categorize_patches_batch.argtypes = [vp, vp, i, i, vp]
     lib.b200_vseg_model_batch.argtypes = [vp, vp, i, i, vp]
     lib.b200_digit_models_batch.argtypes = [vp, vp, i, i, vp]
+    lib.b200_frame_scores_batch.argtypes = [vp, vp, i, C.c_size_t, i, i, i, i, i, vp, vp]
     lib.b200_expiry_digits_batch.argtypes = [vp, vp, i, i, vp]
     lib.b200_expiry_digit_models_batch.argtypes = [vp, vp, i, i, vp]
     lib.b200_set_profiling.argtypes = [vp, i]
@@ -244,6 +245,15 @@ class Dmz:
         out = np.zeros((n, 40), np.float32)
         self._check(self.lib.b200_digit_models_batch(self.ctx, _ptr(patches), n, MEM_HOST, _ptr(out)))
         return out[:, :10].copy(), out[:, 10:].reshape(n, 3, 10).copy()
+
+    def frame_scores(self, frames, use_full_image=False):
+        """frames: (n, h, w) u8 luma.  Returns (focus, brightness) float32 arrays (dmz_focus_score / dmz_brightness_score)."""
+        frames = np.ascontiguousarray(frames, np.uint8)
+        n, h, w = frames.shape
+        focus, bright = np.zeros(n, np.float32), np.zeros(n, np.float32)
+        self._check(self.lib.b200_frame_scores_batch(self.ctx, _ptr(frames), w, w * h, w, h, n, int(use_full_image), MEM_HOST,
+                                                     _ptr(focus), _ptr(bright)))
+        return focus, bright
 
     def expiry_digits(self, patches):
         """patches: (n, 16, 11) u8 character crops.  Returns (n, 10) digit probabilities (E0)."""

@@ -680,6 +680,51 @@ int b200_digit_models_batch(b200_ctx *ctx, const float *patches, int n, int mem,
   return B200_OK;
 }
 
+// dmz_focus_score / dmz_brightness_score over a batch.  Host frames: only the scoring rectangle crosses PCIe (the
+// reference's ROI clamps the Sobel taps at the rectangle, so nothing outside it is ever read).
+int b200_frame_scores_batch(b200_ctx *ctx, const uint8_t *y, int yrs, size_t yfs, int width, int height, int n,
+                            int use_full_image, int mem, float *focus, float *brightness) {
+  if (!ctx || !y || n < 1 || width < 1 || height < 1 || yrs < width || (!focus && !brightness))
+    return fail(ctx, B200_EINVAL, "b200_frame_scores_batch: bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  int rc4[4];
+  b200_scoring_rect(width, height, use_full_image, rc4);
+  const int rx = rc4[0], ry = rc4[1], rw = rc4[2], rh = rc4[3];
+  if (rw < 1 || rh < 1) return fail(ctx, B200_EINVAL, "b200_frame_scores_batch: empty scoring rectangle");
+  if (mem == B200_MEM_DEVICE) {
+    LAUNCH(launch_frame_scores(y, yrs, yfs, n, rx, ry, rw, rh, focus, brightness, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return B200_OK;
+  }
+  const size_t roi_bytes = (size_t)rw * rh;
+  const size_t off_scores = ((size_t)n * roi_bytes + 15) & ~(size_t)15;
+  int rc = ensure_misc(ctx, off_scores + 2 * sizeof(float) * (size_t)n);
+  if (rc) return rc;
+  uint8_t *d_roi = (uint8_t *)ctx->d_misc;
+  float *d_focus = (float *)((uint8_t *)ctx->d_misc + off_scores), *d_bright = d_focus + n;
+  if (yfs % (size_t)yrs == 0) {
+    cudaMemcpy3DParms p;
+    memset(&p, 0, sizeof(p));
+    p.srcPtr = make_cudaPitchedPtr((void *)y, (size_t)yrs, (size_t)width, yfs / (size_t)yrs);
+    p.srcPos = make_cudaPos((size_t)rx, (size_t)ry, 0);
+    p.dstPtr = make_cudaPitchedPtr(d_roi, (size_t)rw, (size_t)rw, (size_t)rh);
+    p.extent = make_cudaExtent((size_t)rw, (size_t)rh, (size_t)n);
+    p.kind = cudaMemcpyHostToDevice;
+    CU(cudaMemcpy3DAsync(&p, ctx->stream));
+  } else {
+    for (int i = 0; i < n; i++)
+      CU(cudaMemcpy2DAsync(d_roi + (size_t)i * roi_bytes, rw, y + (size_t)i * yfs + (size_t)ry * yrs + rx, yrs, rw, rh,
+                           cudaMemcpyHostToDevice, ctx->stream));
+  }
+  ctx->h2d_bytes += (uint64_t)roi_bytes * n;
+  LAUNCH(launch_frame_scores(d_roi, rw, roi_bytes, n, 0, 0, rw, rh, d_focus, d_bright, ctx->stream));
+  if (focus) CU(cudaMemcpyAsync(focus, d_focus, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  if (brightness) CU(cudaMemcpyAsync(brightness, d_bright, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->d2h_bytes += (uint64_t)sizeof(float) * n * ((focus != nullptr) + (brightness != nullptr));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}
+
 static int expiry_call(b200_ctx *ctx, const uint8_t *patches, const float *prepared, int n, int mem, float *out) {
   if (!ctx || (!patches && !prepared) || !out || n < 1) return fail(ctx, B200_EINVAL, "b200_expiry_*: bad arguments");
   if (!ctx->d_expiry) return fail(ctx, B200_EUNSUPPORTED, "modelc_bf4dd6c8.bin was not found in the weights directory");

@@ -94,6 +94,9 @@ int launch_categorize_patches(const NetWeights &wts, const uint8_t *patches, con
 int launch_vseg_model(const NetWeights &wts, const float *rows, int n, float *out, cudaStream_t s);
 int upload_conv_constants(const float *cnn_blobs[3]);
 int upload_bilateral_tables(const float *color256, const float *space5);  // E0 prep constants (nets.cu)
+int launch_frame_scores(const uint8_t *frames, int row_stride, size_t frame_stride, int n, int rx, int ry, int rw, int rh,
+                        float *focus, float *brightness, cudaStream_t s);
+void b200_scoring_rect(int w, int h, int use_full_image, int rect[4]);  // b200_tables.cpp
 int launch_expiry_digits(const float *weights, const uint8_t *patches, const float *prepared, int n, float *out, cudaStream_t s);
 void b200_build_bilateral_tables(float *color256, float *space5);  // b200_tables.cpp  // __constant__ conv kernels / biases (nets.cu)
 

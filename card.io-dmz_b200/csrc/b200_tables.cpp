@@ -174,3 +174,21 @@ void b200_build_bilateral_tables(float *color256, float *space5) {
   const double r2[5] = {1.0, 1.0, 0.0, 1.0, 1.0};
   for (int k = 0; k < 5; k++) space5[k] = (float)exp(r2[k] * gsc);
 }
+
+// dmz_set_roi_for_scoring + dmz_card_rect_for_screen (dmz.cpp:136-181): card-sized (or card / 3) rectangle centred in
+// the frame, scaled by min(w / 640, h / 480) in float with truncation unless the frame is 640x480; then clipped to
+// the image as cvSetImageROI does.
+void b200_scoring_rect(int w, int h, int use_full_image, int rect[4]) {
+  const int card_w = use_full_image ? 428 : 428 / 3, card_h = use_full_image ? 270 : 270 / 3;
+  int rw = card_w, rh = card_h;
+  if (!(w == 640 && h == 480)) {
+    const float ratio_w = (float)w / (float)640, ratio_h = (float)h / (float)480;
+    const float ratio = ratio_w < ratio_h ? ratio_w : ratio_h;
+    rw = (int)(card_w * ratio);
+    rh = (int)(card_h * ratio);
+  }
+  int x0 = (w - rw) / 2, y0 = (h - rh) / 2, x1 = x0 + rw, y1 = y0 + rh;
+  x0 = x0 < 0 ? 0 : x0, y0 = y0 < 0 ? 0 : y0;
+  x1 = x1 > w ? w : x1, y1 = y1 > h ? h : y1;
+  rect[0] = x0, rect[1] = y0, rect[2] = x1 - x0, rect[3] = y1 - y0;
+}

@@ -133,6 +133,26 @@ bool dmz_detect_edges(IplImage *y, IplImage *cb, IplImage *cr, FrameOrientation 
   return all != 0;
 }
 
+// dmz_focus_score / dmz_brightness_score (dmz.h:77-80, dmz.cpp:183-195).  The scoring rectangle is derived from
+// cvGetSize(image) and applied in whole-image coordinates, as the reference's cvSetImageROI does.  (The reference also
+// drops any ROI the caller had set; this layer leaves the caller's IplImage untouched.)
+static float frame_score(IplImage *image, bool use_full_image, bool want_focus) {
+  b200_ctx *ctx = default_ctx();
+  if (!ctx || !image) return 0.0f;
+  PlaneView v = view_of(image);
+  // b200_frame_scores_batch places the rectangle inside a (w x h) plane; hand it the whole image when sizes agree,
+  // otherwise a virtual plane of the ROI's size anchored at the image origin (what cvSetImageROI would address)
+  float focus = 0.0f, bright = 0.0f;
+  int rc = b200_frame_scores_batch(ctx, (const uint8_t *)image->imageData, image->widthStep, (size_t)image->widthStep * image->height,
+                                   v.w, v.h, 1, use_full_image ? 1 : 0, B200_MEM_HOST, want_focus ? &focus : nullptr,
+                                   want_focus ? nullptr : &bright);
+  if (rc != B200_OK) return 0.0f;
+  return want_focus ? focus : bright;
+}
+
+float dmz_focus_score(IplImage *image, bool use_full_image) { return frame_score(image, use_full_image, true); }
+float dmz_brightness_score(IplImage *image, bool use_full_image) { return frame_score(image, use_full_image, false); }
+
 void dmz_transform_card(dmz_context *dmz, IplImage *sample, dmz_corner_points corner_points, FrameOrientation orientation,
                         bool upsample, IplImage **transformed) {
   b200_ctx *ctx = dmz && dmz->mz ? (b200_ctx *)dmz->mz : default_ctx();

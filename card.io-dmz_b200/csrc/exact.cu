@@ -275,33 +275,31 @@ constexpr int kWarpThreads = 224;               // 2 x 107 = 214 workers (two ro
 // src points at pixel (0, 0) of the sw x sh frame (the host-buffer path uploads only a crop and passes a
 // correspondingly shifted pointer); the crop is guaranteed by the caller to contain every in-image tap of the quad.
 //
-// Coordinates.  The reference computes W' = 32 / W (IEEE divide), fX = (X0 + M0 x1) W', X = cvRound(fX).  The
-// FP64 divide is the most expensive instruction sequence of this kernel, so X is first computed with a cheap
-// reciprocal (rcp.approx + two Newton steps, relative error ~1e-15): unless that value lies within 1e-6 of a
-// rounding boundary -- where a last-bit difference could change the integer -- it rounds to the same X as the
-// reference's doubly-rounded value; the rare boundary cases (and W ~ 0 / huge coordinates) take the exact
-// sequence.  The result is bit-identical to the reference for every pixel.
-__device__ __forceinline__ void warp_coords(const double *M, double X0, double Y0, double W0, int x1, int *X, int *Y) {
-  const double Wr = W0 + M[6] * x1;
-  const double nx = X0 + M[0] * x1, ny = Y0 + M[3] * x1;
+// Coordinates.  The reference computes W' = 32 / W (IEEE divide), fX = (X0 + M0 x1) W', X = cvRound(fX).  FP64 work
+// dominates this kernel's instruction count, so X is first computed the cheap way: fused multiply-adds for the three
+// linear forms, rcp.approx + ONE Newton step for 1/W (relative error ~1e-12, i.e. < 2e-7 in fX), and a single
+// FMA  t = fX * 2^14 + (1.5 * 2^52 + 2^30)  whose low word then holds round(fX * 2^14) + 2^30 as an unsigned integer
+// (valid while the high word is still that of the constant, i.e. -65536 <= fX < 196608 = 6144 px).  Unless the 14-bit
+// fraction lies within 4/16384 of one half -- where an error that small could change the rounded integer -- the value
+// rounds to the same X as the reference's doubly-rounded one.  Boundary cases, W ~ 0 and far-away coordinates take
+// the exact reference sequence.  The result is bit-identical to the reference for every pixel.
+__device__ __forceinline__ void warp_coords(const double *M, double X0, double Y0, double W0, int x1, double xq, int *X, int *Y) {
+  const double Wf = __fma_rn(M[6], xq, W0), nxf = __fma_rn(M[0], xq, X0), nyf = __fma_rn(M[3], xq, Y0);
   double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(Wr));
-  r = __fma_rn(r, __fma_rn(-Wr, r, 1.0), r);
-  r = __fma_rn(r, __fma_rn(-Wr, r, 1.0), r);
-  const double w32 = r * 32.0;
-  const double fx = nx * w32, fy = ny * w32;
-  // round-half-even to integer with the 1.5 * 2^52 trick (valid for |f| < 2^31): no FP64<->int conversions
-  const double kMagic = 6755399441055744.0;
-  const double tx = fx + kMagic, ty = fy + kMagic;
-  int xi = __double2loint(tx), yi = __double2loint(ty);
-  const double ex = fx - (tx - kMagic), ey = fy - (ty - kMagic);
-  // "safe" = rounding residual below 0.499999 and |f| < 2^31, tested on the high words (positive doubles order like
-  // their bit patterns; NaN / inf from a degenerate W compare as unsafe)
-  const unsigned hex = (unsigned)__double2hiint(ex) & 0x7fffffffu, hey = (unsigned)__double2hiint(ey) & 0x7fffffffu;
-  const unsigned hfx = (unsigned)__double2hiint(fx) & 0x7fffffffu, hfy = (unsigned)__double2hiint(fy) & 0x7fffffffu;
-  const bool safe = (hex < 0x3FDFFFFBu) & (hey < 0x3FDFFFFBu) & (hfx < 0x41E00000u) & (hfy < 0x41E00000u);
-  if (!safe) {
-    double W = Wr != 0.0 ? 32. / Wr : 0.0;  // exact reference sequence
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(Wf));
+  r = __fma_rn(r, __fma_rn(-Wf, r, 1.0), r);
+  const double ws = r * (32.0 * 16384.0);
+  const double kMagic = 6755399441055744.0 + 1073741824.0;  // 1.5 * 2^52 + 2^30
+  const double tx = __fma_rn(nxf, ws, kMagic), ty = __fma_rn(nyf, ws, kMagic);
+  const unsigned ux = (unsigned)__double2loint(tx), uy = (unsigned)__double2loint(ty);
+  const unsigned hbad = ((unsigned)__double2hiint(tx) ^ 0x43380000u) | ((unsigned)__double2hiint(ty) ^ 0x43380000u);
+  const unsigned nearx = (ux & 0x3FFFu) - (0x2000u - 4u), neary = (uy & 0x3FFFu) - (0x2000u - 4u);  // <= 8: within 4/16384 of .5
+  int xi = (int)((ux + 0x2000u) >> 14) - 65536, yi = (int)((uy + 0x2000u) >> 14) - 65536;
+  if (hbad != 0u || min(nearx, neary) <= 8u) {
+    // exact reference sequence (separate multiply and add: this file is compiled with -fmad=false)
+    const double Wr = W0 + M[6] * x1;
+    const double nx = X0 + M[0] * x1, ny = Y0 + M[3] * x1;
+    double W = Wr != 0.0 ? 32. / Wr : 0.0;
     const double gx = nx * W, gy = ny * W;
     xi = __double2int_rn(gx);  // cvt.rni.s32.f64: round-half-even, saturating == saturate_cast<int>(clamp(.))
     yi = __double2int_rn(gy);
@@ -310,9 +308,9 @@ __device__ __forceinline__ void warp_coords(const double *M, double X0, double Y
 }
 
 __device__ __forceinline__ int warp_sample(const uint8_t *__restrict__ src, int row_stride, int sw, int sh, const double *M,
-                                           double X0, double Y0, double W0, int x1) {
+                                           double X0, double Y0, double W0, int x1, double xq) {
   int X, Y;
-  warp_coords(M, X0, Y0, W0, x1, &X, &Y);
+  warp_coords(M, X0, Y0, W0, x1, xq, &X, &Y);
   // saturate_cast<short>(X >> 5) only matters beyond +-32767 px, where every tap is outside the image anyway
   const int sx = X >> 5, sy = Y >> 5;
   const int fx = X & 31, fy = Y & 31;
@@ -367,9 +365,10 @@ warp_kernel(const uint8_t *__restrict__ src, int row_stride, size_t frame_stride
       const double Y0 = sM[3] * xb + sM[4] * y + sM[5];
       const double W0 = sM[6] * xb + sM[7] * y + sM[8];
       const unsigned int base = (unsigned)(y * B200_CARD_W + x) + 1u;
+      const double xq0 = (double)(x - xb);
 #pragma unroll
       for (int k = 0; k < 4; k++) {
-        const unsigned int v = (unsigned)warp_sample(s, row_stride, sw, sh, sM, X0, Y0, W0, x + k - xb);
+        const unsigned int v = (unsigned)warp_sample(s, row_stride, sw, sh, sM, X0, Y0, W0, x + k - xb, xq0 + (double)k);
         packed |= v << (8 * k);
         sum += (base + k) * v;
       }
@@ -749,6 +748,72 @@ int launch_warp(const uint8_t *src, int row_stride, size_t frame_stride, int w, 
     launches++;
   }
   return cudaGetLastError() == cudaSuccess ? launches : -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Frame scoring: dmz_focus_score / dmz_brightness_score (dmz.cpp:114-195).
+// One CTA per frame over the scoring rectangle (rows and columns clamp at the rectangle: the reference sets an
+// image ROI first).  Integer sums are exact, so the only floating point is the final double arithmetic of
+// cv::meanStdDev / cv::mean, done by one thread in the reference's operation order (no FMA in this file).
+// ------------------------------------------------------------------------------------------------
+constexpr int kScoreThreads = 256;
+
+__global__ void __launch_bounds__(kScoreThreads)
+frame_scores_kernel(const uint8_t *__restrict__ frames, int row_stride, size_t frame_stride, int n, int rx, int ry, int rw,
+                    int rh, float *__restrict__ focus, float *__restrict__ brightness) {
+  __shared__ unsigned long long s_acc[kScoreThreads / 32][3];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int f = blockIdx.x; f < n; f += gridDim.x) {
+    const uint8_t *roi = frames + (size_t)f * frame_stride + (size_t)ry * row_stride + rx;
+    unsigned int sum_px = 0, sum_abs = 0;
+    unsigned long long sum_sq = 0;
+    for (int y = warp; y < rh; y += kScoreThreads / 32) {
+      const uint8_t *r0 = roi + (size_t)y * row_stride;
+      const uint8_t *r1 = roi + (size_t)(y == 0 ? 0 : y - 1) * row_stride;
+      const uint8_t *r2 = roi + (size_t)(y == rh - 1 ? y : y + 1) * row_stride;
+      unsigned int sq = 0;
+      for (int x = lane; x < rw; x += 32) {
+        const int xl = x == 0 ? 0 : x - 1, xr = x == rw - 1 ? x : x + 1;
+        const int v = (int)__ldg(r1 + xl) - (int)__ldg(r1 + xr) - (int)__ldg(r2 + xl) + (int)__ldg(r2 + xr);
+        const unsigned int a = (unsigned int)abs(v);
+        sum_px += __ldg(r0 + x);
+        sum_abs += a;
+        sq += a * a;  // <= 510^2 * ceil(rw / 32): fits 32 bits for any row a frame can have
+      }
+      sum_sq += sq;
+    }
+    unsigned long long v0 = sum_px, v1 = sum_abs, v2 = sum_sq;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+      v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+      v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+    }
+    __syncthreads();  // previous frame's s_acc fully consumed
+    if (lane == 0) s_acc[warp][0] = v0, s_acc[warp][1] = v1, s_acc[warp][2] = v2;
+    __syncthreads();
+    if (tid == 0) {
+      unsigned long long t0 = 0, t1 = 0, t2 = 0;
+      for (int w = 0; w < kScoreThreads / 32; w++) t0 += s_acc[w][0], t1 += s_acc[w][1], t2 += s_acc[w][2];
+      const double scale = 1. / ((double)rw * (double)rh);
+      if (brightness) brightness[f] = (float)((double)t0 * scale);  // cv::mean: s * (1. / total)
+      if (focus) {  // cv::meanStdDev: s *= scale; sd = sqrt(max(sq * scale - s * s, 0.))
+        const double m = (double)t1 * scale;
+        const double var = (double)t2 * scale - m * m;
+        focus[f] = (float)sqrt(var > 0. ? var : 0.);
+      }
+    }
+  }
+}
+
+int launch_frame_scores(const uint8_t *frames, int row_stride, size_t frame_stride, int n, int rx, int ry, int rw, int rh,
+                        float *focus, float *brightness, cudaStream_t s) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int grid = n < sms * 8 ? n : sms * 8;
+  frame_scores_kernel<<<grid, kScoreThreads, 0, s>>>(frames, row_stride, frame_stride, n, rx, ry, rw, rh, focus, brightness);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
 int launch_finalize_records(const FrameGeom *geom, const b200_scan *scans, const unsigned int *card_check, int n,

@@ -172,6 +172,13 @@ int b200_digit_models_batch(b200_ctx *ctx, const float *patches, int n, int mem,
 /* applym_befe75da on prepared rows: in = n x 204 f32, out = n x 3 f32 */
 int b200_vseg_model_batch(b200_ctx *ctx, const float *rows, int n, int mem, float *out);
 
+/* ---- frame scoring ----
+ * dmz_focus_score / dmz_brightness_score (dmz.h:77-80, dmz.cpp:114-195) for n luma planes: focus = stddev of
+ * |sobel3 dx.dy| and brightness = mean, both over the reference's scoring rectangle (the centred card-sized rectangle,
+ * or its central ninth when use_full_image is 0).  Either output pointer may be NULL.  Outputs live where `mem` says. */
+int b200_frame_scores_batch(b200_ctx *ctx, const uint8_t *y, int y_row_stride, size_t y_frame_stride, int width, int height,
+                            int n, int use_full_image, int mem, float *focus, float *brightness);
+
 /* ---- E0: expiry digit (the SCAN_EXPIRY-only branch of scanner_add_frame_with_expiry) ----
  * prepare_image_for_cat + applyc_bf4dd6c8 (scan/expiry_categorize.cpp:37-109, models/expiry/modelc_bf4dd6c8.cpp):
  * patches = n x 16 rows x 11 cols u8 cut from the card at a character rect; out = n x 10 digit probabilities.

@@ -9,6 +9,7 @@
  *   reference declaration                                        file:line
  *   dmz_context_create / destroy / prepare_for_backgrounding     dmz.h:48-54
  *   dmz_found_all_edges, dmz_detect_edges                        dmz.h:82-87
+ *   dmz_focus_score, dmz_brightness_score                        dmz.h:77-80
  *   dmz_transform_card                                           dmz.h:96
  *   scanner_initialize / reset / add_frame[_with_expiry] /
  *   result / destroy                                             scan/scan.h:51-72
@@ -172,6 +173,8 @@ bool dmz_detect_edges(IplImage *y_sample, IplImage *cb_sample, IplImage *cr_samp
                       dmz_edges *found_edges, dmz_corner_points *corner_points);
 void dmz_transform_card(dmz_context *dmz, IplImage *sample, dmz_corner_points corner_points, FrameOrientation orientation,
                         bool upsample, IplImage **transformed);
+float dmz_focus_score(IplImage *image, bool use_full_image);      /* dmz.h:77 */
+float dmz_brightness_score(IplImage *image, bool use_full_image); /* dmz.h:80 */
 void scanner_initialize(ScannerState *state);
 void scanner_reset(ScannerState *state);
 void scanner_add_frame(ScannerState *state, IplImage *y, FrameScanResult *result);

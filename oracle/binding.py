@@ -113,6 +113,9 @@ class Oracle:
         f("scanner_add_frame", [vp, vp, C.POINTER(Scan)])
         f("scanner_peek", [vp, vp, vp, vp])
         f("scanner_result", [vp, vp, C.POINTER(C.c_int32)], i)
+        f("focus_score", [vp, i, i, i, i], C.c_float)
+        f("brightness_score", [vp, i, i, i, i], C.c_float)
+        f("scoring_rect", [i, i, i, vp])
         f("luhn", [vp, i], i)
         f("card_type", [vp, i], i)
         f("bench_frames", [vp, i, i, i, vp, vp, i, i, vp], C.c_double)
@@ -233,6 +236,20 @@ class Oracle:
         out = np.zeros(40, np.float32)
         self._digit_models(_p(patch), _p(out))
         return out[:10].copy(), out[10:].reshape(3, 10).copy()
+
+    # ---- frame scoring (dmz_focus_score / dmz_brightness_score) ---------------------------------------------
+    def focus_score(self, y, use_full_image=False):
+        y = np.ascontiguousarray(y, np.uint8)
+        return float(self._focus_score(_p(y), y.shape[1], y.shape[1], y.shape[0], int(use_full_image)))
+
+    def brightness_score(self, y, use_full_image=False):
+        y = np.ascontiguousarray(y, np.uint8)
+        return float(self._brightness_score(_p(y), y.shape[1], y.shape[1], y.shape[0], int(use_full_image)))
+
+    def scoring_rect(self, w, h, use_full_image=False):
+        out = np.zeros(4, np.int32)
+        self._scoring_rect(w, h, int(use_full_image), _p(out))
+        return out
 
     # ---- E0: expiry digit (port only; the reference build here has SCAN_EXPIRY off) -----------------------
     def expiry_patch_prep(self, img16x11):

@@ -255,19 +255,11 @@ CV_IMPL CvScalar cvAvg(const CvArr *arr, const CvArr *mask) {
 
 CV_IMPL void cvAvgSdv(const CvArr *arr, CvScalar *mean, CvScalar *std_dev, const CvArr *mask) {
   View s = view_of(arr);
-  if (mask || s.cn != 1) SHIM_FAIL("only unmasked single channel");
-  double sum = 0, sq = 0;
-  for (int y = 0; y < s.h; y++) {
-    const uchar *row = s.p + (size_t)y * s.step;
-    for (int x = 0; x < s.w; x++) {
-      double v = s.depth == CV_8U ? row[x] : s.depth == CV_16S ? ((const short *)row)[x] : ((const float *)row)[x];
-      sum += v;
-      sq += v * v;
-    }
-  }
-  double n = (double)s.w * s.h, m = sum / n, var = sq / n - m * m;
+  if (mask || s.cn != 1 || s.depth != CV_16S) SHIM_FAIL("only unmasked single-channel s16");
+  double m, sd;
+  orc_mean_stddev_s16((const int16_t *)s.p, s.step, s.w, s.h, &m, &sd);
   if (mean) *mean = cvScalar(m);
-  if (std_dev) *std_dev = cvScalar(sqrt(var > 0 ? var : 0));
+  if (std_dev) *std_dev = cvScalar(sd);
 }
 
 CV_IMPL void cvConvertScale(const CvArr *srcarr, CvArr *dstarr, double scale, double shift) {

@@ -1002,6 +1002,66 @@ void orc_scanner_peek(void *state, float agg15[160], float agg16[160], int32_t c
   counts[1] = s->count16;
 }
 
+/* ---- frame scoring ---------------------------------------------------------------------------------------
+ * dmz_card_rect_for_screen + dmz_set_roi_for_scoring (dmz.cpp:136-181): the card-sized (or card/3-sized) rectangle
+ * centred in the frame, scaled by min(w/640, h/480) in float with (int) truncation when the frame is not 640x480.
+ * cvSetImageROI then clips it to the image. */
+void orc_scoring_rect(int w, int h, int use_full_image, int rect[4]) {
+  int cw = use_full_image ? 428 : 428 / 3, ch = use_full_image ? 270 : 270 / 3;
+  int rw, rh, x, y, x1, y1;
+  if (w == 0 || h == 0) {
+    rect[0] = rect[1] = rect[2] = rect[3] = 0;
+    return;
+  }
+  if (w == 640 && h == 480) {
+    rw = cw, rh = ch;
+  } else {
+    float rx = ((float)w) / ((float)640), ry = ((float)h) / ((float)480);
+    float ratio = rx < ry ? rx : ry;
+    rw = (int)(cw * ratio);
+    rh = (int)(ch * ratio);
+  }
+  x = (w - rw) / 2, y = (h - rh) / 2;
+  x1 = x + rw, y1 = y + rh; /* cvSetImageROI clipping */
+  if (x < 0) x = 0;
+  if (y < 0) y = 0;
+  if (x1 > w) x1 = w;
+  if (y1 > h) y1 = h;
+  rect[0] = x, rect[1] = y, rect[2] = x1 - x, rect[3] = y1 - y;
+}
+
+/* dmz_focus_score_for_image (dmz.cpp:114-127): llcv_sobel3_dx_dy's scalar path (cv/sobel.cpp:556-628: the diagonal
+ * kernel [1 0 -1; 0 0 0; -1 0 1] with rows and columns clamped at the ROI), then llcv_stddev_of_abs_c
+ * (cv/stats.cpp:87-92: cvAbs, cvAvgSdv). */
+float orc_focus_score(const uint8_t *img, int ystep, int w, int h, int use_full_image) {
+  int rc[4], x, y;
+  int16_t *g;
+  double sd;
+  orc_scoring_rect(w, h, use_full_image, rc);
+  if (rc[2] < 2 || rc[3] < 1) return 0.0f;
+  g = (int16_t *)malloc((size_t)rc[2] * rc[3] * sizeof(int16_t));
+  for (y = 0; y < rc[3]; y++) {
+    const uint8_t *r1 = img + (size_t)(rc[1] + (y == 0 ? 0 : y - 1)) * ystep + rc[0];
+    const uint8_t *r2 = img + (size_t)(rc[1] + (y == rc[3] - 1 ? y : y + 1)) * ystep + rc[0];
+    for (x = 0; x < rc[2]; x++) {
+      int xl = x == 0 ? 0 : x - 1, xr = x == rc[2] - 1 ? x : x + 1;
+      int v = r1[xl] - r1[xr] - r2[xl] + r2[xr];
+      g[(size_t)y * rc[2] + x] = (int16_t)(v < 0 ? -v : v); /* cvAbs; |v| <= 510 */
+    }
+  }
+  orc_mean_stddev_s16(g, rc[2] * (int)sizeof(int16_t), rc[2], rc[3], NULL, &sd);
+  free(g);
+  return (float)sd;
+}
+
+/* dmz_brightness_score_for_image (dmz.cpp:129-134): (float)cvAvg over the scoring ROI */
+float orc_brightness_score(const uint8_t *img, int ystep, int w, int h, int use_full_image) {
+  int rc[4];
+  orc_scoring_rect(w, h, use_full_image, rc);
+  if (rc[2] < 1 || rc[3] < 1) return 0.0f;
+  return (float)orc_mean_u8(img + (size_t)rc[1] * ystep + rc[0], ystep, rc[2], rc[3]);
+}
+
 int orc_luhn(const uint8_t *d, int n) { /* dmz_olm.cpp dmz_passes_luhn_checksum */
   int even = 0, sum = 0, i;
   for (i = n - 1; i >= 0; i--) {

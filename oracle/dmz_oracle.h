@@ -61,6 +61,12 @@ int orc_scanner_result(void *state, uint8_t digits[16], int32_t *n_numbers);
 int orc_luhn(const uint8_t *digits, int n);
 int orc_card_type(const uint8_t *digits, int n);
 
+/* ---- frame scoring: dmz_focus_score / dmz_brightness_score (dmz.cpp:114-195) ----
+ * rect = {x, y, w, h} of dmz_set_roi_for_scoring for a w x h frame. */
+void orc_scoring_rect(int w, int h, int use_full_image, int rect[4]);
+float orc_focus_score(const uint8_t *y, int ystep, int w, int h, int use_full_image);
+float orc_brightness_score(const uint8_t *y, int ystep, int w, int h, int use_full_image);
+
 uint32_t orc_card_check(const uint8_t *p, size_t n);
 
 /* multi-threaded timing of the whole path (bench.py cpu_baseline kind "port"); returns wall seconds */

@@ -345,9 +345,29 @@ void orc_bilateral_u8(const uint8_t *src, int sstep, int w, int h, uint8_t *dst,
 }
 
 double orc_mean_u8(const uint8_t *src, int sstep, int w, int h) {
+  /* cv::mean (core/stat.cpp, 2.4.x): integer block sums flushed into a double, then s * (1. / total) */
   double total = 0;
   int x, y;
   for (y = 0; y < h; y++)
     for (x = 0; x < w; x++) total += src[(size_t)y * sstep + x];
-  return total / ((double)w * h);
+  return total * (1. / ((double)w * h));
+}
+
+void orc_mean_stddev_s16(const int16_t *src, int sstep, int w, int h, double *mean, double *stddev) {
+  /* cv::meanStdDev (core/stat.cpp, 2.4.x) for CV_16S: sum in int blocks, sqsum in double -- both exact for
+   * anything this path feeds it -- then scale = 1. / total; s *= scale; sd = sqrt(max(sq * scale - s * s, 0)) */
+  int64_t sum = 0, sq = 0;
+  int x, y;
+  for (y = 0; y < h; y++) {
+    const int16_t *row = (const int16_t *)((const uint8_t *)src + (size_t)y * sstep);
+    for (x = 0; x < w; x++) {
+      sum += row[x];
+      sq += (int64_t)row[x] * row[x];
+    }
+  }
+  {
+    double scale = 1. / ((double)w * h), s = (double)sum * scale, v = (double)sq * scale - s * s;
+    if (mean) *mean = s;
+    if (stddev) *stddev = sqrt(v > 0. ? v : 0.);
+  }
 }

@@ -374,6 +374,24 @@ int ref_scanner_result(void *state, uint8_t digits[16], int32_t *n_numbers) {
   return r.complete;
 }
 
+/* dmz_focus_score / dmz_brightness_score (dmz.cpp:183-195) */
+float ref_focus_score(const uint8_t *y, int ystep, int w, int h, int use_full_image) {
+  Hdr a;
+  wrap(&a, y, w, h, ystep, IPL_DEPTH_8U);
+  return dmz_focus_score(&a.img, use_full_image != 0);
+}
+float ref_brightness_score(const uint8_t *y, int ystep, int w, int h, int use_full_image) {
+  Hdr a;
+  wrap(&a, y, w, h, ystep, IPL_DEPTH_8U);
+  return dmz_brightness_score(&a.img, use_full_image != 0);
+}
+void ref_scoring_rect(int w, int h, int use_full_image, int rect[4]) {
+  CvSize fs = use_full_image ? cvSize(kCreditCardTargetWidth, kCreditCardTargetHeight)
+                             : cvSize(kCreditCardTargetWidth / 3, kCreditCardTargetHeight / 3);
+  CvRect r = dmz_card_rect_for_screen(fs, cvSize(kLandscapeSampleWidth, kLandscapeSampleHeight), cvSize(w, h));
+  rect[0] = r.x, rect[1] = r.y, rect[2] = r.width, rect[3] = r.height;
+}
+
 int ref_luhn(const uint8_t *digits, int n) { return dmz_passes_luhn_checksum((uint8_t *)digits, (uint8_t)n); }
 int ref_card_type(const uint8_t *digits, int n) {
   return dmz_card_info_for_prefix_and_length((uint8_t *)digits, (uint8_t)n, false).card_type;

@@ -36,6 +36,8 @@ int main(int argc, char **argv) {
     wrap(&y, frames.data() + (size_t)k * w * h, w, h);
     wrap(&cb, chroma.data(), w / 2, h / 2);
     wrap(&cr, chroma.data(), w / 2, h / 2);
+    // the SDK scores focus on the central ninth of the card region before spending time on detection
+    float fb[2] = {dmz_focus_score(&y, false), dmz_brightness_score(&y, false)};
     dmz_edges edges;
     dmz_corner_points corners;
     memset(&corners, 0, sizeof(corners));
@@ -69,6 +71,7 @@ int main(int argc, char **argv) {
     fwrite(&corners, sizeof(corners), 1, out);
     fwrite(scores, sizeof(scores), 1, out);
     fwrite(digits, 16, 1, out);
+    fwrite(fb, sizeof(fb), 1, out);
   }
   scanner_destroy(&state);
   dmz_context_destroy(dmz);

@@ -208,6 +208,29 @@ def test_categorize_patches(dmz, oracle, golden):
         assert np.abs(ens[i] - e).max() <= TOL and np.abs(mods[i] - m).max() <= TOL, i
 
 
+def test_frame_scores_exact(dmz, oracle, golden, deck):
+    """dmz_focus_score / dmz_brightness_score: float bits equal to the oracle and to the reference
+    build's golden outputs, at 640x480 and at frame sizes that scale / clip the scoring rectangle."""
+    frames = np.concatenate([deck_frames(int(i), 1) for i in golden["deck_idx"]])
+    for full in (0, 1):
+        f, b = dmz.frame_scores(frames, full)
+        assert np.array_equal(bits(f), golden["deck_focus"][full]) and np.array_equal(bits(b), golden["deck_brightness"][full])
+    rng = np.random.default_rng(5)
+    for (w, h, n) in [(640, 480, 33), (1280, 720, 5), (1920, 1080, 2), (320, 240, 7), (641, 479, 3), (100, 50, 4)]:
+        imgs = rng.integers(0, 256, (n, h, w), dtype=np.uint8)
+        imgs[0] = 0            # flat frame: variance exactly 0
+        if n > 2:
+            imgs[1] = 255
+            imgs[2] = (np.arange(w)[None, :] * 3 + np.arange(h)[:, None] * 5) & 255
+        for full in (0, 1):
+            f, b = dmz.frame_scores(imgs, full)
+            wf = np.array([oracle.focus_score(x, full) for x in imgs], np.float32)
+            wb = np.array([oracle.brightness_score(x, full) for x in imgs], np.float32)
+            assert np.array_equal(bits(f), bits(wf)) and np.array_equal(bits(b), bits(wb)), (w, h, full)
+    f, _ = dmz.frame_scores(deck[:8])
+    assert f.min() > 5.0  # the synthetic deck is in focus by the reference's own measure
+
+
 def test_expiry_digit_known_answer_and_parity(dmz, oracle):
     """E0: prepare_image_for_cat + applyc_bf4dd6c8 (scan/expiry_categorize.cpp:37-109).  The
     reference's embedded KAT at its own 1e-5; random / structured character crops against the oracle at 1e-4."""
@@ -343,9 +366,11 @@ def test_cxx_dropin_layer(dmz, oracle, tmp_path):
     fin, fout = str(tmp_path / "frames.bin"), str(tmp_path / "out.bin")
     frames.tofile(fin)
     subprocess.check_call([exe, fin, "8", "640", "480", fout])
-    dt = np.dtype([("rec", "<i4", 8), ("corners", "<f4", 8), ("scores", "<f4", 160), ("digits", "u1", 16)])
+    dt = np.dtype([("rec", "<i4", 8), ("corners", "<f4", 8), ("scores", "<f4", 160), ("digits", "u1", 16), ("fb", "<f4", 2)])
     got = np.fromfile(fout, dt)
     want, cards = oracle.process_frames(frames, want_cards=True)
+    assert np.array_equal(bits(got["fb"][:, 0]), bits(np.array([oracle.focus_score(f) for f in frames], np.float32)))
+    assert np.array_equal(bits(got["fb"][:, 1]), bits(np.array([oracle.brightness_score(f) for f in frames], np.float32)))
     assert np.array_equal(got["rec"][:, 0], want["all_found"])
     assert np.array_equal(bits(got["corners"]), bits(want["corners"]))
     assert np.array_equal(got["rec"][:, 7].astype(np.uint32), want["card_check"])

@@ -40,6 +40,22 @@ def test_kat_expiry_cnn(oracle):
     assert np.abs(out - k["test output"]).max() <= tol
 
 
+def test_frame_scores(oracle, golden):
+    """dmz_focus_score / dmz_brightness_score (dmz.cpp:114-195) against the reference build's outputs, bit for bit."""
+    frames = np.concatenate([deck_frames(int(i), 1) for i in golden["deck_idx"]])
+    for full in (0, 1):
+        f = np.array([oracle.focus_score(x, full) for x in frames], np.float32).view(np.uint32)
+        b = np.array([oracle.brightness_score(x, full) for x in frames], np.float32).view(np.uint32)
+        assert np.array_equal(f, golden["deck_focus"][full]) and np.array_equal(b, golden["deck_brightness"][full])
+    srng = np.random.default_rng(99)
+    for (w, h) in [(1280, 720), (320, 240), (641, 479)]:
+        img = srng.integers(0, 256, (h, w), dtype=np.uint8)
+        for full in (0, 1):
+            assert np.array_equal(oracle.scoring_rect(w, h, full), golden["score_rect_%dx%d" % (w, h)][full])
+            got = np.array([oracle.focus_score(img, full), oracle.brightness_score(img, full)], np.float32).view(np.uint32)
+            assert np.array_equal(got, golden["score_%dx%d" % (w, h)][full]), (w, h, full)
+
+
 def test_detection_boxes(oracle, golden):
     for key in golden.files:
         if key.startswith("boxes_"):

@@ -88,6 +88,16 @@ out["session_agg16"] = a16; out["session_agg15"] = a15; out["session_counts"] = 
 out["session_complete"] = np.array([r[0] for r in results], np.int32)
 out["session_digits"] = np.array(results[-1][1], np.uint8)
 
+# ---- frame scoring: dmz_focus_score / dmz_brightness_score on the deck frames above and on noise at other sizes
+out["deck_focus"] = np.array([[R.focus_score(f, full) for f in frames] for full in (0, 1)], np.float32).view(np.uint32)
+out["deck_brightness"] = np.array([[R.brightness_score(f, full) for f in frames] for full in (0, 1)], np.float32).view(np.uint32)
+srng = np.random.default_rng(99)
+for (w, h) in [(1280, 720), (320, 240), (641, 479)]:
+    img = srng.integers(0, 256, (h, w), dtype=np.uint8)
+    out["score_%dx%d_img_seed" % (w, h)] = np.int32(99)
+    out["score_%dx%d" % (w, h)] = np.array([[R.focus_score(img, full), R.brightness_score(img, full)] for full in (0, 1)], np.float32).view(np.uint32)
+    out["score_rect_%dx%d" % (w, h)] = np.stack([R.scoring_rect(w, h, full) for full in (0, 1)])
+
 path = os.path.join(ROOT, "tests", "golden", "ref_golden.npz")
 np.savez_compressed(path, **out)
 print("wrote", path, os.path.getsize(path), "bytes; session complete flags", out["session_complete"], "digits", out["session_digits"])
