@@ -11,6 +11,8 @@
 //   finalize_records_kernel  flat per-frame record + card checksum
 #include <float.h>
 
+#include <stdlib.h>
+
 #include "b200_internal.h"
 
 namespace {
@@ -307,39 +309,39 @@ __device__ __forceinline__ void warp_coords(const double *M, double X0, double Y
   *X = xi, *Y = yi;
 }
 
-__device__ __forceinline__ int warp_sample(const uint8_t *__restrict__ src, int row_stride, int sw, int sh, const double *M,
-                                           double X0, double Y0, double W0, int x1, double xq) {
-  int X, Y;
-  warp_coords(M, X0, Y0, W0, x1, xq, &X, &Y);
+// The four bilinear taps of destination pixel (X, Y) (1/32 px fixed point); out-of-image taps read as 0.
+__device__ __forceinline__ void warp_fetch(const uint8_t *__restrict__ src, int row_stride, int sw, int sh, int X, int Y, int v[4]) {
   // saturate_cast<short>(X >> 5) only matters beyond +-32767 px, where every tap is outside the image anyway
   const int sx = X >> 5, sy = Y >> 5;
-  const int fx = X & 31, fy = Y & 31;
-  int v0, v1, v2, v3;
   if ((unsigned)sx < (unsigned)(sw - 1) && (unsigned)sy < (unsigned)(sh - 1)) {
     const uint8_t *p = src + (sy * row_stride + sx);  // 32-bit offset inside one frame
-    v0 = __ldg(p), v1 = __ldg(p + 1), v2 = __ldg(p + row_stride), v3 = __ldg(p + row_stride + 1);
+    v[0] = __ldg(p), v[1] = __ldg(p + 1), v[2] = __ldg(p + row_stride), v[3] = __ldg(p + row_stride + 1);
   } else if (sx >= sw || sx + 1 < 0 || sy >= sh || sy + 1 < 0) {
-    return 0;
+    v[0] = v[1] = v[2] = v[3] = 0;
   } else {
     const bool x0ok = sx >= 0 && sx < sw, x1ok = sx + 1 >= 0 && sx + 1 < sw;
     const bool y0ok = sy >= 0 && sy < sh, y1ok = sy + 1 >= 0 && sy + 1 < sh;
-    v0 = (x0ok && y0ok) ? __ldg(src + (sy * row_stride + sx)) : 0;
-    v1 = (x1ok && y0ok) ? __ldg(src + (sy * row_stride + sx + 1)) : 0;
-    v2 = (x0ok && y1ok) ? __ldg(src + ((sy + 1) * row_stride + sx)) : 0;
-    v3 = (x1ok && y1ok) ? __ldg(src + ((sy + 1) * row_stride + sx + 1)) : 0;
+    v[0] = (x0ok && y0ok) ? __ldg(src + (sy * row_stride + sx)) : 0;
+    v[1] = (x1ok && y0ok) ? __ldg(src + (sy * row_stride + sx + 1)) : 0;
+    v[2] = (x0ok && y1ok) ? __ldg(src + ((sy + 1) * row_stride + sx)) : 0;
+    v[3] = (x1ok && y1ok) ? __ldg(src + ((sy + 1) * row_stride + sx + 1)) : 0;
   }
-  // The 15-bit weights are (32-fx)(32-fy)*32, fx(32-fy)*32, (32-fx)fy*32, fx*fy*32, so
-  //   (sum w_i v_i + 2^14) >> 15  ==  ((v0 (32-fx) + v1 fx)(32-fy) + (v2 (32-fx) + v3 fx) fy + 2^9) >> 10   exactly.
-  // OpenCV's table holds {32767, 0, 0, 1} at (0,0) (saturate_cast<short>(32768) + compensation); that entry also
-  // evaluates to v0 for every 8-bit v0, v3, as does this formula, so no special case is needed.
+}
+
+// The 15-bit weights are (32-fx)(32-fy)*32, fx(32-fy)*32, (32-fx)fy*32, fx*fy*32, so
+//   (sum w_i v_i + 2^14) >> 15  ==  ((v0 (32-fx) + v1 fx)(32-fy) + (v2 (32-fx) + v3 fx) fy + 2^9) >> 10   exactly.
+// OpenCV's table holds {32767, 0, 0, 1} at (0,0) (saturate_cast<short>(32768) + compensation); that entry also
+// evaluates to v0 for every 8-bit v0, v3, as does this formula, so no special case is needed.
+__device__ __forceinline__ int warp_blend(int X, int Y, const int v[4]) {
+  const int fx = X & 31, fy = Y & 31;
   const int ax = 32 - fx;
-  const int top = v0 * ax + v1 * fx, bot = v2 * ax + v3 * fx;
+  const int top = v[0] * ax + v[1] * fx, bot = v[2] * ax + v[3] * fx;
   return (top * (32 - fy) + bot * fy + 512) >> 10;  // always in [0, 255]
 }
 
 // card_check (optional): per-frame checksum sum_i (i + 1) * card[i] mod 2^32, accumulated while the pixels are
 // still in registers (one global atomic per CTA) so that no later stage has to re-read the card for it.
-__global__ void __launch_bounds__(kWarpThreads, 4)
+__global__ void __launch_bounds__(kWarpThreads, 4)  // measured: 3 or 5 resident CTAs are both ~10 % slower
 warp_kernel(const uint8_t *__restrict__ src, int row_stride, size_t frame_stride, int sw, int sh,
             const FrameGeom *__restrict__ geom, uint8_t *__restrict__ cards, unsigned int *__restrict__ card_check, int ox, int oy) {
   const int frame = blockIdx.y;
@@ -356,24 +358,42 @@ warp_kernel(const uint8_t *__restrict__ src, int row_stride, size_t frame_stride
   const int nrows = min(kWarpRows, B200_CARD_H - row0);
   unsigned int sum = 0;
   const int r0 = threadIdx.x >= kQuadsPerRow ? 1 : 0, q = threadIdx.x - r0 * kQuadsPerRow;
-  for (int r = threadIdx.x < 2 * kQuadsPerRow ? r0 : nrows; r < nrows; r += 2) {
-    const int y = row0 + r, x = q * 4;
+  const int x = q * 4, xb = x & ~63;  // block origin: bw0 = 64
+  const double xq0 = (double)(x - xb);
+  const bool ok = s_ok != 0;
+  int r = threadIdx.x < 2 * kQuadsPerRow ? r0 : nrows;
+  // Software pipeline over this thread's rows: the taps of row r are requested, the (FP64-heavy) coordinates of row
+  // r + 2 are computed while those loads are in flight, and only then are the taps blended.
+  int Xc[4], Yc[4];
+  auto coords = [&](int row, int *Xo, int *Yo) {
+    const int y = row0 + row;
+    const double X0 = sM[0] * xb + sM[1] * y + sM[2];
+    const double Y0 = sM[3] * xb + sM[4] * y + sM[5];
+    const double W0 = sM[6] * xb + sM[7] * y + sM[8];
+#pragma unroll
+    for (int k = 0; k < 4; k++) warp_coords(sM, X0, Y0, W0, x + k - xb, xq0 + (double)k, &Xo[k], &Yo[k]);
+  };
+  if (ok && r < nrows) coords(r, Xc, Yc);
+#pragma unroll 1
+  while (r < nrows) {
+    const int y = row0 + r, rn = r + 2;
     unsigned int packed = 0;
-    if (s_ok) {
-      const int xb = x & ~63;  // block origin: bw0 = 64
-      const double X0 = sM[0] * xb + sM[1] * y + sM[2];
-      const double Y0 = sM[3] * xb + sM[4] * y + sM[5];
-      const double W0 = sM[6] * xb + sM[7] * y + sM[8];
+    if (ok) {
+      int v[4][4], Xn[4], Yn[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) warp_fetch(s, row_stride, sw, sh, Xc[k], Yc[k], v[k]);
+      if (rn < nrows) coords(rn, Xn, Yn);
       const unsigned int base = (unsigned)(y * B200_CARD_W + x) + 1u;
-      const double xq0 = (double)(x - xb);
 #pragma unroll
       for (int k = 0; k < 4; k++) {
-        const unsigned int v = (unsigned)warp_sample(s, row_stride, sw, sh, sM, X0, Y0, W0, x + k - xb, xq0 + (double)k);
-        packed |= v << (8 * k);
-        sum += (base + k) * v;
+        const unsigned int px = (unsigned)warp_blend(Xc[k], Yc[k], v[k]);
+        packed |= px << (8 * k);
+        sum += (base + k) * px;
+        Xc[k] = Xn[k], Yc[k] = Yn[k];
       }
     }
     *reinterpret_cast<unsigned int *>(dst + y * B200_CARD_W + x) = packed;
+    r = rn;
   }
   if (card_check != nullptr) {
 #pragma unroll
