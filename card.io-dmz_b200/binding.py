@@ -105,6 +105,7 @@ def _load():
     lib.b200_categorize_patches_batch.argtypes = [vp, vp, i, i, vp]
     lib.b200_vseg_model_batch.argtypes = [vp, vp, i, i, vp]
     lib.b200_digit_models_batch.argtypes = [vp, vp, i, i, vp]
+    lib.b200_deinterleave_c2_batch.argtypes = [vp, vp, i, C.c_size_t, i, i, i, i, vp, vp]
     lib.b200_frame_scores_batch.argtypes = [vp, vp, i, C.c_size_t, i, i, i, i, i, vp, vp]
     lib.b200_expiry_digits_batch.argtypes = [vp, vp, i, i, vp]
     lib.b200_expiry_digit_models_batch.argtypes = [vp, vp, i, i, vp]
@@ -245,6 +246,14 @@ class Dmz:
         out = np.zeros((n, 40), np.float32)
         self._check(self.lib.b200_digit_models_batch(self.ctx, _ptr(patches), n, MEM_HOST, _ptr(out)))
         return out[:, :10].copy(), out[:, 10:].reshape(n, 3, 10).copy()
+
+    def deinterleave_c2(self, planes):
+        """planes: (n, h, w, 2) u8 interleaved CbCr.  Returns (channel1, channel2), each (n, h, w) (dmz_deinterleave_uint8_c2)."""
+        planes = np.ascontiguousarray(planes, np.uint8)
+        n, h, w, _ = planes.shape
+        c1, c2 = np.zeros((n, h, w), np.uint8), np.zeros((n, h, w), np.uint8)
+        self._check(self.lib.b200_deinterleave_c2_batch(self.ctx, _ptr(planes), 2 * w, 2 * w * h, w, h, n, MEM_HOST, _ptr(c1), _ptr(c2)))
+        return c1, c2
 
     def frame_scores(self, frames, use_full_image=False):
         """frames: (n, h, w) u8 luma.  Returns (focus, brightness) float32 arrays (dmz_focus_score / dmz_brightness_score)."""

@@ -680,6 +680,33 @@ int b200_digit_models_batch(b200_ctx *ctx, const float *patches, int n, int mem,
   return B200_OK;
 }
 
+// dmz_deinterleave_uint8_c2 over a batch: n interleaved 2-channel planes (width pixels = 2 * width bytes per row) into
+// two dense width x height planes each.
+int b200_deinterleave_c2_batch(b200_ctx *ctx, const uint8_t *interleaved, int row_stride, size_t frame_stride, int width, int height,
+                               int n, int mem, uint8_t *channel1, uint8_t *channel2) {
+  if (!ctx || !interleaved || !channel1 || !channel2 || n < 1 || width < 1 || height < 1 || row_stride < 2 * width)
+    return fail(ctx, B200_EINVAL, "b200_deinterleave_c2_batch: bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  if (mem == B200_MEM_DEVICE) {
+    LAUNCH(launch_deinterleave_c2(interleaved, row_stride, frame_stride, width, height, n, channel1, channel2, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return B200_OK;
+  }
+  const size_t plane = (size_t)width * height, in_bytes = ((2 * plane * n) + 15) & ~(size_t)15, out_bytes = (plane * n + 15) & ~(size_t)15;
+  int rc = ensure_misc(ctx, in_bytes + 2 * out_bytes);
+  if (rc) return rc;
+  uint8_t *d_in = (uint8_t *)ctx->d_misc, *d_c1 = d_in + in_bytes, *d_c2 = d_c1 + out_bytes;
+  for (int i = 0; i < n; i++)  // rows are packed on the way up (2 * width bytes each)
+    CU(cudaMemcpy2DAsync(d_in + (size_t)i * 2 * plane, (size_t)2 * width, interleaved + (size_t)i * frame_stride, (size_t)row_stride,
+                         (size_t)2 * width, (size_t)height, cudaMemcpyHostToDevice, ctx->stream));
+  LAUNCH(launch_deinterleave_c2(d_in, 2 * width, 2 * plane, width, height, n, d_c1, d_c2, ctx->stream));
+  CU(cudaMemcpyAsync(channel1, d_c1, plane * n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(channel2, d_c2, plane * n, cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->h2d_bytes += 2 * plane * n, ctx->d2h_bytes += 2 * plane * n;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}
+
 // dmz_focus_score / dmz_brightness_score over a batch.  Host frames: only the scoring rectangle crosses PCIe (the
 // reference's ROI clamps the Sobel taps at the rectangle, so nothing outside it is ever read).
 int b200_frame_scores_batch(b200_ctx *ctx, const uint8_t *y, int yrs, size_t yfs, int width, int height, int n,

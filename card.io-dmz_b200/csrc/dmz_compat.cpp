@@ -50,28 +50,30 @@ PlaneView view_of(const IplImage *img) {
   return v;
 }
 
-IplImage *create_card_image() {
+IplImage *create_gray_image(int width, int height) {
   // Prefer the host application's OpenCV allocator so that its cvReleaseImage frees what we hand out.
   typedef struct { int width, height; } Size2;
   typedef IplImage *(*create_fn)(Size2, int, int);
   static create_fn cv_create = (create_fn)dlsym(RTLD_DEFAULT, "cvCreateImage");
   if (cv_create) {
-    Size2 s = {B200_CARD_W, B200_CARD_H};
+    Size2 s = {width, height};
     return cv_create(s, IPL_DEPTH_8U, 1);
   }
   IplImage *img = (IplImage *)calloc(1, sizeof(IplImage));
   img->nSize = sizeof(IplImage);
   img->nChannels = 1;
   img->depth = IPL_DEPTH_8U;
-  img->width = B200_CARD_W, img->height = B200_CARD_H;
+  img->width = width, img->height = height;
   img->align = 4;
-  img->widthStep = B200_CARD_W;
-  img->imageSize = B200_CARD_W * B200_CARD_H;
+  img->widthStep = (width + 3) & ~3;  // cvCreateImage aligns rows to 4 bytes
+  img->imageSize = img->widthStep * height;
   img->imageData = img->imageDataOrigin = (char *)malloc((size_t)img->imageSize);
   memcpy(img->colorModel, "GRAY", 4);
   memcpy(img->channelSeq, "GRAY", 4);
   return img;
 }
+
+IplImage *create_card_image() { return create_gray_image(B200_CARD_W, B200_CARD_H); }
 
 float tree_sum(const float *v, int start, int len) {  // Eigen unrolled redux, Core/Redux.h:96-118
   if (len == 1) return v[start];
@@ -131,6 +133,25 @@ bool dmz_detect_edges(IplImage *y, IplImage *cb, IplImage *cr, FrameOrientation 
   memcpy(found_edges, &e, sizeof(e));  // identical layouts (include/b200_dmz.h)
   if (all) memcpy(corner_points, &c, sizeof(c));
   return all != 0;
+}
+
+// dmz_deinterleave_uint8_c2 (dmz.h:64, dmz.cpp:49-56): always allocates both channel images; the caller frees them.
+void dmz_deinterleave_uint8_c2(IplImage *interleaved, IplImage **channel1, IplImage **channel2) {
+  PlaneView v = view_of(interleaved);  // width in pixels; two bytes per pixel
+  if (interleaved->roi) v.data += interleaved->roi->xOffset;  // view_of offsets by xOffset bytes; pixels are 2 bytes wide
+  *channel1 = create_gray_image(v.w, v.h);
+  *channel2 = create_gray_image(v.w, v.h);
+  b200_ctx *ctx = default_ctx();
+  if (!ctx) return;
+  const size_t plane = (size_t)v.w * v.h;
+  uint8_t *tmp = (uint8_t *)malloc(2 * plane);
+  if (b200_deinterleave_c2_batch(ctx, v.data, v.step, (size_t)v.step * v.h, v.w, v.h, 1, B200_MEM_HOST, tmp, tmp + plane) == B200_OK) {
+    for (int r = 0; r < v.h; r++) {
+      memcpy((*channel1)->imageData + (size_t)r * (*channel1)->widthStep, tmp + (size_t)r * v.w, (size_t)v.w);
+      memcpy((*channel2)->imageData + (size_t)r * (*channel2)->widthStep, tmp + plane + (size_t)r * v.w, (size_t)v.w);
+    }
+  }
+  free(tmp);
 }
 
 // dmz_focus_score / dmz_brightness_score (dmz.h:77-80, dmz.cpp:183-195).  The scoring rectangle is derived from

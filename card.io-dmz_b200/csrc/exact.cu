@@ -836,6 +836,55 @@ int launch_frame_scores(const uint8_t *frames, int row_stride, size_t frame_stri
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
+// ------------------------------------------------------------------------------------------------
+// dmz_deinterleave_uint8_c2 (dmz.cpp:49-56 -> llcv_split_u8, cv/convert.cpp:74-76 = cvSplit): the CbCr plane of a
+// biplanar camera frame into two dense planes.  Pure streaming: 16 interleaved bytes in, 8 + 8 bytes out per thread
+// step when everything is 16-byte aligned, a byte loop otherwise.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+deinterleave_c2_kernel(const uint8_t *__restrict__ src, int row_stride, size_t frame_stride, int w, int h, size_t n,
+                       uint8_t *__restrict__ ch1, uint8_t *__restrict__ ch2, int vec_ok) {
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (size_t)gridDim.x * blockDim.x;
+  if (vec_ok) {  // w % 8 == 0, all bases and strides 16-byte (src) / 8-byte (dst) aligned
+    const int wv = w >> 3;
+    const size_t total = n * (size_t)h * wv;
+    for (size_t i = tid; i < total; i += nthreads) {
+      const size_t f = i / ((size_t)h * wv);
+      const int rem = (int)(i - f * ((size_t)h * wv)), y = rem / wv, xv = rem - y * wv;
+      const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(src + f * frame_stride + (size_t)y * row_stride) + xv);
+      uint2 a, b;  // even bytes -> channel 1, odd bytes -> channel 2
+      a.x = __byte_perm(v.x, v.y, 0x6420), a.y = __byte_perm(v.z, v.w, 0x6420);
+      b.x = __byte_perm(v.x, v.y, 0x7531), b.y = __byte_perm(v.z, v.w, 0x7531);
+      const size_t o = (f * h + y) * (size_t)w + (size_t)xv * 8;
+      __stcs(reinterpret_cast<uint2 *>(ch1 + o), a);
+      __stcs(reinterpret_cast<uint2 *>(ch2 + o), b);
+    }
+  } else {
+    const size_t total = n * (size_t)h * w;
+    for (size_t i = tid; i < total; i += nthreads) {
+      const size_t f = i / ((size_t)h * w);
+      const int rem = (int)(i - f * ((size_t)h * w)), y = rem / w, x = rem - y * w;
+      const uint8_t *p = src + f * frame_stride + (size_t)y * row_stride + 2 * x;
+      ch1[i] = p[0], ch2[i] = p[1];
+    }
+  }
+}
+
+int launch_deinterleave_c2(const uint8_t *src, int row_stride, size_t frame_stride, int w, int h, int n, uint8_t *ch1, uint8_t *ch2,
+                           cudaStream_t s) {
+  const bool vec_ok = (w % 8 == 0) && (row_stride % 16 == 0) && (frame_stride % 16 == 0) && ((uintptr_t)src % 16 == 0) &&
+                      ((uintptr_t)ch1 % 8 == 0) && ((uintptr_t)ch2 % 8 == 0);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const size_t items = (size_t)n * h * (vec_ok ? w / 8 : w);
+  size_t blocks = (items + 255) / 256;
+  if (blocks > (size_t)sms * 16) blocks = (size_t)sms * 16;  // grid-stride: 16 CTAs x 256 threads per SM
+  if (blocks < 1) blocks = 1;
+  deinterleave_c2_kernel<<<(unsigned)blocks, 256, 0, s>>>(src, row_stride, frame_stride, w, h, (size_t)n, ch1, ch2, vec_ok ? 1 : 0);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
 int launch_finalize_records(const FrameGeom *geom, const b200_scan *scans, const unsigned int *card_check, int n,
                             b200_frame_record *recs, cudaStream_t s, uint8_t *needs_full, int cx0, int cy0, int cx1, int cy1) {
   finalize_records_kernel<<<blocks_for(n, 128), 128, 0, s>>>(geom, scans, card_check, n, recs, needs_full, cx0, cy0, cx1, cy1);

@@ -172,6 +172,12 @@ int b200_digit_models_batch(b200_ctx *ctx, const float *patches, int n, int mem,
 /* applym_befe75da on prepared rows: in = n x 204 f32, out = n x 3 f32 */
 int b200_vseg_model_batch(b200_ctx *ctx, const float *rows, int n, int mem, float *out);
 
+/* ---- chroma de-interleave ----
+ * dmz_deinterleave_uint8_c2 (dmz.h:61, dmz.cpp:49-56): n interleaved CbCr planes (width x height pixels, two bytes per
+ * pixel, row_stride >= 2 * width bytes) into two dense width x height planes each (channel1 = even bytes). */
+int b200_deinterleave_c2_batch(b200_ctx *ctx, const uint8_t *interleaved, int row_stride, size_t frame_stride, int width, int height,
+                               int n, int mem, uint8_t *channel1, uint8_t *channel2);
+
 /* ---- frame scoring ----
  * dmz_focus_score / dmz_brightness_score (dmz.h:77-80, dmz.cpp:114-195) for n luma planes: focus = stddev of
  * |sobel3 dx.dy| and brightness = mean, both over the reference's scoring rectangle (the centred card-sized rectangle,

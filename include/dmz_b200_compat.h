@@ -173,6 +173,7 @@ bool dmz_detect_edges(IplImage *y_sample, IplImage *cb_sample, IplImage *cr_samp
                       dmz_edges *found_edges, dmz_corner_points *corner_points);
 void dmz_transform_card(dmz_context *dmz, IplImage *sample, dmz_corner_points corner_points, FrameOrientation orientation,
                         bool upsample, IplImage **transformed);
+void dmz_deinterleave_uint8_c2(IplImage *interleaved, IplImage **channel1, IplImage **channel2); /* dmz.h:64 */
 float dmz_focus_score(IplImage *image, bool use_full_image);      /* dmz.h:77 */
 float dmz_brightness_score(IplImage *image, bool use_full_image); /* dmz.h:80 */
 void scanner_initialize(ScannerState *state);

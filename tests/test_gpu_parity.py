@@ -208,6 +208,15 @@ def test_categorize_patches(dmz, oracle, golden):
         assert np.abs(ens[i] - e).max() <= TOL and np.abs(mods[i] - m).max() <= TOL, i
 
 
+def test_deinterleave_c2(dmz):
+    """dmz_deinterleave_uint8_c2 (dmz.cpp:49-56 = cvSplit): vector path (aligned, w % 8 == 0) and the byte path."""
+    rng = np.random.default_rng(2)
+    for (n, h, w) in [(3, 240, 320), (2, 7, 13), (1, 1, 1), (5, 360, 640)]:
+        planes = rng.integers(0, 256, (n, h, w, 2), dtype=np.uint8)
+        c1, c2 = dmz.deinterleave_c2(planes)
+        assert np.array_equal(c1, planes[..., 0]) and np.array_equal(c2, planes[..., 1]), (n, h, w)
+
+
 def test_frame_scores_exact(dmz, oracle, golden, deck):
     """dmz_focus_score / dmz_brightness_score: float bits equal to the oracle and to the reference
     build's golden outputs, at 640x480 and at frame sizes that scale / clip the scoring rectangle."""
