@@ -69,7 +69,10 @@ def _p(a):
 
 
 def lib_path(kind):
-    return os.path.join(HERE, "liboracle.so") if kind == "port" else os.path.join(HERE, "_ref", "libdmz_ref.so")
+    """port: the plain-C restatement; ref: the reference's sources (SCAN_EXPIRY=0, re-entrant); refx: the same sources with
+    SCAN_EXPIRY=1 (adds the expiry taps; function statics make it single-threaded)."""
+    return {"port": os.path.join(HERE, "liboracle.so"), "ref": os.path.join(HERE, "_ref", "libdmz_ref.so"),
+            "refx": os.path.join(HERE, "_ref", "libdmz_ref_expiry.so")}[kind]
 
 
 def available(kind):
@@ -80,7 +83,7 @@ class Oracle:
     """Uniform front-end over either checker library."""
 
     def __init__(self, kind="port"):
-        assert kind in ("port", "ref")
+        assert kind in ("port", "ref", "refx")
         self.kind = kind
         self.prefix = "orc_" if kind == "port" else "ref_"
         self.lib = C.CDLL(lib_path(kind))
@@ -119,9 +122,15 @@ class Oracle:
         f("luhn", [vp, i], i)
         f("card_type", [vp, i], i)
         f("bench_frames", [vp, i, i, i, vp, vp, i, i, vp], C.c_double)
-        if kind == "ref":
+        if kind in ("ref", "refx"):
             self.lib.ref_run_kats.restype = i
             self.lib.ref_sizeof.argtypes = [i]
+            if kind == "refx":
+                self.lib.ref_expiry_patch_prep.argtypes = [vp, i, i, i, i, i, vp]
+                self.lib.ref_expiry_digit_model.argtypes = [vp, vp]
+                self.lib.ref_slash_model.argtypes = [vp, vp]
+                self.lib.ref_scharr3_dx_abs.argtypes = [vp, i, i, i, vp]
+                self.lib.ref_best_expiry_seg.argtypes = [vp, i, vp, i, vp]
         else:
             self.lib.orc_expiry_patch_prep.argtypes = [vp, i, vp]
             self.lib.orc_expiry_digit_model.argtypes = [vp, vp, vp, vp, vp]
@@ -256,12 +265,18 @@ class Oracle:
         img = np.ascontiguousarray(img16x11, np.uint8)
         assert img.shape == (16, 11)
         out = np.zeros((16, 11), np.float32)
-        self.lib.orc_expiry_patch_prep(_p(img), 11, _p(out))
+        if self.kind == "refx":  # prepare_image_for_cat with the patch as the whole image, rect at (0, 0)
+            self.lib.ref_expiry_patch_prep(_p(img), 11, 11, 16, 0, 0, _p(out))
+        else:
+            self.lib.orc_expiry_patch_prep(_p(img), 11, _p(out))
         return out
 
     def expiry_digit_model(self, x, taps=False):
         x = np.ascontiguousarray(x, np.float32).reshape(176)
         out = np.zeros(10, np.float32)
+        if self.kind == "refx":
+            self.lib.ref_expiry_digit_model(_p(x), _p(out))
+            return out
         l1, l2, hid = np.zeros(3500, np.float32), np.zeros(120, np.float32), np.zeros(176, np.float32)
         self.lib.orc_expiry_digit_model(_p(x), _p(out), _p(l1), _p(l2), _p(hid))
         return (out, l1, l2, hid) if taps else out

@@ -286,6 +286,31 @@ CV_IMPL void cvConvertScale(const CvArr *srcarr, CvArr *dstarr, double scale, do
 
 CV_IMPL void cvNormalize(const CvArr *srcarr, CvArr *dstarr, double a, double b, int norm_type, const CvArr *mask) {
   View s = view_of(srcarr), d = view_of(dstarr);
+  if (!mask && norm_type == CV_C && s.depth == CV_16S && d.depth == CV_16S && s.cn == 1 && s.w == d.w && s.h == d.h) {
+    /* cv::normalize(NORM_INF): scale = a / max|v| (0 when max|v| <= DBL_EPSILON), then convertTo(16S -> 16S, scale):
+     * cvtScale_<short, short, float> -- float multiply, cvRound, saturate (core/convert.cpp, 2.4.x).
+     * (scan/expiry_seg.cpp:277 call site) */
+    double nrm = 0;
+    for (int y = 0; y < s.h; y++) {
+      const short *sp = (const short *)(s.p + (size_t)y * s.step);
+      for (int x = 0; x < s.w; x++) {
+        double v = sp[x] < 0 ? -(double)sp[x] : (double)sp[x];
+        if (v > nrm) nrm = v;
+      }
+    }
+    double scale = nrm > DBL_EPSILON ? a / nrm : 0.;
+    float fs = (float)scale;
+    for (int y = 0; y < s.h; y++) {
+      const short *sp = (const short *)(s.p + (size_t)y * s.step);
+      short *dp = (short *)(d.p + (size_t)y * d.step);
+      for (int x = 0; x < s.w; x++) {
+        volatile float p = (float)sp[x] * fs;
+        int r = orc_cv_round((double)p);
+        dp[x] = (short)(r < -32768 ? -32768 : (r > 32767 ? 32767 : r));
+      }
+    }
+    return;
+  }
   if (mask || norm_type != CV_MINMAX || s.depth != CV_32F || d.depth != CV_32F || s.cn != 1 || a != 0.0 || b != 1.0)
     SHIM_FAIL("only f32 MINMAX [0,1]");
   if (s.p != d.p) {
@@ -313,7 +338,51 @@ CV_IMPL void cvSplit(const CvArr *srcarr, CvArr *d0, CvArr *d1, CvArr *d2, CvArr
   }
 }
 
+CV_IMPL void cvCopy(const CvArr *srcarr, CvArr *dstarr, const CvArr *mask) {
+  View s = view_of(srcarr), d = view_of(dstarr);
+  if (mask || s.depth != d.depth || s.cn != d.cn || s.w != d.w || s.h != d.h) SHIM_FAIL("cvCopy shape");
+  size_t row = (size_t)s.w * s.cn * (s.depth == CV_8U ? 1 : s.depth == CV_16S ? 2 : 4);
+  for (int y = 0; y < s.h; y++) memcpy(d.p + (size_t)y * d.step, s.p + (size_t)y * s.step, row);
+}
+
+CV_IMPL void cvSetZero(CvArr *arr) {
+  View d = view_of(arr);
+  size_t row = (size_t)d.w * d.cn * (d.depth == CV_8U ? 1 : d.depth == CV_16S ? 2 : 4);
+  for (int y = 0; y < d.h; y++) memset(d.p + (size_t)y * d.step, 0, row);
+}
+
 /* ---------------------------------------------------------------- imgproc */
+
+CV_IMPL void cvSmooth(const CvArr *srcarr, CvArr *dstarr, int smoothtype, int size1, int size2, double sigma1, double sigma2) {
+  View s = view_of(srcarr), d = view_of(dstarr);
+  if (smoothtype != CV_BILATERAL || size1 != size2 || s.depth != CV_8U || d.depth != CV_8U || s.cn != 1 || s.w != d.w || s.h != d.h)
+    SHIM_FAIL("only 8-bit single-channel CV_BILATERAL");
+  /* cvSmooth(CV_BILATERAL): cv::bilateralFilter(src, dst, d = size1, sigmaColor = sigma1, sigmaSpace = sigma2, BORDER_REPLICATE) */
+  orc_bilateral_u8(s.p, s.step, s.w, s.h, d.p, d.step, size1, sigma1, sigma2);
+}
+
+CV_IMPL double cvThreshold(const CvArr *srcarr, CvArr *dstarr, double threshold, double max_value, int threshold_type) {
+  View s = view_of(srcarr), d = view_of(dstarr);
+  if (threshold_type != CV_THRESH_TOZERO || s.depth != d.depth || s.cn != 1 || s.w != d.w || s.h != d.h) SHIM_FAIL("only TOZERO");
+  for (int y = 0; y < s.h; y++) {
+    const uchar *sr = s.p + (size_t)y * s.step;
+    uchar *dr = d.p + (size_t)y * d.step;
+    for (int x = 0; x < s.w; x++) {
+      if (s.depth == CV_16S) {  /* cv::threshold on 16S: integer threshold cvFloor(thresh) */
+        short v = ((const short *)sr)[x];
+        ((short *)dr)[x] = v > (short)orc_cv_floor(threshold) ? v : 0;
+      } else if (s.depth == CV_32F) {
+        float v = ((const float *)sr)[x];
+        ((float *)dr)[x] = v > (float)threshold ? v : 0.f;
+      } else {
+        uchar v = sr[x];
+        dr[x] = v > (uchar)orc_cv_floor(threshold) ? v : 0;
+      }
+    }
+  }
+  return threshold;
+}
+
 
 CV_IMPL void cvSobel(const CvArr *srcarr, CvArr *dstarr, int dx, int dy, int aperture_size) {
   View s = view_of(srcarr), d = view_of(dstarr);

@@ -19,11 +19,13 @@
 
 #include "oracle_types.h"
 
+#if !SCAN_EXPIRY
 /* CYTHON_DMZ declares these (dmz.h:103-120) but with SCAN_EXPIRY=0 nothing defines them. */
 void expiry_extract_group(IplImage *, GroupedRects &, Eigen::Matrix<float, 11, 10, 1, 11, 10> &, int *, int *) { abort(); }
 /* declared static in scan/expiry_seg.h:12 and referenced by the Cython-only dmz_best_expiry_seg */
 static void best_expiry_seg(IplImage *, uint16_t, GroupedRectsList &, GroupedRectsList &) { abort(); }
 static void expiry_extract(IplImage *, GroupedRectsList &, GroupedRectsList &, int *, int *) { abort(); }
+#endif
 
 namespace {
 
@@ -438,5 +440,67 @@ double ref_bench_frames(const uint8_t *frames, int n, int w, int h, const uint8_
   free(jobs);
   return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
 }
+
+#if SCAN_EXPIRY
+/* ---- expiry taps: only in the SCAN_EXPIRY=1 build (oracle/_ref/libdmz_ref_expiry.so) -------------------------- */
+
+/* prepare_image_for_cat (scan/expiry_categorize.cpp:37-73): the 16x11 character crop at (left, top) of a u8 image */
+void ref_expiry_patch_prep(const uint8_t *img, int step, int w, int h, int left, int top, float *out176) {
+  Hdr a;
+  wrap(&a, img, w, h, step, IPL_DEPTH_8U);
+  IplImage *as_float = cvCreateImage(cvSize(kTrimmedCharacterImageWidth, kTrimmedCharacterImageHeight), IPL_DEPTH_32F, 1);
+  CharacterRectList rects;
+  rects.push_back(CharacterRect(top, left, 0));
+  prepare_image_for_cat(&a.img, as_float, rects.begin());
+  for (int r = 0; r < 16; r++) memcpy(out176 + r * 11, as_float->imageData + (size_t)r * as_float->widthStep, 11 * sizeof(float));
+  cvReleaseImage(&as_float);
+}
+
+/* digit_probabilities (scan/expiry_categorize.cpp:77-108) = applyc_bf4dd6c8 on a prepared 16x11 float image */
+void ref_expiry_digit_model(const float *x176, float *out10) {
+  IplImage *as_float = cvCreateImage(cvSize(kTrimmedCharacterImageWidth, kTrimmedCharacterImageHeight), IPL_DEPTH_32F, 1);
+  for (int r = 0; r < 16; r++) memcpy(as_float->imageData + (size_t)r * as_float->widthStep, x176 + r * 11, 11 * sizeof(float));
+  DigitProbabilities *p = digit_probabilities(as_float);
+  for (int i = 0; i < 10; i++) out10[i] = p[0](0, i);
+  cvReleaseImage(&as_float);
+}
+
+/* slash_probabilities (scan/expiry_seg.cpp:41-46) = applym_730c4cbd */
+void ref_slash_model(const float *x176, float *out2) {
+  IplImage *as_float = cvCreateImage(cvSize(kTrimmedCharacterImageWidth, kTrimmedCharacterImageHeight), IPL_DEPTH_32F, 1);
+  for (int r = 0; r < 16; r++) memcpy(as_float->imageData + (size_t)r * as_float->widthStep, x176 + r * 11, 11 * sizeof(float));
+  SlashProbabilities p = slash_probabilities(as_float);
+  out2[0] = p(0, 0), out2[1] = p(0, 1);
+  cvReleaseImage(&as_float);
+}
+
+/* llcv_scharr3_dx_abs (cv/sobel.cpp:700-826) */
+void ref_scharr3_dx_abs(const uint8_t *img, int step, int w, int h, int16_t *out) {
+  Hdr a, d;
+  wrap(&a, img, w, h, step, IPL_DEPTH_8U);
+  wrap(&d, out, w, h, w * (int)sizeof(int16_t), IPL_DEPTH_16S);
+  llcv_scharr3_dx_abs(&a.img, &d.img);
+}
+
+/* best_expiry_seg (scan/expiry_seg.cpp:706-903) on a 428x270 card.  Groups are flattened into int32 records:
+ * {top, left, width, height, character_width, pattern, n_rects, (rect.top, rect.left) x n_rects}.  Returns the number
+ * of expiry groups (or -1 if `cap` ints were not enough); *n_ints = ints written. */
+int ref_best_expiry_seg(const uint8_t *card, int y_offset, int32_t *out, int cap, int *n_ints) {
+  Hdr a;
+  wrap(&a, card, kCreditCardTargetWidth, kCreditCardTargetHeight, kCreditCardTargetWidth, IPL_DEPTH_8U);
+  GroupedRectsList expiry_groups, name_groups;
+  best_expiry_seg(&a.img, (uint16_t)y_offset, expiry_groups, name_groups);
+  int k = 0;
+  for (size_t g = 0; g < expiry_groups.size(); g++) {
+    const GroupedRects &G = expiry_groups[g];
+    if (k + 7 + 2 * (int)G.character_rects.size() > cap) return -1;
+    out[k++] = G.top, out[k++] = G.left, out[k++] = G.width, out[k++] = G.height, out[k++] = G.character_width;
+    out[k++] = (int)G.pattern, out[k++] = (int)G.character_rects.size();
+    for (size_t r = 0; r < G.character_rects.size(); r++) out[k++] = G.character_rects[r].top, out[k++] = G.character_rects[r].left;
+  }
+  *n_ints = k;
+  return (int)expiry_groups.size();
+}
+#endif
 
 }  // extern "C"

@@ -36,6 +36,15 @@ def ref():
 
 
 @pytest.fixture(scope="session")
+def refx():
+    """The reference's sources built with SCAN_EXPIRY=1 (oracle/_ref/libdmz_ref_expiry.so): the expiry taps."""
+    from oracle.binding import Oracle, available
+    if not available("refx"):
+        pytest.skip("oracle/_ref/libdmz_ref_expiry.so not built (no /root/reference on this machine)")
+    return Oracle("refx")
+
+
+@pytest.fixture(scope="session")
 def golden():
     return np.load(os.path.join(HERE, "golden", "ref_golden.npz"))
 

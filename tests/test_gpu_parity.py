@@ -240,13 +240,17 @@ def test_frame_scores_exact(dmz, oracle, golden, deck):
     assert f.min() > 5.0  # the synthetic deck is in focus by the reference's own measure
 
 
-def test_expiry_digit_known_answer_and_parity(dmz, oracle):
+def test_expiry_digit_known_answer_and_parity(dmz, oracle, golden):
     """E0: prepare_image_for_cat + applyc_bf4dd6c8 (scan/expiry_categorize.cpp:37-109).  The
     reference's embedded KAT at its own 1e-5; random / structured character crops against the oracle at 1e-4."""
     meta = json.load(open(os.path.join(G, "kat_modelc_bf4dd6c8.json")))
     data = np.fromfile(os.path.join(G, "kat_modelc_bf4dd6c8.bin"), "<f4")
     k = {v["label"]: data[v["offset"]:v["offset"] + v["count"]] for v in meta["vectors"]}
     assert np.abs(dmz.expiry_digit_models(k["test input"])[0] - k["test output"]).max() <= 1e-5
+    got = dmz.expiry_digits(golden["expiry_patches"])  # outputs of the reference's own SCAN_EXPIRY=1 build
+    assert np.abs(got - golden["expiry_probs"]).max() <= TOL
+    got = dmz.expiry_digit_models(golden["expiry_prep_bits"].view(np.float32).reshape(-1, 176))
+    assert np.abs(got - golden["expiry_probs"]).max() <= TOL
     rng = np.random.default_rng(21)
     n = 203  # not a multiple of the 4 digits a CTA takes per iteration
     patches = rng.integers(0, 256, (n, 16, 11)).astype(np.uint8)

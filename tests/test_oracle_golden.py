@@ -40,6 +40,14 @@ def test_kat_expiry_cnn(oracle):
     assert np.abs(out - k["test output"]).max() <= tol
 
 
+def test_expiry_digit_golden(oracle, golden):
+    """E0 against outputs of the reference's own prepare_image_for_cat / applyc_bf4dd6c8 (SCAN_EXPIRY=1 build)."""
+    for i, patch in enumerate(golden["expiry_patches"]):
+        prep = oracle.expiry_patch_prep(patch)
+        assert np.array_equal(prep.view(np.uint32), golden["expiry_prep_bits"][i]), i
+        assert np.abs(oracle.expiry_digit_model(prep) - golden["expiry_probs"][i]).max() <= 1e-5, i
+
+
 def test_frame_scores(oracle, golden):
     """dmz_focus_score / dmz_brightness_score (dmz.cpp:114-195) against the reference build's outputs, bit for bit."""
     frames = np.concatenate([deck_frames(int(i), 1) for i in golden["deck_idx"]])

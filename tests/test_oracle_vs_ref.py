@@ -75,3 +75,19 @@ def test_chroma_fallback(ref, oracle):
     assert dr.all_found == do.all_found
     if dr.all_found:
         assert np.array_equal(np.array(dr.corners, np.float32).view(np.uint32), np.array(do.corners, np.float32).view(np.uint32))
+
+
+def test_expiry_digit_against_reference_build(refx, oracle):
+    """E0: prepare_image_for_cat + applyc_bf4dd6c8 of the SCAN_EXPIRY=1 reference build vs the restatement: the
+    prepared patch bit for bit, the probabilities within 1e-5."""
+    assert refx.lib.ref_run_kats() == 0b1111
+    rng = np.random.default_rng(1)
+    for t in range(200):
+        patch = rng.integers(0, 256, (16, 11), dtype=np.uint8)
+        if t % 3 == 1:
+            patch = (patch // 32 * 9).astype(np.uint8)
+        if t % 3 == 2 and t % 2:
+            patch[:] = rng.integers(0, 256)
+        a, b = refx.expiry_patch_prep(patch), oracle.expiry_patch_prep(patch)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), t
+        assert np.abs(refx.expiry_digit_model(a) - oracle.expiry_digit_model(b)).max() <= 1e-5, t

@@ -98,6 +98,18 @@ for (w, h) in [(1280, 720), (320, 240), (641, 479)]:
     out["score_%dx%d" % (w, h)] = np.array([[R.focus_score(img, full), R.brightness_score(img, full)] for full in (0, 1)], np.float32).view(np.uint32)
     out["score_rect_%dx%d" % (w, h)] = np.stack([R.scoring_rect(w, h, full) for full in (0, 1)])
 
+# ---- E0 (expiry digit): prepare_image_for_cat + applyc_bf4dd6c8 of the SCAN_EXPIRY=1 build on seeded character crops
+RX = Oracle("refx")
+erng = np.random.default_rng(77)
+ep = erng.integers(0, 256, (48, 16, 11), dtype=np.uint8)
+ep[16:32] = (ep[16:32] // 32) * 9
+ep[32] = 0
+ep[33] = 255
+eprep = np.stack([RX.expiry_patch_prep(p) for p in ep])
+out["expiry_patches"] = ep
+out["expiry_prep_bits"] = eprep.view(np.uint32)
+out["expiry_probs"] = np.stack([RX.expiry_digit_model(p) for p in eprep])
+
 path = os.path.join(ROOT, "tests", "golden", "ref_golden.npz")
 np.savez_compressed(path, **out)
 print("wrote", path, os.path.getsize(path), "bytes; session complete flags", out["session_complete"], "digits", out["session_digits"])
