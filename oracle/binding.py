@@ -281,6 +281,22 @@ class Oracle:
         self.lib.orc_expiry_digit_model(_p(x), _p(out), _p(l1), _p(l2), _p(hid))
         return (out, l1, l2, hid) if taps else out
 
+    def best_expiry_seg(self, card, y_offset):
+        """refx only: best_expiry_seg (scan/expiry_seg.cpp:706-903).  Returns an (n_groups, 17) int32 array:
+        top, left, width, height, character_width, pattern, n_rects, then (rect.top, rect.left) x 5."""
+        card = np.ascontiguousarray(card, np.uint8)
+        out = np.zeros(8192, np.int32)
+        n = C.c_int(0)
+        k = self.lib.ref_best_expiry_seg(_p(card), int(y_offset), _p(out), out.size, C.byref(n))
+        assert k >= 0
+        return out[:n.value].reshape(k, 17).copy()
+
+    def scharr3_dx_abs(self, img):
+        img = np.ascontiguousarray(img, np.uint8)
+        out = np.zeros(img.shape, np.int16)
+        self.lib.ref_scharr3_dx_abs(_p(img), img.shape[1], img.shape[1], img.shape[0], _p(out))
+        return out
+
     def scan_card_image(self, card):
         card = np.ascontiguousarray(card, np.uint8)
         out = Scan()

@@ -82,3 +82,54 @@ def synthetic_strip(rng, w, h, vertical, kind="edge"):
         d = (yy - h / 2 - rng.uniform(-h / 4, h / 4)) * np.cos(ang) + (xx - w / 2) * np.sin(ang)
     img = np.where(d > 0, 175 + rng.normal(0, 6, (h, w)), img)
     return np.clip(img, 0, 255).astype(np.uint8)
+
+
+# ---- synthetic expiry text (SURVEY 8f rank 4 tests): seven-segment digits and a two-pixel slash stamped on a warped card.
+# Plain numpy so the same cards can be rebuilt wherever the tests run; the reference's segmentation does find MM/YY groups
+# on them (about 40 % of the random layouts below), which is all the parity tests need.
+_SEGMENTS = {0: "abcdef", 1: "bc", 2: "abged", 3: "abgcd", 4: "fgbc", 5: "afgcd", 6: "afgedc", 7: "abc", 8: "abcdefg", 9: "abfgcd"}
+
+
+def expiry_glyph(ch, w=9, h=15, t=2):
+    g = np.zeros((h, w), np.uint8)
+    if ch == " ":
+        return g
+    if ch == "/":
+        for y in range(h):
+            x = int(round((w - 2) * (1 - y / (h - 1))))
+            g[y, max(0, x):x + 2] = 1
+        return g
+    s, m = _SEGMENTS[int(ch)], h // 2
+    if "a" in s: g[0:t, :] = 1
+    if "g" in s: g[m - t // 2:m - t // 2 + t, :] = 1
+    if "d" in s: g[h - t:h, :] = 1
+    if "f" in s: g[0:m + 1, 0:t] = 1
+    if "b" in s: g[0:m + 1, w - t:w] = 1
+    if "e" in s: g[m:h, 0:t] = 1
+    if "c" in s: g[m:h, w - t:w] = 1
+    return g
+
+
+def expiry_card(base_card, y_offset0, seed):
+    """A 428x270 card with 1-3 lines of digits / MM/YY text below the number row; returns (card, y_offset)."""
+    rng = np.random.default_rng(seed)
+    c = base_card.copy()
+    if seed % 4 == 3:
+        c = np.clip(c.astype(np.int32) + rng.integers(-12, 13, c.shape), 0, 255).astype(np.uint8)
+    yo = y_offset0 + int(rng.integers(-20, 10))
+    for _ in range(int(rng.integers(1, 4))):
+        txt = "".join(rng.choice(list("0123456789"), int(rng.integers(0, 6)))) + " " * int(rng.integers(0, 2))
+        txt += "%02d/%02d" % (rng.integers(1, 13), rng.integers(15, 40)) + " " * int(rng.integers(0, 2))
+        txt += "".join(rng.choice(list("0123456789 "), int(rng.integers(0, 8))))
+        x, y = int(rng.integers(5, 250)), yo + 27 + int(rng.integers(3, 70))
+        if y + 16 > 270:
+            continue
+        w, h, t = [(9, 15, 2), (8, 14, 2), (9, 15, 3), (7, 13, 2)][int(rng.integers(0, 4))]
+        pitch, fg = int(rng.integers(11, 14)), int(rng.choice([30, 60, 240, 255]))
+        for i, ch in enumerate(txt):
+            xs = x + i * pitch
+            if xs + w > 428:
+                break
+            reg = c[y:y + h, xs:xs + w]
+            reg[expiry_glyph(ch, w, h, t) > 0] = fg
+    return np.ascontiguousarray(c), yo

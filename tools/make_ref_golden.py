@@ -110,6 +110,23 @@ out["expiry_patches"] = ep
 out["expiry_prep_bits"] = eprep.view(np.uint32)
 out["expiry_probs"] = np.stack([RX.expiry_digit_model(p) for p in eprep])
 
+# ---- best_expiry_seg of the SCAN_EXPIRY=1 build on synthetic expiry cards (tests/util.expiry_card)
+from util import expiry_card
+yo0 = int(recs["v_y_offset"][0])
+seg_seeds = np.arange(1000, 1160)
+seg_out, seg_counts = [], []
+for sd in seg_seeds:
+    c, yo = expiry_card(cards[0], yo0, int(sd))
+    gr = RX.best_expiry_seg(c, yo)
+    seg_counts.append(len(gr))
+    seg_out.append(gr)
+out["expiry_seg_seeds"] = seg_seeds
+out["expiry_seg_counts"] = np.array(seg_counts, np.int32)
+out["expiry_seg_groups"] = np.concatenate(seg_out).astype(np.int32) if sum(seg_counts) else np.zeros((0, 17), np.int32)
+c, yo = expiry_card(cards[0], yo0, 1001)
+sch = RX.scharr3_dx_abs(c[yo + 27:])
+out["expiry_scharr_check"] = np.uint64((sch.astype(np.uint64).ravel() * np.arange(1, sch.size + 1, dtype=np.uint64)).sum())
+
 path = os.path.join(ROOT, "tests", "golden", "ref_golden.npz")
 np.savez_compressed(path, **out)
 print("wrote", path, os.path.getsize(path), "bytes; session complete flags", out["session_complete"], "digits", out["session_digits"])
