@@ -105,6 +105,7 @@ def _load():
     lib.b200_categorize_patches_batch.argtypes = [vp, vp, i, i, vp]
     lib.b200_vseg_model_batch.argtypes = [vp, vp, i, i, vp]
     lib.b200_digit_models_batch.argtypes = [vp, vp, i, i, vp]
+    lib.b200_best_expiry_seg_batch.argtypes = [vp, vp, vp, i, i, vp, i, vp, vp, vp]
     lib.b200_deinterleave_c2_batch.argtypes = [vp, vp, i, C.c_size_t, i, i, i, i, vp, vp]
     lib.b200_frame_scores_batch.argtypes = [vp, vp, i, C.c_size_t, i, i, i, i, i, vp, vp]
     lib.b200_expiry_digits_batch.argtypes = [vp, vp, i, i, vp]
@@ -123,6 +124,10 @@ def _load():
     lib.b200_scanner_peek.argtypes = [vp, vp, vp, vp]
     _lib = lib
     return lib
+
+
+EXPIRY_GROUP_DTYPE = np.dtype([("top", "<i4"), ("left", "<i4"), ("width", "<i4"), ("height", "<i4"), ("character_width", "<i4"),
+                               ("pattern", "<i4"), ("n_rects", "<i4"), ("rect_top", "<i4", 5), ("rect_left", "<i4", 5)])
 
 
 def _ptr(a):
@@ -246,6 +251,19 @@ class Dmz:
         out = np.zeros((n, 40), np.float32)
         self._check(self.lib.b200_digit_models_batch(self.ctx, _ptr(patches), n, MEM_HOST, _ptr(out)))
         return out[:, :10].copy(), out[:, 10:].reshape(n, 3, 10).copy()
+
+    def best_expiry_seg(self, cards, y_offsets, max_groups=16, want_sobel=False):
+        """cards: (n, 270, 428) u8; y_offsets: n.  Returns (groups[n, max_groups] EXPIRY_GROUP_DTYPE, counts[n], dropped[n]) and
+        the |Scharr| planes if asked (best_expiry_seg, scan/expiry_seg.cpp:706-903)."""
+        cards = np.ascontiguousarray(cards, np.uint8)
+        n = cards.shape[0]
+        yo = np.ascontiguousarray(y_offsets, np.uint16)
+        groups = np.zeros((n, max_groups), EXPIRY_GROUP_DTYPE)
+        counts, dropped = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        sob = np.zeros((n, 270, 428), np.int16) if want_sobel else None
+        self._check(self.lib.b200_best_expiry_seg_batch(self.ctx, _ptr(cards), _ptr(yo), n, MEM_HOST, _ptr(groups), max_groups,
+                                                        _ptr(counts), _ptr(dropped), _ptr(sob) if want_sobel else None))
+        return (groups, counts, dropped, sob) if want_sobel else (groups, counts, dropped)
 
     def deinterleave_c2(self, planes):
         """planes: (n, h, w, 2) u8 interleaved CbCr.  Returns (channel1, channel2), each (n, h, w) (dmz_deinterleave_uint8_c2)."""

@@ -34,11 +34,12 @@ def build(force=False):
     nvcc = os.environ.get("NVCC", "nvcc")
     obj_dir = os.path.join(HERE, "build")
     os.makedirs(obj_dir, exist_ok=True)
-    hdrs = [os.path.join(CSRC, "b200_internal.h"), os.path.join(ROOT, "include", "b200_dmz.h")]
+    hdrs = [os.path.join(CSRC, "b200_internal.h"), os.path.join(CSRC, "expiry_seg_core.h"), os.path.join(ROOT, "include", "b200_dmz.h")]
     units = [
         # (source, extra flags).  exact.cu / detect.cu: bit-exact float stages -> no FMA contraction.
         ("detect.cu", ["-fmad=false"]),
         ("exact.cu", ["-fmad=false"]),
+        ("expiry_seg.cu", ["-fmad=false"]),
         ("nets.cu", []),
         ("api.cu", ["-fmad=false"]),
         ("b200_tables.cpp", ["-Xcompiler", "-ffp-contract=off"]),

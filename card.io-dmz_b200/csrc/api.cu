@@ -59,6 +59,7 @@ struct b200_ctx {
   float *d_cnn[3] = {nullptr, nullptr, nullptr};
   float *d_hwT = nullptr;
   float *d_expiry = nullptr;  // modelc_bf4dd6c8 blob (optional: E0 entry points need it)
+  float *d_slash = nullptr;   // modelm_730c4cbd blob (optional: b200_best_expiry_seg_batch needs it)
   NetWeights wts{};
 
   // geometry cache
@@ -341,6 +342,10 @@ int b200_ctx_create(b200_ctx **out, int device_ordinal, const char *weights_dir)
       b200_build_bilateral_tables(color, space);
       if (upload_bilateral_tables(color, space) != 0) return fail(ctx, B200_ECUDA, "cudaMemcpyToSymbol (bilateral tables)");
     }
+    if (read_blob(dir + "/modelm_730c4cbd.bin", &eb, 14322)) {
+      CU(cudaMalloc(&ctx->d_slash, eb.size() * sizeof(float)));
+      CU(cudaMemcpy(ctx->d_slash, eb.data(), eb.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
   }
   ctx->wts.vseg = ctx->d_vseg;
   for (int m = 0; m < 3; m++) ctx->wts.cnn[m] = ctx->d_cnn[m];
@@ -359,7 +364,7 @@ void b200_ctx_destroy(b200_ctx *ctx) {
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   cudaFree(ctx->d_misc);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
-  cudaFree(ctx->d_vseg), cudaFree(ctx->d_hwT), cudaFree(ctx->d_expiry);
+  cudaFree(ctx->d_vseg), cudaFree(ctx->d_hwT), cudaFree(ctx->d_expiry), cudaFree(ctx->d_slash);
   for (int m = 0; m < 3; m++) cudaFree(ctx->d_cnn[m]);
   delete ctx;
 }
@@ -749,6 +754,51 @@ int b200_frame_scores_batch(b200_ctx *ctx, const uint8_t *y, int yrs, size_t yfs
   if (brightness) CU(cudaMemcpyAsync(brightness, d_bright, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
   ctx->d2h_bytes += (uint64_t)sizeof(float) * n * ((focus != nullptr) + (brightness != nullptr));
   CU(cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}
+
+// best_expiry_seg over a batch.  The |Scharr| planes are scratch (231 KB per card), so the batch runs in chunks.
+int b200_best_expiry_seg_batch(b200_ctx *ctx, const uint8_t *cards, const uint16_t *y_offsets, int n, int mem,
+                               b200_expiry_group *groups, int max_groups, int32_t *n_groups, int32_t *n_dropped, int16_t *sobel_out) {
+  if (!ctx || !cards || !y_offsets || !groups || !n_groups || n < 1 || max_groups < 1)
+    return fail(ctx, B200_EINVAL, "b200_best_expiry_seg_batch: bad arguments");
+  if (!ctx->d_slash) return fail(ctx, B200_EUNSUPPORTED, "modelm_730c4cbd.bin was not found in the weights directory");
+  CU(cudaSetDevice(ctx->device));
+  const size_t card_bytes = (size_t)B200_CARD_W * B200_CARD_H, sob_bytes = card_bytes * sizeof(int16_t);
+  const int chunk = n < 2048 ? n : 2048;
+  const bool host = mem == B200_MEM_HOST;
+  auto up16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
+  const size_t o_sob = 0, o_ls = o_sob + up16(sob_bytes * chunk), o_cards = o_ls + up16(sizeof(int32_t) * B200_CARD_H * chunk),
+               o_yo = o_cards + up16(host ? card_bytes * chunk : 0), o_grp = o_yo + up16(host ? sizeof(uint16_t) * chunk : 0),
+               o_cnt = o_grp + up16(host ? sizeof(b200_expiry_group) * (size_t)max_groups * chunk : 0),
+               total = o_cnt + up16(host ? 2 * sizeof(int32_t) * chunk : 0);
+  int rc = ensure_misc(ctx, total);
+  if (rc) return rc;
+  uint8_t *base = (uint8_t *)ctx->d_misc;
+  int16_t *d_sob = (int16_t *)(base + o_sob);
+  int32_t *d_ls = (int32_t *)(base + o_ls);
+  for (int f0 = 0; f0 < n; f0 += chunk) {
+    const int cnt = n - f0 < chunk ? n - f0 : chunk;
+    const uint8_t *dc = cards + (size_t)f0 * card_bytes;
+    const uint16_t *dy = y_offsets + f0;
+    b200_expiry_group *dg = groups + (size_t)f0 * max_groups;
+    int32_t *dn = n_groups + f0, *dd = n_dropped ? n_dropped + f0 : nullptr;
+    if (host) {
+      CU(cudaMemcpyAsync(base + o_cards, dc, card_bytes * cnt, cudaMemcpyHostToDevice, ctx->stream));
+      CU(cudaMemcpyAsync(base + o_yo, dy, sizeof(uint16_t) * cnt, cudaMemcpyHostToDevice, ctx->stream));
+      dc = base + o_cards, dy = (const uint16_t *)(base + o_yo), dg = (b200_expiry_group *)(base + o_grp);
+      dn = (int32_t *)(base + o_cnt), dd = dn + chunk;
+    }
+    LAUNCH(launch_expiry_seg(dc, dy, cnt, ctx->d_slash, d_sob, d_ls, dg, max_groups, dn, dd, ctx->stream));
+    if (host) {
+      CU(cudaMemcpyAsync(groups + (size_t)f0 * max_groups, dg, sizeof(b200_expiry_group) * (size_t)max_groups * cnt, cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaMemcpyAsync(n_groups + f0, dn, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, ctx->stream));
+      if (n_dropped) CU(cudaMemcpyAsync(n_dropped + f0, dd, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (sobel_out)
+      CU(cudaMemcpyAsync(sobel_out + (size_t)f0 * card_bytes, d_sob, sob_bytes * cnt, host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));  // the scratch planes are reused by the next chunk
+  }
   return B200_OK;
 }
 

@@ -94,6 +94,8 @@ int launch_categorize_patches(const NetWeights &wts, const uint8_t *patches, con
 int launch_vseg_model(const NetWeights &wts, const float *rows, int n, float *out, cudaStream_t s);
 int upload_conv_constants(const float *cnn_blobs[3]);
 int upload_bilateral_tables(const float *color256, const float *space5);  // E0 prep constants (nets.cu)
+int launch_expiry_seg(const uint8_t *cards, const uint16_t *y_offsets, int n, const float *slash_w, int16_t *sob, int32_t *line_sum,
+                      b200_expiry_group *groups, int max_groups, int32_t *n_groups, int32_t *n_dropped, cudaStream_t s);  // expiry_seg.cu
 int launch_deinterleave_c2(const uint8_t *src, int row_stride, size_t frame_stride, int w, int h, int n, uint8_t *ch1, uint8_t *ch2,
                            cudaStream_t s);
 int launch_frame_scores(const uint8_t *frames, int row_stride, size_t frame_stride, int n, int rx, int ry, int rw, int rh,

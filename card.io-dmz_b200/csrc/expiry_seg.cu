@@ -1,0 +1,73 @@
+// card.io-dmz_b200/csrc/expiry_seg.cu -- best_expiry_seg (scan/expiry_seg.cpp:706-903) for a batch of
+// warped cards.
+//
+//   expiry_scharr_kernel   one CTA per card: llcv_scharr3_dx_abs on the rows below the number (cv/sobel.cpp:706-799)
+//                          -> s16 image in a per-card scratch plane + the 258-column row sums (the cvSum loop of
+//                          expiry_seg.cpp:752-755).  The data-parallel part: 428 x <=243 pixels in, 2 bytes out each.
+//   expiry_groups_kernel   one THREAD per card: stripe selection, character rectangles, grouping, grid fitting,
+//                          trimming and the slash MLP -- the branchy, list-manipulating part -- through the shared
+//                          host/device header expiry_seg_core.h (the same code the CPU unit tests pin on the reference).
+// Compiled with -fmad=false: the few float expressions must round like the reference's (and like the host build of
+// the header).
+#include "b200_internal.h"
+#include "expiry_seg_core.h"
+
+namespace {
+
+constexpr int kScharrThreads = 256;
+
+__global__ void __launch_bounds__(kScharrThreads)
+expiry_scharr_kernel(const uint8_t *__restrict__ cards, const uint16_t *__restrict__ y_offsets, int n, int16_t *__restrict__ sob,
+                     int32_t *__restrict__ line_sum) {
+  const int card_i = blockIdx.x;
+  if (card_i >= n) return;
+  const uint8_t *card = cards + (size_t)card_i * (xseg::kW * xseg::kH);
+  int16_t *out = sob + (size_t)card_i * (xseg::kW * xseg::kH);
+  int32_t *ls = line_sum + (size_t)card_i * xseg::kH;
+  const int y0 = min((int)y_offsets[card_i] + xseg::kNumberHeight, xseg::kH);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // rows the trimming step may touch above the ROI (at most three) are zero, as after the reference's cvSetZero
+  for (int i = threadIdx.x; i < 3 * xseg::kW; i += kScharrThreads) {
+    const int y = y0 - 3 + i / xseg::kW;
+    if (y >= 0) out[y * xseg::kW + (i % xseg::kW)] = 0;
+  }
+  for (int y = y0 + warp; y < xseg::kH; y += kScharrThreads / 32) {  // one warp per row: coalesced loads and stores
+    int s = 0;
+    for (int x = lane; x < xseg::kW; x += 32) {
+      const int v = xseg::scharr_abs_at(card, y0, x, y);
+      out[y * xseg::kW + x] = (int16_t)v;
+      if (x >= 3 * xseg::kSmallW && x < (xseg::kW * 2) / 3) s += v;  // left_edge = 27, right_edge = 285
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) ls[y] = s;
+  }
+}
+
+__global__ void __launch_bounds__(32)
+expiry_groups_kernel(const int16_t *__restrict__ sob, const int32_t *__restrict__ line_sum, const uint16_t *__restrict__ y_offsets,
+                     int n, const float *__restrict__ slash_w, b200_expiry_group *__restrict__ groups, int max_groups,
+                     int32_t *__restrict__ n_groups, int32_t *__restrict__ n_dropped) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int overflow = 0;
+  const int yo = (int)y_offsets[i];
+  int k = 0;
+  if (yo + xseg::kNumberHeight < xseg::kH)
+    k = xseg::best_expiry_groups(sob + (size_t)i * (xseg::kW * xseg::kH), line_sum + (size_t)i * xseg::kH, yo, slash_w,
+                                 reinterpret_cast<xseg::ExpiryGroupOut *>(groups + (size_t)i * max_groups), max_groups, &overflow);
+  n_groups[i] = k;
+  if (n_dropped) n_dropped[i] = overflow;
+}
+
+}  // namespace
+
+static_assert(sizeof(b200_expiry_group) == sizeof(xseg::ExpiryGroupOut), "b200_expiry_group mirrors xseg::ExpiryGroupOut");
+
+int launch_expiry_seg(const uint8_t *cards, const uint16_t *y_offsets, int n, const float *slash_w, int16_t *sob, int32_t *line_sum,
+                      b200_expiry_group *groups, int max_groups, int32_t *n_groups, int32_t *n_dropped, cudaStream_t s) {
+  expiry_scharr_kernel<<<n, kScharrThreads, 0, s>>>(cards, y_offsets, n, sob, line_sum);
+  if (cudaGetLastError() != cudaSuccess) return -1;
+  expiry_groups_kernel<<<(n + 31) / 32, 32, 0, s>>>(sob, line_sum, y_offsets, n, slash_w, groups, max_groups, n_groups, n_dropped);
+  return cudaGetLastError() == cudaSuccess ? 2 : -1;
+}

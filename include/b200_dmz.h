@@ -192,6 +192,23 @@ int b200_frame_scores_batch(b200_ctx *ctx, const uint8_t *y, int y_row_stride, s
 int b200_expiry_digits_batch(b200_ctx *ctx, const uint8_t *patches, int n, int mem, float *out);
 int b200_expiry_digit_models_batch(b200_ctx *ctx, const float *prepared, int n, int mem, float *out);
 
+/* ---- expiry segmentation ----
+ * best_expiry_seg (scan/expiry_seg.h:12, scan/expiry_seg.cpp:706-903; dmz_best_expiry_seg dmz.h:111 is its Cython
+ * wrapper): for each warped 428x270 card and the number row's y offset (NVerticalSegmentation.y_offset), the MM/YY
+ * candidates below the number -- five character rectangles each, the middle one accepted by the slash classifier.
+ * One record mirrors the reference's GroupedRects fields that survive the call. */
+typedef struct b200_expiry_group {
+  int32_t top, left, width, height, character_width;
+  int32_t pattern;   /* ExpiryPattern, always ExpiryPatternMMsYY (0) here: expiry_types.h:36-45 */
+  int32_t n_rects;   /* always 5 */
+  int32_t rect_top[5], rect_left[5];
+} b200_expiry_group;
+/* groups: n x max_groups records, n_groups: n counts (groups beyond max_groups are dropped and counted in n_dropped,
+ * which may be NULL).  sobel_out (may be NULL): n x 270 x 428 int16, the |Scharr-dx| image the search ran on (rows
+ * above y_offset + 24 are not written).  All pointers live where `mem` says. */
+int b200_best_expiry_seg_batch(b200_ctx *ctx, const uint8_t *cards, const uint16_t *y_offsets, int n, int mem,
+                               b200_expiry_group *groups, int max_groups, int32_t *n_groups, int32_t *n_dropped, int16_t *sobel_out);
+
 /* ---- scanner session (scan/scan.h:50-72): host-side aggregation, no GPU work ---- */
 typedef struct b200_scanner b200_scanner;
 b200_scanner *b200_scanner_new(void);

@@ -275,6 +275,45 @@ def test_expiry_digit_known_answer_and_parity(dmz, oracle, golden):
     assert got.argmax(1).tolist() == [int(oracle.expiry_digit_model(prepared[i]).argmax()) for i in range(37)]
 
 
+def test_best_expiry_seg(dmz, golden):
+    """best_expiry_seg on synthetic expiry cards -- groups identical to the golden outputs of the
+    reference's SCAN_EXPIRY=1 build (and to that build itself when oracle/_ref travelled here); the |Scharr| plane
+    against the golden checksum."""
+    from util import expiry_card
+    base, yo0 = golden["deck_card0"], int(golden["deck_records"]["v_y_offset"][0])
+    seeds = [int(s) for s in golden["expiry_seg_seeds"]]
+    made = [expiry_card(base, yo0, sd) for sd in seeds]
+    cards, yos = np.stack([m[0] for m in made]), np.array([m[1] for m in made], np.uint16)
+    groups, counts, dropped, sob = dmz.best_expiry_seg(cards, yos, max_groups=16, want_sobel=True)
+    assert not dropped.any() and np.array_equal(counts, golden["expiry_seg_counts"])
+    flat = lambda g: np.concatenate([[g["top"], g["left"], g["width"], g["height"], g["character_width"], g["pattern"], g["n_rects"]],
+                                     np.stack([g["rect_top"], g["rect_left"]], 1).ravel()]).astype(np.int32)
+    got = [flat(groups[i, k]) for i in range(len(seeds)) for k in range(counts[i])]
+    assert np.array_equal(np.array(got, np.int32).reshape(-1, 17), golden["expiry_seg_groups"])
+    i = seeds.index(1001)
+    part = sob[i, int(yos[i]) + 27:].astype(np.uint64).ravel()
+    assert np.uint64((part * np.arange(1, part.size + 1, dtype=np.uint64)).sum()) == golden["expiry_scharr_check"]
+    # max_groups smaller than what a card yields: the surplus is counted, not written past the end
+    many = int(np.argmax(counts))
+    if counts[many] > 1:
+        g1, c1, d1 = dmz.best_expiry_seg(cards[many:many + 1], yos[many:many + 1], max_groups=1)
+        assert c1[0] == 1 and d1[0] == counts[many] - 1 and flat(g1[0, 0]).tolist() == flat(groups[many, 0]).tolist()
+    # live against the reference build on a larger, fresh sample (ragged vs the 2048-card chunking is covered by n = 2500)
+    from oracle.binding import Oracle, available
+    if available("refx"):
+        rx = Oracle("refx")
+        made = [expiry_card(base, yo0, sd) for sd in range(20000, 22500)]
+        cards, yos = np.stack([m[0] for m in made]), np.array([m[1] for m in made], np.uint16)
+        groups, counts, dropped = dmz.best_expiry_seg(cards, yos, max_groups=16)
+        bad = 0
+        for j in range(0, len(made), 5):
+            want = rx.best_expiry_seg(cards[j], int(yos[j]))
+            gotj = np.array([flat(groups[j, k]) for k in range(counts[j])], np.int32).reshape(-1, 17)
+            bad += not (gotj.shape == want.shape and np.array_equal(gotj, want))
+        assert bad == 0
+        assert (counts > 0).sum() > 500
+
+
 def test_whole_path_records(dmz, deck, orecs):
     rec, ocards = orecs
     got, cards = dmz.process_frames(deck, want_cards=True)
