@@ -154,6 +154,39 @@ void dmz_deinterleave_uint8_c2(IplImage *interleaved, IplImage **channel1, IplIm
   free(tmp);
 }
 
+// dmz_best_expiry_seg (dmz.h:111, dmz.cpp:605-620): malloc'ed array of groups, each with a malloc'ed rectangle list; the
+// caller frees both.  scores / seen counts are not produced by segmentation (the reference copies uninitialised
+// values there); they are zero here.
+void dmz_best_expiry_seg(IplImage *card_y, uint16_t starting_y_offset, CythonGroupedRects **expiry_groups, uint16_t *number_of_groups) {
+  *expiry_groups = NULL;
+  *number_of_groups = 0;
+  b200_ctx *ctx = default_ctx();
+  if (!ctx || !card_y) return;
+  PlaneView v = view_of(card_y);
+  if (v.w != B200_CARD_W || v.h != B200_CARD_H) return;
+  uint8_t *dense = (uint8_t *)malloc((size_t)B200_CARD_W * B200_CARD_H);
+  for (int r = 0; r < B200_CARD_H; r++) memcpy(dense + (size_t)r * B200_CARD_W, v.data + (size_t)r * v.step, B200_CARD_W);
+  const int max_groups = 64;
+  b200_expiry_group *g = (b200_expiry_group *)calloc(max_groups, sizeof(b200_expiry_group));
+  int32_t count = 0;
+  int rc = b200_best_expiry_seg_batch(ctx, dense, &starting_y_offset, 1, B200_MEM_HOST, g, max_groups, &count, nullptr, nullptr);
+  free(dense);
+  if (rc == B200_OK && count > 0) {
+    CythonGroupedRects *out = (CythonGroupedRects *)calloc((size_t)count, sizeof(CythonGroupedRects));
+    for (int i = 0; i < count; i++) {
+      out[i].top = g[i].top, out[i].left = g[i].left, out[i].width = g[i].width, out[i].height = g[i].height;
+      out[i].character_width = g[i].character_width;
+      out[i].pattern = (uint8_t)g[i].pattern;
+      out[i].number_of_character_rects = g[i].n_rects;
+      out[i].character_rects = (CythonCharacterRect *)malloc(sizeof(CythonCharacterRect) * (size_t)g[i].n_rects);
+      for (int k = 0; k < g[i].n_rects; k++) out[i].character_rects[k].top = g[i].rect_top[k], out[i].character_rects[k].left = g[i].rect_left[k];
+    }
+    *expiry_groups = out;
+    *number_of_groups = (uint16_t)count;
+  }
+  free(g);
+}
+
 // dmz_focus_score / dmz_brightness_score (dmz.h:77-80, dmz.cpp:183-195).  The scoring rectangle is derived from
 // cvGetSize(image) and applied in whole-image coordinates, as the reference's cvSetImageROI does.  (The reference also
 // drops any ROI the caller had set; this layer leaves the caller's IplImage untouched.)

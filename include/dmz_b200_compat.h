@@ -175,6 +175,23 @@ void dmz_transform_card(dmz_context *dmz, IplImage *sample, dmz_corner_points co
                         bool upsample, IplImage **transformed);
 void dmz_deinterleave_uint8_c2(IplImage *interleaved, IplImage **channel1, IplImage **channel2); /* dmz.h:64 */
 float dmz_focus_score(IplImage *image, bool use_full_image);      /* dmz.h:77 */
+/* dmz.h:103-120 (the CYTHON_DMZ-only block): the expiry segmentation entry point of cython_dmz/dmz.pyx.  Layout of
+ * CythonGroupedRects as in scan/expiry_types.h:95-118. */
+typedef struct {
+  int top;
+  int left;
+} CythonCharacterRect;
+typedef float CythonGroupScores[11][10];
+typedef struct {
+  int top, left, width, height, character_width;
+  uint8_t pattern;
+  CythonGroupScores scores;
+  int recently_seen_count, total_seen_count;
+  int number_of_character_rects;
+  CythonCharacterRect *character_rects;
+} CythonGroupedRects;
+static_assert(sizeof(CythonGroupedRects) == 488, "CythonGroupedRects layout");
+void dmz_best_expiry_seg(IplImage *card_y, uint16_t starting_y_offset, CythonGroupedRects **expiry_groups, uint16_t *number_of_groups);
 float dmz_brightness_score(IplImage *image, bool use_full_image); /* dmz.h:80 */
 void scanner_initialize(ScannerState *state);
 void scanner_reset(ScannerState *state);

@@ -22,7 +22,7 @@ REFERENCE_SYMBOLS = [
     "_Z17scanner_add_frameP12ScannerStateP9_IplImageP15FrameScanResult",
     "_Z29scanner_add_frame_with_expiryP12ScannerStateP9_IplImagebP15FrameScanResult",
     "_Z14scanner_resultP12ScannerStateP13ScannerResult", "_Z15scanner_destroyP12ScannerState",
-    "_Z25dmz_deinterleave_uint8_c2P9_IplImagePS0_S1_", "_Z15dmz_focus_scoreP9_IplImageb", "_Z20dmz_brightness_scoreP9_IplImageb",
+    "_Z25dmz_deinterleave_uint8_c2P9_IplImagePS0_S1_", "_Z19dmz_best_expiry_segP9_IplImagetPP18CythonGroupedRectsPt", "_Z15dmz_focus_scoreP9_IplImageb", "_Z20dmz_brightness_scoreP9_IplImageb",
 ]
 
 
