@@ -6,7 +6,8 @@ import os
 import numpy as np
 
 __all__ = ["Dmz", "Scanner", "B200Error", "lib_path", "Edges", "CornerPoints", "VSeg", "HSeg", "Scan", "Line",
-           "FrameRecord", "RECORD_DTYPE", "SCAN_DTYPE", "LINE_DTYPE", "MEM_HOST", "MEM_DEVICE", "CARD_W", "CARD_H"]
+           "FrameRecord", "RECORD_DTYPE", "SCAN_DTYPE", "LINE_DTYPE", "EXPIRY_GROUP_DTYPE", "expiry_month_year_from_scores",
+           "MEM_HOST", "MEM_DEVICE", "CARD_W", "CARD_H"]
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 MEM_HOST, MEM_DEVICE = 0, 1
@@ -109,6 +110,11 @@ def _load():
     lib.b200_deinterleave_c2_batch.argtypes = [vp, vp, i, C.c_size_t, i, i, i, i, vp, vp]
     lib.b200_frame_scores_batch.argtypes = [vp, vp, i, C.c_size_t, i, i, i, i, i, vp, vp]
     lib.b200_expiry_digits_batch.argtypes = [vp, vp, i, i, vp]
+    lib.b200_expiry_digits_at_batch.argtypes = [vp, vp, i, vp, i, i, vp]
+    lib.b200_scanner_add_expiry.argtypes = [vp, vp, vp, i, i, i, i]
+    lib.b200_scanner_expiry.argtypes = [vp, vp, vp]
+    lib.b200_expiry_month_year_from_scores.argtypes = [vp, i, i, i, i, vp, vp]
+    lib.b200_scanner_expiry_peek.argtypes = [vp, vp, vp, i]
     lib.b200_expiry_digit_models_batch.argtypes = [vp, vp, i, i, vp]
     lib.b200_set_profiling.argtypes = [vp, i]
     lib.b200_set_crop_margin.argtypes = [vp, i]
@@ -289,6 +295,14 @@ class Dmz:
         self._check(self.lib.b200_expiry_digits_batch(self.ctx, _ptr(patches), patches.shape[0], MEM_HOST, _ptr(out)))
         return out
 
+    def expiry_digits_at(self, cards, where):
+        """cards: (n, 270, 428) u8; where: (m, 3) int32 rows of (card index, top, left).  Returns (m, 10) probabilities."""
+        cards = np.ascontiguousarray(cards, np.uint8)
+        where = np.ascontiguousarray(where, np.int32).reshape(-1, 3)
+        out = np.zeros((where.shape[0], 10), np.float32)
+        self._check(self.lib.b200_expiry_digits_at_batch(self.ctx, _ptr(cards), cards.shape[0], _ptr(where), where.shape[0], MEM_HOST, _ptr(out)))
+        return out
+
     def expiry_digit_models(self, prepared):
         prepared = np.ascontiguousarray(prepared, np.float32).reshape(-1, 176)
         out = np.zeros((prepared.shape[0], 10), np.float32)
@@ -338,6 +352,15 @@ class Dmz:
                                                        MEM_HOST, C.c_void_p(h_records), None))
 
 
+def expiry_month_year_from_scores(scores5x10, current_year, current_month, allow_past_dates=False, month=0, year=0):
+    """get_stable_expiry_month_and_year (expiry_categorize.cpp:398-441); returns (month, year)."""
+    lib = _load()
+    sc = np.ascontiguousarray(scores5x10, np.float32).reshape(5, 10)
+    m, y = C.c_int32(month), C.c_int32(year)
+    lib.b200_expiry_month_year_from_scores(_ptr(sc), 5, int(current_year), int(current_month), int(allow_past_dates), C.byref(m), C.byref(y))
+    return m.value, y.value
+
+
 class Scanner:
     """scanner_* session (scan/scan.h:50-72) over b200_scan records."""
 
@@ -366,6 +389,23 @@ class Scanner:
         cnt = np.zeros(2, np.int32)
         self.lib.b200_scanner_peek(self.s, _ptr(a15), _ptr(a16), _ptr(cnt))
         return a15, a16, cnt
+
+    def add_expiry(self, groups, scores, current_year, current_month, allow_past_dates=False):
+        """groups: EXPIRY_GROUP_DTYPE array of one frame; scores: (len(groups), 4, 10) digit probabilities."""
+        groups = np.ascontiguousarray(groups, EXPIRY_GROUP_DTYPE)
+        scores = np.ascontiguousarray(scores, np.float32)
+        self.lib.b200_scanner_add_expiry(self.s, _ptr(groups), _ptr(scores), len(groups), int(current_year), int(current_month),
+                                         int(allow_past_dates))
+
+    def expiry(self):
+        m, y = C.c_int32(), C.c_int32()
+        self.lib.b200_scanner_expiry(self.s, C.byref(m), C.byref(y))
+        return m.value, y.value
+
+    def expiry_peek(self, cap=64):
+        meta, scores = np.zeros((cap, 4), np.int32), np.zeros((cap, 4, 10), np.float32)
+        n = self.lib.b200_scanner_expiry_peek(self.s, _ptr(meta), _ptr(scores), cap)
+        return meta[:n].copy(), scores[:n].copy()
 
     def result(self):
         digits = np.zeros(16, np.uint8)

@@ -828,6 +828,33 @@ static int expiry_call(b200_ctx *ctx, const uint8_t *patches, const float *prepa
   return B200_OK;
 }
 
+// categorize_expiry_digits' inner step for many characters at once: crop m 16x11 windows out of n_cards warped cards.
+int b200_expiry_digits_at_batch(b200_ctx *ctx, const uint8_t *cards, int n_cards, const int32_t *where, int m, int mem, float *out) {
+  if (!ctx || !cards || !where || !out || n_cards < 1 || m < 1) return fail(ctx, B200_EINVAL, "b200_expiry_digits_at_batch: bad arguments");
+  if (!ctx->d_expiry) return fail(ctx, B200_EUNSUPPORTED, "modelc_bf4dd6c8.bin was not found in the weights directory");
+  CU(cudaSetDevice(ctx->device));
+  const uint8_t *dc = cards;
+  const int32_t *dw = where;
+  float *dout = out;
+  if (mem == B200_MEM_HOST) {
+    for (int i = 0; i < m; i++)
+      if (where[3 * i] < 0 || where[3 * i] >= n_cards) return fail(ctx, B200_EINVAL, "b200_expiry_digits_at_batch: card index out of range");
+    const size_t card_bytes = (size_t)B200_CARD_W * B200_CARD_H;
+    auto up16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
+    const size_t o_out = 0, o_where = up16(sizeof(float) * 10 * (size_t)m), o_cards = o_where + up16(sizeof(int32_t) * 3 * (size_t)m);
+    int rc = ensure_misc(ctx, o_cards + card_bytes * n_cards);
+    if (rc) return rc;
+    uint8_t *base = (uint8_t *)ctx->d_misc;
+    CU(cudaMemcpyAsync(base + o_cards, cards, card_bytes * n_cards, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(base + o_where, where, sizeof(int32_t) * 3 * (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
+    dc = base + o_cards, dw = (const int32_t *)(base + o_where), dout = (float *)(base + o_out);
+  }
+  LAUNCH(launch_expiry_digits(ctx->d_expiry, dc, nullptr, m, dout, ctx->stream, dw));
+  if (mem == B200_MEM_HOST) CU(cudaMemcpyAsync(out, dout, sizeof(float) * 10 * (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}
+
 int b200_expiry_digits_batch(b200_ctx *ctx, const uint8_t *patches, int n, int mem, float *out) {
   return expiry_call(ctx, patches, nullptr, n, mem, out);
 }

@@ -101,7 +101,8 @@ int launch_deinterleave_c2(const uint8_t *src, int row_stride, size_t frame_stri
 int launch_frame_scores(const uint8_t *frames, int row_stride, size_t frame_stride, int n, int rx, int ry, int rw, int rh,
                         float *focus, float *brightness, cudaStream_t s);
 void b200_scoring_rect(int w, int h, int use_full_image, int rect[4]);  // b200_tables.cpp
-int launch_expiry_digits(const float *weights, const uint8_t *patches, const float *prepared, int n, float *out, cudaStream_t s);
+int launch_expiry_digits(const float *weights, const uint8_t *patches, const float *prepared, int n, float *out, cudaStream_t s,
+                         const int32_t *where = nullptr);
 void b200_build_bilateral_tables(float *color256, float *space5);  // b200_tables.cpp  // __constant__ conv kernels / biases (nets.cu)
 
 size_t detect_smem_bytes(const DetectParams &p);

@@ -12,6 +12,8 @@
 
 #include "b200_dmz.h"
 #include "dmz_b200_compat.h"
+#include "expiry_session.h"
+#include <time.h>
 
 namespace {
 
@@ -75,10 +77,6 @@ IplImage *create_gray_image(int width, int height) {
 
 IplImage *create_card_image() { return create_gray_image(B200_CARD_W, B200_CARD_H); }
 
-float tree_sum(const float *v, int start, int len) {  // Eigen unrolled redux, Core/Redux.h:96-118
-  if (len == 1) return v[start];
-  return tree_sum(v, start, len / 2) + tree_sum(v, start + len / 2, len - len / 2);
-}
 
 bool luhn(const uint8_t *d, int n) {
   int even = 0, sum = 0;
@@ -249,37 +247,138 @@ void scanner_add_frame(ScannerState *state, IplImage *y, FrameScanResult *result
   scanner_add_frame_with_expiry(state, y, false, result);
 }
 
-void scanner_add_frame_with_expiry(ScannerState *state, IplImage *y, bool, FrameScanResult *result) {
-  // scan_card_image (frame.cpp:24-81) on the GPU; expiry scanning is outside this build's scope
+// The reference accepts expired cards only in its DMZ_DEBUG / CYTHON_DMZ builds (expiry_categorize.cpp:378-395); SDK
+// builds do not.  Default: SDK behaviour.
+static int g_allow_past_expiry = 0;
+void b200_compat_set_allow_past_expiry(int allow) { g_allow_past_expiry = allow; }
+
+namespace {
+
+// scan_card_image's expiry step + expiry_extract (frame.cpp:72-80, expiry_categorize.cpp:448-497) for one card:
+// segmentation and digit categorization on the GPU, cross-frame aggregation in the caller's ScannerState.
+void expiry_step(b200_ctx *ctx, ScannerState *state, const uint8_t *card, FrameScanResult *result, bool usable) {
+  result->expiry_groups.clear();
+  result->name_groups.clear();
+  const int max_groups = 32;
+  b200_expiry_group g[max_groups];
+  int32_t count = 0;
+  uint16_t yo = result->vseg.y_offset;
+  if (yo < B200_CARD_H - 2 * 15) {  // kCreditCardTargetHeight - 2 * kSmallCharacterHeight, frame.cpp:73
+    if (b200_best_expiry_seg_batch(ctx, card, &yo, 1, B200_MEM_HOST, g, max_groups, &count, nullptr, nullptr) != B200_OK) count = 0;
+    if (count > max_groups) count = max_groups;
+  }
+  for (int i = 0; i < count; i++) {
+    GroupedRects gr;
+    gr.top = g[i].top, gr.left = g[i].left, gr.width = g[i].width, gr.height = g[i].height;
+    gr.grouped_yet = false, gr.sum = 0, gr.character_width = g[i].character_width, gr.pattern = g[i].pattern;
+    gr.recently_seen_count = gr.total_seen_count = 0;
+    memset(gr.scores, 0, sizeof(gr.scores));
+    for (int k = 0; k < g[i].n_rects; k++) {
+      CharacterRect cr;
+      cr.top = g[i].rect_top[k], cr.left = g[i].rect_left[k], cr.sum = 0;
+      gr.character_rects.push_back(cr);
+    }
+    result->expiry_groups.push_back(gr);
+  }
+  if (!usable) return;  // scan.cpp:57-59: unusable frames never reach expiry_extract
+  state->scan_expiry = true;
+  state->name_groups = result->name_groups;
+  if (count == 0) return;  // expiry_extract: nothing new, nothing to do
+  // categorize characters 0, 1, 3, 4 of every group (categorize_expiry_digits)
+  int32_t where[max_groups * 4 * 3];
+  float probs[max_groups * 4 * 10];
+  const int chars[4] = {0, 1, 3, 4};
+  for (int i = 0; i < count; i++)
+    for (int c = 0; c < 4; c++) {
+      int32_t *w = where + (i * 4 + c) * 3;
+      w[0] = 0, w[1] = g[i].rect_top[chars[c]], w[2] = g[i].rect_left[chars[c]];
+    }
+  if (b200_expiry_digits_at_batch(ctx, card, 1, where, count * 4, B200_MEM_HOST, probs) != B200_OK) return;
+  ExpiryAgg fresh[kMaxExpiryAgg], agg[kMaxExpiryAgg];
+  int n_fresh = 0, n_agg = 0;
+  for (int i = 0; i < count && n_fresh < kMaxExpiryAgg; i++) {
+    ExpiryAgg &f = fresh[n_fresh++];
+    f.top = g[i].top, f.left = g[i].left, f.n_rects = g[i].n_rects, f.recently_seen = f.total_seen = 0, f.tag = -(i + 1);
+    memset(f.scores, 0, sizeof(f.scores));
+    for (int c = 0; c < 4; c++) memcpy(f.scores[chars[c]], probs + (i * 4 + c) * 10, sizeof(float) * 10);
+  }
+  for (size_t o = 0; o < state->expiry_groups.size() && n_agg < kMaxExpiryAgg; o++) {
+    const GroupedRects &G = state->expiry_groups[o];
+    ExpiryAgg &a = agg[n_agg++];
+    a.top = G.top, a.left = G.left, a.n_rects = (int)G.character_rects.size();
+    a.recently_seen = G.recently_seen_count, a.total_seen = G.total_seen_count, a.tag = (int)o;
+    memcpy(a.scores, G.scores, sizeof(a.scores));  // rows 0..4 of the 11 x 10 row-major matrix
+  }
+  expiry_aggregate(agg, &n_agg, fresh, n_fresh);
+  GroupedRectsList next;
+  for (int k = 0; k < n_agg; k++) {
+    GroupedRects G = agg[k].tag >= 0 ? state->expiry_groups[(size_t)agg[k].tag] : result->expiry_groups[(size_t)(-agg[k].tag - 1)];
+    G.top = agg[k].top, G.left = agg[k].left;
+    G.recently_seen_count = agg[k].recently_seen, G.total_seen_count = agg[k].total_seen;
+    memcpy(G.scores, agg[k].scores, sizeof(agg[k].scores));
+    next.push_back(G);
+  }
+  // what the reference leaves in result->expiry_groups: the new groups that matched nothing (now also in the aggregate)
+  GroupedRectsList unmatched;
+  for (int k = 0; k < n_agg; k++)
+    if (agg[k].tag < 0) {
+      GroupedRects G = result->expiry_groups[(size_t)(-agg[k].tag - 1)];
+      memcpy(G.scores, agg[k].scores, sizeof(agg[k].scores));
+      unmatched.push_back(G);
+    }
+  state->expiry_groups.swap(next);
+  result->expiry_groups.swap(unmatched);
+  time_t now = time(NULL);
+  struct tm tmv;
+  localtime_r(&now, &tmv);
+  for (size_t o = 0; o < state->expiry_groups.size(); o++) {
+    const GroupedRects &G = state->expiry_groups[o];
+    if (G.total_seen_count < 3) continue;
+    stable_month_year(reinterpret_cast<const float(*)[10]>(G.scores), (int)G.character_rects.size(), tmv.tm_year + 1900, tmv.tm_mon + 1,
+                      g_allow_past_expiry != 0, &state->expiry_month, &state->expiry_year);
+  }
+}
+
+}  // namespace
+
+void scanner_add_frame_with_expiry(ScannerState *state, IplImage *y, bool scan_expiry, FrameScanResult *result) {
+  // scan_card_image (frame.cpp:24-81) on the GPU, then scan.cpp:41-86
   result->upside_down = false;
   result->usable = false;
   b200_ctx *ctx = default_ctx();
   if (!ctx || !y || y->width != B200_CARD_W || y->height != B200_CARD_H) return;
   const bool need_number = state->timeOfCardNumberCompletionInMilliseconds == 0;
+  const bool need_expiry = scan_expiry && (state->expiry_month == 0 || state->expiry_year == 0);
   b200_scan s;
   int rc;
-  if (y->widthStep == B200_CARD_W) {
-    rc = b200_scan_cards_batch(ctx, (const uint8_t *)y->imageData, 1, nullptr, B200_MEM_HOST, &s);
-  } else {
-    uint8_t *tmp = (uint8_t *)malloc((size_t)B200_CARD_W * B200_CARD_H);
+  uint8_t *tmp = nullptr;
+  const uint8_t *card = (const uint8_t *)y->imageData;
+  if (y->widthStep != B200_CARD_W) {
+    tmp = (uint8_t *)malloc((size_t)B200_CARD_W * B200_CARD_H);
     for (int r = 0; r < B200_CARD_H; r++) memcpy(tmp + (size_t)r * B200_CARD_W, y->imageData + (size_t)r * y->widthStep, B200_CARD_W);
-    rc = b200_scan_cards_batch(ctx, tmp, 1, nullptr, B200_MEM_HOST, &s);
-    free(tmp);
+    card = tmp;
   }
-  if (rc != B200_OK) return;
-  memcpy(&result->vseg, &s.vseg, sizeof(s.vseg));
-  result->upside_down = s.upside_down;
-  if (s.upside_down) return;
-  if (!need_number) {  // collect_card_number == false: only the vseg gate applies (frame.cpp:43-49)
-    result->usable = s.vseg.score > 15;
+  rc = b200_scan_cards_batch(ctx, card, 1, nullptr, B200_MEM_HOST, &s);
+  if (rc != B200_OK) {
+    free(tmp);
     return;
   }
-  result->usable = s.usable;
-  if (s.vseg.score > 15) {
+  memcpy(&result->vseg, &s.vseg, sizeof(s.vseg));
+  result->upside_down = s.upside_down;
+  if (s.upside_down || !(s.vseg.score > 15)) {  // frame.cpp:38-49: no expiry work on flipped / unusable-vseg frames
+    free(tmp);
+    return;
+  }
+  if (need_number) {
+    result->usable = s.usable;
     memcpy(&result->hseg, &s.hseg, sizeof(s.hseg));
     memcpy(result->scores.v, s.scores, sizeof(s.scores));
+  } else {
+    result->usable = true;  // collect_card_number == false: only the vseg gate applies
   }
-  if (!result->usable) return;
+  if (need_expiry) expiry_step(ctx, state, card, result, result->usable);
+  free(tmp);
+  if (!result->usable || !need_number) return;
   state->mostRecentUsableHSeg = result->hseg;
   state->mostRecentUsableVSeg = result->vseg;
   NumberScores *agg = nullptr;
@@ -290,7 +389,7 @@ void scanner_add_frame_with_expiry(ScannerState *state, IplImage *y, bool, Frame
   for (int i = 0; i < 160; i++) agg->v[i] += result->scores.v[i] * (1 - 0.8f);
 }
 
-void scanner_result(ScannerState *state, ScannerResult *result) {  // scan.cpp:88-194 with SCAN_EXPIRY off
+void scanner_result(ScannerState *state, ScannerResult *result) {  // scan.cpp:88-194
   result->complete = false;
   if (state->timeOfCardNumberCompletionInMilliseconds > 0) {
     *result = state->successfulCardNumberResult;
@@ -324,10 +423,23 @@ void scanner_result(ScannerState *state, ScannerResult *result) {  // scan.cpp:8
       state->successfulCardNumberResult = *result;
     }
   }
+  // once the number is in, allow a little more time for the expiry if it is being collected (scan.cpp:163-193)
   if (state->timeOfCardNumberCompletionInMilliseconds > 0) {
-    result->expiry_month = 0;
-    result->expiry_year = 0;
-    result->complete = true;
+    if (state->scan_expiry) {
+      struct timeval t;
+      gettimeofday(&t, NULL);
+      const long now = (long)((t.tv_sec * 1000) + (t.tv_usec / 1000));
+      if ((state->expiry_month > 0 && state->expiry_year > 0) ||
+          now - (long)state->timeOfCardNumberCompletionInMilliseconds > 1000 /* EXTRA_TIME_FOR_EXPIRY_IN_MICROSECONDS, compared in ms */) {
+        result->expiry_month = state->expiry_month;
+        result->expiry_year = state->expiry_year;
+        result->complete = true;
+      }
+    } else {
+      result->expiry_month = 0;
+      result->expiry_year = 0;
+      result->complete = true;
+    }
   }
 }
 

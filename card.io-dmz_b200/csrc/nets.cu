@@ -477,7 +477,9 @@ struct ExpirySmem {
 
 __global__ void __launch_bounds__(kEThreads, 1)
 expiry_kernel(const float *__restrict__ W /* modelc_bf4dd6c8 blob */, const uint8_t *__restrict__ patches,
-              const float *__restrict__ prepared, int n, float *__restrict__ out) {
+              const float *__restrict__ prepared, int n, float *__restrict__ out, const int32_t *__restrict__ where) {
+  // where != nullptr: `patches` holds whole 428x270 cards and crop i is the 16x11 window at (where[3i+1], where[3i+2]) of
+  // card where[3i] -- prepare_image_for_cat's cvSetImageROI(rect->left, rect->top, 11, 16), expiry_categorize.cpp:41
   extern __shared__ __align__(16) uint8_t es_raw[];
   ExpirySmem &S = *reinterpret_cast<ExpirySmem *>(es_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -500,7 +502,15 @@ expiry_kernel(const float *__restrict__ W /* modelc_bf4dd6c8 blob */, const uint
         uint8_t *raw = S.raw[d], *g8 = S.g8[d];
         unsigned int *hist = S.hist[d];
         for (int i = lane; i < 256; i += 32) hist[i] = 0;
-        for (int i = lane; i < 176; i += 32) raw[(i / 11) * 12 + (i % 11)] = __ldg(patches + idx * 176 + i);
+        if (where != nullptr) {
+          const int ci = where[3 * idx], top = where[3 * idx + 1], left = where[3 * idx + 2];
+          const bool inside = top >= 0 && top + 16 <= B200_CARD_H && left >= 0 && left + 11 <= B200_CARD_W;
+          const uint8_t *card = patches + (size_t)ci * (B200_CARD_W * B200_CARD_H);
+          for (int i = lane; i < 176; i += 32)
+            raw[(i / 11) * 12 + (i % 11)] = inside ? __ldg(card + (top + i / 11) * B200_CARD_W + left + (i % 11)) : (uint8_t)0;
+        } else {
+          for (int i = lane; i < 176; i += 32) raw[(i / 11) * 12 + (i % 11)] = __ldg(patches + idx * 176 + i);
+        }
         __syncwarp();
         for (int i = lane; i < 176; i += 32) {  // cvMorphologyEx(GRADIENT, 3x3 cross), replicate at the ROI edge
           const int y = i / 11, x = i - y * 11;
@@ -728,7 +738,8 @@ int upload_bilateral_tables(const float *color256, const float *space5) {
   return 0;
 }
 
-int launch_expiry_digits(const float *weights, const uint8_t *patches, const float *prepared, int n, float *out, cudaStream_t s) {
+int launch_expiry_digits(const float *weights, const uint8_t *patches, const float *prepared, int n, float *out, cudaStream_t s,
+                         const int32_t *where) {
   static bool configured = false;
   if (!configured) {
     if (!ensure_smem(expiry_kernel, sizeof(ExpirySmem))) return -1;
@@ -738,7 +749,7 @@ int launch_expiry_digits(const float *weights, const uint8_t *patches, const flo
   const int groups = (n + kEDigits - 1) / kEDigits;
   if (grid > groups) grid = groups;
   if (grid < 1) grid = 1;
-  expiry_kernel<<<grid, kEThreads, sizeof(ExpirySmem), s>>>(weights, patches, prepared, n, out);
+  expiry_kernel<<<grid, kEThreads, sizeof(ExpirySmem), s>>>(weights, patches, prepared, n, out, where);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

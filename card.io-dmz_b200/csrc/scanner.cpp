@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include "b200_dmz.h"
+#include "expiry_session.h"
 
 struct b200_scanner {
   uint16_t count15, count16;
@@ -13,16 +14,11 @@ struct b200_scanner {
   int complete;
   uint8_t digits[16];
   int n_numbers;
+  int expiry_month, expiry_year, n_expiry;
+  ExpiryAgg expiry[kMaxExpiryAgg];
 };
 
 namespace {
-
-// Eigen's completely unrolled non-vectorised redux: balanced binary tree (Core/Redux.h:96-118); used for
-// aggregated.row(i).sum() on the 1x10 row block.
-float tree_sum(const float *v, int start, int len) {
-  if (len == 1) return v[start];
-  return tree_sum(v, start, len / 2) + tree_sum(v, start + len / 2, len - len / 2);
-}
 
 bool luhn(const uint8_t *d, int n) {
   int even = 0, sum = 0;
@@ -127,6 +123,50 @@ int b200_scanner_result(b200_scanner *s, uint8_t digits[16], int32_t *n_numbers)
     return 1;
   }
   return 0;
+}
+
+void b200_scanner_add_expiry(b200_scanner *s, const b200_expiry_group *groups, const float *scores, int n, int current_year,
+                             int current_month, int allow_past_dates) {
+  if (!s || n <= 0 || !groups || !scores) return;  // expiry_extract returns at once when a frame has no groups
+  // the frame's groups with their freshly categorized digits (categorize_expiry_digits, expiry_categorize.cpp:148-256)
+  ExpiryAgg fresh[kMaxExpiryAgg];
+  int n_fresh = 0;
+  for (int g = 0; g < n && n_fresh < kMaxExpiryAgg; g++) {
+    ExpiryAgg &f = fresh[n_fresh++];
+    f.top = groups[g].top, f.left = groups[g].left, f.n_rects = groups[g].n_rects, f.recently_seen = 0, f.total_seen = 0, f.tag = 0;
+    memset(f.scores, 0, sizeof(f.scores));
+    const int rows[4] = {0, 1, 3, 4};
+    for (int r = 0; r < 4; r++) memcpy(f.scores[rows[r]], scores + ((size_t)g * 4 + r) * 10, sizeof(float) * 10);
+  }
+  expiry_aggregate(s->expiry, &s->n_expiry, fresh, n_fresh);
+  // month / year from groups seen at least three times (get_stable_expiry_month_and_year, expiry_categorize.cpp:398-441)
+  for (int o = 0; o < s->n_expiry; o++) {
+    const ExpiryAgg &g = s->expiry[o];
+    if (g.total_seen < 3) continue;
+    stable_month_year(g.scores, g.n_rects, current_year, current_month, allow_past_dates != 0, &s->expiry_month, &s->expiry_year);
+  }
+}
+
+void b200_expiry_month_year_from_scores(const float *scores, int n_chars, int current_year, int current_month, int allow_past_dates,
+                                        int32_t *month, int32_t *year) {
+  int m = *month, y = *year;
+  stable_month_year(reinterpret_cast<const float(*)[10]>(scores), n_chars, current_year, current_month, allow_past_dates != 0, &m, &y);
+  *month = m, *year = y;
+}
+
+void b200_scanner_expiry(const b200_scanner *s, int32_t *month, int32_t *year) {
+  *month = s->expiry_month, *year = s->expiry_year;
+}
+
+int b200_scanner_expiry_peek(const b200_scanner *s, int32_t *meta, float *scores, int cap) {
+  int n = 0;
+  for (; n < s->n_expiry && n < cap; n++) {
+    const ExpiryAgg &g = s->expiry[n];
+    meta[n * 4 + 0] = g.top, meta[n * 4 + 1] = g.left, meta[n * 4 + 2] = g.recently_seen, meta[n * 4 + 3] = g.total_seen;
+    const int rows[4] = {0, 1, 3, 4};
+    for (int r = 0; r < 4; r++) memcpy(scores + ((size_t)n * 4 + r) * 10, g.scores[rows[r]], sizeof(float) * 10);
+  }
+  return n;
 }
 
 }  // extern "C"

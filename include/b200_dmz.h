@@ -191,6 +191,9 @@ int b200_frame_scores_batch(b200_ctx *ctx, const uint8_t *y, int y_row_stride, s
  * The *_models_ variant takes already prepared 16 x 11 float inputs (the reference's embedded KAT entry). */
 int b200_expiry_digits_batch(b200_ctx *ctx, const uint8_t *patches, int n, int mem, float *out);
 int b200_expiry_digit_models_batch(b200_ctx *ctx, const float *prepared, int n, int mem, float *out);
+/* the same, cropping on the device: where = m x {card index, top, left}; crop i is the 16 x 11 window at (top, left) of
+ * that 428x270 card (the character rectangles b200_best_expiry_seg_batch returns).  out = m x 10. */
+int b200_expiry_digits_at_batch(b200_ctx *ctx, const uint8_t *cards, int n_cards, const int32_t *where, int m, int mem, float *out);
 
 /* ---- expiry segmentation ----
  * best_expiry_seg (scan/expiry_seg.h:12, scan/expiry_seg.cpp:706-903; dmz_best_expiry_seg dmz.h:111 is its Cython
@@ -219,6 +222,20 @@ void b200_scanner_add_scan(b200_scanner *s, const b200_scan *scan);
 /* scanner_result (scan.cpp:88-194): returns complete; digits[16], *n_numbers filled when complete
  * (and, as in the reference, with the current best guess while checks are still failing). */
 int b200_scanner_result(b200_scanner *s, uint8_t digits[16], int32_t *n_numbers);
+/* expiry_extract's session half (scan/expiry_categorize.cpp:258-330, 334-441, 448-497): aggregate one frame's MM/YY
+ * groups -- `scores` = n x 4 x 10 digit probabilities of characters 0, 1, 3, 4 of each group -- with the groups seen on
+ * earlier frames (position tolerance 8 / 5 px, 0.7 decay, three-frame presence), then pick month / year from groups seen
+ * at least three times.  The reference reads the wall clock here; the caller passes the date instead.  allow_past_dates
+ * selects the reference's DMZ_DEBUG / CYTHON_DMZ variant that also accepts expired cards. */
+void b200_scanner_add_expiry(b200_scanner *s, const b200_expiry_group *groups, const float *scores, int n, int current_year,
+                             int current_month, int allow_past_dates);
+void b200_scanner_expiry(const b200_scanner *s, int32_t *month, int32_t *year);
+/* get_stable_expiry_month_and_year (expiry_categorize.cpp:398-441) on its own: scores = n_chars x 10 rows (n_chars = 5,
+ * row 2 is the slash and ignored); month / year are in-out: a date is taken only if it is later than the one passed in. */
+void b200_expiry_month_year_from_scores(const float *scores, int n_chars, int current_year, int current_month, int allow_past_dates,
+                                        int32_t *month, int32_t *year);
+/* aggregated groups: meta = {top, left, recently_seen, total_seen} x count, scores = count x 4 x 10; returns count */
+int b200_scanner_expiry_peek(const b200_scanner *s, int32_t *meta, float *scores, int cap);
 void b200_scanner_peek(const b200_scanner *s, float agg15[160], float agg16[160], int32_t counts[2]);
 
 #ifdef __cplusplus

@@ -199,5 +199,8 @@ void scanner_add_frame(ScannerState *state, IplImage *y, FrameScanResult *result
 void scanner_add_frame_with_expiry(ScannerState *state, IplImage *y, bool scan_expiry, FrameScanResult *result);
 void scanner_result(ScannerState *state, ScannerResult *result);
 void scanner_destroy(ScannerState *state);
+/* Not in the reference: its DMZ_DEBUG / CYTHON_DMZ builds also accept expiry dates in the past
+ * (scan/expiry_categorize.cpp:378-395); 0 (default) = SDK behaviour, 1 = that variant. */
+void b200_compat_set_allow_past_expiry(int allow);
 
 #endif

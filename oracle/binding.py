@@ -131,6 +131,10 @@ class Oracle:
                 self.lib.ref_slash_model.argtypes = [vp, vp]
                 self.lib.ref_scharr3_dx_abs.argtypes = [vp, i, i, i, vp]
                 self.lib.ref_best_expiry_seg.argtypes = [vp, i, vp, i, vp]
+                self.lib.ref_scanner_add_frame_with_expiry.argtypes = [vp, vp, i, vp, vp]
+                self.lib.ref_scanner_expiry_peek.argtypes = [vp, vp, vp, vp, vp, i]
+                self.lib.ref_scanner_result_expiry.argtypes = [vp, vp, vp, vp, vp]
+                self.lib.ref_expiry_month_year.argtypes = [vp, vp, vp]
         else:
             self.lib.orc_expiry_patch_prep.argtypes = [vp, i, vp]
             self.lib.orc_expiry_digit_model.argtypes = [vp, vp, vp, vp, vp]
@@ -290,6 +294,30 @@ class Oracle:
         k = self.lib.ref_best_expiry_seg(_p(card), int(y_offset), _p(out), out.size, C.byref(n))
         assert k >= 0
         return out[:n.value].reshape(k, 17).copy()
+
+    # ---- refx only: the session with its expiry branch live (scan/scan.cpp:41-86, expiry_categorize.cpp:448-497)
+    def scanner_add_frame_with_expiry(self, s, card, scan_expiry=True):
+        card = np.ascontiguousarray(card, np.uint8)
+        out, n = Scan(), C.c_int32(0)
+        self.lib.ref_scanner_add_frame_with_expiry(s, _p(card), int(scan_expiry), C.byref(out), C.byref(n))
+        return out, n.value
+
+    def scanner_expiry_peek(self, s, cap=64):
+        m, y = C.c_int32(0), C.c_int32(0)
+        meta, scores = np.zeros((cap, 4), np.int32), np.zeros((cap, 4, 10), np.float32)
+        n = self.lib.ref_scanner_expiry_peek(s, C.byref(m), C.byref(y), _p(meta), _p(scores), cap)
+        return (m.value, y.value), meta[:n].copy(), scores[:n].copy()
+
+    def scanner_result_expiry(self, s):
+        d, n, m, y = np.zeros(16, np.uint8), C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        done = self.lib.ref_scanner_result_expiry(s, _p(d), C.byref(n), C.byref(m), C.byref(y))
+        return bool(done), d[:n.value].copy(), m.value, y.value
+
+    def expiry_month_year(self, scores5x10, month=0, year=0):
+        sc = np.ascontiguousarray(scores5x10, np.float32).reshape(50)
+        m, y = C.c_int32(month), C.c_int32(year)
+        self.lib.ref_expiry_month_year(_p(sc), C.byref(m), C.byref(y))
+        return m.value, y.value
 
     def scharr3_dx_abs(self, img):
         img = np.ascontiguousarray(img, np.uint8)

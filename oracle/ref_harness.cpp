@@ -501,6 +501,66 @@ int ref_best_expiry_seg(const uint8_t *card, int y_offset, int32_t *out, int cap
   *n_ints = k;
   return (int)expiry_groups.size();
 }
+
+/* scanner_add_frame_with_expiry (scan/scan.cpp:41-86) with the expiry branch live */
+void ref_scanner_add_frame_with_expiry(void *state, const uint8_t *card, int scan_expiry, orc_scan *out, int32_t *n_frame_groups) {
+  Hdr c;
+  wrap(&c, card, 428, 270, 428, IPL_DEPTH_8U);
+  FrameScanResult r;
+  r.scores = NumberScores::Zero();
+  memset(&r.hseg, 0, sizeof(r.hseg));
+  memset(&r.vseg, 0, sizeof(r.vseg));
+  r.flipped = false;
+  r.focus_score = 0;
+  scanner_add_frame_with_expiry((ScannerState *)state, &c.img, scan_expiry != 0, &r);
+  if (out) flatten_scan(r, out);
+  if (n_frame_groups) *n_frame_groups = (int32_t)r.expiry_groups.size();
+}
+
+/* the session's expiry state: month, year, and per aggregated group {top, left, recently_seen, total_seen} + the four
+ * digit rows (characters 0, 1, 3, 4) of its score matrix.  Returns the number of aggregated groups. */
+int ref_scanner_expiry_peek(void *state, int32_t *month, int32_t *year, int32_t *meta, float *scores, int cap) {
+  ScannerState *s = (ScannerState *)state;
+  *month = s->expiry_month, *year = s->expiry_year;
+  int n = 0;
+  for (size_t g = 0; g < s->expiry_groups.size() && n < cap; g++, n++) {
+    const GroupedRects &G = s->expiry_groups[g];
+    meta[n * 4 + 0] = G.top, meta[n * 4 + 1] = G.left, meta[n * 4 + 2] = G.recently_seen_count, meta[n * 4 + 3] = G.total_seen_count;
+    const int rows[4] = {0, 1, 3, 4};
+    for (int r = 0; r < 4; r++)
+      for (int d = 0; d < 10; d++) scores[(n * 4 + r) * 10 + d] = G.scores(rows[r], d);
+  }
+  return n;
+}
+
+/* get_stable_expiry_month_and_year (scan/expiry_categorize.cpp:398-441) on a five-character group with the given
+ * 5 x 10 score rows; month / year are in-out (the best date so far). */
+void ref_expiry_month_year(const float *scores50, int32_t *month, int32_t *year) {
+  GroupedRects g;
+  g.pattern = ExpiryPatternMMsYY;
+  for (int i = 0; i < 5; i++) g.character_rects.push_back(CharacterRect(0, 12 * i, 0));
+  g.scores = ExpiryGroupScores::Zero();
+  for (int i = 0; i < 5; i++)
+    for (int d = 0; d < 10; d++) g.scores(i, d) = scores50[i * 10 + d];
+  int m = *month, y = *year;
+  get_stable_expiry_month_and_year(g, &m, &y);
+  *month = m, *year = y;
+}
+
+/* scanner_result with the expiry fields */
+int ref_scanner_result_expiry(void *state, uint8_t digits[16], int32_t *n_numbers, int32_t *month, int32_t *year) {
+  ScannerResult r;
+  memset(&r.hseg, 0, sizeof(r.hseg));
+  memset(&r.vseg, 0, sizeof(r.vseg));
+  r.n_numbers = 0;
+  r.expiry_month = r.expiry_year = 0;
+  for (int i = 0; i < 16; i++) r.predictions(i, 0) = 0;
+  scanner_result((ScannerState *)state, &r);
+  for (int i = 0; i < 16; i++) digits[i] = (uint8_t)r.predictions(i, 0);
+  *n_numbers = r.n_numbers;
+  *month = r.expiry_month, *year = r.expiry_year;
+  return r.complete;
+}
 #endif
 
 }  // extern "C"

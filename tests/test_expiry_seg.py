@@ -96,3 +96,79 @@ def test_against_reference_build(host, slash_w, golden, refx):
         assert got.shape == want.shape and np.array_equal(got, want), sd
         found += len(want) > 0
     assert found > 100
+
+
+def _stamp(card, txt, x, y, pitch=12, fg=60):
+    from util import expiry_glyph
+    c = card.copy()
+    for i, ch in enumerate(txt):
+        xs = x + i * pitch
+        reg = c[y:y + 15, xs:xs + 9]
+        reg[expiry_glyph(ch) > 0] = fg
+    return np.ascontiguousarray(c)
+
+
+def test_session_expiry_logic_against_reference_build(refx, oracle, pkg):
+    """expiry_extract's session half (aggregation across frames, stability, date rules) in scanner.cpp -- host logic, no
+    GPU -- fed with the reference's own per-frame groups and digit probabilities, against the reference session."""
+    import datetime
+    from util import deck_frames
+    now = datetime.datetime.now()
+    recs, cards = oracle.process_frames(deck_frames(16, 8), want_cards=True)
+    for txt, fg, drift in (("08/27", 40, 0), ("11/29", 250, 0), ("03/30", 40, 3), ("05/28", 250, 7)):
+        rs = refx.scanner_new()
+        mine = pkg.Scanner()
+        for k in range(8):
+            yo = int(recs["v_y_offset"][k])
+            x = 70 + (drift * k if drift == 3 else (drift if k % 2 else 0))  # slow drift / jumps beyond the 5-px tolerance
+            card = _stamp(cards[k], txt, x, min(yo + 27 + 40, 250), 12, fg)
+            groups = refx.best_expiry_seg(card, yo)  # what scan_card_image hands to expiry_extract
+            scan, _ = refx.scanner_add_frame_with_expiry(rs, card, True)
+            if scan.usable and len(groups):
+                g = np.zeros(len(groups), pkg.EXPIRY_GROUP_DTYPE)
+                sc = np.zeros((len(groups), 4, 10), np.float32)
+                for i, row in enumerate(groups):
+                    for f, name in enumerate(("top", "left", "width", "height", "character_width", "pattern", "n_rects")):
+                        g[i][name] = row[f]
+                    rects = row[7:].reshape(5, 2)
+                    g[i]["rect_top"], g[i]["rect_left"] = rects[:, 0], rects[:, 1]
+                    for r, ci in enumerate((0, 1, 3, 4)):
+                        t, l = rects[ci]
+                        sc[i, r] = refx.expiry_digit_model(refx.expiry_patch_prep(card[t:t + 16, l:l + 11]))
+                mine.add_expiry(g, sc, now.year, now.month, allow_past_dates=True)
+            (m, y), meta, scores = refx.scanner_expiry_peek(rs)
+            mmeta, mscores = mine.expiry_peek()
+            assert mine.expiry() == (m, y), (txt, k)
+            assert np.array_equal(meta, mmeta), (txt, k, meta, mmeta)
+            assert np.array_equal(scores.view(np.uint32), mscores.view(np.uint32)), (txt, k)
+        refx.scanner_free(rs)
+        mine.close()
+
+
+def test_expiry_date_rules_against_reference_build(refx, pkg):
+    """get_stable_expiry_month_and_year + expiry_string_to_expiry_month_and_year on crafted score rows (CYTHON_DMZ build:
+    past dates allowed), including unstable digits, YY/MM swapping, out-of-range months and the 'later date wins' rule."""
+    import datetime
+    now = datetime.datetime.now()
+    rng = np.random.default_rng(4)
+    accepted = 0
+    for t in range(1500):
+        digits = [int(rng.integers(0, 10)) for _ in range(5)]
+        if t % 3 == 0:
+            digits[0], digits[1] = divmod(int(rng.integers(1, 13)), 10)
+        if t % 5 == 0:
+            digits[3], digits[4] = divmod(int(rng.integers(now.year % 100 - 2, now.year % 100 + 7)) % 100, 10)
+        if t % 7 == 0:  # YY/MM order
+            digits[3], digits[4] = divmod(int(rng.integers(1, 13)), 10)
+            digits[0], digits[1] = divmod(int(rng.integers(13, 40)), 10)
+        sc = rng.random((5, 10)).astype(np.float32) * 0.05
+        for i in range(5):
+            sc[i, digits[i]] = 1.0 if rng.random() > 0.1 else 0.12  # some rows fall below the 0.7 stability bar
+        if t % 11 == 0:
+            sc[1, (digits[1] + 1) % 10] = sc[1, digits[1]]  # exact tie: first maximum wins, stability 0.5
+        m0, y0 = (0, 0) if t % 4 else (int(rng.integers(1, 13)), int(now.year + rng.integers(-1, 4)))
+        want = refx.expiry_month_year(sc, m0, y0)
+        got = pkg.expiry_month_year_from_scores(sc, now.year, now.month, True, m0, y0)
+        assert got == want, (t, digits, got, want)
+        accepted += want != (m0, y0)
+    assert accepted > 100

@@ -439,3 +439,51 @@ def test_cxx_dropin_layer(dmz, oracle, tmp_path):
             assert got["digits"][k][: len(digits)].tolist() == digits.tolist()
     assert done
     oracle.scanner_free(s)
+
+
+def test_cxx_dropin_expiry(dmz, oracle, tmp_path):
+    """scanner_add_frame_with_expiry(scan_expiry = true) through the C++ drop-in layer: GPU segmentation + expiry digit CNN,
+    cross-frame aggregation in the caller's ScannerState -- against the reference's SCAN_EXPIRY=1 build on the same cards
+    (needs oracle/_ref/libdmz_ref_expiry.so, which travels with the repo snapshot)."""
+    from oracle.binding import Oracle, available
+    from util import expiry_glyph
+    if not available("refx"):
+        pytest.skip("oracle/_ref/libdmz_ref_expiry.so not present")
+    rx = Oracle("refx")
+    exe = str(tmp_path / "compat_expiry_main")
+    subprocess.check_call(["g++", "-std=c++14", "-O1", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "compat_expiry_main.cpp"),
+                           "-o", exe, "-L" + os.path.join(ROOT, "card.io-dmz_b200"), "-lb200dmz",
+                           "-Wl,-rpath," + os.path.join(ROOT, "card.io-dmz_b200"), "-ldl"])
+    recs, cards = oracle.process_frames(deck_frames(16, 8), want_cards=True)
+    dt = np.dtype([("head", "<i4", 8), ("groups", [("meta", "<i4", 4), ("rows", "<f4", 40)], 8)])
+    for case, (txt, fg, jump) in enumerate((("08/27", 40, 0), ("11/29", 250, 0), ("03/30", 40, 7), ("05/28", 250, 3))):
+        stamped = []
+        for k in range(8):
+            yo = int(recs["v_y_offset"][k])
+            c = cards[k].copy()
+            x0 = 70 + (jump if k % 2 else 0)
+            for i, ch in enumerate(txt):
+                reg = c[min(yo + 67, 250):min(yo + 67, 250) + 15, x0 + 12 * i:x0 + 12 * i + 9]
+                reg[expiry_glyph(ch) > 0] = fg
+            stamped.append(c)
+        stamped = np.ascontiguousarray(np.stack(stamped))
+        fin, fout = str(tmp_path / ("cards%d.bin" % case)), str(tmp_path / ("out%d.bin" % case))
+        stamped.tofile(fin)
+        subprocess.check_call([exe, fin, "8", fout])
+        got = np.fromfile(fout, dt)
+        rs = rx.scanner_new()
+        seen = 0
+        for k in range(8):
+            scan, _ = rx.scanner_add_frame_with_expiry(rs, stamped[k], True)
+            done, _, rm, ry = rx.scanner_result_expiry(rs)
+            (m, y), meta, scores = rx.scanner_expiry_peek(rs)
+            h = got["head"][k]
+            assert (h[0], h[1]) == (scan.usable, scan.upside_down), (case, k)
+            assert (h[2], h[3]) == (m, y) and h[7] == len(meta), (case, k, h, m, y, len(meta))
+            assert (h[4], h[5], h[6]) == (int(done), rm, ry), (case, k)
+            for g in range(min(len(meta), 8)):
+                assert np.array_equal(got["groups"][k]["meta"][g], meta[g]), (case, k, g)
+                assert np.abs(got["groups"][k]["rows"][g].reshape(4, 10) - scores[g]).max() <= TOL, (case, k, g)
+            seen = max(seen, len(meta))
+        rx.scanner_free(rs)
+        assert seen >= 1
