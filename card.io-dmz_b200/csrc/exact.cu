@@ -267,11 +267,10 @@ __global__ void homography_only_kernel(const float *__restrict__ src, const floa
 // evaluates X0 = M0*x_block + M1*y + M2 once per block row, then (X0 + M0*x1) * (32 / W) per pixel; the
 // coordinates are rounded (half-to-even) to 1/32 px and the four taps are blended with 15-bit integer
 // weights, out-of-image taps being 0.  Each thread produces four horizontally adjacent pixels (one
-// 32-bit store); a CTA covers kWarpRows destination rows of one frame.
+// 32-bit store); a CTA covers ROWS destination rows of one frame.
 // ------------------------------------------------------------------------------------------------
-constexpr int kWarpRows = 10;                   // 270 = 27 x 10: no ragged last block
 constexpr int kQuadsPerRow = B200_CARD_W / 4;  // 107 four-pixel groups per destination row
-constexpr int kWarpThreads = 224;               // 2 x 107 = 214 workers (two rows per pass, five passes, equal work each),
+constexpr int kWarpThreads = 224;               // 2 x 107 = 214 workers (two rows per pass, equal work each),
                                                 // padded to whole warps so the final warp-shuffle reduction is well defined
 
 // src points at pixel (0, 0) of the sw x sh frame (the host-buffer path uploads only a crop and passes a
@@ -285,7 +284,10 @@ constexpr int kWarpThreads = 224;               // 2 x 107 = 214 workers (two ro
 // fraction lies within 4/16384 of one half -- where an error that small could change the rounded integer -- the value
 // rounds to the same X as the reference's doubly-rounded one.  Boundary cases, W ~ 0 and far-away coordinates take
 // the exact reference sequence.  The result is bit-identical to the reference for every pixel.
-__device__ __forceinline__ void warp_coords(const double *M, double X0, double Y0, double W0, int x1, double xq, int *X, int *Y) {
+//
+// warp_coords_fast returns a nonzero flag when the pixel needs the exact sequence; the caller ORs the flags of its
+// four pixels and branches ONCE per quad (the slow path is rare, so four separate branches only cost issue slots).
+__device__ __forceinline__ unsigned warp_coords_fast(const double *M, double X0, double Y0, double W0, double xq, int *X, int *Y) {
   const double Wf = __fma_rn(M[6], xq, W0), nxf = __fma_rn(M[0], xq, X0), nyf = __fma_rn(M[3], xq, Y0);
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(Wf));
@@ -296,25 +298,27 @@ __device__ __forceinline__ void warp_coords(const double *M, double X0, double Y
   const unsigned ux = (unsigned)__double2loint(tx), uy = (unsigned)__double2loint(ty);
   const unsigned hbad = ((unsigned)__double2hiint(tx) ^ 0x43380000u) | ((unsigned)__double2hiint(ty) ^ 0x43380000u);
   const unsigned nearx = (ux & 0x3FFFu) - (0x2000u - 4u), neary = (uy & 0x3FFFu) - (0x2000u - 4u);  // <= 8: within 4/16384 of .5
-  int xi = (int)((ux + 0x2000u) >> 14) - 65536, yi = (int)((uy + 0x2000u) >> 14) - 65536;
-  if (hbad != 0u || min(nearx, neary) <= 8u) {
-    // exact reference sequence (separate multiply and add: this file is compiled with -fmad=false)
-    const double Wr = W0 + M[6] * x1;
-    const double nx = X0 + M[0] * x1, ny = Y0 + M[3] * x1;
-    double W = Wr != 0.0 ? 32. / Wr : 0.0;
-    const double gx = nx * W, gy = ny * W;
-    xi = __double2int_rn(gx);  // cvt.rni.s32.f64: round-half-even, saturating == saturate_cast<int>(clamp(.))
-    yi = __double2int_rn(gy);
-  }
-  *X = xi, *Y = yi;
+  *X = (int)((ux + 0x2000u) >> 14) - 65536, *Y = (int)((uy + 0x2000u) >> 14) - 65536;
+  return hbad | (unsigned)(min(nearx, neary) <= 8u);
+}
+
+// the exact reference sequence (separate multiply and add: this file is compiled with -fmad=false)
+__device__ __noinline__ int2 warp_coords_exact(double M0, double M3, double M6, double X0, double Y0, double W0, int x1) {
+  const double Wr = W0 + M6 * x1;
+  const double nx = X0 + M0 * x1, ny = Y0 + M3 * x1;
+  double W = Wr != 0.0 ? 32. / Wr : 0.0;
+  const double gx = nx * W, gy = ny * W;
+  // cvt.rni.s32.f64: round-half-even, saturating == saturate_cast<int>(clamp(.))
+  return make_int2(__double2int_rn(gx), __double2int_rn(gy));
 }
 
 // The four bilinear taps of destination pixel (X, Y) (1/32 px fixed point); out-of-image taps read as 0.
-__device__ __forceinline__ void warp_fetch(const uint8_t *__restrict__ src, int row_stride, int sw, int sh, int X, int Y, int v[4]) {
+// (the all-taps-inside case is handled by the caller for the four pixels of a quad at once)
+__device__ __forceinline__ void warp_fetch_border(const uint8_t *__restrict__ src, int row_stride, int sw, int sh, int X, int Y, int v[4]) {
   // saturate_cast<short>(X >> 5) only matters beyond +-32767 px, where every tap is outside the image anyway
   const int sx = X >> 5, sy = Y >> 5;
   if ((unsigned)sx < (unsigned)(sw - 1) && (unsigned)sy < (unsigned)(sh - 1)) {
-    const uint8_t *p = src + (sy * row_stride + sx);  // 32-bit offset inside one frame
+    const uint8_t *p = src + (sy * row_stride + sx);
     v[0] = __ldg(p), v[1] = __ldg(p + 1), v[2] = __ldg(p + row_stride), v[3] = __ldg(p + row_stride + 1);
   } else if (sx >= sw || sx + 1 < 0 || sy >= sh || sy + 1 < 0) {
     v[0] = v[1] = v[2] = v[3] = 0;
@@ -341,11 +345,15 @@ __device__ __forceinline__ int warp_blend(int X, int Y, const int v[4]) {
 
 // card_check (optional): per-frame checksum sum_i (i + 1) * card[i] mod 2^32, accumulated while the pixels are
 // still in registers (one global atomic per CTA) so that no later stage has to re-read the card for it.
+// ROWS = destination rows per CTA (a divisor of 270: no ragged last block).  The per-thread set-up (column block,
+// hoisted M products) is amortised over ROWS / 2 quads, which is why ROWS is not small.
+template <int ROWS>
 __global__ void __launch_bounds__(kWarpThreads, 4)  // measured: 3 or 5 resident CTAs are both ~10 % slower
 warp_kernel(const uint8_t *__restrict__ src, int row_stride, size_t frame_stride, int sw, int sh,
             const FrameGeom *__restrict__ geom, uint8_t *__restrict__ cards, unsigned int *__restrict__ card_check, int ox, int oy) {
+  static_assert(B200_CARD_H % ROWS == 0 && ROWS % 2 == 0, "ROWS must be an even divisor of the card height");
   const int frame = blockIdx.y;
-  const int row0 = blockIdx.x * kWarpRows;
+  const int row0 = blockIdx.x * ROWS;
   __shared__ double sM[9];
   __shared__ int s_ok;
   __shared__ unsigned int s_sum;
@@ -355,34 +363,55 @@ warp_kernel(const uint8_t *__restrict__ src, int row_stride, size_t frame_stride
   uint8_t *dst = cards + (size_t)frame * (B200_CARD_W * B200_CARD_H);
   // pointer to the (virtual) pixel (0, 0) of the frame; only addresses inside the uploaded crop are dereferenced
   const uint8_t *s = src + (size_t)frame * frame_stride - ((ptrdiff_t)oy * row_stride + ox);
-  const int nrows = min(kWarpRows, B200_CARD_H - row0);
   unsigned int sum = 0;
   const int r0 = threadIdx.x >= kQuadsPerRow ? 1 : 0, q = threadIdx.x - r0 * kQuadsPerRow;
   const int x = q * 4, xb = x & ~63;  // block origin: bw0 = 64
   const double xq0 = (double)(x - xb);
   const bool ok = s_ok != 0;
-  int r = threadIdx.x < 2 * kQuadsPerRow ? r0 : nrows;
+  int r = threadIdx.x < 2 * kQuadsPerRow ? r0 : ROWS;
   // Software pipeline over this thread's rows: the taps of row r are requested, the (FP64-heavy) coordinates of row
   // r + 2 are computed while those loads are in flight, and only then are the taps blended.
   int Xc[4], Yc[4];
+  const double bX = sM[0] * xb, bY = sM[3] * xb, bW = sM[6] * xb;  // the reference's M0 * x_block etc. (rounded products)
   auto coords = [&](int row, int *Xo, int *Yo) {
     const int y = row0 + row;
-    const double X0 = sM[0] * xb + sM[1] * y + sM[2];
-    const double Y0 = sM[3] * xb + sM[4] * y + sM[5];
-    const double W0 = sM[6] * xb + sM[7] * y + sM[8];
+    const double X0 = bX + sM[1] * y + sM[2];
+    const double Y0 = bY + sM[4] * y + sM[5];
+    const double W0 = bW + sM[7] * y + sM[8];
+    unsigned bad = 0;
 #pragma unroll
-    for (int k = 0; k < 4; k++) warp_coords(sM, X0, Y0, W0, x + k - xb, xq0 + (double)k, &Xo[k], &Yo[k]);
+    for (int k = 0; k < 4; k++) bad |= warp_coords_fast(sM, X0, Y0, W0, xq0 + (double)k, &Xo[k], &Yo[k]);
+    if (bad) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int2 e = warp_coords_exact(sM[0], sM[3], sM[6], X0, Y0, W0, x + k - xb);
+        Xo[k] = e.x, Yo[k] = e.y;
+      }
+    }
   };
-  if (ok && r < nrows) coords(r, Xc, Yc);
+  if (ok && r < ROWS) coords(r, Xc, Yc);
 #pragma unroll 1
-  while (r < nrows) {
+  while (r < ROWS) {
     const int y = row0 + r, rn = r + 2;
     unsigned int packed = 0;
     if (ok) {
       int v[4][4], Xn[4], Yn[4];
+      // all sixteen taps inside the image (the usual case): one test per quad, no per-pixel branches
+      unsigned inside = 1u;
 #pragma unroll
-      for (int k = 0; k < 4; k++) warp_fetch(s, row_stride, sw, sh, Xc[k], Yc[k], v[k]);
-      if (rn < nrows) coords(rn, Xn, Yn);
+      for (int k = 0; k < 4; k++)
+        inside &= (unsigned)((unsigned)(Xc[k] >> 5) < (unsigned)(sw - 1)) & (unsigned)((unsigned)(Yc[k] >> 5) < (unsigned)(sh - 1));
+      if (inside) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const uint8_t *p = s + ((Yc[k] >> 5) * row_stride + (Xc[k] >> 5));  // 32-bit offset inside one frame
+          v[k][0] = __ldg(p), v[k][1] = __ldg(p + 1), v[k][2] = __ldg(p + row_stride), v[k][3] = __ldg(p + row_stride + 1);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++) warp_fetch_border(s, row_stride, sw, sh, Xc[k], Yc[k], v[k]);
+      }
+      if (rn < ROWS) coords(rn, Xn, Yn);
       const unsigned int base = (unsigned)(y * B200_CARD_W + x) + 1u;
 #pragma unroll
       for (int k = 0; k < 4; k++) {
@@ -759,12 +788,22 @@ int launch_warp(const uint8_t *src, int row_stride, size_t frame_stride, int w, 
                 uint8_t *cards, unsigned int *card_check, cudaStream_t s, int ox, int oy) {
   if (card_check && cudaMemsetAsync(card_check, 0, sizeof(unsigned int) * (size_t)n, s) != cudaSuccess) return -1;
   int launches = 0;
-  const int row_blocks = (B200_CARD_H + kWarpRows - 1) / kWarpRows;
+  static int rows = 0;  // destination rows per CTA; B200_DMZ_WARP_ROWS is a tuning knob (10, 30, 54 or 90)
+  if (rows == 0) {
+    const char *e = getenv("B200_DMZ_WARP_ROWS");
+    rows = e ? atoi(e) : 30;
+    if (rows != 10 && rows != 30 && rows != 54 && rows != 90) rows = 30;
+  }
   for (int f0 = 0; f0 < n; f0 += 65535) {
     const int cnt = n - f0 < 65535 ? n - f0 : 65535;
-    warp_kernel<<<dim3(row_blocks, cnt), kWarpThreads, 0, s>>>(src + (size_t)f0 * frame_stride, row_stride, frame_stride, w, h, geom + f0,
-                                                      cards + (size_t)f0 * (B200_CARD_W * B200_CARD_H),
-                                                      card_check ? card_check + f0 : nullptr, ox, oy);
+    const dim3 grid(B200_CARD_H / rows, cnt);
+    const uint8_t *sp = src + (size_t)f0 * frame_stride;
+    uint8_t *cp = cards + (size_t)f0 * (B200_CARD_W * B200_CARD_H);
+    unsigned int *kp = card_check ? card_check + f0 : nullptr;
+    if (rows == 10) warp_kernel<10><<<grid, kWarpThreads, 0, s>>>(sp, row_stride, frame_stride, w, h, geom + f0, cp, kp, ox, oy);
+    else if (rows == 30) warp_kernel<30><<<grid, kWarpThreads, 0, s>>>(sp, row_stride, frame_stride, w, h, geom + f0, cp, kp, ox, oy);
+    else if (rows == 54) warp_kernel<54><<<grid, kWarpThreads, 0, s>>>(sp, row_stride, frame_stride, w, h, geom + f0, cp, kp, ox, oy);
+    else warp_kernel<90><<<grid, kWarpThreads, 0, s>>>(sp, row_stride, frame_stride, w, h, geom + f0, cp, kp, ox, oy);
     launches++;
   }
   return cudaGetLastError() == cudaSuccess ? launches : -1;

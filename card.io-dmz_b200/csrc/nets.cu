@@ -158,6 +158,7 @@ vseg_rows_kernel(const float *__restrict__ wts, const uint8_t *__restrict__ card
 #pragma unroll
       for (int q = 0; q < 7; q++) acc[q] = 0.0f;
       const float4 *w4 = reinterpret_cast<const float4 *>(S.w1 + i * kVStride);
+#pragma unroll 3  // 51 = 3 x 17: the LDS of the next steps are in flight while this step's FMAs issue
       for (int k4 = 0; k4 < 51; k4++) {
         const float4 wv = w4[k4];
 #pragma unroll

@@ -26,7 +26,7 @@ for l in dis.splitlines():
         line = (os.path.basename(m.group(1)), int(m.group(2))); continue
     if cur and re.match(r"\s+/\*[0-9a-f]{4}\*/", l):
         funcs[cur].append(line)
-name = [f for f in funcs if re.search(kernel_re, f)][0]
+name = [f for f in funcs if re.search(os.environ.get("NCU_LINES_FUNC", kernel_re), f)][0]
 lines = funcs[name]
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kernel_re], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
