@@ -285,27 +285,39 @@ constexpr int kWarpThreads = 224;               // 2 x 107 = 214 workers (two ro
 // rounds to the same X as the reference's doubly-rounded one.  Boundary cases, W ~ 0 and far-away coordinates take
 // the exact reference sequence.  The result is bit-identical to the reference for every pixel.
 //
-// warp_coords_fast returns a nonzero flag when the pixel needs the exact sequence; the caller ORs the flags of its
-// four pixels and branches ONCE per quad (the slow path is rare, so four separate branches only cost issue slots).
-__device__ __forceinline__ unsigned warp_coords_fast(const double *M, double X0, double Y0, double W0, double xq, int *X, int *Y) {
-  const double Wf = __fma_rn(M[6], xq, W0), nxf = __fma_rn(M[0], xq, X0), nyf = __fma_rn(M[3], xq, Y0);
-  double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(Wf));
-  r = __fma_rn(r, __fma_rn(-Wf, r, 1.0), r);
-  const double ws = r * (32.0 * 16384.0);
-  const double kMagic = 6755399441055744.0 + 1073741824.0;  // 1.5 * 2^52 + 2^30
-  const double tx = __fma_rn(nxf, ws, kMagic), ty = __fma_rn(nyf, ws, kMagic);
-  const unsigned ux = (unsigned)__double2loint(tx), uy = (unsigned)__double2loint(ty);
-  const unsigned hbad = ((unsigned)__double2hiint(tx) ^ 0x43380000u) | ((unsigned)__double2hiint(ty) ^ 0x43380000u);
-  const unsigned nearx = (ux & 0x3FFFu) - (0x2000u - 4u), neary = (uy & 0x3FFFu) - (0x2000u - 4u);  // <= 8: within 4/16384 of .5
-  *X = (int)((ux + 0x2000u) >> 14) - 65536, *Y = (int)((uy + 0x2000u) >> 14) - 65536;
-  return hbad | (unsigned)(min(nearx, neary) <= 8u);
+// The fast path also steps its three linear forms from row to row by addition (the products M1 * y of the reference
+// are only needed bit-exactly on the exact path); the accumulated rounding over a CTA's rows is ~1e-14 relative, far
+// inside the margin above.  W is carried pre-scaled by 2^-19 (exact), so its reciprocal is already 32 * 2^14 / W.
+// warp_quad_fast returns a nonzero flag when any of the four pixels needs the exact sequence; the caller branches
+// ONCE per quad (the slow path is rare, so four separate branches only cost issue slots).
+__device__ __forceinline__ unsigned warp_quad_fast(double tX, double tY, double tW, double m0, double m3, double m6s, int X[4], int Y[4]) {
+  unsigned bad = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const double kd = (double)k;  // immediate operand
+    const double Wf = k ? __fma_rn(m6s, kd, tW) : tW, nxf = k ? __fma_rn(m0, kd, tX) : tX, nyf = k ? __fma_rn(m3, kd, tY) : tY;
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(Wf));
+    r = __fma_rn(r, __fma_rn(-Wf, r, 1.0), r);
+    const double kMagic = 6755399441055744.0 + 1073741824.0;  // 1.5 * 2^52 + 2^30
+    const double tx = __fma_rn(nxf, r, kMagic), ty = __fma_rn(nyf, r, kMagic);
+    const unsigned ux = (unsigned)__double2loint(tx), uy = (unsigned)__double2loint(ty);
+    bad |= ((unsigned)__double2hiint(tx) ^ 0x43380000u) | ((unsigned)__double2hiint(ty) ^ 0x43380000u);
+    const unsigned nearx = (ux & 0x3FFFu) - (0x2000u - 4u), neary = (uy & 0x3FFFu) - (0x2000u - 4u);  // <= 8: within 4/16384 of .5
+    bad |= (unsigned)(min(nearx, neary) <= 8u);
+    X[k] = (int)((ux + 0x2000u) >> 14) - 65536, Y[k] = (int)((uy + 0x2000u) >> 14) - 65536;
+  }
+  return bad;
 }
 
-// the exact reference sequence (separate multiply and add: this file is compiled with -fmad=false)
-__device__ __noinline__ int2 warp_coords_exact(double M0, double M3, double M6, double X0, double Y0, double W0, int x1) {
-  const double Wr = W0 + M6 * x1;
-  const double nx = X0 + M0 * x1, ny = Y0 + M3 * x1;
+// the exact reference sequence for destination pixel (xb + x1, y), xb = origin of its 64-wide block
+// (separate multiply and add: this file is compiled with -fmad=false)
+__device__ __noinline__ int2 warp_coords_exact(const double *M, int xb, int y, int x1) {
+  const double X0 = M[0] * xb + M[1] * y + M[2];
+  const double Y0 = M[3] * xb + M[4] * y + M[5];
+  const double W0 = M[6] * xb + M[7] * y + M[8];
+  const double Wr = W0 + M[6] * x1;
+  const double nx = X0 + M[0] * x1, ny = Y0 + M[3] * x1;
   double W = Wr != 0.0 ? 32. / Wr : 0.0;
   const double gx = nx * W, gy = ny * W;
   // cvt.rni.s32.f64: round-half-even, saturating == saturate_cast<int>(clamp(.))
@@ -357,7 +369,13 @@ warp_kernel(const uint8_t *__restrict__ src, int row_stride, size_t frame_stride
   __shared__ double sM[9];
   __shared__ int s_ok;
   __shared__ unsigned int s_sum;
+  __shared__ double sF[6];  // fast-path coefficients: M0, M3, M6 * 2^-19 (per pixel), 2 M1, 2 M4, 2 M7 * 2^-19 (per row pair)
   if (threadIdx.x < 9) sM[threadIdx.x] = geom[frame].Minv[threadIdx.x];
+  if (threadIdx.x >= 32 && threadIdx.x < 38) {
+    const int i = threadIdx.x - 32;  // 0..2: column 0 of row i; 3..5: column 1 of row i - 3, doubled
+    const double m = geom[frame].Minv[i < 3 ? 3 * i : 3 * (i - 3) + 1];
+    sF[i] = m * (i < 3 ? 1.0 : 2.0) * ((i == 2 || i == 5) ? 1.0 / 524288.0 : 1.0);
+  }
   if (threadIdx.x == 0) s_ok = geom[frame].all_found, s_sum = 0u;
   __syncthreads();
   uint8_t *dst = cards + (size_t)frame * (B200_CARD_W * B200_CARD_H);
@@ -366,33 +384,33 @@ warp_kernel(const uint8_t *__restrict__ src, int row_stride, size_t frame_stride
   unsigned int sum = 0;
   const int r0 = threadIdx.x >= kQuadsPerRow ? 1 : 0, q = threadIdx.x - r0 * kQuadsPerRow;
   const int x = q * 4, xb = x & ~63;  // block origin: bw0 = 64
-  const double xq0 = (double)(x - xb);
   const bool ok = s_ok != 0;
   int r = threadIdx.x < 2 * kQuadsPerRow ? r0 : ROWS;
+  // fast-path linear forms of this thread's first pixel, stepped two rows at a time
+  const double kWScale = 1.0 / 524288.0;  // 2^-19: 1 / (W * 2^-19) = 32 * 2^14 / W
+  double tX = __fma_rn(sM[0], (double)x, __fma_rn(sM[1], (double)(row0 + r0), sM[2]));
+  double tY = __fma_rn(sM[3], (double)x, __fma_rn(sM[4], (double)(row0 + r0), sM[5]));
+  double tW = __fma_rn(sM[6], (double)x, __fma_rn(sM[7], (double)(row0 + r0), sM[8])) * kWScale;
   // Software pipeline over this thread's rows: the taps of row r are requested, the (FP64-heavy) coordinates of row
   // r + 2 are computed while those loads are in flight, and only then are the taps blended.
   int Xc[4], Yc[4];
-  const double bX = sM[0] * xb, bY = sM[3] * xb, bW = sM[6] * xb;  // the reference's M0 * x_block etc. (rounded products)
   auto coords = [&](int row, int *Xo, int *Yo) {
-    const int y = row0 + row;
-    const double X0 = bX + sM[1] * y + sM[2];
-    const double Y0 = bY + sM[4] * y + sM[5];
-    const double W0 = bW + sM[7] * y + sM[8];
-    unsigned bad = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) bad |= warp_coords_fast(sM, X0, Y0, W0, xq0 + (double)k, &Xo[k], &Yo[k]);
+    const volatile double *F = sF;  // re-read from shared memory every time: cheaper than holding 12 registers
+    const unsigned bad = warp_quad_fast(tX, tY, tW, F[0], F[1], F[2], Xo, Yo);
+    tX += F[3], tY += F[4], tW += F[5];
     if (bad) {
 #pragma unroll
       for (int k = 0; k < 4; k++) {
-        const int2 e = warp_coords_exact(sM[0], sM[3], sM[6], X0, Y0, W0, x + k - xb);
+        const int2 e = warp_coords_exact(sM, xb, row0 + row, x + k - xb);
         Xo[k] = e.x, Yo[k] = e.y;
       }
     }
   };
   if (ok && r < ROWS) coords(r, Xc, Yc);
+  unsigned int doff = (unsigned)((row0 + r0) * B200_CARD_W + x);  // destination offset of this thread's quad
 #pragma unroll 1
   while (r < ROWS) {
-    const int y = row0 + r, rn = r + 2;
+    const int rn = r + 2;
     unsigned int packed = 0;
     if (ok) {
       int v[4][4], Xn[4], Yn[4];
@@ -404,15 +422,16 @@ warp_kernel(const uint8_t *__restrict__ src, int row_stride, size_t frame_stride
       if (inside) {
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-          const uint8_t *p = s + ((Yc[k] >> 5) * row_stride + (Xc[k] >> 5));  // 32-bit offset inside one frame
-          v[k][0] = __ldg(p), v[k][1] = __ldg(p + 1), v[k][2] = __ldg(p + row_stride), v[k][3] = __ldg(p + row_stride + 1);
+          const unsigned int o0 = (unsigned)((Yc[k] >> 5) * row_stride + (Xc[k] >> 5));  // non-negative 32-bit offset inside one frame
+          const unsigned int o1 = o0 + (unsigned)row_stride;
+          v[k][0] = __ldg(s + o0), v[k][1] = __ldg(s + o0 + 1u), v[k][2] = __ldg(s + o1), v[k][3] = __ldg(s + o1 + 1u);
         }
       } else {
 #pragma unroll
         for (int k = 0; k < 4; k++) warp_fetch_border(s, row_stride, sw, sh, Xc[k], Yc[k], v[k]);
       }
       if (rn < ROWS) coords(rn, Xn, Yn);
-      const unsigned int base = (unsigned)(y * B200_CARD_W + x) + 1u;
+      const unsigned int base = doff + 1u;
 #pragma unroll
       for (int k = 0; k < 4; k++) {
         const unsigned int px = (unsigned)warp_blend(Xc[k], Yc[k], v[k]);
@@ -421,7 +440,8 @@ warp_kernel(const uint8_t *__restrict__ src, int row_stride, size_t frame_stride
         Xc[k] = Xn[k], Yc[k] = Yn[k];
       }
     }
-    *reinterpret_cast<unsigned int *>(dst + y * B200_CARD_W + x) = packed;
+    *reinterpret_cast<unsigned int *>(dst + doff) = packed;
+    doff += 2u * B200_CARD_W;
     r = rn;
   }
   if (card_check != nullptr) {
@@ -791,8 +811,8 @@ int launch_warp(const uint8_t *src, int row_stride, size_t frame_stride, int w, 
   static int rows = 0;  // destination rows per CTA; B200_DMZ_WARP_ROWS is a tuning knob (10, 30, 54 or 90)
   if (rows == 0) {
     const char *e = getenv("B200_DMZ_WARP_ROWS");
-    rows = e ? atoi(e) : 30;
-    if (rows != 10 && rows != 30 && rows != 54 && rows != 90) rows = 30;
+    rows = e ? atoi(e) : 90;
+    if (rows != 10 && rows != 30 && rows != 54 && rows != 90) rows = 90;
   }
   for (int f0 = 0; f0 < n; f0 += 65535) {
     const int cnt = n - f0 < 65535 ? n - f0 : 65535;
