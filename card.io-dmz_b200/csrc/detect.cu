@@ -53,6 +53,8 @@ struct SmemLayout {
 };
 
 __host__ __device__ __forceinline__ size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
+// source row stride: up to 6 bytes before the strip, 3-px halo after it, 4-byte aligned, room for the 12-byte reads
+__host__ __device__ __forceinline__ int detect_src_stride(int w) { return ((w + 6 + 3 + 3) & ~3) + 8; }
 
 // Per-thread 2-D walk over a w x h strip without integer division inside the loop:
 //   w <= T: tx = tid % w, ty = tid / w (computed once), rows advance by T / w;  w > T: tx = tid, columns advance by T.
@@ -88,7 +90,12 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
   const StripDesc &S = P.strip[strip];
   const int w = S.w, h = S.h, npx = w * h;
   const int wp = w + 2, npad = wp * (h + 2);
-  const int ws = ((w + 6 + 3) & ~3) + 4;  // source row stride: 3-px halo each side, 4-byte aligned, room for 12-byte reads
+  // Source rows in shared memory: pixel c of the strip sits at byte H + c, H in [3, 6] chosen so that the aligned 32-bit
+  // words of the global row land on aligned shared-memory words (whole-word copies); 3-px replicated halo each side.
+  const bool word_ok = ((reinterpret_cast<uintptr_t>(plane) | (uintptr_t)row_stride | (uintptr_t)frame_stride) & 3u) == 0;
+  const int shift = word_ok ? ((S.x - ox) & 3) : 0;  // bytes of the first aligned word that precede the strip
+  const int H = 3 + ((shift + 1) & 3);               // (H - shift) % 4 == 0
+  const int ws = detect_src_stride(w);
   const size_t out_idx = (size_t)frame * 4 + strip;
 
   // Fallback planes: skip strips whose edge was already found on an earlier plane (dmz.cpp:351).
@@ -127,28 +134,20 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
   // ---- 1. load the strip (32-bit coalesced loads of the covering aligned words); clear borders / accumulator
   {
     const uint8_t *base = plane + (size_t)frame * frame_stride + (size_t)(S.y - oy) * row_stride + (S.x - ox);  // plane origin = (ox, oy)
-    const bool word_ok = ((reinterpret_cast<uintptr_t>(plane) | (uintptr_t)row_stride | (uintptr_t)frame_stride) & 3u) == 0;
     if (word_ok) {
-      const int shift = (S.x - ox) & 3;        // bytes of the first word that precede the strip
-      const int words = (shift + w + 3) >> 2;  // words per row
+      const int words = (shift + w + 3) >> 2;  // words per row; the bytes around the strip they carry are overwritten by the halo
+      const int q0 = (H - shift) >> 2;         // shared-memory word of the first global word
       const Walk k = make_walk(tid, words, kThreads);
       if (k.active)
         for (int row = k.ty; row < h; row += k.ystep)
-          for (int q = k.tx; q < words; q += k.xstep) {
-            const unsigned int v = __ldg(reinterpret_cast<const unsigned int *>(base + (size_t)row * row_stride - shift) + q);
-            const int c0 = q * 4 - shift;
-            uint8_t *dst = L.src + row * ws + 3;
-#pragma unroll
-            for (int b = 0; b < 4; b++) {
-              const int c = c0 + b;
-              if (c >= 0 && c < w) dst[c] = (uint8_t)(v >> (8 * b));
-            }
-          }
+          for (int q = k.tx; q < words; q += k.xstep)
+            reinterpret_cast<unsigned int *>(L.src + row * ws)[q0 + q] =
+                __ldg(reinterpret_cast<const unsigned int *>(base + (size_t)row * row_stride - shift) + q);
     } else {
       const Walk k = make_walk(tid, w, kThreads);
       if (k.active)
         for (int row = k.ty; row < h; row += k.ystep)
-          for (int c = k.tx; c < w; c += k.xstep) L.src[row * ws + 3 + c] = __ldg(base + (size_t)row * row_stride + c);
+          for (int c = k.tx; c < w; c += k.xstep) L.src[row * ws + H + c] = __ldg(base + (size_t)row * row_stride + c);
     }
   }
   for (int i = tid; i < S.ncells; i += kThreads) L.acc[i] = 0u;
@@ -167,10 +166,10 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
   __syncthreads();
   // BORDER_REPLICATE halo: three copies of the first / last pixel of every row
   for (int y = tid; y < h; y += kThreads) {
-    uint8_t *r = L.src + y * ws;
-    const uint8_t a = r[3], b = r[3 + w - 1];
-    r[0] = a, r[1] = a, r[2] = a;
-    r[3 + w] = b, r[4 + w] = b, r[5 + w] = b;
+    uint8_t *r = L.src + y * ws + H;
+    const uint8_t a = r[0], b = r[w - 1];
+    r[-3] = a, r[-2] = a, r[-1] = a;
+    r[w] = b, r[w + 1] = b, r[w + 2] = b;
   }
   __syncthreads();
 
@@ -182,7 +181,8 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
       const int chunk = it / w, x = it - chunk * w;
       const int y0 = chunk * S.chunk_rows;
       const int y1 = min(h, y0 + S.chunk_rows);
-      const int word = x >> 2, sh = (x & 3) * 8;  // padded column x holds pixel x - 3: bytes x .. x+6 are the seven taps
+      const int xs = x + H - 3;                     // byte of the first of the seven taps (pixel x - 3)
+      const int word = xs >> 2, sh = (xs & 3) * 8;
       int hx[7], sx[7];  // ring of row-filter results: derivative taps [-1,-4,-5,0,5,4,1], smoothing taps [1,6,15,20,15,6,1]
       auto row_filter = [&](int row, int &hxo, int &sxo) {
         const unsigned int *r32 = reinterpret_cast<const unsigned int *>(L.src + row * ws) + word;
@@ -262,10 +262,12 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
           uint8_t out = 1;
           if (m > low) {
             auto mag = [&](int j) -> int { return abs((int)L.dx[j]) + abs((int)L.dy[j]); };
-            const long long ax = abs(gx), ay = abs(gy);
-            const long long tg22x = ax * 13573;  // TG22 = (int)(0.41421356 * 2^15 + 0.5)
-            const long long tg67x = tg22x + ((ax + ax) << 15);
-            const long long ys = ay << 15;
+            // the reference's int64 products fit in 32 unsigned bits here: |dx|, |dy| <= 32768 after the s16 saturation,
+            // so tg22x <= 4.5e8, tg67x <= 2.6e9 < 2^32, ys <= 2^30
+            const unsigned int ax = (unsigned)abs(gx), ay = (unsigned)abs(gy);
+            const unsigned int tg22x = ax * 13573u;  // TG22 = (int)(0.41421356 * 2^15 + 0.5)
+            const unsigned int tg67x = tg22x + ((ax + ax) << 15);
+            const unsigned int ys = ay << 15;
             bool is_max;
             if (ys < tg22x) {
               is_max = m > mag(o - 1) && m >= mag(o + 1);
@@ -416,7 +418,7 @@ size_t detect_smem_bytes(const DetectParams &p) {
   for (int s = 0; s < 4; s++) {
     const StripDesc &d = p.strip[s];
     const size_t npad = (size_t)(d.w + 2) * (d.h + 2);
-    const size_t ws = (((size_t)d.w + 6 + 3) & ~(size_t)3) + 4;
+    const size_t ws = (size_t)detect_src_stride(d.w);
     size_t b = align16(ws * d.h) + align16(npad);  // padded src (later the work lists), map
     if (!p.use_global_grad) b += 2 * align16(npad * 2);
     b += (size_t)d.ncells * 4 + 64;
