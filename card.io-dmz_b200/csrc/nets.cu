@@ -31,29 +31,41 @@ __constant__ float c_conv_w[3][8][9];
 __constant__ float c_conv_b[3][8];
 
 // ------------------------------------------------------------------------------------------------
-// V1 + V2.  A CTA owns a tile of kVRows (frame,row) work items; W1 (50 x 204, padded rows) stays in shared
-// memory across the persistent tile loop.
+// V1 + V2.  Warp-autonomous tiles: every warp of a persistent CTA owns tiles of kVTile = 16 (frame,row) work items
+// and takes each through preparation, hidden layer and output layer by itself -- no block barrier inside the tile
+// loop, so the preparation of one warp overlaps the FMAs of another.  W1 (50 x 204, rows padded to 212 floats, units
+// padded to 56 with zeros) stays in shared memory for the CTA's lifetime.
+//
+// Hidden layer: lane = (row lane lr = lane / 8, unit lane lu = lane % 8); a thread accumulates rows lr + 4i (i < 4)
+// x units lu + 8j (j < 7) = 28 sums in registers.  Per 4-float K step it issues 4 + 7 LDS.128 (each row address is
+// shared by 8 lanes, each unit address by 4: 64 B resp. 128 B unique per request) for 112 FMAs, so the shared-memory
+// crossbar stays at ~0.4 of the FMA issue rate (the earlier 1 unit x 7 rows tiling was crossbar-bound at ~54 % issue).
 // ------------------------------------------------------------------------------------------------
-constexpr int kVThreads = 256;
-constexpr int kVRows = 32;
-constexpr int kVStride = 212;  // 53 16-byte units per row (odd): conflict-free LDS.128 across hidden units
+constexpr int kVWarps = 12;
+constexpr int kVThreads = kVWarps * 32;
+constexpr int kVTile = 16;     // work items per warp tile
+constexpr int kVStride = 212;  // 53 16-byte units per row (odd): the 4 row / 8 unit addresses of a request hit distinct bank groups
+constexpr int kVUnits = 56;    // 50 hidden units padded to 7 x 8
 constexpr int kFineSlots = 43; // rows [y0 - 8, y0 + 35)
 
+struct VsegWarp {
+  alignas(16) float x[kVTile][kVStride];  // prepared rows of the current tile
+  alignas(4) uint8_t raw[412];            // one staged card row (408 px)
+  int item_frame[kVTile];
+  int item_row[kVTile];
+  int pad[3];
+};
 struct VsegSmem {
-  alignas(16) float w1[50 * kVStride];
-  float b1[50];
-  float w2[3 * 50];
-  float b2[3];
-  alignas(16) float x[kVRows][204];
-  float h[kVRows][52];
-  alignas(4) uint8_t raw[kVThreads / 32][412];  // one staged card row (408 px) per warp
-  int item_frame[kVRows];
-  int item_row[kVRows];
+  alignas(16) float w1[kVUnits * kVStride];
+  float b1[kVUnits];
+  float w2[3][kVUnits];
+  float b2[4];
+  VsegWarp warp[kVWarps];
 };
 
 // mode 0: coarse rows 0,4,..,268 of every gated frame.  mode 1: fine rows around the coarse best.
 // mode 2: raw prepared rows (stage tap): in = n x 204 floats, out = n x 3.
-__global__ void __launch_bounds__(kVThreads)
+__global__ void __launch_bounds__(kVThreads, 1)
 vseg_rows_kernel(const float *__restrict__ wts, const uint8_t *__restrict__ cards, const uint8_t *__restrict__ gate,
                  const b200_scan *__restrict__ scans, int n, int mode, float *__restrict__ vprob,
                  const float *__restrict__ raw_rows, float *__restrict__ raw_out) {
@@ -61,21 +73,29 @@ vseg_rows_kernel(const float *__restrict__ wts, const uint8_t *__restrict__ card
   VsegSmem &S = *reinterpret_cast<VsegSmem *>(vs_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  for (int i = tid; i < 50 * 204; i += kVThreads) S.w1[(i / 204) * kVStride + (i % 204)] = __ldg(wts + i);
-  for (int i = tid; i < 50; i += kVThreads) S.b1[i] = __ldg(wts + 10200 + i);
-  for (int i = tid; i < 150; i += kVThreads) S.w2[i] = __ldg(wts + 10250 + i);
+  for (int i = tid; i < kVUnits * kVStride; i += kVThreads) {
+    const int u = i / kVStride, k = i - u * kVStride;
+    S.w1[i] = (u < 50 && k < 204) ? __ldg(wts + u * 204 + k) : 0.0f;
+  }
+  for (int i = tid; i < kVUnits; i += kVThreads) S.b1[i] = i < 50 ? __ldg(wts + 10200 + i) : 0.0f;
+  for (int i = tid; i < 3 * kVUnits; i += kVThreads) {
+    const int c = i / kVUnits, u = i - c * kVUnits;
+    S.w2[c][u] = u < 50 ? __ldg(wts + 10250 + c * 50 + u) : 0.0f;
+  }
   if (tid < 3) S.b2[tid] = __ldg(wts + 10400 + tid);
+  __syncthreads();  // the only block barrier: weights visible
 
+  VsegWarp &Wp = S.warp[warp];
   const int per_frame = mode == 0 ? 68 : (mode == 1 ? kFineSlots : 1);
   const long long total = (long long)n * per_frame;
-  const long long ntiles = (total + kVRows - 1) / kVRows;
+  const long long ntiles = (total + kVTile - 1) / kVTile;
+  const int lr = lane >> 3, lu = lane & 7;
 
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    __syncthreads();  // weights visible / previous tile consumed
-    // ---- resolve the work items of this tile
-    if (tid < kVRows) {
-      const long long item = tile * kVRows + tid;
-      int fr = -1, row = -1;
+  for (long long tile = (long long)blockIdx.x * kVWarps + warp; tile < ntiles; tile += (long long)gridDim.x * kVWarps) {
+    // ---- resolve the work items of this tile (lanes 0..15)
+    int fr = -1, row = -1;
+    if (lane < kVTile) {
+      const long long item = tile * kVTile + lane;
       if (item < total) {
         const int f = (int)(item / per_frame), j = (int)(item % per_frame);
         if (mode == 2) {
@@ -92,114 +112,156 @@ vseg_rows_kernel(const float *__restrict__ wts, const uint8_t *__restrict__ card
           }
         }
       }
-      S.item_frame[tid] = fr;
-      S.item_row[tid] = row;
     }
-    __syncthreads();
-    // ---- V1: row preparation, one warp per row (4 rows per warp)
-    for (int r = warp; r < kVRows; r += kVThreads / 32) {
-      const int fr = S.item_frame[r];
-      if (fr < 0) continue;  // warp-uniform
-      if (mode == 2) {
-        for (int k = lane; k < 204; k += 32) S.x[r][k] = __ldg(raw_rows + (size_t)fr * 204 + k);
-        continue;
+    const unsigned active = __ballot_sync(0xffffffffu, fr >= 0);
+    if (active == 0u) continue;  // warp-uniform: nothing to score in this tile
+    __syncwarp();                // the previous tile's readers of x / item_* are done
+    if (lane < kVTile) Wp.item_frame[lane] = fr, Wp.item_row[lane] = row;
+    __syncwarp();
+
+    // ---- V1: row preparation, one row at a time; the 16-bit loads of the next active row are issued before the
+    // current row is processed (software prefetch: one global-latency exposure per tile, not per row)
+    if (mode == 2) {
+      for (int r = 0; r < kVTile; r++) {
+        const int f = Wp.item_frame[r];
+        if (f < 0) continue;
+        for (int k = lane; k < 204; k += 32) Wp.x[r][k] = __ldg(raw_rows + (size_t)f * 204 + k);
       }
-      const uint8_t *src = cards + (size_t)fr * kCardBytes + (size_t)S.item_row[r] * B200_CARD_W + 10;
-      // stage the 408-byte row with coalesced 16-bit loads (the row starts at an even, not 4-aligned, offset)
-      uint8_t *raw = S.raw[warp];
-      __syncwarp();
-#pragma unroll
-      for (int q = 0; q < 7; q++) {
-        const int k = lane + 32 * q;
-        if (k < 204) reinterpret_cast<unsigned short *>(raw)[k] = __ldg(reinterpret_cast<const unsigned short *>(src) + k);
-      }
-      __syncwarp();
-      // ROI (10, row, 408, 1): 3-tap max - min with replicate at the ROI edge, then (a + b + 1) >> 1
-      int vals[7];
-      int mn = 255, mx = 0;
-#pragma unroll
-      for (int q = 0; q < 7; q++) {
-        const int k = lane + 32 * q;  // output index 0..203
-        int v = 0;
-        if (k < 204) {
-          const int j0 = 2 * k, j1 = 2 * k + 1;
-          const int a = raw[j0 > 0 ? j0 - 1 : 0], b = raw[j0], c = raw[j1], d = raw[j1 < 407 ? j1 + 1 : 407];
-          const int g0 = max(a, max(b, c)) - min(a, min(b, c));
-          const int g1 = max(b, max(c, d)) - min(b, min(c, d));
-          v = (g0 + g1 + 1) >> 1;
-          mn = min(mn, v);
-          mx = max(mx, v);
-        }
-        vals[q] = v;
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      }
-      // cvConvertScale(1/255) then cvNormalize(MINMAX 0..1): float multiply, then float multiply + float add
-      const float k255 = 1.0f / 255.0f;
-      const float fmn = __fmul_rn((float)mn, k255), fmx = __fmul_rn((float)mx, k255);
-      const double smin = (double)fmn, smax = (double)fmx;
-      const double scale = (smax - smin > DBL_EPSILON) ? 1. / (smax - smin) : 0.0;
-      const double shift = 0.0 - smin * scale;
-      const float fs = (float)scale, fb = (float)shift;
-#pragma unroll
-      for (int q = 0; q < 7; q++) {
-        const int k = lane + 32 * q;
-        if (k < 204) S.x[r][k] = __fadd_rn(__fmul_rn(__fmul_rn((float)vals[q], k255), fs), fb);
-      }
-    }
-    __syncthreads();
-    // ---- V2 hidden layer: thread -> (unit i, row group g); rows g, g+5, ...
-    if (tid < 250) {
-      const int i = tid % 50, g = tid / 50;
-      float acc[7];
-#pragma unroll
-      for (int q = 0; q < 7; q++) acc[q] = 0.0f;
-      const float4 *w4 = reinterpret_cast<const float4 *>(S.w1 + i * kVStride);
-#pragma unroll 3  // 51 = 3 x 17: the LDS of the next steps are in flight while this step's FMAs issue
-      for (int k4 = 0; k4 < 51; k4++) {
-        const float4 wv = w4[k4];
+    } else {
+      unsigned short pre[7];
+      auto fetch = [&](int r) {
+        const uint8_t *src = cards + (size_t)Wp.item_frame[r] * kCardBytes + (size_t)Wp.item_row[r] * B200_CARD_W + 10;
+        // the row starts at an even, not 4-aligned, offset: coalesced 16-bit loads
 #pragma unroll
         for (int q = 0; q < 7; q++) {
-          const int r = g + 5 * q;
-          if (r < kVRows) {
-            const float4 xv = reinterpret_cast<const float4 *>(S.x[r])[k4];  // broadcast within the row group
-            acc[q] = fmaf(wv.x, xv.x, acc[q]);
-            acc[q] = fmaf(wv.y, xv.y, acc[q]);
-            acc[q] = fmaf(wv.z, xv.z, acc[q]);
-            acc[q] = fmaf(wv.w, xv.w, acc[q]);
+          const int k = lane + 32 * q;
+          pre[q] = k < 204 ? __ldg(reinterpret_cast<const unsigned short *>(src) + k) : (unsigned short)0;
+        }
+      };
+      unsigned todo = active;
+      int r = __ffs(todo) - 1;
+      fetch(r);
+      while (todo) {
+        todo &= todo - 1;
+        uint8_t *raw = Wp.raw;
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 7; q++) {
+          const int k = lane + 32 * q;
+          if (k < 204) reinterpret_cast<unsigned short *>(raw)[k] = pre[q];
+        }
+        __syncwarp();
+        const int rnext = todo ? __ffs(todo) - 1 : -1;
+        if (rnext >= 0) fetch(rnext);
+        // ROI (10, row, 408, 1): 3-tap max - min with replicate at the ROI edge, then (a + b + 1) >> 1
+        int vals[7];
+        int mn = 255, mx = 0;
+#pragma unroll
+        for (int q = 0; q < 7; q++) {
+          const int k = lane + 32 * q;  // output index 0..203
+          int v = 0;
+          if (k < 204) {
+            const int j0 = 2 * k, j1 = 2 * k + 1;
+            const int a = raw[j0 > 0 ? j0 - 1 : 0], b = raw[j0], c = raw[j1], d = raw[j1 < 407 ? j1 + 1 : 407];
+            const int g0 = max(a, max(b, c)) - min(a, min(b, c));
+            const int g1 = max(b, max(c, d)) - min(b, min(c, d));
+            v = (g0 + g1 + 1) >> 1;
+            mn = min(mn, v);
+            mx = max(mx, v);
+          }
+          vals[q] = v;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+          mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        // cvConvertScale(1/255) then cvNormalize(MINMAX 0..1): float multiply, then float multiply + float add
+        const float k255 = 1.0f / 255.0f;
+        const float fmn = __fmul_rn((float)mn, k255), fmx = __fmul_rn((float)mx, k255);
+        const double smin = (double)fmn, smax = (double)fmx;
+        const double scale = (smax - smin > DBL_EPSILON) ? 1. / (smax - smin) : 0.0;
+        const double shift = 0.0 - smin * scale;
+        const float fs = (float)scale, fb = (float)shift;
+#pragma unroll
+        for (int q = 0; q < 7; q++) {
+          const int k = lane + 32 * q;
+          if (k < 204) Wp.x[r][k] = __fadd_rn(__fmul_rn(__fmul_rn((float)vals[q], k255), fs), fb);
+        }
+        r = rnext;
+      }
+    }
+    __syncwarp();
+
+    // ---- V2 hidden layer: 4 rows x 7 units per thread (rows of inactive items hold stale data; their sums are dropped)
+    float acc[4][7];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < 7; j++) acc[i][j] = 0.0f;
+    {
+      const float4 *x4 = reinterpret_cast<const float4 *>(&Wp.x[lr][0]);       // row lr + 4i at x4 + i * 4 * 53
+      const float4 *w4 = reinterpret_cast<const float4 *>(S.w1 + lu * kVStride);  // unit lu + 8j at w4 + j * 8 * 53
+#pragma unroll 3
+      for (int k4 = 0; k4 < 51; k4++) {
+        float4 xv[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) xv[i] = x4[i * 4 * (kVStride / 4) + k4];
+#pragma unroll
+        for (int j = 0; j < 7; j++) {
+          const float4 wv = w4[j * 8 * (kVStride / 4) + k4];
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            acc[i][j] = fmaf(wv.x, xv[i].x, acc[i][j]);
+            acc[i][j] = fmaf(wv.y, xv[i].y, acc[i][j]);
+            acc[i][j] = fmaf(wv.z, xv[i].z, acc[i][j]);
+            acc[i][j] = fmaf(wv.w, xv[i].w, acc[i][j]);
           }
         }
       }
+    }
+    // ---- logistic layer: per-thread partial sums over its 7 units, butterfly over the 8 unit lanes, then softmax
+    // (expf / sum, no max shift -- as the generated model does)
+    float o[4][3];
 #pragma unroll
-      for (int q = 0; q < 7; q++) {
-        const int r = g + 5 * q;
-        if (r < kVRows) S.h[r][i] = tanhf(acc[q] + S.b1[i]);
+    for (int i = 0; i < 4; i++) o[i][0] = o[i][1] = o[i][2] = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 7; j++) {
+      const int u = lu + 8 * j;
+      const float b = S.b1[u], w20 = S.w2[0][u], w21 = S.w2[1][u], w22 = S.w2[2][u];
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const float hv = tanhf(acc[i][j] + b);
+        o[i][0] = fmaf(w20, hv, o[i][0]);
+        o[i][1] = fmaf(w21, hv, o[i][1]);
+        o[i][2] = fmaf(w22, hv, o[i][2]);
       }
     }
-    __syncthreads();
-    // ---- logistic layer + softmax (expf / sum, no max shift -- as the generated model does)
-    if (tid < kVRows) {
-      const int fr = S.item_frame[tid];
-      if (fr >= 0) {
-        float o[3];
 #pragma unroll
-        for (int c = 0; c < 3; c++) {
-          float acc = 0.0f;
-          for (int k = 0; k < 50; k++) acc = fmaf(S.w2[c * 50 + k], S.h[tid][k], acc);
-          o[c] = expf(acc + S.b2[c]);
-        }
-        const float sum = (o[0] + o[1]) + o[2];
+    for (int sft = 1; sft < 8; sft <<= 1)
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) o[i][c] += __shfl_xor_sync(0xffffffffu, o[i][c], sft);
+    // unit lane i (< 4) finishes row lr + 4i
+    if (lu < 4) {
+      float z0 = o[0][0], z1 = o[0][1], z2 = o[0][2];
+#pragma unroll
+      for (int i = 1; i < 4; i++)
+        if (lu == i) z0 = o[i][0], z1 = o[i][1], z2 = o[i][2];
+      const int r = lr + 4 * lu;
+      const int f = Wp.item_frame[r];
+      if (f >= 0) {
+        const float e0 = expf(z0 + S.b2[0]), e1 = expf(z1 + S.b2[1]), e2 = expf(z2 + S.b2[2]);
+        const float sum = (e0 + e1) + e2;
         if (mode == 2) {
-          raw_out[(size_t)fr * 3 + 0] = o[0] / sum;
-          raw_out[(size_t)fr * 3 + 1] = o[1] / sum;
-          raw_out[(size_t)fr * 3 + 2] = o[2] / sum;
+          raw_out[(size_t)f * 3 + 0] = e0 / sum;
+          raw_out[(size_t)f * 3 + 1] = e1 / sum;
+          raw_out[(size_t)f * 3 + 2] = e2 / sum;
         } else {
-          float *dst = vprob + ((size_t)fr * 270 + S.item_row[tid]) * 2;
-          dst[0] = o[1] / sum;  // visa-like
-          dst[1] = o[2] / sum;  // amex-like
+          float *dst = vprob + ((size_t)f * 270 + Wp.item_row[r]) * 2;
+          dst[0] = e1 / sum;  // visa-like
+          dst[1] = e2 / sum;  // amex-like
         }
       }
     }
@@ -702,10 +764,9 @@ static int launch_vseg_rows(const NetWeights &wts, const uint8_t *cards, const u
     configured = true;
   }
   const int per_frame = mode == 0 ? 68 : (mode == 1 ? kFineSlots : 1);
-  const long long tiles = ((long long)n * per_frame + kVRows - 1) / kVRows;
-  const int ctas_per_sm = 2;
-  long long grid = (long long)num_sms() * ctas_per_sm;
-  if (grid > tiles) grid = tiles;
+  const long long tiles = ((long long)n * per_frame + kVTile - 1) / kVTile;
+  long long grid = (long long)num_sms();  // one persistent CTA (12 autonomous warps) per SM
+  if (grid > (tiles + kVWarps - 1) / kVWarps) grid = (tiles + kVWarps - 1) / kVWarps;
   if (grid < 1) grid = 1;
   vseg_rows_kernel<<<(int)grid, kVThreads, sizeof(VsegSmem), s>>>(wts.vseg, cards, gate, scans, n, mode, vprob, raw_rows, raw_out);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
