@@ -280,9 +280,10 @@ struct CatPrep {  // patch-preparation scratch, one slice per warp; dead once th
   uint8_t g8[16][27 * 20];
   uint8_t lut[16][256];
 };
+constexpr int kFeatStride = 324;  // 81 16-byte units (odd): the four digit rows of a hidden-layer request hit distinct bank groups
 struct CatWork {  // network activations of the current group
-  alignas(16) float feat[16][320];  // tanh(pool + bias) of the current model
-  float part[4][16][32];            // hidden-layer partial sums over the four K quarters
+  alignas(16) float feat[16][kFeatStride];  // tanh(pool + bias) of the current model
+  alignas(16) float part[16][16][32];       // hidden-layer partial sums of the sixteen K slices: [slice][digit][unit]
   float hid[16][3][32];
   float prob[16][3][10];
 };
@@ -442,32 +443,46 @@ categorize_kernel(NetWeights W, const uint8_t *__restrict__ cards, b200_scan *__
         else conv_pool_four<4>(m, win, &S.u.work.feat[d][cell]);
       }
       __syncthreads();
-      // hidden layer 320 -> 32: thread -> (unit u, digit quad dq, K quarter jq); 4 digits x 80 features each
+      // hidden layer 320 -> 32 as a [16 digits x 320] . [320 x 32] product: warp = K slice of 20 features, lane =
+      // (digit lane dg = lane / 8, unit lane ug = lane % 8), thread = digits dg + 4i x units 4ug .. 4ug+3 (16 sums).
+      // Per four features a thread issues 4 + 4 LDS.128 (weights: 128 B unique per request, features: 64 B) for 64 FMAs.
       {
-        const int u = tid & 31, dq = (tid >> 5) & 3, jq = tid >> 7;
-        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+        const int dg = lane >> 3, ug = lane & 7;
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0f;
         const float (*wT)[32] = S.hwT[m];
-        for (int j = jq * 80; j < jq * 80 + 80; j += 4) {
-          const float w0 = wT[j][u], w1 = wT[j + 1][u], w2 = wT[j + 2][u], w3 = wT[j + 3][u];
-          const float4 f0 = *reinterpret_cast<const float4 *>(&S.u.work.feat[dq][j]);
-          const float4 f1 = *reinterpret_cast<const float4 *>(&S.u.work.feat[dq + 4][j]);
-          const float4 f2 = *reinterpret_cast<const float4 *>(&S.u.work.feat[dq + 8][j]);
-          const float4 f3 = *reinterpret_cast<const float4 *>(&S.u.work.feat[dq + 12][j]);
-          a0 = fmaf(w0, f0.x, a0), a0 = fmaf(w1, f0.y, a0), a0 = fmaf(w2, f0.z, a0), a0 = fmaf(w3, f0.w, a0);
-          a1 = fmaf(w0, f1.x, a1), a1 = fmaf(w1, f1.y, a1), a1 = fmaf(w2, f1.z, a1), a1 = fmaf(w3, f1.w, a1);
-          a2 = fmaf(w0, f2.x, a2), a2 = fmaf(w1, f2.y, a2), a2 = fmaf(w2, f2.z, a2), a2 = fmaf(w3, f2.w, a2);
-          a3 = fmaf(w0, f3.x, a3), a3 = fmaf(w1, f3.y, a3), a3 = fmaf(w2, f3.z, a3), a3 = fmaf(w3, f3.w, a3);
+#pragma unroll
+        for (int js = 0; js < 5; js++) {
+          const int j = warp * 20 + js * 4;
+          float4 f[4], wv[4];
+#pragma unroll
+          for (int i = 0; i < 4; i++) f[i] = *reinterpret_cast<const float4 *>(&S.u.work.feat[dg + 4 * i][j]);
+#pragma unroll
+          for (int t = 0; t < 4; t++) wv[t] = *reinterpret_cast<const float4 *>(&wT[j + t][4 * ug]);
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const float fv[4] = {f[i].x, f[i].y, f[i].z, f[i].w};
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+              acc[i][0] = fmaf(wv[t].x, fv[t], acc[i][0]);
+              acc[i][1] = fmaf(wv[t].y, fv[t], acc[i][1]);
+              acc[i][2] = fmaf(wv[t].z, fv[t], acc[i][2]);
+              acc[i][3] = fmaf(wv[t].w, fv[t], acc[i][3]);
+            }
+          }
         }
-        S.u.work.part[jq][dq][u] = a0;
-        S.u.work.part[jq][dq + 4][u] = a1;
-        S.u.work.part[jq][dq + 8][u] = a2;
-        S.u.work.part[jq][dq + 12][u] = a3;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+          *reinterpret_cast<float4 *>(&S.u.work.part[warp][dg + 4 * i][4 * ug]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
       }
       __syncthreads();
       {
         const int u = tid & 31, d = tid >> 5;  // 16 digits x 32 units
         if (d < nd) {
-          const float sum = ((S.u.work.part[0][d][u] + S.u.work.part[1][d][u]) + S.u.work.part[2][d][u]) + S.u.work.part[3][d][u];
+          float sum = 0.0f;
+#pragma unroll
+          for (int q = 0; q < 16; q++) sum += S.u.work.part[q][d][u];
           S.u.work.hid[d][m][u] = tanhf(sum + S.hb[m][u]);
         }
       }
