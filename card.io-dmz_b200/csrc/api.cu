@@ -46,8 +46,8 @@ struct b200_ctx {
   uint64_t full_frame_redos = 0;
   uint64_t h2d_bytes = 0, d2h_bytes = 0;  // bytes moved by b200_process_frames_batch(B200_MEM_HOST)  // host-buffer frames that had to be re-uploaded whole (crop too small)
   Lane lane[2];
-  int host_chunk = 2048;  // frames per pipelined chunk on the host-buffer path
-  int crop_margin = 8;    // host-buffer path uploads only the detection region + this margin (< 0: whole frames)
+  int host_chunk = 1024;  // frames per pipelined chunk on the host-buffer path (measured: 1024 > 2048 > 4096)
+  int crop_margin = 2;    // host-buffer path uploads only the detection region + this margin (< 0: whole frames)
   // per-stage device time (CUDA events on the lane stream), accumulated while profiling is on
   int profiling = 0;
   double stage_ms[ST_COUNT] = {0};

@@ -250,54 +250,52 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
   int n_edge = 0;
 
   // ---- 4. non-maxima suppression, canny.cpp:220-285.  The source strip is dead now: weak candidates go to the
-  // hysteresis work list, strong pixels (edges for sure) are gated and queued for voting right away.
+  // hysteresis work list, strong pixels (edges for sure) to the vote list (the direction gate is applied when voting).
+  // Nearly every warp holds pixels of all three direction sectors, so the sector is turned into a neighbour OFFSET
+  // by selects and both neighbour magnitudes are fetched unconditionally: one straight-line body instead of three
+  // divergent ones.  Pixels are dealt round-robin over the flat index (x, y advance without a division).
   {
-    const Walk k = make_walk(tid, w, kThreads);
-    if (k.active)
-      for (int y = k.ty; y < h; y += k.ystep)
-        for (int x = k.tx; x < w; x += k.xstep) {
-          const int o = (y + 1) * wp + x + 1;
-          const int gx = L.dx[o], gy = L.dy[o];
-          const int m = abs(gx) + abs(gy);
-          uint8_t out = 1;
-          if (m > low) {
-            auto mag = [&](int j) -> int { return abs((int)L.dx[j]) + abs((int)L.dy[j]); };
-            // the reference's int64 products fit in 32 unsigned bits here: |dx|, |dy| <= 32768 after the s16 saturation,
-            // so tg22x <= 4.5e8, tg67x <= 2.6e9 < 2^32, ys <= 2^30
-            const unsigned int ax = (unsigned)abs(gx), ay = (unsigned)abs(gy);
-            const unsigned int tg22x = ax * 13573u;  // TG22 = (int)(0.41421356 * 2^15 + 0.5)
-            const unsigned int tg67x = tg22x + ((ax + ax) << 15);
-            const unsigned int ys = ay << 15;
-            bool is_max;
-            if (ys < tg22x) {
-              is_max = m > mag(o - 1) && m >= mag(o + 1);
-            } else if (ys > tg67x) {
-              is_max = m > mag(o - wp) && m >= mag(o + wp);
-            } else {
-              const int s = ((gx ^ gy) < 0) ? -1 : 1;
-              is_max = m > mag(o - wp - s) && m > mag(o + wp + s);
-            }
-            if (is_max) {
-              if (m > high) {
-                out = 2;
-                n_edge++;
-                if (gate(o)) push_vote(o);
-              } else {
-                out = 0;
-                const int slot = atomicAdd(&s_ncand, 1);
-                if (slot < list_cap) L.list[slot] = (unsigned short)o;
-                else s_overflow = 1;
-              }
-            }
-          }
-          L.map[o] = out;
+    const int ystep = kThreads / w, xstep = kThreads - ystep * w;
+    int y = tid / w, x = tid - y * w;
+    auto mag = [&](int j) -> int { return abs((int)L.dx[j]) + abs((int)L.dy[j]); };
+    for (; y < h;) {
+      const int o = (y + 1) * wp + x + 1;
+      const int gx = L.dx[o], gy = L.dy[o];
+      // the reference's int64 products fit in 32 unsigned bits here: |dx|, |dy| <= 32768 after the s16 saturation,
+      // so tg22x <= 4.5e8, tg67x <= 2.6e9 < 2^32, ys <= 2^30
+      const unsigned int ax = (unsigned)abs(gx), ay = (unsigned)abs(gy);
+      const int m = (int)(ax + ay);
+      const unsigned int tg22x = ax * 13573u;  // TG22 = (int)(0.41421356 * 2^15 + 0.5)
+      const unsigned int tg67x = tg22x + (ax << 16);
+      const unsigned int ys = ay << 15;
+      const bool horiz = ys < tg22x, vert = ys > tg67x;
+      // horizontal: m > left && m >= right; vertical: m > up && m >= down; diagonal: m > both, along the gradient sign
+      const int sgn = ((gx ^ gy) < 0) ? -1 : 1;
+      const int off = horiz ? 1 : (vert ? wp : wp + sgn);
+      const int ge = (horiz || vert) ? 1 : 0;
+      const bool is_max = m > mag(o - off) && m + ge > mag(o + off);
+      const bool cand = is_max && m > low;
+      const bool strong = cand && m > high;
+      L.map[o] = cand ? (strong ? 2 : 0) : 1;
+      if (cand) {
+        if (strong) {
+          n_edge++;
+          push_vote(o);
+        } else {
+          const int slot = atomicAdd(&s_ncand, 1);
+          if (slot < list_cap) L.list[slot] = (unsigned short)o;
+          else s_overflow = 1;
         }
+      }
+      x += xstep, y += ystep;
+      if (x >= w) x -= w, y++;
+    }
   }
   __syncthreads();
 
   // ---- 5. hysteresis: a candidate 8-connected to an edge pixel becomes an edge pixel; iterate over the (short)
   // candidate list to the fixed point, which is the reference's stack-walk result whatever the visiting order.
-  // A promoted candidate is gated and queued for voting on the spot (each candidate is promoted exactly once).
+  // A promoted candidate is queued for voting on the spot (each candidate is promoted exactly once).
   {
     const int ncand = s_ncand;
     if (ncand <= list_cap) {
@@ -313,7 +311,7 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
             L.map[o] = 2;
             changed = 1;
             n_edge++;
-            if (gate(o)) push_vote(o);
+            push_vote(o);
           }
         }
         if (!__syncthreads_or(changed)) break;
@@ -347,6 +345,7 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
     const int nvote = s_nvote;
     for (int e = tid; e < nvote; e += kThreads) {
       const int o = vote_list[e];
+      if (!gate(o)) continue;  // gradient-direction gate, hough.cpp:126-150: dense here, divergent if applied while queueing
       const int yy = o / wp;
       const int x = o - yy * wp - 1, y = yy - 1;
 #pragma unroll
