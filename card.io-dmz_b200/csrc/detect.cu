@@ -76,6 +76,10 @@ __device__ __forceinline__ Walk make_walk(int tid, int w, int T) {
   return k;
 }
 
+// kGlobalGrad: dx / dy live in a global scratch (strips too large for shared memory, 1080p).  A template parameter and
+// not a run-time switch so that in the usual case every dx / dy access is a plain 32-bit-addressed LDS / STS (a pointer
+// that may be shared OR global compiles to generic 64-bit-addressed loads).
+template <bool kGlobalGrad>
 __global__ void __launch_bounds__(kThreads, 3)
 detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__restrict__ plane, int row_stride,
                      size_t frame_stride, const b200_line *__restrict__ prev_lines, const b200_line *__restrict__ prev_lines2,
@@ -114,7 +118,7 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
   size_t off = 0;
   L.src = smem_raw + off;
   off = align16(off + (size_t)ws * h);
-  if (P.use_global_grad) {
+  if constexpr (kGlobalGrad) {
     L.dx = grad_scratch + ((size_t)frame * 4 + strip) * grad_scratch_stride;
     L.dy = L.dx + grad_scratch_stride / 2;
   } else {
@@ -432,7 +436,8 @@ int launch_detect(const DetectParams &p, const uint8_t *plane, int row_stride, s
   size_t smem = detect_smem_bytes(p);
   static size_t configured = 0;
   if (smem > configured) {
-    if (cudaFuncSetAttribute(detect_strips_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(detect_strips_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(detect_strips_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
     configured = smem;
   }
   size_t max_npad = 0;
@@ -444,10 +449,13 @@ int launch_detect(const DetectParams &p, const uint8_t *plane, int row_stride, s
   int launches = 0;
   for (int f0 = 0; f0 < n; f0 += 65535) {
     int cnt = n - f0 < 65535 ? n - f0 : 65535;
-    detect_strips_kernel<<<dim3(4, cnt), kThreads, smem, s>>>(
-        p, plane + (size_t)f0 * frame_stride, row_stride, frame_stride, prev_lines ? prev_lines + (size_t)f0 * 4 : nullptr,
-        prev_lines2 ? prev_lines2 + (size_t)f0 * 4 : nullptr, lines + (size_t)f0 * 4,
-        grad_scratch ? grad_scratch + (size_t)f0 * 4 * max_npad * 2 : nullptr, max_npad * 2, ox, oy);
+    const uint8_t *pp = plane + (size_t)f0 * frame_stride;
+    const b200_line *p1 = prev_lines ? prev_lines + (size_t)f0 * 4 : nullptr, *p2 = prev_lines2 ? prev_lines2 + (size_t)f0 * 4 : nullptr;
+    int16_t *gs = grad_scratch ? grad_scratch + (size_t)f0 * 4 * max_npad * 2 : nullptr;
+    if (p.use_global_grad)
+      detect_strips_kernel<true><<<dim3(4, cnt), kThreads, smem, s>>>(p, pp, row_stride, frame_stride, p1, p2, lines + (size_t)f0 * 4, gs, max_npad * 2, ox, oy);
+    else
+      detect_strips_kernel<false><<<dim3(4, cnt), kThreads, smem, s>>>(p, pp, row_stride, frame_stride, p1, p2, lines + (size_t)f0 * 4, gs, max_npad * 2, ox, oy);
     launches++;
   }
   return cudaGetLastError() == cudaSuccess ? launches : -1;
