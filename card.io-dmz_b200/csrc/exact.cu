@@ -474,23 +474,41 @@ __device__ void best_segmentation(const float *__restrict__ vp /* [270][2] visa,
   *score = best, *ptype = bt, *yoff = by;
 }
 
-__global__ void vseg_select_kernel(const float *__restrict__ vprob, const uint8_t *__restrict__ gate, int n, int pass,
-                                   b200_scan *__restrict__ scans) {
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= n) return;
-  b200_scan *sc = scans + f;
-  unsigned int *words = reinterpret_cast<unsigned int *>(sc);  // sizeof(b200_scan) == 720: padding bytes must be 0 too
-  if (gate && !gate[f]) {
-    if (pass == 1) {
-      for (int i = 0; i < 180; i++) words[i] = 0u;
-    } else {
-      sc->vseg.y_offset = 0xFFFF;  // no fine rows
+// One thread per frame runs the sequential scan, but out of SHARED memory: a CTA first stages the score rows of its 32
+// frames with coalesced 128-bit loads (row stride 541 floats: the 32 lanes of the scanning warp hit 32 different banks),
+// and clears the 32 scan records cooperatively.  (One thread per frame reading global memory directly touched a new
+// cache line per lane per step: ~1 ms per pass and 100k frames; staged: a few tens of microseconds.)
+constexpr int kSelFrames = 32, kSelThreads = 128, kSelStride = 541;
+
+__global__ void __launch_bounds__(kSelThreads)
+vseg_select_kernel(const float *__restrict__ vprob, const uint8_t *__restrict__ gate, int n, int pass, b200_scan *__restrict__ scans) {
+  extern __shared__ float sel_rows[];  // [kSelFrames][kSelStride]
+  const int f0 = blockIdx.x * kSelFrames, tid = threadIdx.x;
+  const int nf = min(kSelFrames, n - f0);
+  {
+    const float4 *src = reinterpret_cast<const float4 *>(vprob + (size_t)f0 * 540);  // 2160-byte rows: 16-byte aligned
+    for (int i = tid; i < nf * 135; i += kSelThreads) {
+      const int fr = i / 135, k = (i - fr * 135) * 4;
+      const float4 v = __ldg(src + i);
+      float *d = sel_rows + fr * kSelStride + k;
+      d[0] = v.x, d[1] = v.y, d[2] = v.z, d[3] = v.w;
     }
+    if (pass == 1) {  // sizeof(b200_scan) == 720: padding bytes must be 0 too
+      unsigned int *words = reinterpret_cast<unsigned int *>(scans + f0);
+      for (int i = tid; i < nf * 180; i += kSelThreads) words[i] = 0u;
+    }
+  }
+  __syncthreads();
+  if (tid >= nf) return;
+  const int f = f0 + tid;
+  b200_scan *sc = scans + f;
+  if (gate && !gate[f]) {
+    if (pass == 0) sc->vseg.y_offset = 0xFFFF;  // no fine rows
     return;
   }
   float score;
   int pt, yo;
-  best_segmentation(vprob + (size_t)f * 540, &score, &pt, &yo);
+  best_segmentation(sel_rows + tid * kSelStride, &score, &pt, &yo);
   if (pass == 0) {
     sc->vseg.y_offset = (uint16_t)yo;
     return;
@@ -499,7 +517,6 @@ __global__ void vseg_select_kernel(const float *__restrict__ vprob, const uint8_
                               {1, 1, 1, 1, 0, 1, 1, 1, 1, 0, 1, 1, 1, 1, 0, 1, 1, 1, 1},
                               {1, 1, 1, 1, 0, 1, 1, 1, 1, 1, 1, 0, 1, 1, 1, 1, 1, 0, 0}};
   const uint8_t pat_len[3] = {0, 19, 17}, num_len[3] = {0, 16, 15};
-  for (int i = 0; i < 180; i++) words[i] = 0u;
   sc->vseg.score = score;
   sc->vseg.y_offset = (uint16_t)yo;
   sc->vseg.pattern_type = (uint8_t)pt;
@@ -956,7 +973,13 @@ int launch_scan_gate(const FrameGeom *geom, const uint8_t *valid, int n, uint8_t
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 int launch_vseg_select(const float *vprob, const uint8_t *gate, int n, int pass, b200_scan *scans, cudaStream_t s) {
-  vseg_select_kernel<<<blocks_for(n, 64), 64, 0, s>>>(vprob, gate, n, pass, scans);
+  const size_t smem = sizeof(float) * kSelFrames * kSelStride;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(vseg_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    configured = true;
+  }
+  vseg_select_kernel<<<blocks_for(n, kSelFrames), kSelThreads, smem, s>>>(vprob, gate, n, pass, scans);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 int launch_hseg(const uint8_t *cards, int n, b200_scan *scans, cudaStream_t s) {
