@@ -280,10 +280,11 @@ constexpr int kWarpThreads = 224;               // 2 x 107 = 214 workers (two ro
 // dominates this kernel's instruction count, so X is first computed the cheap way: fused multiply-adds for the three
 // linear forms, rcp.approx + ONE Newton step for 1/W (relative error ~1e-12, i.e. < 2e-7 in fX), and a single
 // FMA  t = fX * 2^14 + (1.5 * 2^52 + 2^30)  whose low word then holds round(fX * 2^14) + 2^30 as an unsigned integer
-// (valid while the high word is still that of the constant, i.e. -65536 <= fX < 196608 = 6144 px).  Unless the 14-bit
-// fraction lies within 4/16384 of one half -- where an error that small could change the rounded integer -- the value
-// rounds to the same X as the reference's doubly-rounded one.  Boundary cases, W ~ 0 and far-away coordinates take
-// the exact reference sequence.  The result is bit-identical to the reference for every pixel.
+// (valid while the high word is still that of the constant, i.e. -65536 <= fX < 196608 = 6144 px).  The fast value differs
+// from the real-number one by < 1e-3 of that integer's unit (2^-40 relative from the Newton step, times < 2^28.4), the
+// reference's own doubly-rounded value by far less, so both round to the same X unless the 14-bit fraction is EXACTLY
+// one half; the test below sends fractions within 1/16384 of one half (three values) to the exact reference sequence,
+// as it does W ~ 0 and far-away coordinates.  The result is bit-identical to the reference for every pixel.
 //
 // The fast path also steps its three linear forms from row to row by addition (the products M1 * y of the reference
 // are only needed bit-exactly on the exact path); the accumulated rounding over a CTA's rows is ~1e-14 relative, far
@@ -303,8 +304,8 @@ __device__ __forceinline__ unsigned warp_quad_fast(double tX, double tY, double 
     const double tx = __fma_rn(nxf, r, kMagic), ty = __fma_rn(nyf, r, kMagic);
     const unsigned ux = (unsigned)__double2loint(tx), uy = (unsigned)__double2loint(ty);
     bad |= ((unsigned)__double2hiint(tx) ^ 0x43380000u) | ((unsigned)__double2hiint(ty) ^ 0x43380000u);
-    const unsigned nearx = (ux & 0x3FFFu) - (0x2000u - 4u), neary = (uy & 0x3FFFu) - (0x2000u - 4u);  // <= 8: within 4/16384 of .5
-    bad |= (unsigned)(min(nearx, neary) <= 8u);
+    const unsigned nearx = (ux & 0x3FFFu) - (0x2000u - 1u), neary = (uy & 0x3FFFu) - (0x2000u - 1u);  // <= 2: within 1/16384 of .5
+    bad |= (unsigned)(min(nearx, neary) <= 2u);
     X[k] = (int)((ux + 0x2000u) >> 14) - 65536, Y[k] = (int)((uy + 0x2000u) >> 14) - 65536;
   }
   return bad;
