@@ -28,6 +28,7 @@ struct Lane {
   FrameGeom *d_geom = nullptr;
   uint8_t *d_cards = nullptr;
   float *d_vprob = nullptr;
+  uint8_t *d_q8 = nullptr;  // prepared digit patches, 16 x B200_Q8_STRIDE bytes per frame
   b200_scan *d_scan = nullptr;
   b200_frame_record *d_records = nullptr;
   unsigned int *d_check = nullptr;
@@ -123,6 +124,7 @@ std::string default_weights_dir() {
 
 void free_lane(Lane *l) {
   cudaFree(l->d_frames), cudaFree(l->d_cb), cudaFree(l->d_cr), cudaFree(l->d_lines), cudaFree(l->d_geom);
+  cudaFree(l->d_q8), l->d_q8 = nullptr;
   cudaFree(l->d_cards), cudaFree(l->d_vprob), cudaFree(l->d_scan), cudaFree(l->d_records), cudaFree(l->d_grad), cudaFree(l->d_check), cudaFree(l->d_flags);
   l->d_frames = l->d_cb = l->d_cr = nullptr;
   l->d_lines = nullptr, l->d_geom = nullptr, l->d_cards = nullptr, l->d_vprob = nullptr, l->d_scan = nullptr;
@@ -167,6 +169,7 @@ int ensure_capacity(b200_ctx *ctx, Lane *l, int n, int w, int h, bool need_frame
     CU(cudaMalloc(&l->d_geom, sizeof(FrameGeom) * (size_t)n));
     CU(cudaMalloc(&l->d_cards, kCardBytes * (size_t)n));
     CU(cudaMalloc(&l->d_vprob, (size_t)n * (540 * sizeof(float) + 16)));
+    CU(cudaMalloc(&l->d_q8, (size_t)n * 16 * B200_Q8_STRIDE));
     CU(cudaMalloc(&l->d_scan, sizeof(b200_scan) * (size_t)n));
     CU(cudaMalloc(&l->d_records, sizeof(b200_frame_record) * (size_t)n));
     CU(cudaMalloc(&l->d_check, sizeof(unsigned int) * (size_t)n));
@@ -272,7 +275,7 @@ int pipeline_on_lane(b200_ctx *ctx, Lane *l, const uint8_t *dy, int drs, size_t 
   if (timed) CU(cudaEventRecord(ctx->ev[ST_WARP], l->stream));
   LAUNCH(launch_warp(dy, drs, dfs, width, height, n, l->d_geom, dcards, l->d_check, l->stream, crop.x0, crop.y0));
   cudaEvent_t *ev = timed ? ctx->ev : nullptr;
-  LAUNCH(launch_scan(ctx->wts, dcards, n, l->d_geom, nullptr, l->d_vprob, l->d_scan, l->stream,
+  LAUNCH(launch_scan(ctx->wts, dcards, n, l->d_geom, nullptr, l->d_vprob, l->d_q8, l->d_scan, l->stream,
                      ev ? ev[ST_VSEG] : nullptr, ev ? ev[ST_HSEG] : nullptr, ev ? ev[ST_CATEGORIZE] : nullptr,
                      ev ? ev[ST_FINALIZE] : nullptr));
   LAUNCH(launch_finalize_records(l->d_geom, l->d_scan, l->d_check, n, drec, l->stream, crop.active() ? l->d_flags : nullptr, crop.x0,
@@ -502,7 +505,7 @@ int b200_scan_cards_batch(b200_ctx *ctx, const uint8_t *cards, int n, const uint
     }
   }
   b200_scan *ds = mem == B200_MEM_DEVICE ? scans : l->d_scan;
-  LAUNCH(launch_scan(ctx->wts, dc, n, nullptr, dv, l->d_vprob, ds, l->stream, nullptr, nullptr, nullptr, nullptr));
+  LAUNCH(launch_scan(ctx->wts, dc, n, nullptr, dv, l->d_vprob, l->d_q8, ds, l->stream, nullptr, nullptr, nullptr, nullptr));
   if (mem == B200_MEM_HOST) CU(cudaMemcpyAsync(scans, l->d_scan, sizeof(b200_scan) * n, cudaMemcpyDeviceToHost, l->stream));
   CU(cudaStreamSynchronize(l->stream));
   return B200_OK;
@@ -652,15 +655,18 @@ int b200_categorize_patches_batch(b200_ctx *ctx, const uint8_t *patches, int n, 
   CU(cudaSetDevice(ctx->device));
   const uint8_t *dp = patches;
   float *dout = out;
+  // scratch layout: [prepared patches n * 528][scores n * 160 (host mode)][raw patches n * 513 (host mode)]
+  const size_t o_scores = (size_t)n * B200_Q8_STRIDE, o_raw = o_scores + (size_t)n * 160;
+  int rc = ensure_misc(ctx, o_raw + (size_t)n * 513 + 64);
+  if (rc) return rc;
+  uint8_t *q8 = (uint8_t *)ctx->d_misc;
   if (mem == B200_MEM_HOST) {
-    int rc = ensure_misc(ctx, (size_t)n * (513 + 160) + 64);
-    if (rc) return rc;
-    dout = (float *)ctx->d_misc;
-    uint8_t *p = (uint8_t *)ctx->d_misc + (size_t)n * 160;
+    dout = (float *)((uint8_t *)ctx->d_misc + o_scores);
+    uint8_t *p = (uint8_t *)ctx->d_misc + o_raw;
     CU(cudaMemcpyAsync(p, patches, (size_t)n * 513, cudaMemcpyHostToDevice, ctx->stream));
     dp = p;
   }
-  LAUNCH(launch_categorize_patches(ctx->wts, dp, nullptr, n, dout, ctx->stream));
+  LAUNCH(launch_categorize_patches(ctx->wts, dp, nullptr, n, dout, q8, ctx->stream));
   if (mem == B200_MEM_HOST) CU(cudaMemcpyAsync(out, dout, (size_t)n * 160, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return B200_OK;
@@ -679,7 +685,7 @@ int b200_digit_models_batch(b200_ctx *ctx, const float *patches, int n, int mem,
     dp = p;
     dout = p + (size_t)n * 513;
   }
-  LAUNCH(launch_categorize_patches(ctx->wts, nullptr, dp, n, dout, ctx->stream));
+  LAUNCH(launch_categorize_patches(ctx->wts, nullptr, dp, n, dout, nullptr, ctx->stream));
   if (mem == B200_MEM_HOST) CU(cudaMemcpyAsync(out, dout, (size_t)n * 40 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return B200_OK;

@@ -84,13 +84,14 @@ int launch_corners_to_geom(const b200_corner_points *corners, const uint8_t *val
 int launch_warp(const uint8_t *src, int row_stride, size_t frame_stride, int w, int h, int n, const FrameGeom *geom,
                 uint8_t *cards, unsigned int *card_check, cudaStream_t s, int ox = 0, int oy = 0);
 int launch_scan(const NetWeights &wts, const uint8_t *cards, int n, const FrameGeom *geom_or_null, const uint8_t *valid,
-                float *vprob, b200_scan *scans, cudaStream_t s, cudaEvent_t ev_vseg, cudaEvent_t ev_hseg, cudaEvent_t ev_cat,
-                cudaEvent_t ev_fin);
+                float *vprob, uint8_t *q8 /* n * 16 * B200_Q8_STRIDE bytes: prepared digit patches */, b200_scan *scans, cudaStream_t s,
+                cudaEvent_t ev_vseg, cudaEvent_t ev_hseg, cudaEvent_t ev_cat, cudaEvent_t ev_fin);
 int launch_finalize_records(const FrameGeom *geom, const b200_scan *scans, const unsigned int *card_check, int n,
                             b200_frame_record *recs, cudaStream_t s, uint8_t *needs_full = nullptr, int cx0 = 0, int cy0 = 0,
                             int cx1 = 0, int cy1 = 0);
+#define B200_Q8_STRIDE 528  // bytes per prepared digit patch (27 x 19 = 513 padded to 33 x 16)
 int launch_categorize_patches(const NetWeights &wts, const uint8_t *patches, const float *float_patches, int n, float *out,
-                              cudaStream_t s);
+                              uint8_t *q8 /* n * B200_Q8_STRIDE bytes of scratch when `patches` is given */, cudaStream_t s);
 int launch_vseg_model(const NetWeights &wts, const float *rows, int n, float *out, cudaStream_t s);
 int upload_conv_constants(const float *cnn_blobs[3]);
 int upload_bilateral_tables(const float *color256, const float *space5);  // E0 prep constants (nets.cu)

@@ -274,11 +274,13 @@ vseg_rows_kernel(const float *__restrict__ wts, const uint8_t *__restrict__ card
 // ------------------------------------------------------------------------------------------------
 constexpr int kCThreads = 512;
 
-struct CatPrep {  // patch-preparation scratch, one slice per warp; dead once the float patches exist
-  unsigned int hist[16][256];
-  uint8_t raw[16][27 * 24];
-  uint8_t g8[16][27 * 20];
-  uint8_t lut[16][256];
+constexpr int kQStride = 528;  // bytes per prepared digit patch in global memory (27 x 19 = 513, padded to 33 x 16)
+
+struct CatPrepWarp {  // patch-preparation scratch of one warp (digit_prep_kernel)
+  unsigned int hist[256];
+  uint8_t raw[27 * 24];
+  uint8_t g8[27 * 20];
+  uint8_t lut[256];
 };
 constexpr int kFeatStride = 324;  // 81 16-byte units (odd): the four digit rows of a hidden-layer request hit distinct bank groups
 struct CatWork {  // network activations of the current group
@@ -292,11 +294,8 @@ struct CatSmem {
   float hb[3][32];
   float lw[3][10][32];
   float lb[3][10];
-  float patch[16][27 * 19 + 3];  // normalised digit images
-  union {
-    CatPrep prep;
-    CatWork work;
-  } u;
+  alignas(16) float patch[16][kQStride];  // normalised digit images (513 floats used per row)
+  CatWork work;
 };
 
 // four of the eight kernels of model m on one pooled cell: conv 3x3 over the 5x5 window, 3x3 max, + bias, tanh
@@ -321,14 +320,97 @@ __device__ __forceinline__ void conv_pool_four(int m, const float (&win)[5][5], 
   }
 }
 
+// C0 + C1: digit patch preparation, one warp per (frame, digit slot): ROI (offsets[d], y_off, 19, 27) ->
+// llcv_morph_grad3_2d_cross_u8 on the isolated ROI -> llcv_equalize_hist.  Writes the equalised bytes (the CNN kernel
+// applies cvConvertScale's * 1/255 when it expands them), kQStride bytes per digit.  A kernel of its own so that it runs
+// at full occupancy (2.5 KB of scratch per warp) instead of inside the one-CTA-per-SM CNN kernel between barriers.
+constexpr int kPrepWarps = 8;
+
+template <bool kRaw>
+__global__ void __launch_bounds__(kPrepWarps * 32)
+digit_prep_kernel(const uint8_t *__restrict__ cards, const b200_scan *__restrict__ scans, const uint8_t *__restrict__ raw_patches,
+                  int n_digits /* frames * 16, or raw patches */, uint8_t *__restrict__ q8) {
+  __shared__ CatPrepWarp s_prep[kPrepWarps];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int item = blockIdx.x * kPrepWarps + warp;
+  if (item >= n_digits) return;
+  CatPrepWarp &P = s_prep[warp];
+  uint8_t *raw = P.raw;  // [27][24], patch column c at byte c + a of each row
+  int a = 0;
+  if (kRaw) {
+    const uint8_t *src = raw_patches + (size_t)item * (27 * 19);
+    for (int i = lane; i < 27 * 19; i += 32) raw[(i / 19) * 24 + (i % 19)] = __ldg(src + i);
+  } else {
+    const int f = item >> 4, d = item & 15;
+    const b200_scan *sc = scans + f;
+    if (!sc->usable || d >= (int)sc->hseg.n_offsets) return;  // warp-uniform: upside-down / vseg gate (frame.cpp:38-47)
+    // rows of a card are 428 = 4 * 107 bytes apart, so every row of the patch has the same word alignment:
+    // fetch the <= 6 aligned words covering the 19 bytes of each row
+    const uint8_t *src = cards + (size_t)f * kCardBytes + (size_t)sc->vseg.y_offset * B200_CARD_W + sc->hseg.offsets[d];
+    a = (int)(reinterpret_cast<uintptr_t>(src) & 3u);
+    const unsigned int *wsrc = reinterpret_cast<const unsigned int *>(src - a);
+    const int words = (a + 19 + 3) >> 2;
+    for (int i = lane; i < 27 * 6; i += 32) {
+      const int row = i / 6, q = i - row * 6;
+      if (q < words) reinterpret_cast<unsigned int *>(raw)[row * 6 + q] = __ldg(wsrc + row * (B200_CARD_W / 4) + q);
+    }
+  }
+  for (int i = lane; i < 256; i += 32) P.hist[i] = 0;
+  __syncwarp();
+  // 5-point cross max - min with replicate at the PATCH edge (cv/morph.cpp:177-255 on the 19x27 ROI)
+  for (int i = lane; i < 27 * 19; i += 32) {
+    const int y = i / 19, x = i - y * 19;
+    const int yu = y > 0 ? y - 1 : y, yd = y < 26 ? y + 1 : y, xl = x > 0 ? x - 1 : x, xr = x < 18 ? x + 1 : x;
+    const int p = raw[yu * 24 + x + a], q = raw[y * 24 + xl + a], c = raw[y * 24 + x + a];
+    const int e = raw[y * 24 + xr + a], f = raw[yd * 24 + x + a];
+    const int v = max(p, max(q, max(c, max(e, f)))) - min(p, min(q, min(c, min(e, f))));
+    P.g8[y * 20 + x] = (uint8_t)v;
+    atomicAdd(&P.hist[v], 1u);
+  }
+  __syncwarp();
+  // llcv_equalize_hist (cv/stats.cpp:116-159): lut[i] = sat8(cvRound(cum(i) * (255.f / 513))), lut[0] = 0
+  {
+    unsigned int local[8], run = 0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      run += P.hist[lane * 8 + q];
+      local[q] = run;
+    }
+    unsigned int incl = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    const unsigned int excl = incl - run;
+    const float scale = 255.f / (19 * 27);
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const int val = __float2int_rn(__fmul_rn((float)(int)(excl + local[q]), scale));
+      P.lut[lane * 8 + q] = (uint8_t)(val < 0 ? 0 : (val > 255 ? 255 : val));
+    }
+    __syncwarp();
+    if (lane == 0) P.lut[0] = 0;
+    __syncwarp();
+  }
+  uint8_t *dst = q8 + (size_t)item * kQStride;
+  for (int i = lane; i < 27 * 19; i += 32) {
+    const int y = i / 19, x = i - y * 19;
+    dst[i] = P.lut[P.g8[y * 20 + x]];
+  }
+}
+
+// C2 on prepared patches.  One CTA (16 warps) per SM, persistent over groups (= one frame's 16 digit slots, or 16 raw
+// patches) so the 123 KB of transposed hidden weights are staged once per CTA.  The 8.4 KB of prepared bytes of the NEXT
+// group are requested (one 128-bit load per thread) before the current group is computed and expanded to floats after it.
 template <bool kRaw>
 __global__ void __launch_bounds__(kCThreads, 1)
-categorize_kernel(NetWeights W, const uint8_t *__restrict__ cards, b200_scan *__restrict__ scans,
-                  const uint8_t *__restrict__ raw_patches, const float *__restrict__ raw_float, int n_items /* frames, or raw patches */,
-                  float *__restrict__ raw_out) {
+categorize_kernel(NetWeights W, const uint8_t *__restrict__ q8, b200_scan *__restrict__ scans,
+                  const float *__restrict__ raw_float, int n_items /* frames, or raw patches */, float *__restrict__ raw_out) {
   extern __shared__ __align__(16) uint8_t cs_raw[];
   CatSmem &S = *reinterpret_cast<CatSmem *>(cs_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  (void)lane;
 
   for (int i = tid; i < 3 * 320 * 32; i += kCThreads) (&S.hwT[0][0][0])[i] = __ldg(W.cnn_hwT + i);
   for (int m = 0; m < 3; m++) {
@@ -339,89 +421,47 @@ categorize_kernel(NetWeights W, const uint8_t *__restrict__ cards, b200_scan *__
   }
 
   const int n_groups = kRaw ? (n_items + 15) / 16 : n_items;
+  const size_t q8_limit = (size_t)n_items * (kRaw ? kQStride : 16 * kQStride);  // bytes of q8 that exist
+  // 16 digits x kQStride bytes = 528 uint4 per group: thread t holds uint4 t, threads 0..15 also uint4 512 + t
+  uint4 pre0 = make_uint4(0, 0, 0, 0), pre1 = make_uint4(0, 0, 0, 0);
+  auto prefetch = [&](int grp) {
+    if (q8 == nullptr || grp >= n_groups) return;
+    const size_t base = (size_t)grp * 16 * kQStride;
+    const size_t o0 = base + (size_t)tid * 16, o1 = base + (size_t)(512 + tid) * 16;
+    if (o0 + 16 <= q8_limit) pre0 = __ldg(reinterpret_cast<const uint4 *>(q8 + o0));
+    if (tid < 16 && o1 + 16 <= q8_limit) pre1 = __ldg(reinterpret_cast<const uint4 *>(q8 + o1));
+  };
+  auto expand = [&](const uint4 &v, int u4 /* uint4 index inside the group */) {
+    const int d = u4 / (kQStride / 16), k0 = (u4 - d * (kQStride / 16)) * 16;
+    float *dst = &S.patch[d][k0];
+    const unsigned int w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+#pragma unroll
+      for (int b = 0; b < 4; b++) dst[q * 4 + b] = __fmul_rn((float)((w[q] >> (8 * b)) & 0xFFu), 1.0f / 255.0f);  // cvConvertScale
+  };
+  prefetch(blockIdx.x);
   for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
-    __syncthreads();
+    __syncthreads();  // previous group's readers of patch / work are done
     int nd;
-    const uint8_t *src_base = nullptr;
-    const b200_scan *sc = nullptr;
+    bool skip = false;
     if (kRaw) {
       nd = min(16, n_items - grp * 16);
     } else {
-      sc = scans + grp;
-      if (!sc->usable) continue;  // block-uniform: upside-down / vseg gate (frame.cpp:38-47)
+      const b200_scan *sc = scans + grp;
+      skip = !sc->usable;  // block-uniform: upside-down / vseg gate (frame.cpp:38-47)
       nd = min(16, (int)sc->hseg.n_offsets);
-      src_base = cards + (size_t)grp * kCardBytes + (size_t)sc->vseg.y_offset * B200_CARD_W;
     }
-    // ---- C0 + C1: patch preparation, one warp per digit
-    if (warp < nd) {
-      const int d = warp;
-      if (kRaw && raw_float != nullptr) {  // already-prepared float patches (model known-answer tests)
-        for (int i = lane; i < 27 * 19; i += 32) S.patch[d][i] = __ldg(raw_float + (size_t)(grp * 16 + d) * (27 * 19) + i);
-      } else {
-        uint8_t *raw = S.u.prep.raw[warp];  // [27][24], patch column c at byte c + a of each row
-        uint8_t *g8 = S.u.prep.g8[warp];
-        unsigned int *hist = S.u.prep.hist[warp];
-        int a = 0;
-        for (int i = lane; i < 256; i += 32) hist[i] = 0;
-        if (kRaw) {
-          const uint8_t *src = raw_patches + (size_t)(grp * 16 + d) * (27 * 19);
-          for (int i = lane; i < 27 * 19; i += 32) raw[(i / 19) * 24 + (i % 19)] = __ldg(src + i);
-        } else {
-          // rows of a card are 428 = 4 * 107 bytes apart, so every row of the patch has the same word alignment:
-          // fetch the <= 6 aligned words covering the 19 bytes of each row
-          const uint8_t *src = src_base + sc->hseg.offsets[d];
-          a = (int)(reinterpret_cast<uintptr_t>(src) & 3u);
-          const unsigned int *wsrc = reinterpret_cast<const unsigned int *>(src - a);
-          const int words = (a + 19 + 3) >> 2;
-          for (int i = lane; i < 27 * 6; i += 32) {
-            const int row = i / 6, q = i - row * 6;
-            if (q < words) reinterpret_cast<unsigned int *>(raw)[row * 6 + q] = __ldg(wsrc + row * (B200_CARD_W / 4) + q);
-          }
-        }
-        __syncwarp();
-        // 5-point cross max - min with replicate at the PATCH edge (cv/morph.cpp:177-255 on the 19x27 ROI)
-        for (int i = lane; i < 27 * 19; i += 32) {
-          const int y = i / 19, x = i - y * 19;
-          const int yu = y > 0 ? y - 1 : y, yd = y < 26 ? y + 1 : y, xl = x > 0 ? x - 1 : x, xr = x < 18 ? x + 1 : x;
-          const int p = raw[yu * 24 + x + a], q = raw[y * 24 + xl + a], c = raw[y * 24 + x + a];
-          const int e = raw[y * 24 + xr + a], f = raw[yd * 24 + x + a];
-          const int v = max(p, max(q, max(c, max(e, f)))) - min(p, min(q, min(c, min(e, f))));
-          g8[y * 20 + x] = (uint8_t)v;
-          atomicAdd(&hist[v], 1u);
-        }
-        __syncwarp();
-        // llcv_equalize_hist (cv/stats.cpp:116-159): lut[i] = sat8(cvRound(cum(i) * (255.f / 513))), lut[0] = 0
-        {
-          unsigned int local[8], run = 0;
-#pragma unroll
-          for (int q = 0; q < 8; q++) {
-            run += hist[lane * 8 + q];
-            local[q] = run;
-          }
-          unsigned int incl = run;
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-          }
-          const unsigned int excl = incl - run;
-          const float scale = 255.f / (19 * 27);
-#pragma unroll
-          for (int q = 0; q < 8; q++) {
-            const int val = __float2int_rn(__fmul_rn((float)(int)(excl + local[q]), scale));
-            S.u.prep.lut[warp][lane * 8 + q] = (uint8_t)(val < 0 ? 0 : (val > 255 ? 255 : val));
-          }
-          __syncwarp();
-          if (lane == 0) S.u.prep.lut[warp][0] = 0;
-          __syncwarp();
-        }
-        for (int i = lane; i < 27 * 19; i += 32) {
-          const int y = i / 19, x = i - y * 19;
-          S.patch[d][i] = __fmul_rn((float)S.u.prep.lut[warp][g8[y * 20 + x]], 1.0f / 255.0f);  // cvConvertScale
-        }
-      }
+    if (kRaw && raw_float != nullptr) {  // already-prepared float patches (model known-answer tests)
+      if (warp < nd)
+        for (int i = lane; i < 27 * 19; i += 32) S.patch[warp][i] = __ldg(raw_float + (size_t)(grp * 16 + warp) * (27 * 19) + i);
+    } else if (!skip) {
+      expand(pre0, tid);
+      if (tid < 16) expand(pre1, 512 + tid);
     }
-    __syncthreads();  // patches complete; the prep scratch is dead from here on (aliased by u.work)
+    prefetch(grp + gridDim.x);
+    if (skip) continue;
+    __syncthreads();  // patches complete
     // ---- C2, model by model
     for (int m = 0; m < 3; m++) {
       // conv 3x3 (valid, 24 x 15 computed) -> 3x3/3 max pool (8 x 5) -> + bias -> tanh.  Work item = (kernel half,
@@ -439,8 +479,8 @@ categorize_kernel(NetWeights W, const uint8_t *__restrict__ cards, b200_scan *__
         for (int i = 0; i < 5; i++)
 #pragma unroll
           for (int j = 0; j < 5; j++) win[i][j] = p[i * 19 + j];
-        if (kh == 0) conv_pool_four<0>(m, win, &S.u.work.feat[d][cell]);
-        else conv_pool_four<4>(m, win, &S.u.work.feat[d][cell]);
+        if (kh == 0) conv_pool_four<0>(m, win, &S.work.feat[d][cell]);
+        else conv_pool_four<4>(m, win, &S.work.feat[d][cell]);
       }
       __syncthreads();
       // hidden layer 320 -> 32 as a [16 digits x 320] . [320 x 32] product: warp = K slice of 20 features, lane =
@@ -457,7 +497,7 @@ categorize_kernel(NetWeights W, const uint8_t *__restrict__ cards, b200_scan *__
           const int j = warp * 20 + js * 4;
           float4 f[4], wv[4];
 #pragma unroll
-          for (int i = 0; i < 4; i++) f[i] = *reinterpret_cast<const float4 *>(&S.u.work.feat[dg + 4 * i][j]);
+          for (int i = 0; i < 4; i++) f[i] = *reinterpret_cast<const float4 *>(&S.work.feat[dg + 4 * i][j]);
 #pragma unroll
           for (int t = 0; t < 4; t++) wv[t] = *reinterpret_cast<const float4 *>(&wT[j + t][4 * ug]);
 #pragma unroll
@@ -474,7 +514,7 @@ categorize_kernel(NetWeights W, const uint8_t *__restrict__ cards, b200_scan *__
         }
 #pragma unroll
         for (int i = 0; i < 4; i++)
-          *reinterpret_cast<float4 *>(&S.u.work.part[warp][dg + 4 * i][4 * ug]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+          *reinterpret_cast<float4 *>(&S.work.part[warp][dg + 4 * i][4 * ug]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
       }
       __syncthreads();
       {
@@ -482,8 +522,8 @@ categorize_kernel(NetWeights W, const uint8_t *__restrict__ cards, b200_scan *__
         if (d < nd) {
           float sum = 0.0f;
 #pragma unroll
-          for (int q = 0; q < 16; q++) sum += S.u.work.part[q][d][u];
-          S.u.work.hid[d][m][u] = tanhf(sum + S.hb[m][u]);
+          for (int q = 0; q < 16; q++) sum += S.work.part[q][d][u];
+          S.work.hid[d][m][u] = tanhf(sum + S.hb[m][u]);
         }
       }
       // (feat is rewritten by the next model's conv only after the barrier below; part after the one above)
@@ -494,8 +534,8 @@ categorize_kernel(NetWeights W, const uint8_t *__restrict__ cards, b200_scan *__
       const int d = it / 30, r = it - d * 30, m = r / 10, c = r - m * 10;
       float acc = 0.0f;
 #pragma unroll
-      for (int j = 0; j < 32; j++) acc = fmaf(S.lw[m][c][j], S.u.work.hid[d][m][j], acc);
-      S.u.work.prob[d][m][c] = expf(acc + S.lb[m][c]);
+      for (int j = 0; j < 32; j++) acc = fmaf(S.lw[m][c][j], S.work.hid[d][m][j], acc);
+      S.work.prob[d][m][c] = expf(acc + S.lb[m][c]);
     }
     __syncthreads();
     for (int it = tid; it < 16 * 10; it += kCThreads) {
@@ -506,8 +546,8 @@ categorize_kernel(NetWeights W, const uint8_t *__restrict__ cards, b200_scan *__
         for (int m = 0; m < 3; m++) {
           float sum = 0.0f;
 #pragma unroll
-          for (int j = 0; j < 10; j++) sum += S.u.work.prob[d][m][j];
-          pm[m] = S.u.work.prob[d][m][c] / sum;
+          for (int j = 0; j < 10; j++) sum += S.work.prob[d][m][j];
+          pm[m] = S.work.prob[d][m][c] / sum;
         }
         const float mx = fmaxf(pm[0], fmaxf(pm[1], pm[2]));
         e = (((pm[0] + pm[1]) + pm[2]) - mx) / 2.0f;  // n_categorize.cpp:69-70
@@ -792,7 +832,7 @@ int launch_vseg_model(const NetWeights &wts, const float *rows, int n, float *ou
 }
 
 static int launch_categorize(const NetWeights &wts, const uint8_t *cards, b200_scan *scans, const uint8_t *raw,
-                             const float *raw_float, int n, float *raw_out, cudaStream_t s) {
+                             const float *raw_float, int n, float *raw_out, uint8_t *q8, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
     if (!ensure_smem(categorize_kernel<false>, sizeof(CatSmem))) return -1;
@@ -804,9 +844,18 @@ static int launch_categorize(const NetWeights &wts, const uint8_t *cards, b200_s
   int grid = num_sms();
   if (grid > groups) grid = groups;
   if (grid < 1) grid = 1;
-  if (is_raw) categorize_kernel<true><<<grid, kCThreads, sizeof(CatSmem), s>>>(wts, nullptr, nullptr, raw, raw_float, n, raw_out);
-  else categorize_kernel<false><<<grid, kCThreads, sizeof(CatSmem), s>>>(wts, cards, scans, nullptr, nullptr, n, nullptr);
-  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+  int launches = 1;
+  if (raw_float == nullptr) {  // C0 + C1 into q8
+    if (q8 == nullptr) return -1;
+    const long long digits = is_raw ? n : (long long)n * 16;
+    const int pgrid = (int)((digits + kPrepWarps - 1) / kPrepWarps);
+    if (is_raw) digit_prep_kernel<true><<<pgrid, kPrepWarps * 32, 0, s>>>(nullptr, nullptr, raw, (int)digits, q8);
+    else digit_prep_kernel<false><<<pgrid, kPrepWarps * 32, 0, s>>>(cards, scans, nullptr, (int)digits, q8);
+    launches++;
+  }
+  if (is_raw) categorize_kernel<true><<<grid, kCThreads, sizeof(CatSmem), s>>>(wts, raw_float ? nullptr : q8, nullptr, raw_float, n, raw_out);
+  else categorize_kernel<false><<<grid, kCThreads, sizeof(CatSmem), s>>>(wts, q8, scans, nullptr, n, nullptr);
+  return cudaGetLastError() == cudaSuccess ? launches : -1;
 }
 
 int upload_bilateral_tables(const float *color256, const float *space5) {
@@ -830,15 +879,15 @@ int launch_expiry_digits(const float *weights, const uint8_t *patches, const flo
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
-int launch_categorize_patches(const NetWeights &wts, const uint8_t *patches, const float *float_patches, int n, float *out,
+int launch_categorize_patches(const NetWeights &wts, const uint8_t *patches, const float *float_patches, int n, float *out, uint8_t *q8,
                               cudaStream_t s) {
-  return launch_categorize(wts, nullptr, nullptr, patches, float_patches, n, out, s);
+  return launch_categorize(wts, nullptr, nullptr, patches, float_patches, n, out, q8, s);
 }
 
 // scan_card_image for a batch: gate -> vseg (coarse, select, fine, select) -> hseg -> categorize -> finish.
 // vprob doubles as scratch: its tail holds the per-frame gate bytes.
 int launch_scan(const NetWeights &wts, const uint8_t *cards, int n, const FrameGeom *geom, const uint8_t *valid,
-                float *vprob, b200_scan *scans, cudaStream_t s, cudaEvent_t ev_vseg, cudaEvent_t ev_hseg, cudaEvent_t ev_cat,
+                float *vprob, uint8_t *q8, b200_scan *scans, cudaStream_t s, cudaEvent_t ev_vseg, cudaEvent_t ev_hseg, cudaEvent_t ev_cat,
                 cudaEvent_t ev_fin) {
   int launches = 0, rc;
   uint8_t *gate = reinterpret_cast<uint8_t *>(vprob + (size_t)n * 540);
@@ -856,7 +905,7 @@ int launch_scan(const NetWeights &wts, const uint8_t *cards, int n, const FrameG
   if (ev_hseg) cudaEventRecord(ev_hseg, s);
   STEP(launch_hseg(cards, n, scans, s));
   if (ev_cat) cudaEventRecord(ev_cat, s);
-  STEP(launch_categorize(wts, cards, scans, nullptr, nullptr, n, nullptr, s));
+  STEP(launch_categorize(wts, cards, scans, nullptr, nullptr, n, nullptr, q8, s));
   if (ev_fin) cudaEventRecord(ev_fin, s);
   STEP(launch_scan_finish(n, scans, s));
 #undef STEP

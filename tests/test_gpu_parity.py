@@ -153,6 +153,20 @@ def test_warp_identity_is_idempotent(dmz):
     assert np.array_equal(dmz.transform_card(img, c)[0], img[0])
 
 
+def test_warp_rounding_ties(dmz, oracle):
+    """Unit-scale maps shifted by odd multiples of 1/64 px put (almost) every fixed-point coordinate on or next to a
+    rounding tie of cvRound(fX * 32): the kernel's fast coordinates must hand exactly those to the exact sequence."""
+    frame = np.random.default_rng(7).integers(0, 256, (1, 480, 640)).astype(np.uint8)
+    for s in (1 / 64, 3 / 64, 33 / 64, 1 / 128, 1 / 64 + 2.0 ** -12, 1 / 64 - 2.0 ** -12, 0.5, 0.25):
+        for sx, sy in ((s, s), (s, 0.0), (0.0, s)):
+            c = np.array([[100 + sx, 100 + sy, 100 + sx, 369 + sy, 527 + sx, 100 + sy, 527 + sx, 369 + sy]], np.float32)  # tl, bl, tr, br
+            assert np.array_equal(dmz.transform_card(frame, c)[0], oracle.transform_card(frame[0], c[0])), (s, sx, sy)
+    # scale 1/2 and 2 (coordinates exact multiples of 16 resp. 64 thirty-seconds) with half-pixel origins
+    for c in ([100.5, 100.5, 100.5, 235.0, 314.0, 100.5, 314.0, 235.0], [10.25, 10.25, 10.25, 470.75, 630.5, 10.25, 630.5, 470.75]):
+        c = np.array([c], np.float32)
+        assert np.array_equal(dmz.transform_card(frame, c)[0], oracle.transform_card(frame[0], c[0]))
+
+
 def test_scan_cards(dmz, orecs):
     rec, ocards = orecs
     scans = dmz.scan_cards(ocards, valid=rec["all_found"].astype(np.uint8))
