@@ -279,6 +279,22 @@ def main():
                "note": "host frames are full 640x480 planes in pinned memory; the library uploads only the detection-region rectangle (+8 px) of each and re-uploads a whole frame if its card quad reaches outside it",
                "timing": "wall clock around the synchronous C-ABI calls, max over ranks"}
 
+    # ---- BASELINE configs[0]: ONE frame through the whole path (latency of a batch of one through the C ABI, host
+    # buffers, copies and the final synchronisation inside) -- outside the throughput timing, rank 0 only
+    single = None
+    if rank == 0 and not args.no_e2e:
+        h1 = torch.empty((64, H, W), dtype=torch.uint8).pin_memory()
+        h1.copy_(frames[:64])
+        r1 = torch.zeros((1, RECORD_BYTES), dtype=torch.uint8).pin_memory()
+        lat = []
+        for i in range(264):
+            t1 = time.perf_counter()
+            dmz.process_frames_host_ptr(h1[i % 64].data_ptr(), 1, W, H, r1.data_ptr())
+            lat.append(time.perf_counter() - t1)
+        lat = np.sort(np.array(lat[64:])) * 1e6
+        single = {"gpu_call_us_median": float(np.median(lat)), "gpu_call_us_p90": float(lat[int(0.9 * len(lat))]), "calls": int(len(lat)),
+                  "what": "b200_process_frames_batch(n=1, host buffers): H2D, 15 kernels, D2H, sync"}
+
     # ---- CPU baseline on the host cores (rank 0 only, bounded sample)
     cpu = None
     if rank == 0 and not args.no_cpu and world == 1:
@@ -295,6 +311,9 @@ def main():
         ok = (orecs["usable"] == 1)
         agree["scores_max_abs_diff"] = float(np.abs(grecs["scores"][ok] - orecs["scores"][ok]).max()) if ok.any() else 0.0
         agree["digit_string_mismatches"] = int((grecs["scores"][ok].reshape(-1, 16, 10).argmax(2) != orecs["scores"][ok].reshape(-1, 16, 10).argmax(2)).any(1).sum())
+        if single is not None:
+            s1, _ = orc.bench_frames(sample[:256], 1)
+            single["cpu_reference_us_per_frame_1_thread"] = 1e6 * s1 / min(256, S)
         cpu = {"value": S / secs, "unit": "frames/s", "cores": cores, "kind": "reference" if kind == "ref" else "port",
                "sample": "%d frames of the same deck, %d threads, %.2f s wall (%s)" % (S, cores, secs, "oracle/_ref" if kind == "ref" else "oracle port"),
                "parity_vs_gpu_on_sample": agree}
@@ -330,7 +349,7 @@ def main():
                        "l2": "inputs (%.1f GB per step) are larger than L2; no flush needed" % (F * FRAME_BYTES / 1e9),
                        "parallelism": "frames sharded across %d GPU(s), NCCL gather of 32-byte digit strings to rank 0%s" % (world, "" if world > 1 else " (n/a at 1 GPU)")},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "stages": per_stage,
-            "cpu_baseline": cpu, "wall_s_timed_region": wall,
+            "cpu_baseline": cpu, "single_frame": single, "wall_s_timed_region": wall,
         }
         print(json.dumps(out), flush=True)
     if dist is not None:

@@ -572,8 +572,8 @@ categorize_kernel(NetWeights W, const uint8_t *__restrict__ q8, b200_scan *__res
 // (models/expiry/modelc_bf4dd6c8.cpp:12500-13505).  Secondary path (SCAN_EXPIRY builds only); four digits per CTA
 // iteration, layer-2 weights (200 KB) streamed through shared memory one input map at a time.
 // ------------------------------------------------------------------------------------------------
-constexpr int kEThreads = 288;  // 4 digits x 70 pooled cells = 280 layer-1 items; 4 x 18 x 4 = 288 layer-2 items
-constexpr int kEDigits = 4;
+constexpr int kEDigits = 8;
+constexpr int kEThreads = 320;  // layer 2: 8 digits x 40 output maps; layer 1: 8 x 70 pooled cells in two rounds
 
 __constant__ float c_bil_color[256];  // bilateral colour LUT / spatial weights, computed on the host (b200_tables.cpp)
 __constant__ float c_bil_space[5];    // mask order N, W, C, E, S
@@ -583,7 +583,7 @@ struct ExpirySmem {
   float c1b[50];
   float xpad[kEDigits][24][20];   // mean-subtracted input with a 4-pixel zero border (full correlation), row stride 20
   float l1[kEDigits][50][70];     // ReLU(pool(conv1) + b)
-  float wk[40][25];               // layer-2 kernels of the current input map
+  float wk[2][40][25];            // layer-2 kernels of the current and the next input map (double buffer)
   float c2[kEDigits][40][18];
   float l2[kEDigits][120];
   float hid[kEDigits][176];
@@ -693,8 +693,8 @@ expiry_kernel(const float *__restrict__ W /* modelc_bf4dd6c8 blob */, const uint
     }
     __syncthreads();
     // ---- layer 1: item = (digit, pooled cell); the 6x6 input window feeds all 50 kernels (weights broadcast from smem)
-    if (tid < nd * 70) {
-      const int d = tid / 70, cell = tid - d * 70, pr = cell / 7, pc = cell - pr * 7;
+    for (int it = tid; it < nd * 70; it += kEThreads) {
+      const int d = it / 70, cell = it - d * 70, pr = cell / 7, pc = cell - pr * 7;
       float win[6][6];
 #pragma unroll
       for (int i = 0; i < 6; i++)
@@ -715,36 +715,50 @@ expiry_kernel(const float *__restrict__ W /* modelc_bf4dd6c8 blob */, const uint
         S.l1[d][f][cell] = fmaxf(fmaxf(fmaxf(a00, a01), fmaxf(a10, a11)) + S.c1b[f], 0.0f);
       }
     }
-    __syncthreads();
-    // ---- layer 2: thread = (digit, position, map group); maps fg, fg+4, ..; K loop over the 50 input maps
+    // ---- layer 2 (40 x 50 x 5 x 5 valid correlation on the 10 x 7 pooled maps -> 6 x 3): thread = (output map f, digit d)
+    // with all 18 positions in registers.  Per input map k the thread pulls its 25 weights and the digit's 70 inputs
+    // into registers (60 shared-memory requests) and issues 450 FMAs on them; the kernels of map k + 1 are staged into the
+    // other half of wk meanwhile (one barrier per k).  (The first cut re-read a weight from shared memory for every FMA.)
     {
-      const int dp = tid % 72, fg = tid / 72, d = dp / 18, pos = dp - d * 18, r = pos / 3, c = pos - r * 3;
-      float acc[10];
+      const int f = tid % 40, d = tid / 40;
+      float acc[18];
 #pragma unroll
-      for (int q = 0; q < 10; q++) acc[q] = 0.0f;
+      for (int q = 0; q < 18; q++) acc[q] = 0.0f;
+      auto stage = [&](int k, int buf) {
+        for (int i = tid; i < 1000; i += kEThreads) S.wk[buf][i / 25][i % 25] = __ldg(c2w + (size_t)(i / 25) * 1250 + k * 25 + (i % 25));
+      };
+      stage(0, 0);
+      __syncthreads();  // layer 1 complete, wk[0] staged
       for (int k = 0; k < 50; k++) {
-        __syncthreads();
-        for (int i = tid; i < 1000; i += kEThreads) S.wk[i / 25][i % 25] = __ldg(c2w + (size_t)(i / 25) * 1250 + k * 25 + (i % 25));
-        __syncthreads();
+        const int buf = k & 1;
+        if (k + 1 < 50) stage(k + 1, buf ^ 1);  // its last readers passed the barrier that ended step k - 1
         if (d < nd) {
-          float win[25];
+          float w[25], in[70];
 #pragma unroll
-          for (int i = 0; i < 5; i++)
+          for (int t = 0; t < 25; t++) w[t] = S.wk[buf][f][t];
+          const float2 *src = reinterpret_cast<const float2 *>(&S.l1[d][k][0]);  // (d * 50 + k) * 70 floats: 8-byte aligned
 #pragma unroll
-            for (int j = 0; j < 5; j++) win[i * 5 + j] = S.l1[d][k][(r + i) * 7 + c + j];
-#pragma unroll
-          for (int q = 0; q < 10; q++) {
-            const float *w = S.wk[fg + 4 * q];
-            float a = 0.0f;
-#pragma unroll
-            for (int t = 0; t < 25; t++) a = fmaf(w[t], win[t], a);
-            acc[q] += a;
+          for (int t = 0; t < 35; t++) {
+            const float2 v = src[t];
+            in[2 * t] = v.x, in[2 * t + 1] = v.y;
           }
+#pragma unroll
+          for (int r = 0; r < 6; r++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+              float a = acc[r * 3 + c];
+#pragma unroll
+              for (int i = 0; i < 5; i++)
+#pragma unroll
+                for (int j = 0; j < 5; j++) a = fmaf(w[i * 5 + j], in[(r + i) * 7 + c + j], a);
+              acc[r * 3 + c] = a;
+            }
         }
+        __syncthreads();
       }
       if (d < nd) {
 #pragma unroll
-        for (int q = 0; q < 10; q++) S.c2[d][fg + 4 * q][pos] = acc[q];
+        for (int q = 0; q < 18; q++) S.c2[d][f][q] = acc[q];
       }
     }
     __syncthreads();
