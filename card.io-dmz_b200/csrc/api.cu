@@ -339,6 +339,12 @@ int b200_ctx_create(b200_ctx **out, int device_ordinal, const char *weights_dir)
   {  // E0 (expiry digit): optional weights + bilateral tables
     std::vector<float> eb;
     if (read_blob(dir + "/modelc_bf4dd6c8.bin", &eb, 74406)) {
+      // appended for expiry_kernel's layer 2: the 40 x 50 x 25 kernels regrouped by INPUT map, [k][f][28] (25 taps padded to
+      // seven 16-byte units), so that the kernels of a few input maps are one contiguous block to stage into shared memory
+      eb.resize(B200_EXPIRY_C2K_OFFSET + 50 * 40 * 28, 0.0f);
+      for (int f = 0; f < 40; f++)
+        for (int k = 0; k < 50; k++)
+          for (int t = 0; t < 25; t++) eb[B200_EXPIRY_C2K_OFFSET + ((size_t)k * 40 + f) * 28 + t] = eb[1300 + (size_t)f * 1250 + k * 25 + t];
       CU(cudaMalloc(&ctx->d_expiry, eb.size() * sizeof(float)));
       CU(cudaMemcpy(ctx->d_expiry, eb.data(), eb.size() * sizeof(float), cudaMemcpyHostToDevice));
       float color[256], space[5];

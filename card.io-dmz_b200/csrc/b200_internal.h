@@ -89,6 +89,7 @@ int launch_scan(const NetWeights &wts, const uint8_t *cards, int n, const FrameG
 int launch_finalize_records(const FrameGeom *geom, const b200_scan *scans, const unsigned int *card_check, int n,
                             b200_frame_record *recs, cudaStream_t s, uint8_t *needs_full = nullptr, int cx0 = 0, int cy0 = 0,
                             int cx1 = 0, int cy1 = 0);
+#define B200_EXPIRY_C2K_OFFSET 74408  // floats: modelc_bf4dd6c8 blob (74406) rounded up to a 16-byte boundary
 #define B200_Q8_STRIDE 528  // bytes per prepared digit patch (27 x 19 = 513 padded to 33 x 16)
 int launch_categorize_patches(const NetWeights &wts, const uint8_t *patches, const float *float_patches, int n, float *out,
                               uint8_t *q8 /* n * B200_Q8_STRIDE bytes of scratch when `patches` is given */, cudaStream_t s);

@@ -573,6 +573,7 @@ categorize_kernel(NetWeights W, const uint8_t *__restrict__ q8, b200_scan *__res
 // iteration, layer-2 weights (200 KB) streamed through shared memory one input map at a time.
 // ------------------------------------------------------------------------------------------------
 constexpr int kEDigits = 8;
+constexpr int kEStage = 5;      // input maps per staged block of layer-2 kernels
 constexpr int kEThreads = 320;  // layer 2: 8 digits x 40 output maps; layer 1: 8 x 70 pooled cells in two rounds
 
 __constant__ float c_bil_color[256];  // bilateral colour LUT / spatial weights, computed on the host (b200_tables.cpp)
@@ -583,7 +584,7 @@ struct ExpirySmem {
   float c1b[50];
   float xpad[kEDigits][24][20];   // mean-subtracted input with a 4-pixel zero border (full correlation), row stride 20
   float l1[kEDigits][50][70];     // ReLU(pool(conv1) + b)
-  float wk[2][40][25];            // layer-2 kernels of the current and the next input map (double buffer)
+  alignas(16) float wk[2][kEStage][40][28];  // layer-2 kernels of kEStage input maps, double-buffered (25 taps padded to 28)
   float c2[kEDigits][40][18];
   float l2[kEDigits][120];
   float hid[kEDigits][176];
@@ -601,7 +602,7 @@ expiry_kernel(const float *__restrict__ W /* modelc_bf4dd6c8 blob */, const uint
   extern __shared__ __align__(16) uint8_t es_raw[];
   ExpirySmem &S = *reinterpret_cast<ExpirySmem *>(es_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float *c2w = W + 1300, *c2b = W + 51300, *hw = W + 51340, *hb = W + 72460, *lw = W + 72636, *lb = W + 74396;
+  const float *c2b = W + 51300, *hw = W + 51340, *hb = W + 72460, *lw = W + 72636, *lb = W + 74396;
   for (int i = tid; i < 1250; i += kEThreads) (&S.c1w[0][0])[i] = __ldg(W + i);
   for (int i = tid; i < 50; i += kEThreads) S.c1b[i] = __ldg(W + 1250 + i);
 
@@ -716,45 +717,64 @@ expiry_kernel(const float *__restrict__ W /* modelc_bf4dd6c8 blob */, const uint
       }
     }
     // ---- layer 2 (40 x 50 x 5 x 5 valid correlation on the 10 x 7 pooled maps -> 6 x 3): thread = (output map f, digit d)
-    // with all 18 positions in registers.  Per input map k the thread pulls its 25 weights and the digit's 70 inputs
-    // into registers (60 shared-memory requests) and issues 450 FMAs on them; the kernels of map k + 1 are staged into the
-    // other half of wk meanwhile (one barrier per k).  (The first cut re-read a weight from shared memory for every FMA.)
+    // with all 18 position sums in registers.  The kernels are staged kEStage input maps at a time with cp.async from the
+    // [k][f][28] copy of the weights (double buffer: the next block is in flight during the FMAs of the current one, two
+    // barriers per block).  Per input map a thread pulls its 25 weights (7 conflict-free LDS.128) and the digit's 70 inputs
+    // (35 LDS.64) into registers and issues 450 FMAs on them.  (The first cut re-read a weight from shared memory for
+    // every FMA; reading the weights straight from global memory touched 32 cache lines per request and was L1-bound.)
     {
       const int f = tid % 40, d = tid / 40;
       float acc[18];
 #pragma unroll
       for (int q = 0; q < 18; q++) acc[q] = 0.0f;
-      auto stage = [&](int k, int buf) {
-        for (int i = tid; i < 1000; i += kEThreads) S.wk[buf][i / 25][i % 25] = __ldg(c2w + (size_t)(i / 25) * 1250 + k * 25 + (i % 25));
-      };
-      stage(0, 0);
-      __syncthreads();  // layer 1 complete, wk[0] staged
-      for (int k = 0; k < 50; k++) {
-        const int buf = k & 1;
-        if (k + 1 < 50) stage(k + 1, buf ^ 1);  // its last readers passed the barrier that ended step k - 1
-        if (d < nd) {
-          float w[25], in[70];
-#pragma unroll
-          for (int t = 0; t < 25; t++) w[t] = S.wk[buf][f][t];
-          const float2 *src = reinterpret_cast<const float2 *>(&S.l1[d][k][0]);  // (d * 50 + k) * 70 floats: 8-byte aligned
-#pragma unroll
-          for (int t = 0; t < 35; t++) {
-            const float2 v = src[t];
-            in[2 * t] = v.x, in[2 * t + 1] = v.y;
-          }
-#pragma unroll
-          for (int r = 0; r < 6; r++)
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-              float a = acc[r * 3 + c];
-#pragma unroll
-              for (int i = 0; i < 5; i++)
-#pragma unroll
-                for (int j = 0; j < 5; j++) a = fmaf(w[i * 5 + j], in[(r + i) * 7 + c + j], a);
-              acc[r * 3 + c] = a;
-            }
+      const float *c2k = W + B200_EXPIRY_C2K_OFFSET;
+      auto stage = [&](int blk) {
+        const float4 *src = reinterpret_cast<const float4 *>(c2k + (size_t)blk * kEStage * 40 * 28);
+        float4 *dst = reinterpret_cast<float4 *>(&S.wk[blk & 1][0][0][0]);
+        for (int i = tid; i < kEStage * 40 * 7; i += kEThreads) {
+          const unsigned int sa = (unsigned int)__cvta_generic_to_shared(dst + i);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src + i) : "memory");
         }
-        __syncthreads();
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      };
+      stage(0);
+      for (int blk = 0; blk < 50 / kEStage; blk++) {
+        if (blk + 1 < 50 / kEStage) {
+          stage(blk + 1);  // the other buffer: its readers passed the barrier that ended block blk - 1
+          asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+          asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();  // block blk staged by every thread (and, for blk == 0, layer 1 complete)
+        if (d < nd) {
+#pragma unroll 1
+          for (int kk = 0; kk < kEStage; kk++) {
+            const int k = blk * kEStage + kk;
+            float w[28], in[70];
+            const float4 *wsrc = reinterpret_cast<const float4 *>(&S.wk[blk & 1][kk][f][0]);
+#pragma unroll
+            for (int t = 0; t < 7; t++) {
+              const float4 v = wsrc[t];
+              w[4 * t] = v.x, w[4 * t + 1] = v.y, w[4 * t + 2] = v.z, w[4 * t + 3] = v.w;
+            }
+            const float2 *src = reinterpret_cast<const float2 *>(&S.l1[d][k][0]);  // (d * 50 + k) * 70 floats: 8-byte aligned
+#pragma unroll
+            for (int t = 0; t < 35; t++) {
+              const float2 v = src[t];
+              in[2 * t] = v.x, in[2 * t + 1] = v.y;
+            }
+            // tap-major order: the 18 position sums are independent, so consecutive FMAs never wait on each other
+#pragma unroll
+            for (int i = 0; i < 5; i++)
+#pragma unroll
+              for (int j = 0; j < 5; j++)
+#pragma unroll
+                for (int r = 0; r < 6; r++)
+#pragma unroll
+                  for (int c = 0; c < 3; c++) acc[r * 3 + c] = fmaf(w[i * 5 + j], in[(r + i) * 7 + c + j], acc[r * 3 + c]);
+          }
+        }
+        __syncthreads();  // block blk consumed
       }
       if (d < nd) {
 #pragma unroll
