@@ -532,8 +532,9 @@ vseg_select_kernel(const float *__restrict__ vprob, const uint8_t *__restrict__ 
 // H0 / H1: best_n_hseg.  One CTA per frame.
 // ------------------------------------------------------------------------------------------------
 constexpr int kHsegThreads = 256;
-constexpr int kMaxWidths = 16;
+constexpr int kMaxWidths = 8;   // widths per pass: the four (min, max, step) triples of n_hseg.cpp:110-147 give at most 6
 constexpr int kMaxCands = 1024;
+constexpr int kPatPad = 192;  // zeros in front of a pattern row: a valid candidate's offset is <= 428 - 17 * 16.3 = 151
 
 __device__ __constant__ float kNumberGradSumPattern[19] = {
     0.26228655f, 0.30289554f, 0.34632607f, 0.38725636f, 0.42745813f, 0.45875135f, 0.46498017f,
@@ -564,15 +565,17 @@ hseg_kernel(const uint8_t *__restrict__ cards, int n, b200_scan *__restrict__ sc
   b200_hseg &s_best = *reinterpret_cast<b200_hseg *>(s_best_words);
   __shared__ uint8_t s_pat[19];
   __shared__ int s_npl;
-  __shared__ float s_tpl[64];                           // the 19-tap template followed by zeros
-  __shared__ short s_centers[kHsegThreads / 8][18];     // digit centres of the candidates in flight (+ sentinel)
+  // The pattern of a candidate (width w, offset o) is the pattern of (w, 0) shifted right by o (every digit centre is
+  // o + lrintf(index * w)), so each pass builds ONE 428-float pattern row per width -- kPatPad zeros in front -- and a
+  // candidate reads it at [i - o].
+  __shared__ float s_patw[kMaxWidths][kPatPad + B200_CARD_W + 4];
+  __shared__ short s_last_center[kMaxWidths];           // centre of the last digit at offset 0: validity is o + centre + 19 < 428
 
   const int y_off = sc->vseg.y_offset;
   const uint8_t *card = cards + (size_t)f * (B200_CARD_W * B200_CARD_H) + (size_t)y_off * B200_CARD_W;
   for (int i = tid; i < 27 * B200_CARD_W / 4; i += kHsegThreads)
     reinterpret_cast<unsigned int *>(&s_strip[0][0])[i] = __ldg(reinterpret_cast<const unsigned int *>(card) + i);
   if (tid < 19) s_pat[tid] = sc->vseg.number_pattern[tid];
-  if (tid < 64) s_tpl[tid] = tid < 19 ? kNumberGradSumPattern[tid] : 0.0f;
   if (tid == 0) {
     s_npl = sc->vseg.number_pattern_length;
     s_mn = 0x7fffffff, s_mx = 0;
@@ -646,55 +649,58 @@ hseg_kernel(const uint8_t *__restrict__ cards, int n, b200_scan *__restrict__ sc
     }
     __syncthreads();
     const int total = s_pass.start[s_pass.nwidths];
+    // pattern rows of this pass: warp wi builds width wi (zeros, then the 19-tap template at every digit centre in digit
+    // order -- a later digit overwrites the overlapping tail of the previous one, as the reference's sequential copy does)
+    for (int wi = tid >> 5; wi < s_pass.nwidths; wi += kHsegThreads / 32) {
+      const int lane = tid & 31;
+      float *row = s_patw[wi];
+      for (int i = lane; i < kPatPad + B200_CARD_W + 4; i += 32) row[i] = 0.0f;
+      __syncwarp();
+      const float width = s_pass.width[wi];
+      int nd = 0, last = 0;
+      for (int pi = 0; pi < s_npl; pi++) {
+        if (s_pat[pi]) {
+          if (nd < 16) {
+            const int center = __float2int_rn((float)pi * width);
+            if (lane < 19 && center + lane < B200_CARD_W + 4) row[kPatPad + center + lane] = kNumberGradSumPattern[lane];
+            last = center;
+            __syncwarp();
+          }
+          nd++;
+        }
+      }
+      if (lane == 0) s_last_center[wi] = (short)last;
+    }
+    __syncthreads();
     unsigned long long best_key = ~0ull;
-    // eight lanes per candidate reproduce Eigen's two 4-lane packet accumulators over the 428 coefficients
+    // eight lanes per candidate reproduce Eigen's two 4-lane packet accumulators over the 428 coefficients:
+    // lane8 takes i = lane8, lane8 + 8, ...
     const int lane8 = tid & 7;
+    const float *g = s_g + lane8;
     for (int c0 = 0; c0 < total; c0 += kHsegThreads / 8) {
-      const int slot = tid >> 3;
-      const int c = c0 + slot;
+      const int c = c0 + (tid >> 3);
       float score = 0.0f;
       bool valid = c < total;
-      int nd = 0;
-      __syncthreads();  // previous round's centres consumed
+      const float *pw = s_patw[0] + kPatPad;
       if (valid) {
         int wi = 0;
         while (c >= s_pass.start[wi + 1]) wi++;
-        const float width = s_pass.width[wi];
         const int offset = s_pass.omin[wi] + (c - s_pass.start[wi]) * s_pass.ostep;
-        for (int pi = 0; pi < s_npl; pi++) {
-          if (s_pat[pi]) {
-            const int center = (uint16_t)(offset + __float2int_rn((float)pi * width));
-            if (!(center + 19 < 428)) valid = false;
-            if (nd < 16 && lane8 == 0) s_centers[slot][nd] = (short)center;
-            nd++;
-          }
-        }
-        if (nd > 16) nd = 16;
-        if (lane8 == 0) s_centers[slot][nd] = 32767;  // sentinel: no further digit
+        // every centre must satisfy centre + 19 < 428 (n_hseg.cpp:57); centres increase, so the last one decides
+        // (an offset beyond kPatPad fails that test anyway: the last centre alone is >= 16 * 16.3)
+        valid = ((offset + s_last_center[wi]) & 0xFFFF) + 19 < 428 && offset <= kPatPad;
+        pw = s_patw[wi] + (kPatPad - offset) + lane8;
       }
-      __syncthreads();
       // (valid is uniform across the eight lanes of a candidate; the shuffles stay outside any branch)
-      // Walk i = lane8, lane8 + 8, ...: `cur` is the centre of the last digit starting at or before i, `nxt` the
-      // next centre.  Centres are >= 17 apart and i advances by 8, so at most one digit boundary is crossed per step.
-      int d = 0, cur = -1000, nxt = valid ? s_centers[slot][0] : 32767;
-      auto coeff = [&](int i) -> float {
-        if (i >= nxt) {
-          cur = nxt;
-          d++;
-          nxt = s_centers[slot][d];
-        }
-        const int rel = min(i - cur, 63);  // >= 19 -> zero tail of the table
-        return fabsf(s_g[i] - s_tpl[rel]);
-      };
       float acc = 0.0f;
       if (valid) {
-        acc = coeff(lane8);
-#pragma unroll 4
-        for (int k = 1; k < 53; k++) acc = acc + coeff(8 * k + lane8);
+        acc = fabsf(g[0] - pw[0]);
+#pragma unroll
+        for (int k = 1; k < 53; k++) acc = acc + fabsf(g[8 * k] - pw[8 * k]);
       }
       const float hi = __shfl_down_sync(0xffffffffu, acc, 4, 8);
       float r = acc + hi;                                         // packet_res0 + packet_res1
-      if (valid && lane8 < 4) r = r + coeff(424 + lane8);         // the 107th packet
+      if (valid && lane8 < 4) r = r + fabsf(g[424] - pw[424]);    // the 107th packet
       const float r2 = __shfl_down_sync(0xffffffffu, r, 2, 8);
       const float t = r + r2;                                     // lanes 0,1: (r0 + r2), (r1 + r3)
       const float t1 = __shfl_down_sync(0xffffffffu, t, 1, 8);
