@@ -587,6 +587,7 @@ hseg_kernel(const uint8_t *__restrict__ cards, int n, b200_scan *__restrict__ sc
   __syncthreads();
 
   // llcv_morph_grad3_2d_cross_u8 on the isolated 428 x 27 strip (cv/morph.cpp:177-255), then cvReduce column sums
+  int cmn = 0x7fffffff, cmx = 0;
   for (int x = tid; x < B200_CARD_W; x += kHsegThreads) {
     const int xl = x > 0 ? x - 1 : x, xr = x < B200_CARD_W - 1 ? x + 1 : x;
     int acc = 0;
@@ -597,9 +598,14 @@ hseg_kernel(const uint8_t *__restrict__ cards, int n, b200_scan *__restrict__ sc
       acc += mx - mn;
     }
     s_isum[x] = acc;
-    atomicMin(&s_mn, acc);
-    atomicMax(&s_mx, acc);
+    cmn = min(cmn, acc), cmx = max(cmx, acc);
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    cmn = min(cmn, __shfl_xor_sync(0xffffffffu, cmn, o));
+    cmx = max(cmx, __shfl_xor_sync(0xffffffffu, cmx, o));
+  }
+  if ((tid & 31) == 0) atomicMin(&s_mn, cmn), atomicMax(&s_mx, cmx);  // one pair of atomics per warp
   __syncthreads();
   {
     // cvNormalize(MINMAX, 0, 1): scale / shift in double, applied as float multiply then float add
@@ -611,8 +617,35 @@ hseg_kernel(const uint8_t *__restrict__ cards, int n, b200_scan *__restrict__ sc
   }
   __syncthreads();
 
+  // thread 0, after a pass: fold the pass's best candidate (s_red) into s_best.  Runs right before the same thread
+  // sets up the next pass, so the two single-thread sections share one barrier interval.
+  auto update_best = [&]() {
+      unsigned long long k = ~0ull;
+      for (int i = 0; i < kHsegThreads / 32; i++) k = s_red[i] < k ? s_red[i] : k;
+      if (k != ~0ull) {
+        const float score = __uint_as_float((unsigned)(k >> 32));
+        const int c = (int)(k & 0xFFFFFFFFu);
+        if (score < s_best.score) {
+          int wi = 0;
+          while (c >= s_pass.start[wi + 1]) wi++;
+          const float width = s_pass.width[wi];
+          const int offset = s_pass.omin[wi] + (c - s_pass.start[wi]) * s_pass.ostep;
+          int oi = 0;
+          for (int i = 0; i < 16; i++) s_best.offsets[i] = 0;
+          for (int pi = 0; pi < s_npl; pi++)
+            if (s_pat[pi]) {
+              if (oi < 16) s_best.offsets[oi] = (uint16_t)(offset + __float2int_rn((float)pi * width));
+              oi++;
+            }
+          s_best.score = score;
+          s_best.number_width = width;
+          s_best.pattern_offset = (uint16_t)offset;
+        }
+      }
+  };
   for (int pass = 0; pass < 4; pass++) {
     if (tid == 0) {
+      if (pass > 0) update_best();
       float wmin, wmax, wstep;
       unsigned omin, omax, ostep;
       const b200_hseg &b = s_best;
@@ -718,32 +751,9 @@ hseg_kernel(const uint8_t *__restrict__ cards, int n, b200_scan *__restrict__ sc
     }
     if ((tid & 31) == 0) s_red[tid >> 5] = best_key;
     __syncthreads();
-    if (tid == 0) {
-      unsigned long long k = ~0ull;
-      for (int i = 0; i < kHsegThreads / 32; i++) k = s_red[i] < k ? s_red[i] : k;
-      if (k != ~0ull) {
-        const float score = __uint_as_float((unsigned)(k >> 32));
-        const int c = (int)(k & 0xFFFFFFFFu);
-        if (score < s_best.score) {
-          int wi = 0;
-          while (c >= s_pass.start[wi + 1]) wi++;
-          const float width = s_pass.width[wi];
-          const int offset = s_pass.omin[wi] + (c - s_pass.start[wi]) * s_pass.ostep;
-          int oi = 0;
-          for (int i = 0; i < 16; i++) s_best.offsets[i] = 0;
-          for (int pi = 0; pi < s_npl; pi++)
-            if (s_pat[pi]) {
-              if (oi < 16) s_best.offsets[oi] = (uint16_t)(offset + __float2int_rn((float)pi * width));
-              oi++;
-            }
-          s_best.score = score;
-          s_best.number_width = width;
-          s_best.pattern_offset = (uint16_t)offset;
-        }
-      }
-    }
-    __syncthreads();
   }
+  if (tid == 0) update_best();
+  __syncthreads();
   if (tid < 12) reinterpret_cast<unsigned int *>(&sc->hseg)[tid] = s_best_words[tid];
 }
 
