@@ -167,9 +167,11 @@ int ensure_capacity(b200_ctx *ctx, Lane *l, int n, int w, int h, bool need_frame
     l->frame_bytes = keep_bytes;
     CU(cudaMalloc(&l->d_lines, sizeof(b200_line) * 3 * (size_t)n * 4));
     CU(cudaMalloc(&l->d_geom, sizeof(FrameGeom) * (size_t)n));
+    CU(cudaMemset(l->d_geom, 0, sizeof(FrameGeom) * (size_t)n));  // struct padding is copied to the host with the records
     CU(cudaMalloc(&l->d_cards, kCardBytes * (size_t)n));
     CU(cudaMalloc(&l->d_vprob, (size_t)n * (540 * sizeof(float) + 16)));
     CU(cudaMalloc(&l->d_q8, (size_t)n * 16 * B200_Q8_STRIDE));
+    CU(cudaMemset(l->d_q8, 0, (size_t)n * 16 * B200_Q8_STRIDE));  // the CNN kernel prefetches all 16 slots of a frame, written or not
     CU(cudaMalloc(&l->d_scan, sizeof(b200_scan) * (size_t)n));
     CU(cudaMalloc(&l->d_records, sizeof(b200_frame_record) * (size_t)n));
     CU(cudaMalloc(&l->d_check, sizeof(unsigned int) * (size_t)n));
@@ -801,6 +803,7 @@ int b200_best_expiry_seg_batch(b200_ctx *ctx, const uint8_t *cards, const uint16
       dc = base + o_cards, dy = (const uint16_t *)(base + o_yo), dg = (b200_expiry_group *)(base + o_grp);
       dn = (int32_t *)(base + o_cnt), dd = dn + chunk;
     }
+    if (host) CU(cudaMemsetAsync(dg, 0, sizeof(b200_expiry_group) * (size_t)max_groups * cnt, ctx->stream));  // unused slots are copied back too
     LAUNCH(launch_expiry_seg(dc, dy, cnt, ctx->d_slash, d_sob, d_ls, dg, max_groups, dn, dd, ctx->stream));
     if (host) {
       CU(cudaMemcpyAsync(groups + (size_t)f0 * max_groups, dg, sizeof(b200_expiry_group) * (size_t)max_groups * cnt, cudaMemcpyDeviceToHost, ctx->stream));

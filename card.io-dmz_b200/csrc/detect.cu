@@ -300,6 +300,9 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
   // ---- 5. hysteresis: a candidate 8-connected to an edge pixel becomes an edge pixel; iterate over the (short)
   // candidate list to the fixed point, which is the reference's stack-walk result whatever the visiting order.
   // A promoted candidate is queued for voting on the spot (each candidate is promoted exactly once).
+  // Within one sweep a thread may read a neighbour's map byte while its owner promotes it (racecheck reports that
+  // read/write pair as a warning): the byte only ever goes 0 -> 2, a stale 0 just defers the promotion to the next sweep,
+  // and the loop ends only after a sweep without any promotion, so the fixed point does not depend on the interleaving.
   {
     const int ncand = s_ncand;
     if (ncand <= list_cap) {

@@ -398,6 +398,7 @@ digit_prep_kernel(const uint8_t *__restrict__ cards, const b200_scan *__restrict
     const int y = i / 19, x = i - y * 19;
     dst[i] = P.lut[P.g8[y * 20 + x]];
   }
+  if (lane < kQStride - 27 * 19) dst[27 * 19 + lane] = 0;  // the padding is fetched (and ignored) by the CNN kernel
 }
 
 // C2 on prepared patches.  One CTA (16 warps) per SM, persistent over groups (= one frame's 16 digit slots, or 16 raw
@@ -611,6 +612,7 @@ expiry_kernel(const float *__restrict__ W /* modelc_bf4dd6c8 blob */, const uint
     const int nd = min(kEDigits, n - grp * kEDigits);
     __syncthreads();
     for (int i = tid; i < kEDigits * 24 * 20; i += kEThreads) (&S.xpad[0][0][0])[i] = 0.0f;
+    __syncthreads();  // the preparation warps write the interior of xpad: every zero must have landed first
     // ---- patch preparation: one warp per digit
     if (warp < nd) {
       const int d = warp;

@@ -13,6 +13,10 @@ d.detect_edges(fr[:2], np.ascontiguousarray(fr[:2, ::2, ::2]), np.full((2, 240, 
 d.scan_cards(c[:3]); d.categorize_patches(c[0][150:177, 30:49][None]); d.vseg_model(np.zeros((3, 204), np.float32))
 d.set_crop_margin(-1); d.process_frames(fr[:3])
 big = deck_frames(0, 1, 1920, 1080); d.process_frames(big)
+rng = np.random.default_rng(0)
+d.expiry_digits(rng.integers(0, 256, (11, 16, 11)).astype(np.uint8))
+d.frame_scores(fr[:2])
+d.best_expiry_seg(c[:2], r["v_y_offset"][:2].astype(np.uint16))
 print("ok", r["all_found"].sum())
 PY
 for tool in memcheck racecheck initcheck; do
