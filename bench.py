@@ -120,6 +120,23 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Multi-rank runs: move this rank onto the CPUs next to its GPU before any pinned host memory is allocated, so the
+    e2e leg's host buffers sit on the GPU's own NUMA node (with all ranks on one socket half of the H2D traffic crosses
+    the inter-socket link).  Best effort: a cpuset that does not include those CPUs leaves the affinity as it was."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+        h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        before = len(os.sched_getaffinity(0))
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return {"cpus_before": before, "cpus_after": len(os.sched_getaffinity(0))}
+    except Exception as e:  # noqa: BLE001 -- reported in the JSON line, never fatal
+        return {"unchanged": str(e)[:120]}
+
+
 def reference_arm(args, rank, world):
     """The reference's own CPU implementation of the path, all host threads, bounded sample per step."""
     if rank != 0:
@@ -179,6 +196,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
@@ -277,7 +295,7 @@ def main():
                "d2h_bytes_per_step": (d2h1 - d2h0) // args.steps, "frames_per_step": Fe, "records_equal_device_path": same,
                "host_frame_bytes_per_step": Fe * FRAME_BYTES, "full_frame_redos": dmz.full_frame_redos,
                "note": "host frames are full 640x480 planes in pinned memory; the library uploads only the detection-region rectangle (+8 px) of each and re-uploads a whole frame if its card quad reaches outside it",
-               "timing": "wall clock around the synchronous C-ABI calls, max over ranks"}
+               "timing": "wall clock around the synchronous C-ABI calls, max over ranks", "rank0_cpu_binding": numa}
 
     # ---- BASELINE configs[0]: ONE frame through the whole path (latency of a batch of one through the C ABI, host
     # buffers, copies and the final synchronisation inside) -- outside the throughput timing, rank 0 only

@@ -66,7 +66,7 @@ def test_sessions_read_the_true_number(pkg, full):
 
 def test_random_sample_against_oracle(oracle, full):
     frames, _, r = full
-    idx = np.sort(np.random.default_rng(0).choice(N, size=min(96, N), replace=False))
+    idx = np.sort(np.random.default_rng(0).choice(N, size=min(256, N), replace=False))
     host = frames[idx.tolist()].cpu().numpy()
     want = oracle.process_frames(host)
     got = r[idx]
@@ -83,3 +83,46 @@ def test_host_buffer_path_equals_device_path(dmz, pkg, full):
     host = frames[:n].cpu().numpy()
     got = dmz.process_frames(host)
     assert np.array_equal(got.view(np.uint8).reshape(n, 808), recs[:n].cpu().numpy())
+
+
+def test_categorize_only_at_scale(dmz, oracle):
+    """BASELINE configs[2] (n_categorize alone), reduced to 2^18 patches (B200_FULLSIZE_PATCHES overrides): half i.i.d. noise, half crops with digit-like
+    structure.  Size-independent properties (rows of every model are distributions, the ensemble is (r0+r1+r2-max)/2 of
+    them, results do not depend on how the batch is cut) plus a random sample against the oracle."""
+    n = int(os.environ.get("B200_FULLSIZE_PATCHES", str(1 << 18)))
+    rng = np.random.default_rng(5)
+    patches = rng.integers(0, 256, (n, 27, 19), dtype=np.uint8)
+    yy, xx = np.mgrid[0:27, 0:19]
+    for i in range(n // 2, n, max(1, n // 1024)):  # some hundred structured patches spread over the second half
+        cx, cy, r = rng.uniform(5, 13), rng.uniform(8, 18), rng.uniform(3, 8)
+        ring = np.abs(np.hypot(xx - cx, (yy - cy) * 0.8) - r) < 1.5
+        patches[i] = np.where(ring, 210, 60).astype(np.uint8) + rng.integers(0, 20, (27, 19)).astype(np.uint8)
+    ens, per_model = dmz.categorize_patches(patches)
+    assert ens.shape == (n, 10) and np.isfinite(ens).all()
+    assert np.abs(per_model.sum(2) - 1).max() < 1e-5
+    want = (per_model.sum(1) - per_model.max(1)) / 2.0
+    assert np.abs(ens - want).max() < 1e-6
+    lo, cnt = n // 3 + 5, 1001  # a ragged slice on its own: byte-identical
+    e2, p2 = dmz.categorize_patches(patches[lo:lo + cnt])
+    assert np.array_equal(e2, ens[lo:lo + cnt]) and np.array_equal(p2, per_model[lo:lo + cnt])
+    idx = np.sort(rng.choice(n, size=96, replace=False))
+    for i in idx:
+        e, m = oracle.digit_models(oracle.digit_patch_prep(patches[i]))
+        assert np.abs(e - ens[i]).max() <= 1e-4 and np.abs(m - per_model[i]).max() <= 1e-4, i
+
+
+def test_expiry_digits_at_scale(dmz, oracle):
+    """E0 at 2^15 crops: run-to-run determinism (the kernel keeps eight crops in flight per CTA), batch invariance,
+    and a random sample against the oracle."""
+    n = 1 << 15
+    rng = np.random.default_rng(9)
+    crops = rng.integers(0, 256, (n, 16, 11), dtype=np.uint8)
+    crops[: n // 2] = (crops[: n // 2] // 40) * 40  # few grey levels
+    a = dmz.expiry_digits(crops)
+    assert np.array_equal(a, dmz.expiry_digits(crops))
+    assert np.abs(a.sum(1) - 1).max() < 1e-5
+    lo, cnt = 12345, 777
+    assert np.array_equal(dmz.expiry_digits(crops[lo:lo + cnt]), a[lo:lo + cnt])
+    idx = np.sort(rng.choice(n, size=48, replace=False))
+    for i in idx:
+        assert np.abs(a[i] - oracle.expiry_digit_model(oracle.expiry_patch_prep(crops[i]))).max() <= 1e-4, i
