@@ -26,6 +26,7 @@
 namespace {
 
 constexpr int kThreads = 416;  // 13 warps: one Sobel work item per thread for the 389-wide strips
+constexpr int kWarps = kThreads / 32;
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
@@ -86,7 +87,9 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
                      b200_line *__restrict__ lines, int16_t *__restrict__ grad_scratch, size_t grad_scratch_stride, int ox, int oy) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __shared__ unsigned long long s_red[kThreads / 32];
-  __shared__ int s_low, s_high, s_ncand, s_nvote, s_nedge, s_overflow;
+  __shared__ int s_low, s_high, s_nvote, s_nedge, s_overflow;
+  __shared__ unsigned short s_q[kWarps][64];  // per-warp ring of pixels whose magnitude exceeds the low threshold
+  __shared__ int s_cpre[kWarps + 1];          // per-warp candidate counts, then their exclusive prefix
 
   const int strip = blockIdx.x;
   const int frame = blockIdx.y;
@@ -130,10 +133,12 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
   L.map = smem_raw + off;
   off = align16(off + (size_t)npad);
   L.acc = reinterpret_cast<unsigned int *>(smem_raw + off);
-  // work lists alias the (by then dead) source strip: candidates in the first half, votes in the second
+  // work lists alias the (by then dead) source strip: one candidate segment per warp (filled without atomics), then
+  // the vote list; overflow falls back to full scans
   L.list = reinterpret_cast<unsigned short *>(L.src);
-  const int list_cap = (ws * h) >> 2;  // entries per list; overflow falls back to full scans
-  unsigned short *vote_list = L.list + list_cap;
+  const int cand_cap = (((ws * h) >> 1) * 3 / 5) / kWarps;  // entries per warp segment
+  unsigned short *vote_list = L.list + cand_cap * kWarps;
+  const int list_cap = ((ws * h) >> 1) - cand_cap * kWarps;  // entries of the vote list
 
   // ---- 1. load the strip (32-bit coalesced loads of the covering aligned words); clear borders / accumulator
   {
@@ -166,7 +171,7 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
     L.dx[a] = 0, L.dy[a] = 0, L.map[a] = 1;
     L.dx[b] = 0, L.dy[b] = 0, L.map[b] = 1;
   }
-  if (tid == 0) s_ncand = 0, s_nvote = 0, s_nedge = 0, s_overflow = 0;
+  if (tid == 0) s_nvote = 0, s_nedge = 0, s_overflow = 0;
   __syncthreads();
   // BORDER_REPLICATE halo: three copies of the first / last pixel of every row
   for (int y = tid; y < h; y += kThreads) {
@@ -254,62 +259,109 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
   int n_edge = 0;
 
   // ---- 4. non-maxima suppression, canny.cpp:220-285.  The source strip is dead now: weak candidates go to the
-  // hysteresis work list, strong pixels (edges for sure) to the vote list (the direction gate is applied when voting).
-  // Nearly every warp holds pixels of all three direction sectors, so the sector is turned into a neighbour OFFSET
-  // by selects and both neighbour magnitudes are fetched unconditionally: one straight-line body instead of three
-  // divergent ones.  Pixels are dealt round-robin over the flat index (x, y advance without a division).
+  // hysteresis work lists, strong pixels (edges for sure) to the vote list (the direction gate is applied when voting).
+  // Two steps per warp, no block barrier between them.  Step 1, every pixel (flat round-robin walk, x and y advance
+  // without a division): |dx| + |dy| against the low threshold; the ~45 % that pass are queued in a 64-entry ring of
+  // the warp (ballot + popc, no atomics).  Step 2, whenever 32 are queued: the direction test on 32 DENSE lanes -- the
+  // sector becomes a neighbour OFFSET by selects and both neighbour magnitudes are fetched, one straight-line body.
+  // (Testing every pixel in place made all 32 lanes pay for the 45 %; branching per pixel made every warp pay for all
+  // three sectors.)  Weak candidates are appended to the warp's own list segment, again without atomics.
   {
+    const int lane = tid & 31, wid = tid >> 5;
+    const unsigned int lt = (1u << lane) - 1u;
+    unsigned short *q = s_q[wid];
+    unsigned short *clist = L.list + wid * cand_cap;
+    int qhead = 0, qtail = 0, ccount = 0;
+    auto mag = [&](int j) -> int { return abs((int)L.dx[j]) + abs((int)L.dy[j]); };
+    auto direction_test = [&](int cnt) {  // the first cnt queued pixels, one per lane
+      bool weak = false, strong = false;
+      int o = 0;
+      if (lane < cnt) {
+        o = q[(qhead + lane) & 63];
+        const int gx = L.dx[o], gy = L.dy[o];
+        // the reference's int64 products fit in 32 unsigned bits here: |dx|, |dy| <= 32768 after the s16 saturation,
+        // so tg22x <= 4.5e8, tg67x <= 2.6e9 < 2^32, ys <= 2^30
+        const unsigned int ax = (unsigned)abs(gx), ay = (unsigned)abs(gy);
+        const int m = (int)(ax + ay);
+        const unsigned int tg22x = ax * 13573u;  // TG22 = (int)(0.41421356 * 2^15 + 0.5)
+        const unsigned int tg67x = tg22x + (ax << 16);
+        const unsigned int ys = ay << 15;
+        const bool horiz = ys < tg22x, vert = ys > tg67x;
+        // horizontal: m > left && m >= right; vertical: m > up && m >= down; diagonal: m > both, along the gradient sign
+        const int sgn = ((gx ^ gy) < 0) ? -1 : 1;
+        const int off = horiz ? 1 : (vert ? wp : wp + sgn);
+        const int ge = (horiz || vert) ? 1 : 0;
+        const bool is_max = m > mag(o - off) && m + ge > mag(o + off);
+        strong = is_max && m > high;
+        weak = is_max && !strong;
+        L.map[o] = is_max ? (strong ? 2 : 0) : 1;
+      }
+      const unsigned int wm = __ballot_sync(0xffffffffu, weak);
+      if (weak) {
+        const int slot = ccount + __popc(wm & lt);
+        if (slot < cand_cap) clist[slot] = (unsigned short)o;
+        else s_overflow = 1;
+      }
+      ccount += __popc(wm);
+      if (strong) {
+        n_edge++;
+        push_vote(o);
+      }
+    };
     const int ystep = kThreads / w, xstep = kThreads - ystep * w;
     int y = tid / w, x = tid - y * w;
-    auto mag = [&](int j) -> int { return abs((int)L.dx[j]) + abs((int)L.dy[j]); };
-    for (; y < h;) {
-      const int o = (y + 1) * wp + x + 1;
-      const int gx = L.dx[o], gy = L.dy[o];
-      // the reference's int64 products fit in 32 unsigned bits here: |dx|, |dy| <= 32768 after the s16 saturation,
-      // so tg22x <= 4.5e8, tg67x <= 2.6e9 < 2^32, ys <= 2^30
-      const unsigned int ax = (unsigned)abs(gx), ay = (unsigned)abs(gy);
-      const int m = (int)(ax + ay);
-      const unsigned int tg22x = ax * 13573u;  // TG22 = (int)(0.41421356 * 2^15 + 0.5)
-      const unsigned int tg67x = tg22x + (ax << 16);
-      const unsigned int ys = ay << 15;
-      const bool horiz = ys < tg22x, vert = ys > tg67x;
-      // horizontal: m > left && m >= right; vertical: m > up && m >= down; diagonal: m > both, along the gradient sign
-      const int sgn = ((gx ^ gy) < 0) ? -1 : 1;
-      const int off = horiz ? 1 : (vert ? wp : wp + sgn);
-      const int ge = (horiz || vert) ? 1 : 0;
-      const bool is_max = m > mag(o - off) && m + ge > mag(o + off);
-      const bool cand = is_max && m > low;
-      const bool strong = cand && m > high;
-      L.map[o] = cand ? (strong ? 2 : 0) : 1;
-      if (cand) {
-        if (strong) {
-          n_edge++;
-          push_vote(o);
-        } else {
-          const int slot = atomicAdd(&s_ncand, 1);
-          if (slot < list_cap) L.list[slot] = (unsigned short)o;
-          else s_overflow = 1;
-        }
+    const int iters = (npx + kThreads - 1) / kThreads;  // the same trip count for every lane: the loop holds warp votes
+    for (int it = 0; it < iters; it++) {
+      bool pend = false;
+      int o = 0;
+      if (y < h) {
+        o = (y + 1) * wp + x + 1;
+        pend = mag(o) > low;
+        if (!pend) L.map[o] = 1;
+      }
+      const unsigned int pm = __ballot_sync(0xffffffffu, pend);
+      if (pend) q[(qtail + __popc(pm & lt)) & 63] = (unsigned short)o;
+      qtail += __popc(pm);
+      if (qtail - qhead >= 32) {
+        __syncwarp();  // queue entries visible
+        direction_test(32);
+        qhead += 32;
+        __syncwarp();  // entries consumed before the ring wraps onto them
       }
       x += xstep, y += ystep;
       if (x >= w) x -= w, y++;
     }
+    __syncwarp();
+    if (qtail > qhead) direction_test(qtail - qhead);
+    if (lane == 0) s_cpre[wid] = min(ccount, cand_cap);
+  }
+  __syncthreads();
+  if (tid == 0) {  // exclusive prefix of the per-warp candidate counts
+    int run = 0;
+    for (int i = 0; i < kWarps; i++) {
+      const int c = s_cpre[i];
+      s_cpre[i] = run;
+      run += c;
+    }
+    s_cpre[kWarps] = run;
   }
   __syncthreads();
 
   // ---- 5. hysteresis: a candidate 8-connected to an edge pixel becomes an edge pixel; iterate over the (short)
-  // candidate list to the fixed point, which is the reference's stack-walk result whatever the visiting order.
+  // candidate lists to the fixed point, which is the reference's stack-walk result whatever the visiting order.
   // A promoted candidate is queued for voting on the spot (each candidate is promoted exactly once).
   // Within one sweep a thread may read a neighbour's map byte while its owner promotes it (racecheck reports that
   // read/write pair as a warning): the byte only ever goes 0 -> 2, a stale 0 just defers the promotion to the next sweep,
   // and the loop ends only after a sweep without any promotion, so the fixed point does not depend on the interleaving.
   {
-    const int ncand = s_ncand;
-    if (ncand <= list_cap) {
+    if (!s_overflow) {
+      const int ncand = s_cpre[kWarps];
       while (true) {
         int changed = 0;
         for (int c = tid; c < ncand; c += kThreads) {
-          const int o = L.list[c];
+          int seg = 0;
+          while (c >= s_cpre[seg + 1]) seg++;
+          const int o = L.list[seg * cand_cap + (c - s_cpre[seg])];
           const uint8_t *m = L.map + o;
           if (*m != 0) continue;
           const bool hit = m[-wp - 1] == 2 || m[-wp] == 2 || m[-wp + 1] == 2 || m[-1] == 2 || m[1] == 2 || m[wp - 1] == 2 ||
@@ -324,7 +376,7 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
         if (!__syncthreads_or(changed)) break;
       }
     } else {
-      // more candidates than list slots (pathological texture): sweep the whole map instead
+      // a candidate segment overflowed (pathological texture): sweep the whole map instead
       const Walk k = make_walk(tid, w, kThreads);
       while (true) {
         int changed = 0;
