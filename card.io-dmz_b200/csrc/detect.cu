@@ -88,7 +88,6 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __shared__ unsigned long long s_red[kThreads / 32];
   __shared__ int s_low, s_high, s_nvote, s_nedge, s_overflow;
-  __shared__ unsigned short s_q[kWarps][64];  // per-warp ring of pixels whose magnitude exceeds the low threshold
   __shared__ int s_cpre[kWarps + 1];          // per-warp candidate counts, then their exclusive prefix
 
   const int strip = blockIdx.x;
@@ -133,6 +132,10 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
   L.map = smem_raw + off;
   off = align16(off + (size_t)npad);
   L.acc = reinterpret_cast<unsigned int *>(smem_raw + off);
+  off = align16(off + (size_t)S.ncells * 4);
+  // per-warp rings of pixels whose magnitude exceeds the low threshold (64 entries each), in the dynamic block so that
+  // their addresses derive from the same base register as everything else
+  unsigned short *q_rings = reinterpret_cast<unsigned short *>(smem_raw + off);
   // work lists alias the (by then dead) source strip: one candidate segment per warp (filled without atomics), then
   // the vote list; overflow falls back to full scans
   L.list = reinterpret_cast<unsigned short *>(L.src);
@@ -269,7 +272,7 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
   {
     const int lane = tid & 31, wid = tid >> 5;
     const unsigned int lt = (1u << lane) - 1u;
-    unsigned short *q = s_q[wid];
+    unsigned short *q = q_rings + wid * 64;
     unsigned short *clist = L.list + wid * cand_cap;
     int qhead = 0, qtail = 0, ccount = 0;
     auto mag = [&](int j) -> int { return abs((int)L.dx[j]) + abs((int)L.dy[j]); };
@@ -312,13 +315,11 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
     int y = tid / w, x = tid - y * w;
     const int iters = (npx + kThreads - 1) / kThreads;  // the same trip count for every lane: the loop holds warp votes
     for (int it = 0; it < iters; it++) {
-      bool pend = false;
-      int o = 0;
-      if (y < h) {
-        o = (y + 1) * wp + x + 1;
-        pend = mag(o) > low;
-        if (!pend) L.map[o] = 1;
-      }
+      // (lanes past the end of the strip re-read its last row and are masked out: no branch around the loads)
+      const bool in_strip = y < h;
+      const int o = (min(y, h - 1) + 1) * wp + x + 1;
+      const bool pend = in_strip && mag(o) > low;
+      if (in_strip && !pend) L.map[o] = 1;
       const unsigned int pm = __ballot_sync(0xffffffffu, pend);
       if (pend) q[(qtail + __popc(pm & lt)) & 63] = (unsigned short)o;
       qtail += __popc(pm);
@@ -479,7 +480,7 @@ size_t detect_smem_bytes(const DetectParams &p) {
     const size_t ws = (size_t)detect_src_stride(d.w);
     size_t b = align16(ws * d.h) + align16(npad);  // padded src (later the work lists), map
     if (!p.use_global_grad) b += 2 * align16(npad * 2);
-    b += (size_t)d.ncells * 4 + 64;
+    b += align16((size_t)d.ncells * 4) + (size_t)kWarps * 64 * 2 + 64;  // accumulator, per-warp rings
     worst = b > worst ? b : worst;
   }
   return worst;
