@@ -26,6 +26,11 @@ namespace {
 
 constexpr int kCardBytes = B200_CARD_W * B200_CARD_H;
 
+// tanh x = 1 - 2 / (exp(2x) + 1) on the special-function unit: ex2.approx and rcp.approx are good to ~2^-22 relative,
+// the result to ~2e-7 ABSOLUTE (the same order as tanhf's own 2 ulp near +-1); saturates to +-1 for large |x|.
+// tanhf costs ~22 instructions, this 6; used by the digit CNNs (1e-4 contract on probabilities), not by vseg (index).
+__device__ __forceinline__ float tanh_sfu(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
+
 // conv kernels and post-pool biases of the three digit CNNs: [model][kernel][9] and [model][kernel]
 __constant__ float c_conv_w[3][8][9];
 __constant__ float c_conv_b[3][8];
@@ -231,7 +236,7 @@ vseg_rows_kernel(const float *__restrict__ wts, const uint8_t *__restrict__ card
       const float b = S.b1[u], w20 = S.w2[0][u], w21 = S.w2[1][u], w22 = S.w2[2][u];
 #pragma unroll
       for (int i = 0; i < 4; i++) {
-        const float hv = tanhf(acc[i][j] + b);
+        const float hv = tanhf(acc[i][j] + b);  // feeds an arg-max index: keep the accurate version
         o[i][0] = fmaf(w20, hv, o[i][0]);
         o[i][1] = fmaf(w21, hv, o[i][1]);
         o[i][2] = fmaf(w22, hv, o[i][2]);
@@ -316,7 +321,7 @@ __device__ __forceinline__ void conv_pool_four(int m, const float (&win)[5][5], 
           for (int j = 0; j < 3; j++) acc = fmaf(c_conv_w[m][k][i * 3 + j], win[r + i][c + j], acc);
         best = fmaxf(best, acc);
       }
-    feat_cell[k * 40] = tanhf(best + c_conv_b[m][k]);
+    feat_cell[k * 40] = tanh_sfu(best + c_conv_b[m][k]);
   }
 }
 
@@ -524,7 +529,7 @@ categorize_kernel(NetWeights W, const uint8_t *__restrict__ q8, b200_scan *__res
           float sum = 0.0f;
 #pragma unroll
           for (int q = 0; q < 16; q++) sum += S.work.part[q][d][u];
-          S.work.hid[d][m][u] = tanhf(sum + S.hb[m][u]);
+          S.work.hid[d][m][u] = tanh_sfu(sum + S.hb[m][u]);
         }
       }
       // (feat is rewritten by the next model's conv only after the barrier below; part after the one above)
