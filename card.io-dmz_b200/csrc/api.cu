@@ -59,6 +59,7 @@ struct b200_ctx {
   float *d_vseg = nullptr;
   float *d_cnn[3] = {nullptr, nullptr, nullptr};
   float *d_hwT = nullptr;
+  float *d_vnorm = nullptr;   // (min, max) -> scale / shift table of the vseg row normalisation
   float *d_expiry = nullptr;  // modelc_bf4dd6c8 blob (optional: E0 entry points need it)
   float *d_slash = nullptr;   // modelm_730c4cbd blob (optional: b200_best_expiry_seg_batch needs it)
   NetWeights wts{};
@@ -361,6 +362,13 @@ int b200_ctx_create(b200_ctx **out, int device_ordinal, const char *weights_dir)
   ctx->wts.vseg = ctx->d_vseg;
   for (int m = 0; m < 3; m++) ctx->wts.cnn[m] = ctx->d_cnn[m];
   ctx->wts.cnn_hwT = ctx->d_hwT;
+  {
+    std::vector<float> tab(256 * 256 * 2);
+    b200_build_minmax_norm_table(tab.data());
+    CU(cudaMalloc(&ctx->d_vnorm, tab.size() * sizeof(float)));
+    CU(cudaMemcpy(ctx->d_vnorm, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  ctx->wts.vseg_norm = ctx->d_vnorm;
   return B200_OK;
 }
 
@@ -375,6 +383,7 @@ void b200_ctx_destroy(b200_ctx *ctx) {
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   cudaFree(ctx->d_misc);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  cudaFree(ctx->d_vnorm);
   cudaFree(ctx->d_vseg), cudaFree(ctx->d_hwT), cudaFree(ctx->d_expiry), cudaFree(ctx->d_slash);
   for (int m = 0; m < 3; m++) cudaFree(ctx->d_cnn[m]);
   delete ctx;

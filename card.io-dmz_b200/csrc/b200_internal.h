@@ -71,6 +71,7 @@ struct NetWeights {  // device pointers
   const float *vseg;     // modelm_befe75da blob: hidden W 50x204, hidden b 50, logistic W 3x50, logistic b 3
   const float *cnn[3];   // modelc blobs: conv W 8x9, conv b 8, hidden W 32x320, hidden b 32, logistic W 10x32, b 10
   const float *cnn_hwT;  // 3 x [320][32] transposed hidden weights (built on the host)
+  const float *vseg_norm;  // [256][256][2]: cvNormalize(MINMAX 0..1) scale / shift of a row whose 8-bit min / max are (mn, mx)
 };
 
 // launchers (each returns the number of kernels it launched, or -1 after setting a CUDA error)
@@ -105,6 +106,7 @@ int launch_frame_scores(const uint8_t *frames, int row_stride, size_t frame_stri
 void b200_scoring_rect(int w, int h, int use_full_image, int rect[4]);  // b200_tables.cpp
 int launch_expiry_digits(const float *weights, const uint8_t *patches, const float *prepared, int n, float *out, cudaStream_t s,
                          const int32_t *where = nullptr);
+void b200_build_minmax_norm_table(float *table /* 256 * 256 * 2 */);  // b200_tables.cpp
 void b200_build_bilateral_tables(float *color256, float *space5);  // b200_tables.cpp  // __constant__ conv kernels / biases (nets.cu)
 
 size_t detect_smem_bytes(const DetectParams &p);

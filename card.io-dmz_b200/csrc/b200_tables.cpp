@@ -165,6 +165,23 @@ void b200_build_geom_params(int width, int height, int orientation, int n_planes
 // space_sigma, color_sigma) == cv::bilateralFilter(d = 3, sigmaColor = space_sigma, sigmaSpace = color_sigma)
 // -- the reference's variable names are swapped relative to OpenCV's parameter order.  Colour LUT and the
 // five in-circle spatial weights (mask order N, W, C, E, S) as imgproc/smooth.cpp builds them: (float)exp(double).
+// llcv_norm_convert_1d_u8_to_f32 (cv/convert.cpp:380-383) = cvConvertScale(1/255) then cvNormalize(MINMAX, 0, 1): the float
+// scale and shift cv::normalize derives (in double) from the row's min and max.  A row's 8-bit values only enter through
+// their min mn and max mx, so the pair is tabulated for every (mn, mx) here -- the same IEEE operations as the reference,
+// on the host -- and the row kernel needs no double-precision arithmetic.
+void b200_build_minmax_norm_table(float *table) {
+  const float k255 = 1.0f / 255.0f;
+  for (int mn = 0; mn < 256; mn++)
+    for (int mx = 0; mx < 256; mx++) {
+      const float fmn = (float)mn * k255, fmx = (float)mx * k255;
+      const double smin = (double)fmn, smax = (double)fmx;
+      const double scale = (smax - smin > DBL_EPSILON) ? 1. / (smax - smin) : 0.0;
+      const double shift = 0.0 - smin * scale;
+      table[(mn * 256 + mx) * 2 + 0] = (float)scale;
+      table[(mn * 256 + mx) * 2 + 1] = (float)shift;
+    }
+}
+
 void b200_build_bilateral_tables(float *color256, float *space5) {
   const int aperture = 3;
   const double sigma_color = (aperture / 2.0 - 1) * 0.3 + 0.8;  // the reference's "space_sigma"

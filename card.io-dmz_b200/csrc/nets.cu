@@ -71,8 +71,8 @@ struct VsegSmem {
 // mode 0: coarse rows 0,4,..,268 of every gated frame.  mode 1: fine rows around the coarse best.
 // mode 2: raw prepared rows (stage tap): in = n x 204 floats, out = n x 3.
 __global__ void __launch_bounds__(kVThreads, 1)
-vseg_rows_kernel(const float *__restrict__ wts, const uint8_t *__restrict__ cards, const uint8_t *__restrict__ gate,
-                 const b200_scan *__restrict__ scans, int n, int mode, float *__restrict__ vprob,
+vseg_rows_kernel(const float *__restrict__ wts, const float *__restrict__ norm_tab, const uint8_t *__restrict__ cards,
+                 const uint8_t *__restrict__ gate, const b200_scan *__restrict__ scans, int n, int mode, float *__restrict__ vprob,
                  const float *__restrict__ raw_rows, float *__restrict__ raw_out) {
   extern __shared__ __align__(16) uint8_t vs_raw[];
   VsegSmem &S = *reinterpret_cast<VsegSmem *>(vs_raw);
@@ -182,12 +182,10 @@ vseg_rows_kernel(const float *__restrict__ wts, const uint8_t *__restrict__ card
           mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         }
         // cvConvertScale(1/255) then cvNormalize(MINMAX 0..1): float multiply, then float multiply + float add
+        // (scale and shift as cv::normalize derives them in double from min and max: host-built table, b200_tables.cpp)
         const float k255 = 1.0f / 255.0f;
-        const float fmn = __fmul_rn((float)mn, k255), fmx = __fmul_rn((float)mx, k255);
-        const double smin = (double)fmn, smax = (double)fmx;
-        const double scale = (smax - smin > DBL_EPSILON) ? 1. / (smax - smin) : 0.0;
-        const double shift = 0.0 - smin * scale;
-        const float fs = (float)scale, fb = (float)shift;
+        const float2 nrm = __ldg(reinterpret_cast<const float2 *>(norm_tab) + (mn * 256 + mx));
+        const float fs = nrm.x, fb = nrm.y;
 #pragma unroll
         for (int q = 0; q < 7; q++) {
           const int k = lane + 32 * q;
@@ -864,7 +862,7 @@ static int launch_vseg_rows(const NetWeights &wts, const uint8_t *cards, const u
   long long grid = (long long)num_sms();  // one persistent CTA (12 autonomous warps) per SM
   if (grid > (tiles + kVWarps - 1) / kVWarps) grid = (tiles + kVWarps - 1) / kVWarps;
   if (grid < 1) grid = 1;
-  vseg_rows_kernel<<<(int)grid, kVThreads, sizeof(VsegSmem), s>>>(wts.vseg, cards, gate, scans, n, mode, vprob, raw_rows, raw_out);
+  vseg_rows_kernel<<<(int)grid, kVThreads, sizeof(VsegSmem), s>>>(wts.vseg, wts.vseg_norm, cards, gate, scans, n, mode, vprob, raw_rows, raw_out);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
