@@ -44,8 +44,8 @@ struct b200_ctx {
   cudaStream_t stream = nullptr;  // == lane[0].stream
   std::string error;
   uint64_t launches = 0;
-  uint64_t full_frame_redos = 0;
-  uint64_t h2d_bytes = 0, d2h_bytes = 0;  // bytes moved by b200_process_frames_batch(B200_MEM_HOST)  // host-buffer frames that had to be re-uploaded whole (crop too small)
+  uint64_t full_frame_redos = 0;           // host-buffer frames that had to be re-uploaded whole (crop too small)
+  uint64_t h2d_bytes = 0, d2h_bytes = 0;  // bytes moved by the host-buffer entry points
   Lane lane[2];
   int host_chunk = 1024;  // frames per pipelined chunk on the host-buffer path (measured: 1024 > 2048 > 4096)
   int crop_margin = 2;    // host-buffer path uploads only the detection region + this margin (< 0: whole frames)
