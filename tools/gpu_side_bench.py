@@ -47,4 +47,16 @@ frames = deck_frames_cuda(0, F, 640, 480, 8.0, 0xCA2D10)
 fo = torch.zeros(F, dtype=torch.float32, device="cuda"); br = torch.zeros(F, dtype=torch.float32, device="cuda")
 timed("frame_scores", lambda: dmz._check(lib.b200_frame_scores_batch(ctx, C.c_void_p(frames.data_ptr()), 640, 640 * 480, 640, 480, F, 0, MEM_DEVICE,
                                                                         C.c_void_p(fo.data_ptr()), C.c_void_p(br.data_ptr()))), F)
+# best_expiry_seg on warped cards of the deck (8f rank 4): Scharr + row sums + the one-thread-per-card group search
+recs = torch.zeros((F, 808), dtype=torch.uint8, device="cuda")
+cards = torch.zeros((F, 270, 428), dtype=torch.uint8, device="cuda")
+dmz.process_frames_device(frames.data_ptr(), F, 640, 480, recs.data_ptr(), cards.data_ptr())
+r = recs.cpu().numpy().view(pkg.RECORD_DTYPE).reshape(F)
+yo = torch.from_numpy(r["v_y_offset"].astype("uint16").view("int16")).cuda()
+MAXG = 16
+groups = torch.zeros((F, MAXG, 68), dtype=torch.uint8, device="cuda")
+ng = torch.zeros(F, dtype=torch.int32, device="cuda"); nd = torch.zeros(F, dtype=torch.int32, device="cuda")
+timed("best_expiry_seg", lambda: dmz._check(lib.b200_best_expiry_seg_batch(ctx, C.c_void_p(cards.data_ptr()), C.c_void_p(yo.data_ptr()), F, MEM_DEVICE,
+                                                                          C.c_void_p(groups.data_ptr()), MAXG, C.c_void_p(ng.data_ptr()), C.c_void_p(nd.data_ptr()), None)), F, reps=3)
+out["best_expiry_seg"]["cards_with_groups"] = int((ng > 0).sum().item())
 print(json.dumps(out))
