@@ -311,7 +311,7 @@ def main():
             lat.append(time.perf_counter() - t1)
         lat = np.sort(np.array(lat[64:])) * 1e6
         single = {"gpu_call_us_median": float(np.median(lat)), "gpu_call_us_p90": float(lat[int(0.9 * len(lat))]), "calls": int(len(lat)),
-                  "what": "b200_process_frames_batch(n=1, host buffers): H2D, 15 kernels, D2H, sync"}
+                  "what": "b200_process_frames_batch(n=1, host buffers): H2D, 13 kernels, D2H, sync"}
 
     # ---- CPU baseline on the host cores (rank 0 only, bounded sample)
     cpu = None
