@@ -11,6 +11,7 @@
 #ifndef B200_INTERNAL_H
 #define B200_INTERNAL_H
 
+#include <atomic>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -72,6 +73,22 @@ struct NetWeights {  // device pointers
   const float *cnn[3];   // modelc blobs: conv W 8x9, conv b 8, hidden W 32x320, hidden b 32, logistic W 10x32, b 10
   const float *cnn_hwT;  // 3 x [320][32] transposed hidden weights (built on the host)
   const float *vseg_norm;  // [256][256][2]: cvNormalize(MINMAX 0..1) scale / shift of a row whose 8-bit min / max are (mn, mx)
+};
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-DEVICE setting, and one process may hold contexts on several
+// devices: remember per kernel which devices have been configured (configuring twice is harmless, so no lock).
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> done{0};
+  template <typename F>
+  bool ensure(F &&configure) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (done.load(std::memory_order_acquire) & bit) return true;
+    if (!configure()) return false;
+    done.fetch_or(bit, std::memory_order_release);
+    return true;
+  }
 };
 
 // launchers (each returns the number of kernels it launched, or -1 after setting a CUDA error)

@@ -490,11 +490,13 @@ int launch_detect(const DetectParams &p, const uint8_t *plane, int row_stride, s
                   const b200_line *prev_lines, const b200_line *prev_lines2, b200_line *lines, int16_t *grad_scratch,
                   cudaStream_t s, int ox, int oy) {
   size_t smem = detect_smem_bytes(p);
-  static size_t configured = 0;
-  if (smem > configured) {
+  static size_t configured[64] = {0};  // largest dynamic shared-memory size opted into, per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (smem > configured[dev & 63]) {
     if (cudaFuncSetAttribute(detect_strips_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(detect_strips_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-    configured = smem;
+    configured[dev & 63] = smem;
   }
   size_t max_npad = 0;
   for (int i = 0; i < 4; i++) {

@@ -991,11 +991,9 @@ int launch_scan_gate(const FrameGeom *geom, const uint8_t *valid, int n, uint8_t
 }
 int launch_vseg_select(const float *vprob, const uint8_t *gate, int n, int pass, b200_scan *scans, cudaStream_t s) {
   const size_t smem = sizeof(float) * kSelFrames * kSelStride;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(vseg_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-    configured = true;
-  }
+  static PerDeviceOnce once;
+  if (!once.ensure([smem] { return cudaFuncSetAttribute(vseg_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess; }))
+    return -1;
   vseg_select_kernel<<<blocks_for(n, kSelFrames), kSelThreads, smem, s>>>(vprob, gate, n, pass, scans);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }

@@ -820,16 +820,18 @@ expiry_kernel(const float *__restrict__ W /* modelc_bf4dd6c8 blob */, const uint
   }
 }
 
-int g_num_sms = 0;
+int g_num_sms[64] = {0};  // per device
 
 int num_sms() {
-  if (!g_num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int &n = g_num_sms[dev & 63];
+  if (!n) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    n = v > 0 ? v : 148;
   }
-  return g_num_sms;
+  return n;
 }
 
 template <typename K>
@@ -852,11 +854,8 @@ int upload_conv_constants(const float *cnn_blobs[3]) {
 
 static int launch_vseg_rows(const NetWeights &wts, const uint8_t *cards, const uint8_t *gate, const b200_scan *scans, int n,
                             int mode, float *vprob, const float *raw_rows, float *raw_out, cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
-    if (!ensure_smem(vseg_rows_kernel, sizeof(VsegSmem))) return -1;
-    configured = true;
-  }
+  static PerDeviceOnce once;
+  if (!once.ensure([] { return ensure_smem(vseg_rows_kernel, sizeof(VsegSmem)); })) return -1;
   const int per_frame = mode == 0 ? 68 : (mode == 1 ? kFineSlots : 1);
   const long long tiles = ((long long)n * per_frame + kVTile - 1) / kVTile;
   long long grid = (long long)num_sms();  // one persistent CTA (12 autonomous warps) per SM
@@ -872,12 +871,9 @@ int launch_vseg_model(const NetWeights &wts, const float *rows, int n, float *ou
 
 static int launch_categorize(const NetWeights &wts, const uint8_t *cards, b200_scan *scans, const uint8_t *raw,
                              const float *raw_float, int n, float *raw_out, uint8_t *q8, cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
-    if (!ensure_smem(categorize_kernel<false>, sizeof(CatSmem))) return -1;
-    if (!ensure_smem(categorize_kernel<true>, sizeof(CatSmem))) return -1;
-    configured = true;
-  }
+  static PerDeviceOnce once;
+  if (!once.ensure([] { return ensure_smem(categorize_kernel<false>, sizeof(CatSmem)) && ensure_smem(categorize_kernel<true>, sizeof(CatSmem)); }))
+    return -1;
   const bool is_raw = raw != nullptr || raw_float != nullptr;
   const int groups = is_raw ? (n + 15) / 16 : n;
   int grid = num_sms();
@@ -905,11 +901,8 @@ int upload_bilateral_tables(const float *color256, const float *space5) {
 
 int launch_expiry_digits(const float *weights, const uint8_t *patches, const float *prepared, int n, float *out, cudaStream_t s,
                          const int32_t *where) {
-  static bool configured = false;
-  if (!configured) {
-    if (!ensure_smem(expiry_kernel, sizeof(ExpirySmem))) return -1;
-    configured = true;
-  }
+  static PerDeviceOnce once;
+  if (!once.ensure([] { return ensure_smem(expiry_kernel, sizeof(ExpirySmem)); })) return -1;
   int grid = num_sms();
   const int groups = (n + kEDigits - 1) / kEDigits;
   if (grid > groups) grid = groups;

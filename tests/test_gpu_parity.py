@@ -417,6 +417,18 @@ def test_1080p_detect_and_path(dmz, oracle):
         assert np.array_equal(got[f], want[f]), f
 
 
+def test_second_device_in_one_process(pkg, dmz, deck, orecs):
+    """Contexts on two devices in one process (kernel attributes such as the dynamic shared-memory opt-in are per device)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    rec, _ = orecs
+    other = pkg.Dmz(device=1)
+    got = other.process_frames(deck)
+    for f in ("all_found", "card_check", "v_y_offset", "usable", "h_offsets"):
+        assert np.array_equal(got[f], rec[f]), f
+
+
 def test_bad_arguments_fail_cleanly(dmz, pkg):
     with pytest.raises(pkg.B200Error):
         dmz.process_frames(np.zeros((1, 16, 16), np.uint8))  # frame too small for detection strips
