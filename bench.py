@@ -294,7 +294,7 @@ def main():
         e2e = {"value": Fe * world * args.steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": (h2d1 - h2d0) // args.steps,
                "d2h_bytes_per_step": (d2h1 - d2h0) // args.steps, "frames_per_step": Fe, "records_equal_device_path": same,
                "host_frame_bytes_per_step": Fe * FRAME_BYTES, "full_frame_redos": dmz.full_frame_redos,
-               "note": "host frames are full 640x480 planes in pinned memory; the library uploads only the detection-region rectangle (+8 px) of each and re-uploads a whole frame if its card quad reaches outside it",
+               "note": "host frames are full 640x480 planes in pinned memory; the library uploads only the detection-region rectangle (+2 px) of each and re-uploads a whole frame if its card quad reaches outside it",
                "timing": "wall clock around the synchronous C-ABI calls, max over ranks", "rank0_cpu_binding": numa}
 
     # ---- BASELINE configs[0]: ONE frame through the whole path (latency of a batch of one through the C ABI, host

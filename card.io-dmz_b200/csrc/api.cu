@@ -22,7 +22,8 @@ constexpr size_t kCardBytes = (size_t)B200_CARD_W * B200_CARD_H;
 struct Lane {
   cudaStream_t stream = nullptr;
   int cap = 0, cap_w = 0, cap_h = 0;
-  size_t frame_bytes = 0;  // size of d_frames (host-buffer staging)
+  size_t frame_bytes = 0;   // size of d_frames (host-buffer staging)
+  size_t chroma_bytes = 0;  // size of d_cb and of d_cr (tracked on their own: (w/2)(h/2) is not w*h/4 for odd sizes)
   uint8_t *d_frames = nullptr, *d_cb = nullptr, *d_cr = nullptr;
   b200_line *d_lines = nullptr;  // 3 * cap * 4
   FrameGeom *d_geom = nullptr;
@@ -132,6 +133,7 @@ void free_lane(Lane *l) {
   l->d_records = nullptr, l->d_grad = nullptr, l->d_check = nullptr, l->d_flags = nullptr;
   l->grad_elems = 0;
   l->frame_bytes = 0;
+  l->chroma_bytes = 0;
   l->cap = 0;
 }
 
@@ -145,7 +147,12 @@ int ensure_config(b200_ctx *ctx, int w, int h, int orientation, int planes) {
   cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
   for (int p = 0; p < 2; p++) {
     ctx->dp[p].use_global_grad = 0;
-    if (detect_smem_bytes(ctx->dp[p]) > (size_t)max_smem - 1024) {
+    // the shared-memory variant stores padded pixel indices in 16 bits (detect.cu): larger strips (1080p portrait,
+    // 88 x 899) take the global-gradient variant with 32-bit work lists even where their gradients would fit
+    bool wide_index = false;
+    for (int s = 0; s < 4; s++)
+      wide_index = wide_index || (size_t)(ctx->dp[p].strip[s].w + 2) * (ctx->dp[p].strip[s].h + 2) > 65535;
+    if (wide_index || detect_smem_bytes(ctx->dp[p]) > (size_t)max_smem - 1024) {
       ctx->dp[p].use_global_grad = 1;
       if (detect_smem_bytes(ctx->dp[p]) > (size_t)max_smem - 1024)
         return fail(ctx, B200_EUNSUPPORTED, "detection strips of a %dx%d frame do not fit in shared memory", w, h);
@@ -157,15 +164,15 @@ int ensure_config(b200_ctx *ctx, int w, int h, int orientation, int planes) {
   return B200_OK;
 }
 
-int ensure_capacity(b200_ctx *ctx, Lane *l, int n, int w, int h, bool need_frames) {
+int ensure_capacity(b200_ctx *ctx, Lane *l, int n, int w, int h, bool need_frames, bool need_chroma = false) {
   // per-frame records / cards: sized by frame COUNT
   if (n > l->cap) {
     uint8_t *keep_frames = l->d_frames, *keep_cb = l->d_cb, *keep_cr = l->d_cr;
-    const size_t keep_bytes = l->frame_bytes;
+    const size_t keep_bytes = l->frame_bytes, keep_chroma = l->chroma_bytes;
     l->d_frames = l->d_cb = l->d_cr = nullptr;  // staging buffers are managed below
     free_lane(l);
     l->d_frames = keep_frames, l->d_cb = keep_cb, l->d_cr = keep_cr;
-    l->frame_bytes = keep_bytes;
+    l->frame_bytes = keep_bytes, l->chroma_bytes = keep_chroma;
     CU(cudaMalloc(&l->d_lines, sizeof(b200_line) * 3 * (size_t)n * 4));
     CU(cudaMalloc(&l->d_geom, sizeof(FrameGeom) * (size_t)n));
     CU(cudaMemset(l->d_geom, 0, sizeof(FrameGeom) * (size_t)n));  // struct padding is copied to the host with the records
@@ -183,13 +190,20 @@ int ensure_capacity(b200_ctx *ctx, Lane *l, int n, int w, int h, bool need_frame
   if (need_frames) {
     const size_t need = (size_t)n * w * h;
     if (need > l->frame_bytes) {
-      cudaFree(l->d_frames), cudaFree(l->d_cb), cudaFree(l->d_cr);
-      l->d_frames = l->d_cb = l->d_cr = nullptr;
+      cudaFree(l->d_frames);
+      l->d_frames = nullptr;
       l->frame_bytes = 0;
       CU(cudaMalloc(&l->d_frames, need));
-      CU(cudaMalloc(&l->d_cb, (size_t)n * (w / 2) * (h / 2) + 16));
-      CU(cudaMalloc(&l->d_cr, (size_t)n * (w / 2) * (h / 2) + 16));
       l->frame_bytes = need;
+    }
+    const size_t need_c = (size_t)n * (w / 2) * (h / 2) + 16;
+    if (need_chroma && need_c > l->chroma_bytes) {
+      cudaFree(l->d_cb), cudaFree(l->d_cr);
+      l->d_cb = l->d_cr = nullptr;
+      l->chroma_bytes = 0;
+      CU(cudaMalloc(&l->d_cb, need_c));
+      CU(cudaMalloc(&l->d_cr, need_c));
+      l->chroma_bytes = need_c;
     }
   }
   if ((size_t)w * h > (size_t)l->cap_w * l->cap_h) l->cap_w = w, l->cap_h = h;
@@ -245,6 +259,11 @@ int stage_planes(b200_ctx *ctx, cudaStream_t stream, const uint8_t *src, int row
   }
   *out_ptr = d_dense, *out_row_stride = w, *out_frame_stride = (size_t)w * h;
   return B200_OK;
+}
+
+// a plane description is usable when rows do not overlap and frames do not overlap (n == 1 callers may pass any frame stride)
+bool strides_ok(int row_stride, size_t frame_stride, int w, int h) {
+  return w > 0 && h > 0 && row_stride >= w && frame_stride >= (size_t)row_stride * (size_t)(h - 1) + (size_t)w;
 }
 
 struct Crop {  // uploaded sub-rectangle [x0, x1) x [y0, y1) of the frame; x0 == x1 means "whole frame"
@@ -425,11 +444,13 @@ int b200_detect_edges_batch(b200_ctx *ctx, const uint8_t *y, int yrs, size_t yfs
                             int crs, size_t cfs, int width, int height, int n, int orientation, int mem, b200_edges *edges,
                             b200_corner_points *corners, uint8_t *all_found, b200_line *lines) {
   if (!ctx || !y || n < 1 || (!cb) != (!cr)) return fail(ctx, B200_EINVAL, "b200_detect_edges_batch: bad arguments");
+  if (!strides_ok(yrs, yfs, width, height) || (cb && !strides_ok(crs, cfs, width / 2, height / 2)))
+    return fail(ctx, B200_EINVAL, "b200_detect_edges_batch: row_stride < width or frame_stride < row_stride * height");
   CU(cudaSetDevice(ctx->device));
   Lane *l = &ctx->lane[0];
   int rc = ensure_config(ctx, width, height, orientation, cb ? 3 : 1);
   if (rc) return rc;
-  rc = ensure_capacity(ctx, l, n, width, height, mem == B200_MEM_HOST);
+  rc = ensure_capacity(ctx, l, n, width, height, mem == B200_MEM_HOST, cb != nullptr);
   if (rc) return rc;
   const uint8_t *dy, *dcb = nullptr, *dcr = nullptr;
   int drs, dcrs = 0;
@@ -474,6 +495,8 @@ int b200_transform_card_batch(b200_ctx *ctx, const uint8_t *sample, int row_stri
                               int height, int n, const b200_corner_points *corners, const uint8_t *valid, int orientation,
                               int upsample, int mem, uint8_t *cards) {
   if (!ctx || !sample || !corners || !cards || n < 1) return fail(ctx, B200_EINVAL, "b200_transform_card_batch: bad arguments");
+  if (!strides_ok(row_stride, frame_stride, width, height))
+    return fail(ctx, B200_EINVAL, "b200_transform_card_batch: row_stride < width or frame_stride < row_stride * height");
   CU(cudaSetDevice(ctx->device));
   Lane *l = &ctx->lane[0];
   int rc = ensure_capacity(ctx, l, n, width, height, mem == B200_MEM_HOST);
@@ -531,6 +554,8 @@ int b200_scan_cards_batch(b200_ctx *ctx, const uint8_t *cards, int n, const uint
 int b200_process_frames_batch(b200_ctx *ctx, const uint8_t *y, int yrs, size_t yfs, int width, int height, int n,
                               int orientation, int mem, b200_frame_record *records, uint8_t *cards_out) {
   if (!ctx || !y || !records || n < 1) return fail(ctx, B200_EINVAL, "b200_process_frames_batch: bad arguments");
+  if (!strides_ok(yrs, yfs, width, height))
+    return fail(ctx, B200_EINVAL, "b200_process_frames_batch: row_stride < width or frame_stride < row_stride * height");
   CU(cudaSetDevice(ctx->device));
   int rc = ensure_config(ctx, width, height, orientation, 1);
   if (rc) return rc;

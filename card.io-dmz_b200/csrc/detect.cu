@@ -21,6 +21,8 @@
 // division appears inside any per-pixel loop (2-D walks are set up once per thread).
 #include <float.h>
 
+#include <type_traits>
+
 #include "b200_internal.h"
 
 namespace {
@@ -45,11 +47,15 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
   return v;
 }
 
+// Work-list entries are padded pixel indices o < (w + 2)(h + 2).  16 bits hold them for every strip that keeps its
+// gradients in shared memory (npad <= 65535 is part of that variant's admission test in api.cu); the global-gradient
+// variant serves the large strips (1080p portrait: 88 x 899 = 79112) and stores 32-bit indices.
+template <typename IdxT>
 struct SmemLayout {
   uint8_t *src;          // h x w source strip (dead after Sobel: its storage then holds the work lists)
   int16_t *dx, *dy;      // (h + 2) x (w + 2), zero border: no bounds checks in the NMS neighbourhood
   uint8_t *map;          // (h + 2) x (w + 2): 0 candidate, 1 no edge (also the border), 2 edge
-  unsigned short *list;  // candidate list (hysteresis), then vote list (Hough): padded pixel indices; aliases src
+  IdxT *list;            // candidate list (hysteresis), then vote list (Hough): padded pixel indices; aliases src
   unsigned int *acc;     // compacted Hough accumulator
 };
 
@@ -116,7 +122,9 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
   }
 
   // ---- carve shared memory
-  SmemLayout L;
+  using IdxT = typename std::conditional<kGlobalGrad, unsigned int, unsigned short>::type;
+  constexpr int kIdxShift = kGlobalGrad ? 2 : 1;  // log2(sizeof(IdxT))
+  SmemLayout<IdxT> L;
   size_t off = 0;
   L.src = smem_raw + off;
   off = align16(off + (size_t)ws * h);
@@ -135,13 +143,13 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
   off = align16(off + (size_t)S.ncells * 4);
   // per-warp rings of pixels whose magnitude exceeds the low threshold (64 entries each), in the dynamic block so that
   // their addresses derive from the same base register as everything else
-  unsigned short *q_rings = reinterpret_cast<unsigned short *>(smem_raw + off);
+  IdxT *q_rings = reinterpret_cast<IdxT *>(smem_raw + off);
   // work lists alias the (by then dead) source strip: one candidate segment per warp (filled without atomics), then
   // the vote list; overflow falls back to full scans
-  L.list = reinterpret_cast<unsigned short *>(L.src);
-  const int cand_cap = (((ws * h) >> 1) * 3 / 5) / kWarps;  // entries per warp segment
-  unsigned short *vote_list = L.list + cand_cap * kWarps;
-  const int list_cap = ((ws * h) >> 1) - cand_cap * kWarps;  // entries of the vote list
+  L.list = reinterpret_cast<IdxT *>(L.src);
+  const int cand_cap = (((ws * h) >> kIdxShift) * 3 / 5) / kWarps;  // entries per warp segment
+  IdxT *vote_list = L.list + cand_cap * kWarps;
+  const int list_cap = ((ws * h) >> kIdxShift) - cand_cap * kWarps;  // entries of the vote list
 
   // ---- 1. load the strip (32-bit coalesced loads of the covering aligned words); clear borders / accumulator
   {
@@ -256,7 +264,7 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
   };
   auto push_vote = [&](int o) {
     const int slot = atomicAdd(&s_nvote, 1);
-    if (slot < list_cap) vote_list[slot] = (unsigned short)o;
+    if (slot < list_cap) vote_list[slot] = (IdxT)o;
     else s_overflow = 1;
   };
   int n_edge = 0;
@@ -272,8 +280,8 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
   {
     const int lane = tid & 31, wid = tid >> 5;
     const unsigned int lt = (1u << lane) - 1u;
-    unsigned short *q = q_rings + wid * 64;
-    unsigned short *clist = L.list + wid * cand_cap;
+    IdxT *q = q_rings + wid * 64;
+    IdxT *clist = L.list + wid * cand_cap;
     int qhead = 0, qtail = 0, ccount = 0;
     auto mag = [&](int j) -> int { return abs((int)L.dx[j]) + abs((int)L.dy[j]); };
     auto direction_test = [&](int cnt) {  // the first cnt queued pixels, one per lane
@@ -302,7 +310,7 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
       const unsigned int wm = __ballot_sync(0xffffffffu, weak);
       if (weak) {
         const int slot = ccount + __popc(wm & lt);
-        if (slot < cand_cap) clist[slot] = (unsigned short)o;
+        if (slot < cand_cap) clist[slot] = (IdxT)o;
         else s_overflow = 1;
       }
       ccount += __popc(wm);
@@ -321,7 +329,7 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
       const bool pend = in_strip && mag(o) > low;
       if (in_strip && !pend) L.map[o] = 1;
       const unsigned int pm = __ballot_sync(0xffffffffu, pend);
-      if (pend) q[(qtail + __popc(pm & lt)) & 63] = (unsigned short)o;
+      if (pend) q[(qtail + __popc(pm & lt)) & 63] = (IdxT)o;
       qtail += __popc(pm);
       if (qtail - qhead >= 32) {
         __syncwarp();  // queue entries visible
@@ -480,7 +488,7 @@ size_t detect_smem_bytes(const DetectParams &p) {
     const size_t ws = (size_t)detect_src_stride(d.w);
     size_t b = align16(ws * d.h) + align16(npad);  // padded src (later the work lists), map
     if (!p.use_global_grad) b += 2 * align16(npad * 2);
-    b += align16((size_t)d.ncells * 4) + (size_t)kWarps * 64 * 2 + 64;  // accumulator, per-warp rings
+    b += align16((size_t)d.ncells * 4) + (size_t)kWarps * 64 * (p.use_global_grad ? 4 : 2) + 64;  // accumulator, per-warp rings
     worst = b > worst ? b : worst;
   }
   return worst;
@@ -490,13 +498,17 @@ int launch_detect(const DetectParams &p, const uint8_t *plane, int row_stride, s
                   const b200_line *prev_lines, const b200_line *prev_lines2, b200_line *lines, int16_t *grad_scratch,
                   cudaStream_t s, int ox, int oy) {
   size_t smem = detect_smem_bytes(p);
-  static size_t configured[64] = {0};  // largest dynamic shared-memory size opted into, per device
+  // largest dynamic shared-memory size opted into, per device (contexts on distinct threads may race here: the attribute
+  // call is idempotent and the recorded maximum only grows)
+  static std::atomic<size_t> configured[64];
   int dev = 0;
   cudaGetDevice(&dev);
-  if (smem > configured[dev & 63]) {
+  if (smem > configured[dev & 63].load(std::memory_order_acquire)) {
     if (cudaFuncSetAttribute(detect_strips_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(detect_strips_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-    configured[dev & 63] = smem;
+    size_t seen = configured[dev & 63].load(std::memory_order_relaxed);
+    while (seen < smem && !configured[dev & 63].compare_exchange_weak(seen, smem, std::memory_order_release)) {
+    }
   }
   size_t max_npad = 0;
   for (int i = 0; i < 4; i++) {

@@ -119,7 +119,7 @@ uint64_t b200_launch_count(const b200_ctx *ctx);
 /* The CUDA stream (cudaStream_t) all work of this context is enqueued on. */
 void *b200_ctx_stream(const b200_ctx *ctx);
 /* Host-buffer path of b200_process_frames_batch: only the bounding rectangle of the four detection strips plus
- * `margin` pixels is copied to the device (margin < 0: whole frames; default 8 or $B200_DMZ_CROP_MARGIN).  Frames
+ * `margin` pixels is copied to the device (margin < 0: whole frames; default 2 or $B200_DMZ_CROP_MARGIN).  Frames
  * whose detected card quad reaches outside that rectangle are transparently redone from a full-frame upload;
  * b200_full_frame_redos counts them.  Results never depend on the margin. */
 void b200_set_crop_margin(b200_ctx *ctx, int margin);

@@ -101,6 +101,7 @@ class Oracle:
         f("detect_edges", [vp, i, i, i, vp, vp, i, i, C.POINTER(Detect)], i)
         f("calc_persp_transform", [vp, vp, vp])
         f("transform_card", [vp, i, i, i, vp, i, vp])
+        f("transform_card_up", [vp, i, i, i, vp, i, i, vp])
         f("vseg_row", [vp, i, vp])
         f("vseg_model", [vp, vp])
         f("best_n_vseg", [vp, C.POINTER(VSeg)])
@@ -199,12 +200,12 @@ class Oracle:
         self._calc_persp_transform(_p(src), _p(dst), _p(m))
         return m.reshape(3, 3)
 
-    def transform_card(self, y, corners, orientation=3):
+    def transform_card(self, y, corners, orientation=3, upsample=False):
         y = np.ascontiguousarray(y, np.uint8)
         h, w = y.shape
         corners = np.ascontiguousarray(corners, np.float32).reshape(8)
         card = np.zeros((270, 428), np.uint8)
-        self._transform_card(_p(y), w, h, w, _p(corners), orientation, _p(card))
+        self._transform_card_up(_p(y), w, h, w, _p(corners), orientation, int(upsample), _p(card))
         return card
 
     def vseg_row(self, card, row):

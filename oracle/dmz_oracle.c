@@ -500,6 +500,12 @@ void orc_calc_persp_transform(const float s[8], const float d[8], float M[9]) {
 
 /* W0 + W2: dmz_transform_card (dmz.cpp:443-497) -> llcv_unwarp (cv/warp.cpp:130-167) */
 void orc_transform_card(const uint8_t *y, int w, int h, int ystep, const float c[8], int orientation, uint8_t *card) {
+  orc_transform_card_up(y, w, h, ystep, c, orientation, 0, card);
+}
+
+/* upsample: the sample is a half-size chroma plane, so the (luma-space) corners are halved (dmz.cpp:473-481;
+ * llcv_warp_auto_upsamples() is false outside IOS_DMZ, cv/warp.cpp:26-32) */
+void orc_transform_card_up(const uint8_t *y, int w, int h, int ystep, const float c[8], int orientation, int upsample, uint8_t *card) {
   /* corner order in c: tl, bl, tr, br */
   const float *tl = c, *bl = c + 2, *tr = c + 4, *br = c + 6;
   const float *sp[4];
@@ -513,6 +519,8 @@ void orc_transform_card(const uint8_t *y, int w, int h, int ystep, const float c
     default: sp[0] = tl, sp[1] = tr, sp[2] = bl, sp[3] = br; break;
   }
   for (i = 0; i < 4; i++) src[2 * i] = sp[i][0], src[2 * i + 1] = sp[i][1];
+  if (upsample)
+    for (i = 0; i < 8; i++) src[i] /= 2.0f;
   orc_calc_persp_transform(src, dst, M);
   orc_warp_perspective_u8(y, ystep, w, h, card, kCardW, kCardW, kCardH, M);
 }

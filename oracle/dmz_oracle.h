@@ -36,6 +36,8 @@ int orc_detect_edges(const uint8_t *y, int w, int h, int ystep, const uint8_t *c
 void orc_calc_persp_transform(const float src_pts[8], const float dst_pts[8], float M[9]);
 void orc_transform_card(const uint8_t *y, int w, int h, int ystep, const float corners[8], int orientation,
                         uint8_t *card);
+void orc_transform_card_up(const uint8_t *y, int w, int h, int ystep, const float corners[8], int orientation, int upsample,
+                           uint8_t *card);
 void orc_vseg_row(const uint8_t *card, int row, float probs[3]);
 void orc_vseg_model(const float *in204, float probs[3]);
 void orc_best_n_vseg(const uint8_t *card, orc_vseg *out);

@@ -211,6 +211,17 @@ void ref_transform_card(const uint8_t *y, int w, int h, int ystep, const float c
   dmz_transform_card(NULL, &a.img, p, (FrameOrientation)orientation, false, &outp);
 }
 
+/* the same with the caller's `upsample` flag (sample = a half-size chroma plane, dmz.cpp:473-481) */
+void ref_transform_card_up(const uint8_t *y, int w, int h, int ystep, const float corners[8], int orientation, int upsample, uint8_t *card) {
+  Hdr a, o;
+  wrap(&a, y, w, h, ystep, IPL_DEPTH_8U);
+  wrap(&o, card, 428, 270, 428, IPL_DEPTH_8U);
+  dmz_corner_points p;
+  memcpy(&p, corners, sizeof(p));
+  IplImage *outp = &o.img;
+  dmz_transform_card(NULL, &a.img, p, (FrameOrientation)orientation, upsample != 0, &outp);
+}
+
 /* V1+V2: the three softmax outputs for one image row of a 428x270 card (scan/n_vseg.cpp:39-47). */
 void ref_vseg_row(const uint8_t *card, int row, float probs[3]) {
   Hdr c;

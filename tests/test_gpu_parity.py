@@ -105,7 +105,8 @@ def test_detect_textured_frames(dmz, oracle):
                 assert (int(gl["r"]), int(gl["n"])) == (ol.r, ol.n), (k, s_)
 
 
-
+def test_chroma_fallback_exact(dmz, oracle):
+    """Y plane flat on the left -> the left edge comes from Cb (rho doubled), dmz.cpp:351-367."""
     f = deck_frames(5, 1)[0]
     cb = np.ascontiguousarray(f[::2, ::2])
     cr = np.full((240, 320), 128, np.uint8)
@@ -117,6 +118,118 @@ def test_detect_textured_frames(dmz, oracle):
     assert bits(edges["rho"][0]).tolist() == bits(list(want.rho)).tolist()
     if want.all_found:
         assert bits(corners[0]).tolist() == bits(list(want.corners)).tolist()
+
+
+def test_chroma_cr_supplies_edge(dmz, oracle):
+    """Y misses the left and the top edge, Cb has the top edge only, Cr has every edge: the top edge comes from Cb and
+    the left edge from the THIRD plane (dmz.cpp:351-367, rho multiplier 2 on both chroma planes)."""
+    from test_oracle_vs_ref import chroma_case
+    y, cb, cr = chroma_case()
+    want = oracle.detect_edges(y, cb, cr)
+    assert list(want.found) == [1, 1, 1, 1]
+    edges, corners, found, _ = dmz.detect_edges(y[None], cb[None], cr[None])
+    assert list(edges["found"][0]) == [1, 1, 1, 1] and int(found[0]) == 1
+    assert bits(edges["rho"][0]).tolist() == bits(list(want.rho)).tolist()
+    assert bits(edges["theta"][0]).tolist() == bits(list(want.theta)).tolist()
+    assert bits(corners[0]).tolist() == bits(list(want.corners)).tolist()
+    # a flat Cr leaves the left edge missing: the line above really came from the third plane
+    flat = np.full_like(cr, 128)
+    e2, _, f2, _ = dmz.detect_edges(y[None], cb[None], flat[None])
+    assert list(e2["found"][0]) == list(oracle.detect_edges(y, cb, flat).found) == [1, 0, 1, 1] and int(f2[0]) == 0
+    # a batch mixing the three situations keeps every frame's planes apart
+    ys, cbs, crs = np.stack([y, y, deck_frames(5, 1)[0]]), np.stack([cb, cb, cb]), np.stack([cr, flat, flat])
+    e3, c3, f3, _ = dmz.detect_edges(ys, cbs, crs)
+    for k in range(3):
+        w = oracle.detect_edges(ys[k], cbs[k], crs[k])
+        assert list(e3["found"][k]) == list(w.found) and int(f3[k]) == w.all_found, k
+        if w.all_found:
+            assert bits(c3[k]).tolist() == bits(list(w.corners)).tolist(), k
+
+
+@pytest.fixture(scope="module")
+def upright_cards(oracle):
+    recs, cards = oracle.process_frames(deck_frames(300, 8), want_cards=True)
+    return cards[recs["usable"] == 1][:4]
+
+
+@pytest.mark.parametrize("orientation", [1, 2, 4])
+def test_detect_other_orientations(dmz, oracle, upright_cards, orientation):
+    """Portrait (1, 2) and landscape-left (4): other strip rectangles (dmz.cpp:279-341) and, downstream, another corner
+    permutation.  Per-strip taps, edges and corners bit-equal to the oracle."""
+    from util import oriented_frames
+    boxes = oracle.detection_boxes(640, 480, orientation)
+    frames = oriented_frames(upright_cards, orientation, boxes, seed=10 + orientation)
+    edges, corners, found, lines = dmz.detect_edges(frames, orientation=orientation, want_lines=True)
+    for k in range(len(frames)):
+        for s, (x, y, w, h) in enumerate(boxes):
+            ol = oracle.best_line(frames[k][y:y + h, x:x + w], s >= 2)
+            gl = lines[k, s]
+            for f in ("found", "max_votes", "low", "high", "n_edge_px"):
+                assert int(gl[f]) == getattr(ol, f), (k, s, f)
+            if ol.found:
+                assert (int(gl["r"]), int(gl["n"])) == (ol.r, ol.n)
+        want = oracle.detect_edges(frames[k], orientation=orientation)
+        assert list(edges["found"][k]) == list(want.found) and int(found[k]) == want.all_found == 1
+        assert bits(edges["rho"][k]).tolist() == bits(list(want.rho)).tolist()
+        assert bits(corners[k]).tolist() == bits(list(want.corners)).tolist()
+
+
+@pytest.mark.parametrize("orientation", [1, 2, 4])
+def test_whole_path_other_orientations(dmz, oracle, upright_cards, orientation):
+    """detect -> transform -> scan in the other three orientations against the oracle, and against the reference's own
+    sources where that build travelled (oracle/_ref)."""
+    from util import oriented_frames
+    from oracle.binding import Oracle, available
+    frames = oriented_frames(upright_cards, orientation, oracle.detection_boxes(640, 480, orientation), seed=20 + orientation)
+    recs, cards = dmz.process_frames(frames, orientation=orientation, want_cards=True)
+    checkers = [oracle] + ([Oracle("ref")] if available("ref") else [])
+    for chk in checkers:
+        want, wcards = chk.process_frames(frames, orientation=orientation, want_cards=True)
+        assert want["all_found"].all() and (want["usable"] == 1).any()
+        assert np.array_equal(cards, wcards)
+        for f in ("found", "all_found", "card_check", "v_y_offset", "v_pattern_type", "usable", "upside_down", "h_n_offsets", "h_offsets",
+                  "h_pattern_offset"):
+            assert np.array_equal(recs[f], want[f]), (chk.kind, f)
+        assert np.array_equal(bits(recs["corners"]), bits(want["corners"]))
+        assert np.array_equal(bits(recs["h_score"]), bits(want["h_score"]))
+        assert np.abs(recs["scores"] - want["scores"]).max() <= TOL
+
+
+def test_transform_card_upsample(dmz, oracle, deck, orecs):
+    """upsample = true (dmz.cpp:473-481): a half-size chroma plane is warped with the luma-space corners halved."""
+    rec = orecs[0]
+    cb = np.ascontiguousarray(deck[:6, ::2, ::2])
+    for o in (1, 2, 3, 4):
+        got = dmz.transform_card(cb, rec["corners"][:6], orientation=o, upsample=True)
+        for k in range(6):
+            assert np.array_equal(got[k], oracle.transform_card(cb[k], rec["corners"][k], o, upsample=True)), (o, k)
+    plain = dmz.transform_card(cb, rec["corners"][:6], upsample=False)
+    assert not np.array_equal(plain, dmz.transform_card(cb, rec["corners"][:6], upsample=True))
+
+
+def test_detect_1080p_portrait_wide_indices(dmz, oracle, upright_cards):
+    """1920x1080 portrait: the side strips are 86 x 897, (w + 2)(h + 2) = 79112 > 65535, so padded pixel indices no
+    longer fit 16 bits (the detect kernel's 32-bit work-list variant)."""
+    from util import oriented_frames
+    boxes = oracle.detection_boxes(1920, 1080, 1)
+    assert max((w + 2) * (h + 2) for (_, _, w, h) in boxes) > 65535
+    frames = oriented_frames(upright_cards[:2], 1, boxes, w=1920, h=1080, seed=5)
+    edges, corners, found, lines = dmz.detect_edges(frames, orientation=1, want_lines=True)
+    for k in range(len(frames)):
+        for s, (x, y, w, h) in enumerate(boxes):
+            ol = oracle.best_line(frames[k][y:y + h, x:x + w], s >= 2)
+            gl = lines[k, s]
+            for f in ("found", "max_votes", "low", "high", "n_edge_px"):
+                assert int(gl[f]) == getattr(ol, f), (k, s, f, int(gl[f]), getattr(ol, f))
+            if ol.found:
+                assert (int(gl["r"]), int(gl["n"])) == (ol.r, ol.n)
+        want = oracle.detect_edges(frames[k], orientation=1)
+        assert int(found[k]) == want.all_found == 1
+        assert bits(corners[k]).tolist() == bits(list(want.corners)).tolist()
+    recs, cards = dmz.process_frames(frames, orientation=1, want_cards=True)
+    want, wcards = oracle.process_frames(frames, orientation=1, want_cards=True)
+    assert np.array_equal(cards, wcards) and np.array_equal(recs["card_check"], want["card_check"])
+    assert np.array_equal(recs["v_y_offset"], want["v_y_offset"]) and np.array_equal(recs["usable"], want["usable"])
 
 
 def test_homography_bits(dmz, oracle, golden):

@@ -91,3 +91,62 @@ def test_expiry_digit_against_reference_build(refx, oracle):
         a, b = refx.expiry_patch_prep(patch), oracle.expiry_patch_prep(patch)
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), t
         assert np.abs(refx.expiry_digit_model(a) - oracle.expiry_digit_model(b)).max() <= 1e-5, t
+
+
+def _upright_cards(oracle, first=300, n=6):
+    recs, cards = oracle.process_frames(deck_frames(first, n), want_cards=True)
+    return cards[recs["usable"] == 1]
+
+
+def test_whole_path_all_orientations(ref, oracle):
+    """FrameOrientation 1, 2, 4 change the strip geometry (dmz.cpp:279-341) and the corner permutation
+    (dmz.cpp:446-471): the restatement must follow the reference in every one of them."""
+    from util import oriented_frames
+    cards = _upright_cards(oracle)[:3]
+    for o in (1, 2, 3, 4):
+        assert np.array_equal(ref.detection_boxes(640, 480, o), oracle.detection_boxes(640, 480, o))
+        frames = oriented_frames(cards, o, oracle.detection_boxes(640, 480, o), seed=o)
+        rr, rc = ref.process_frames(frames, orientation=o, want_cards=True)
+        po, pc = oracle.process_frames(frames, orientation=o, want_cards=True)
+        assert rr["all_found"].all(), o
+        assert np.array_equal(rc, pc), o
+        for f in ("found", "all_found", "card_check", "v_y_offset", "v_pattern_type", "usable", "upside_down", "h_n_offsets", "h_offsets"):
+            assert np.array_equal(rr[f], po[f]), (o, f)
+        assert np.array_equal(rr["corners"].view(np.uint32), po["corners"].view(np.uint32)), o
+        assert np.abs(rr["scores"] - po["scores"]).max() <= 1e-5
+
+
+def test_transform_card_upsample(ref, oracle):
+    """upsample = true: the sample is a half-size chroma plane and the corners are halved (dmz.cpp:473-481)."""
+    frames = deck_frames(40, 2)
+    rec = oracle.process_frames(frames)
+    for k in range(2):
+        cb = np.ascontiguousarray(frames[k][::2, ::2])
+        for o in (1, 2, 3, 4):
+            a = ref.transform_card(cb, rec["corners"][k], o, upsample=True)
+            b = oracle.transform_card(cb, rec["corners"][k], o, upsample=True)
+            assert np.array_equal(a, b), (k, o)
+            assert not np.array_equal(a, oracle.transform_card(cb, rec["corners"][k], o, upsample=False))
+
+
+def chroma_case():
+    """Y misses the left and the top edge; Cb has the top edge only; Cr has every edge: top comes from Cb, left from Cr."""
+    f = deck_frames(5, 1)[0]
+    half = np.ascontiguousarray(f[::2, ::2])
+    y = f.copy()
+    y[:, :160] = 60
+    y[:100, :] = 60
+    cb = half.copy()
+    cb[:, :80] = 60
+    return y, cb, half.copy()
+
+
+def test_chroma_cr_supplies_edge(ref, oracle):
+    y, cb, cr = chroma_case()
+    dr, do = ref.detect_edges(y, cb, cr), oracle.detect_edges(y, cb, cr)
+    assert fields(dr)["found"] == [1, 1, 1, 1] == fields(do)["found"]
+    assert np.array_equal(np.array(dr.rho, np.float32).view(np.uint32), np.array(do.rho, np.float32).view(np.uint32))
+    assert np.array_equal(np.array(dr.corners, np.float32).view(np.uint32), np.array(do.corners, np.float32).view(np.uint32))
+    # without Cr the left edge stays missing: it really is the third plane that supplies it
+    flat = np.full_like(cr, 128)
+    assert fields(ref.detect_edges(y, cb, flat))["found"] == [1, 0, 1, 1]

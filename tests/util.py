@@ -133,3 +133,53 @@ def expiry_card(base_card, y_offset0, seed):
             reg = c[y:y + h, xs:xs + w]
             reg[expiry_glyph(ch, w, h, t) > 0] = fg
     return np.ascontiguousarray(c), yo
+
+
+# ---- frames for the other three FrameOrientations (dmz_olm.h:16-22).  The deck generator renders landscape-right
+# cards only; here a warped 428x270 card is projected back into a frame so that its quad sits in the guide rectangle of
+# the requested orientation and dmz_transform_card's corner permutation (dmz.cpp:446-471) turns it upright again.
+def _homography(src, dst):
+    """3x3 H with H @ (x, y, 1) ~ (u, v, 1) for the four correspondences src[i] -> dst[i] (float64, numpy solve)."""
+    a, b = [], []
+    for (x, y), (u, v) in zip(src, dst):
+        a.append([x, y, 1, 0, 0, 0, -x * u, -y * u]); b.append(u)
+        a.append([0, 0, 0, x, y, 1, -x * v, -y * v]); b.append(v)
+    h = np.linalg.solve(np.array(a, np.float64), np.array(b, np.float64))
+    return np.append(h, 1.0).reshape(3, 3)
+
+
+def guide_quad(boxes):
+    """Centre lines of the four detection strips (top, bottom, left, right rows of detection_boxes) -> tl, bl, tr, br."""
+    top = boxes[0][1] + boxes[0][3] / 2.0
+    bot = boxes[1][1] + boxes[1][3] / 2.0
+    left = boxes[2][0] + boxes[2][2] / 2.0
+    right = boxes[3][0] + boxes[3][2] / 2.0
+    return np.array([[left, top], [left, bot], [right, top], [right, bot]], np.float64)
+
+
+def oriented_frames(cards, orientation, boxes, w=640, h=480, jitter=None, seed=1):
+    """cards: (n, 270, 428) u8 upright cards.  Returns (n, h, w) u8 frames showing each card as a camera held in
+    `orientation` sees it, corners jittered inside the detection strips given by `boxes` (oracle.detection_boxes)."""
+    rng = np.random.default_rng(seed)
+    quad = guide_quad(boxes)  # tl, bl, tr, br in the frame
+    if jitter is None:
+        jitter = 0.3 * min(boxes[0][3], boxes[2][2])
+    # card corner (0,0),(427,0),(0,269),(427,269) <- frame corner, per dmz_transform_card's permutation
+    perm = {1: (1, 0, 3, 2), 4: (3, 1, 2, 0), 2: (2, 3, 0, 1), 3: (0, 2, 1, 3)}[orientation]
+    card_pts = [(0, 0), (427, 0), (0, 269), (427, 269)]
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float64)
+    out = np.zeros((len(cards), h, w), np.uint8)
+    for k, card in enumerate(cards):
+        q = quad + rng.uniform(-jitter, jitter, quad.shape)
+        H = _homography([tuple(q[i]) for i in perm], card_pts)  # frame -> card
+        den = H[2, 0] * xx + H[2, 1] * yy + H[2, 2]
+        u = (H[0, 0] * xx + H[0, 1] * yy + H[0, 2]) / den
+        v = (H[1, 0] * xx + H[1, 1] * yy + H[1, 2]) / den
+        inside = (u >= 0) & (u <= 427) & (v >= 0) & (v <= 269)
+        u0 = np.clip(np.floor(u), 0, 426).astype(np.int64); v0 = np.clip(np.floor(v), 0, 268).astype(np.int64)
+        fu = np.clip(u - u0, 0, 1); fv = np.clip(v - v0, 0, 1)
+        c = card.astype(np.float64)
+        val = (c[v0, u0] * (1 - fu) + c[v0, u0 + 1] * fu) * (1 - fv) + (c[v0 + 1, u0] * (1 - fu) + c[v0 + 1, u0 + 1] * fu) * fv
+        bg = np.clip(rng.normal(60, 8, (h, w)), 0, 255)
+        out[k] = np.where(inside, np.clip(np.rint(val), 0, 255), bg).astype(np.uint8)
+    return out
