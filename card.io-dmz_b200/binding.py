@@ -118,6 +118,7 @@ def _load():
     lib.b200_expiry_digit_models_batch.argtypes = [vp, vp, i, i, vp]
     lib.b200_set_profiling.argtypes = [vp, i]
     lib.b200_set_crop_margin.argtypes = [vp, i]
+    lib.b200_set_card_mode.argtypes = [vp, i]
     lib.b200_full_frame_redos.argtypes = [vp]
     lib.b200_full_frame_redos.restype = C.c_uint64
     lib.b200_transfer_bytes.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
@@ -148,7 +149,10 @@ class Dmz:
     """One b200_ctx (device, stream, weights, scratch).  NumPy arrays = host buffers (B200_MEM_HOST);
     integer addresses = device pointers (B200_MEM_DEVICE)."""
 
-    def __init__(self, device=0, weights_dir=None):
+    def __init__(self, device=0, weights_dir=None, materialise_cards=True):
+        """materialise_cards: b200_set_card_mode -- True (the default of this mirror, so that records always carry the
+        card checksum the parity tests compare) warps every card in full; False is the library's own default: calls that do
+        not ask for the cards warp only the rows scan_card_image reads and leave card_check 0."""
         self.lib = _load()
         self.ctx = C.c_void_p()
         rc = self.lib.b200_ctx_create(C.byref(self.ctx), device, weights_dir.encode() if weights_dir else None)
@@ -158,6 +162,7 @@ class Dmz:
                 self.lib.b200_ctx_destroy(self.ctx)
                 self.ctx = None
             raise B200Error("b200_ctx_create failed (%d): %s" % (rc, msg))
+        self.set_card_mode(materialise_cards)
 
     def close(self):
         if getattr(self, "ctx", None):
@@ -310,6 +315,9 @@ class Dmz:
         return out
 
     STAGES = ("detect", "geometry", "warp", "vseg", "hseg", "categorize", "finalize")
+
+    def set_card_mode(self, always_materialise):
+        self.lib.b200_set_card_mode(self.ctx, int(bool(always_materialise)))
 
     def set_crop_margin(self, margin):
         self.lib.b200_set_crop_margin(self.ctx, int(margin))

@@ -39,6 +39,7 @@ def build(force=False):
         # (source, extra flags).  exact.cu / detect.cu: bit-exact float stages -> no FMA contraction.
         ("detect.cu", ["-fmad=false"]),
         ("exact.cu", ["-fmad=false"]),
+        ("warp.cu", ["-fmad=false"]),
         ("expiry_seg.cu", ["-fmad=false"]),
         ("nets.cu", []),
         ("api.cu", ["-fmad=false"]),

@@ -50,10 +50,13 @@ struct b200_ctx {
   Lane lane[2];
   int host_chunk = 1024;  // frames per pipelined chunk on the host-buffer path (measured: 1024 > 2048 > 4096)
   int crop_margin = 2;    // host-buffer path uploads only the detection region + this margin (< 0: whole frames)
+  int card_mode = 0;      // 0: cards are materialised only when the caller asks for them (lazy rows otherwise); 1: always
+  cudaEvent_t lazy_ev[6] = {nullptr};  // brackets of the three lazy warp launches (profiling)
   // per-stage device time (CUDA events on the lane stream), accumulated while profiling is on
   int profiling = 0;
   double stage_ms[ST_COUNT] = {0};
   uint64_t stage_frames = 0;
+  bool lazy_timed = false;
   cudaEvent_t ev[ST_COUNT + 1] = {nullptr};
 
   // weights
@@ -289,19 +292,32 @@ int detect_sequence(b200_ctx *ctx, Lane *l, const uint8_t *y, int yrs, size_t yf
   return B200_OK;
 }
 
-// detect -> warp -> scan -> records for n frames already visible to the device on lane l.
+WarpSource warp_source(const uint8_t *base, int row_stride, size_t frame_stride, int width, int height, int n, const Crop &crop) {
+  WarpSource S;
+  S.base = base, S.row_stride = row_stride, S.frame_stride = frame_stride, S.frame_w = width, S.frame_h = height, S.n = n;
+  S.ox = crop.active() ? crop.x0 : 0, S.oy = crop.active() ? crop.y0 : 0;
+  S.bw = crop.active() ? crop.x1 - crop.x0 : width, S.bh = crop.active() ? crop.y1 - crop.y0 : height;
+  return S;
+}
+
+// detect -> warp -> scan -> records for n frames already visible to the device on lane l.  lazy: the caller does not
+// want the cards, so only the rows scan_card_image reads are warped (inside launch_scan) and card_check stays 0.
 int pipeline_on_lane(b200_ctx *ctx, Lane *l, const uint8_t *dy, int drs, size_t dfs, int width, int height, int n,
-                     uint8_t *dcards, b200_frame_record *drec, bool timed, Crop crop = Crop()) {
+                     uint8_t *dcards, b200_frame_record *drec, bool timed, bool lazy, Crop crop = Crop()) {
   int rc = detect_sequence(ctx, l, dy, drs, dfs, nullptr, nullptr, 0, 0, n, timed, crop);
   if (rc) return rc;
+  LazyWarp lw;
+  lw.src = warp_source(dy, drs, dfs, width, height, n, crop);
+  lw.portrait = ctx->cfg_orient == B200_ORIENT_PORTRAIT || ctx->cfg_orient == B200_ORIENT_PORTRAIT_UPSIDE_DOWN;
   if (timed) CU(cudaEventRecord(ctx->ev[ST_WARP], l->stream));
-  LAUNCH(launch_warp(dy, drs, dfs, width, height, n, l->d_geom, dcards, l->d_check, l->stream, crop.x0, crop.y0));
+  if (!lazy) LAUNCH(launch_warp(lw.src, l->d_geom, dcards, l->d_check, WARP_FULL, nullptr, nullptr, lw.portrait, l->stream));
   cudaEvent_t *ev = timed ? ctx->ev : nullptr;
   LAUNCH(launch_scan(ctx->wts, dcards, n, l->d_geom, nullptr, l->d_vprob, l->d_q8, l->d_scan, l->stream,
                      ev ? ev[ST_VSEG] : nullptr, ev ? ev[ST_HSEG] : nullptr, ev ? ev[ST_CATEGORIZE] : nullptr,
-                     ev ? ev[ST_FINALIZE] : nullptr));
-  LAUNCH(launch_finalize_records(l->d_geom, l->d_scan, l->d_check, n, drec, l->stream, crop.active() ? l->d_flags : nullptr, crop.x0,
-                                 crop.y0, crop.x1, crop.y1));
+                     ev ? ev[ST_FINALIZE] : nullptr, lazy ? &lw : nullptr, dcards, timed && lazy ? ctx->lazy_ev : nullptr));
+  ctx->lazy_timed = timed && lazy;
+  LAUNCH(launch_finalize_records(l->d_geom, l->d_scan, lazy ? nullptr : l->d_check, n, drec, l->stream, crop.active() ? l->d_flags : nullptr,
+                                 crop.x0, crop.y0, crop.x1, crop.y1));
   if (timed) CU(cudaEventRecord(ctx->ev[ST_COUNT], l->stream));
   return B200_OK;
 }
@@ -311,6 +327,14 @@ int collect_stage_times(b200_ctx *ctx, int n) {
     float ms = 0.0f;
     CU(cudaEventElapsedTime(&ms, ctx->ev[s], ctx->ev[s + 1]));
     ctx->stage_ms[s] += ms;
+  }
+  if (ctx->lazy_timed) {  // the lazy warp launches run inside the vseg bracket: book them under "warp"
+    for (int k = 0; k < 3; k++) {
+      float ms = 0.0f;
+      CU(cudaEventElapsedTime(&ms, ctx->lazy_ev[2 * k], ctx->lazy_ev[2 * k + 1]));
+      ctx->stage_ms[ST_WARP] += ms;
+      ctx->stage_ms[ST_VSEG] -= ms;
+    }
   }
   ctx->stage_frames += (uint64_t)n;
   return B200_OK;
@@ -334,6 +358,9 @@ int b200_ctx_create(b200_ctx **out, int device_ordinal, const char *weights_dir)
   for (int i = 0; i < 2; i++) CU(cudaStreamCreateWithFlags(&ctx->lane[i].stream, cudaStreamNonBlocking));
   ctx->stream = ctx->lane[0].stream;
   for (int i = 0; i <= ST_COUNT; i++) CU(cudaEventCreate(&ctx->ev[i]));
+  for (int i = 0; i < 6; i++) CU(cudaEventCreate(&ctx->lazy_ev[i]));
+  const char *mode_env = getenv("B200_DMZ_CARD_MODE");
+  if (mode_env && *mode_env) ctx->card_mode = atoi(mode_env) != 0;
   const char *chunk_env = getenv("B200_DMZ_HOST_CHUNK");
   if (chunk_env && atoi(chunk_env) > 0) ctx->host_chunk = atoi(chunk_env);
   const char *crop_env = getenv("B200_DMZ_CROP_MARGIN");
@@ -400,6 +427,8 @@ void b200_ctx_destroy(b200_ctx *ctx) {
   }
   for (int i = 0; i <= ST_COUNT; i++)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  for (int i = 0; i < 6; i++)
+    if (ctx->lazy_ev[i]) cudaEventDestroy(ctx->lazy_ev[i]);
   cudaFree(ctx->d_misc);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   cudaFree(ctx->d_vnorm);
@@ -418,6 +447,9 @@ void b200_transfer_bytes(const b200_ctx *ctx, uint64_t *h2d, uint64_t *d2h) {
 }
 void b200_set_crop_margin(b200_ctx *ctx, int margin) {
   if (ctx) ctx->crop_margin = margin;
+}
+void b200_set_card_mode(b200_ctx *ctx, int always_materialise) {
+  if (ctx) ctx->card_mode = always_materialise != 0;
 }
 
 int b200_ctx_reserve(b200_ctx *ctx, int max_frames, int width, int height) {
@@ -521,7 +553,13 @@ int b200_transform_card_batch(b200_ctx *ctx, const uint8_t *sample, int row_stri
   }
   LAUNCH(launch_corners_to_geom(dc, dv, n, orientation, upsample, l->d_geom, l->stream));
   uint8_t *dcards = mem == B200_MEM_DEVICE ? cards : l->d_cards;
-  LAUNCH(launch_warp(ds, drs, dfs, width, height, n, l->d_geom, dcards, nullptr, l->stream));
+  {
+    // the tile heuristics assume a card that fills the guide rectangle of a frame; a half-size chroma plane shows it at
+    // half that scale, which frame_h (the plane's own height) already expresses
+    const WarpSource S = warp_source(ds, drs, dfs, width, height, n, Crop());
+    const int portrait = orientation == B200_ORIENT_PORTRAIT || orientation == B200_ORIENT_PORTRAIT_UPSIDE_DOWN;
+    LAUNCH(launch_warp(S, l->d_geom, dcards, nullptr, WARP_FULL, nullptr, nullptr, portrait, l->stream));
+  }
   if (mem == B200_MEM_HOST) CU(cudaMemcpyAsync(cards, l->d_cards, kCardBytes * n, cudaMemcpyDeviceToHost, l->stream));
   CU(cudaStreamSynchronize(l->stream));
   return B200_OK;
@@ -559,12 +597,13 @@ int b200_process_frames_batch(b200_ctx *ctx, const uint8_t *y, int yrs, size_t y
   CU(cudaSetDevice(ctx->device));
   int rc = ensure_config(ctx, width, height, orientation, 1);
   if (rc) return rc;
+  const bool lazy = cards_out == nullptr && ctx->card_mode == 0;
   if (mem == B200_MEM_DEVICE) {
     Lane *l = &ctx->lane[0];
     rc = ensure_capacity(ctx, l, n, width, height, false);
     if (rc) return rc;
     uint8_t *dcards = cards_out ? cards_out : l->d_cards;
-    rc = pipeline_on_lane(ctx, l, y, yrs, yfs, width, height, n, dcards, records, ctx->profiling != 0);
+    rc = pipeline_on_lane(ctx, l, y, yrs, yfs, width, height, n, dcards, records, ctx->profiling != 0, lazy);
     if (rc) return rc;
     CU(cudaStreamSynchronize(l->stream));
     if (ctx->profiling) return collect_stage_times(ctx, n);
@@ -648,7 +687,7 @@ int b200_process_frames_batch(b200_ctx *ctx, const uint8_t *y, int yrs, size_t y
       if (rc) return rc;
       ctx->h2d_bytes += (uint64_t)width * height * cnt;
     }
-    rc = pipeline_on_lane(ctx, l, dy, drs, dfs, width, height, cnt, l->d_cards, l->d_records, false, crop);
+    rc = pipeline_on_lane(ctx, l, dy, drs, dfs, width, height, cnt, l->d_cards, l->d_records, false, lazy, crop);
     if (rc) return rc;
     CU(cudaMemcpyAsync(records + f0, l->d_records, sizeof(b200_frame_record) * cnt, cudaMemcpyDeviceToHost, l->stream));
     ctx->d2h_bytes += sizeof(b200_frame_record) * (uint64_t)cnt + (crop.active() ? cnt : 0) + (cards_out ? kCardBytes * cnt : 0);
@@ -666,7 +705,7 @@ int b200_process_frames_batch(b200_ctx *ctx, const uint8_t *y, int yrs, size_t y
     size_t dfs;
     rc = stage_planes(ctx, l->stream, y + (size_t)i * yfs, yrs, yfs, width, height, 1, B200_MEM_HOST, l->d_frames, &dy, &drs, &dfs);
     if (rc) return rc;
-    rc = pipeline_on_lane(ctx, l, dy, drs, dfs, width, height, 1, l->d_cards, l->d_records, false);
+    rc = pipeline_on_lane(ctx, l, dy, drs, dfs, width, height, 1, l->d_cards, l->d_records, false, lazy);
     if (rc) return rc;
     CU(cudaMemcpyAsync(records + i, l->d_records, sizeof(b200_frame_record), cudaMemcpyDeviceToHost, l->stream));
     if (cards_out) CU(cudaMemcpyAsync(cards_out + (size_t)i * kCardBytes, l->d_cards, kCardBytes, cudaMemcpyDeviceToHost, l->stream));

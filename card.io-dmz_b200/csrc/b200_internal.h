@@ -14,6 +14,7 @@
 #include <atomic>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "b200_dmz.h"
 
@@ -99,11 +100,27 @@ int launch_geometry(const GeomParams &g, const b200_line *lines, size_t plane_st
 int launch_homography_only(const float *src_pts, const float *dst_pts, int n, float *M, cudaStream_t s);
 int launch_corners_to_geom(const b200_corner_points *corners, const uint8_t *valid, int n, int orientation, int upsample,
                            FrameGeom *geom, cudaStream_t s);
-int launch_warp(const uint8_t *src, int row_stride, size_t frame_stride, int w, int h, int n, const FrameGeom *geom,
-                uint8_t *cards, unsigned int *card_check, cudaStream_t s, int ox = 0, int oy = 0);
+// W2 (warp.cu).  The planes the warp reads: n buffers of bw x bh pixels whose pixel (0, 0) sits at (ox, oy) of a
+// frame_w x frame_h frame (the whole plane: ox = oy = 0, bw x bh = the frame; host-buffer path: the uploaded crop).
+// Taps outside the buffer read as 0 (BORDER_CONSTANT for whole planes; for crops the caller redoes such frames).
+struct WarpSource {
+  const uint8_t *base;
+  int row_stride;
+  size_t frame_stride;
+  int bw, bh, ox, oy, frame_w, frame_h, n;
+};
+enum { WARP_FULL = 0, WARP_COARSE = 1, WARP_FINE = 2, WARP_STRIP = 3 };  // which card rows a launch produces (warp.cu)
+int launch_warp(const WarpSource &src, const FrameGeom *geom, uint8_t *cards, unsigned int *card_check, int mode,
+                const b200_scan *scans, const uint16_t *coarse_y, int portrait, cudaStream_t s);
+// lazy cards: launch_scan warps only the rows scan_card_image reads, at the points of the sequence where they are known
+struct LazyWarp {
+  WarpSource src;
+  int portrait;
+};
 int launch_scan(const NetWeights &wts, const uint8_t *cards, int n, const FrameGeom *geom_or_null, const uint8_t *valid,
                 float *vprob, uint8_t *q8 /* n * 16 * B200_Q8_STRIDE bytes: prepared digit patches */, b200_scan *scans, cudaStream_t s,
-                cudaEvent_t ev_vseg, cudaEvent_t ev_hseg, cudaEvent_t ev_cat, cudaEvent_t ev_fin);
+                cudaEvent_t ev_vseg, cudaEvent_t ev_hseg, cudaEvent_t ev_cat, cudaEvent_t ev_fin, const LazyWarp *lazy = nullptr,
+                uint8_t *lazy_cards = nullptr, cudaEvent_t *lazy_ev = nullptr);
 int launch_finalize_records(const FrameGeom *geom, const b200_scan *scans, const unsigned int *card_check, int n,
                             b200_frame_record *recs, cudaStream_t s, uint8_t *needs_full = nullptr, int cx0 = 0, int cy0 = 0,
                             int cx1 = 0, int cy1 = 0);

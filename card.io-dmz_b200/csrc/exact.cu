@@ -4,7 +4,7 @@
 //
 //   geometry_kernel        find_line_in_detection_rects tail + corner intersections   dmz.cpp:346-438, geometry.cpp
 //   householder_qr_solve8  llcv_calc_persp_transform = Eigen 3.2.4 householderQr().solve cv/warp.cpp:34-125
-//   warp_kernel            cvWarpPerspective(INTER_LINEAR + FILL_OUTLIERS, 0)          cv/warp.cpp:153-166
+//   (the warp itself, cvWarpPerspective, lives in warp.cu)
 //   vseg_select_kernel     best_segmentation_for_vseg_scores + gating                  scan/n_vseg.cpp:49-92, frame.cpp:38-47
 //   hseg_kernel            best_n_hseg / best_n_hseg_constrained                        scan/n_hseg.cpp:39-152
 //   scan_finish_kernel     number_score gate                                            scan/frame.cpp:63-64
@@ -263,198 +263,6 @@ __global__ void homography_only_kernel(const float *__restrict__ src, const floa
 }
 
 // ------------------------------------------------------------------------------------------------
-// W2: fixed-point perspective warp.  cv::warpPerspective traverses the destination in 64 x 16 blocks and
-// evaluates X0 = M0*x_block + M1*y + M2 once per block row, then (X0 + M0*x1) * (32 / W) per pixel; the
-// coordinates are rounded (half-to-even) to 1/32 px and the four taps are blended with 15-bit integer
-// weights, out-of-image taps being 0.  Each thread produces four horizontally adjacent pixels (one
-// 32-bit store); a CTA covers ROWS destination rows of one frame.
-// ------------------------------------------------------------------------------------------------
-constexpr int kQuadsPerRow = B200_CARD_W / 4;  // 107 four-pixel groups per destination row
-constexpr int kWarpThreads = 224;               // 2 x 107 = 214 workers (two rows per pass, equal work each),
-                                                // padded to whole warps so the final warp-shuffle reduction is well defined
-
-// src points at pixel (0, 0) of the sw x sh frame (the host-buffer path uploads only a crop and passes a
-// correspondingly shifted pointer); the crop is guaranteed by the caller to contain every in-image tap of the quad.
-//
-// Coordinates.  The reference computes W' = 32 / W (IEEE divide), fX = (X0 + M0 x1) W', X = cvRound(fX).  FP64 work
-// dominates this kernel's instruction count, so X is first computed the cheap way: fused multiply-adds for the three
-// linear forms, rcp.approx + ONE Newton step for 1/W (relative error ~1e-12, i.e. < 2e-7 in fX), and a single
-// FMA  t = fX * 2^14 + (1.5 * 2^52 + 2^30)  whose low word then holds round(fX * 2^14) + 2^30 as an unsigned integer
-// (valid while the high word is still that of the constant, i.e. -65536 <= fX < 196608 = 6144 px).  The fast value differs
-// from the real-number one by < 1e-3 of that integer's unit (2^-40 relative from the Newton step, times < 2^28.4), the
-// reference's own doubly-rounded value by far less, so both round to the same X unless the 14-bit fraction is EXACTLY
-// one half; the test below sends fractions within 1/16384 of one half (three values) to the exact reference sequence,
-// as it does W ~ 0 and far-away coordinates.  The result is bit-identical to the reference for every pixel.
-//
-// The fast path also steps its three linear forms from row to row by addition (the products M1 * y of the reference
-// are only needed bit-exactly on the exact path); the accumulated rounding over a CTA's rows is ~1e-14 relative, far
-// inside the margin above.  W is carried pre-scaled by 2^-19 (exact), so its reciprocal is already 32 * 2^14 / W.
-// warp_quad_fast returns a nonzero flag when any of the four pixels needs the exact sequence; the caller branches
-// ONCE per quad (the slow path is rare, so four separate branches only cost issue slots).
-__device__ __forceinline__ unsigned warp_quad_fast(double tX, double tY, double tW, double m0, double m3, double m6s, int X[4], int Y[4]) {
-  unsigned bad = 0;
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    const double kd = (double)k;  // immediate operand
-    const double Wf = k ? __fma_rn(m6s, kd, tW) : tW, nxf = k ? __fma_rn(m0, kd, tX) : tX, nyf = k ? __fma_rn(m3, kd, tY) : tY;
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(Wf));
-    r = __fma_rn(r, __fma_rn(-Wf, r, 1.0), r);
-    const double kMagic = 6755399441055744.0 + 1073741824.0;  // 1.5 * 2^52 + 2^30
-    const double tx = __fma_rn(nxf, r, kMagic), ty = __fma_rn(nyf, r, kMagic);
-    const unsigned ux = (unsigned)__double2loint(tx), uy = (unsigned)__double2loint(ty);
-    bad |= ((unsigned)__double2hiint(tx) ^ 0x43380000u) | ((unsigned)__double2hiint(ty) ^ 0x43380000u);
-    const unsigned nearx = (ux & 0x3FFFu) - (0x2000u - 1u), neary = (uy & 0x3FFFu) - (0x2000u - 1u);  // <= 2: within 1/16384 of .5
-    bad |= (unsigned)(min(nearx, neary) <= 2u);
-    X[k] = (int)((ux + 0x2000u) >> 14) - 65536, Y[k] = (int)((uy + 0x2000u) >> 14) - 65536;
-  }
-  return bad;
-}
-
-// the exact reference sequence for destination pixel (xb + x1, y), xb = origin of its 64-wide block
-// (separate multiply and add: this file is compiled with -fmad=false)
-__device__ __noinline__ int2 warp_coords_exact(const double *M, int xb, int y, int x1) {
-  const double X0 = M[0] * xb + M[1] * y + M[2];
-  const double Y0 = M[3] * xb + M[4] * y + M[5];
-  const double W0 = M[6] * xb + M[7] * y + M[8];
-  const double Wr = W0 + M[6] * x1;
-  const double nx = X0 + M[0] * x1, ny = Y0 + M[3] * x1;
-  double W = Wr != 0.0 ? 32. / Wr : 0.0;
-  const double gx = nx * W, gy = ny * W;
-  // cvt.rni.s32.f64: round-half-even, saturating == saturate_cast<int>(clamp(.))
-  return make_int2(__double2int_rn(gx), __double2int_rn(gy));
-}
-
-// The four bilinear taps of destination pixel (X, Y) (1/32 px fixed point); out-of-image taps read as 0.
-// (the all-taps-inside case is handled by the caller for the four pixels of a quad at once)
-__device__ __forceinline__ void warp_fetch_border(const uint8_t *__restrict__ src, int row_stride, int sw, int sh, int X, int Y, int v[4]) {
-  // saturate_cast<short>(X >> 5) only matters beyond +-32767 px, where every tap is outside the image anyway
-  const int sx = X >> 5, sy = Y >> 5;
-  if ((unsigned)sx < (unsigned)(sw - 1) && (unsigned)sy < (unsigned)(sh - 1)) {
-    const uint8_t *p = src + (sy * row_stride + sx);
-    v[0] = __ldg(p), v[1] = __ldg(p + 1), v[2] = __ldg(p + row_stride), v[3] = __ldg(p + row_stride + 1);
-  } else if (sx >= sw || sx + 1 < 0 || sy >= sh || sy + 1 < 0) {
-    v[0] = v[1] = v[2] = v[3] = 0;
-  } else {
-    const bool x0ok = sx >= 0 && sx < sw, x1ok = sx + 1 >= 0 && sx + 1 < sw;
-    const bool y0ok = sy >= 0 && sy < sh, y1ok = sy + 1 >= 0 && sy + 1 < sh;
-    v[0] = (x0ok && y0ok) ? __ldg(src + (sy * row_stride + sx)) : 0;
-    v[1] = (x1ok && y0ok) ? __ldg(src + (sy * row_stride + sx + 1)) : 0;
-    v[2] = (x0ok && y1ok) ? __ldg(src + ((sy + 1) * row_stride + sx)) : 0;
-    v[3] = (x1ok && y1ok) ? __ldg(src + ((sy + 1) * row_stride + sx + 1)) : 0;
-  }
-}
-
-// The 15-bit weights are (32-fx)(32-fy)*32, fx(32-fy)*32, (32-fx)fy*32, fx*fy*32, so
-//   (sum w_i v_i + 2^14) >> 15  ==  ((v0 (32-fx) + v1 fx)(32-fy) + (v2 (32-fx) + v3 fx) fy + 2^9) >> 10   exactly.
-// OpenCV's table holds {32767, 0, 0, 1} at (0,0) (saturate_cast<short>(32768) + compensation); that entry also
-// evaluates to v0 for every 8-bit v0, v3, as does this formula, so no special case is needed.
-__device__ __forceinline__ int warp_blend(int X, int Y, const int v[4]) {
-  const int fx = X & 31, fy = Y & 31;
-  const int ax = 32 - fx;
-  const int top = v[0] * ax + v[1] * fx, bot = v[2] * ax + v[3] * fx;
-  return (top * (32 - fy) + bot * fy + 512) >> 10;  // always in [0, 255]
-}
-
-// card_check (optional): per-frame checksum sum_i (i + 1) * card[i] mod 2^32, accumulated while the pixels are
-// still in registers (one global atomic per CTA) so that no later stage has to re-read the card for it.
-// ROWS = destination rows per CTA (a divisor of 270: no ragged last block).  The per-thread set-up (column block,
-// hoisted M products) is amortised over ROWS / 2 quads, which is why ROWS is not small.
-template <int ROWS>
-__global__ void __launch_bounds__(kWarpThreads, 4)  // measured: 3 resident CTAs (80 registers, no spills) are 4 % slower, 5 are ~10 % slower
-warp_kernel(const uint8_t *__restrict__ src, int row_stride, size_t frame_stride, int sw, int sh,
-            const FrameGeom *__restrict__ geom, uint8_t *__restrict__ cards, unsigned int *__restrict__ card_check, int ox, int oy) {
-  static_assert(B200_CARD_H % ROWS == 0 && ROWS % 2 == 0, "ROWS must be an even divisor of the card height");
-  const int frame = blockIdx.y;
-  const int row0 = blockIdx.x * ROWS;
-  __shared__ double sM[9];
-  __shared__ int s_ok;
-  __shared__ unsigned int s_sum;
-  __shared__ double sF[6];  // fast-path coefficients: M0, M3, M6 * 2^-19 (per pixel), 2 M1, 2 M4, 2 M7 * 2^-19 (per row pair)
-  if (threadIdx.x < 9) sM[threadIdx.x] = geom[frame].Minv[threadIdx.x];
-  if (threadIdx.x >= 32 && threadIdx.x < 38) {
-    const int i = threadIdx.x - 32;  // 0..2: column 0 of row i; 3..5: column 1 of row i - 3, doubled
-    const double m = geom[frame].Minv[i < 3 ? 3 * i : 3 * (i - 3) + 1];
-    sF[i] = m * (i < 3 ? 1.0 : 2.0) * ((i == 2 || i == 5) ? 1.0 / 524288.0 : 1.0);
-  }
-  if (threadIdx.x == 0) s_ok = geom[frame].all_found, s_sum = 0u;
-  __syncthreads();
-  uint8_t *dst = cards + (size_t)frame * (B200_CARD_W * B200_CARD_H);
-  // pointer to the (virtual) pixel (0, 0) of the frame; only addresses inside the uploaded crop are dereferenced
-  const uint8_t *s = src + (size_t)frame * frame_stride - ((ptrdiff_t)oy * row_stride + ox);
-  unsigned int sum = 0;
-  const int r0 = threadIdx.x >= kQuadsPerRow ? 1 : 0, q = threadIdx.x - r0 * kQuadsPerRow;
-  const int x = q * 4, xb = x & ~63;  // block origin: bw0 = 64
-  const bool ok = s_ok != 0;
-  int r = threadIdx.x < 2 * kQuadsPerRow ? r0 : ROWS;
-  // fast-path linear forms of this thread's first pixel, stepped two rows at a time
-  const double kWScale = 1.0 / 524288.0;  // 2^-19: 1 / (W * 2^-19) = 32 * 2^14 / W
-  double tX = __fma_rn(sM[0], (double)x, __fma_rn(sM[1], (double)(row0 + r0), sM[2]));
-  double tY = __fma_rn(sM[3], (double)x, __fma_rn(sM[4], (double)(row0 + r0), sM[5]));
-  double tW = __fma_rn(sM[6], (double)x, __fma_rn(sM[7], (double)(row0 + r0), sM[8])) * kWScale;
-  // Software pipeline over this thread's rows: the taps of row r are requested, the (FP64-heavy) coordinates of row
-  // r + 2 are computed while those loads are in flight, and only then are the taps blended.
-  int Xc[4], Yc[4];
-  auto coords = [&](int row, int *Xo, int *Yo) {
-    const volatile double *F = sF;  // re-read from shared memory every time: cheaper than holding 12 registers
-    const unsigned bad = warp_quad_fast(tX, tY, tW, F[0], F[1], F[2], Xo, Yo);
-    tX += F[3], tY += F[4], tW += F[5];
-    if (bad) {
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const int2 e = warp_coords_exact(sM, xb, row0 + row, x + k - xb);
-        Xo[k] = e.x, Yo[k] = e.y;
-      }
-    }
-  };
-  if (ok && r < ROWS) coords(r, Xc, Yc);
-  unsigned int doff = (unsigned)((row0 + r0) * B200_CARD_W + x);  // destination offset of this thread's quad
-#pragma unroll 1
-  while (r < ROWS) {
-    const int rn = r + 2;
-    unsigned int packed = 0;
-    if (ok) {
-      int v[4][4], Xn[4], Yn[4];
-      // all sixteen taps inside the image (the usual case): one test per quad, no per-pixel branches
-      unsigned inside = 1u;
-#pragma unroll
-      for (int k = 0; k < 4; k++)
-        inside &= (unsigned)((unsigned)(Xc[k] >> 5) < (unsigned)(sw - 1)) & (unsigned)((unsigned)(Yc[k] >> 5) < (unsigned)(sh - 1));
-      if (inside) {
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const unsigned int o0 = (unsigned)((Yc[k] >> 5) * row_stride + (Xc[k] >> 5));  // non-negative 32-bit offset inside one frame
-          const unsigned int o1 = o0 + (unsigned)row_stride;
-          v[k][0] = __ldg(s + o0), v[k][1] = __ldg(s + o0 + 1u), v[k][2] = __ldg(s + o1), v[k][3] = __ldg(s + o1 + 1u);
-        }
-      } else {
-#pragma unroll
-        for (int k = 0; k < 4; k++) warp_fetch_border(s, row_stride, sw, sh, Xc[k], Yc[k], v[k]);
-      }
-      if (rn < ROWS) coords(rn, Xn, Yn);
-      const unsigned int base = doff + 1u;
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const unsigned int px = (unsigned)warp_blend(Xc[k], Yc[k], v[k]);
-        packed |= px << (8 * k);
-        sum += (base + k) * px;
-        Xc[k] = Xn[k], Yc[k] = Yn[k];
-      }
-    }
-    *reinterpret_cast<unsigned int *>(dst + doff) = packed;
-    doff += 2u * B200_CARD_W;
-    r = rn;
-  }
-  if (card_check != nullptr) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    if ((threadIdx.x & 31) == 0 && sum) atomicAdd(&s_sum, sum);
-    __syncthreads();
-    if (threadIdx.x == 0 && s_sum) atomicAdd(&card_check[frame], s_sum);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
 // V0 tail: best_segmentation_for_vseg_scores (n_vseg.cpp:49-92), sequential float running sums.
 // pass 0: coarse best -> window for the fine rows.  pass 1: final vseg + gating (frame.cpp:38-47).
 // ------------------------------------------------------------------------------------------------
@@ -482,7 +290,8 @@ __device__ void best_segmentation(const float *__restrict__ vp /* [270][2] visa,
 constexpr int kSelFrames = 32, kSelThreads = 128, kSelStride = 541;
 
 __global__ void __launch_bounds__(kSelThreads)
-vseg_select_kernel(const float *__restrict__ vprob, const uint8_t *__restrict__ gate, int n, int pass, b200_scan *__restrict__ scans) {
+vseg_select_kernel(const float *__restrict__ vprob, const uint8_t *__restrict__ gate, int n, int pass, b200_scan *__restrict__ scans,
+                   uint16_t *__restrict__ coarse_y) {
   extern __shared__ float sel_rows[];  // [kSelFrames][kSelStride]
   const int f0 = blockIdx.x * kSelFrames, tid = threadIdx.x;
   const int nf = min(kSelFrames, n - f0);
@@ -504,7 +313,10 @@ vseg_select_kernel(const float *__restrict__ vprob, const uint8_t *__restrict__ 
   const int f = f0 + tid;
   b200_scan *sc = scans + f;
   if (gate && !gate[f]) {
-    if (pass == 0) sc->vseg.y_offset = 0xFFFF;  // no fine rows
+    if (pass == 0) {
+      sc->vseg.y_offset = 0xFFFF;  // no fine rows
+      if (coarse_y) coarse_y[f] = 0xFFFF;
+    }
     return;
   }
   float score;
@@ -512,6 +324,7 @@ vseg_select_kernel(const float *__restrict__ vprob, const uint8_t *__restrict__ 
   best_segmentation(sel_rows + tid * kSelStride, &score, &pt, &yo);
   if (pass == 0) {
     sc->vseg.y_offset = (uint16_t)yo;
+    if (coarse_y) coarse_y[f] = (uint16_t)yo;  // kept for the lazy warp: pass 1 overwrites the record
     return;
   }
   const uint8_t pat[3][19] = {{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0},
@@ -802,7 +615,7 @@ __global__ void finalize_records_kernel(const FrameGeom *__restrict__ geom, cons
   const unsigned int *sw_ = reinterpret_cast<const unsigned int *>(src);
   if (g.all_found) {
     for (int i = 0; i < 180; i++) dw[i] = sw_[i];
-    r->card_check = card_check[f];
+    r->card_check = card_check ? card_check[f] : 0u;  // lazy cards: no card, no checksum
   } else {
     for (int i = 0; i < 180; i++) dw[i] = 0u;
     r->card_check = 0u;
@@ -836,36 +649,6 @@ int launch_corners_to_geom(const b200_corner_points *corners, const uint8_t *val
                            FrameGeom *geom, cudaStream_t s) {
   corners_to_geom_kernel<<<blocks_for(n, 64), 64, 0, s>>>(corners, valid, n, orientation, upsample, geom);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
-}
-
-int launch_warp(const uint8_t *src, int row_stride, size_t frame_stride, int w, int h, int n, const FrameGeom *geom,
-                uint8_t *cards, unsigned int *card_check, cudaStream_t s, int ox, int oy) {
-  if (card_check && cudaMemsetAsync(card_check, 0, sizeof(unsigned int) * (size_t)n, s) != cudaSuccess) return -1;
-  int launches = 0;
-  // destination rows per CTA: the whole card for large batches (set-up amortised over 135 quads per thread; measured
-  // 26.75 ms per 100 k frames against 27.1 for 90 rows, 32 for 54, 34.7 for 10), 27 CTAs per frame for small ones
-  // (latency of a batch of one).  B200_DMZ_WARP_ROWS (10, 30, 54, 90 or 270) overrides.
-  static int forced = -1;
-  if (forced < 0) {
-    const char *e = getenv("B200_DMZ_WARP_ROWS");
-    forced = e ? atoi(e) : 0;
-    if (forced != 10 && forced != 30 && forced != 54 && forced != 90 && forced != 270) forced = 0;
-  }
-  const int rows = forced ? forced : (n >= 1024 ? 270 : (n >= 64 ? 90 : 10));
-  for (int f0 = 0; f0 < n; f0 += 65535) {
-    const int cnt = n - f0 < 65535 ? n - f0 : 65535;
-    const dim3 grid(B200_CARD_H / rows, cnt);
-    const uint8_t *sp = src + (size_t)f0 * frame_stride;
-    uint8_t *cp = cards + (size_t)f0 * (B200_CARD_W * B200_CARD_H);
-    unsigned int *kp = card_check ? card_check + f0 : nullptr;
-    if (rows == 10) warp_kernel<10><<<grid, kWarpThreads, 0, s>>>(sp, row_stride, frame_stride, w, h, geom + f0, cp, kp, ox, oy);
-    else if (rows == 30) warp_kernel<30><<<grid, kWarpThreads, 0, s>>>(sp, row_stride, frame_stride, w, h, geom + f0, cp, kp, ox, oy);
-    else if (rows == 54) warp_kernel<54><<<grid, kWarpThreads, 0, s>>>(sp, row_stride, frame_stride, w, h, geom + f0, cp, kp, ox, oy);
-    else if (rows == 270) warp_kernel<270><<<grid, kWarpThreads, 0, s>>>(sp, row_stride, frame_stride, w, h, geom + f0, cp, kp, ox, oy);
-    else warp_kernel<90><<<grid, kWarpThreads, 0, s>>>(sp, row_stride, frame_stride, w, h, geom + f0, cp, kp, ox, oy);
-    launches++;
-  }
-  return cudaGetLastError() == cudaSuccess ? launches : -1;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -994,12 +777,12 @@ int launch_scan_gate(const FrameGeom *geom, const uint8_t *valid, int n, uint8_t
   scan_gate_kernel<<<blocks_for(n, 256), 256, 0, s>>>(geom, valid, n, gate);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
-int launch_vseg_select(const float *vprob, const uint8_t *gate, int n, int pass, b200_scan *scans, cudaStream_t s) {
+int launch_vseg_select(const float *vprob, const uint8_t *gate, int n, int pass, b200_scan *scans, cudaStream_t s, uint16_t *coarse_y) {
   const size_t smem = sizeof(float) * kSelFrames * kSelStride;
   static PerDeviceOnce once;
   if (!once.ensure([smem] { return cudaFuncSetAttribute(vseg_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess; }))
     return -1;
-  vseg_select_kernel<<<blocks_for(n, kSelFrames), kSelThreads, smem, s>>>(vprob, gate, n, pass, scans);
+  vseg_select_kernel<<<blocks_for(n, kSelFrames), kSelThreads, smem, s>>>(vprob, gate, n, pass, scans, coarse_y);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 int launch_hseg(const uint8_t *cards, int n, b200_scan *scans, cudaStream_t s) {

@@ -18,7 +18,7 @@
 
 // exact.cu
 int launch_scan_gate(const FrameGeom *geom, const uint8_t *valid, int n, uint8_t *gate, cudaStream_t s);
-int launch_vseg_select(const float *vprob, const uint8_t *gate, int n, int pass, b200_scan *scans, cudaStream_t s);
+int launch_vseg_select(const float *vprob, const uint8_t *gate, int n, int pass, b200_scan *scans, cudaStream_t s, uint16_t *coarse_y = nullptr);
 int launch_hseg(const uint8_t *cards, int n, b200_scan *scans, cudaStream_t s);
 int launch_scan_finish(int n, b200_scan *scans, cudaStream_t s);
 
@@ -918,22 +918,35 @@ int launch_categorize_patches(const NetWeights &wts, const uint8_t *patches, con
 
 // scan_card_image for a batch: gate -> vseg (coarse, select, fine, select) -> hseg -> categorize -> finish.
 // vprob doubles as scratch: its tail holds the per-frame gate bytes.
+// Lazy cards (lazy != nullptr): nobody asked for the 428 x 270 cards, so only the rows this sequence reads are warped, each
+// set as soon as it is known -- the 68 coarse rows up front, the fine window once the coarse pass has chosen y0, and (rarely)
+// the final number strip if it left that window.  lazy_ev (optional): 6 events bracketing the three warp launches.
 int launch_scan(const NetWeights &wts, const uint8_t *cards, int n, const FrameGeom *geom, const uint8_t *valid,
                 float *vprob, uint8_t *q8, b200_scan *scans, cudaStream_t s, cudaEvent_t ev_vseg, cudaEvent_t ev_hseg, cudaEvent_t ev_cat,
-                cudaEvent_t ev_fin) {
+                cudaEvent_t ev_fin, const LazyWarp *lazy, uint8_t *lazy_cards, cudaEvent_t *lazy_ev) {
   int launches = 0, rc;
   uint8_t *gate = reinterpret_cast<uint8_t *>(vprob + (size_t)n * 540);
+  uint16_t *coarse_y = reinterpret_cast<uint16_t *>(gate) + n;  // bytes [2n, 4n) of the 16n-byte tail; gate uses [0, n)
+  auto lazy_warp = [&](int mode, int k) -> int {
+    if (lazy_ev && cudaEventRecord(lazy_ev[2 * k], s) != cudaSuccess) return -1;
+    const int r = launch_warp(lazy->src, geom, lazy_cards, nullptr, mode, scans, coarse_y, lazy->portrait, s);
+    if (lazy_ev && cudaEventRecord(lazy_ev[2 * k + 1], s) != cudaSuccess) return -1;
+    return r;
+  };
 #define STEP(call)          \
   rc = (call);              \
   if (rc < 0) return -1;    \
   launches += rc;
   if (ev_vseg) cudaEventRecord(ev_vseg, s);
   STEP(launch_scan_gate(geom, valid, n, gate, s));
+  if (lazy) { STEP(lazy_warp(WARP_COARSE, 0)); }
   if (cudaMemsetAsync(vprob, 0, (size_t)n * 540 * sizeof(float), s) != cudaSuccess) return -1;
   STEP(launch_vseg_rows(wts, cards, gate, scans, n, 0, vprob, nullptr, nullptr, s));
-  STEP(launch_vseg_select(vprob, gate, n, 0, scans, s));
+  STEP(launch_vseg_select(vprob, gate, n, 0, scans, s, coarse_y));
+  if (lazy) { STEP(lazy_warp(WARP_FINE, 1)); }
   STEP(launch_vseg_rows(wts, cards, gate, scans, n, 1, vprob, nullptr, nullptr, s));
   STEP(launch_vseg_select(vprob, gate, n, 1, scans, s));
+  if (lazy) { STEP(lazy_warp(WARP_STRIP, 2)); }
   if (ev_hseg) cudaEventRecord(ev_hseg, s);
   STEP(launch_hseg(cards, n, scans, s));
   if (ev_cat) cudaEventRecord(ev_cat, s);

@@ -102,7 +102,8 @@ typedef struct {
   float corners[8]; /* tl, bl, tr, br (x,y) */
   int32_t all_found;
   b200_scan scan;      /* valid iff all_found */
-  uint32_t card_check; /* sum_i (i+1)*card[i] mod 2^32 over the 428x270 card; 0 if !all_found */
+  uint32_t card_check; /* sum_i (i+1)*card[i] mod 2^32 over the 428x270 card; 0 if !all_found or if the cards were
+                          not materialised (b200_set_card_mode) */
 } b200_frame_record;
 
 /* ---- life cycle (replaces dmz_context_create / destroy + mz_create, dmz.h:45-51, mz.h:19-25) ---- */
@@ -123,6 +124,11 @@ void *b200_ctx_stream(const b200_ctx *ctx);
  * whose detected card quad reaches outside that rectangle are transparently redone from a full-frame upload;
  * b200_full_frame_redos counts them.  Results never depend on the margin. */
 void b200_set_crop_margin(b200_ctx *ctx, int margin);
+/* b200_process_frames_batch without cards_out: by default the 428 x 270 cards are never materialised -- only the ~111
+ * card rows scan_card_image reads (68 coarse vseg rows, the 43-row fine window, the 27-row number strip) are warped, and
+ * b200_frame_record.card_check is 0.  always_materialise != 0 (or $B200_DMZ_CARD_MODE=1) warps every card in full, as a
+ * call with cards_out does; every other field of the records is identical either way. */
+void b200_set_card_mode(b200_ctx *ctx, int always_materialise);
 uint64_t b200_full_frame_redos(const b200_ctx *ctx);
 /* Bytes copied host->device / device->host so far by b200_process_frames_batch(B200_MEM_HOST) calls. */
 void b200_transfer_bytes(const b200_ctx *ctx, uint64_t *h2d, uint64_t *d2h);
