@@ -178,6 +178,8 @@ def main():
     ap.add_argument("--frames", type=int, default=100000, help="frames per GPU per step (BASELINE configs[1]: 100k)")
     ap.add_argument("--e2e-frames", type=int, default=16384, help="frames per step on the host-buffer (e2e) path")
     ap.add_argument("--cpu-sample", type=int, default=4096, help="frames in the bounded CPU-baseline sample")
+    ap.add_argument("--card-mode", default="lazy", choices=["lazy", "full"],
+                    help="lazy (library default): no cards_out -> only the card rows the scan reads are warped; full: every card materialised")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -203,7 +205,7 @@ def main():
         dist = dist_mod
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     pkg = load_pkg()
-    dmz = pkg.Dmz(device=local_rank)
+    dmz = pkg.Dmz(device=local_rank, materialise_cards=args.card_mode == "full")
     F = args.frames
 
     # ---- synthetic deck of this rank, generated on the device (frames [rank*F, (rank+1)*F))
