@@ -99,6 +99,7 @@ def _load():
     lib.b200_ctx_stream.argtypes = [vp]
     lib.b200_ctx_stream.restype = vp
     lib.b200_detect_edges_batch.argtypes = [vp, vp, i, sz, vp, vp, i, sz, i, i, i, i, i, vp, vp, vp, vp]
+    lib.b200_detect_lines_batch.argtypes = [vp, vp, i, sz, i, i, i, i, i, vp]
     lib.b200_transform_card_batch.argtypes = [vp, vp, i, sz, i, i, i, vp, vp, i, i, i, vp]
     lib.b200_scan_cards_batch.argtypes = [vp, vp, i, vp, i, vp]
     lib.b200_process_frames_batch.argtypes = [vp, vp, i, sz, i, i, i, i, i, vp, vp]
@@ -353,6 +354,22 @@ class Dmz:
         self._check(self.lib.b200_process_frames_batch(self.ctx, C.c_void_p(d_frames), row_stride or w, frame_stride or w * h,
                                                        w, h, n, orientation, MEM_DEVICE, C.c_void_p(d_records),
                                                        C.c_void_p(d_cards) if d_cards else None))
+
+    def detect_lines_device(self, d_frames, n, w, h, d_lines, orientation=3):
+        """D1-D4 only on device-resident planes; d_lines: 4 * n LINE_DTYPE entries in device memory."""
+        self._check(self.lib.b200_detect_lines_batch(self.ctx, C.c_void_p(d_frames), w, w * h, w, h, n, orientation, MEM_DEVICE,
+                                                     C.c_void_p(d_lines)))
+
+    def detect_lines(self, y, orientation=3):
+        y = np.ascontiguousarray(y, np.uint8)
+        n, h, w = y.shape
+        lines = np.zeros((n, 4), LINE_DTYPE)
+        self._check(self.lib.b200_detect_lines_batch(self.ctx, _ptr(y), w, w * h, w, h, n, orientation, MEM_HOST, _ptr(lines)))
+        return lines
+
+    def categorize_patches_device(self, d_patches, n, d_out):
+        """n_categorize only on device-resident 27x19 u8 patches; d_out: n x 40 floats in device memory."""
+        self._check(self.lib.b200_categorize_patches_batch(self.ctx, C.c_void_p(d_patches), n, MEM_DEVICE, C.c_void_p(d_out)))
 
     def process_frames_host_ptr(self, h_frames, n, w, h, h_records, orientation=3):
         """Host pointers given as integers (e.g. pinned torch tensors): the e2e path, copies inside the call."""

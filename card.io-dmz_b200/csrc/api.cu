@@ -154,7 +154,7 @@ int ensure_config(b200_ctx *ctx, int w, int h, int orientation, int planes) {
     // 88 x 899) take the global-gradient variant with 32-bit work lists even where their gradients would fit
     bool wide_index = false;
     for (int s = 0; s < 4; s++)
-      wide_index = wide_index || (size_t)(ctx->dp[p].strip[s].w + 2) * (ctx->dp[p].strip[s].h + 2) > 65535;
+      wide_index = wide_index || (size_t)((ctx->dp[p].strip[s].w + 2 + 3) & ~3) * (ctx->dp[p].strip[s].h + 2) > 65535;
     if (wide_index || detect_smem_bytes(ctx->dp[p]) > (size_t)max_smem - 1024) {
       ctx->dp[p].use_global_grad = 1;
       if (detect_smem_bytes(ctx->dp[p]) > (size_t)max_smem - 1024)
@@ -219,7 +219,7 @@ int ensure_grad(b200_ctx *ctx, Lane *l, int n) {
     if (!ctx->dp[p].use_global_grad) continue;
     size_t mx = 0;
     for (int s = 0; s < 4; s++) {
-      size_t v = (size_t)(ctx->dp[p].strip[s].w + 2) * (ctx->dp[p].strip[s].h + 2);
+      size_t v = (size_t)((ctx->dp[p].strip[s].w + 2 + 3) & ~3) * (ctx->dp[p].strip[s].h + 2);  // detect_pad_pitch
       mx = v > mx ? v : mx;
     }
     size_t e = (size_t)n * 4 * mx * 2;
@@ -520,6 +520,36 @@ int b200_detect_edges_batch(b200_ctx *ctx, const uint8_t *y, int yrs, size_t yfs
   if (corners) CU(cudaMemcpy(corners, hc.data(), sizeof(b200_corner_points) * n, kind));
   if (all_found) CU(cudaMemcpy(all_found, hf.data(), n, kind));
   if (lines) CU(cudaMemcpy(lines, hl.data(), sizeof(b200_line) * n * 4, kind));
+  return B200_OK;
+}
+
+// D1-D4 alone: the four strips of every Y plane through Sobel-7 / adaptive Canny / gated Hough (best_line_for_sample,
+// dmz.cpp:224-271).  BASELINE configs[3] times this entry; the parity tests read the same taps through
+// b200_detect_edges_batch's `lines`.
+int b200_detect_lines_batch(b200_ctx *ctx, const uint8_t *y, int yrs, size_t yfs, int width, int height, int n, int orientation,
+                            int mem, b200_line *lines) {
+  if (!ctx || !y || !lines || n < 1) return fail(ctx, B200_EINVAL, "b200_detect_lines_batch: bad arguments");
+  if (!strides_ok(yrs, yfs, width, height)) return fail(ctx, B200_EINVAL, "b200_detect_lines_batch: bad strides");
+  CU(cudaSetDevice(ctx->device));
+  Lane *l = &ctx->lane[0];
+  int rc = ensure_config(ctx, width, height, orientation, 1);
+  if (rc) return rc;
+  const uint8_t *dy = y;
+  int drs = yrs;
+  size_t dfs = yfs;
+  b200_line *dl = lines;
+  if (mem == B200_MEM_HOST) {
+    rc = ensure_capacity(ctx, l, n, width, height, true);
+    if (rc) return rc;
+    rc = stage_planes(ctx, l->stream, y, yrs, yfs, width, height, n, mem, l->d_frames, &dy, &drs, &dfs);
+    if (rc) return rc;
+    dl = l->d_lines;
+  }
+  rc = ensure_grad(ctx, l, n);
+  if (rc) return rc;
+  LAUNCH(launch_detect(ctx->dp[0], dy, drs, dfs, n, nullptr, nullptr, dl, l->d_grad, l->stream));
+  if (mem == B200_MEM_HOST) CU(cudaMemcpyAsync(lines, dl, sizeof(b200_line) * 4 * (size_t)n, cudaMemcpyDeviceToHost, l->stream));
+  CU(cudaStreamSynchronize(l->stream));
   return B200_OK;
 }
 

@@ -9,9 +9,16 @@
 //   global u8 strip --(32-bit coalesced loads)--> s_src[h][ws] with a 3-pixel replicated halo left and right
 //   Sobel: one work item per (column, row chunk) walks down its rows; each row filter is two dp4a over the eight
 //          bytes around the pixel (3 aligned LDS.32 + funnel shifts), the last seven row results of both kernels
-//          live in a register ring (no intermediate image) --> s_dx, s_dy (s16, zero-padded border)
+//          live in a register ring (no intermediate image).  What is stored per pixel is what the later stages read:
+//            s_mag  u16  |dx| + |dy| (65536 is stored as 65535 + a flag bit, see below)
+//            s_dx   s16  dx (the Hough gate needs dx and dy: dy = +-(mag - |dx|), sign in the flag byte)
+//            s_map  u8   bits 0-1 state {0 candidate, 1 no edge, 2 edge}, bits 2-3 NMS sector {0 horizontal, 1 vertical,
+//                        2 diagonal with dx dy > 0, 3 diagonal with dx dy < 0}, bit 4 dy < 0, bit 5 mag == 65536
+//          all three with a zero / "no edge" border and a row pitch that is a multiple of four pixels
 //   thresholds: block reduction (warp shuffles) of the saturated |dx| + |dy| sums, 64-bit exact
-//   NMS: per pixel from s_dx / s_dy --> s_map {0 candidate, 1 no edge, 2 edge}; candidates go to a work list
+//   NMS step 1: FOUR magnitudes per LDS.64 against the low threshold; the ~45 % that pass are queued per warp
+//   NMS step 2: 32 dense lanes: sector -> neighbour offset, two neighbour magnitudes, state byte; weak candidates go to
+//          a work list, strong ones straight to the vote list
 //   hysteresis: propagation over the candidate list to the unique fixed point (= the reference's stack walk)
 //   Hough: gated edge pixels go to a vote list; shared-memory atomics into a compacted accumulator (only the
 //          reachable rho range per angle)
@@ -53,8 +60,9 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
 template <typename IdxT>
 struct SmemLayout {
   uint8_t *src;          // h x w source strip (dead after Sobel: its storage then holds the work lists)
-  int16_t *dx, *dy;      // (h + 2) x (w + 2), zero border: no bounds checks in the NMS neighbourhood
-  uint8_t *map;          // (h + 2) x (w + 2): 0 candidate, 1 no edge (also the border), 2 edge
+  unsigned short *mag;   // (h + 2) x wpm: |dx| + |dy|, zero border: no bounds checks in the NMS neighbourhood
+  int16_t *dx;           // (h + 2) x wpm (borders never read)
+  uint8_t *map;          // (h + 2) x wpm: state | sector << 2 | (dy < 0) << 4 | (mag == 65536) << 5; border = 1
   IdxT *list;            // candidate list (hysteresis), then vote list (Hough): padded pixel indices; aliases src
   unsigned int *acc;     // compacted Hough accumulator
 };
@@ -62,6 +70,8 @@ struct SmemLayout {
 __host__ __device__ __forceinline__ size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 // source row stride: up to 6 bytes before the strip, 3-px halo after it, 4-byte aligned, room for the 12-byte reads
 __host__ __device__ __forceinline__ int detect_src_stride(int w) { return ((w + 6 + 3 + 3) & ~3) + 8; }
+// row pitch (pixels) of the padded magnitude / dx / map arrays: w + 2 rounded up to four (LDS.64 = four magnitudes)
+__host__ __device__ __forceinline__ int detect_pad_pitch(int w) { return (w + 2 + 3) & ~3; }
 
 // Per-thread 2-D walk over a w x h strip without integer division inside the loop:
 //   w <= T: tx = tid % w, ty = tid / w (computed once), rows advance by T / w;  w > T: tx = tid, columns advance by T.
@@ -93,7 +103,7 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
                      b200_line *__restrict__ lines, int16_t *__restrict__ grad_scratch, size_t grad_scratch_stride, int ox, int oy) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __shared__ unsigned long long s_red[kThreads / 32];
-  __shared__ int s_low, s_high, s_nvote, s_nedge, s_overflow;
+  __shared__ int s_low, s_high, s_nvote, s_nedge, s_overflow, s_sat;
   __shared__ int s_cpre[kWarps + 1];          // per-warp candidate counts, then their exclusive prefix
 
   const int strip = blockIdx.x;
@@ -101,7 +111,7 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
   const int tid = threadIdx.x;
   const StripDesc &S = P.strip[strip];
   const int w = S.w, h = S.h, npx = w * h;
-  const int wp = w + 2, npad = wp * (h + 2);
+  const int wp = detect_pad_pitch(w), npad = wp * (h + 2);  // padded arrays: pixel (x, y) at (y + 1) * wp + x + 1
   // Source rows in shared memory: pixel c of the strip sits at byte H + c, H in [3, 6] chosen so that the aligned 32-bit
   // words of the global row land on aligned shared-memory words (whole-word copies); 3-px replicated halo each side.
   const bool word_ok = ((reinterpret_cast<uintptr_t>(plane) | (uintptr_t)row_stride | (uintptr_t)frame_stride) & 3u) == 0;
@@ -129,12 +139,12 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
   L.src = smem_raw + off;
   off = align16(off + (size_t)ws * h);
   if constexpr (kGlobalGrad) {
-    L.dx = grad_scratch + ((size_t)frame * 4 + strip) * grad_scratch_stride;
-    L.dy = L.dx + grad_scratch_stride / 2;
+    L.mag = reinterpret_cast<unsigned short *>(grad_scratch + ((size_t)frame * 4 + strip) * grad_scratch_stride);
+    L.dx = reinterpret_cast<int16_t *>(L.mag) + grad_scratch_stride / 2;
   } else {
-    L.dx = reinterpret_cast<int16_t *>(smem_raw + off);
+    L.mag = reinterpret_cast<unsigned short *>(smem_raw + off);
     off = align16(off + (size_t)npad * 2);
-    L.dy = reinterpret_cast<int16_t *>(smem_raw + off);
+    L.dx = reinterpret_cast<int16_t *>(smem_raw + off);
     off = align16(off + (size_t)npad * 2);
   }
   L.map = smem_raw + off;
@@ -158,11 +168,28 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
       const int words = (shift + w + 3) >> 2;  // words per row; the bytes around the strip they carry are overwritten by the halo
       const int q0 = (H - shift) >> 2;         // shared-memory word of the first global word
       const Walk k = make_walk(tid, words, kThreads);
-      if (k.active)
-        for (int row = k.ty; row < h; row += k.ystep)
-          for (int q = k.tx; q < words; q += k.xstep)
-            reinterpret_cast<unsigned int *>(L.src + row * ws)[q0 + q] =
-                __ldg(reinterpret_cast<const unsigned int *>(base + (size_t)row * row_stride - shift) + q);
+      if (k.active) {
+        if (k.xstep >= words) {
+          // one column of words per thread (every strip narrower than 4 * kThreads pixels): pointers advance by
+          // constants, four independent loads in flight
+          const unsigned int *gp = reinterpret_cast<const unsigned int *>(base + (size_t)k.ty * row_stride - shift) + k.tx;
+          unsigned int *sp = reinterpret_cast<unsigned int *>(L.src + k.ty * ws) + q0 + k.tx;
+          const size_t gstep = ((size_t)k.ystep * row_stride) >> 2;
+          const int sstep = (k.ystep * ws) >> 2;
+          int row = k.ty;
+          for (; row + 3 * k.ystep < h; row += 4 * k.ystep) {
+            const unsigned int a = __ldg(gp), b = __ldg(gp + gstep), c = __ldg(gp + 2 * gstep), d = __ldg(gp + 3 * gstep);
+            sp[0] = a, sp[sstep] = b, sp[2 * sstep] = c, sp[3 * sstep] = d;
+            gp += 4 * gstep, sp += 4 * sstep;
+          }
+          for (; row < h; row += k.ystep, gp += gstep, sp += sstep) *sp = __ldg(gp);
+        } else {
+          for (int row = k.ty; row < h; row += k.ystep)
+            for (int q = k.tx; q < words; q += k.xstep)
+              reinterpret_cast<unsigned int *>(L.src + row * ws)[q0 + q] =
+                  __ldg(reinterpret_cast<const unsigned int *>(base + (size_t)row * row_stride - shift) + q);
+        }
+      }
     } else {
       const Walk k = make_walk(tid, w, kThreads);
       if (k.active)
@@ -171,18 +198,21 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
     }
   }
   for (int i = tid; i < S.ncells; i += kThreads) L.acc[i] = 0u;
-  // zero the one-pixel border of dx / dy, mark the border of the map as "no edge"
+  // border of the padded arrays: magnitude 0, state "no edge" (top and bottom rows, column 0 and columns w + 1 .. wp - 1)
   for (int i = tid; i < wp; i += kThreads) {
     const int j = (h + 1) * wp + i;
-    L.dx[i] = 0, L.dy[i] = 0, L.map[i] = 1;
-    L.dx[j] = 0, L.dy[j] = 0, L.map[j] = 1;
+    L.mag[i] = 0, L.map[i] = 1;
+    L.mag[j] = 0, L.map[j] = 1;
   }
-  for (int y = tid; y < h; y += kThreads) {
-    const int a = (y + 1) * wp, b = a + wp - 1;
-    L.dx[a] = 0, L.dy[a] = 0, L.map[a] = 1;
-    L.dx[b] = 0, L.dy[b] = 0, L.map[b] = 1;
+  {
+    const int nb = wp - w;  // border columns per row: 1 on the left, nb - 1 on the right
+    for (int i = tid; i < h * nb; i += kThreads) {
+      const int y = i / nb, c = i - y * nb;
+      const int a = (y + 1) * wp + (c == 0 ? 0 : w + c);
+      L.mag[a] = 0, L.map[a] = 1;
+    }
   }
-  if (tid == 0) s_nvote = 0, s_nedge = 0, s_overflow = 0;
+  if (tid == 0) s_nvote = 0, s_nedge = 0, s_overflow = 0, s_sat = 0;
   __syncthreads();
   // BORDER_REPLICATE halo: three copies of the first / last pixel of every row
   for (int y = tid; y < h; y += kThreads) {
@@ -230,9 +260,19 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
                      5 * (sx[(k + 4) % 7] - sx[(k + 2) % 7]);                                  // derivative down the column
             gx = clampi(gx, -32768, 32767);  // saturate_cast<short>
             gy = clampi(gy, -32768, 32767);
+            // NMS inputs (canny.cpp:222-236) while dx, dy are in registers.  The reference's int64 products fit in 32
+            // unsigned bits here: |dx|, |dy| <= 32768 after the s16 saturation, so tg22x <= 4.5e8, tg67x <= 2.6e9 < 2^32
+            const unsigned int ax = (unsigned)abs(gx), ay = (unsigned)abs(gy);
+            const unsigned int m = ax + ay;          // <= 65536
+            const unsigned int tg22x = ax * 13573u;  // TG22 = (int)(0.41421356 * 2^15 + 0.5)
+            const unsigned int ys = ay << 15;
+            const unsigned int sector = ys < tg22x ? 0u : (ys > tg22x + (ax << 16) ? 1u : (((gx ^ gy) < 0) ? 3u : 2u));
+            const unsigned int hi16 = m >> 16;       // 1 only for dx == dy == -32768
+            L.mag[o] = (unsigned short)(m - hi16);   // 65536 -> 65535 + flag bit
             L.dx[o] = (int16_t)gx;
-            L.dy[o] = (int16_t)gy;
-            abs_sum += (unsigned)min(abs(gx), 32767) + (unsigned)min(abs(gy), 32767);  // cvAbs saturates, canny.cpp:355-361
+            L.map[o] = (uint8_t)(1u | (sector << 2) | ((unsigned)(gy < 0) << 4) | (hi16 << 5));
+            if (hi16) s_sat = 1;  // (block-wide flag: step 2 then rebuilds the 17-bit magnitudes)
+            abs_sum += min(ax, 32767u) + min(ay, 32767u);  // cvAbs saturates, canny.cpp:355-361
             o += wp;
           }
         }
@@ -252,10 +292,14 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
   }
   __syncthreads();
   const int low = s_low, high = s_high;
+  const bool sat = s_sat != 0;  // some magnitude is 65536: compare 17-bit values (mag + flag bit)
 
   // gradient-direction gate of the Hough stage (hough.cpp:126-150) for the pixel at padded index o
   auto gate = [&](int o) -> bool {
-    const int del_x = L.dx[o], del_y = L.dy[o];
+    const int del_x = L.dx[o];
+    const unsigned int b = L.map[o];
+    const int ady = (int)L.mag[o] + (int)((b >> 5) & 1u) - abs(del_x);
+    const int del_y = (b & 16u) ? -ady : ady;
     if (del_x != 0) {
       const float slope = (float)del_y / (float)del_x;
       return S.vertical ? (slope >= S.slope_a && slope <= S.slope_b) : (slope >= S.slope_a || slope <= S.slope_b);
@@ -271,41 +315,33 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
 
   // ---- 4. non-maxima suppression, canny.cpp:220-285.  The source strip is dead now: weak candidates go to the
   // hysteresis work lists, strong pixels (edges for sure) to the vote list (the direction gate is applied when voting).
-  // Two steps per warp, no block barrier between them.  Step 1, every pixel (flat round-robin walk, x and y advance
-  // without a division): |dx| + |dy| against the low threshold; the ~45 % that pass are queued in a 64-entry ring of
-  // the warp (ballot + popc, no atomics).  Step 2, whenever 32 are queued: the direction test on 32 DENSE lanes -- the
-  // sector becomes a neighbour OFFSET by selects and both neighbour magnitudes are fetched, one straight-line body.
-  // (Testing every pixel in place made all 32 lanes pay for the 45 %; branching per pixel made every warp pay for all
-  // three sectors.)  Weak candidates are appended to the warp's own list segment, again without atomics.
+  // Two steps per warp, no block barrier between them.  Step 1 walks the padded magnitude array four pixels per lane
+  // (one 64-bit load; border pixels hold 0 and never pass): magnitude against the low threshold, the ~45 % that pass are
+  // queued in a 64-entry ring of the warp (ballot + popc, no atomics).  Step 2, whenever 32 are queued: 32 DENSE lanes
+  // turn the stored sector into a neighbour offset, fetch the two neighbour magnitudes and set the state -- one
+  // straight-line body.  Weak candidates are appended to the warp's own list segment, again without atomics.
   {
     const int lane = tid & 31, wid = tid >> 5;
     const unsigned int lt = (1u << lane) - 1u;
     IdxT *q = q_rings + wid * 64;
     IdxT *clist = L.list + wid * cand_cap;
     int qhead = 0, qtail = 0, ccount = 0;
-    auto mag = [&](int j) -> int { return abs((int)L.dx[j]) + abs((int)L.dy[j]); };
     auto direction_test = [&](int cnt) {  // the first cnt queued pixels, one per lane
       bool weak = false, strong = false;
       int o = 0;
       if (lane < cnt) {
         o = q[(qhead + lane) & 63];
-        const int gx = L.dx[o], gy = L.dy[o];
-        // the reference's int64 products fit in 32 unsigned bits here: |dx|, |dy| <= 32768 after the s16 saturation,
-        // so tg22x <= 4.5e8, tg67x <= 2.6e9 < 2^32, ys <= 2^30
-        const unsigned int ax = (unsigned)abs(gx), ay = (unsigned)abs(gy);
-        const int m = (int)(ax + ay);
-        const unsigned int tg22x = ax * 13573u;  // TG22 = (int)(0.41421356 * 2^15 + 0.5)
-        const unsigned int tg67x = tg22x + (ax << 16);
-        const unsigned int ys = ay << 15;
-        const bool horiz = ys < tg22x, vert = ys > tg67x;
+        const unsigned int b = L.map[o];
+        const unsigned int sector = (b >> 2) & 3u;
         // horizontal: m > left && m >= right; vertical: m > up && m >= down; diagonal: m > both, along the gradient sign
-        const int sgn = ((gx ^ gy) < 0) ? -1 : 1;
-        const int off = horiz ? 1 : (vert ? wp : wp + sgn);
-        const int ge = (horiz || vert) ? 1 : 0;
-        const bool is_max = m > mag(o - off) && m + ge > mag(o + off);
+        const int off = sector == 0u ? 1 : (sector == 1u ? wp : (sector == 2u ? wp + 1 : wp - 1));
+        const int ge = sector < 2u ? 1 : 0;
+        int m = L.mag[o], m0 = L.mag[o - off], m1 = L.mag[o + off];
+        if (sat) m += (int)((b >> 5) & 1u), m0 += (int)((L.map[o - off] >> 5) & 1u), m1 += (int)((L.map[o + off] >> 5) & 1u);
+        const bool is_max = m > m0 && m + ge > m1;
         strong = is_max && m > high;
         weak = is_max && !strong;
-        L.map[o] = is_max ? (strong ? 2 : 0) : 1;
+        if (is_max) L.map[o] = (uint8_t)((b & ~3u) | (strong ? 2u : 0u));  // (non-maxima keep state 1)
       }
       const unsigned int wm = __ballot_sync(0xffffffffu, weak);
       if (weak) {
@@ -319,26 +355,30 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
         push_vote(o);
       }
     };
-    const int ystep = kThreads / w, xstep = kThreads - ystep * w;
-    int y = tid / w, x = tid - y * w;
-    const int iters = (npx + kThreads - 1) / kThreads;  // the same trip count for every lane: the loop holds warp votes
+    // groups of four padded pixels, rows 1 .. h (the all-zero border rows are skipped)
+    const int g0 = wp >> 2, ngroups = (wp >> 2) * h;
+    const int iters = (ngroups + kThreads - 1) / kThreads;  // the same trip count for every lane: the loop holds warp votes
+    const uint2 *mag4 = reinterpret_cast<const uint2 *>(L.mag);
+    const unsigned int ulow = (unsigned)low;
     for (int it = 0; it < iters; it++) {
-      // (lanes past the end of the strip re-read its last row and are masked out: no branch around the loads)
-      const bool in_strip = y < h;
-      const int o = (min(y, h - 1) + 1) * wp + x + 1;
-      const bool pend = in_strip && mag(o) > low;
-      if (in_strip && !pend) L.map[o] = 1;
-      const unsigned int pm = __ballot_sync(0xffffffffu, pend);
-      if (pend) q[(qtail + __popc(pm & lt)) & 63] = (IdxT)o;
-      qtail += __popc(pm);
-      if (qtail - qhead >= 32) {
-        __syncwarp();  // queue entries visible
-        direction_test(32);
-        qhead += 32;
-        __syncwarp();  // entries consumed before the ring wraps onto them
+      const int g = it * kThreads + tid;
+      uint2 v = make_uint2(0u, 0u);
+      if (g < ngroups) v = mag4[g0 + g];
+      const int o4 = (g0 + g) << 2;
+      const unsigned int mg[4] = {v.x & 0xFFFFu, v.x >> 16, v.y & 0xFFFFu, v.y >> 16};
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const bool pend = mg[k] > ulow;  // (a clipped 65536 reads 65535 > low as well: low <= 65534)
+        const unsigned int pm = __ballot_sync(0xffffffffu, pend);
+        if (pend) q[(qtail + __popc(pm & lt)) & 63] = (IdxT)(o4 + k);
+        qtail += __popc(pm);
+        if (qtail - qhead >= 32) {
+          __syncwarp();  // queue entries visible
+          direction_test(32);
+          qhead += 32;
+          __syncwarp();  // entries consumed before the ring wraps onto them
+        }
       }
-      x += xstep, y += ystep;
-      if (x >= w) x -= w, y++;
     }
     __syncwarp();
     if (qtail > qhead) direction_test(qtail - qhead);
@@ -360,8 +400,9 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
   // candidate lists to the fixed point, which is the reference's stack-walk result whatever the visiting order.
   // A promoted candidate is queued for voting on the spot (each candidate is promoted exactly once).
   // Within one sweep a thread may read a neighbour's map byte while its owner promotes it (racecheck reports that
-  // read/write pair as a warning): the byte only ever goes 0 -> 2, a stale 0 just defers the promotion to the next sweep,
+  // read/write pair as a warning): the state only ever goes 0 -> 2, a stale 0 just defers the promotion to the next sweep,
   // and the loop ends only after a sweep without any promotion, so the fixed point does not depend on the interleaving.
+  // (state 2 is the only one with bit 1 set: "some neighbour is an edge" is one OR over the eight bytes)
   {
     if (!s_overflow) {
       const int ncand = s_cpre[kWarps];
@@ -372,11 +413,11 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
           while (c >= s_cpre[seg + 1]) seg++;
           const int o = L.list[seg * cand_cap + (c - s_cpre[seg])];
           const uint8_t *m = L.map + o;
-          if (*m != 0) continue;
-          const bool hit = m[-wp - 1] == 2 || m[-wp] == 2 || m[-wp + 1] == 2 || m[-1] == 2 || m[1] == 2 || m[wp - 1] == 2 ||
-                           m[wp] == 2 || m[wp + 1] == 2;
-          if (hit) {
-            L.map[o] = 2;
+          const unsigned int b = *m;
+          if ((b & 3u) != 0u) continue;
+          const unsigned int any = m[-wp - 1] | m[-wp] | m[-wp + 1] | m[-1] | m[1] | m[wp - 1] | m[wp] | m[wp + 1];
+          if (any & 2u) {
+            L.map[o] = (uint8_t)(b | 2u);
             changed = 1;
             n_edge++;
             push_vote(o);
@@ -394,11 +435,11 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
             for (int x = k.tx; x < w; x += k.xstep) {
               const int o = (y + 1) * wp + x + 1;
               const uint8_t *m = L.map + o;
-              if (*m != 0) continue;
-              const bool hit = m[-wp - 1] == 2 || m[-wp] == 2 || m[-wp + 1] == 2 || m[-1] == 2 || m[1] == 2 ||
-                               m[wp - 1] == 2 || m[wp] == 2 || m[wp + 1] == 2;
-              if (hit) {
-                L.map[o] = 2;
+              const unsigned int b = *m;
+              if ((b & 3u) != 0u) continue;
+              const unsigned int any = m[-wp - 1] | m[-wp] | m[-wp + 1] | m[-1] | m[1] | m[wp - 1] | m[wp] | m[wp + 1];
+              if (any & 2u) {
+                L.map[o] = (uint8_t)(b | 2u);
                 changed = 1;
               }
             }
@@ -430,7 +471,7 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
       for (int y = k.ty; y < h; y += k.ystep)
         for (int x = k.tx; x < w; x += k.xstep) {
           const int o = (y + 1) * wp + x + 1;
-          if (L.map[o] != 2) continue;
+          if ((L.map[o] & 3u) != 2u) continue;
           n_edge++;
           if (gate(o)) {
 #pragma unroll
@@ -484,7 +525,7 @@ size_t detect_smem_bytes(const DetectParams &p) {
   size_t worst = 0;
   for (int s = 0; s < 4; s++) {
     const StripDesc &d = p.strip[s];
-    const size_t npad = (size_t)(d.w + 2) * (d.h + 2);
+    const size_t npad = (size_t)detect_pad_pitch(d.w) * (d.h + 2);
     const size_t ws = (size_t)detect_src_stride(d.w);
     size_t b = align16(ws * d.h) + align16(npad);  // padded src (later the work lists), map
     if (!p.use_global_grad) b += 2 * align16(npad * 2);
@@ -512,7 +553,7 @@ int launch_detect(const DetectParams &p, const uint8_t *plane, int row_stride, s
   }
   size_t max_npad = 0;
   for (int i = 0; i < 4; i++) {
-    size_t v = (size_t)(p.strip[i].w + 2) * (p.strip[i].h + 2);
+    size_t v = (size_t)detect_pad_pitch(p.strip[i].w) * (p.strip[i].h + 2);
     max_npad = v > max_npad ? v : max_npad;
   }
   // grid.y is limited to 65535 blocks: split very large batches

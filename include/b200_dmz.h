@@ -149,6 +149,12 @@ int b200_detect_edges_batch(b200_ctx *ctx, const uint8_t *y, int y_row_stride, s
                             int width, int height, int n, int orientation, int mem,
                             b200_edges *edges, b200_corner_points *corners, uint8_t *all_found, b200_line *lines);
 
+/* ---- best_line_for_sample (dmz.cpp:224-271) for the four detection strips of n Y planes: llcv_sobel7 x2 (cv/sobel.cpp:500),
+ * llcv_adaptive_canny7_precomputed_sobel (cv/canny.cpp:568), llcv_hough (cv/hough.cpp:52).  lines: 4*n taps in detection
+ * order top, bottom, left, right.  This is BASELINE.json configs[3]'s unit of work (Canny+Hough alone). */
+int b200_detect_lines_batch(b200_ctx *ctx, const uint8_t *y, int y_row_stride, size_t y_frame_stride, int width, int height,
+                            int n, int orientation, int mem, b200_line *lines);
+
 /* ---- dmz_transform_card (dmz.h:96, dmz.cpp:443-497), batched ----
  * valid (optional): frames with valid[i] == 0 are skipped (their card is zero-filled).
  * cards: n dense 428 x 270 planes. */

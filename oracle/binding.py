@@ -72,10 +72,19 @@ def lib_path(kind):
     """port: the plain-C restatement; ref: the reference's sources (SCAN_EXPIRY=0, re-entrant); refx: the same sources with
     SCAN_EXPIRY=1 (adds the expiry taps; function statics make it single-threaded)."""
     return {"port": os.path.join(HERE, "liboracle.so"), "ref": os.path.join(HERE, "_ref", "libdmz_ref.so"),
-            "refx": os.path.join(HERE, "_ref", "libdmz_ref_expiry.so")}[kind]
+            "refx": os.path.join(HERE, "_ref", "libdmz_ref_expiry.so"),
+            # timing only: the reference's sources at -O3 -march=x86-64-v3 (needs AVX2 + FMA on the host)
+            "refo3": os.path.join(HERE, "_ref", "libdmz_ref_o3.so")}[kind]
 
 
 def available(kind):
+    if kind == "refo3":
+        try:
+            flags = open("/proc/cpuinfo").read()
+        except OSError:
+            return False
+        if " avx2" not in flags or " fma" not in flags or " bmi2" not in flags:
+            return False
     return os.path.exists(lib_path(kind))
 
 
@@ -83,7 +92,7 @@ class Oracle:
     """Uniform front-end over either checker library."""
 
     def __init__(self, kind="port"):
-        assert kind in ("port", "ref", "refx")
+        assert kind in ("port", "ref", "refx", "refo3")
         self.kind = kind
         self.prefix = "orc_" if kind == "port" else "ref_"
         self.lib = C.CDLL(lib_path(kind))
@@ -123,7 +132,10 @@ class Oracle:
         f("luhn", [vp, i], i)
         f("card_type", [vp, i], i)
         f("bench_frames", [vp, i, i, i, vp, vp, i, i, vp], C.c_double)
-        if kind in ("ref", "refx"):
+        f("bench_stages", [vp, i, i, i, vp, vp, i, vp, vp])
+        f("bench_detect", [vp, i, i, i, vp, vp, i, i, vp], C.c_double)
+        f("bench_patches", [vp, i, i, vp], C.c_double)
+        if kind in ("ref", "refx", "refo3"):
             self.lib.ref_run_kats.restype = i
             self.lib.ref_sizeof.argtypes = [i]
             if kind == "refx":
@@ -352,6 +364,29 @@ class Oracle:
         recs = np.zeros(n, RECORD_DTYPE)
         secs = self._bench_frames(_p(frames), n, w, h, _p(cb), _p(cb), orientation, int(nthreads), _p(recs))
         return secs, recs
+
+    def bench_stages(self, frames, orientation=3):
+        """One thread: seconds spent in detect / transform / scan over the frames, and how many frames reached each."""
+        frames = np.ascontiguousarray(frames, np.uint8)
+        n, h, w = frames.shape
+        cb = np.full((h // 2, w // 2), 128, np.uint8)
+        secs, counts = np.zeros(3, np.float64), np.zeros(3, np.int32)
+        self._bench_stages(_p(frames), n, w, h, _p(cb), _p(cb), orientation, _p(secs), _p(counts))
+        return secs, counts
+
+    def bench_detect(self, frames, nthreads, orientation=3):
+        frames = np.ascontiguousarray(frames, np.uint8)
+        n, h, w = frames.shape
+        cb = np.full((h // 2, w // 2), 128, np.uint8)
+        found = C.c_int32(0)
+        secs = self._bench_detect(_p(frames), n, w, h, _p(cb), _p(cb), orientation, int(nthreads), C.byref(found))
+        return secs, found.value
+
+    def bench_patches(self, patches, nthreads):
+        patches = np.ascontiguousarray(patches, np.uint8).reshape(-1, 27 * 19)
+        out = np.zeros((patches.shape[0], 40), np.float32)
+        secs = self._bench_patches(_p(patches), patches.shape[0], int(nthreads), _p(out))
+        return secs, out
 
     # ---- scanner session --------------------------------------------------------------------
     def scanner_new(self):

@@ -1182,3 +1182,7 @@ double orc_bench_frames(const uint8_t *frames, int n, int w, int h, const uint8_
   free(jobs);
   return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
 }
+
+#define BT(x) orc_##x
+#include "bench_taps.inc"
+#undef BT

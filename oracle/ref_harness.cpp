@@ -452,6 +452,10 @@ double ref_bench_frames(const uint8_t *frames, int n, int w, int h, const uint8_
   return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
 }
 
+#define BT(x) ref_##x
+#include "bench_taps.inc"
+#undef BT
+
 #if SCAN_EXPIRY
 /* ---- expiry taps: only in the SCAN_EXPIRY=1 build (oracle/_ref/libdmz_ref_expiry.so) -------------------------- */
 
