@@ -7,6 +7,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <exception>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -82,15 +84,27 @@ struct b200_ctx {
 
 namespace {
 
-int fail(b200_ctx *c, int code, const char *fmt, ...) {
+int fail(b200_ctx *c, int code, const char *fmt, ...) noexcept {
   char buf[512];
   va_list ap;
   va_start(ap, fmt);
   vsnprintf(buf, sizeof(buf), fmt, ap);
   va_end(ap);
-  if (c) c->error = buf;
+  if (c) {
+    try {
+      c->error = buf;
+    } catch (...) {  // (out of memory while recording the message: the code still says what happened)
+    }
+  }
   return code;
 }
+
+// Every extern "C" entry point is a function-try-block closed by this: no C++ exception (std::bad_alloc from the host
+// vectors and strings, anything else) crosses the C ABI -- include/b200_dmz.h promises "never throw".
+#define B200_GUARD(ctx_expr)                                                                              \
+  catch (const std::bad_alloc &) { return fail((ctx_expr), B200_ENOMEM, "out of host memory"); }          \
+  catch (const std::exception &e_) { return fail((ctx_expr), B200_ECUDA, "internal error: %s", e_.what()); } \
+  catch (...) { return fail((ctx_expr), B200_ECUDA, "internal error (unknown exception)"); }
 
 #define CU(call)                                                                                     \
   do {                                                                                               \
@@ -344,7 +358,7 @@ int collect_stage_times(b200_ctx *ctx, int n) {
 
 extern "C" {
 
-int b200_ctx_create(b200_ctx **out, int device_ordinal, const char *weights_dir) {
+int b200_ctx_create(b200_ctx **out, int device_ordinal, const char *weights_dir) try {
   if (!out) return B200_EINVAL;
   *out = nullptr;
   b200_ctx *ctx = new b200_ctx();
@@ -416,7 +430,7 @@ int b200_ctx_create(b200_ctx **out, int device_ordinal, const char *weights_dir)
   }
   ctx->wts.vseg_norm = ctx->d_vnorm;
   return B200_OK;
-}
+} B200_GUARD(out ? *out : nullptr)
 
 void b200_ctx_destroy(b200_ctx *ctx) {
   if (!ctx) return;
@@ -452,11 +466,11 @@ void b200_set_card_mode(b200_ctx *ctx, int always_materialise) {
   if (ctx) ctx->card_mode = always_materialise != 0;
 }
 
-int b200_ctx_reserve(b200_ctx *ctx, int max_frames, int width, int height) {
+int b200_ctx_reserve(b200_ctx *ctx, int max_frames, int width, int height) try {
   if (!ctx || max_frames < 1) return B200_EINVAL;
   CU(cudaSetDevice(ctx->device));
   return ensure_capacity(ctx, &ctx->lane[0], max_frames, width, height, false);
-}
+} B200_GUARD(ctx)
 
 void b200_set_profiling(b200_ctx *ctx, int on) {
   if (!ctx) return;
@@ -474,7 +488,7 @@ int b200_stage_times(const b200_ctx *ctx, double ms[7], uint64_t *frames) {
 
 int b200_detect_edges_batch(b200_ctx *ctx, const uint8_t *y, int yrs, size_t yfs, const uint8_t *cb, const uint8_t *cr,
                             int crs, size_t cfs, int width, int height, int n, int orientation, int mem, b200_edges *edges,
-                            b200_corner_points *corners, uint8_t *all_found, b200_line *lines) {
+                            b200_corner_points *corners, uint8_t *all_found, b200_line *lines) try {
   if (!ctx || !y || n < 1 || (!cb) != (!cr)) return fail(ctx, B200_EINVAL, "b200_detect_edges_batch: bad arguments");
   if (!strides_ok(yrs, yfs, width, height) || (cb && !strides_ok(crs, cfs, width / 2, height / 2)))
     return fail(ctx, B200_EINVAL, "b200_detect_edges_batch: row_stride < width or frame_stride < row_stride * height");
@@ -521,13 +535,13 @@ int b200_detect_edges_batch(b200_ctx *ctx, const uint8_t *y, int yrs, size_t yfs
   if (all_found) CU(cudaMemcpy(all_found, hf.data(), n, kind));
   if (lines) CU(cudaMemcpy(lines, hl.data(), sizeof(b200_line) * n * 4, kind));
   return B200_OK;
-}
+} B200_GUARD(ctx)
 
 // D1-D4 alone: the four strips of every Y plane through Sobel-7 / adaptive Canny / gated Hough (best_line_for_sample,
 // dmz.cpp:224-271).  BASELINE configs[3] times this entry; the parity tests read the same taps through
 // b200_detect_edges_batch's `lines`.
 int b200_detect_lines_batch(b200_ctx *ctx, const uint8_t *y, int yrs, size_t yfs, int width, int height, int n, int orientation,
-                            int mem, b200_line *lines) {
+                            int mem, b200_line *lines) try {
   if (!ctx || !y || !lines || n < 1) return fail(ctx, B200_EINVAL, "b200_detect_lines_batch: bad arguments");
   if (!strides_ok(yrs, yfs, width, height)) return fail(ctx, B200_EINVAL, "b200_detect_lines_batch: bad strides");
   CU(cudaSetDevice(ctx->device));
@@ -551,11 +565,11 @@ int b200_detect_lines_batch(b200_ctx *ctx, const uint8_t *y, int yrs, size_t yfs
   if (mem == B200_MEM_HOST) CU(cudaMemcpyAsync(lines, dl, sizeof(b200_line) * 4 * (size_t)n, cudaMemcpyDeviceToHost, l->stream));
   CU(cudaStreamSynchronize(l->stream));
   return B200_OK;
-}
+} B200_GUARD(ctx)
 
 int b200_transform_card_batch(b200_ctx *ctx, const uint8_t *sample, int row_stride, size_t frame_stride, int width,
                               int height, int n, const b200_corner_points *corners, const uint8_t *valid, int orientation,
-                              int upsample, int mem, uint8_t *cards) {
+                              int upsample, int mem, uint8_t *cards) try {
   if (!ctx || !sample || !corners || !cards || n < 1) return fail(ctx, B200_EINVAL, "b200_transform_card_batch: bad arguments");
   if (!strides_ok(row_stride, frame_stride, width, height))
     return fail(ctx, B200_EINVAL, "b200_transform_card_batch: row_stride < width or frame_stride < row_stride * height");
@@ -593,9 +607,9 @@ int b200_transform_card_batch(b200_ctx *ctx, const uint8_t *sample, int row_stri
   if (mem == B200_MEM_HOST) CU(cudaMemcpyAsync(cards, l->d_cards, kCardBytes * n, cudaMemcpyDeviceToHost, l->stream));
   CU(cudaStreamSynchronize(l->stream));
   return B200_OK;
-}
+} B200_GUARD(ctx)
 
-int b200_scan_cards_batch(b200_ctx *ctx, const uint8_t *cards, int n, const uint8_t *valid, int mem, b200_scan *scans) {
+int b200_scan_cards_batch(b200_ctx *ctx, const uint8_t *cards, int n, const uint8_t *valid, int mem, b200_scan *scans) try {
   if (!ctx || !cards || !scans || n < 1) return fail(ctx, B200_EINVAL, "b200_scan_cards_batch: bad arguments");
   CU(cudaSetDevice(ctx->device));
   Lane *l = &ctx->lane[0];
@@ -617,10 +631,10 @@ int b200_scan_cards_batch(b200_ctx *ctx, const uint8_t *cards, int n, const uint
   if (mem == B200_MEM_HOST) CU(cudaMemcpyAsync(scans, l->d_scan, sizeof(b200_scan) * n, cudaMemcpyDeviceToHost, l->stream));
   CU(cudaStreamSynchronize(l->stream));
   return B200_OK;
-}
+} B200_GUARD(ctx)
 
 int b200_process_frames_batch(b200_ctx *ctx, const uint8_t *y, int yrs, size_t yfs, int width, int height, int n,
-                              int orientation, int mem, b200_frame_record *records, uint8_t *cards_out) {
+                              int orientation, int mem, b200_frame_record *records, uint8_t *cards_out) try {
   if (!ctx || !y || !records || n < 1) return fail(ctx, B200_EINVAL, "b200_process_frames_batch: bad arguments");
   if (!strides_ok(yrs, yfs, width, height))
     return fail(ctx, B200_EINVAL, "b200_process_frames_batch: row_stride < width or frame_stride < row_stride * height");
@@ -745,9 +759,9 @@ int b200_process_frames_batch(b200_ctx *ctx, const uint8_t *y, int yrs, size_t y
     ctx->d2h_bytes += sizeof(b200_frame_record);
   }
   return B200_OK;
-}
+} B200_GUARD(ctx)
 
-int b200_calc_persp_transform_batch(b200_ctx *ctx, const float *src_pts, const float *dst_pts, int n, float *M) {
+int b200_calc_persp_transform_batch(b200_ctx *ctx, const float *src_pts, const float *dst_pts, int n, float *M) try {
   if (!ctx || !src_pts || !dst_pts || !M || n < 1) return fail(ctx, B200_EINVAL, "b200_calc_persp_transform_batch: bad arguments");
   CU(cudaSetDevice(ctx->device));
   int rc = ensure_misc(ctx, sizeof(float) * 25 * (size_t)n);
@@ -759,9 +773,9 @@ int b200_calc_persp_transform_batch(b200_ctx *ctx, const float *src_pts, const f
   CU(cudaMemcpyAsync(M, dm, sizeof(float) * 9 * n, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return B200_OK;
-}
+} B200_GUARD(ctx)
 
-int b200_categorize_patches_batch(b200_ctx *ctx, const uint8_t *patches, int n, int mem, float *out) {
+int b200_categorize_patches_batch(b200_ctx *ctx, const uint8_t *patches, int n, int mem, float *out) try {
   if (!ctx || !patches || !out || n < 1) return fail(ctx, B200_EINVAL, "b200_categorize_patches_batch: bad arguments");
   CU(cudaSetDevice(ctx->device));
   const uint8_t *dp = patches;
@@ -781,9 +795,9 @@ int b200_categorize_patches_batch(b200_ctx *ctx, const uint8_t *patches, int n, 
   if (mem == B200_MEM_HOST) CU(cudaMemcpyAsync(out, dout, (size_t)n * 160, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return B200_OK;
-}
+} B200_GUARD(ctx)
 
-int b200_digit_models_batch(b200_ctx *ctx, const float *patches, int n, int mem, float *out) {
+int b200_digit_models_batch(b200_ctx *ctx, const float *patches, int n, int mem, float *out) try {
   if (!ctx || !patches || !out || n < 1) return fail(ctx, B200_EINVAL, "b200_digit_models_batch: bad arguments");
   CU(cudaSetDevice(ctx->device));
   const float *dp = patches;
@@ -800,12 +814,12 @@ int b200_digit_models_batch(b200_ctx *ctx, const float *patches, int n, int mem,
   if (mem == B200_MEM_HOST) CU(cudaMemcpyAsync(out, dout, (size_t)n * 40 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return B200_OK;
-}
+} B200_GUARD(ctx)
 
 // dmz_deinterleave_uint8_c2 over a batch: n interleaved 2-channel planes (width pixels = 2 * width bytes per row) into
 // two dense width x height planes each.
 int b200_deinterleave_c2_batch(b200_ctx *ctx, const uint8_t *interleaved, int row_stride, size_t frame_stride, int width, int height,
-                               int n, int mem, uint8_t *channel1, uint8_t *channel2) {
+                               int n, int mem, uint8_t *channel1, uint8_t *channel2) try {
   if (!ctx || !interleaved || !channel1 || !channel2 || n < 1 || width < 1 || height < 1 || row_stride < 2 * width)
     return fail(ctx, B200_EINVAL, "b200_deinterleave_c2_batch: bad arguments");
   CU(cudaSetDevice(ctx->device));
@@ -827,12 +841,12 @@ int b200_deinterleave_c2_batch(b200_ctx *ctx, const uint8_t *interleaved, int ro
   ctx->h2d_bytes += 2 * plane * n, ctx->d2h_bytes += 2 * plane * n;
   CU(cudaStreamSynchronize(ctx->stream));
   return B200_OK;
-}
+} B200_GUARD(ctx)
 
 // dmz_focus_score / dmz_brightness_score over a batch.  Host frames: only the scoring rectangle crosses PCIe (the
 // reference's ROI clamps the Sobel taps at the rectangle, so nothing outside it is ever read).
 int b200_frame_scores_batch(b200_ctx *ctx, const uint8_t *y, int yrs, size_t yfs, int width, int height, int n,
-                            int use_full_image, int mem, float *focus, float *brightness) {
+                            int use_full_image, int mem, float *focus, float *brightness) try {
   if (!ctx || !y || n < 1 || width < 1 || height < 1 || yrs < width || (!focus && !brightness))
     return fail(ctx, B200_EINVAL, "b200_frame_scores_batch: bad arguments");
   CU(cudaSetDevice(ctx->device));
@@ -872,11 +886,11 @@ int b200_frame_scores_batch(b200_ctx *ctx, const uint8_t *y, int yrs, size_t yfs
   ctx->d2h_bytes += (uint64_t)sizeof(float) * n * ((focus != nullptr) + (brightness != nullptr));
   CU(cudaStreamSynchronize(ctx->stream));
   return B200_OK;
-}
+} B200_GUARD(ctx)
 
 // best_expiry_seg over a batch.  The |Scharr| planes are scratch (231 KB per card), so the batch runs in chunks.
 int b200_best_expiry_seg_batch(b200_ctx *ctx, const uint8_t *cards, const uint16_t *y_offsets, int n, int mem,
-                               b200_expiry_group *groups, int max_groups, int32_t *n_groups, int32_t *n_dropped, int16_t *sobel_out) {
+                               b200_expiry_group *groups, int max_groups, int32_t *n_groups, int32_t *n_dropped, int16_t *sobel_out) try {
   if (!ctx || !cards || !y_offsets || !groups || !n_groups || n < 1 || max_groups < 1)
     return fail(ctx, B200_EINVAL, "b200_best_expiry_seg_batch: bad arguments");
   if (!ctx->d_slash) return fail(ctx, B200_EUNSUPPORTED, "modelm_730c4cbd.bin was not found in the weights directory");
@@ -918,9 +932,9 @@ int b200_best_expiry_seg_batch(b200_ctx *ctx, const uint8_t *cards, const uint16
     CU(cudaStreamSynchronize(ctx->stream));  // the scratch planes are reused by the next chunk
   }
   return B200_OK;
-}
+} B200_GUARD(ctx)
 
-static int expiry_call(b200_ctx *ctx, const uint8_t *patches, const float *prepared, int n, int mem, float *out) {
+static int expiry_call(b200_ctx *ctx, const uint8_t *patches, const float *prepared, int n, int mem, float *out) try {
   if (!ctx || (!patches && !prepared) || !out || n < 1) return fail(ctx, B200_EINVAL, "b200_expiry_*: bad arguments");
   if (!ctx->d_expiry) return fail(ctx, B200_EUNSUPPORTED, "modelc_bf4dd6c8.bin was not found in the weights directory");
   CU(cudaSetDevice(ctx->device));
@@ -944,10 +958,10 @@ static int expiry_call(b200_ctx *ctx, const uint8_t *patches, const float *prepa
   if (mem == B200_MEM_HOST) CU(cudaMemcpyAsync(out, dout, (size_t)n * 10 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return B200_OK;
-}
+} B200_GUARD(ctx)
 
 // categorize_expiry_digits' inner step for many characters at once: crop m 16x11 windows out of n_cards warped cards.
-int b200_expiry_digits_at_batch(b200_ctx *ctx, const uint8_t *cards, int n_cards, const int32_t *where, int m, int mem, float *out) {
+int b200_expiry_digits_at_batch(b200_ctx *ctx, const uint8_t *cards, int n_cards, const int32_t *where, int m, int mem, float *out) try {
   if (!ctx || !cards || !where || !out || n_cards < 1 || m < 1) return fail(ctx, B200_EINVAL, "b200_expiry_digits_at_batch: bad arguments");
   if (!ctx->d_expiry) return fail(ctx, B200_EUNSUPPORTED, "modelc_bf4dd6c8.bin was not found in the weights directory");
   CU(cudaSetDevice(ctx->device));
@@ -971,17 +985,17 @@ int b200_expiry_digits_at_batch(b200_ctx *ctx, const uint8_t *cards, int n_cards
   if (mem == B200_MEM_HOST) CU(cudaMemcpyAsync(out, dout, sizeof(float) * 10 * (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return B200_OK;
-}
+} B200_GUARD(ctx)
 
-int b200_expiry_digits_batch(b200_ctx *ctx, const uint8_t *patches, int n, int mem, float *out) {
+int b200_expiry_digits_batch(b200_ctx *ctx, const uint8_t *patches, int n, int mem, float *out) try {
   return expiry_call(ctx, patches, nullptr, n, mem, out);
-}
+} B200_GUARD(ctx)
 
-int b200_expiry_digit_models_batch(b200_ctx *ctx, const float *prepared, int n, int mem, float *out) {
+int b200_expiry_digit_models_batch(b200_ctx *ctx, const float *prepared, int n, int mem, float *out) try {
   return expiry_call(ctx, nullptr, prepared, n, mem, out);
-}
+} B200_GUARD(ctx)
 
-int b200_vseg_model_batch(b200_ctx *ctx, const float *rows, int n, int mem, float *out) {
+int b200_vseg_model_batch(b200_ctx *ctx, const float *rows, int n, int mem, float *out) try {
   if (!ctx || !rows || !out || n < 1) return fail(ctx, B200_EINVAL, "b200_vseg_model_batch: bad arguments");
   CU(cudaSetDevice(ctx->device));
   const float *dr = rows;
@@ -998,6 +1012,6 @@ int b200_vseg_model_batch(b200_ctx *ctx, const float *rows, int n, int mem, floa
   if (mem == B200_MEM_HOST) CU(cudaMemcpyAsync(out, dout, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return B200_OK;
-}
+} B200_GUARD(ctx)
 
 }  // extern "C"

@@ -10,15 +10,14 @@
 //   Sobel: one work item per (column, row chunk) walks down its rows; each row filter is two dp4a over the eight
 //          bytes around the pixel (3 aligned LDS.32 + funnel shifts), the last seven row results of both kernels
 //          live in a register ring (no intermediate image).  What is stored per pixel is what the later stages read:
-//            s_mag  u16  |dx| + |dy| (65536 is stored as 65535 + a flag bit, see below)
-//            s_dx   s16  dx (the Hough gate needs dx and dy: dy = +-(mag - |dx|), sign in the flag byte)
-//            s_map  u8   bits 0-1 state {0 candidate, 1 no edge, 2 edge}, bits 2-3 NMS sector {0 horizontal, 1 vertical,
-//                        2 diagonal with dx dy > 0, 3 diagonal with dx dy < 0}, bit 4 dy < 0, bit 5 mag == 65536
-//          all three with a zero / "no edge" border and a row pitch that is a multiple of four pixels
+//            s_md   u32  low half |dx| + |dy| (65536 is stored as 65535 + a flag bit), high half dx (s16): ONE store, and
+//                        one LDS.128 later yields four magnitudes; dy = +-(mag - |dx|) with its sign in the flag byte
+//            s_map  u8   bits 0-1 state {0 candidate, 1 no edge, 2 edge}, bit 4 dy < 0, bit 5 mag == 65536
+//          both with a zero / "no edge" border and a row pitch that is a multiple of four pixels
 //   thresholds: block reduction (warp shuffles) of the saturated |dx| + |dy| sums, 64-bit exact
-//   NMS step 1: FOUR magnitudes per LDS.64 against the low threshold; the ~45 % that pass are queued per warp
-//   NMS step 2: 32 dense lanes: sector -> neighbour offset, two neighbour magnitudes, state byte; weak candidates go to
-//          a work list, strong ones straight to the vote list
+//   NMS step 1: FOUR magnitudes per LDS.128 against the low threshold; the ones that pass are queued per warp
+//   NMS step 2: 32 dense lanes: sector from (|dx|, |dy|, signs) -> neighbour offset, two neighbour magnitudes, state
+//          byte; weak candidates go to a work list, strong ones straight to the vote list
 //   hysteresis: propagation over the candidate list to the unique fixed point (= the reference's stack walk)
 //   Hough: gated edge pixels go to a vote list; shared-memory atomics into a compacted accumulator (only the
 //          reachable rho range per angle)
@@ -60,9 +59,8 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
 template <typename IdxT>
 struct SmemLayout {
   uint8_t *src;          // h x w source strip (dead after Sobel: its storage then holds the work lists)
-  unsigned short *mag;   // (h + 2) x wpm: |dx| + |dy|, zero border: no bounds checks in the NMS neighbourhood
-  int16_t *dx;           // (h + 2) x wpm (borders never read)
-  uint8_t *map;          // (h + 2) x wpm: state | sector << 2 | (dy < 0) << 4 | (mag == 65536) << 5; border = 1
+  unsigned int *md;      // (h + 2) x wpm: |dx| + |dy| (low half, zero border: no bounds checks in the NMS neighbourhood) | dx << 16
+  uint8_t *map;          // (h + 2) x wpm: state | (dy < 0) << 4 | (mag == 65536) << 5; border = 1
   IdxT *list;            // candidate list (hysteresis), then vote list (Hough): padded pixel indices; aliases src
   unsigned int *acc;     // compacted Hough accumulator
 };
@@ -139,20 +137,15 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
   L.src = smem_raw + off;
   off = align16(off + (size_t)ws * h);
   if constexpr (kGlobalGrad) {
-    L.mag = reinterpret_cast<unsigned short *>(grad_scratch + ((size_t)frame * 4 + strip) * grad_scratch_stride);
-    L.dx = reinterpret_cast<int16_t *>(L.mag) + grad_scratch_stride / 2;
+    L.md = reinterpret_cast<unsigned int *>(grad_scratch + ((size_t)frame * 4 + strip) * grad_scratch_stride);  // stride = 2 npad int16
   } else {
-    L.mag = reinterpret_cast<unsigned short *>(smem_raw + off);
-    off = align16(off + (size_t)npad * 2);
-    L.dx = reinterpret_cast<int16_t *>(smem_raw + off);
-    off = align16(off + (size_t)npad * 2);
+    L.md = reinterpret_cast<unsigned int *>(smem_raw + off);
+    off = align16(off + (size_t)npad * 4);
   }
   L.map = smem_raw + off;
   off = align16(off + (size_t)npad);
+  // the Hough accumulator (used after the NMS) shares its storage with the per-warp rings of the NMS (128 entries each)
   L.acc = reinterpret_cast<unsigned int *>(smem_raw + off);
-  off = align16(off + (size_t)S.ncells * 4);
-  // per-warp rings of pixels whose magnitude exceeds the low threshold (64 entries each), in the dynamic block so that
-  // their addresses derive from the same base register as everything else
   IdxT *q_rings = reinterpret_cast<IdxT *>(smem_raw + off);
   // work lists alias the (by then dead) source strip: one candidate segment per warp (filled without atomics), then
   // the vote list; overflow falls back to full scans
@@ -197,19 +190,18 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
           for (int c = k.tx; c < w; c += k.xstep) L.src[row * ws + H + c] = __ldg(base + (size_t)row * row_stride + c);
     }
   }
-  for (int i = tid; i < S.ncells; i += kThreads) L.acc[i] = 0u;
   // border of the padded arrays: magnitude 0, state "no edge" (top and bottom rows, column 0 and columns w + 1 .. wp - 1)
   for (int i = tid; i < wp; i += kThreads) {
     const int j = (h + 1) * wp + i;
-    L.mag[i] = 0, L.map[i] = 1;
-    L.mag[j] = 0, L.map[j] = 1;
+    L.md[i] = 0u, L.map[i] = 1;
+    L.md[j] = 0u, L.map[j] = 1;
   }
   {
     const int nb = wp - w;  // border columns per row: 1 on the left, nb - 1 on the right
     for (int i = tid; i < h * nb; i += kThreads) {
       const int y = i / nb, c = i - y * nb;
       const int a = (y + 1) * wp + (c == 0 ? 0 : w + c);
-      L.mag[a] = 0, L.map[a] = 1;
+      L.md[a] = 0u, L.map[a] = 1;
     }
   }
   if (tid == 0) s_nvote = 0, s_nedge = 0, s_overflow = 0, s_sat = 0;
@@ -228,6 +220,7 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
   {
     const int items = w * S.nchunks;
     for (int it = tid; it < items; it += kThreads) {
+      unsigned int col_sum = 0;  // <= chunk_rows * 65534: 32 bits hold any strip a frame can have
       const int chunk = it / w, x = it - chunk * w;
       const int y0 = chunk * S.chunk_rows;
       const int y1 = min(h, y0 + S.chunk_rows);
@@ -260,23 +253,19 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
                      5 * (sx[(k + 4) % 7] - sx[(k + 2) % 7]);                                  // derivative down the column
             gx = clampi(gx, -32768, 32767);  // saturate_cast<short>
             gy = clampi(gy, -32768, 32767);
-            // NMS inputs (canny.cpp:222-236) while dx, dy are in registers.  The reference's int64 products fit in 32
-            // unsigned bits here: |dx|, |dy| <= 32768 after the s16 saturation, so tg22x <= 4.5e8, tg67x <= 2.6e9 < 2^32
+            // what the NMS reads (canny.cpp:222-236): the magnitude, dx, and two flag bits from which dy follows
             const unsigned int ax = (unsigned)abs(gx), ay = (unsigned)abs(gy);
-            const unsigned int m = ax + ay;          // <= 65536
-            const unsigned int tg22x = ax * 13573u;  // TG22 = (int)(0.41421356 * 2^15 + 0.5)
-            const unsigned int ys = ay << 15;
-            const unsigned int sector = ys < tg22x ? 0u : (ys > tg22x + (ax << 16) ? 1u : (((gx ^ gy) < 0) ? 3u : 2u));
-            const unsigned int hi16 = m >> 16;       // 1 only for dx == dy == -32768
-            L.mag[o] = (unsigned short)(m - hi16);   // 65536 -> 65535 + flag bit
-            L.dx[o] = (int16_t)gx;
-            L.map[o] = (uint8_t)(1u | (sector << 2) | ((unsigned)(gy < 0) << 4) | (hi16 << 5));
+            const unsigned int m = ax + ay;      // <= 65536
+            const unsigned int hi16 = m >> 16;   // 1 only for dx == dy == -32768
+            L.md[o] = (m - hi16) | ((unsigned)gx << 16);  // 65536 -> 65535 + flag bit
+            L.map[o] = (uint8_t)(1u | (((unsigned)gy >> 31) << 4) | (hi16 << 5));
             if (hi16) s_sat = 1;  // (block-wide flag: step 2 then rebuilds the 17-bit magnitudes)
-            abs_sum += min(ax, 32767u) + min(ay, 32767u);  // cvAbs saturates, canny.cpp:355-361
+            col_sum += min(ax, 32767u) + min(ay, 32767u);  // cvAbs saturates, canny.cpp:355-361
             o += wp;
           }
         }
       }
+      abs_sum += col_sum;
     }
   }
   // ---- 3. adaptive thresholds: low = floor(mean), high = floor(3 * mean), canny.cpp:568-580
@@ -296,9 +285,9 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
 
   // gradient-direction gate of the Hough stage (hough.cpp:126-150) for the pixel at padded index o
   auto gate = [&](int o) -> bool {
-    const int del_x = L.dx[o];
-    const unsigned int b = L.map[o];
-    const int ady = (int)L.mag[o] + (int)((b >> 5) & 1u) - abs(del_x);
+    const unsigned int mdv = L.md[o], b = L.map[o];
+    const int del_x = (int)mdv >> 16;
+    const int ady = (int)(mdv & 0xFFFFu) + (int)((b >> 5) & 1u) - abs(del_x);
     const int del_y = (b & 16u) ? -ady : ady;
     if (del_x != 0) {
       const float slope = (float)del_y / (float)del_x;
@@ -315,29 +304,40 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
 
   // ---- 4. non-maxima suppression, canny.cpp:220-285.  The source strip is dead now: weak candidates go to the
   // hysteresis work lists, strong pixels (edges for sure) to the vote list (the direction gate is applied when voting).
-  // Two steps per warp, no block barrier between them.  Step 1 walks the padded magnitude array four pixels per lane
-  // (one 64-bit load; border pixels hold 0 and never pass): magnitude against the low threshold, the ~45 % that pass are
-  // queued in a 64-entry ring of the warp (ballot + popc, no atomics).  Step 2, whenever 32 are queued: 32 DENSE lanes
-  // turn the stored sector into a neighbour offset, fetch the two neighbour magnitudes and set the state -- one
-  // straight-line body.  Weak candidates are appended to the warp's own list segment, again without atomics.
+  // Two steps per warp, no block barrier between them.  Step 1 walks the padded array four pixels per lane (one 128-bit
+  // load; border pixels hold 0 and never pass): magnitude against the low threshold, the pixels that pass are queued in a
+  // 128-entry ring of the warp -- two pixels per ballot round (a lane's count is 0..2: two ballots give its slot and the
+  // warp total, no atomics).  Step 2, whenever 32 are queued: 32 DENSE lanes rebuild (|dx|, |dy|, signs) from the packed
+  // word and the flag byte, turn the sector into a neighbour offset by selects, fetch the two neighbour magnitudes and set
+  // the state -- one straight-line body.  Weak candidates are appended to the warp's own list segment, again without
+  // atomics.  (The reference's int64 products fit in 32 bits here: |dx|, |dy| <= 32768 after the s16 saturation.)
   {
     const int lane = tid & 31, wid = tid >> 5;
     const unsigned int lt = (1u << lane) - 1u;
-    IdxT *q = q_rings + wid * 64;
+    IdxT *q = q_rings + wid * 128;
     IdxT *clist = L.list + wid * cand_cap;
     int qhead = 0, qtail = 0, ccount = 0;
     auto direction_test = [&](int cnt) {  // the first cnt queued pixels, one per lane
       bool weak = false, strong = false;
       int o = 0;
       if (lane < cnt) {
-        o = q[(qhead + lane) & 63];
-        const unsigned int b = L.map[o];
-        const unsigned int sector = (b >> 2) & 3u;
+        o = q[(qhead + lane) & 127];
+        const unsigned int mdv = L.md[o], b = L.map[o];
+        const unsigned int hi = sat ? (b >> 5) & 1u : 0u;
+        const int gx = (int)mdv >> 16;
+        const int m = (int)((mdv & 0xFFFFu) + hi);
+        const unsigned int ax = (unsigned)abs(gx), ay = (unsigned)m - ax;
+        const unsigned int tg22x = ax * 13573u;  // TG22 = (int)(0.41421356 * 2^15 + 0.5)
+        const unsigned int ys = ay << 15;        // tg22x <= 4.5e8, tg67x = tg22x + ax 2^16 <= 2.6e9 < 2^32, ys <= 2^30
+        const bool horiz = ys < tg22x, vert = ys > tg22x + (ax << 16);
+        const unsigned int opposite = ((unsigned)gx >> 31) ^ ((b >> 4) & 1u);  // sign(dx) != sign(dy), as (dx ^ dy) < 0
         // horizontal: m > left && m >= right; vertical: m > up && m >= down; diagonal: m > both, along the gradient sign
-        const int off = sector == 0u ? 1 : (sector == 1u ? wp : (sector == 2u ? wp + 1 : wp - 1));
-        const int ge = sector < 2u ? 1 : 0;
-        int m = L.mag[o], m0 = L.mag[o - off], m1 = L.mag[o + off];
-        if (sat) m += (int)((b >> 5) & 1u), m0 += (int)((L.map[o - off] >> 5) & 1u), m1 += (int)((L.map[o + off] >> 5) & 1u);
+        int off = wp + 1 - 2 * (int)opposite;
+        off = vert ? wp : off;
+        off = horiz ? 1 : off;
+        const int ge = (horiz || vert) ? 1 : 0;
+        int m0 = (int)(L.md[o - off] & 0xFFFFu), m1 = (int)(L.md[o + off] & 0xFFFFu);
+        if (sat) m0 += (int)((L.map[o - off] >> 5) & 1u), m1 += (int)((L.map[o + off] >> 5) & 1u);
         const bool is_max = m > m0 && m + ge > m1;
         strong = is_max && m > high;
         weak = is_max && !strong;
@@ -358,21 +358,24 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
     // groups of four padded pixels, rows 1 .. h (the all-zero border rows are skipped)
     const int g0 = wp >> 2, ngroups = (wp >> 2) * h;
     const int iters = (ngroups + kThreads - 1) / kThreads;  // the same trip count for every lane: the loop holds warp votes
-    const uint2 *mag4 = reinterpret_cast<const uint2 *>(L.mag);
+    const uint4 *md4 = reinterpret_cast<const uint4 *>(L.md);
     const unsigned int ulow = (unsigned)low;
     for (int it = 0; it < iters; it++) {
       const int g = it * kThreads + tid;
-      uint2 v = make_uint2(0u, 0u);
-      if (g < ngroups) v = mag4[g0 + g];
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (g < ngroups) v = md4[g0 + g];
       const int o4 = (g0 + g) << 2;
-      const unsigned int mg[4] = {v.x & 0xFFFFu, v.x >> 16, v.y & 0xFFFFu, v.y >> 16};
+      const unsigned int mg[4] = {v.x & 0xFFFFu, v.y & 0xFFFFu, v.z & 0xFFFFu, v.w & 0xFFFFu};
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const bool pend = mg[k] > ulow;  // (a clipped 65536 reads 65535 > low as well: low <= 65534)
-        const unsigned int pm = __ballot_sync(0xffffffffu, pend);
-        if (pend) q[(qtail + __popc(pm & lt)) & 63] = (IdxT)(o4 + k);
-        qtail += __popc(pm);
-        if (qtail - qhead >= 32) {
+      for (int k = 0; k < 4; k += 2) {
+        // (a clipped 65536 reads 65535 > low as well: low <= 65534)
+        const bool p0 = mg[k] > ulow, p1 = mg[k + 1] > ulow;
+        const unsigned int b1 = __ballot_sync(0xffffffffu, p0 != p1), b2 = __ballot_sync(0xffffffffu, p0 && p1);  // count 1, count 2
+        int pos = qtail + __popc(b1 & lt) + 2 * __popc(b2 & lt);
+        if (p0) q[pos & 127] = (IdxT)(o4 + k), pos++;
+        if (p1) q[pos & 127] = (IdxT)(o4 + k + 1);
+        qtail += __popc(b1) + 2 * __popc(b2);
+        while (qtail - qhead >= 32) {  // (at most 31 + 64 queued: the ring never wraps onto live entries)
           __syncwarp();  // queue entries visible
           direction_test(32);
           qhead += 32;
@@ -385,6 +388,7 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
     if (lane == 0) s_cpre[wid] = min(ccount, cand_cap);
   }
   __syncthreads();
+  for (int i = tid; i < S.ncells; i += kThreads) L.acc[i] = 0u;  // the rings are dead: their storage becomes the accumulator
   if (tid == 0) {  // exclusive prefix of the per-warp candidate counts
     int run = 0;
     for (int i = 0; i < kWarps; i++) {
@@ -488,14 +492,15 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
 
   // ---- 8. argmax in the reference's scan order (r outer, n inner, first strict maximum), hough.cpp:165-176
   unsigned long long best = 0;
-  for (int n = 0; n < B200_NUMANGLE; n++) {
-    for (int c = tid; c < S.rcount[n]; c += kThreads) {
-      const unsigned int v = L.acc[S.cell_base[n] + c];
-      if (v == 0) continue;
-      const unsigned int r = (unsigned)(S.rlo[n] + c);
-      const unsigned long long key = ((unsigned long long)v << 32) | (0xFFFFFFFFu - (r * 16u + (unsigned)n));
-      best = key > best ? key : best;
-    }
+  for (int c = tid; c < S.ncells; c += kThreads) {  // one flat pass over the compacted cells; angle n owns [cell_base[n], cell_base[n + 1])
+    const unsigned int v = L.acc[c];
+    if (v == 0) continue;
+    int n = 0;
+#pragma unroll
+    for (int k = 1; k < B200_NUMANGLE; k++) n += c >= S.cell_base[k];
+    const unsigned int r = (unsigned)(S.rlo[n] + (c - S.cell_base[n]));
+    const unsigned long long key = ((unsigned long long)v << 32) | (0xFFFFFFFFu - (r * 16u + (unsigned)n));
+    best = key > best ? key : best;
   }
   best = warp_max_u64(best);
   if ((tid & 31) == 0) s_red[tid >> 5] = best;  // s_red's threshold use ended several barriers ago
@@ -528,8 +533,9 @@ size_t detect_smem_bytes(const DetectParams &p) {
     const size_t npad = (size_t)detect_pad_pitch(d.w) * (d.h + 2);
     const size_t ws = (size_t)detect_src_stride(d.w);
     size_t b = align16(ws * d.h) + align16(npad);  // padded src (later the work lists), map
-    if (!p.use_global_grad) b += 2 * align16(npad * 2);
-    b += align16((size_t)d.ncells * 4) + (size_t)kWarps * 64 * (p.use_global_grad ? 4 : 2) + 64;  // accumulator, per-warp rings
+    if (!p.use_global_grad) b += align16(npad * 4);
+    const size_t acc = align16((size_t)d.ncells * 4), rings = (size_t)kWarps * 128 * (p.use_global_grad ? 4 : 2);
+    b += (acc > rings ? acc : rings) + 64;  // accumulator and per-warp rings share storage
     worst = b > worst ? b : worst;
   }
   return worst;

@@ -39,3 +39,30 @@ def gather_digit_records(local, n_total, dist, rank, world, device=None):
     if rank != 0:
         return None
     return np.concatenate([o[:c].cpu().numpy() for o, c in zip(outs, counts)])
+
+
+# ---- the same records, built on the device from raw b200_frame_record bytes (bench.py's device-resident path)
+REC_SCORES, REC_N_OFFSETS, REC_USABLE, REC_UPSIDE_DOWN, REC_ALL_FOUND = 84, 84 + 640, 84 + 640 + 48 + 28, 84 + 640 + 48 + 29, 80
+
+
+def digit_records_torch(rec_bytes):
+    """(n, 32) uint8 digit-string records from an (n, 808) uint8 tensor of b200_frame_record bytes (any device)."""
+    import torch
+    n = rec_bytes.shape[0]
+    scores = rec_bytes[:, REC_SCORES:REC_SCORES + 640].contiguous().view(torch.float32).view(n, 16, 10)
+    out = torch.zeros((n, DIGIT_RECORD_BYTES), dtype=torch.uint8, device=rec_bytes.device)
+    out[:, :16] = scores.argmax(dim=2).to(torch.uint8)
+    out[:, 16] = rec_bytes[:, REC_N_OFFSETS]
+    out[:, 17] = rec_bytes[:, REC_USABLE]
+    out[:, 18] = rec_bytes[:, REC_UPSIDE_DOWN]
+    out[:, 19] = rec_bytes[:, REC_ALL_FOUND]
+    return out
+
+
+def gather_equal_shards_torch(local, dist, rank, world):
+    """Equal-size shards already on the device: one gather to rank 0 (the only collective of the path).  Returns the
+    (world * n, 32) tensor on rank 0, None elsewhere."""
+    import torch
+    outs = [torch.empty_like(local) for _ in range(world)] if rank == 0 else None
+    dist.gather(local, outs, dst=0)
+    return torch.cat(outs) if rank == 0 else None
