@@ -59,6 +59,12 @@ def build(force=False):
     lib = os.path.join(HERE, "libb200dmz.so")
     if force or newer(lib, objs):
         run([nvcc] + ARCH + ["-shared", "-o", lib] + objs + ["-lcudart", "-ldl"])
+    # the SDK call sequence timed through the C++ drop-in layer (bench.py single_frame.dropin_sequence)
+    lat = os.path.join(obj_dir, "dropin_latency")
+    lat_src = os.path.join(ROOT, "tools", "dropin_latency.cpp")
+    if force or newer(lat, [lat_src, lib, os.path.join(ROOT, "include", "dmz_b200_compat.h")]):
+        run(["g++", "-std=c++14", "-O2", "-I" + os.path.join(ROOT, "include"), lat_src, "-o", lat, "-L" + HERE, "-lb200dmz",
+             "-Wl,-rpath,$ORIGIN/..", "-ldl"])
     # deck generators (support code)
     deck = os.path.join(ROOT, "tools", "deck")
     dsrc = [os.path.join(deck, f) for f in ("deck_gen.h", "glyphs.h")]

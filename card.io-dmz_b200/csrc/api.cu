@@ -398,7 +398,7 @@ int b200_ctx_create(b200_ctx **out, int device_ordinal, const char *weights_dir)
   }
   CU(cudaMalloc(&ctx->d_hwT, hwT.size() * sizeof(float)));
   CU(cudaMemcpy(ctx->d_hwT, hwT.data(), hwT.size() * sizeof(float), cudaMemcpyHostToDevice));
-  if (upload_conv_constants(ptrs) != 0) return fail(ctx, B200_ECUDA, "cudaMemcpyToSymbol: %s", cudaGetErrorString(cudaGetLastError()));
+  fill_conv_constants(ptrs, &ctx->wts.conv);
   {  // E0 (expiry digit): optional weights + bilateral tables
     std::vector<float> eb;
     if (read_blob(dir + "/modelc_bf4dd6c8.bin", &eb, 74406)) {
@@ -529,11 +529,16 @@ int b200_detect_edges_batch(b200_ctx *ctx, const uint8_t *y, int yrs, size_t yfs
     memcpy(&hc[i], hg[i].corners, sizeof(float) * 8);
     hf[i] = (uint8_t)hg[i].all_found;
   }
-  const cudaMemcpyKind kind = mem == B200_MEM_DEVICE ? cudaMemcpyHostToDevice : cudaMemcpyHostToHost;
-  if (edges) CU(cudaMemcpy(edges, he.data(), sizeof(b200_edges) * n, kind));
-  if (corners) CU(cudaMemcpy(corners, hc.data(), sizeof(b200_corner_points) * n, kind));
-  if (all_found) CU(cudaMemcpy(all_found, hf.data(), n, kind));
-  if (lines) CU(cudaMemcpy(lines, hl.data(), sizeof(b200_line) * n * 4, kind));
+  // host callers get plain memcpy (a cudaMemcpy HostToHost costs a driver round trip per call: the drop-in latency path)
+  auto give = [&](void *dst, const void *src, size_t bytes) -> cudaError_t {
+    if (mem == B200_MEM_DEVICE) return cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+    memcpy(dst, src, bytes);
+    return cudaSuccess;
+  };
+  if (edges) CU(give(edges, he.data(), sizeof(b200_edges) * n));
+  if (corners) CU(give(corners, hc.data(), sizeof(b200_corner_points) * n));
+  if (all_found) CU(give(all_found, hf.data(), n));
+  if (lines) CU(give(lines, hl.data(), sizeof(b200_line) * n * 4));
   return B200_OK;
 } B200_GUARD(ctx)
 

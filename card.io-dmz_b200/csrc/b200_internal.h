@@ -69,11 +69,20 @@ struct FrameGeom {
   double Minv[9];    // cv::invert of M promoted to double (dst -> src), used by the warp
 };
 
-struct NetWeights {  // device pointers
+// The 3 x 8 convolution kernels and biases of the digit CNNs travel BY VALUE inside NetWeights, i.e. in the kernel
+// parameter space (constant bank 0): warp-uniform constant-cache reads like a __constant__ array, but per launch and so
+// per context -- two contexts with different weight directories on one device never share them.
+struct ConvConsts {
+  float w[3][8][9];
+  float b[3][8];
+};
+
+struct NetWeights {  // device pointers (+ the by-value convolution constants)
   const float *vseg;     // modelm_befe75da blob: hidden W 50x204, hidden b 50, logistic W 3x50, logistic b 3
   const float *cnn[3];   // modelc blobs: conv W 8x9, conv b 8, hidden W 32x320, hidden b 32, logistic W 10x32, b 10
   const float *cnn_hwT;  // 3 x [320][32] transposed hidden weights (built on the host)
   const float *vseg_norm;  // [256][256][2]: cvNormalize(MINMAX 0..1) scale / shift of a row whose 8-bit min / max are (mn, mx)
+  ConvConsts conv;
 };
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-DEVICE setting, and one process may hold contexts on several
@@ -129,7 +138,7 @@ int launch_finalize_records(const FrameGeom *geom, const b200_scan *scans, const
 int launch_categorize_patches(const NetWeights &wts, const uint8_t *patches, const float *float_patches, int n, float *out,
                               uint8_t *q8 /* n * B200_Q8_STRIDE bytes of scratch when `patches` is given */, cudaStream_t s);
 int launch_vseg_model(const NetWeights &wts, const float *rows, int n, float *out, cudaStream_t s);
-int upload_conv_constants(const float *cnn_blobs[3]);
+void fill_conv_constants(const float *cnn_blobs[3], ConvConsts *out);  // host side (nets.cu)
 int upload_bilateral_tables(const float *color256, const float *space5);  // E0 prep constants (nets.cu)
 int launch_expiry_seg(const uint8_t *cards, const uint16_t *y_offsets, int n, const float *slash_w, int16_t *sob, int32_t *line_sum,
                       b200_expiry_group *groups, int max_groups, int32_t *n_groups, int32_t *n_dropped, cudaStream_t s);  // expiry_seg.cu

@@ -31,9 +31,7 @@ constexpr int kCardBytes = B200_CARD_W * B200_CARD_H;
 // tanhf costs ~22 instructions, this 6; used by the digit CNNs (1e-4 contract on probabilities), not by vseg (index).
 __device__ __forceinline__ float tanh_sfu(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
 
-// conv kernels and post-pool biases of the three digit CNNs: [model][kernel][9] and [model][kernel]
-__constant__ float c_conv_w[3][8][9];
-__constant__ float c_conv_b[3][8];
+// (the conv kernels and post-pool biases of the three digit CNNs arrive as kernel parameters: ConvConsts, b200_internal.h)
 
 // ------------------------------------------------------------------------------------------------
 // V1 + V2.  Warp-autonomous tiles: every warp of a persistent CTA owns tiles of kVTile = 16 (frame,row) work items
@@ -303,7 +301,7 @@ struct CatSmem {
 
 // four of the eight kernels of model m on one pooled cell: conv 3x3 over the 5x5 window, 3x3 max, + bias, tanh
 template <int K0>
-__device__ __forceinline__ void conv_pool_four(int m, const float (&win)[5][5], float *feat_cell /* stride 40 per kernel */) {
+__device__ __forceinline__ void conv_pool_four(const ConvConsts &C, int m, const float (&win)[5][5], float *feat_cell /* stride 40 per kernel */) {
 #pragma unroll
   for (int kk = 0; kk < 4; kk++) {
     const int k = K0 + kk;
@@ -316,10 +314,10 @@ __device__ __forceinline__ void conv_pool_four(int m, const float (&win)[5][5], 
 #pragma unroll
         for (int i = 0; i < 3; i++)
 #pragma unroll
-          for (int j = 0; j < 3; j++) acc = fmaf(c_conv_w[m][k][i * 3 + j], win[r + i][c + j], acc);
+          for (int j = 0; j < 3; j++) acc = fmaf(C.w[m][k][i * 3 + j], win[r + i][c + j], acc);
         best = fmaxf(best, acc);
       }
-    feat_cell[k * 40] = tanh_sfu(best + c_conv_b[m][k]);
+    feat_cell[k * 40] = tanh_sfu(best + C.b[m][k]);
   }
 }
 
@@ -409,7 +407,7 @@ digit_prep_kernel(const uint8_t *__restrict__ cards, const b200_scan *__restrict
 // group are requested (one 128-bit load per thread) before the current group is computed and expanded to floats after it.
 template <bool kRaw>
 __global__ void __launch_bounds__(kCThreads, 1)
-categorize_kernel(NetWeights W, const uint8_t *__restrict__ q8, b200_scan *__restrict__ scans,
+categorize_kernel(const __grid_constant__ NetWeights W, const uint8_t *__restrict__ q8, b200_scan *__restrict__ scans,
                   const float *__restrict__ raw_float, int n_items /* frames, or raw patches */, float *__restrict__ raw_out) {
   extern __shared__ __align__(16) uint8_t cs_raw[];
   CatSmem &S = *reinterpret_cast<CatSmem *>(cs_raw);
@@ -483,8 +481,8 @@ categorize_kernel(NetWeights W, const uint8_t *__restrict__ q8, b200_scan *__res
         for (int i = 0; i < 5; i++)
 #pragma unroll
           for (int j = 0; j < 5; j++) win[i][j] = p[i * 19 + j];
-        if (kh == 0) conv_pool_four<0>(m, win, &S.work.feat[d][cell]);
-        else conv_pool_four<4>(m, win, &S.work.feat[d][cell]);
+        if (kh == 0) conv_pool_four<0>(W.conv, m, win, &S.work.feat[d][cell]);
+        else conv_pool_four<4>(W.conv, m, win, &S.work.feat[d][cell]);
       }
       __syncthreads();
       // hidden layer 320 -> 32 as a [16 digits x 320] . [320 x 32] product: warp = K slice of 20 features, lane =
@@ -841,15 +839,11 @@ bool ensure_smem(K kernel, size_t bytes) {
 
 }  // namespace
 
-int upload_conv_constants(const float *cnn_blobs[3]) {
-  float w[3][8][9], b[3][8];
+void fill_conv_constants(const float *cnn_blobs[3], ConvConsts *out) {
   for (int m = 0; m < 3; m++) {
-    for (int i = 0; i < 72; i++) (&w[m][0][0])[i] = cnn_blobs[m][i];
-    for (int i = 0; i < 8; i++) b[m][i] = cnn_blobs[m][72 + i];
+    for (int i = 0; i < 72; i++) (&out->w[m][0][0])[i] = cnn_blobs[m][i];
+    for (int i = 0; i < 8; i++) out->b[m][i] = cnn_blobs[m][72 + i];
   }
-  if (cudaMemcpyToSymbol(c_conv_w, w, sizeof(w)) != cudaSuccess) return -1;
-  if (cudaMemcpyToSymbol(c_conv_b, b, sizeof(b)) != cudaSuccess) return -1;
-  return 0;
 }
 
 static int launch_vseg_rows(const NetWeights &wts, const uint8_t *cards, const uint8_t *gate, const b200_scan *scans, int n,

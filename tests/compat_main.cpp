@@ -1,5 +1,10 @@
-// tests/compat_main.cpp -- a caller written against the reference's own API shape (dmz.h / scan/scan.h), compiled
-// against include/dmz_b200_compat.h and linked with libb200dmz.so: the per-frame SDK sequence of SURVEY 3.4.
+// tests/compat_main.cpp -- a caller written against the reference's own API (dmz.h / scan/scan.h) and linked with
+// libb200dmz.so: the per-frame SDK sequence of SURVEY 3.4.  Built two ways from this one source:
+//   (default)                    against include/dmz_b200_compat.h (tests build it on the spot)
+//   -DCOMPAT_REFERENCE_HEADERS   against the reference's own UNMODIFIED dmz.h + scan/scan.h with its vendored opencv2 /
+//                                Eigen headers (oracle/Makefile target `dropin` -> oracle/_ref/compat_main_refhdr, which
+//                                travels to the GPU box like the other oracle/_ref files): the caller's structs, inline
+//                                Eigen accessors and mangled call sites are then the reference's, only the library differs
 // usage: compat_main frames.bin n width height out.bin
 #include <stdio.h>
 #include <stdlib.h>
@@ -7,7 +12,14 @@
 
 #include <vector>
 
+#ifdef COMPAT_REFERENCE_HEADERS
+#include "dmz.h"
+#include "scan/scan.h"
+#define MATRIX_DATA(m) ((m).data())
+#else
 #include "dmz_b200_compat.h"
+#define MATRIX_DATA(m) ((m).v)
+#endif
 
 static void wrap(IplImage *img, uint8_t *data, int w, int h) {
   memset(img, 0, sizeof(*img));
@@ -53,12 +65,12 @@ int main(int argc, char **argv) {
       FrameScanResult fr;
       fr.flipped = false;
       fr.focus_score = 0;
-      memset(fr.scores.v, 0, sizeof(fr.scores.v));
+      memset(MATRIX_DATA(fr.scores), 0, sizeof(float) * 160);
       scanner_add_frame_with_expiry(&state, card, false, &fr);
       rec[2] = fr.usable, rec[3] = fr.upside_down, rec[4] = fr.vseg.y_offset;
-      memcpy(scores, fr.scores.v, sizeof(scores));
+      memcpy(scores, MATRIX_DATA(fr.scores), sizeof(scores));
       ScannerResult sr;
-      memset(sr.predictions.v, 0, sizeof(sr.predictions.v));
+      memset(MATRIX_DATA(sr.predictions), 0, sizeof(ptrdiff_t) * 16);
       sr.n_numbers = 0;
       scanner_result(&state, &sr);
       rec[5] = sr.complete, rec[6] = sr.n_numbers;

@@ -63,6 +63,26 @@ def test_struct_layouts(pkg, ref):
     assert C.sizeof(pkg.Edges) == sizes[6] and C.sizeof(pkg.CornerPoints) == sizes[7]
 
 
+def test_member_layouts_match_reference_headers(tmp_path):
+    """offsetof / sizeof of EVERY member that crosses the boundary: include/dmz_b200_compat.h against the listing the same
+    probe (tests/layout_probe.cpp) printed when compiled against the reference's own unmodified dmz.h + scan/scan.h
+    (tests/golden/ref_layout.txt, written by `make -C oracle layout`; regenerated here when /root/reference exists)."""
+    golden = os.path.join(ROOT, "tests", "golden", "ref_layout.txt")
+    want = open(golden).read()
+    ref_dir = os.environ.get("DMZ_REFERENCE", "/root/reference")
+    if os.path.isdir(ref_dir):
+        exe = str(tmp_path / "probe_ref")
+        subprocess.check_call(["g++", "-std=gnu++03", "-w", "-DCYTHON_DMZ=1", "-DPROBE_REFERENCE_HEADERS",
+                               "-I" + os.path.join(ROOT, "oracle", "stub_include"), "-I" + ref_dir,
+                               os.path.join(ROOT, "tests", "layout_probe.cpp"), "-o", exe])
+        assert subprocess.check_output([exe], text=True) == want, "tests/golden/ref_layout.txt is stale: make -C oracle layout"
+    exe = str(tmp_path / "probe_b200")
+    subprocess.check_call(["g++", "-std=c++14", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "layout_probe.cpp"), "-o", exe])
+    got = subprocess.check_output([exe], text=True)
+    assert len(want.splitlines()) > 120
+    assert got == want
+
+
 def test_no_context_without_cuda(pkg):
     import torch
     if torch.cuda.is_available():

@@ -547,12 +547,7 @@ def test_bad_arguments_fail_cleanly(dmz, pkg):
         dmz.process_frames(np.zeros((1, 16, 16), np.uint8))  # frame too small for detection strips
 
 
-def test_cxx_dropin_layer(dmz, oracle, tmp_path):
-    """A caller written against the reference's dmz.h / scan.h shape, linked with libb200dmz.so."""
-    exe = str(tmp_path / "compat_main")
-    subprocess.check_call(["g++", "-std=c++14", "-O1", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "compat_main.cpp"),
-                           "-o", exe, "-L" + os.path.join(ROOT, "card.io-dmz_b200"), "-lb200dmz",
-                           "-Wl,-rpath," + os.path.join(ROOT, "card.io-dmz_b200"), "-ldl"])
+def _run_dropin_caller(exe, oracle, tmp_path):
     frames = deck_frames(16, 8)
     fin, fout = str(tmp_path / "frames.bin"), str(tmp_path / "out.bin")
     frames.tofile(fin)
@@ -578,6 +573,25 @@ def test_cxx_dropin_layer(dmz, oracle, tmp_path):
             assert got["digits"][k][: len(digits)].tolist() == digits.tolist()
     assert done
     oracle.scanner_free(s)
+
+
+def test_cxx_dropin_layer(dmz, oracle, tmp_path):
+    """A caller written against the reference's dmz.h / scan.h shape, linked with libb200dmz.so."""
+    exe = str(tmp_path / "compat_main")
+    subprocess.check_call(["g++", "-std=c++14", "-O1", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "compat_main.cpp"),
+                           "-o", exe, "-L" + os.path.join(ROOT, "card.io-dmz_b200"), "-lb200dmz",
+                           "-Wl,-rpath," + os.path.join(ROOT, "card.io-dmz_b200"), "-ldl"])
+    _run_dropin_caller(exe, oracle, tmp_path)
+
+
+def test_cxx_dropin_reference_headers(dmz, oracle, tmp_path):
+    """The same caller compiled against the reference's own UNMODIFIED dmz.h + scan/scan.h (vendored opencv2 / Eigen
+    headers; oracle/Makefile target `dropin`, built where /root/reference exists and shipped under oracle/_ref): its
+    structs, inline Eigen accessors and mangled call sites are the reference's, the library behind them is this repo's."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "compat_main_refhdr")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/compat_main_refhdr not present (built only where /root/reference exists)")
+    _run_dropin_caller(exe, oracle, tmp_path)
 
 
 def test_cxx_dropin_expiry(dmz, oracle, tmp_path):
