@@ -106,6 +106,7 @@ def _load():
     lib.b200_calc_persp_transform_batch.argtypes = [vp, vp, vp, i, vp]
     lib.b200_categorize_patches_batch.argtypes = [vp, vp, i, i, vp]
     lib.b200_vseg_model_batch.argtypes = [vp, vp, i, i, vp]
+    lib.b200_vseg_rows_batch.argtypes = [vp, vp, i, i, vp]
     lib.b200_digit_models_batch.argtypes = [vp, vp, i, i, vp]
     lib.b200_best_expiry_seg_batch.argtypes = [vp, vp, vp, i, i, vp, i, vp, vp, vp]
     lib.b200_deinterleave_c2_batch.argtypes = [vp, vp, i, C.c_size_t, i, i, i, i, vp, vp]
@@ -347,6 +348,14 @@ class Dmz:
         n = rows.shape[0]
         out = np.zeros((n, 3), np.float32)
         self._check(self.lib.b200_vseg_model_batch(self.ctx, _ptr(rows), n, MEM_HOST, _ptr(out)))
+        return out
+
+    def vseg_rows(self, cards):
+        """(visa-like, amex-like) probability of the coarse rows 0, 4, .., 268 of each card: (n, 270, 2), 0 elsewhere."""
+        cards = np.ascontiguousarray(cards, np.uint8).reshape(-1, 270, 428)
+        n = cards.shape[0]
+        out = np.zeros((n, 270, 2), np.float32)
+        self._check(self.lib.b200_vseg_rows_batch(self.ctx, _ptr(cards), n, MEM_HOST, _ptr(out)))
         return out
 
     # ---- device-pointer API (bench: inputs resident in HBM) ----------------------------------------

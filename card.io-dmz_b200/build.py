@@ -34,7 +34,7 @@ def build(force=False):
     nvcc = os.environ.get("NVCC", "nvcc")
     obj_dir = os.path.join(HERE, "build")
     os.makedirs(obj_dir, exist_ok=True)
-    hdrs = [os.path.join(CSRC, "b200_internal.h"), os.path.join(CSRC, "expiry_seg_core.h"), os.path.join(ROOT, "include", "b200_dmz.h")]
+    hdrs = [os.path.join(CSRC, "b200_internal.h"), os.path.join(CSRC, "expiry_seg_core.h"), os.path.join(CSRC, "umma.cuh"), os.path.join(ROOT, "include", "b200_dmz.h")]
     units = [
         # (source, extra flags).  exact.cu / detect.cu: bit-exact float stages -> no FMA contraction.
         ("detect.cu", ["-fmad=false"]),
@@ -42,6 +42,7 @@ def build(force=False):
         ("warp.cu", ["-fmad=false"]),
         ("expiry_seg.cu", ["-fmad=false"]),
         ("nets.cu", []),
+        ("vseg_mma.cu", []),
         ("api.cu", ["-fmad=false"]),
         ("b200_tables.cpp", ["-Xcompiler", "-ffp-contract=off"]),
         ("scanner.cpp", ["-Xcompiler", "-ffp-contract=off"]),

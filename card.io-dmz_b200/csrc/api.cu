@@ -66,6 +66,8 @@ struct b200_ctx {
   float *d_cnn[3] = {nullptr, nullptr, nullptr};
   float *d_hwT = nullptr;
   float *d_vnorm = nullptr;   // (min, max) -> scale / shift table of the vseg row normalisation
+  int8_t *d_vseg_wq = nullptr;  // tensor-core form of the vseg hidden layer: weight digits, per-unit constants, (s, d0) table
+  float *d_vseg_unit = nullptr, *d_vseg_sd = nullptr;
   float *d_expiry = nullptr;  // modelc_bf4dd6c8 blob (optional: E0 entry points need it)
   float *d_slash = nullptr;   // modelm_730c4cbd blob (optional: b200_best_expiry_seg_batch needs it)
   NetWeights wts{};
@@ -429,6 +431,19 @@ int b200_ctx_create(b200_ctx **out, int device_ordinal, const char *weights_dir)
     CU(cudaMemcpy(ctx->d_vnorm, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice));
   }
   ctx->wts.vseg_norm = ctx->d_vnorm;
+  {
+    std::vector<int8_t> wq((size_t)4 * 14 * 64 * 16);
+    std::vector<VsegUnit> units(64);
+    std::vector<float> sd((size_t)256 * 256 * 2);
+    b200_build_vseg_mma_tables(blob.data(), wq.data(), units.data(), sd.data());
+    CU(cudaMalloc(&ctx->d_vseg_wq, wq.size()));
+    CU(cudaMemcpy(ctx->d_vseg_wq, wq.data(), wq.size(), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&ctx->d_vseg_unit, sizeof(VsegUnit) * units.size()));
+    CU(cudaMemcpy(ctx->d_vseg_unit, units.data(), sizeof(VsegUnit) * units.size(), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&ctx->d_vseg_sd, sd.size() * sizeof(float)));
+    CU(cudaMemcpy(ctx->d_vseg_sd, sd.data(), sd.size() * sizeof(float), cudaMemcpyHostToDevice));
+    ctx->wts.vseg_wq = ctx->d_vseg_wq, ctx->wts.vseg_unit = ctx->d_vseg_unit, ctx->wts.vseg_sd = ctx->d_vseg_sd;
+  }
   return B200_OK;
 } B200_GUARD(out ? *out : nullptr)
 
@@ -445,7 +460,7 @@ void b200_ctx_destroy(b200_ctx *ctx) {
     if (ctx->lazy_ev[i]) cudaEventDestroy(ctx->lazy_ev[i]);
   cudaFree(ctx->d_misc);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
-  cudaFree(ctx->d_vnorm);
+  cudaFree(ctx->d_vnorm), cudaFree(ctx->d_vseg_wq), cudaFree(ctx->d_vseg_unit), cudaFree(ctx->d_vseg_sd);
   cudaFree(ctx->d_vseg), cudaFree(ctx->d_hwT), cudaFree(ctx->d_expiry), cudaFree(ctx->d_slash);
   for (int m = 0; m < 3; m++) cudaFree(ctx->d_cnn[m]);
   delete ctx;
@@ -998,6 +1013,26 @@ int b200_expiry_digits_batch(b200_ctx *ctx, const uint8_t *patches, int n, int m
 
 int b200_expiry_digit_models_batch(b200_ctx *ctx, const float *prepared, int n, int mem, float *out) try {
   return expiry_call(ctx, nullptr, prepared, n, mem, out);
+} B200_GUARD(ctx)
+
+int b200_vseg_rows_batch(b200_ctx *ctx, const uint8_t *cards, int n, int mem, float *out) try {
+  if (!ctx || !cards || !out || n < 1) return fail(ctx, B200_EINVAL, "b200_vseg_rows_batch: bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  const uint8_t *dc = cards;
+  float *dout = out;
+  if (mem == B200_MEM_HOST) {
+    const size_t o_cards = ((size_t)n * 540 * sizeof(float) + 15) & ~(size_t)15;
+    int rc = ensure_misc(ctx, o_cards + kCardBytes * (size_t)n);
+    if (rc) return rc;
+    dout = (float *)ctx->d_misc;
+    uint8_t *p = (uint8_t *)ctx->d_misc + o_cards;
+    CU(cudaMemcpyAsync(p, cards, kCardBytes * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    dc = p;
+  }
+  LAUNCH(launch_vseg_coarse_rows(ctx->wts, dc, n, dout, ctx->stream));
+  if (mem == B200_MEM_HOST) CU(cudaMemcpyAsync(out, dout, (size_t)n * 540 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
 } B200_GUARD(ctx)
 
 int b200_vseg_model_batch(b200_ctx *ctx, const float *rows, int n, int mem, float *out) try {

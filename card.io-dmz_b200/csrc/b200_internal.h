@@ -82,8 +82,24 @@ struct NetWeights {  // device pointers (+ the by-value convolution constants)
   const float *cnn[3];   // modelc blobs: conv W 8x9, conv b 8, hidden W 32x320, hidden b 32, logistic W 10x32, b 10
   const float *cnn_hwT;  // 3 x [320][32] transposed hidden weights (built on the host)
   const float *vseg_norm;  // [256][256][2]: cvNormalize(MINMAX 0..1) scale / shift of a row whose 8-bit min / max are (mn, mx)
+  // tensor-core form of the vseg hidden layer (vseg_mma.cu; built on the host by b200_build_vseg_mma_tables)
+  const int8_t *vseg_wq;   // [4 digits][14 K chunks][64 units][16] signed base-128 digits of W1, operand layout of umma.cuh
+  const float *vseg_unit;  // [64] VsegUnit
+  const float *vseg_sd;    // [256][256][2]: (s, d0) of a row with 8-bit min / max (mn, mx): x_k = (v_k - mn) * s + d0
   ConvConsts conv;
 };
+
+struct VsegUnit {  // per hidden unit u (zeros for the padding units 50 .. 63)
+  float cu;        // S_u * 2^-27, S_u = max_k |W1[u][k]|: W1[u][k] = cu * Q[u][k], Q a 28-bit integer
+  float sumw;      // sum_k W1[u][k]
+  float b1;
+  float w20, w21, w22;  // logistic weights of the three classes
+  float pad[2];
+};
+void b200_build_vseg_mma_tables(const float *blob /* modelm_befe75da */, int8_t *wq /* 4 * 14 * 64 * 16 */, VsegUnit *units /* 64 */,
+                                float *sd /* 256 * 256 * 2 */);  // b200_tables.cpp
+int launch_vseg_rows_mma(const NetWeights &wts, const uint8_t *cards, const uint8_t *gate, const b200_scan *scans, int n, int mode,
+                         float *vprob, cudaStream_t s);  // vseg_mma.cu
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-DEVICE setting, and one process may hold contexts on several
 // devices: remember per kernel which devices have been configured (configuring twice is harmless, so no lock).
@@ -138,6 +154,7 @@ int launch_finalize_records(const FrameGeom *geom, const b200_scan *scans, const
 int launch_categorize_patches(const NetWeights &wts, const uint8_t *patches, const float *float_patches, int n, float *out,
                               uint8_t *q8 /* n * B200_Q8_STRIDE bytes of scratch when `patches` is given */, cudaStream_t s);
 int launch_vseg_model(const NetWeights &wts, const float *rows, int n, float *out, cudaStream_t s);
+int launch_vseg_coarse_rows(const NetWeights &wts, const uint8_t *cards, int n, float *vprob /* n * 540, zeroed here */, cudaStream_t s);
 void fill_conv_constants(const float *cnn_blobs[3], ConvConsts *out);  // host side (nets.cu)
 int upload_bilateral_tables(const float *color256, const float *space5);  // E0 prep constants (nets.cu)
 int launch_expiry_seg(const uint8_t *cards, const uint16_t *y_offsets, int n, const float *slash_w, int16_t *sob, int32_t *line_sum,

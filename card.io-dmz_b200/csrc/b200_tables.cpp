@@ -182,6 +182,53 @@ void b200_build_minmax_norm_table(float *table) {
     }
 }
 
+// Tensor-core form of the vseg hidden layer (vseg_mma.cu).  modelm_befe75da blob: W1 50 x 204 row-major, b1 50, W2 3 x 50, b2 3.
+//   W1[u][k] = cu * Q[u][k],  Q = llround(W1 / S_u * 2^27)  (|Q| <= 2^27),  Q = ((q0 * 128 + q1) * 128 + q2) * 128 + q3 with
+//   balanced digits q1..q3 in [-64, 63] and q0 in [-64, 64]: four s8 operand matrices, K-major in 16-byte chunks:
+//   digit t, K chunk c, unit u at ((t * 14 + c) * 64 + u) * 16.
+//   (s, d0) per (mn, mx): the reference's x_k = fl(fl(fl(v_k * k255) * scale) + shift) is, before its three roundings,
+//   (v_k - mn) * s + d0 with s = k255 * scale and d0 = shift + mn * s -- evaluated here in double from the same float
+//   scale / shift cv::normalize produces (b200_build_minmax_norm_table).
+void b200_build_vseg_mma_tables(const float *blob, int8_t *wq, VsegUnit *units, float *sd) {
+  memset(wq, 0, (size_t)4 * 14 * 64 * 16);
+  memset(units, 0, sizeof(VsegUnit) * 64);
+  for (int u = 0; u < 50; u++) {
+    const float *w = blob + (size_t)u * 204;
+    double smax = 0.0, sum = 0.0;
+    for (int k = 0; k < 204; k++) {
+      smax = fabs((double)w[k]) > smax ? fabs((double)w[k]) : smax;
+      sum += (double)w[k];
+    }
+    if (smax == 0.0) smax = 1.0;
+    for (int k = 0; k < 204; k++) {
+      long long q = llround((double)w[k] / smax * 134217728.0);  // 2^27
+      int digit[4];
+      for (int t = 3; t >= 1; t--) {
+        long long d = ((q + 64) % 128 + 128) % 128 - 64;  // balanced remainder in [-64, 63]
+        digit[t] = (int)d;
+        q = (q - d) / 128;
+      }
+      digit[0] = (int)q;  // |q| <= 64
+      for (int t = 0; t < 4; t++) wq[(((size_t)t * 14 + k / 16) * 64 + u) * 16 + k % 16] = (int8_t)digit[t];
+    }
+    units[u].cu = (float)(smax / 134217728.0);
+    units[u].sumw = (float)sum;
+    units[u].b1 = blob[10200 + u];
+    units[u].w20 = blob[10250 + u], units[u].w21 = blob[10250 + 50 + u], units[u].w22 = blob[10250 + 100 + u];
+  }
+  const float k255 = 1.0f / 255.0f;
+  for (int mn = 0; mn < 256; mn++)
+    for (int mx = 0; mx < 256; mx++) {
+      const float fmn = (float)mn * k255, fmx = (float)mx * k255;
+      const double smin = (double)fmn, smax = (double)fmx;
+      const double scale = (smax - smin > DBL_EPSILON) ? 1. / (smax - smin) : 0.0;
+      const float fs = (float)scale, fb = (float)(0.0 - smin * scale);
+      const double s = (double)k255 * (double)fs;
+      sd[(mn * 256 + mx) * 2 + 0] = (float)s;
+      sd[(mn * 256 + mx) * 2 + 1] = (float)((double)fb + (double)mn * s);
+    }
+}
+
 void b200_build_bilateral_tables(float *color256, float *space5) {
   const int aperture = 3;
   const double sigma_color = (aperture / 2.0 - 1) * 0.3 + 0.8;  // the reference's "space_sigma"

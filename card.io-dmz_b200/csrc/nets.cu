@@ -14,6 +14,8 @@
 // memory, FC weights sit in shared memory for the lifetime of a persistent CTA.
 #include <float.h>
 
+#include <stdlib.h>
+
 #include "b200_internal.h"
 
 // exact.cu
@@ -848,6 +850,11 @@ void fill_conv_constants(const float *cnn_blobs[3], ConvConsts *out) {
 
 static int launch_vseg_rows(const NetWeights &wts, const uint8_t *cards, const uint8_t *gate, const b200_scan *scans, int n,
                             int mode, float *vprob, const float *raw_rows, float *raw_out, cudaStream_t s) {
+  // card rows go through the tensor-core kernel (vseg_mma.cu); raw float rows (the model tap) and B200_DMZ_VSEG_FP32=1
+  // (A / B measurements) through the FP32 kernel of this file
+  const char *fp32_env = getenv("B200_DMZ_VSEG_FP32");  // (read per call: tests flip it between calls)
+  const bool force_fp32 = fp32_env && *fp32_env && atoi(fp32_env) != 0;
+  if (mode != 2 && !force_fp32) return launch_vseg_rows_mma(wts, cards, gate, scans, n, mode, vprob, s);
   static PerDeviceOnce once;
   if (!once.ensure([] { return ensure_smem(vseg_rows_kernel, sizeof(VsegSmem)); })) return -1;
   const int per_frame = mode == 0 ? 68 : (mode == 1 ? kFineSlots : 1);
@@ -857,6 +864,11 @@ static int launch_vseg_rows(const NetWeights &wts, const uint8_t *cards, const u
   if (grid < 1) grid = 1;
   vseg_rows_kernel<<<(int)grid, kVThreads, sizeof(VsegSmem), s>>>(wts.vseg, wts.vseg_norm, cards, gate, scans, n, mode, vprob, raw_rows, raw_out);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int launch_vseg_coarse_rows(const NetWeights &wts, const uint8_t *cards, int n, float *vprob, cudaStream_t s) {
+  if (cudaMemsetAsync(vprob, 0, (size_t)n * 540 * sizeof(float), s) != cudaSuccess) return -1;
+  return launch_vseg_rows(wts, cards, nullptr, nullptr, n, 0, vprob, nullptr, nullptr, s);
 }
 
 int launch_vseg_model(const NetWeights &wts, const float *rows, int n, float *out, cudaStream_t s) {

@@ -183,6 +183,10 @@ int b200_categorize_patches_batch(b200_ctx *ctx, const uint8_t *patches, int n, 
 int b200_digit_models_batch(b200_ctx *ctx, const float *patches, int n, int mem, float *out);
 /* applym_befe75da on prepared rows: in = n x 204 f32, out = n x 3 f32 */
 int b200_vseg_model_batch(b200_ctx *ctx, const float *rows, int n, int mem, float *out);
+/* vseg_probabilities_for_hstrip (scan/n_vseg.cpp:39-47) on the coarse rows 0, 4, .., 268 of n warped cards (428 x 270 u8,
+ * dense): out = n x 270 x 2 f32, (visa-like, amex-like) probability per card row, 0 for the rows not scored.  The tap of
+ * the row kernel the whole path uses (row preparation + hidden layer on the tensor cores + logistic layer). */
+int b200_vseg_rows_batch(b200_ctx *ctx, const uint8_t *cards, int n, int mem, float *out);
 
 /* ---- chroma de-interleave ----
  * dmz_deinterleave_uint8_c2 (dmz.h:61, dmz.cpp:49-56): n interleaved CbCr planes (width x height pixels, two bytes per

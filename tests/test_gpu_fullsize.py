@@ -43,6 +43,25 @@ def test_deterministic_and_batch_invariant(dmz, pkg, full):
     assert bool((part == recs[lo:lo + cnt]).all())
 
 
+def test_tensor_core_vseg_equals_fp32_vseg(dmz, pkg, full):
+    """The tcgen05 form of the vseg hidden layer (exact integer MMAs, vseg_mma.cu) against the FP32 FMA kernel on every
+    frame of the deck: every index the scan derives from the row probabilities is identical, the 27-row score sums agree
+    to float noise (the two kernels round differently, neither is the reference's summation order)."""
+    import torch
+    frames, recs, r = full
+    os.environ["B200_DMZ_VSEG_FP32"] = "1"
+    try:
+        other = torch.zeros_like(recs)
+        dmz.process_frames_device(frames.data_ptr(), N, 640, 480, other.data_ptr())
+    finally:
+        del os.environ["B200_DMZ_VSEG_FP32"]
+    o = other.cpu().numpy().view(pkg.RECORD_DTYPE).reshape(N)
+    for k in ("v_y_offset", "v_pattern_type", "usable", "upside_down", "h_n_offsets", "h_pattern_offset"):
+        assert np.array_equal(r[k], o[k]), k
+    assert np.array_equal(r["h_offsets"], o["h_offsets"])
+    assert np.abs(r["v_score"] - o["v_score"]).max() <= 2e-4
+
+
 def test_sessions_read_the_true_number(pkg, full):
     """Each 8-frame session shows one card number; the per-session scanner result must complete for most sessions
     and equal the deck's ground truth (Luhn-valid by construction)."""

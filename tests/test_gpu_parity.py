@@ -321,6 +321,38 @@ def test_model_known_answer_vectors(dmz):
         assert np.abs(per_model[0, i] - k["test output"]).max() <= 1e-5, m
 
 
+def test_vseg_rows_tensor_core_path(dmz, oracle):
+    """vseg_probabilities_for_hstrip (n_vseg.cpp:39-47) through the row kernel the whole path uses -- row preparation +
+    hidden layer as exact integer MMAs on the tensor cores (vseg_mma.cu) + logistic layer -- against the oracle row by
+    row: real card rows, and rows built to stress the normalisation (flat rows: all x = 0; a two-level row: scale 255;
+    rows whose minimum gradient is large; saturated steps; pure noise)."""
+    _, cards = oracle.process_frames(deck_frames(32, 6), want_cards=True)
+    rng = np.random.default_rng(11)
+    synth = np.zeros((4, 270, 428), np.uint8)
+    synth[0] = 77                                                     # flat: every row all-equal after the gradient
+    synth[1] = rng.integers(0, 256, (270, 428))                      # noise
+    synth[2] = (np.arange(428)[None, :] // 3 % 2 * 255).astype(np.uint8)  # saturated steps everywhere: large min gradient
+    synth[2, ::2] = np.where(rng.random((135, 428)) < 0.1, 200, synth[2, ::2])
+    synth[3] = 100
+    synth[3, :, 200] = 101                                            # a single unit step: v in {0, 1}
+    synth[3, 8::8, 300:320] = rng.integers(0, 256, (33, 20))
+    allc = np.concatenate([cards, synth])
+    got = dmz.vseg_rows(allc)
+    worst = 0.0
+    for c in range(allc.shape[0]):
+        for row in range(0, 270, 4):
+            want = oracle.vseg_row(allc[c], row)  # (p0, visa-like, amex-like)
+            worst = max(worst, float(np.abs(got[c, row] - want[1:]).max()))
+    assert worst <= 1e-5, worst
+    assert not got[:, 1::4].any() and not got[:, 2::4].any() and not got[:, 3::4].any()  # rows outside the coarse set stay 0
+    os.environ["B200_DMZ_VSEG_FP32"] = "1"
+    try:
+        fp32 = dmz.vseg_rows(allc)
+    finally:
+        del os.environ["B200_DMZ_VSEG_FP32"]
+    assert np.abs(fp32 - got).max() <= 1e-5
+
+
 def test_categorize_patches(dmz, oracle, golden):
     patches = golden["card0_patches"]
     ens, mods = dmz.categorize_patches(patches)
