@@ -28,7 +28,8 @@ for obj in sorted(f for f in os.listdir(build) if f.endswith(".cu.o")):
             if m.group(1) in SHOW and len(lines[cur]) < 24:
                 lines[cur].append(l.strip()[:150])
     for fn, c in cnt.items():
-        short = subprocess.run(["c++filt", fn], capture_output=True, text=True).stdout.strip().split("(")[0][-90:]
+        dem = subprocess.run(["c++filt", fn], capture_output=True, text=True).stdout.strip().replace("(anonymous namespace)::", "")
+        short = re.sub(r"^void ", "", dem).split("(")[0][:90]
         out.append("\n## %s  %s\n" % (obj[:-2], short))
         out.append("  " + ", ".join("%s x%d" % (o, n) for o, n in sorted(c.items())) + "\n")
         out.extend("    " + l + "\n" for l in lines[fn])
