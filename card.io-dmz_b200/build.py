@@ -43,6 +43,7 @@ def build(force=False):
         ("expiry_seg.cu", ["-fmad=false"]),
         ("nets.cu", []),
         ("vseg_mma.cu", []),
+        ("categorize_mma.cu", []),
         ("api.cu", ["-fmad=false"]),
         ("b200_tables.cpp", ["-Xcompiler", "-ffp-contract=off"]),
         ("scanner.cpp", ["-Xcompiler", "-ffp-contract=off"]),

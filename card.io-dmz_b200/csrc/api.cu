@@ -68,6 +68,9 @@ struct b200_ctx {
   float *d_vnorm = nullptr;   // (min, max) -> scale / shift table of the vseg row normalisation
   int8_t *d_vseg_wq = nullptr;  // tensor-core form of the vseg hidden layer: weight digits, per-unit constants, (s, d0) table
   float *d_vseg_unit = nullptr, *d_vseg_sd = nullptr;
+  int8_t *d_cnn_convb = nullptr;  // tensor-core form of the digit CNNs: conv tap digits, per-kernel scale / bias, fp16 hidden weights
+  float *d_cnn_convf = nullptr;
+  uint16_t *d_cnn_hidb = nullptr;
   float *d_expiry = nullptr;  // modelc_bf4dd6c8 blob (optional: E0 entry points need it)
   float *d_slash = nullptr;   // modelm_730c4cbd blob (optional: b200_best_expiry_seg_batch needs it)
   NetWeights wts{};
@@ -401,6 +404,19 @@ int b200_ctx_create(b200_ctx **out, int device_ordinal, const char *weights_dir)
   CU(cudaMalloc(&ctx->d_hwT, hwT.size() * sizeof(float)));
   CU(cudaMemcpy(ctx->d_hwT, hwT.data(), hwT.size() * sizeof(float), cudaMemcpyHostToDevice));
   fill_conv_constants(ptrs, &ctx->wts.conv);
+  {
+    std::vector<int8_t> convb((size_t)3 * 3 * 2 * 80 * 16);
+    std::vector<float> convf(48);
+    std::vector<uint16_t> hidb((size_t)3 * 2 * 40 * 32 * 8);
+    b200_build_cnn_mma_tables(ptrs, convb.data(), convf.data(), hidb.data());
+    CU(cudaMalloc(&ctx->d_cnn_convb, convb.size()));
+    CU(cudaMemcpy(ctx->d_cnn_convb, convb.data(), convb.size(), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&ctx->d_cnn_convf, convf.size() * sizeof(float)));
+    CU(cudaMemcpy(ctx->d_cnn_convf, convf.data(), convf.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&ctx->d_cnn_hidb, hidb.size() * sizeof(uint16_t)));
+    CU(cudaMemcpy(ctx->d_cnn_hidb, hidb.data(), hidb.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    ctx->wts.cnn_convb = ctx->d_cnn_convb, ctx->wts.cnn_convf = ctx->d_cnn_convf, ctx->wts.cnn_hidb = ctx->d_cnn_hidb;
+  }
   {  // E0 (expiry digit): optional weights + bilateral tables
     std::vector<float> eb;
     if (read_blob(dir + "/modelc_bf4dd6c8.bin", &eb, 74406)) {
@@ -461,6 +477,7 @@ void b200_ctx_destroy(b200_ctx *ctx) {
   cudaFree(ctx->d_misc);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   cudaFree(ctx->d_vnorm), cudaFree(ctx->d_vseg_wq), cudaFree(ctx->d_vseg_unit), cudaFree(ctx->d_vseg_sd);
+  cudaFree(ctx->d_cnn_convb), cudaFree(ctx->d_cnn_convf), cudaFree(ctx->d_cnn_hidb);
   cudaFree(ctx->d_vseg), cudaFree(ctx->d_hwT), cudaFree(ctx->d_expiry), cudaFree(ctx->d_slash);
   for (int m = 0; m < 3; m++) cudaFree(ctx->d_cnn[m]);
   delete ctx;

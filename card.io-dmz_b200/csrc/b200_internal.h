@@ -86,6 +86,10 @@ struct NetWeights {  // device pointers (+ the by-value convolution constants)
   const int8_t *vseg_wq;   // [4 digits][14 K chunks][64 units][16] signed base-128 digits of W1, operand layout of umma.cuh
   const float *vseg_unit;  // [64] VsegUnit
   const float *vseg_sd;    // [256][256][2]: (s, d0) of a row with 8-bit min / max (mn, mx): x_k = (v_k - mn) * s + d0
+  // tensor-core form of the digit CNNs (categorize_mma.cu; built on the host by b200_build_cnn_mma_tables)
+  const int8_t *cnn_convb;   // [3 models][3 digits][2 K chunks][80][16]: conv taps as signed base-128 digits, operand layout
+  const float *cnn_convf;    // [24] (1/255) / F per (model, kernel), then [24] conv biases
+  const uint16_t *cnn_hidb;  // fp16 [3 models][Whi, Wlo][40 cells][32 units][8 kernels]
   ConvConsts conv;
 };
 
@@ -98,6 +102,9 @@ struct VsegUnit {  // per hidden unit u (zeros for the padding units 50 .. 63)
 };
 void b200_build_vseg_mma_tables(const float *blob /* modelm_befe75da */, int8_t *wq /* 4 * 14 * 64 * 16 */, VsegUnit *units /* 64 */,
                                 float *sd /* 256 * 256 * 2 */);  // b200_tables.cpp
+void b200_build_cnn_mma_tables(const float *const blobs[3] /* modelc_* */, int8_t *convb /* 23040 */, float *convf /* 48 */,
+                               uint16_t *hidb /* 3 * 2 * 40 * 32 * 8 */);  // b200_tables.cpp
+int launch_categorize_mma(const NetWeights &wts, const uint8_t *q8, b200_scan *scans, int n, bool raw, float *raw_out, cudaStream_t s);  // categorize_mma.cu
 int launch_vseg_rows_mma(const NetWeights &wts, const uint8_t *cards, const uint8_t *gate, const b200_scan *scans, int n, int mode,
                          float *vprob, cudaStream_t s);  // vseg_mma.cu
 

@@ -229,6 +229,101 @@ void b200_build_vseg_mma_tables(const float *blob, int8_t *wq, VsegUnit *units, 
     }
 }
 
+// float -> IEEE half, round to nearest even (subnormals kept, overflow -> inf)
+static uint16_t half_bits_rn(float f) {
+  uint32_t x;
+  memcpy(&x, &f, 4);
+  const uint32_t sign = (x >> 16) & 0x8000u;
+  x &= 0x7FFFFFFFu;
+  if (x >= 0x7F800000u) return (uint16_t)(sign | (x > 0x7F800000u ? 0x7E00u : 0x7C00u));
+  if (x >= 0x477FF000u) return (uint16_t)(sign | 0x7C00u);  // rounds to >= 65520: inf
+  if (x < 0x38800000u) {                                      // below the smallest normal half: subnormal
+    if (x < 0x33000000u) return (uint16_t)sign;               // < 2^-25: zero
+    const int shift = 126 - (int)(x >> 23);                   // 14 .. 24
+    const uint32_t mant = (x & 0x7FFFFFu) | 0x800000u;
+    uint32_t h = mant >> shift;
+    const uint32_t rem = mant & ((1u << shift) - 1u), halfway = 1u << (shift - 1);
+    if (rem > halfway || (rem == halfway && (h & 1u))) h++;
+    return (uint16_t)(sign | h);
+  }
+  uint32_t h = ((x >> 13) - (112u << 10));
+  const uint32_t rem = x & 0x1FFFu;
+  if (rem > 0x1000u || (rem == 0x1000u && (h & 1u))) h++;
+  return (uint16_t)(sign | h);
+}
+static float half_bits_to_float(uint16_t h) {
+  const uint32_t sign = (uint32_t)(h & 0x8000u) << 16, e = (h >> 10) & 31u, m = h & 0x3FFu;
+  float out;
+  if (e == 0) {
+    out = (float)m * 5.9604644775390625e-08f;  // 2^-24
+    return sign ? -out : out;
+  }
+  const uint32_t x = sign | ((e + 112u) << 23) | (m << 13);
+  memcpy(&out, &x, 4);
+  return out;
+}
+
+// Tensor-core form of the digit CNNs (categorize_mma.cu).  modelc blob: conv W 8 x 9, conv b 8, hidden W 32 x 320, hidden b 32,
+// logistic W 10 x 32, logistic b 10.
+//   conv: per (model, kernel) w = Q / F with integer |Q| <= 2^20 and 255 * sum |Q| < 2^31 (so that sum_taps Q q fits 32 bits for
+//   any bytes q); Q = (d0 << 14) + (d1 << 7) + d2 with balanced digits.  Operand column n = kernel * 9 + (pr * 3 + pc) (the conv
+//   position inside the 3 x 3 pool window), row k = wy * 5 + wx (byte of the cell's 5 x 5 window): tap (wy - pr, wx - pc).
+//   convf: (1/255 as float, in double) / F per (model, kernel), then the biases (added after the pool maximum).
+//   hidden: W[u][kernel * 40 + cell] as fp16 hi + fp16 lo, operand chunk = cell, row = unit, element = kernel.
+void b200_build_cnn_mma_tables(const float *const blobs[3], int8_t *convb, float *convf, uint16_t *hidb) {
+  memset(convb, 0, (size_t)3 * 3 * 2 * 80 * 16);
+  const double k255 = (double)(1.0f / 255.0f);
+  for (int m = 0; m < 3; m++) {
+    const float *b = blobs[m];
+    for (int k = 0; k < 8; k++) {
+      const float *w = b + k * 9;
+      double smax = 0.0;
+      for (int t = 0; t < 9; t++) smax = fabs((double)w[t]) > smax ? fabs((double)w[t]) : smax;
+      if (smax == 0.0) smax = 1.0;
+      double F = 1048576.0 / smax;  // 2^20 / max |w|
+      long long Q[9];
+      for (;;) {
+        long long sum = 0;
+        for (int t = 0; t < 9; t++) {
+          Q[t] = llround((double)w[t] * F);
+          sum += Q[t] < 0 ? -Q[t] : Q[t];
+        }
+        if (255 * sum < 2147483647LL - 64 * 1024 * 1024) break;
+        F *= 0.5;
+      }
+      convf[m * 8 + k] = (float)(k255 / F);
+      convf[24 + m * 8 + k] = b[72 + k];
+      for (int t = 0; t < 9; t++) {
+        long long q = Q[t];
+        int digit[3];
+        for (int j = 2; j >= 1; j--) {
+          const long long d = ((q + 64) % 128 + 128) % 128 - 64;
+          digit[j] = (int)d;
+          q = (q - d) / 128;
+        }
+        digit[0] = (int)q;
+        const int ti = t / 3, tj = t % 3;  // tap row / column
+        for (int pr = 0; pr < 3; pr++)
+          for (int pc = 0; pc < 3; pc++) {
+            const int n = k * 9 + pr * 3 + pc, kk = (pr + ti) * 5 + (pc + tj);
+            for (int j = 0; j < 3; j++) convb[((((size_t)m * 3 + j) * 2 + kk / 16) * 80 + n) * 16 + kk % 16] = (int8_t)digit[j];
+          }
+      }
+    }
+    const float *hw = b + 80;  // [32][320]
+    for (int c = 0; c < 40; c++)
+      for (int u = 0; u < 32; u++)
+        for (int k = 0; k < 8; k++) {
+          const float v = hw[(size_t)u * 320 + k * 40 + c];
+          const uint16_t hi = half_bits_rn(v);
+          const uint16_t lo = half_bits_rn(v - half_bits_to_float(hi));
+          const size_t at = (((size_t)c * 32) + u) * 8 + k;
+          hidb[((size_t)m * 2 + 0) * (40 * 32 * 8) + at] = hi;
+          hidb[((size_t)m * 2 + 1) * (40 * 32 * 8) + at] = lo;
+        }
+  }
+}
+
 void b200_build_bilateral_tables(float *color256, float *space5) {
   const int aperture = 3;
   const double sigma_color = (aperture / 2.0 - 1) * 0.3 + 0.8;  // the reference's "space_sigma"

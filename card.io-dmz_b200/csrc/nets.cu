@@ -894,6 +894,13 @@ static int launch_categorize(const NetWeights &wts, const uint8_t *cards, b200_s
     else digit_prep_kernel<false><<<pgrid, kPrepWarps * 32, 0, s>>>(cards, scans, nullptr, (int)digits, q8);
     launches++;
   }
+  // prepared byte patches go through the tensor-core kernel (categorize_mma.cu); float patches (the model tap) and
+  // B200_DMZ_CNN_FP32=1 (A / B measurements) through the FP32 kernel of this file
+  const char *fp32_env = getenv("B200_DMZ_CNN_FP32");
+  if (raw_float == nullptr && !(fp32_env && *fp32_env && atoi(fp32_env) != 0)) {
+    const int rc = launch_categorize_mma(wts, q8, scans, n, is_raw, raw_out, s);
+    return rc < 0 ? -1 : launches - 1 + rc;
+  }
   if (is_raw) categorize_kernel<true><<<grid, kCThreads, sizeof(CatSmem), s>>>(wts, raw_float ? nullptr : q8, nullptr, raw_float, n, raw_out);
   else categorize_kernel<false><<<grid, kCThreads, sizeof(CatSmem), s>>>(wts, q8, scans, nullptr, n, nullptr);
   return cudaGetLastError() == cudaSuccess ? launches : -1;
