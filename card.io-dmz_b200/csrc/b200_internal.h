@@ -87,7 +87,7 @@ struct NetWeights {  // device pointers (+ the by-value convolution constants)
   const float *vseg_unit;  // [64] VsegUnit
   const float *vseg_sd;    // [256][256][2]: (s, d0) of a row with 8-bit min / max (mn, mx): x_k = (v_k - mn) * s + d0
   // tensor-core form of the digit CNNs (categorize_mma.cu; built on the host by b200_build_cnn_mma_tables)
-  const int8_t *cnn_convb;   // [3 models][3 digits][2 K chunks][80][16]: conv taps as signed base-128 digits, operand layout
+  const int8_t *cnn_convb;   // [3 models][2 K chunks][3 digits x 80][16]: conv taps as signed base-128 digits, operand layout
   const float *cnn_convf;    // [24] (1/255) / F per (model, kernel), then [24] conv biases
   const uint16_t *cnn_hidb;  // fp16 [3 models][Whi, Wlo][40 cells][32 units][8 kernels]
   ConvConsts conv;

@@ -267,7 +267,8 @@ static float half_bits_to_float(uint16_t h) {
 // logistic W 10 x 32, logistic b 10.
 //   conv: per (model, kernel) w = Q / F with integer |Q| <= 2^20 and 255 * sum |Q| < 2^31 (so that sum_taps Q q fits 32 bits for
 //   any bytes q); Q = (d0 << 14) + (d1 << 7) + d2 with balanced digits.  Operand column n = kernel * 9 + (pr * 3 + pc) (the conv
-//   position inside the 3 x 3 pool window), row k = wy * 5 + wx (byte of the cell's 5 x 5 window): tap (wy - pr, wx - pc).
+//   position inside the 3 x 3 pool window), row k = wy * 5 + wx (byte of the cell's 5 x 5 window): tap (wy - pr, wx - pc);
+//   the three digit matrices are stacked along N (column 80 j + n), so one N = 240 MMA fills the three accumulators.
 //   convf: (1/255 as float, in double) / F per (model, kernel), then the biases (added after the pool maximum).
 //   hidden: W[u][kernel * 40 + cell] as fp16 hi + fp16 lo, operand chunk = cell, row = unit, element = kernel.
 void b200_build_cnn_mma_tables(const float *const blobs[3], int8_t *convb, float *convf, uint16_t *hidb) {
@@ -306,7 +307,7 @@ void b200_build_cnn_mma_tables(const float *const blobs[3], int8_t *convb, float
         for (int pr = 0; pr < 3; pr++)
           for (int pc = 0; pc < 3; pc++) {
             const int n = k * 9 + pr * 3 + pc, kk = (pr + ti) * 5 + (pc + tj);
-            for (int j = 0; j < 3; j++) convb[((((size_t)m * 3 + j) * 2 + kk / 16) * 80 + n) * 16 + kk % 16] = (int8_t)digit[j];
+            for (int j = 0; j < 3; j++) convb[((((size_t)m * 2 + kk / 16) * 240) + 80 * j + n) * 16 + kk % 16] = (int8_t)digit[j];
           }
       }
     }

@@ -40,14 +40,14 @@ constexpr int kQStride = B200_Q8_STRIDE;   // 528
 constexpr int kConvN = 80;                 // 8 kernels x 9 pool positions = 72 columns, padded to a multiple of 16
 constexpr int kFeatPart = 40 * kSlots * 16;   // 20 480: one fp16 part of the feature operand: [40 cells][32 slots][8 kernels]
 constexpr int kHidBPart = 40 * 32 * 16;       // 20 480: one fp16 part of a model's hidden weights: [40 cells][32 units][8 kernels]
-constexpr int kConvBBytes = 3 * 3 * 2 * kConvN * 16;  // 23 040
+constexpr int kConvBBytes = 3 * 2 * (3 * kConvN) * 16;  // 23 040: [model][2 K chunks][3 digits x 80][16]
 
 struct Smem {
   alignas(128) uint8_t feat[2][2 * kFeatPart];       // double buffered by model parity; each: hi part, lo part
   alignas(128) uint8_t hidb[2 * kHidBPart];          // Whi, Wlo of the current model (the MMA's unused rows 32 .. 127 of the
                                                      // feature operand read on into here: harmless)
   alignas(128) uint8_t conva[kG * 5 * 2 * 128 * 16];  // window tiles: [frame][tile][2 K chunks][128 cells][16]
-  alignas(128) uint8_t convb[kConvBBytes];           // [model][digit][2 K chunks][80][16]
+  alignas(128) uint8_t convb[kConvBBytes];           // [model][2 K chunks][digit * 80 + column][16]
   alignas(16) uint8_t q8[kSlots * kQStride];
   float hid[3][32][kSlots];                          // [model][unit][slot]
   float prob[kSlots][3][10];
@@ -136,10 +136,17 @@ categorize_mma_kernel(const int8_t *__restrict__ convb_g, const float *__restric
 
   if (warp == 16) {
     // ================= MMA issuer (one thread) =================
+    // Measured on B200 (ms per 100 k frames for the categorize stage): conv units double buffered + each model's 60 hidden
+    // MMAs as ONE burst 11.1; hidden MMAs sliced between the next model's conv units 12.1; a warp-uniform issue loop with
+    // an elected lane 14.1; hidden MMAs issued one at a time whenever the conv slots are busy 17.7 -- alternating between the
+    // integer and the fp16 MMA kinds is what costs, so the two kinds are kept in long runs.
     if (lane == 0) {
-      const uint32_t idesc_c = umma::instr_desc(umma::kAccS32, umma::kFmtU8, umma::kFmtS8, 128, kConvN);
+      const uint32_t idesc_c = umma::instr_desc(umma::kAccS32, umma::kFmtU8, umma::kFmtS8, 128, 3 * kConvN);
       const uint32_t idesc_h = umma::instr_desc(umma::kAccF32, umma::kFmtF16, umma::kFmtF16, 128, 32);
-      const uint32_t conva = umma::smem_addr(S.conva), convb = umma::smem_addr(S.convb), hidb = umma::smem_addr(S.hidb);
+      const uint64_t conva_d = umma::smem_desc(umma::smem_addr(S.conva), 2048, 128);
+      const uint64_t convb_d = umma::smem_desc(umma::smem_addr(S.convb), 3 * kConvN * 16, 128);
+      const uint64_t feat_d = umma::smem_desc(umma::smem_addr(&S.feat[0][0]), kSlots * 16, 128);
+      const uint64_t hidb_d = umma::smem_desc(umma::smem_addr(S.hidb), 32 * 16, 128);
       uint32_t pe0 = 1, pe1 = 1, pfr = 0, phr = 1, pa = 0, phb = 0;  // (waiting on parity 1 of a fresh barrier passes at once)
       for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
         int nd0, nd1;
@@ -149,16 +156,13 @@ categorize_mma_kernel(const int8_t *__restrict__ convb_g, const float *__restric
         umma::mbar_wait(&S.a_ready, pa), pa ^= 1u;
         umma::fence_after_sync();
         for (int m = 0; m < 3; m++) {
+          const uint64_t bd = umma::desc_advance(convb_d, (m * 2) * (3 * kConvN * 16));
           for (int u = 0; u < nunits; u++) {
             if (u & 1) umma::mbar_wait(&S.empty[1], pe1), pe1 ^= 1u;
             else umma::mbar_wait(&S.empty[0], pe0), pe0 ^= 1u;
             umma::fence_after_sync();
             const int fi = u >= nt0, t = u - (fi ? nt0 : 0);
-            const uint64_t ad = umma::smem_desc(conva + ((fi * 5 + t) * 2) * 2048, 2048, 128);
-#pragma unroll
-            for (int j = 0; j < 3; j++)
-              umma::mma_i8(tmem + 240u * (u & 1) + kConvN * j, ad, umma::smem_desc(convb + ((m * 3 + j) * 2) * (kConvN * 16), kConvN * 16, 128),
-                           idesc_c, 0u);
+            umma::mma_i8(tmem + 240u * (u & 1), umma::desc_advance(conva_d, ((fi * 5 + t) * 2) * 2048), bd, idesc_c, 0u);
             umma::mma_commit(&S.full[u & 1]);
           }
           // hidden layer of model m: [32 slots x 960] . [960 x 32] into columns 480 .. 511
@@ -166,14 +170,14 @@ categorize_mma_kernel(const int8_t *__restrict__ convb_g, const float *__restric
           umma::mbar_wait(&S.hread, phr), phr ^= 1u;
           umma::mbar_wait(&S.hidb_ready, phb), phb ^= 1u;
           umma::fence_after_sync();
-          const uint32_t fa = umma::smem_addr(&S.feat[m & 1][0]);
+          const uint64_t fa = umma::desc_advance(feat_d, (m & 1) * (2 * kFeatPart));
 #pragma unroll 1
           for (int part = 0; part < 3; part++) {
-            const uint32_t ab = fa + (part == 1 ? kFeatPart : 0), bb = hidb + (part == 2 ? kHidBPart : 0);
+            const uint64_t ab = umma::desc_advance(fa, part == 1 ? kFeatPart : 0), bb = umma::desc_advance(hidb_d, part == 2 ? kHidBPart : 0);
 #pragma unroll 4
-            for (int s = 0; s < 20; s++)
-              umma::mma_f16(tmem + 480u, umma::smem_desc(ab + 2 * s * (kSlots * 16), kSlots * 16, 128),
-                            umma::smem_desc(bb + 2 * s * (32 * 16), 32 * 16, 128), idesc_h, (uint32_t)((part | s) != 0));
+            for (int st = 0; st < 20; st++)
+              umma::mma_f16(tmem + 480u, umma::desc_advance(ab, 2 * st * (kSlots * 16)), umma::desc_advance(bb, 2 * st * (32 * 16)), idesc_h,
+                            (uint32_t)((part | st) != 0));
           }
           umma::mma_commit(&S.hfull);
         }

@@ -63,6 +63,16 @@ __host__ __device__ constexpr uint32_t instr_desc(int acc_fmt, int a_fmt, int b_
   return ((uint32_t)acc_fmt << 4) | ((uint32_t)a_fmt << 7) | ((uint32_t)b_fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+// One lane of a fully converged warp (warp-uniform control flow around the issue keeps descriptors and addresses in uniform
+// registers: an `if (lane == 0)` region would pay an R2UR round trip per operand).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{ .reg .pred p; elect.sync _|p, 0xffffffff; selp.u32 %0, 1, 0, p; }" : "=r"(pred));
+  return pred != 0;
+}
+// descriptor of the same matrix `bytes` further on (start-address field only; no carry out of its 14 bits for shared memory)
+__device__ __forceinline__ uint64_t desc_advance(uint64_t d, uint32_t bytes) { return d + (uint64_t)(bytes >> 4); }
+
 // ---- MMA issue (ONE thread): D[tmem] (+)= A[smem] * B[smem]^T
 __device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
