@@ -19,6 +19,16 @@ namespace {
 
 std::mutex g_mutex;
 b200_ctx *g_default_ctx = nullptr;  // scanner_* carry no dmz_context: they share one lazily created context
+// A b200_ctx is not thread-safe.  The reference's functions can be called from any thread (each call is self-contained), so
+// calls that go through the SHARED default context are serialised here; a context owned by a dmz_context is the caller's
+// (one thread per dmz_context, as in the SDKs).
+std::recursive_mutex g_call_mutex;
+struct CtxCall {
+  std::unique_lock<std::recursive_mutex> lock;
+  explicit CtxCall(b200_ctx *ctx) {
+    if (ctx != nullptr && ctx == g_default_ctx) lock = std::unique_lock<std::recursive_mutex>(g_call_mutex);
+  }
+};
 
 b200_ctx *default_ctx() {
   std::lock_guard<std::mutex> lock(g_mutex);
@@ -119,6 +129,7 @@ bool dmz_detect_edges(IplImage *y, IplImage *cb, IplImage *cr, FrameOrientation 
                       dmz_corner_points *corner_points) {
   found_edges->top.found = found_edges->bottom.found = found_edges->left.found = found_edges->right.found = 0;
   b200_ctx *ctx = default_ctx();
+  CtxCall call_guard(ctx);
   if (!ctx || !y || !cb || !cr) return false;
   PlaneView vy = view_of(y), vb = view_of(cb), vr = view_of(cr);
   if (vb.w != vy.w / 2 || vb.h != vy.h / 2 || vr.w != vb.w || vr.h != vb.h || vr.step != vb.step) return false;
@@ -140,6 +151,7 @@ void dmz_deinterleave_uint8_c2(IplImage *interleaved, IplImage **channel1, IplIm
   *channel1 = create_gray_image(v.w, v.h);
   *channel2 = create_gray_image(v.w, v.h);
   b200_ctx *ctx = default_ctx();
+  CtxCall call_guard(ctx);
   if (!ctx) return;
   const size_t plane = (size_t)v.w * v.h;
   uint8_t *tmp = (uint8_t *)malloc(2 * plane);
@@ -159,6 +171,7 @@ void dmz_best_expiry_seg(IplImage *card_y, uint16_t starting_y_offset, CythonGro
   *expiry_groups = NULL;
   *number_of_groups = 0;
   b200_ctx *ctx = default_ctx();
+  CtxCall call_guard(ctx);
   if (!ctx || !card_y) return;
   PlaneView v = view_of(card_y);
   if (v.w != B200_CARD_W || v.h != B200_CARD_H) return;
@@ -190,6 +203,7 @@ void dmz_best_expiry_seg(IplImage *card_y, uint16_t starting_y_offset, CythonGro
 // drops any ROI the caller had set; this layer leaves the caller's IplImage untouched.)
 static float frame_score(IplImage *image, bool use_full_image, bool want_focus) {
   b200_ctx *ctx = default_ctx();
+  CtxCall call_guard(ctx);
   if (!ctx || !image) return 0.0f;
   PlaneView v = view_of(image);
   // b200_frame_scores_batch places the rectangle inside a (w x h) plane; hand it the whole image when sizes agree,
@@ -208,6 +222,7 @@ float dmz_brightness_score(IplImage *image, bool use_full_image) { return frame_
 void dmz_transform_card(dmz_context *dmz, IplImage *sample, dmz_corner_points corner_points, FrameOrientation orientation,
                         bool upsample, IplImage **transformed) {
   b200_ctx *ctx = dmz && dmz->mz ? (b200_ctx *)dmz->mz : default_ctx();
+  CtxCall call_guard(ctx);
   if (*transformed == NULL) *transformed = create_card_image();  // dmz.cpp:493-495; the caller frees it
   if (!ctx || !sample) return;
   PlaneView v = view_of(sample);
@@ -259,13 +274,17 @@ namespace {
 void expiry_step(b200_ctx *ctx, ScannerState *state, const uint8_t *card, FrameScanResult *result, bool usable) {
   result->expiry_groups.clear();
   result->name_groups.clear();
-  const int max_groups = 32;
-  b200_expiry_group g[max_groups];
-  int32_t count = 0;
+  // the reference's lists are unbounded: start with room for 32 groups and retry with what the kernel reports it had to drop
+  std::vector<b200_expiry_group> g(32);
+  int32_t count = 0, dropped = 0;
   uint16_t yo = result->vseg.y_offset;
   if (yo < B200_CARD_H - 2 * 15) {  // kCreditCardTargetHeight - 2 * kSmallCharacterHeight, frame.cpp:73
-    if (b200_best_expiry_seg_batch(ctx, card, &yo, 1, B200_MEM_HOST, g, max_groups, &count, nullptr, nullptr) != B200_OK) count = 0;
-    if (count > max_groups) count = max_groups;
+    for (int attempt = 0; attempt < 2; attempt++) {
+      if (b200_best_expiry_seg_batch(ctx, card, &yo, 1, B200_MEM_HOST, g.data(), (int)g.size(), &count, &dropped, nullptr) != B200_OK) count = dropped = 0;
+      if (dropped <= 0) break;
+      g.assign((size_t)count + (size_t)dropped + 8, b200_expiry_group());
+    }
+    if (count > (int)g.size()) count = (int)g.size();
   }
   for (int i = 0; i < count; i++) {
     GroupedRects gr;
@@ -285,8 +304,10 @@ void expiry_step(b200_ctx *ctx, ScannerState *state, const uint8_t *card, FrameS
   state->name_groups = result->name_groups;
   if (count == 0) return;  // expiry_extract: nothing new, nothing to do
   // categorize characters 0, 1, 3, 4 of every group (categorize_expiry_digits)
-  int32_t where[max_groups * 4 * 3];
-  float probs[max_groups * 4 * 10];
+  std::vector<int32_t> where_v((size_t)count * 4 * 3);
+  std::vector<float> probs_v((size_t)count * 4 * 10);
+  int32_t *where = where_v.data();
+  float *probs = probs_v.data();
   const int chars[4] = {0, 1, 3, 4};
   for (int i = 0; i < count; i++)
     for (int c = 0; c < 4; c++) {
@@ -294,22 +315,24 @@ void expiry_step(b200_ctx *ctx, ScannerState *state, const uint8_t *card, FrameS
       w[0] = 0, w[1] = g[i].rect_top[chars[c]], w[2] = g[i].rect_left[chars[c]];
     }
   if (b200_expiry_digits_at_batch(ctx, card, 1, where, count * 4, B200_MEM_HOST, probs) != B200_OK) return;
-  ExpiryAgg fresh[kMaxExpiryAgg], agg[kMaxExpiryAgg];
+  const int cap = count + (int)state->expiry_groups.size();
+  std::vector<ExpiryAgg> fresh_v((size_t)count), agg_v((size_t)cap);
+  ExpiryAgg *fresh = fresh_v.data(), *agg = agg_v.data();
   int n_fresh = 0, n_agg = 0;
-  for (int i = 0; i < count && n_fresh < kMaxExpiryAgg; i++) {
+  for (int i = 0; i < count; i++) {
     ExpiryAgg &f = fresh[n_fresh++];
     f.top = g[i].top, f.left = g[i].left, f.n_rects = g[i].n_rects, f.recently_seen = f.total_seen = 0, f.tag = -(i + 1);
     memset(f.scores, 0, sizeof(f.scores));
     for (int c = 0; c < 4; c++) memcpy(f.scores[chars[c]], probs + (i * 4 + c) * 10, sizeof(float) * 10);
   }
-  for (size_t o = 0; o < state->expiry_groups.size() && n_agg < kMaxExpiryAgg; o++) {
+  for (size_t o = 0; o < state->expiry_groups.size(); o++) {
     const GroupedRects &G = state->expiry_groups[o];
     ExpiryAgg &a = agg[n_agg++];
     a.top = G.top, a.left = G.left, a.n_rects = (int)G.character_rects.size();
     a.recently_seen = G.recently_seen_count, a.total_seen = G.total_seen_count, a.tag = (int)o;
     memcpy(a.scores, G.scores, sizeof(a.scores));  // rows 0..4 of the 11 x 10 row-major matrix
   }
-  expiry_aggregate(agg, &n_agg, fresh, n_fresh);
+  expiry_aggregate(agg, &n_agg, fresh, n_fresh, cap);
   GroupedRectsList next;
   for (int k = 0; k < n_agg; k++) {
     GroupedRects G = agg[k].tag >= 0 ? state->expiry_groups[(size_t)agg[k].tag] : result->expiry_groups[(size_t)(-agg[k].tag - 1)];
@@ -346,6 +369,7 @@ void scanner_add_frame_with_expiry(ScannerState *state, IplImage *y, bool scan_e
   result->upside_down = false;
   result->usable = false;
   b200_ctx *ctx = default_ctx();
+  CtxCall call_guard(ctx);
   if (!ctx || !y || y->width != B200_CARD_W || y->height != B200_CARD_H) return;
   const bool need_number = state->timeOfCardNumberCompletionInMilliseconds == 0;
   const bool need_expiry = scan_expiry && (state->expiry_month == 0 || state->expiry_year == 0);

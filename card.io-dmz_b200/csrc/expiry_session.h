@@ -21,7 +21,7 @@ struct ExpiryAgg {  // what survives of a GroupedRects across frames (expiry_typ
   float scores[5][10];  // rows = character index; row 2 (the slash) is never scored
   int tag;              // caller's handle (dmz_compat.cpp: index of the GroupedRects this entry came from)
 };
-constexpr int kMaxExpiryAgg = 64;
+constexpr int kMaxExpiryAgg = 64;  // capacity of the C-ABI session (b200_scanner); the C++ drop-in layer sizes its lists per frame
 
 bool same_place(int top_a, int left_a, int n_a, int top_b, int left_b, int n_b) {
   // GROUPED_RECTS_VERTICAL_ALLOWANCE = 16 / 2, GROUPED_RECTS_HORIZONTAL_ALLOWANCE = 11 / 2 (expiry_categorize.cpp:24-25)
@@ -68,7 +68,7 @@ void stable_month_year(const float (*scores)[10], int n_chars, int current_year,
 }
 
 // expiry_aggregate_grouped_rects (expiry_categorize.cpp:258-330): merges the frame's groups `fresh` into the session's `agg`.
-inline void expiry_aggregate(ExpiryAgg *agg, int *n_agg, ExpiryAgg *fresh, int n_fresh) {
+inline void expiry_aggregate(ExpiryAgg *agg, int *n_agg, ExpiryAgg *fresh, int n_fresh, int agg_capacity = kMaxExpiryAgg) {
   // (a) equivalent groups inside the new list: running mean into the earlier one
   for (int i = 0; i < n_fresh; i++) {
     const int top1 = fresh[i].top, left1 = fresh[i].left, n1 = fresh[i].n_rects;
@@ -105,7 +105,7 @@ inline void expiry_aggregate(ExpiryAgg *agg, int *n_agg, ExpiryAgg *fresh, int n
       (*n_agg)--;
     }
   }
-  for (int j = 0; j < n_fresh && (*n_agg) < kMaxExpiryAgg; j++) {
+  for (int j = 0; j < n_fresh && (*n_agg) < agg_capacity; j++) {
     fresh[j].recently_seen = 3, fresh[j].total_seen = 1;
     agg[(*n_agg)++] = fresh[j];
   }
