@@ -925,7 +925,9 @@ int b200_frame_scores_batch(b200_ctx *ctx, const uint8_t *y, int yrs, size_t yfs
   return B200_OK;
 } B200_GUARD(ctx)
 
-// best_expiry_seg over a batch.  The |Scharr| planes are scratch (231 KB per card), so the batch runs in chunks.
+// best_expiry_seg over a batch.  The |Scharr| planes are scratch (231 KB per card), so the batch runs in chunks -- deep ones:
+// the one-thread-per-card search is latency-bound and its throughput grows with the cards in flight (2048 per chunk: 55 k
+// cards/s, 32768: 344 k cards/s; 7.6 GB of scratch, allocated only when a call is that large).
 int b200_best_expiry_seg_batch(b200_ctx *ctx, const uint8_t *cards, const uint16_t *y_offsets, int n, int mem,
                                b200_expiry_group *groups, int max_groups, int32_t *n_groups, int32_t *n_dropped, int16_t *sobel_out) try {
   if (!ctx || !cards || !y_offsets || !groups || !n_groups || n < 1 || max_groups < 1)
@@ -933,7 +935,8 @@ int b200_best_expiry_seg_batch(b200_ctx *ctx, const uint8_t *cards, const uint16
   if (!ctx->d_slash) return fail(ctx, B200_EUNSUPPORTED, "modelm_730c4cbd.bin was not found in the weights directory");
   CU(cudaSetDevice(ctx->device));
   const size_t card_bytes = (size_t)B200_CARD_W * B200_CARD_H, sob_bytes = card_bytes * sizeof(int16_t);
-  const int chunk = n < 2048 ? n : 2048;
+  static const int max_chunk = [] { const char *e = getenv("B200_DMZ_EXPIRY_CHUNK"); return e && atoi(e) > 0 ? atoi(e) : 32768; }();
+  const int chunk = n < max_chunk ? n : max_chunk;
   const bool host = mem == B200_MEM_HOST;
   auto up16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
   const size_t o_sob = 0, o_ls = o_sob + up16(sob_bytes * chunk), o_cards = o_ls + up16(sizeof(int32_t) * B200_CARD_H * chunk),

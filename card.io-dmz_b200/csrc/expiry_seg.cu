@@ -9,6 +9,8 @@
 //                          host/device header expiry_seg_core.h (the same code the CPU unit tests pin on the reference).
 // Compiled with -fmad=false: the few float expressions must round like the reference's (and like the host build of
 // the header).
+#include <stdlib.h>
+
 #include "b200_internal.h"
 #include "expiry_seg_core.h"
 
@@ -47,8 +49,14 @@ expiry_scharr_kernel(const uint8_t *__restrict__ cards, const uint16_t *__restri
 __global__ void __launch_bounds__(32)
 expiry_groups_kernel(const int16_t *__restrict__ sob, const int32_t *__restrict__ line_sum, const uint16_t *__restrict__ y_offsets,
                      int n, const float *__restrict__ slash_w, b200_expiry_group *__restrict__ groups, int max_groups,
-                     int32_t *__restrict__ n_groups, int32_t *__restrict__ n_dropped) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+                     int32_t *__restrict__ n_groups, int32_t *__restrict__ n_dropped, int cards_per_warp) {
+  // The search is branchy and data dependent: the cards of one warp execute one after the other wherever they diverge.
+  // cards_per_warp < 32 spreads them over more warps (lanes 0, 32 / cpw, ...), but a lone lane uses 4 bytes of every
+  // 128-byte local-memory line: measured on B200 (65 536 deck cards, cards/s) 32 per warp wins once the batch is deep --
+  // chunk 2048: 55 k (32) / 75 k (8) / 88 k (2); chunk 8192: 168 k / 172 k / 100 k; chunk 32768: 344 k (32) / 239 k (16) / 180 k (8).
+  const int stride = 32 / cards_per_warp;
+  if (threadIdx.x % stride != 0) return;
+  const int i = blockIdx.x * cards_per_warp + threadIdx.x / stride;
   if (i >= n) return;
   int overflow = 0;
   const int yo = (int)y_offsets[i];
@@ -68,6 +76,11 @@ int launch_expiry_seg(const uint8_t *cards, const uint16_t *y_offsets, int n, co
                       b200_expiry_group *groups, int max_groups, int32_t *n_groups, int32_t *n_dropped, cudaStream_t s) {
   expiry_scharr_kernel<<<n, kScharrThreads, 0, s>>>(cards, y_offsets, n, sob, line_sum);
   if (cudaGetLastError() != cudaSuccess) return -1;
-  expiry_groups_kernel<<<(n + 31) / 32, 32, 0, s>>>(sob, line_sum, y_offsets, n, slash_w, groups, max_groups, n_groups, n_dropped);
+  static const int cpw = [] {  // measured on B200 (tools/gpu_side_bench.py): see DESIGN.md
+    const char *e = getenv("B200_DMZ_EXPIRY_CARDS_PER_WARP");
+    const int v = e && *e ? atoi(e) : 32;
+    return v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32 ? v : 32;
+  }();
+  expiry_groups_kernel<<<(n + cpw - 1) / cpw, 32, 0, s>>>(sob, line_sum, y_offsets, n, slash_w, groups, max_groups, n_groups, n_dropped, cpw);
   return cudaGetLastError() == cudaSuccess ? 2 : -1;
 }

@@ -42,8 +42,8 @@ p2 = torch.randint(0, 256, (n, 513), dtype=torch.uint8, device="cuda", generator
 o2 = torch.zeros((n, 40), dtype=torch.float32, device="cuda")
 timed("categorize_patches", lambda: dmz._check(lib.b200_categorize_patches_batch(ctx, C.c_void_p(p2.data_ptr()), n, MEM_DEVICE, C.c_void_p(o2.data_ptr()))), n)
 # frame scores on deck frames
-F = 8192
-frames = deck_frames_cuda(0, F, 640, 480, 8.0, 0xCA2D10)
+F = int(os.environ.get("SIDE_BENCH_CARDS", "8192"))
+frames = torch.cat([deck_frames_cuda(f0, min(8192, F - f0), 640, 480, 8.0, 0xCA2D10) for f0 in range(0, F, 8192)])
 fo = torch.zeros(F, dtype=torch.float32, device="cuda"); br = torch.zeros(F, dtype=torch.float32, device="cuda")
 timed("frame_scores", lambda: dmz._check(lib.b200_frame_scores_batch(ctx, C.c_void_p(frames.data_ptr()), 640, 640 * 480, 640, 480, F, 0, MEM_DEVICE,
                                                                         C.c_void_p(fo.data_ptr()), C.c_void_p(br.data_ptr()))), F)
