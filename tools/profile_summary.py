@@ -30,9 +30,12 @@ METRICS = [
     "smsp__inst_executed.sum", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
+    "sm__inst_executed_pipe_tc.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tmem.avg.pct_of_peak_sustained_active",
+    "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
 ]
-STAGE_OF = {"detect_strips": "detect", "warp_kernel": "warp", "vseg_rows": "vseg", "hseg_kernel": "hseg",
-            "categorize_kernel": "categorize", "finalize_records": "finalize"}
+STAGE_OF = {"detect_strips": "detect", "warp_kernel": "warp", "warp_rows": "warp", "vseg_rows": "vseg", "vseg_mma": "vseg", "hseg_kernel": "hseg",
+            "categorize_kernel": "categorize", "categorize_mma": "categorize", "digit_prep": "categorize", "finalize_records": "finalize"}
+SUMMED = ("vseg", "warp", "categorize")  # stages made of several launches per step: their traffic adds up
 
 
 def short(name):
@@ -40,7 +43,9 @@ def short(name):
 
 
 def launch_shares(tag):
-    src = os.path.join(OUT, "launches.csv")
+    src = os.path.join(OUT, tag + "_launches.csv")
+    if not os.path.exists(src):
+        src = os.path.join(OUT, "launches.csv")
     shutil.copy(src, os.path.join(PROF, tag + "_launches.csv"))
     lines = [l for l in open(src) if l.startswith('"')]
     rows = list(csv.DictReader(io.StringIO("".join(lines))))
@@ -53,12 +58,14 @@ def launch_shares(tag):
         t[0] += 1
         t[1] += float(r["Metric Value"]) / 1e3
     total = sum(v[1] for v in per.values())
-    cmd = "python bench.py --steps 2 --warmup 1 --frames 8192 --no-e2e --no-cpu"
+    cmd = "python bench.py --frames 4096 --steps 1 --warmup 1 --no-e2e --no-cpu --no-materialised"
     md = ["# ncu launch list (gpu__time_duration.sum --clock-control none), `%s`" % cmd, "",
           "| kernel | launches | total us | share of step |", "|---|---|---|---|"]
     for k, (n, us) in sorted(per.items(), key=lambda kv: -kv[1][1]):
         md.append("| %s | %d | %.1f | %.3f |" % (k, n, us, us / total))
-    bench = os.path.join(OUT, "bench.json")
+    bench = os.path.join(OUT, tag + "_bench.json")
+    if not os.path.exists(bench):
+        bench = os.path.join(OUT, "bench.json")
     if os.path.exists(bench):
         try:
             b = json.loads(open(bench).read().strip().splitlines()[-1])
@@ -74,12 +81,14 @@ def launch_shares(tag):
 
 
 def full_summary(tag, frames):
-    rep = os.path.join(OUT, "prof.ncu-rep")
+    rep = os.path.join(OUT, tag + "_prof.ncu-rep")
+    if not os.path.exists(rep):
+        rep = os.path.join(OUT, "prof.ncu-rep")
     raw = subprocess.check_output(["ncu", "-i", rep, "--page", "raw", "--csv"], text=True)
     rows = list(csv.reader(io.StringIO(raw)))
     head, units = rows[0], rows[1]
     md = ["# ncu --set full capture (%s), %d frames per launch, B200, --clock-control none" % (tag, frames), "",
-          "Command: see tools/gpu_round.sh.  Per-launch values (cold cache, serialised: compare shares, not absolutes).", ""]
+          "Command: see tools/gpu_final.sh.  Per-launch values (cold cache, serialised: compare shares, not absolutes).", ""]
     traffic = {}
     seen = set()
     for r in rows[2:]:
@@ -97,7 +106,7 @@ def full_summary(tag, frames):
             md.append("- derived: DRAM traffic per frame = %.1f KB" % (per_frame / 1e3))
             for key, stage in STAGE_OF.items():
                 if key in name:
-                    if stage == "vseg":  # coarse + fine launches add up
+                    if stage in SUMMED:  # several launches per step add up
                         traffic[stage] = traffic.get(stage, 0) + int(per_frame)
                     elif stage not in seen:
                         traffic[stage] = int(per_frame)
