@@ -406,8 +406,8 @@ def pipeline_config(args):
 
         def e2e_step():
             dmz.process_frames_host_ptr(h_frames.data_ptr(), Fe, W, H, h_records.data_ptr())
-            if dist is not None:
-                sh.gather_digit_records(sh.digit_records(h_np), Fe * world, dist, rank, world, device="cuda")
+            if dist is not None:  # digit strings of this rank's records -> rank 0 (records go back up: 80 MB, ~1.6 ms; arg-max on the GPU)
+                sh.gather_equal_shards_torch(sh.digit_records_torch(h_records.to("cuda", non_blocking=True)), dist, rank, world)
 
         e2e_step()
         g.barrier()
@@ -538,7 +538,7 @@ def pipeline_config(args):
                     "note": "per-stage CUDA-event times on the launching stream.  No stage of this path is HBM-bound: detect / warp are "
                             "instruction-issue bound integer kernels, vseg / categorize are FP32-FMA bound (their fp32_frac is in `stages`)"}
         out = base_line(g, args, METRIC, value, "frames/s", t_ms, "u8/int32 (detect, warp, hseg) + f32 (vseg, digit CNNs)",
-                        "100k synthetic 640x480 frames, full detect->warp->OCR pipeline on 1xB200 (per GPU)",
+                        "100k synthetic 640x480 frames per GPU, full detect->warp->OCR pipeline on %dxB200" % world,
                         {"frames_per_gpu_per_step": F, "width": W, "height": H, "deck_seed": DECK_SEED, "card_mode": args.card_mode,
                          "l2": "inputs (%.1f GB per step) are larger than L2; no flush needed" % (F * FRAME_BYTES / 1e9),
                          "parallelism": "frames sharded across %d GPU(s), NCCL gather of 32-byte digit strings to rank 0%s" % (world, "" if world > 1 else " (n/a at 1 GPU)")})

@@ -83,6 +83,21 @@ def test_member_layouts_match_reference_headers(tmp_path):
     assert got == want
 
 
+def test_tensor_core_operand_tables(tmp_path):
+    """The host-built operand tables of the tensor-core kernels (b200_tables.cpp) against the float weights: vseg W1 as four
+    base-128 digits (exact to 2^-27 of the unit's largest weight, padding zero), the (s, d0) table against the reference's
+    three-rounding normalisation for every (min, max, value), CNN conv taps as three digits placed at the right
+    (pool position, window byte) with 255 * sum |Q| < 2^31, hidden weights as fp16 hi + lo."""
+    exe = str(tmp_path / "tables_main")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-I" + os.path.join(ROOT, "include"),
+                           "-I" + os.path.join(ROOT, "card.io-dmz_b200", "csrc"), "-I/usr/local/cuda/include",
+                           os.path.join(ROOT, "tests", "tables_main.cpp"), os.path.join(ROOT, "card.io-dmz_b200", "csrc", "b200_tables.cpp"), "-o", exe])
+    out = subprocess.run([exe, os.path.join(ROOT, "card.io-dmz_b200", "weights")], capture_output=True, text=True)
+    vals = dict(line.split() for line in out.stdout.splitlines())
+    assert out.returncode == 0 and vals["failed_checks"] == "0", out.stdout
+    assert float(vals["vseg_weight_rel_err"]) < 8e-9 and float(vals["cnn_conv_weight_rel_err"]) < 1e-6
+
+
 def test_no_context_without_cuda(pkg):
     import torch
     if torch.cuda.is_available():
