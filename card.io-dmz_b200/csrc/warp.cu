@@ -33,6 +33,12 @@
 // u's unit, so X is the reference's unless fX * 2^14 sits within that distance of a rounding tie, i.e. unless the low
 // 14 bits of u are 0 (the tie itself).  Low bits 0 OR 1 send the PIXEL (not the quad) to the exact reference sequence
 // -- one call in ~0.1 % of the quads -- so the result is bit-identical for every pixel.
+//
+// Tried and dropped (B200, ms per 100 k frames, lazy rows / materialised card): persistent CTAs with a producer warp that plans
+// and TMA-fetches one task ahead into a second tile buffer (tools/experiments/warp_persistent.cu.txt: bit-exact, all tests
+// green) 11.0 / 26.4 with three CTAs per SM, 11.4 / 23.2 with two, against 9.7 / 18.9 for this one-task-per-CTA kernel: the
+// kernel is issue-bound, four resident CTAs already cover each other's plan and TMA latency, and the second tile buffer
+// costs a quarter of the resident consumer warps.
 #include <cuda.h>
 #include <float.h>
 #include <stdlib.h>
