@@ -403,7 +403,10 @@ int launch_warp(const WarpSource &S, const FrameGeom *geom, uint8_t *cards, unsi
   // short side is 128 (measured on B200, ms per 100 k frames, 128 against 64: materialised card 18.9 / 21.3, lazy rows
   // 9.7 / 11.4 -- fewer, larger CTAs amortise the per-CTA set-up).  B200_DMZ_WARP_TILE=64|128 overrides.
   static const int force_tile = env_int("B200_DMZ_WARP_TILE", 0);
-  const int tshort = force_tile == 64 || force_tile == 128 ? force_tile : 128;
+  // The 43-row fine window and the 27-row strip need ~60 source lines: a 256 x 64 box fetches half the bytes of the 256 x 128
+  // one the full card / the coarse rows use (B200_DMZ_WARP_FINE_TILE overrides).
+  static const int fine_tile = env_int("B200_DMZ_WARP_FINE_TILE", 64);
+  const int tshort = force_tile == 64 || force_tile == 128 ? force_tile : ((mode == WARP_FINE || mode == WARP_STRIP) && fine_tile == 64 ? 64 : 128);
   const int tw = portrait ? tshort : 256, th = portrait ? 256 : tshort;
   // along a destination row the source advances `scale` pixels per pixel; keep ~8 % slack for corner jitter and 24 for
   // the aligned start and the tap margins
