@@ -67,6 +67,12 @@ def build(force=False):
     if force or newer(lat, [lat_src, lib, os.path.join(ROOT, "include", "dmz_b200_compat.h")]):
         run(["g++", "-std=c++14", "-O2", "-I" + os.path.join(ROOT, "include"), lat_src, "-o", lat, "-L" + HERE, "-lb200dmz",
              "-Wl,-rpath,$ORIGIN/..", "-ldl"])
+    # device-side checks of the primitives (tools/microbench: tcgen05 kind::i8 against a host product; FFMA / FFMA2 rates)
+    mb = os.path.join(ROOT, "tools", "microbench")
+    for name, extra in (("umma_i8", ["-I" + CSRC]), ("ffma2", [])):
+        src, exe = os.path.join(mb, name + ".cu"), os.path.join(mb, name)
+        if os.path.exists(src) and (force or newer(exe, [src, os.path.join(CSRC, "umma.cuh")])):
+            run([nvcc] + ARCH + ["-O2", "-o", exe, src] + extra)
     # deck generators (support code)
     deck = os.path.join(ROOT, "tools", "deck")
     dsrc = [os.path.join(deck, f) for f in ("deck_gen.h", "glyphs.h")]

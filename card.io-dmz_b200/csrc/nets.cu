@@ -1,17 +1,20 @@
-// card.io-dmz_b200/csrc/nets.cu -- the two generated networks of the number path, as direct small-filter
-// CUDA-core kernels (FP32 FMA; contract: <= 1e-4 on the probabilities, scan/../models KATs at 1e-5).
+// card.io-dmz_b200/csrc/nets.cu -- the generated networks of the number path as FP32 CUDA-core kernels (FMA; contract:
+// <= 1e-4 on the probabilities, scan/../models KATs at 1e-5), the digit patch preparation, the expiry digit CNN, and the
+// launch sequence of scan_card_image.
 //
 //   vseg_rows_kernel    vseg_probabilities_for_hstrip = llcv_morph_grad3_1d_u8 -> llcv_lineardown2_1d_u8 ->
 //                       llcv_norm_convert_1d_u8_to_f32 -> applym_befe75da      scan/n_vseg.cpp:39-47,
 //                                                                               models/generated/modelm_befe75da.cpp:1770-1786
-//   categorize_kernel   number_scores: per digit ROI -> llcv_morph_grad3_2d_cross_u8 -> llcv_equalize_hist -> /255 ->
-//                       applyc_{5c241121,01266c1b,b00bf70c} -> (r0+r1+r2-max)/2 scan/n_categorize.cpp:45-108,
+//   digit_prep_kernel   per digit ROI -> llcv_morph_grad3_2d_cross_u8 -> llcv_equalize_hist     scan/n_categorize.cpp:75-108
+//   categorize_kernel   applyc_{5c241121,01266c1b,b00bf70c} -> (r0+r1+r2-max)/2                 scan/n_categorize.cpp:45-73,
 //                                                                               models/generated/modelc_*.cpp:1844-1937
 //
-// Neither contraction is large enough to fill a tcgen05 MMA tile at FP32-equivalent accuracy (the 3x3
-// convolutions have K = 9; the FC layers are 320x32 and 204x50 and would need a 3xTF32 split to hold 1e-4),
-// so they run on the FP32 pipe: convolution weights are warp-uniform operands served from __constant__
-// memory, FC weights sit in shared memory for the lifetime of a persistent CTA.
+// Since round 2 the card rows and the prepared byte patches of the whole path go through the tensor-core kernels
+// (vseg_mma.cu, categorize_mma.cu: batched over frames the contractions do fill MMA tiles, and with byte activations they
+// are exact integer products).  The FP32 kernels of this file remain the route of FLOAT inputs -- the reference's embedded
+// model known-answer vectors are float rows / float patches -- and the A / B reference (B200_DMZ_VSEG_FP32 /
+// B200_DMZ_CNN_FP32): convolution weights are warp-uniform kernel-parameter operands, FC weights sit in shared memory for
+// the lifetime of a persistent CTA.
 #include <float.h>
 
 #include <stdlib.h>
