@@ -139,7 +139,9 @@ categorize_mma_kernel(const int8_t *__restrict__ convb_g, const float *__restric
     // Measured on B200 (ms per 100 k frames for the categorize stage): conv units double buffered + each model's 60 hidden
     // MMAs as ONE burst 11.1; hidden MMAs sliced between the next model's conv units 12.1; a warp-uniform issue loop with
     // an elected lane 14.1; hidden MMAs issued one at a time whenever the conv slots are busy 17.7 -- alternating between the
-    // integer and the fp16 MMA kinds is what costs, so the two kinds are kept in long runs.
+    // integer and the fp16 MMA kinds is what costs, so the two kinds are kept in long runs.  Conv units split into kernel
+    // halves (N = 112, four accumulator slots instead of two, thread = (cell, one kernel)): 14.6 -- twice the barrier traffic
+    // and MMAs for the same arithmetic; fewer, larger units win.
     if (lane == 0) {
       const uint32_t idesc_c = umma::instr_desc(umma::kAccS32, umma::kFmtU8, umma::kFmtS8, 128, 3 * kConvN);
       const uint32_t idesc_h = umma::instr_desc(umma::kAccF32, umma::kFmtF16, umma::kFmtF16, 128, 32);
