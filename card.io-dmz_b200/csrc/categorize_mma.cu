@@ -32,6 +32,20 @@
 
 namespace {
 
+#ifdef B200_CNN_TRACE
+__device__ long long g_trace[3][2048];  // three tracer threads of block 0, private regions: no atomics in the timed path
+#define TRACE(tag, cond)                                                                         \
+  do {                                                                                           \
+    if ((cond) && blockIdx.x == 0) {                                                             \
+      const int who_ = threadIdx.x == 0 ? 0 : (threadIdx.x == 480 ? 1 : 2);                      \
+      if (trace_n < 1000) g_trace[who_][2 * trace_n] = (tag), g_trace[who_][2 * trace_n + 1] = clock64(); \
+      trace_n++;                                                                                 \
+    }                                                                                            \
+  } while (0)
+#else
+#define TRACE(tag, cond) do {} while (0)
+#endif
+
 constexpr int kConsumers = 512;            // 16 warps: window tiles, conv / hidden epilogues, logistic layers
 constexpr int kThreads = kConsumers + 64;  // + warp 16: MMA issuer, warp 17: hidden-weight loader
 constexpr int kG = 2;                      // frames per group
@@ -89,6 +103,8 @@ categorize_mma_kernel(const int8_t *__restrict__ convb_g, const float *__restric
   extern __shared__ __align__(128) uint8_t smem_raw[];
   Smem &S = *reinterpret_cast<Smem *>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int trace_n = 0;
+  (void)trace_n;
   const int lq = warp & 3, kq = (warp >> 2) & 3;  // consumers: TMEM lane quarter; kernel pair (conv) / unit octet (hidden)
 
   // ---- set-up
@@ -163,15 +179,18 @@ categorize_mma_kernel(const int8_t *__restrict__ convb_g, const float *__restric
             if (u & 1) umma::mbar_wait(&S.empty[1], pe1), pe1 ^= 1u;
             else umma::mbar_wait(&S.empty[0], pe0), pe0 ^= 1u;
             umma::fence_after_sync();
+            TRACE(100 + (u & 1), true);
             const int fi = u >= nt0, t = u - (fi ? nt0 : 0);
             umma::mma_i8(tmem + 240u * (u & 1), umma::desc_advance(conva_d, ((fi * 5 + t) * 2) * 2048), bd, idesc_c, 0u);
             umma::mma_commit(&S.full[u & 1]);
+            TRACE(110 + (u & 1), true);
           }
           // hidden layer of model m: [32 slots x 960] . [960 x 32] into columns 480 .. 511
           umma::mbar_wait(&S.feat_ready, pfr), pfr ^= 1u;
           umma::mbar_wait(&S.hread, phr), phr ^= 1u;
           umma::mbar_wait(&S.hidb_ready, phb), phb ^= 1u;
           umma::fence_after_sync();
+          TRACE(120, true);
           const uint64_t fa = umma::desc_advance(feat_d, (m & 1) * (2 * kFeatPart));
 #pragma unroll 1
           for (int part = 0; part < 3; part++) {
@@ -182,6 +201,7 @@ categorize_mma_kernel(const int8_t *__restrict__ convb_g, const float *__restric
                             (uint32_t)((part | st) != 0));
           }
           umma::mma_commit(&S.hfull);
+          TRACE(121, true);
         }
       }
     }
@@ -218,7 +238,9 @@ categorize_mma_kernel(const int8_t *__restrict__ convb_g, const float *__restric
     uint32_t pf0 = 0, pf1 = 0, ph = 0;
     // hidden epilogue of model m: accumulator rows 0 .. 31 = TMEM lanes 0 .. 31 -> warps 0, 4, 8, 12 take eight units each
     auto hidden_finish = [&](int m) {
+      TRACE(230, tid == 0);
       umma::mbar_wait(&S.hfull, ph), ph ^= 1u;  // (every consumer warp follows the barrier's phases)
+      TRACE(231, tid == 0);
       if (lq != 0) return;
       umma::fence_after_sync();
       uint32_t v[8];
@@ -272,6 +294,8 @@ categorize_mma_kernel(const int8_t *__restrict__ convb_g, const float *__restric
           if (u & 1) umma::mbar_wait(&S.full[1], pf1), pf1 ^= 1u;
           else umma::mbar_wait(&S.full[0], pf0), pf0 ^= 1u;
           umma::fence_after_sync();
+          TRACE(200 + (u & 1), tid == 0);
+          TRACE(250 + (u & 1), tid == 480);
           // conv epilogue: thread = (cell = TMEM lane, kernels 2 kq and 2 kq + 1)
           const int fi = u >= nt0, t = u - (fi ? nt0 : 0);
           const int ci = 128 * t + 32 * lq + lane, d = ci / 40, cell = ci - d * 40;
@@ -281,6 +305,7 @@ categorize_mma_kernel(const int8_t *__restrict__ convb_g, const float *__restric
           umma::tmem_ld16(ta + kConvN, a1), tmem_ld2(ta + kConvN + 16u, b1);
           umma::tmem_ld16(ta + 2 * kConvN, a2), tmem_ld2(ta + 2 * kConvN + 16u, b2);
           umma::tmem_ld_wait();
+          TRACE(210 + (u & 1), tid == 0);
           umma::fence_before_sync();
           __syncwarp();
           if (lane == 0) mbar_arrive(&S.empty[u & 1]);  // this warp has read its part of the slot
@@ -308,6 +333,7 @@ categorize_mma_kernel(const int8_t *__restrict__ convb_g, const float *__restric
             *reinterpret_cast<__half2 *>(dst + kFeatPart) = __halves2half2(l0, l1);
           }
         }
+        TRACE(220, tid == 0);
         umma::fence_async_smem();  // this warp's features -> visible to the tensor core
         __syncwarp();
         if (lane == 0) mbar_arrive(&S.feat_ready);
@@ -358,6 +384,17 @@ categorize_mma_kernel(const int8_t *__restrict__ convb_g, const float *__restric
 }
 
 }  // namespace
+
+#ifdef B200_CNN_TRACE
+extern "C" int b200_cnn_trace(long long *out, int cap) {  // out: 3 x 2048 stamps (tag, clock); unused entries 0
+  (void)cap;
+  cudaMemcpyFromSymbol(out, g_trace, sizeof(long long) * 3 * 2048);
+  cudaMemset(nullptr, 0, 0);
+  static long long zeros[3 * 2048];
+  cudaMemcpyToSymbol(g_trace, zeros, sizeof(zeros));
+  return 3 * 1024;
+}
+#endif
 
 int launch_categorize_mma(const NetWeights &wts, const uint8_t *q8, b200_scan *scans, int n, bool raw, float *raw_out, cudaStream_t s) {
   static PerDeviceOnce once;
