@@ -368,7 +368,12 @@ hseg_kernel(const uint8_t *__restrict__ cards, int n, b200_scan *__restrict__ sc
   b200_scan *sc = scans + f;
   if (!sc->usable) return;  // upside_down / vseg gate (block-uniform)
 
-  __shared__ uint8_t s_strip[27][B200_CARD_W];
+  // the source strip is dead once the column sums exist, two barriers before the first pattern row is written: the two
+  // share storage (36 -> 25 KB per CTA: eight resident CTAs per SM instead of six for this barrier-bound kernel)
+  constexpr int kPatRow = kPatPad + B200_CARD_W + 4;
+  __shared__ __align__(16) uint8_t s_buf[kMaxWidths * kPatRow * 4 > 27 * B200_CARD_W ? kMaxWidths * kPatRow * 4 : 27 * B200_CARD_W];
+  uint8_t (*s_strip)[B200_CARD_W] = reinterpret_cast<uint8_t (*)[B200_CARD_W]>(s_buf);
+  float (*s_patw)[kPatRow] = reinterpret_cast<float (*)[kPatRow]>(s_buf);
   __shared__ float s_g[B200_CARD_W];
   __shared__ int s_isum[B200_CARD_W];
   __shared__ int s_mn, s_mx;
@@ -381,7 +386,6 @@ hseg_kernel(const uint8_t *__restrict__ cards, int n, b200_scan *__restrict__ sc
   // The pattern of a candidate (width w, offset o) is the pattern of (w, 0) shifted right by o (every digit centre is
   // o + lrintf(index * w)), so each pass builds ONE 428-float pattern row per width -- kPatPad zeros in front -- and a
   // candidate reads it at [i - o].
-  __shared__ float s_patw[kMaxWidths][kPatPad + B200_CARD_W + 4];
   __shared__ short s_last_center[kMaxWidths];           // centre of the last digit at offset 0: validity is o + centre + 19 < 428
 
   const int y_off = sc->vseg.y_offset;
