@@ -353,6 +353,39 @@ def test_vseg_rows_tensor_core_path(dmz, oracle):
     assert np.abs(fp32 - got).max() <= 1e-5
 
 
+def test_tensor_core_cnn_equals_fp32_cnn(dmz, oracle):
+    """The tcgen05 CNN path (categorize_mma.cu: exact integer conv + pool, split-fp16 hidden layer) against the FP32 FMA
+    kernel: loose patches at counts around the 32-slot group size (1, 31, 32, 33, 100), and whole frames in odd batch
+    sizes (1, 3, 7: the last group holds one frame) -- probabilities within the 1e-4 contract, arg-max digits equal."""
+    rng = np.random.default_rng(21)
+    _, cards = oracle.process_frames(deck_frames(8, 4), want_cards=True)
+    pool = np.concatenate([cards[k][150:177, x:x + 19][None] for k in range(4) for x in range(20, 380, 23)])
+    for n in (1, 31, 32, 33, 100):
+        patches = pool[rng.integers(0, len(pool), n)].copy()
+        patches[::3] = rng.integers(0, 256, patches[::3].shape)
+        ens, mods = dmz.categorize_patches(patches)
+        os.environ["B200_DMZ_CNN_FP32"] = "1"
+        try:
+            ens32, mods32 = dmz.categorize_patches(patches)
+        finally:
+            del os.environ["B200_DMZ_CNN_FP32"]
+        assert np.abs(ens - ens32).max() <= TOL and np.abs(mods - mods32).max() <= TOL, n
+        sure = np.sort(ens32, axis=1)[:, -1] - np.sort(ens32, axis=1)[:, -2] > 1e-3
+        assert np.array_equal(ens.argmax(1)[sure], ens32.argmax(1)[sure]), n
+    for n in (1, 3, 7):
+        frames = deck_frames(40, n)
+        got = dmz.process_frames(frames)
+        os.environ["B200_DMZ_CNN_FP32"] = "1"
+        try:
+            ref = dmz.process_frames(frames)
+        finally:
+            del os.environ["B200_DMZ_CNN_FP32"]
+        for k in ("usable", "h_n_offsets", "v_y_offset"):
+            assert np.array_equal(got[k], ref[k]), (n, k)
+        assert np.abs(got["scores"] - ref["scores"]).max() <= TOL, n
+        assert (got["scores"][got["usable"] == 0] == 0).all()
+
+
 def test_categorize_patches(dmz, oracle, golden):
     patches = golden["card0_patches"]
     ens, mods = dmz.categorize_patches(patches)
