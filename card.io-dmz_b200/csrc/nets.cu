@@ -356,9 +356,17 @@ digit_prep_kernel(const uint8_t *__restrict__ cards, const b200_scan *__restrict
     a = (int)(reinterpret_cast<uintptr_t>(src) & 3u);
     const unsigned int *wsrc = reinterpret_cast<const unsigned int *>(src - a);
     const int words = (a + 19 + 3) >> 2;
-    for (int i = lane; i < 27 * 6; i += 32) {
-      const int row = i / 6, q = i - row * 6;
-      if (q < words) reinterpret_cast<unsigned int *>(raw)[row * 6 + q] = __ldg(wsrc + row * (B200_CARD_W / 4) + q);
+    // all six loads of a lane are issued before the first store: one global-latency exposure per digit, not six
+    unsigned int wv[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      const int i = lane + 32 * k, row = i / 6, q = i - row * 6;
+      wv[k] = (i < 27 * 6 && q < words) ? __ldg(wsrc + row * (B200_CARD_W / 4) + q) : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      const int i = lane + 32 * k;
+      if (i < 27 * 6) reinterpret_cast<unsigned int *>(raw)[i] = wv[k];
     }
   }
   for (int i = lane; i < 256; i += 32) P.hist[i] = 0;
