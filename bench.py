@@ -399,8 +399,21 @@ def pipeline_config(args):
         avail = mem_available_bytes()
         budget = int(0.6 * avail / max(world, 1)) if avail else Fe * FRAME_BYTES
         Fe = max(1024, min(Fe, budget // FRAME_BYTES) // 1024 * 1024) if Fe >= 1024 else Fe
-        h_frames = torch.empty((Fe, H, W), dtype=torch.uint8).pin_memory()
-        h_frames.copy_(frames[:Fe])
+        wc_ptr = None
+        if os.environ.get("B200_BENCH_WC"):  # experiment: write-combined pinned upload buffer (cudaHostAllocWriteCombined)
+            import ctypes as C
+            rt = C.CDLL("libcudart.so")
+            wc_ptr = C.c_void_p()
+            assert rt.cudaHostAlloc(C.byref(wc_ptr), C.c_size_t(Fe * FRAME_BYTES), C.c_uint(4)) == 0
+            assert rt.cudaMemcpy(wc_ptr, C.c_void_p(frames.data_ptr()), C.c_size_t(Fe * FRAME_BYTES), C.c_int(2)) == 0
+
+            class _Wc:
+                def data_ptr(self):
+                    return wc_ptr.value
+            h_frames = _Wc()
+        else:
+            h_frames = torch.empty((Fe, H, W), dtype=torch.uint8).pin_memory()
+            h_frames.copy_(frames[:Fe])
         h_records = torch.zeros((Fe, RECORD_BYTES), dtype=torch.uint8).pin_memory()
         h_np = h_records.numpy().view(g.pkg.RECORD_DTYPE).reshape(Fe)
 
@@ -420,6 +433,8 @@ def pipeline_config(args):
         same = bool((h_records.cuda() == records[:Fe]).all().item())
         h2d1, d2h1 = dmz.transfer_bytes()
         del h_frames
+        if wc_ptr is not None:
+            rt.cudaFreeHost(wc_ptr)
         ceiling = host_h2d_ceiling(g)
         h2d_per_frame = (h2d1 - h2d0) / args.steps / Fe
         e2e_value = Fe * world * args.steps / e2e_s
