@@ -44,6 +44,7 @@ def build(force=False):
         ("nets.cu", []),
         ("vseg_mma.cu", []),
         ("categorize_mma.cu", []),
+        ("expiry_mma.cu", []),
         ("api.cu", ["-fmad=false"]),
         ("b200_tables.cpp", ["-Xcompiler", "-ffp-contract=off"]),
         ("scanner.cpp", ["-Xcompiler", "-ffp-contract=off"]),

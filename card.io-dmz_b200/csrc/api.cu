@@ -426,11 +426,21 @@ int b200_ctx_create(b200_ctx **out, int device_ordinal, const char *weights_dir)
       for (int f = 0; f < 40; f++)
         for (int k = 0; k < 50; k++)
           for (int t = 0; t < 25; t++) eb[B200_EXPIRY_C2K_OFFSET + ((size_t)k * 40 + f) * 28 + t] = eb[1300 + (size_t)f * 1250 + k * 25 + t];
+      {  // + the layer-2 kernels as fp16 hi / lo operand slices for the tensor-core kernel (expiry_mma.cu)
+        std::vector<uint16_t> halfs((size_t)13 * 2 * 14 * 48 * 8);
+        b200_build_expiry_c2_halfs(eb.data(), halfs.data());
+        eb.resize(B200_EXPIRY_C2H_OFFSET + B200_EXPIRY_C2H_FLOATS, 0.0f);
+        memcpy(eb.data() + B200_EXPIRY_C2H_OFFSET, halfs.data(), halfs.size() * sizeof(uint16_t));
+        eb.resize(B200_EXPIRY_HWT_OFFSET + 120 * 176, 0.0f);  // + the hidden weights [176][120] transposed to [120][176] (coalesced reads)
+        for (int i = 0; i < 176; i++)
+          for (int j = 0; j < 120; j++) eb[B200_EXPIRY_HWT_OFFSET + (size_t)j * 176 + i] = eb[51340 + (size_t)i * 120 + j];
+      }
       CU(cudaMalloc(&ctx->d_expiry, eb.size() * sizeof(float)));
       CU(cudaMemcpy(ctx->d_expiry, eb.data(), eb.size() * sizeof(float), cudaMemcpyHostToDevice));
       float color[256], space[5];
       b200_build_bilateral_tables(color, space);
-      if (upload_bilateral_tables(color, space) != 0) return fail(ctx, B200_ECUDA, "cudaMemcpyToSymbol (bilateral tables)");
+      if (upload_bilateral_tables(color, space) != 0 || upload_bilateral_tables_mma(color, space) != 0)
+        return fail(ctx, B200_ECUDA, "cudaMemcpyToSymbol (bilateral tables)");
     }
     if (read_blob(dir + "/modelm_730c4cbd.bin", &eb, 14322)) {
       CU(cudaMalloc(&ctx->d_slash, eb.size() * sizeof(float)));

@@ -157,6 +157,9 @@ int launch_finalize_records(const FrameGeom *geom, const b200_scan *scans, const
                             b200_frame_record *recs, cudaStream_t s, uint8_t *needs_full = nullptr, int cx0 = 0, int cy0 = 0,
                             int cx1 = 0, int cy1 = 0);
 #define B200_EXPIRY_C2K_OFFSET 74408  // floats: modelc_bf4dd6c8 blob (74406) rounded up to a 16-byte boundary
+#define B200_EXPIRY_C2H_OFFSET (B200_EXPIRY_C2K_OFFSET + 50 * 40 * 28)  // floats: start of the fp16 layer-2 weight slices (expiry_mma.cu)
+#define B200_EXPIRY_C2H_FLOATS (13 * 2 * 14 * 48 * 8 / 2)                // 139 776 halfs
+#define B200_EXPIRY_HWT_OFFSET (B200_EXPIRY_C2H_OFFSET + B200_EXPIRY_C2H_FLOATS)  // floats: hidden weights transposed [120][176]
 #define B200_Q8_STRIDE 528  // bytes per prepared digit patch (27 x 19 = 513 padded to 33 x 16)
 int launch_categorize_patches(const NetWeights &wts, const uint8_t *patches, const float *float_patches, int n, float *out,
                               uint8_t *q8 /* n * B200_Q8_STRIDE bytes of scratch when `patches` is given */, cudaStream_t s);
@@ -173,6 +176,9 @@ int launch_frame_scores(const uint8_t *frames, int row_stride, size_t frame_stri
 void b200_scoring_rect(int w, int h, int use_full_image, int rect[4]);  // b200_tables.cpp
 int launch_expiry_digits(const float *weights, const uint8_t *patches, const float *prepared, int n, float *out, cudaStream_t s,
                          const int32_t *where = nullptr);
+void b200_build_expiry_c2_halfs(const float *blob /* modelc_bf4dd6c8 */, uint16_t *out /* 13 * 2 * 14 * 48 * 8 */);  // b200_tables.cpp
+int launch_expiry_digits_mma(const float *weights, const uint8_t *patches, int n, float *out, cudaStream_t s, const int32_t *where);  // expiry_mma.cu
+int upload_bilateral_tables_mma(const float *color256, const float *space5);
 void b200_build_minmax_norm_table(float *table /* 256 * 256 * 2 */);  // b200_tables.cpp
 void b200_build_bilateral_tables(float *color256, float *space5);  // b200_tables.cpp  // __constant__ conv kernels / biases (nets.cu)
 

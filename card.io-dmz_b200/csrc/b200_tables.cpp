@@ -325,6 +325,29 @@ void b200_build_cnn_mma_tables(const float *const blobs[3], int8_t *convb, float
   }
 }
 
+// Layer-2 weights of the expiry CNN as fp16 operand slices (expiry_mma.cu): slice s = taps 2s, 2s + 1 (tap = i * 5 + j),
+// part hi / lo, 14 chunks (tap slot * 7 + k) of 48 rows (output map f; rows 40 .. 47 zero) x 8 halfs (input map 8k + e).
+// Blob: conv2 kernels at 1300 + f * 1250 + map * 25 + tap.
+void b200_build_expiry_c2_halfs(const float *blob, uint16_t *out) {
+  memset(out, 0, (size_t)13 * 2 * 14 * 48 * 8 * sizeof(uint16_t));
+  for (int s = 0; s < 13; s++)
+    for (int ts = 0; ts < 2; ts++) {
+      const int tap = 2 * s + ts;
+      if (tap >= 25) continue;
+      for (int k = 0; k < 7; k++)
+        for (int f = 0; f < 40; f++)
+          for (int e = 0; e < 8; e++) {
+            const int m = 8 * k + e;
+            if (m >= 50) continue;
+            const float w = blob[1300 + (size_t)f * 1250 + m * 25 + tap];
+            const uint16_t hi = half_bits_rn(w), lo = half_bits_rn(w - half_bits_to_float(hi));
+            const size_t at = (((size_t)(ts * 7 + k)) * 48 + f) * 8 + e;
+            out[((size_t)s * 2 + 0) * (14 * 48 * 8) + at] = hi;
+            out[((size_t)s * 2 + 1) * (14 * 48 * 8) + at] = lo;
+          }
+    }
+}
+
 void b200_build_bilateral_tables(float *color256, float *space5) {
   const int aperture = 3;
   const double sigma_color = (aperture / 2.0 - 1) * 0.3 + 0.8;  // the reference's "space_sigma"

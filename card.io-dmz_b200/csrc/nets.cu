@@ -925,6 +925,10 @@ int upload_bilateral_tables(const float *color256, const float *space5) {
 
 int launch_expiry_digits(const float *weights, const uint8_t *patches, const float *prepared, int n, float *out, cudaStream_t s,
                          const int32_t *where) {
+  // byte crops go through the tensor-core kernel (expiry_mma.cu); prepared float inputs (the per-layer KAT tap) and
+  // B200_DMZ_EXPIRY_FP32=1 (A / B measurements) through the FP32 kernel of this file
+  const char *fp32_env = getenv("B200_DMZ_EXPIRY_FP32");
+  if (prepared == nullptr && !(fp32_env && *fp32_env && atoi(fp32_env) != 0)) return launch_expiry_digits_mma(weights, patches, n, out, s, where);
   static PerDeviceOnce once;
   if (!once.ensure([] { return ensure_smem(expiry_kernel, sizeof(ExpirySmem)); })) return -1;
   int grid = num_sms();
