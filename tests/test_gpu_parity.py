@@ -467,6 +467,25 @@ def test_expiry_digit_known_answer_and_parity(dmz, oracle, golden):
     assert got.argmax(1).tolist() == [int(oracle.expiry_digit_model(prepared[i]).argmax()) for i in range(37)]
 
 
+def test_tensor_core_expiry_cnn_equals_fp32(dmz):
+    """E0 with layer 2 on the tensor cores (expiry_mma.cu, split-fp16 operands) against the FP32 kernel: crop counts around the
+    seven-crop batch (1, 6, 7, 8, 50: the last batch is partial), noise and flat crops; probabilities within 1e-4."""
+    rng = np.random.default_rng(5)
+    for n in (1, 6, 7, 8, 50):
+        crops = rng.integers(0, 256, (n, 16, 11)).astype(np.uint8)
+        crops[::4] = (rng.integers(0, 2, (len(crops[::4]), 16, 11)) * 180 + 40).astype(np.uint8)
+        if n > 2:
+            crops[2] = 99
+        got = dmz.expiry_digits(crops)
+        os.environ["B200_DMZ_EXPIRY_FP32"] = "1"
+        try:
+            ref = dmz.expiry_digits(crops)
+        finally:
+            del os.environ["B200_DMZ_EXPIRY_FP32"]
+        assert np.abs(got - ref).max() <= TOL, (n, float(np.abs(got - ref).max()))
+        assert np.abs(got.sum(1) - 1).max() < 1e-5
+
+
 def test_best_expiry_seg(dmz, golden):
     """best_expiry_seg on synthetic expiry cards -- groups identical to the golden outputs of the
     reference's SCAN_EXPIRY=1 build (and to that build itself when oracle/_ref travelled here); the |Scharr| plane
