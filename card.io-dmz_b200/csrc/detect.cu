@@ -218,6 +218,14 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
   // ---- 2. Sobel-7 dx, dy; accumulate the saturated |.| sums on the fly
   unsigned long long abs_sum = 0;
   {
+    // the four dp4a tap words live in per-thread registers for the whole pass: as uniform values the compiler would
+    // re-materialise them (UMOV) for every output pixel
+    unsigned int kd0, kd1, ks0, ks1;
+    asm volatile("mov.u32 %0, 0x00FBFCFF;" : "=r"(kd0));  // -1 -4 -5  0
+    asm volatile("mov.u32 %0, 0x00010405;" : "=r"(kd1));  //  5  4  1  .
+    asm volatile("mov.u32 %0, 0x140F0601;" : "=r"(ks0));  //  1  6 15 20
+    asm volatile("mov.u32 %0, 0x0001060F;" : "=r"(ks1));  // 15  6  1  .
+    unsigned int sat_any = 0;
     const int items = w * S.nchunks;
     for (int it = tid; it < items; it += kThreads) {
       unsigned int col_sum = 0;  // <= chunk_rows * 65534: 32 bits hold any strip a frame can have
@@ -232,41 +240,45 @@ detect_strips_kernel(const __grid_constant__ DetectParams P, const uint8_t *__re
         const unsigned int w0 = r32[0], w1 = r32[1], w2 = r32[2];
         const unsigned int lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);  // p0..p3, p4..p7
         int a, b;
-        asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(a) : "r"(lo), "r"(0x00FBFCFF), "r"(0));   // -1 -4 -5  0
-        asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(a) : "r"(hi), "r"(0x00010405), "r"(a));   //  5  4  1  .
-        asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(b) : "r"(lo), "r"(0x140F0601), "r"(0));   //  1  6 15 20
-        asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(b) : "r"(hi), "r"(0x0001060F), "r"(b));   // 15  6  1  .
+        asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(a) : "r"(lo), "r"(kd0), "r"(0));
+        asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(a) : "r"(hi), "r"(kd1), "r"(a));
+        asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(b) : "r"(lo), "r"(ks0), "r"(0));
+        asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(b) : "r"(hi), "r"(ks1), "r"(b));
         hxo = a, sxo = b;
       };
 #pragma unroll
       for (int k = 0; k < 6; k++) row_filter(clampi(y0 + k - 3, 0, h - 1), hx[k], sx[k]);  // rows y0-3 .. y0+2
       int o = (y0 + 1) * wp + x + 1;
-      for (int y = y0; y < y1; y += 7) {
-        // seven output rows per trip: the ring slot of every tap is a compile-time constant, no register shuffling
+      // one output row; ring slot k of every tap is a compile-time constant, no register shuffling
+      auto out_row = [&](int y, int k) {
+        row_filter(min(y + 3, h - 1), hx[(k + 6) % 7], sx[(k + 6) % 7]);
+        int gx = (hx[k % 7] + hx[(k + 6) % 7]) + 6 * (hx[(k + 1) % 7] + hx[(k + 5) % 7]) +
+                 15 * (hx[(k + 2) % 7] + hx[(k + 4) % 7]) + 20 * hx[(k + 3) % 7];        // smooth down the column
+        int gy = (sx[(k + 6) % 7] - sx[k % 7]) + 4 * (sx[(k + 5) % 7] - sx[(k + 1) % 7]) +
+                 5 * (sx[(k + 4) % 7] - sx[(k + 2) % 7]);                                  // derivative down the column
+        gx = clampi(gx, -32768, 32767);  // saturate_cast<short>
+        gy = clampi(gy, -32768, 32767);
+        // what the NMS reads (canny.cpp:222-236): the magnitude, dx, and two flag bits from which dy follows
+        const unsigned int ax = (unsigned)abs(gx), ay = (unsigned)abs(gy);
+        const unsigned int m = ax + ay;      // <= 65536
+        const unsigned int hi16 = m >> 16;   // 1 only for dx == dy == -32768
+        L.md[o] = (m - hi16) | ((unsigned)gx << 16);  // 65536 -> 65535 + flag bit
+        L.map[o] = (uint8_t)(1u | (((unsigned)gy >> 31) << 4) | (hi16 << 5));
+        sat_any |= hi16;  // (block-wide flag below: step 2 then rebuilds the 17-bit magnitudes)
+        col_sum += min(ax, 32767u) + min(ay, 32767u);  // cvAbs saturates, canny.cpp:355-361
+        o += wp;
+      };
+      int y = y0;
+      for (; y + 7 <= y1; y += 7) {  // seven output rows per trip, no per-row bound test
 #pragma unroll
-        for (int k = 0; k < 7; k++) {
-          if (y + k < y1) {
-            row_filter(min(y + k + 3, h - 1), hx[(k + 6) % 7], sx[(k + 6) % 7]);
-            int gx = (hx[k % 7] + hx[(k + 6) % 7]) + 6 * (hx[(k + 1) % 7] + hx[(k + 5) % 7]) +
-                     15 * (hx[(k + 2) % 7] + hx[(k + 4) % 7]) + 20 * hx[(k + 3) % 7];        // smooth down the column
-            int gy = (sx[(k + 6) % 7] - sx[k % 7]) + 4 * (sx[(k + 5) % 7] - sx[(k + 1) % 7]) +
-                     5 * (sx[(k + 4) % 7] - sx[(k + 2) % 7]);                                  // derivative down the column
-            gx = clampi(gx, -32768, 32767);  // saturate_cast<short>
-            gy = clampi(gy, -32768, 32767);
-            // what the NMS reads (canny.cpp:222-236): the magnitude, dx, and two flag bits from which dy follows
-            const unsigned int ax = (unsigned)abs(gx), ay = (unsigned)abs(gy);
-            const unsigned int m = ax + ay;      // <= 65536
-            const unsigned int hi16 = m >> 16;   // 1 only for dx == dy == -32768
-            L.md[o] = (m - hi16) | ((unsigned)gx << 16);  // 65536 -> 65535 + flag bit
-            L.map[o] = (uint8_t)(1u | (((unsigned)gy >> 31) << 4) | (hi16 << 5));
-            if (hi16) s_sat = 1;  // (block-wide flag: step 2 then rebuilds the 17-bit magnitudes)
-            col_sum += min(ax, 32767u) + min(ay, 32767u);  // cvAbs saturates, canny.cpp:355-361
-            o += wp;
-          }
-        }
+        for (int k = 0; k < 7; k++) out_row(y + k, k);
       }
+#pragma unroll
+      for (int k = 0; k < 6; k++)  // the last y1 - y < 7 rows
+        if (y + k < y1) out_row(y + k, k);
       abs_sum += col_sum;
     }
+    if (sat_any) s_sat = 1;
   }
   // ---- 3. adaptive thresholds: low = floor(mean), high = floor(3 * mean), canny.cpp:568-580
   abs_sum = warp_sum_u64(abs_sum);
