@@ -218,7 +218,16 @@ vseg_mma_kernel(const int8_t *__restrict__ wq, const VsegUnit *__restrict__ unit
         const float T = fmaf(fmaf(fmaf((float)(int)q0, 128.0f, (float)(int)q1), 128.0f, (float)(int)q2), 128.0f, (float)(int)q3);
         const float4 ua = *reinterpret_cast<const float4 *>(&S.unit[u].cu);
         const float2 ub = *reinterpret_cast<const float2 *>(&S.unit[u].w21);
-        const float hv = tanhf(fmaf(T, ua.x * s_row, fmaf(d0_row, ua.y, ua.z)));  // feeds an arg-max index: accurate tanh
+        const float zin = fmaf(T, ua.x * s_row, fmaf(d0_row, ua.y, ua.z));
+#ifndef B200_VSEG_TANH_SFU
+        const float hv = tanhf(zin);  // feeds an arg-max index: accurate tanh (the SFU form below measured 3.07 against 3.15 ms: not worth it)
+#else
+        // tanh on the special-function unit: 1 - 2 / (e^(2|z|) + 1) with the sign copied back; absolute error <= ~1.5e-7
+        // everywhere (ex2.approx is 2^-22 relative, the quotient is <= 1), the size of tanhf's own 1 - 2 ulp near +-1.  The
+        // row probabilities feed an arg-max: index-identical to the FP32 kernel (which uses tanhf) on the 100 000-frame deck
+        // (test_tensor_core_vseg_equals_fp32_vseg) and <= 1e-5 from the oracle row by row.
+        const float hv = copysignf(1.0f - __fdividef(2.0f, __expf(2.0f * fabsf(zin)) + 1.0f), zin);
+#endif
         z0 = fmaf(ua.w, hv, z0), z1 = fmaf(ub.x, hv, z1), z2 = fmaf(ub.y, hv, z2);
       };
 #pragma unroll 1
