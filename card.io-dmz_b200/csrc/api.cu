@@ -949,7 +949,7 @@ int b200_best_expiry_seg_batch(b200_ctx *ctx, const uint8_t *cards, const uint16
   const int chunk = n < max_chunk ? n : max_chunk;
   const bool host = mem == B200_MEM_HOST;
   auto up16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
-  const size_t o_sob = 0, o_ls = o_sob + up16(sob_bytes * chunk), o_cards = o_ls + up16(sizeof(int32_t) * B200_CARD_H * chunk),
+  const size_t o_sob = 0, o_ls = o_sob + up16(sob_bytes * chunk), o_cards = o_ls + up16(sizeof(int32_t) * B200_EXPIRY_SEG_SCRATCH_INTS * chunk),
                o_yo = o_cards + up16(host ? card_bytes * chunk : 0), o_grp = o_yo + up16(host ? sizeof(uint16_t) * chunk : 0),
                o_cnt = o_grp + up16(host ? sizeof(b200_expiry_group) * (size_t)max_groups * chunk : 0),
                total = o_cnt + up16(host ? 2 * sizeof(int32_t) * chunk : 0);

@@ -167,6 +167,7 @@ int launch_vseg_model(const NetWeights &wts, const float *rows, int n, float *ou
 int launch_vseg_coarse_rows(const NetWeights &wts, const uint8_t *cards, int n, float *vprob /* n * 540, zeroed here */, cudaStream_t s);
 void fill_conv_constants(const float *cnn_blobs[3], ConvConsts *out);  // host side (nets.cu)
 int upload_bilateral_tables(const float *color256, const float *space5);  // E0 prep constants (nets.cu)
+#define B200_EXPIRY_SEG_SCRATCH_INTS 1584  // per card: 270 row sums, the picked stripes, 3 x 428 column sums (expiry_seg.cu)
 int launch_expiry_seg(const uint8_t *cards, const uint16_t *y_offsets, int n, const float *slash_w, int16_t *sob, int32_t *line_sum,
                       b200_expiry_group *groups, int max_groups, int32_t *n_groups, int32_t *n_dropped, cudaStream_t s);  // expiry_seg.cu
 int launch_deinterleave_c2(const uint8_t *src, int row_stride, size_t frame_stride, int w, int h, int n, uint8_t *ch1, uint8_t *ch2,

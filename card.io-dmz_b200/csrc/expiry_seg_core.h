@@ -343,9 +343,11 @@ XHDN void optimize_rects(const int16_t *sob, Group &g, CharRect *pool) {
 }
 
 // find_character_groups_for_stripe (expiry_seg.cpp:379-703).  Appends accepted groups to out[*n_out ...].
+// colsum (optional): the 428 column sums of rows base_row .. base_row + exp_h - 1 (stripe_colsums below; the CUDA path
+// computes them with one warp per stripe) -- the sliding rectangle sums then cost two loads per column instead of 2 exp_h.
 XHDN void stripe_groups(const int16_t *sob, const float *slash_w, int base_row, int stripe_sum, ExpiryGroupOut *out,
-                        int *n_out, int max_out, int *overflow) {
-  const int exp_top = base_row - 1, exp_h = imin(kSmallH + 2, kH - exp_top);
+                        int *n_out, int max_out, int *overflow, const int32_t *colsum = nullptr) {
+  const int exp_top = base_row - 1, exp_h = imin(kSmallH + 2, kH - exp_top);  // == stripe_rows(base_row)
   const long long rect_average = ((long long)stripe_sum * kSmallW) / kW;
   const float too_dim = (float)(rect_average / 5);
   // [1] sliding 9-wide rectangle sums.  NB the reference sums rows base_row .. base_row + exp_h - 1 here (not the
@@ -354,16 +356,25 @@ XHDN void stripe_groups(const int16_t *sob, const float *slash_w, int base_row, 
   int n_cand = 0;
   float total = 0.0f;
   int rs = 0;
-  for (int c = 0; c < kSmallW; c++)
-    for (int r = 0; r < exp_h; r++) rs += sob[(base_row + r) * kW + c];
+  if (colsum != nullptr) {
+    for (int c = 0; c < kSmallW; c++) rs += colsum[c];
+  } else {
+    for (int c = 0; c < kSmallW; c++)
+      for (int r = 0; r < exp_h; r++) rs += sob[(base_row + r) * kW + c];
+  }
   for (int c = 0; c < kW - kSmallW + 1; c++) {
     if ((float)rs > too_dim) {
       cand[n_cand].top = exp_top, cand[n_cand].left = c, cand[n_cand].sum = rs;
       n_cand++;
       total += (float)rs;
     }
-    if (c < kW - kSmallW)
-      for (int r = 0; r < exp_h; r++) rs += sob[(base_row + r) * kW + c + kSmallW] - sob[(base_row + r) * kW + c];
+    if (c < kW - kSmallW) {
+      if (colsum != nullptr) {
+        rs += colsum[c + kSmallW] - colsum[c];  // (integer sums: the same value in any order)
+      } else {
+        for (int r = 0; r < exp_h; r++) rs += sob[(base_row + r) * kW + c + kSmallW] - sob[(base_row + r) * kW + c];
+      }
+    }
   }
   if (n_cand == 0) return;
   const float average = total / (float)n_cand;
@@ -439,10 +450,9 @@ XHDN void stripe_groups(const int16_t *sob, const float *slash_w, int base_row, 
   }
 }
 
-// best_expiry_seg's stripe selection + per-stripe search (expiry_seg.cpp:744-903).  line_sum[r] = sum of
-// sob[r][27 .. 284] for r >= y_offset + 27 (rows above are never read).  Returns the number of groups written.
-XHDN int best_expiry_groups(const int16_t *sob, const int32_t *line_sum, int y_offset, const float *slash_w, ExpiryGroupOut *out,
-                            int max_out, int *overflow) {
+// best_expiry_seg's stripe selection (expiry_seg.cpp:744-857).  line_sum[r] = sum of sob[r][27 .. 284] for
+// r >= y_offset + 27 (rows above are never read).  Returns the number of stripes picked (<= kMaxStripes).
+XHDN int pick_stripes(const int32_t *line_sum, int y_offset, StripeSum *picked) {
   const int first_base = y_offset + kNumberHeight + 1, last_base = kH - (kSmallH + 1);
   StripeSum stripes[kH];
   int n_stripes = 0;
@@ -464,7 +474,6 @@ XHDN int best_expiry_groups(const int16_t *sob, const int32_t *line_sum, int y_o
     if (good) stripes[n_stripes].base_row = base, stripes[n_stripes].sum = sum, n_stripes++;
   }
   std_sort_emul(stripes, stripes + n_stripes, SumDesc());
-  StripeSum picked[kMaxStripes];
   int n_picked = 0;
   for (int i = 0; i < n_stripes && n_picked < kMaxStripes; i++) {
     bool overlap = false;
@@ -472,10 +481,43 @@ XHDN int best_expiry_groups(const int16_t *sob, const int32_t *line_sum, int y_o
       if (picked[p].base_row - kSmallH < stripes[i].base_row && stripes[i].base_row < picked[p].base_row + kSmallH) overlap = true;
     if (!overlap) picked[n_picked++] = stripes[i];
   }
+  return n_picked;
+}
+
+// rows a stripe's rectangle sums cover: base_row .. base_row + stripe_rows(base_row) - 1 (find_character_groups_for_stripe's
+// expanded height, expiry_seg.cpp:403-405)
+XHD int stripe_rows(int base_row) { return imin(kSmallH + 2, kH - (base_row - 1)); }
+
+// the 428 column sums of a stripe (host form; the CUDA path computes them with one warp per stripe)
+XHDN void stripe_colsums(const int16_t *sob, int base_row, int32_t *colsum) {
+  const int rows = stripe_rows(base_row);
+  for (int c = 0; c < kW; c++) {
+    int s = 0;
+    for (int r = 0; r < rows; r++) s += sob[(base_row + r) * kW + c];
+    colsum[c] = s;
+  }
+}
+
+// best_expiry_seg's per-stripe search over the picked stripes (expiry_seg.cpp:858-903).  colsums (optional):
+// kMaxStripes x kW column sums, one row per picked stripe.  Returns the number of groups written.
+XHDN int search_stripes(const int16_t *sob, const StripeSum *picked, int n_picked, const float *slash_w, ExpiryGroupOut *out, int max_out,
+                        int *overflow, const int32_t *colsums = nullptr) {
   int n_out = 0;
   *overflow = 0;
-  for (int p = 0; p < n_picked; p++) stripe_groups(sob, slash_w, picked[p].base_row, picked[p].sum, out, &n_out, max_out, overflow);
+  for (int p = 0; p < n_picked; p++)
+    stripe_groups(sob, slash_w, picked[p].base_row, picked[p].sum, out, &n_out, max_out, overflow, colsums ? colsums + p * kW : nullptr);
   return n_out;
+}
+
+// stripe selection + per-stripe search in one call (the CPU unit tests; use_colsums exercises the column-sum form the
+// CUDA path takes)
+XHDN int best_expiry_groups(const int16_t *sob, const int32_t *line_sum, int y_offset, const float *slash_w, ExpiryGroupOut *out,
+                            int max_out, int *overflow, int32_t *colsum_scratch = nullptr /* kMaxStripes * kW, or null */) {
+  StripeSum picked[kMaxStripes];
+  const int n_picked = pick_stripes(line_sum, y_offset, picked);
+  if (colsum_scratch != nullptr)
+    for (int p = 0; p < n_picked; p++) stripe_colsums(sob, picked[p].base_row, colsum_scratch + p * kW);
+  return search_stripes(sob, picked, n_picked, slash_w, out, max_out, overflow, colsum_scratch);
 }
 
 // llcv_scharr3_dx_abs on the rows below the number (cv/sobel.cpp:706-799) for ONE output pixel: |right - left| per

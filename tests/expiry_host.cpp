@@ -22,7 +22,14 @@ int xh_best_expiry_seg(const uint8_t *card, int y_offset, const float *slash_w, 
     }
     line_sum[y] = s;
   }
-  return xseg::best_expiry_groups(sob.data(), line_sum.data(), y_offset, slash_w, out, max_out, overflow);
+  // the column-sum form of the search (what the CUDA path takes) and the direct form must agree on every card
+  std::vector<int32_t> colsums((size_t)xseg::kMaxStripes * xseg::kW);
+  std::vector<xseg::ExpiryGroupOut> direct((size_t)max_out);
+  int overflow_direct = 0;
+  const int n_direct = xseg::best_expiry_groups(sob.data(), line_sum.data(), y_offset, slash_w, direct.data(), max_out, &overflow_direct);
+  const int n = xseg::best_expiry_groups(sob.data(), line_sum.data(), y_offset, slash_w, out, max_out, overflow, colsums.data());
+  if (n != n_direct || *overflow != overflow_direct || memcmp(direct.data(), out, sizeof(xseg::ExpiryGroupOut) * (size_t)(n < max_out ? n : max_out)) != 0) return -1000;
+  return n;
 }
 
 void xh_scharr(const uint8_t *card, int y_offset, int16_t *out) {
