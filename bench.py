@@ -543,7 +543,17 @@ def pipeline_config(args):
                 traffic = {"bytes_per_launch": tj["per_frame"][dom] * F, "bytes_per_frame": tj["per_frame"][dom], "source": tj["source"]}
             except Exception:
                 pass
-            roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            issue = None
+            try:
+                wi = tj["warp_instructions_per_frame"][dom]
+                rate = wi * stage_frames / (stage_ms[dom] * 1e-3)
+                issue_peak = g.sm_count * 4 * sm_mhz * 1e6  # one warp instruction per scheduler per cycle
+                issue = {"warp_instructions_per_frame": wi, "achieved_per_s": rate, "peak_per_s": issue_peak, "frac": rate / issue_peak,
+                         "what": "the limiter of this kernel: warp instructions (ncu smsp__inst_executed.sum of the same build, "
+                                 "profiles/traffic.json) / the kernel's CUDA-event time, against SMs x 4 schedulers x clock"}
+            except Exception:
+                pass
+            roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "issue_slots": issue,
                     "traffic": traffic, "peak_source": peak_src, "alg_bytes_per_frame": alg[dom],
                     "share_of_step": stage_ms[dom] / total_ms,
                     "pipeline": {"alg_bytes_per_frame": ALG_BYTES["pipeline_fused"], "achieved": fused, "frac": fused / peak,

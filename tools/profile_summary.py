@@ -90,6 +90,7 @@ def full_summary(tag, frames):
     md = ["# ncu --set full capture (%s), %d frames per launch, B200, --clock-control none" % (tag, frames), "",
           "Command: see tools/gpu_final.sh.  Per-launch values (cold cache, serialised: compare shares, not absolutes).", ""]
     traffic = {}
+    insts = {}
     seen = set()
     for r in rows[2:]:
         d = dict(zip(head, r))
@@ -104,8 +105,11 @@ def full_summary(tag, frames):
             wr = float(d["dram__bytes_write.sum"]) * scale[units[head.index("dram__bytes_write.sum")]]
             per_frame = (rd + wr) / frames
             md.append("- derived: DRAM traffic per frame = %.1f KB" % (per_frame / 1e3))
+            ipf = float(d.get("smsp__inst_executed.sum", 0) or 0) / frames
             for key, stage in STAGE_OF.items():
                 if key in name:
+                    if stage in SUMMED or stage not in seen:
+                        insts[stage] = insts.get(stage, 0) + int(ipf)
                     if stage in SUMMED:  # several launches per step add up
                         traffic[stage] = traffic.get(stage, 0) + int(per_frame)
                     elif stage not in seen:
@@ -116,7 +120,8 @@ def full_summary(tag, frames):
         md.append("")
     open(os.path.join(PROF, tag + "_ncu_full_summary.md"), "w").write("\n".join(md))
     json.dump({"source": "ncu --set full --clock-control none, %d frames per launch (profiles/%s_ncu_full_summary.md)" % (frames, tag),
-               "unit": "DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per frame", "per_frame": traffic},
+               "unit": "DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per frame", "per_frame": traffic,
+               "warp_instructions_per_frame": insts},
               open(os.path.join(PROF, "traffic.json"), "w"), indent=1)
     return traffic
 
