@@ -218,6 +218,21 @@ def reference_arm(args, rank, world):
         metric, unit, units = "digit patches/sec through n_categorize (3-CNN ensemble)", "patches/s", sample
         workload = "n_categorize only: 10M synthetic digit patches (bounded CPU sample)"
         desc = "%d patches per step on %d threads (%s)" % (sample, cores, kind_desc)
+    elif args.config == "formats":
+        from concurrent.futures import ThreadPoolExecutor
+        sample = 32 * cores
+        rng = np.random.default_rng(3)
+        planes = rng.integers(0, 256, (3, sample, H, W), dtype=np.uint8)
+        pool = ThreadPoolExecutor(cores)  # the reference function is single-threaded: one frame per call, ctypes drops the GIL
+
+        def run():
+            t0 = time.perf_counter()
+            list(pool.map(lambda k: orc.ycbcr_to_rgb(planes[0, k], planes[1, k], planes[2, k], 3), range(sample)))
+            return time.perf_counter() - t0
+        warm = run
+        metric, unit, units = "pixels/sec through dmz_YCbCr_to_RGB (640x480 planes -> interleaved RGB)", "pixels/s", sample * W * H
+        workload = "pixel formats around the path: dmz_YCbCr_to_RGB on 640x480 planes (bounded CPU sample)"
+        desc = "%d frames per step, one frame per call on %d threads (%s)" % (sample, cores, kind_desc)
     else:
         per = {"480p": 4096, "720p": 2048, "1080p": 1024}
         decks = {k: deck_frames(0, per[k], w, h, JITTER, DECK_SEED, threads=min(cores, 64)) for k, (w, h) in DETECT_SIZES.items()}
@@ -647,13 +662,15 @@ def categorize_config(args):
                          {"patches_per_gpu_per_step": n, "mix": "half i.i.d. U{0..255}, half 19x27 digit crops from the deck",
                           "l2": "inputs (%.1f GB per step) are larger than L2; no flush needed" % (n * 513 / 1e9)})
         line.update({"e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-                     "roofline": {"bound": "fp32", "kernel": "digit_prep_kernel + categorize_kernel", "achieved": tf, "peak": fp32_peak, "unit": "TFLOP/s",
+                     "roofline": {"bound": "fp32", "kernel": "digit_prep_kernel + categorize_mma_kernel", "achieved": tf, "peak": fp32_peak, "unit": "TFLOP/s",
                                   "frac": tf / fp32_peak, "traffic": None,
                                   "peak_source": "FP32 CUDA-core peak = %d SMs x 128 lanes x 2 x %.0f MHz (clock sampled during the run)" % (g.sm_count, sm_mhz),
                                   "flop_per_patch": CNN_FLOP_PER_PATCH,
                                   "hbm": {"alg_bytes_per_patch": 553, "achieved_GBps": gbps, "peak_GBps": peak, "frac": gbps / peak, "peak_source": peak_src},
-                                  "note": "218 880 flop per 553 B: ~400 flop/B, far right of the FP32 ridge; tensor cores are not used (K = 9 / 320 / 32 contractions, "
-                                          "1e-4 contract needs FP32-equivalent accuracy)"},
+                                  "note": "218 880 flop per 553 B: ~400 flop/B, far right of the FP32 ridge.  The figure is the reference's FP32 flop count over the "
+                                          "CUDA-core FP32 peak (what SURVEY 8d asks for); since round 2 the conv and hidden contractions run on the tensor cores "
+                                          "(tcgen05 kind::i8 on exact base-128 weight digits, split-fp16 hidden layer; categorize_mma.cu), which is how the "
+                                          "fraction can pass what FFMA alone would reach"},
                      "cpu_baseline": cpu, "wall_s_timed_region": wall})
         print(json.dumps(line), flush=True)
     g.finish()
@@ -743,18 +760,106 @@ def detect_sweep_config(args):
     g.finish()
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# pixel formats either side of the path (widening rows): dmz_YCbCr_to_RGB, dmz_deinterleave_RGBA_to_R, Cython stencils
+# ---------------------------------------------------------------------------------------------------------------------
+def formats_config(args):
+    g = Gpu(args)
+    torch, dmz, rank, world = g.torch, g.dmz, g.rank, g.world
+    lib, ctx, MEM_DEVICE = dmz.lib, dmz.ctx, g.pkg.MEM_DEVICE
+    n = args.format_frames
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(11 + rank)
+    planes = torch.randint(0, 256, (3, n, H, W), dtype=torch.uint8, device="cuda", generator=gen)
+    rgb = torch.empty((n, H, W, 4), dtype=torch.uint8, device="cuda")  # also the RGBA source of the R extraction
+    st = torch.empty((n, H, W), dtype=torch.int16, device="cuda")
+    nc = n * 2  # warped cards: 428 wide, so only 4-pixel vectors apply
+    cplanes = torch.randint(0, 256, (3, nc, 270, 428), dtype=torch.uint8, device="cuda", generator=gen)
+    crgb = torch.empty((nc, 270, 428, 3), dtype=torch.uint8, device="cuda")
+    px, cpx = n * W * H, nc * 428 * 270
+
+    def ycc(ch):
+        return lambda: dmz._check(lib.b200_ycbcr_to_rgb_batch(ctx, planes[0].data_ptr(), W, W * H, planes[1].data_ptr(), planes[2].data_ptr(), W, W * H,
+                                                              W, H, n, ch, MEM_DEVICE, rgb.data_ptr()))
+
+    legs = {  # name -> (call, algorithmic bytes per launch, pixels)
+        "ycbcr_to_rgb_640x480": (ycc(3), px * 6, px),
+        "ycbcr_to_rgba_640x480": (ycc(4), px * 7, px),
+        "ycbcr_to_rgb_card_428x270": (lambda: dmz._check(lib.b200_ycbcr_to_rgb_batch(ctx, cplanes[0].data_ptr(), 428, 428 * 270, cplanes[1].data_ptr(),
+                                                                                    cplanes[2].data_ptr(), 428, 428 * 270, 428, 270, nc, 3, MEM_DEVICE,
+                                                                                    crgb.data_ptr())), cpx * 6, cpx),
+        "rgba_to_r": (lambda: dmz._check(lib.b200_rgba_to_r_batch(ctx, rgb.data_ptr(), px, MEM_DEVICE, st.data_ptr())), px * 5, px),
+    }
+    for kind, name in enumerate(("scharr3_dx_abs", "scharr3_dy_abs", "sobel3_dx_dy")):
+        legs[name + "_640x480"] = ((lambda k: lambda: dmz._check(lib.b200_stencil3_batch(ctx, planes[0].data_ptr(), W, W * H, W, H, n, k, MEM_DEVICE,
+                                                                                         st.data_ptr())))(kind), px * 3, px)
+    peak, peak_src = measured_peaks()
+    results, clocks, launches, wall_total = {}, None, 0, 0.0
+    for name, (call, nbytes, pixels) in legs.items():
+        l0 = dmz.launches
+        t_ms, ck, wall = g.timed(call, args.steps, args.warmup)
+        launches += (dmz.launches - l0) * args.steps // max(args.steps + args.warmup, 1)
+        wall_total += wall
+        gbps = nbytes * args.steps / (t_ms * 1e-3) / 1e9
+        results[name] = {"ms_per_launch": t_ms / args.steps, "pixels/s": pixels * world * args.steps / (t_ms * 1e-3), "alg_bytes_per_pixel": nbytes // pixels,
+                         "achieved_GBps": gbps, "frac_of_hbm_peak": gbps / peak}
+        if name == "ycbcr_to_rgb_640x480":
+            clocks, head_ms = ck, t_ms
+
+    e2e = None
+    if not args.no_e2e:
+        ne = min(n, 256)
+        hp = planes[:, :ne].cpu().numpy()
+        dmz.ycbcr_to_rgb(hp[0][:8], hp[1][:8], hp[2][:8])
+        te = time.perf_counter()
+        for _ in range(args.steps):
+            dmz.ycbcr_to_rgb(hp[0], hp[1], hp[2])
+        e2e_s = g.max_over_ranks(time.perf_counter() - te)
+        e2e = {"value": ne * W * H * world * args.steps / e2e_s, "unit": "pixels/s", "h2d_bytes_per_step": 3 * ne * W * H, "d2h_bytes_per_step": 3 * ne * W * H,
+               "frames_per_step": ne, "note": "pageable numpy planes through b200_ycbcr_to_rgb_batch(B200_MEM_HOST)"}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu and world == 1:
+        orc, kind, kind_desc = cpu_checker()
+        S = 48
+        hp = planes[:, :S].cpu().numpy()
+        dmz._check(lib.b200_ycbcr_to_rgb_batch(ctx, planes[0].data_ptr(), W, W * H, planes[1].data_ptr(), planes[2].data_ptr(), W, W * H, W, H, S, 3,
+                                               MEM_DEVICE, rgb.data_ptr()))
+        gpu_rgb = rgb.view(-1)[: S * H * W * 3].cpu().numpy().reshape(S, H, W, 3)
+        t0 = time.perf_counter()
+        cpu_rgb = np.stack([orc.ycbcr_to_rgb(hp[0, k], hp[1, k], hp[2, k], 3) for k in range(S)])
+        secs = time.perf_counter() - t0
+        cpu = {"value": S * W * H / secs, "unit": "pixels/s", "cores": 1, "kind": "reference" if kind == "ref" else "port",
+               "sample": "%d random 640x480 frames, one thread, %.2f s wall (%s)" % (S, secs, kind_desc),
+               "parity_vs_gpu_on_sample": {"mismatching_bytes": int((gpu_rgb != cpu_rgb).sum())}}
+    if rank == 0:
+        head = results["ycbcr_to_rgb_640x480"]
+        line = base_line(g, args, "pixels/sec through dmz_YCbCr_to_RGB (640x480 planes -> interleaved RGB)", head["pixels/s"], "pixels/s", head_ms, "u8",
+                         "pixel formats around the path: dmz_YCbCr_to_RGB on 640x480 planes, 1xB200 (+ RGBA->R and the Cython stencils as side legs)",
+                         {"frames_per_gpu_per_launch": n, "cards_per_gpu_per_launch": nc, "data_note": "i.i.d. U{0..255} planes (the arithmetic is data independent)",
+                          "l2": "every leg streams %.1f GB or more per launch: larger than L2, no flush needed" % (px * 3 / 1e9)})
+        line.update({"e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                     "roofline": {"bound": "hbm", "kernel": "ycbcr_to_rgb_kernel<16, 3>", "achieved": head["achieved_GBps"], "peak": peak, "unit": "GB/s",
+                                  "frac": head["frac_of_hbm_peak"], "traffic": None, "peak_source": peak_src,
+                                  "alg_bytes": "3 B read + 3 B written per pixel (4 written for RGBA; RGBA->R 4 + 1; stencils 1 + 2)"},
+                     "legs": results, "cpu_baseline": cpu, "wall_s_timed_region": wall_total})
+        print(json.dumps(line), flush=True)
+    g.finish()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="pipeline", choices=["pipeline", "categorize", "detect-sweep"])
+    ap.add_argument("--config", default="pipeline", choices=["pipeline", "categorize", "detect-sweep", "formats"])
     ap.add_argument("--frames", type=int, default=100000, help="frames per GPU per step (BASELINE configs[1]: 100k)")
     ap.add_argument("--e2e-frames", type=int, default=100000, help="frames per step on the host-buffer (e2e) path (clipped to what host memory allows)")
     ap.add_argument("--cpu-sample", type=int, default=4096, help="frames in the bounded CPU-baseline sample")
     ap.add_argument("--patches", type=int, default=10000000, help="--config categorize: patches per GPU per step (BASELINE configs[2]: 10 M)")
     ap.add_argument("--detect-frames", type=int, default=100000, help="--config detect-sweep: frames per resolution per step")
+    ap.add_argument("--format-frames", type=int, default=8192, help="--config formats: 640x480 frames per GPU per launch")
     ap.add_argument("--sizes", default="", help="--config detect-sweep: comma-separated subset of 480p,720p,1080p")
     ap.add_argument("--card-mode", default="lazy", choices=["lazy", "full"],
                     help="lazy (library default): no cards_out -> only the card rows the scan reads are warped; full: every card materialised")
@@ -769,6 +874,8 @@ def main():
         reference_arm(args, rank, world)
     elif args.config == "categorize":
         categorize_config(args)
+    elif args.config == "formats":
+        formats_config(args)
     elif args.config == "detect-sweep":
         detect_sweep_config(args)
     else:

@@ -111,6 +111,9 @@ def _load():
     lib.b200_best_expiry_seg_batch.argtypes = [vp, vp, vp, i, i, vp, i, vp, vp, vp]
     lib.b200_deinterleave_c2_batch.argtypes = [vp, vp, i, C.c_size_t, i, i, i, i, vp, vp]
     lib.b200_frame_scores_batch.argtypes = [vp, vp, i, C.c_size_t, i, i, i, i, i, vp, vp]
+    lib.b200_ycbcr_to_rgb_batch.argtypes = [vp, vp, i, C.c_size_t, vp, vp, i, C.c_size_t, i, i, i, i, i, vp]
+    lib.b200_rgba_to_r_batch.argtypes = [vp, vp, C.c_size_t, i, vp]
+    lib.b200_stencil3_batch.argtypes = [vp, vp, i, C.c_size_t, i, i, i, i, i, vp]
     lib.b200_expiry_digits_batch.argtypes = [vp, vp, i, i, vp]
     lib.b200_expiry_digits_at_batch.argtypes = [vp, vp, i, vp, i, i, vp]
     lib.b200_scanner_add_expiry.argtypes = [vp, vp, vp, i, i, i, i]
@@ -285,6 +288,33 @@ class Dmz:
         c1, c2 = np.zeros((n, h, w), np.uint8), np.zeros((n, h, w), np.uint8)
         self._check(self.lib.b200_deinterleave_c2_batch(self.ctx, _ptr(planes), 2 * w, 2 * w * h, w, h, n, MEM_HOST, _ptr(c1), _ptr(c2)))
         return c1, c2
+
+    def ycbcr_to_rgb(self, y, cb, cr, channels=3):
+        """y, cb, cr: (n, h, w) u8 planes of the same size.  Returns (n, h, w, channels) R, G, B (, 255) (dmz_YCbCr_to_RGB)."""
+        y, cb, cr = (np.ascontiguousarray(a, np.uint8) for a in (y, cb, cr))
+        n, h, w = y.shape
+        assert cb.shape == y.shape and cr.shape == y.shape
+        out = np.zeros((n, h, w, channels), np.uint8)
+        self._check(self.lib.b200_ycbcr_to_rgb_batch(self.ctx, _ptr(y), w, w * h, _ptr(cb), _ptr(cr), w, w * h, w, h, n, channels,
+                                                     MEM_HOST, _ptr(out)))
+        return out
+
+    def rgba_to_r(self, rgba):
+        """rgba: u8 array of 4 * n_pixels bytes (any shape).  Returns the n_pixels R bytes (dmz_deinterleave_RGBA_to_R)."""
+        if not (rgba.dtype == np.uint8 and rgba.ndim == 1 and rgba.strides[0] == 1):  # keep a caller's (mis)alignment
+            rgba = np.ascontiguousarray(rgba, np.uint8).reshape(-1)
+        n = rgba.size // 4
+        out = np.zeros(n, np.uint8)
+        self._check(self.lib.b200_rgba_to_r_batch(self.ctx, _ptr(rgba), n, MEM_HOST, _ptr(out)))
+        return out
+
+    def stencil3(self, planes, kind):
+        """planes: (n, h, w) u8.  kind 0 / 1 / 2 = dmz_scharr3_dx_abs / dmz_scharr3_dy_abs / dmz_sobel3_dx_dy.  Returns int16 (n, h, w)."""
+        planes = np.ascontiguousarray(planes, np.uint8)
+        n, h, w = planes.shape
+        out = np.zeros((n, h, w), np.int16)
+        self._check(self.lib.b200_stencil3_batch(self.ctx, _ptr(planes), w, w * h, w, h, n, int(kind), MEM_HOST, _ptr(out)))
+        return out
 
     def frame_scores(self, frames, use_full_image=False):
         """frames: (n, h, w) u8 luma.  Returns (focus, brightness) float32 arrays (dmz_focus_score / dmz_brightness_score)."""

@@ -45,6 +45,7 @@ def build(force=False):
         ("vseg_mma.cu", []),
         ("categorize_mma.cu", []),
         ("expiry_mma.cu", []),
+        ("formats.cu", []),
         ("api.cu", ["-fmad=false"]),
         ("b200_tables.cpp", ["-Xcompiler", "-ffp-contract=off"]),
         ("scanner.cpp", ["-Xcompiler", "-ffp-contract=off"]),

@@ -890,6 +890,87 @@ int b200_deinterleave_c2_batch(b200_ctx *ctx, const uint8_t *interleaved, int ro
   return B200_OK;
 } B200_GUARD(ctx)
 
+// dmz_YCbCr_to_RGB over a batch (formats.cu).  Host planes are packed on the way up; the RGB image comes back dense.
+int b200_ycbcr_to_rgb_batch(b200_ctx *ctx, const uint8_t *y, int yrs, size_t yfs, const uint8_t *cb, const uint8_t *cr, int crs,
+                            size_t cfs, int width, int height, int n, int channels, int mem, uint8_t *rgb) try {
+  if (!ctx || !y || !cb || !cr || !rgb || n < 1 || (channels != 3 && channels != 4))
+    return fail(ctx, B200_EINVAL, "b200_ycbcr_to_rgb_batch: bad arguments");
+  if (!strides_ok(yrs, yfs, width, height) || !strides_ok(crs, cfs, width, height))
+    return fail(ctx, B200_EINVAL, "b200_ycbcr_to_rgb_batch: row_stride < width or frame_stride < row_stride * height");
+  CU(cudaSetDevice(ctx->device));
+  if (mem == B200_MEM_DEVICE) {
+    LAUNCH(launch_ycbcr_to_rgb(y, yrs, yfs, cb, cr, crs, cfs, width, height, n, channels, rgb, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return B200_OK;
+  }
+  const size_t plane = (size_t)width * height, in_bytes = (plane * n + 15) & ~(size_t)15, out_bytes = plane * n * channels;
+  int rc = ensure_misc(ctx, 3 * in_bytes + out_bytes);
+  if (rc) return rc;
+  uint8_t *d_in[3] = {(uint8_t *)ctx->d_misc, (uint8_t *)ctx->d_misc + in_bytes, (uint8_t *)ctx->d_misc + 2 * in_bytes};
+  uint8_t *d_out = (uint8_t *)ctx->d_misc + 3 * in_bytes;
+  const uint8_t *dp[3];
+  int drs = 0;
+  size_t dfs = 0;
+  if ((rc = stage_planes(ctx, ctx->stream, y, yrs, yfs, width, height, n, mem, d_in[0], &dp[0], &drs, &dfs))) return rc;
+  if ((rc = stage_planes(ctx, ctx->stream, cb, crs, cfs, width, height, n, mem, d_in[1], &dp[1], &drs, &dfs))) return rc;
+  if ((rc = stage_planes(ctx, ctx->stream, cr, crs, cfs, width, height, n, mem, d_in[2], &dp[2], &drs, &dfs))) return rc;
+  LAUNCH(launch_ycbcr_to_rgb(dp[0], drs, dfs, dp[1], dp[2], drs, dfs, width, height, n, channels, d_out, ctx->stream));
+  CU(cudaMemcpyAsync(rgb, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->h2d_bytes += 3 * plane * n, ctx->d2h_bytes += out_bytes;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+} B200_GUARD(ctx)
+
+// dmz_deinterleave_RGBA_to_R (formats.cu)
+int b200_rgba_to_r_batch(b200_ctx *ctx, const uint8_t *rgba, size_t n_pixels, int mem, uint8_t *r) try {
+  if (!ctx || !rgba || !r || n_pixels < 1) return fail(ctx, B200_EINVAL, "b200_rgba_to_r_batch: bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  if (mem == B200_MEM_DEVICE) {
+    LAUNCH(launch_rgba_to_r(rgba, n_pixels, r, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return B200_OK;
+  }
+  const size_t in_bytes = (4 * n_pixels + 15) & ~(size_t)15;
+  int rc = ensure_misc(ctx, in_bytes + n_pixels);
+  if (rc) return rc;
+  uint8_t *d_in = (uint8_t *)ctx->d_misc, *d_out = d_in + in_bytes;
+  CU(cudaMemcpyAsync(d_in, rgba, 4 * n_pixels, cudaMemcpyHostToDevice, ctx->stream));
+  LAUNCH(launch_rgba_to_r(d_in, n_pixels, d_out, ctx->stream));
+  CU(cudaMemcpyAsync(r, d_out, n_pixels, cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->h2d_bytes += 4 * n_pixels, ctx->d2h_bytes += n_pixels;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+} B200_GUARD(ctx)
+
+// dmz_scharr3_dx_abs / dmz_scharr3_dy_abs / dmz_sobel3_dx_dy over a batch of planes (formats.cu)
+int b200_stencil3_batch(b200_ctx *ctx, const uint8_t *img, int row_stride, size_t frame_stride, int width, int height, int n, int kind,
+                        int mem, int16_t *out) try {
+  if (!ctx || !img || !out || n < 1 || kind < B200_STENCIL_SCHARR_DX_ABS || kind > B200_STENCIL_SOBEL_DX_DY)
+    return fail(ctx, B200_EINVAL, "b200_stencil3_batch: bad arguments");
+  if (!strides_ok(row_stride, frame_stride, width, height))
+    return fail(ctx, B200_EINVAL, "b200_stencil3_batch: row_stride < width or frame_stride < row_stride * height");
+  CU(cudaSetDevice(ctx->device));
+  if (mem == B200_MEM_DEVICE) {
+    LAUNCH(launch_stencil3(img, row_stride, frame_stride, width, height, n, kind, out, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return B200_OK;
+  }
+  const size_t plane = (size_t)width * height, in_bytes = (plane * n + 15) & ~(size_t)15, out_bytes = plane * n * sizeof(int16_t);
+  int rc = ensure_misc(ctx, in_bytes + out_bytes);
+  if (rc) return rc;
+  uint8_t *d_in = (uint8_t *)ctx->d_misc;
+  int16_t *d_out = (int16_t *)(d_in + in_bytes);
+  const uint8_t *dp = nullptr;
+  int drs = 0;
+  size_t dfs = 0;
+  if ((rc = stage_planes(ctx, ctx->stream, img, row_stride, frame_stride, width, height, n, mem, d_in, &dp, &drs, &dfs))) return rc;
+  LAUNCH(launch_stencil3(dp, drs, dfs, width, height, n, kind, d_out, ctx->stream));
+  CU(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->h2d_bytes += plane * n, ctx->d2h_bytes += out_bytes;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+} B200_GUARD(ctx)
+
 // dmz_focus_score / dmz_brightness_score over a batch.  Host frames: only the scoring rectangle crosses PCIe (the
 // reference's ROI clamps the Sobel taps at the rectangle, so nothing outside it is ever read).
 int b200_frame_scores_batch(b200_ctx *ctx, const uint8_t *y, int yrs, size_t yfs, int width, int height, int n,

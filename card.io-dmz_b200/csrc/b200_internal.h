@@ -172,6 +172,12 @@ int launch_expiry_seg(const uint8_t *cards, const uint16_t *y_offsets, int n, co
                       b200_expiry_group *groups, int max_groups, int32_t *n_groups, int32_t *n_dropped, cudaStream_t s);  // expiry_seg.cu
 int launch_deinterleave_c2(const uint8_t *src, int row_stride, size_t frame_stride, int w, int h, int n, uint8_t *ch1, uint8_t *ch2,
                            cudaStream_t s);
+// formats.cu: pixel formats either side of the path (dmz_YCbCr_to_RGB, dmz_deinterleave_RGBA_to_R, the Cython stencils)
+int launch_ycbcr_to_rgb(const uint8_t *y, int yrs, size_t yfs, const uint8_t *cb, const uint8_t *cr, int crs, size_t cfs, int w, int h,
+                        int n, int channels, uint8_t *dst /* n x h x w x channels, dense */, cudaStream_t s);
+int launch_rgba_to_r(const uint8_t *src, size_t n_px, uint8_t *dst, cudaStream_t s);
+int launch_stencil3(const uint8_t *src, int row_stride, size_t frame_stride, int w, int h, int n, int kind /* 0 scharr dx abs, 1 scharr dy abs, 2 sobel dx dy */,
+                    int16_t *out /* n x h x w, dense */, cudaStream_t s);
 int launch_frame_scores(const uint8_t *frames, int row_stride, size_t frame_stride, int n, int rx, int ry, int rw, int rh,
                         float *focus, float *brightness, cudaStream_t s);
 void b200_scoring_rect(int w, int h, int use_full_image, int rect[4]);  // b200_tables.cpp

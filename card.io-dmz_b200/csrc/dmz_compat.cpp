@@ -62,27 +62,41 @@ PlaneView view_of(const IplImage *img) {
   return v;
 }
 
-IplImage *create_gray_image(int width, int height) {
+IplImage *create_image(int width, int height, int depth, int channels) {
   // Prefer the host application's OpenCV allocator so that its cvReleaseImage frees what we hand out.
   typedef struct { int width, height; } Size2;
   typedef IplImage *(*create_fn)(Size2, int, int);
   static create_fn cv_create = (create_fn)dlsym(RTLD_DEFAULT, "cvCreateImage");
   if (cv_create) {
     Size2 s = {width, height};
-    return cv_create(s, IPL_DEPTH_8U, 1);
+    return cv_create(s, depth, channels);
   }
   IplImage *img = (IplImage *)calloc(1, sizeof(IplImage));
   img->nSize = sizeof(IplImage);
-  img->nChannels = 1;
-  img->depth = IPL_DEPTH_8U;
+  img->nChannels = channels;
+  img->depth = depth;
   img->width = width, img->height = height;
   img->align = 4;
-  img->widthStep = (width + 3) & ~3;  // cvCreateImage aligns rows to 4 bytes
+  img->widthStep = (width * channels * ((depth & 255) / 8) + 3) & ~3;  // cvCreateImage aligns rows to 4 bytes
   img->imageSize = img->widthStep * height;
   img->imageData = img->imageDataOrigin = (char *)malloc((size_t)img->imageSize);
-  memcpy(img->colorModel, "GRAY", 4);
-  memcpy(img->channelSeq, "GRAY", 4);
+  memcpy(img->colorModel, channels == 1 ? "GRAY" : "RGB\0", 4);
+  memcpy(img->channelSeq, channels == 1 ? "GRAY" : (channels == 3 ? "BGR\0" : "BGRA"), 4);
   return img;
+}
+
+IplImage *create_gray_image(int width, int height) { return create_image(width, height, IPL_DEPTH_8U, 1); }
+
+// a view of a multi-byte-per-pixel image (ROI honoured): px_bytes per pixel
+PlaneView view_of_px(const IplImage *img, int px_bytes) {
+  PlaneView v = view_of(img);
+  if (img->roi) v.data += (size_t)img->roi->xOffset * (px_bytes - 1);
+  return v;
+}
+
+// rows of a u8 plane packed into a dense w x h buffer
+void pack_rows(const PlaneView &v, uint8_t *dense) {
+  for (int r = 0; r < v.h; r++) memcpy(dense + (size_t)r * v.w, v.data + (size_t)r * v.step, (size_t)v.w);
 }
 
 IplImage *create_card_image() { return create_gray_image(B200_CARD_W, B200_CARD_H); }
@@ -163,6 +177,62 @@ void dmz_deinterleave_uint8_c2(IplImage *interleaved, IplImage **channel1, IplIm
   }
   free(tmp);
 }
+
+// dmz_has_opencv (dmz.h:60, dmz.cpp:42-47): "can a card-sized image be allocated" -- here: is the GPU path usable
+int dmz_has_opencv(void) { return default_ctx() != nullptr; }
+
+// dmz_YCbCr_to_RGB (dmz.h:72, dmz.cpp:58-64): allocates a 3-channel image when *rgb is NULL; a caller-provided image may
+// have 3 or 4 channels (llcv_YCbCr2RGB_u8_c writes alpha = 255 into the fourth, cv/convert.cpp:453, 496-498).
+void dmz_YCbCr_to_RGB(IplImage *y, IplImage *cb, IplImage *cr, IplImage **rgb) {
+  if (!y || !cb || !cr || !rgb) return;
+  const PlaneView vy = view_of(y), vb = view_of(cb), vr = view_of(cr);
+  if (*rgb == NULL) *rgb = create_image(vy.w, vy.h, y->depth, 3);
+  IplImage *out = *rgb;
+  const int ch = out->nChannels;
+  if ((ch != 3 && ch != 4) || vb.w != vy.w || vb.h != vy.h || vr.w != vy.w || vr.h != vy.h) return;
+  const PlaneView vo = view_of_px(out, ch);
+  if (vo.w != vy.w || vo.h != vy.h) return;
+  b200_ctx *ctx = default_ctx();
+  CtxCall call_guard(ctx);
+  if (!ctx) return;
+  const size_t plane = (size_t)vy.w * vy.h;
+  uint8_t *tmp = (uint8_t *)malloc(plane * (size_t)(3 + ch));
+  pack_rows(vy, tmp), pack_rows(vb, tmp + plane), pack_rows(vr, tmp + 2 * plane);
+  uint8_t *dense = tmp + 3 * plane;
+  if (b200_ycbcr_to_rgb_batch(ctx, tmp, vy.w, plane, tmp + plane, tmp + 2 * plane, vy.w, plane, vy.w, vy.h, 1, ch, B200_MEM_HOST, dense) == B200_OK)
+    for (int r = 0; r < vy.h; r++) memcpy((uint8_t *)vo.data + (size_t)r * vo.step, dense + (size_t)r * vy.w * ch, (size_t)vy.w * ch);
+  free(tmp);
+}
+
+// dmz_deinterleave_RGBA_to_R (dmz.h:67, dmz.cpp:66-109)
+void dmz_deinterleave_RGBA_to_R(uint8_t *source, uint8_t *dest, int size) {
+  if (!source || !dest || size < 1) return;
+  b200_ctx *ctx = default_ctx();
+  CtxCall call_guard(ctx);
+  if (ctx) b200_rgba_to_r_batch(ctx, source, (size_t)size, B200_MEM_HOST, dest);
+}
+
+namespace {
+// the three Cython-only stencil wrappers (dmz.h:105-107, dmz.cpp:519-531): u8 source (ROI honoured), int16 destination
+void stencil_into(IplImage *src, IplImage *dst, int kind) {
+  if (!src || !dst || dst->depth != (int)IPL_DEPTH_16S) return;
+  const PlaneView vs = view_of(src), vd = view_of_px(dst, 2);
+  if (vd.w != vs.w || vd.h != vs.h) return;
+  b200_ctx *ctx = default_ctx();
+  CtxCall call_guard(ctx);
+  if (!ctx) return;
+  const size_t plane = (size_t)vs.w * vs.h;
+  uint8_t *tmp = (uint8_t *)malloc(plane * 3);
+  pack_rows(vs, tmp);
+  int16_t *dense = (int16_t *)(tmp + plane + (plane & 1));
+  if (b200_stencil3_batch(ctx, tmp, vs.w, plane, vs.w, vs.h, 1, kind, B200_MEM_HOST, dense) == B200_OK)
+    for (int r = 0; r < vs.h; r++) memcpy((uint8_t *)vd.data + (size_t)r * vd.step, dense + (size_t)r * vs.w, (size_t)vs.w * sizeof(int16_t));
+  free(tmp);
+}
+}  // namespace
+void dmz_scharr3_dx_abs(IplImage *src, IplImage *dst) { stencil_into(src, dst, B200_STENCIL_SCHARR_DX_ABS); }
+void dmz_scharr3_dy_abs(IplImage *src, IplImage *dst) { stencil_into(src, dst, B200_STENCIL_SCHARR_DY_ABS); }
+void dmz_sobel3_dx_dy(IplImage *src, IplImage *dst) { stencil_into(src, dst, B200_STENCIL_SOBEL_DX_DY); }
 
 // dmz_best_expiry_seg (dmz.h:111, dmz.cpp:605-620): malloc'ed array of groups, each with a malloc'ed rectangle list; the
 // caller frees both.  scores / seen counts are not produced by segmentation (the reference copies uninitialised

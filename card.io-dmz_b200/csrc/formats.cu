@@ -1,0 +1,304 @@
+// formats.cu -- the pixel-format steps either side of the detect -> warp -> OCR path (widening rows):
+//
+//   ycbcr_to_rgb_kernel   dmz_YCbCr_to_RGB            dmz.cpp:58-64 -> llcv_YCbCr2RGB_u8_c, cv/convert.cpp:449-504
+//   rgba_to_r_kernel      dmz_deinterleave_RGBA_to_R  dmz.cpp:66-109
+//   stencil3_kernel       dmz_scharr3_dx_abs / dmz_scharr3_dy_abs / dmz_sobel3_dx_dy   dmz.cpp:519-531, cv/sobel.cpp:556-900
+//
+// All three are byte / int16 streaming work bounded by HBM (6 - 7, 5 and 3 bytes per pixel), so the kernels are about
+// instructions per byte: 128-bit accesses where the shapes allow, the colour arithmetic as two-way dot products
+// (IDP.2A: one instruction per channel per pixel with the luma and the rounding constant riding in the accumulator) and
+// saturating packs (I2IP: clamp + pack of two bytes), the stencils on four pixels per thread with byte-SIMD absolute
+// differences and 16-bit pairs in one register.  Results are integers: bit-exact against the reference.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "b200_internal.h"
+
+namespace {
+
+inline int sm_count() {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms;
+}
+
+// ------------------------------------------------------------------------------------------------
+// YCbCr -> RGB(A).  Per pixel (convert.cpp:480-487), with sCb = Cb - 128, sCr = Cr - 128 as int8:
+//   B = sat8(Y + ((sCb * 29049                + 8192) >> 14))
+//   G = sat8(Y + ((sCb * -5636 + sCr * -11698 + 8192) >> 14))
+//   R = sat8(Y + ((sCr * 22987                + 8192) >> 14))
+// Y * 16384 + 8192 goes into the accumulator of the dot product: (x + Y 2^14) >> 14 == (x >> 14) + Y for the arithmetic
+// shift, so each channel is IDP.2A + SHF, and the saturation happens in the pack.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int pack_sat_u8x4(int b0, int b1, int b2, int b3) {
+  unsigned int hi, w;
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(b3), "r"(b2), "r"(0));
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(w) : "r"(b1), "r"(b0), "r"(hi));
+  return w;
+}
+
+struct Rgb4 {
+  int r[4], g[4], b[4];
+};
+
+// four pixels from one word of each plane
+__device__ __forceinline__ void ycc4(unsigned int yw, unsigned int cbw, unsigned int crw, Rgb4 &o) {
+  constexpr int kOne = 16384, kB = 29049, kR = 22987, kGb = -5636, kGr = -11698;
+  constexpr unsigned int sel_lo = (unsigned)kOne, sel_hi = (unsigned)kOne << 16;       // (16384, 0) / (0, 16384) as u16 x 2
+  constexpr int b_lo = kB, b_hi = (int)((unsigned)kB << 16), r_lo = kR, r_hi = (int)((unsigned)kR << 16);
+  constexpr int g_pair = (int)(((unsigned)kGr << 16) | ((unsigned)kGb & 0xFFFFu));     // (kGb, kGr) as s16 x 2
+  const int scb = (int)(cbw ^ 0x80808080u), scr = (int)(crw ^ 0x80808080u);            // u8 - 128 as s8, four at once
+  const int g01 = (int)__byte_perm((unsigned)scb, (unsigned)scr, 0x5140), g23 = (int)__byte_perm((unsigned)scb, (unsigned)scr, 0x7362);
+  int yc[4];
+  yc[0] = (int)__dp2a_lo(sel_lo, yw, 8192u), yc[1] = (int)__dp2a_lo(sel_hi, yw, 8192u);
+  yc[2] = (int)__dp2a_hi(sel_lo, yw, 8192u), yc[3] = (int)__dp2a_hi(sel_hi, yw, 8192u);
+  o.b[0] = __dp2a_lo(b_lo, scb, yc[0]) >> 14, o.b[1] = __dp2a_lo(b_hi, scb, yc[1]) >> 14;
+  o.b[2] = __dp2a_hi(b_lo, scb, yc[2]) >> 14, o.b[3] = __dp2a_hi(b_hi, scb, yc[3]) >> 14;
+  o.r[0] = __dp2a_lo(r_lo, scr, yc[0]) >> 14, o.r[1] = __dp2a_lo(r_hi, scr, yc[1]) >> 14;
+  o.r[2] = __dp2a_hi(r_lo, scr, yc[2]) >> 14, o.r[3] = __dp2a_hi(r_hi, scr, yc[3]) >> 14;
+  o.g[0] = __dp2a_lo(g_pair, g01, yc[0]) >> 14, o.g[1] = __dp2a_hi(g_pair, g01, yc[1]) >> 14;
+  o.g[2] = __dp2a_lo(g_pair, g23, yc[2]) >> 14, o.g[3] = __dp2a_hi(g_pair, g23, yc[3]) >> 14;
+}
+
+// V pixels per work item (1: byte path for any shape; 4: 32-bit accesses; 16: 128-bit accesses), CH = 3 or 4
+template <int V, int CH>
+__global__ void __launch_bounds__(256)
+ycbcr_to_rgb_kernel(const uint8_t *__restrict__ y, int yrs, size_t yfs, const uint8_t *__restrict__ cb, const uint8_t *__restrict__ cr,
+                    int crs, size_t cfs, int w, int h, size_t n, uint8_t *__restrict__ dst) {
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (size_t)gridDim.x * blockDim.x;
+  const int wv = w / V;
+  // (frame, row, column group) of this thread's item, advanced by the grid size without dividing again
+  const size_t per_frame = (size_t)h * wv;
+  size_t f = tid / per_frame;
+  int row = (int)((tid - f * per_frame) / wv), xv = (int)(tid - f * per_frame - (size_t)row * wv);
+  const size_t step_f = nthreads / per_frame;
+  const int step_row = (int)((nthreads - step_f * per_frame) / wv), step_x = (int)(nthreads - step_f * per_frame - (size_t)step_row * wv);
+  for (; f < n; f += step_f, row += step_row, xv += step_x) {
+    if (xv >= wv) xv -= wv, row++;
+    if (row >= h) row -= h, f++;
+    if (f >= n) break;
+    const int x = xv * V;
+    const uint8_t *py = y + f * yfs + (size_t)row * yrs + x, *pb = cb + f * cfs + (size_t)row * crs + x, *pr = cr + f * cfs + (size_t)row * crs + x;
+    uint8_t *o = dst + ((f * h + row) * (size_t)w + x) * CH;
+    if constexpr (V == 1) {
+      Rgb4 p;
+      ycc4(*py, *pb, *pr, p);
+      const unsigned int px = pack_sat_u8x4(p.r[0], p.g[0], p.b[0], 255);
+      o[0] = (uint8_t)px, o[1] = (uint8_t)(px >> 8), o[2] = (uint8_t)(px >> 16);
+      if (CH == 4) o[3] = 0xff;
+    } else {
+      unsigned int yw[V / 4], bw[V / 4], rw[V / 4], ow[V / 4 * CH];
+      if constexpr (V == 16) {
+        const uint4 a = __ldcs(reinterpret_cast<const uint4 *>(py)), b = __ldcs(reinterpret_cast<const uint4 *>(pb)),
+                    c = __ldcs(reinterpret_cast<const uint4 *>(pr));
+        yw[0] = a.x, yw[1] = a.y, yw[2] = a.z, yw[3] = a.w;
+        bw[0] = b.x, bw[1] = b.y, bw[2] = b.z, bw[3] = b.w;
+        rw[0] = c.x, rw[1] = c.y, rw[2] = c.z, rw[3] = c.w;
+      } else {
+        yw[0] = __ldcs(reinterpret_cast<const unsigned int *>(py)), bw[0] = __ldcs(reinterpret_cast<const unsigned int *>(pb));
+        rw[0] = __ldcs(reinterpret_cast<const unsigned int *>(pr));
+      }
+#pragma unroll
+      for (int q = 0; q < V / 4; q++) {
+        Rgb4 p;
+        ycc4(yw[q], bw[q], rw[q], p);
+        if (CH == 3) {  // R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3
+          ow[3 * q + 0] = pack_sat_u8x4(p.r[0], p.g[0], p.b[0], p.r[1]);
+          ow[3 * q + 1] = pack_sat_u8x4(p.g[1], p.b[1], p.r[2], p.g[2]);
+          ow[3 * q + 2] = pack_sat_u8x4(p.b[2], p.r[3], p.g[3], p.b[3]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; k++) ow[4 * q + k] = pack_sat_u8x4(p.r[k], p.g[k], p.b[k], 255);
+        }
+      }
+      if constexpr (V == 16 || CH == 4) {
+#pragma unroll
+        for (int k = 0; k < V / 4 * CH / 4; k++)
+          __stcs(reinterpret_cast<uint4 *>(o) + k, make_uint4(ow[4 * k], ow[4 * k + 1], ow[4 * k + 2], ow[4 * k + 3]));
+      } else {
+#pragma unroll
+        for (int k = 0; k < 3; k++) __stcs(reinterpret_cast<unsigned int *>(o) + k, ow[k]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// RGBA -> R: dest[i] = source[4 i].  A warp takes 2 KB of source per step: lane l reads 16 bytes at 16 l + 512 j
+// (j = 0..3, coalesced 128-bit loads) and writes the four R bytes at 4 l + 128 j (coalesced 32-bit stores).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rgba_to_r_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, size_t n_px, int vec_ok) {
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (size_t)gridDim.x * blockDim.x;
+  size_t done = 0;
+  if (vec_ok) {  // src 16-byte aligned, dst 4-byte aligned
+    const size_t warps = nthreads >> 5, warp = tid >> 5, n_steps = n_px >> 9;  // 512 pixels per warp step
+    const int lane = (int)(tid & 31);
+    for (size_t s = warp; s < n_steps; s += warps) {
+      const uint4 *p = reinterpret_cast<const uint4 *>(src + (s << 11)) + lane;
+      unsigned int *q = reinterpret_cast<unsigned int *>(dst + (s << 9)) + lane;
+      uint4 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) v[j] = __ldcs(p + 32 * j);
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        __stcs(q + 32 * j, __byte_perm(__byte_perm(v[j].x, v[j].y, 0x0040), __byte_perm(v[j].z, v[j].w, 0x0040), 0x5410));
+    }
+    done = n_steps << 9;
+  }
+  for (size_t i = done + tid; i < n_px; i += nthreads) dst[i] = src[4 * i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3 x 3 stencils, rows and columns clamped at the image.  A CTA stages a (64 + 2) x (128 + 8) byte tile in shared memory
+// (clamping happens there, once), then every thread produces four pixels a row for eight rows, sliding a three-row
+// window of the words left of / at / right of its four columns.
+//   KIND 0  t = |p(x+1) - p(x-1)| in every row;      out = 3 (t(y-1) + t(y+1)) + 10 t(y)
+//   KIND 1  t = |p(y+1) - p(y-1)| in every column;   out = 3 (t(x-1) + t(x+1)) + 10 t(x)
+//   KIND 2  out = p(x-1,y-1) - p(x+1,y-1) - p(x-1,y+1) + p(x+1,y+1)
+// t <= 255 and out <= 4080: two 16-bit lanes per register never carry into each other.  KIND 2 is signed (+-510): the
+// difference is taken with a bias of 1024 per lane, removed when the lanes are stored.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTileW = 128, kTileH = 64, kStThreads = 256, kPitchW = kTileW / 4 + 2;  // words per staged row
+
+__device__ __forceinline__ unsigned int lo_pair(unsigned int t) { return __byte_perm(t, 0u, 0x4140); }  // (t0, t1) as u16 x 2
+__device__ __forceinline__ unsigned int hi_pair(unsigned int t) { return __byte_perm(t, 0u, 0x4342); }  // (t2, t3)
+
+template <int KIND>
+__global__ void __launch_bounds__(kStThreads)
+stencil3_kernel(const uint8_t *__restrict__ src, int row_stride, size_t frame_stride, int w, int h, int tiles_x, int tiles_y,
+                size_t n_tiles, int16_t *__restrict__ out, int word_ok) {
+  __shared__ unsigned int s_tile[(kTileH + 2) * kPitchW];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const bool store8 = (w % 4 == 0) && ((uintptr_t)out % 8 == 0);
+  for (size_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const size_t f = t / ((size_t)tiles_x * tiles_y);
+    const int rem = (int)(t - f * ((size_t)tiles_x * tiles_y)), ty = rem / tiles_x, tx = rem - ty * tiles_x;
+    const int x0 = tx * kTileW, y0 = ty * kTileH;
+    const uint8_t *img = src + f * frame_stride;
+    // staged word (r, k) holds image columns x0 - 4 + 4 k .. + 3 of image row y0 - 1 + r, clamped
+    for (int i = threadIdx.x; i < (kTileH + 2) * kPitchW; i += kStThreads) {
+      const int r = i / kPitchW, k = i - r * kPitchW;
+      int gy = y0 - 1 + r;
+      gy = gy < 0 ? 0 : (gy > h - 1 ? h - 1 : gy);
+      const uint8_t *row = img + (size_t)gy * row_stride;
+      const int gx = x0 - 4 + 4 * k;
+      unsigned int v;
+      if (word_ok && gx >= 0 && gx + 3 < w) {
+        v = __ldg(reinterpret_cast<const unsigned int *>(row + gx));
+      } else {
+        v = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          int c = gx + j;
+          c = c < 0 ? 0 : (c > w - 1 ? w - 1 : c);
+          v |= (unsigned int)__ldg(row + c) << (8 * j);
+        }
+      }
+      s_tile[i] = v;
+    }
+    __syncthreads();
+    const int x = x0 + 4 * lane;
+    if (x < w) {
+      // window of staged rows: index 0 = the row above the output row, 1 = the output row, 2 = the row below
+      unsigned int a[3], b[3], c[3];  // KIND 0: t pairs (lo, hi) are kept in a / b;  KIND 1, 2: the words left / at / right
+      auto fetch = [&](int r, unsigned int &L, unsigned int &C, unsigned int &R) {
+        const unsigned int *p = s_tile + r * kPitchW + lane;
+        L = p[0], C = p[1], R = p[2];
+      };
+      auto prepare = [&](int r, int slot) {
+        unsigned int L, C, R;
+        fetch(r, L, C, R);
+        if (KIND == 0) {
+          const unsigned int tt = __vabsdiffu4(__byte_perm(C, R, 0x4321), __byte_perm(L, C, 0x6543));  // |p(x+1) - p(x-1)| x 4
+          a[slot] = lo_pair(tt), b[slot] = hi_pair(tt);
+        } else {
+          a[slot] = L, b[slot] = C, c[slot] = R;
+        }
+      };
+      const int r0 = wid * 8;  // first output row of this warp inside the tile
+      prepare(r0, 0);
+      prepare(r0 + 1, 1);
+#pragma unroll
+      for (int rr = 0; rr < 8; rr++) {
+        prepare(r0 + rr + 2, 2);
+        const int yy = y0 + r0 + rr;
+        unsigned int o_lo, o_hi;
+        if (KIND == 0) {
+          o_lo = (a[0] + a[2]) * 3u + a[1] * 10u, o_hi = (b[0] + b[2]) * 3u + b[1] * 10u;
+        } else if (KIND == 1) {
+          const unsigned int tL = __vabsdiffu4(a[2], a[0]), tC = __vabsdiffu4(b[2], b[0]), tR = __vabsdiffu4(c[2], c[0]);
+          const unsigned int tl = __byte_perm(tL, tC, 0x6543), tr = __byte_perm(tC, tR, 0x4321);  // t(x-1), t(x+1)
+          o_lo = (lo_pair(tl) + lo_pair(tr)) * 3u + lo_pair(tC) * 10u, o_hi = (hi_pair(tl) + hi_pair(tr)) * 3u + hi_pair(tC) * 10u;
+        } else {
+          const unsigned int ul = __byte_perm(a[0], b[0], 0x6543), ur = __byte_perm(b[0], c[0], 0x4321);  // row above: p(x-1), p(x+1)
+          const unsigned int dl = __byte_perm(a[2], b[2], 0x6543), dr = __byte_perm(b[2], c[2], 0x4321);  // row below
+          o_lo = lo_pair(ul) + lo_pair(dr) + 0x04000400u - lo_pair(ur) - lo_pair(dl);
+          o_hi = hi_pair(ul) + hi_pair(dr) + 0x04000400u - hi_pair(ur) - hi_pair(dl);
+          const int v0 = (int)(o_lo & 0xFFFFu) - 1024, v1 = (int)(o_lo >> 16) - 1024, v2 = (int)(o_hi & 0xFFFFu) - 1024, v3 = (int)(o_hi >> 16) - 1024;
+          o_lo = __byte_perm((unsigned)v0, (unsigned)v1, 0x5410), o_hi = __byte_perm((unsigned)v2, (unsigned)v3, 0x5410);
+        }
+        if (yy < h) {
+          int16_t *o = out + (f * h + yy) * (size_t)w + x;
+          if (store8 && x + 3 < w) {
+            __stcs(reinterpret_cast<uint2 *>(o), make_uint2(o_lo, o_hi));
+          } else {
+            const unsigned int ww[2] = {o_lo, o_hi};
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+              if (x + j < w) o[j] = (int16_t)(ww[j >> 1] >> (16 * (j & 1)));
+          }
+        }
+        a[0] = a[1], a[1] = a[2], b[0] = b[1], b[1] = b[2];
+        if (KIND != 0) c[0] = c[1], c[1] = c[2];
+      }
+    }
+    __syncthreads();  // the tile is reused by the next trip
+  }
+}
+
+}  // namespace
+
+int launch_ycbcr_to_rgb(const uint8_t *y, int yrs, size_t yfs, const uint8_t *cb, const uint8_t *cr, int crs, size_t cfs, int w, int h,
+                        int n, int channels, uint8_t *dst, cudaStream_t s) {
+  auto aligned = [&](int a) {
+    return w % a == 0 && yrs % a == 0 && crs % a == 0 && yfs % a == 0 && cfs % a == 0 && (uintptr_t)y % a == 0 && (uintptr_t)cb % a == 0 &&
+           (uintptr_t)cr % a == 0 && (uintptr_t)dst % a == 0;
+  };
+  // a 4-channel word store of four pixels needs 16-byte destination alignment: rows are 4 w bytes, so w % 4 == 0 gives it
+  const int v = aligned(16) ? 16 : (aligned(4) && (channels == 3 || (uintptr_t)dst % 16 == 0) ? 4 : 1);
+  const size_t items = (size_t)n * h * (w / v);
+  size_t blocks = (items + 255) / 256;
+  const size_t cap = (size_t)sm_count() * 8;  // grid-stride: 8 CTAs x 256 threads per SM
+  blocks = blocks > cap ? cap : (blocks < 1 ? 1 : blocks);
+#define YCC(V, CH) ycbcr_to_rgb_kernel<V, CH><<<(unsigned)blocks, 256, 0, s>>>(y, yrs, yfs, cb, cr, crs, cfs, w, h, (size_t)n, dst)
+  if (channels == 3) {
+    if (v == 16) YCC(16, 3); else if (v == 4) YCC(4, 3); else YCC(1, 3);
+  } else {
+    if (v == 16) YCC(16, 4); else if (v == 4) YCC(4, 4); else YCC(1, 4);
+  }
+#undef YCC
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int launch_rgba_to_r(const uint8_t *src, size_t n_px, uint8_t *dst, cudaStream_t s) {
+  const int vec_ok = ((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 4 == 0);
+  size_t blocks = ((n_px >> 4) + 255) / 256;  // a thread moves 16 pixels per step
+  const size_t cap = (size_t)sm_count() * 8;
+  blocks = blocks > cap ? cap : (blocks < 1 ? 1 : blocks);
+  rgba_to_r_kernel<<<(unsigned)blocks, 256, 0, s>>>(src, dst, n_px, vec_ok);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int launch_stencil3(const uint8_t *src, int row_stride, size_t frame_stride, int w, int h, int n, int kind, int16_t *out, cudaStream_t s) {
+  const int tiles_x = (w + kTileW - 1) / kTileW, tiles_y = (h + kTileH - 1) / kTileH;
+  const size_t n_tiles = (size_t)n * tiles_x * tiles_y;
+  const int word_ok = ((uintptr_t)src % 4 == 0) && (row_stride % 4 == 0) && (frame_stride % 4 == 0);
+  const size_t cap = (size_t)sm_count() * 8;
+  const unsigned blocks = (unsigned)(n_tiles > cap ? cap : n_tiles);
+  if (kind == 0) stencil3_kernel<0><<<blocks, kStThreads, 0, s>>>(src, row_stride, frame_stride, w, h, tiles_x, tiles_y, n_tiles, out, word_ok);
+  else if (kind == 1) stencil3_kernel<1><<<blocks, kStThreads, 0, s>>>(src, row_stride, frame_stride, w, h, tiles_x, tiles_y, n_tiles, out, word_ok);
+  else stencil3_kernel<2><<<blocks, kStThreads, 0, s>>>(src, row_stride, frame_stride, w, h, tiles_x, tiles_y, n_tiles, out, word_ok);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}

@@ -194,6 +194,26 @@ int b200_vseg_rows_batch(b200_ctx *ctx, const uint8_t *cards, int n, int mem, fl
 int b200_deinterleave_c2_batch(b200_ctx *ctx, const uint8_t *interleaved, int row_stride, size_t frame_stride, int width, int height,
                                int n, int mem, uint8_t *channel1, uint8_t *channel2);
 
+/* ---- pixel formats either side of the path (the widening after SURVEY 8f's four rows) ----
+ * dmz_YCbCr_to_RGB (dmz.h:72, dmz.cpp:58-64 -> llcv_YCbCr2RGB_u8_c, cv/convert.cpp:449-504): n triples of SAME-SIZED
+ * u8 planes (the SDK converts the warped card: Cb / Cr come out of dmz_transform_card with upsample = true) into
+ * interleaved R, G, B bytes, or R, G, B, 255 when channels == 4 (the reference keys that on dst->nChannels).
+ * rgb = n x height x width x channels, dense.  Cb and Cr share their strides. */
+int b200_ycbcr_to_rgb_batch(b200_ctx *ctx, const uint8_t *y, int y_row_stride, size_t y_frame_stride, const uint8_t *cb,
+                            const uint8_t *cr, int c_row_stride, size_t c_frame_stride, int width, int height, int n, int channels,
+                            int mem, uint8_t *rgb);
+/* dmz_deinterleave_RGBA_to_R (dmz.h:67, dmz.cpp:66-109): r[i] = rgba[4 i] for n_pixels pixels (frames of a batch are
+ * just more pixels).  The reference assumes n_pixels % 4 == 0 and writes past `dest` otherwise; this one never does. */
+int b200_rgba_to_r_batch(b200_ctx *ctx, const uint8_t *rgba, size_t n_pixels, int mem, uint8_t *r);
+/* dmz_scharr3_dx_abs / dmz_scharr3_dy_abs / dmz_sobel3_dx_dy (dmz.h:105-107, dmz.cpp:519-531 -> cv/sobel.cpp:556-900),
+ * kind = B200_STENCIL_*: n u8 planes -> n x height x width int16, dense; rows and columns clamp at the plane's edge.
+ * (The "abs" pair takes |difference| BEFORE the 3-10-3 smoothing, as the reference does: it is not |Scharr|.) */
+#define B200_STENCIL_SCHARR_DX_ABS 0
+#define B200_STENCIL_SCHARR_DY_ABS 1
+#define B200_STENCIL_SOBEL_DX_DY 2
+int b200_stencil3_batch(b200_ctx *ctx, const uint8_t *img, int row_stride, size_t frame_stride, int width, int height, int n,
+                        int kind, int mem, int16_t *out);
+
 /* ---- frame scoring ----
  * dmz_focus_score / dmz_brightness_score (dmz.h:77-80, dmz.cpp:114-195) for n luma planes: focus = stddev of
  * |sobel3 dx.dy| and brightness = mean, both over the reference's scoring rectangle (the centred card-sized rectangle,

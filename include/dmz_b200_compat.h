@@ -50,6 +50,8 @@ typedef struct _IplImage {
   char *imageDataOrigin;
 } IplImage;
 #define IPL_DEPTH_8U 8
+#define IPL_DEPTH_SIGN 0x80000000
+#define IPL_DEPTH_16S (IPL_DEPTH_SIGN | 16)
 #endif
 
 /* ---- dmz_olm.h / dmz.h types ---- */
@@ -175,6 +177,12 @@ void dmz_transform_card(dmz_context *dmz, IplImage *sample, dmz_corner_points co
                         bool upsample, IplImage **transformed);
 void dmz_deinterleave_uint8_c2(IplImage *interleaved, IplImage **channel1, IplImage **channel2); /* dmz.h:64 */
 float dmz_focus_score(IplImage *image, bool use_full_image);      /* dmz.h:77 */
+int dmz_has_opencv(void);                                          /* dmz.h:60 */
+void dmz_deinterleave_RGBA_to_R(uint8_t *source, uint8_t *dest, int size);        /* dmz.h:67 */
+void dmz_YCbCr_to_RGB(IplImage *y, IplImage *cb, IplImage *cr, IplImage **rgb);   /* dmz.h:72: allocates *rgb (3 channels) when NULL */
+void dmz_scharr3_dx_abs(IplImage *src, IplImage *dst);             /* dmz.h:105-107 (CYTHON_DMZ): u8 -> IPL_DEPTH_16S */
+void dmz_scharr3_dy_abs(IplImage *src, IplImage *dst);
+void dmz_sobel3_dx_dy(IplImage *src, IplImage *dst);
 /* dmz.h:103-120 (the CYTHON_DMZ-only block): the expiry segmentation entry point of cython_dmz/dmz.pyx.  Layout of
  * CythonGroupedRects as in scan/expiry_types.h:95-118. */
 typedef struct {

@@ -129,6 +129,9 @@ class Oracle:
         f("focus_score", [vp, i, i, i, i], C.c_float)
         f("brightness_score", [vp, i, i, i, i], C.c_float)
         f("scoring_rect", [i, i, i, vp])
+        f("ycbcr_to_rgb", [vp, i, vp, vp, i, i, i, i, vp, i])
+        f("rgba_to_r", [vp, vp, C.c_size_t])
+        f("stencil3", [vp, i, i, i, i, vp])
         f("luhn", [vp, i], i)
         f("card_type", [vp, i], i)
         f("bench_frames", [vp, i, i, i, vp, vp, i, i, vp], C.c_double)
@@ -275,6 +278,27 @@ class Oracle:
     def scoring_rect(self, w, h, use_full_image=False):
         out = np.zeros(4, np.int32)
         self._scoring_rect(w, h, int(use_full_image), _p(out))
+        return out
+
+    # ---- pixel formats either side of the path (dmz_YCbCr_to_RGB, dmz_deinterleave_RGBA_to_R, Cython stencils) ----
+    def ycbcr_to_rgb(self, y, cb, cr, channels=3):
+        y, cb, cr = (np.ascontiguousarray(a, np.uint8) for a in (y, cb, cr))
+        h, w = y.shape
+        out = np.zeros((h, w, channels), np.uint8)
+        self._ycbcr_to_rgb(_p(y), w, _p(cb), _p(cr), w, w, h, channels, _p(out), w * channels)
+        return out
+
+    def rgba_to_r(self, rgba):
+        rgba = np.ascontiguousarray(rgba, np.uint8).reshape(-1)
+        out = np.zeros(rgba.size // 4, np.uint8)
+        self._rgba_to_r(_p(rgba), _p(out), out.size)
+        return out
+
+    def stencil3(self, img, kind):
+        """kind 0 / 1 / 2 = llcv_scharr3_dx_abs / llcv_scharr3_dy_abs / llcv_sobel3_dx_dy on a whole u8 image -> int16."""
+        img = np.ascontiguousarray(img, np.uint8)
+        out = np.zeros(img.shape, np.int16)
+        self._stencil3(_p(img), img.shape[1], img.shape[1], img.shape[0], kind, _p(out))
         return out
 
     # ---- E0: expiry digit (port only; the reference build here has SCAN_EXPIRY off) -----------------------

@@ -1070,6 +1070,60 @@ float orc_brightness_score(const uint8_t *img, int ystep, int w, int h, int use_
   return (float)orc_mean_u8(img + (size_t)rc[1] * ystep + rc[0], ystep, rc[2], rc[3]);
 }
 
+/* ---- pixel formats either side of the path (widening rows) --------------------------------------- */
+
+/* llcv_YCbCr2RGB_u8_c (cv/convert.cpp:449-504, behind dmz_YCbCr_to_RGB dmz.cpp:58-64): three same-sized planes ->
+ * interleaved R, G, B (, A = 255) bytes.  Fixed point, 14 fractional bits, round-half-up by the arithmetic shift
+ * (which rounds negative products towards minus infinity, as gcc's >> on int does), then saturation. */
+void orc_ycbcr_to_rgb(const uint8_t *y, int ystep, const uint8_t *cb, const uint8_t *cr, int cstep, int w, int h, int channels,
+                      uint8_t *dst, int dstep) {
+  int r, c;
+  for (r = 0; r < h; r++)
+    for (c = 0; c < w; c++) {
+      const int py = y[(size_t)r * ystep + c];
+      const int scb = (int)cb[(size_t)r * cstep + c] - 128, scr = (int)cr[(size_t)r * cstep + c] - 128; /* int8_t range */
+      const int pb = py + ((scb * 29049 + (1 << 13)) >> 14);
+      const int pg = py + ((scb * -5636 + scr * -11698 + (1 << 13)) >> 14);
+      const int pr = py + ((scr * 22987 + (1 << 13)) >> 14);
+      uint8_t *o = dst + (size_t)r * dstep + (size_t)c * channels;
+      o[0] = (uint8_t)(pr < 0 ? 0 : pr > 255 ? 255 : pr);
+      o[1] = (uint8_t)(pg < 0 ? 0 : pg > 255 ? 255 : pg);
+      o[2] = (uint8_t)(pb < 0 ? 0 : pb > 255 ? 255 : pb);
+      if (channels == 4) o[3] = 0xff;
+    }
+}
+
+/* dmz_deinterleave_RGBA_to_R (dmz.cpp:66-109): dest[i] = source[4 i] for the `size` pixels (the scalar path's groups of
+ * eight and of four cover every index when size % 4 == 0, which the reference assumes). */
+void orc_rgba_to_r(const uint8_t *source, uint8_t *dest, size_t size) {
+  size_t i;
+  for (i = 0; i < size; i++) dest[i] = source[4 * i];
+}
+
+/* The three 3x3 stencils the Cython layer exposes (dmz.cpp:519-531), all with rows and columns clamped at the image:
+ *   kind 0  llcv_scharr3_dx_abs (cv/sobel.cpp:706-799): t = |p(x+1) - p(x-1)| per row, then 3 t(y-1) + 10 t(y) + 3 t(y+1)
+ *   kind 1  llcv_scharr3_dy_abs (cv/sobel.cpp:826-900): t = |p(y+1) - p(y-1)| per column, then 3 t(x-1) + 10 t(x) + 3 t(x+1)
+ *   kind 2  llcv_sobel3_dx_dy   (cv/sobel.cpp:556-628): p(x-1,y-1) - p(x+1,y-1) - p(x-1,y+1) + p(x+1,y+1)
+ * (the absolute value is taken BEFORE the smoothing pass: these are not |Scharr|). */
+void orc_stencil3(const uint8_t *img, int step, int w, int h, int kind, int16_t *out) {
+  int x, y;
+  for (y = 0; y < h; y++) {
+    const uint8_t *r0 = img + (size_t)(y == 0 ? 0 : y - 1) * step, *r1 = img + (size_t)y * step,
+                  *r2 = img + (size_t)(y == h - 1 ? y : y + 1) * step;
+    for (x = 0; x < w; x++) {
+      const int xl = x == 0 ? 0 : x - 1, xr = x == w - 1 ? x : x + 1;
+      int v;
+      if (kind == 0)
+        v = 3 * (abs(r0[xr] - r0[xl]) + abs(r2[xr] - r2[xl])) + 10 * abs(r1[xr] - r1[xl]);
+      else if (kind == 1)
+        v = 3 * (abs(r2[xl] - r0[xl]) + abs(r2[xr] - r0[xr])) + 10 * abs(r2[x] - r0[x]);
+      else
+        v = r0[xl] - r0[xr] - r2[xl] + r2[xr];
+      out[(size_t)y * w + x] = (int16_t)v;
+    }
+  }
+}
+
 int orc_luhn(const uint8_t *d, int n) { /* dmz_olm.cpp dmz_passes_luhn_checksum */
   int even = 0, sum = 0, i;
   for (i = n - 1; i >= 0; i--) {

@@ -69,6 +69,14 @@ void orc_scoring_rect(int w, int h, int use_full_image, int rect[4]);
 float orc_focus_score(const uint8_t *y, int ystep, int w, int h, int use_full_image);
 float orc_brightness_score(const uint8_t *y, int ystep, int w, int h, int use_full_image);
 
+/* ---- pixel formats either side of the path: dmz_YCbCr_to_RGB (dmz.cpp:58-64, cv/convert.cpp:449-504),
+ * dmz_deinterleave_RGBA_to_R (dmz.cpp:66-109), and the 3x3 stencils of the Cython layer (dmz.cpp:519-531; kind 0 / 1 / 2 =
+ * llcv_scharr3_dx_abs / llcv_scharr3_dy_abs / llcv_sobel3_dx_dy, cv/sobel.cpp:556-900) ---- */
+void orc_ycbcr_to_rgb(const uint8_t *y, int ystep, const uint8_t *cb, const uint8_t *cr, int cstep, int w, int h, int channels,
+                      uint8_t *dst, int dstep);
+void orc_rgba_to_r(const uint8_t *source, uint8_t *dest, size_t size);
+void orc_stencil3(const uint8_t *img, int step, int w, int h, int kind, int16_t *out);
+
 uint32_t orc_card_check(const uint8_t *p, size_t n);
 
 /* multi-threaded timing of the whole path (bench.py cpu_baseline kind "port"); returns wall seconds */

@@ -452,6 +452,34 @@ double ref_bench_frames(const uint8_t *frames, int n, int w, int h, const uint8_
   return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
 }
 
+/* ---- pixel formats either side of the path ---------------------------------------------------------------------- */
+
+/* dmz_YCbCr_to_RGB (dmz.cpp:58-64 -> llcv_YCbCr2RGB_u8, cv/convert.cpp:449-504) into caller memory (3 or 4 channels) */
+void ref_ycbcr_to_rgb(const uint8_t *y, int ystep, const uint8_t *cb, const uint8_t *cr, int cstep, int w, int h, int channels,
+                      uint8_t *dst, int dstep) {
+  Hdr a, b, c, d;
+  wrap(&a, y, w, h, ystep, IPL_DEPTH_8U);
+  wrap(&b, cb, w, h, cstep, IPL_DEPTH_8U);
+  wrap(&c, cr, w, h, cstep, IPL_DEPTH_8U);
+  wrap(&d, dst, w, h, dstep, IPL_DEPTH_8U);
+  d.img.nChannels = channels;
+  IplImage *out = &d.img;
+  dmz_YCbCr_to_RGB(&a.img, &b.img, &c.img, &out);
+}
+
+/* dmz_deinterleave_RGBA_to_R (dmz.cpp:66-109) */
+void ref_rgba_to_r(const uint8_t *source, uint8_t *dest, size_t size) { dmz_deinterleave_RGBA_to_R((uint8_t *)source, dest, (int)size); }
+
+/* dmz_scharr3_dx_abs / dmz_scharr3_dy_abs / dmz_sobel3_dx_dy (dmz.cpp:519-531; cv/sobel.cpp:556-900), kind 0 / 1 / 2 */
+void ref_stencil3(const uint8_t *img, int step, int w, int h, int kind, int16_t *out) {
+  Hdr a, d;
+  wrap(&a, img, w, h, step, IPL_DEPTH_8U);
+  wrap(&d, out, w, h, w * (int)sizeof(int16_t), IPL_DEPTH_16S);
+  if (kind == 0) dmz_scharr3_dx_abs(&a.img, &d.img);
+  else if (kind == 1) dmz_scharr3_dy_abs(&a.img, &d.img);
+  else dmz_sobel3_dx_dy(&a.img, &d.img);
+}
+
 #define BT(x) ref_##x
 #include "bench_taps.inc"
 #undef BT

@@ -50,6 +50,12 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def golden_formats():
+    """dmz_YCbCr_to_RGB / dmz_deinterleave_RGBA_to_R / Cython stencil outputs of the reference build (tools/make_ref_formats_golden.py)."""
+    return np.load(os.path.join(HERE, "golden", "ref_formats.npz"))
+
+
+@pytest.fixture(scope="session")
 def pkg():
     from util import load_pkg
     return load_pkg()

@@ -23,6 +23,8 @@ REFERENCE_SYMBOLS = [
     "_Z29scanner_add_frame_with_expiryP12ScannerStateP9_IplImagebP15FrameScanResult",
     "_Z14scanner_resultP12ScannerStateP13ScannerResult", "_Z15scanner_destroyP12ScannerState",
     "_Z25dmz_deinterleave_uint8_c2P9_IplImagePS0_S1_", "_Z19dmz_best_expiry_segP9_IplImagetPP18CythonGroupedRectsPt", "_Z15dmz_focus_scoreP9_IplImageb", "_Z20dmz_brightness_scoreP9_IplImageb",
+    "_Z14dmz_has_opencvv", "_Z16dmz_YCbCr_to_RGBP9_IplImageS0_S0_PS0_", "_Z26dmz_deinterleave_RGBA_to_RPhS_i",
+    "_Z18dmz_scharr3_dx_absP9_IplImageS0_", "_Z18dmz_scharr3_dy_absP9_IplImageS0_", "_Z16dmz_sobel3_dx_dyP9_IplImageS0_",
 ]
 
 

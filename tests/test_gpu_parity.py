@@ -636,9 +636,27 @@ def _run_dropin_caller(exe, oracle, tmp_path):
     fin, fout = str(tmp_path / "frames.bin"), str(tmp_path / "out.bin")
     frames.tofile(fin)
     subprocess.check_call([exe, fin, "8", "640", "480", fout])
-    dt = np.dtype([("rec", "<i4", 8), ("corners", "<f4", 8), ("scores", "<f4", 160), ("digits", "u1", 16), ("fb", "<f4", 2)])
+    dt = np.dtype([("rec", "<i4", 8), ("corners", "<f4", 8), ("scores", "<f4", 160), ("digits", "u1", 16), ("fb", "<f4", 2), ("fmt", "<u4", 6)])
     got = np.fromfile(fout, dt)
     want, cards = oracle.process_frames(frames, want_cards=True)
+
+    def wsum(a):  # compat_main's weighted_sum over the bytes of a
+        b = np.ascontiguousarray(a).view(np.uint8).ravel().astype(np.uint64)
+        return int((b * np.arange(1, b.size + 1, dtype=np.uint64)).sum() & 0xFFFFFFFF)
+
+    # the colour card (dmz_YCbCr_to_RGB on the card and its upsampled chroma), RGBA -> R, and the Cython stencil taps
+    for k in range(8):
+        if not want["all_found"][k]:
+            continue
+        cb, cr = np.ascontiguousarray(frames[k][::2, ::2]), np.ascontiguousarray(255 - frames[k][::2, ::2])
+        cbc = oracle.transform_card(cb, want["corners"][k], upsample=True)
+        crc = oracle.transform_card(cr, want["corners"][k], upsample=True)
+        rgb, rgba = oracle.ycbcr_to_rgb(cards[k], cbc, crc, 3), oracle.ycbcr_to_rgb(cards[k], cbc, crc, 4)
+        rows = sum((r + 1) * wsum(rgb[r]) for r in range(270)) & 0xFFFFFFFF
+        assert got["fmt"][k, 0] == rows, k
+        assert got["fmt"][k, 1] == wsum(rgba) and got["fmt"][k, 2] == wsum(rgba[..., 0]), k
+        for kind in range(3):
+            assert got["fmt"][k, 3 + kind] == wsum(oracle.stencil3(cards[k], kind)), (k, kind)
     assert np.array_equal(bits(got["fb"][:, 0]), bits(np.array([oracle.focus_score(f) for f in frames], np.float32)))
     assert np.array_equal(bits(got["fb"][:, 1]), bits(np.array([oracle.brightness_score(f) for f in frames], np.float32)))
     assert np.array_equal(got["rec"][:, 0], want["all_found"])
