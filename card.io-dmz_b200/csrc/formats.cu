@@ -11,6 +11,7 @@
 // differences and 16-bit pairs in one register.  Results are integers: bit-exact against the reference.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "b200_internal.h"
 
@@ -61,64 +62,102 @@ __device__ __forceinline__ void ycc4(unsigned int yw, unsigned int cbw, unsigned
   o.g[2] = __dp2a_lo(g_pair, g23, yc[2]) >> 14, o.g[3] = __dp2a_hi(g_pair, g23, yc[3]) >> 14;
 }
 
-// V pixels per work item (1: byte path for any shape; 4: 32-bit accesses; 16: 128-bit accesses), CH = 3 or 4
-template <int V, int CH>
+// V pixels per work item (1: byte path for any shape; 4: 32-bit accesses; 16: 128-bit accesses), CH = 3 or 4.
+// The output is dense, so the 32 items of a warp own one contiguous run of bytes; a lane's own 12 / 16 / 48 / 64 bytes
+// would be a strided store (every 32-byte sector written in halves by different instructions).  STAGED: the warp
+// transposes through shared memory (conflict-free slots, XOR-swizzled when a lane owns four units) and every store
+// instruction writes 128 / 512 contiguous bytes.  (Measured on B200, 8192 frames of 640x480: direct 5.6 TB/s,
+// staged -- see DESIGN.md section 10.)
+template <int V, int CH, bool STAGED>
 __global__ void __launch_bounds__(256)
 ycbcr_to_rgb_kernel(const uint8_t *__restrict__ y, int yrs, size_t yfs, const uint8_t *__restrict__ cb, const uint8_t *__restrict__ cr,
                     int crs, size_t cfs, int w, int h, size_t n, uint8_t *__restrict__ dst) {
+  constexpr int WPT = V >= 4 ? V / 4 * CH : 1;              // output words per item
+  constexpr int UW = V == 16 ? 4 : 1, UPT = WPT / UW;       // words per store unit (uint4 / u32), units per item: 3 or 4
+  __shared__ unsigned int s_stage[STAGED ? 8 * 32 * WPT : 1];
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (size_t)gridDim.x * blockDim.x;
+  const int lane = threadIdx.x & 31;
   const int wv = w / V;
   // (frame, row, column group) of this thread's item, advanced by the grid size without dividing again
-  const size_t per_frame = (size_t)h * wv;
+  const size_t per_frame = (size_t)h * wv, total = n * per_frame;
   size_t f = tid / per_frame;
   int row = (int)((tid - f * per_frame) / wv), xv = (int)(tid - f * per_frame - (size_t)row * wv);
   const size_t step_f = nthreads / per_frame;
   const int step_row = (int)((nthreads - step_f * per_frame) / wv), step_x = (int)(nthreads - step_f * per_frame - (size_t)step_row * wv);
-  for (; f < n; f += step_f, row += step_row, xv += step_x) {
+  for (size_t i = tid; i - lane < total; i += nthreads, f += step_f, row += step_row, xv += step_x) {  // warp-uniform trip count
     if (xv >= wv) xv -= wv, row++;
     if (row >= h) row -= h, f++;
-    if (f >= n) break;
+    const bool live = i < total;
     const int x = xv * V;
     const uint8_t *py = y + f * yfs + (size_t)row * yrs + x, *pb = cb + f * cfs + (size_t)row * crs + x, *pr = cr + f * cfs + (size_t)row * crs + x;
-    uint8_t *o = dst + ((f * h + row) * (size_t)w + x) * CH;
+    uint8_t *o = dst + i * (size_t)(V * CH);  // dense output: item i starts at byte i V CH
     if constexpr (V == 1) {
-      Rgb4 p;
-      ycc4(*py, *pb, *pr, p);
-      const unsigned int px = pack_sat_u8x4(p.r[0], p.g[0], p.b[0], 255);
-      o[0] = (uint8_t)px, o[1] = (uint8_t)(px >> 8), o[2] = (uint8_t)(px >> 16);
-      if (CH == 4) o[3] = 0xff;
-    } else {
-      unsigned int yw[V / 4], bw[V / 4], rw[V / 4], ow[V / 4 * CH];
-      if constexpr (V == 16) {
-        const uint4 a = __ldcs(reinterpret_cast<const uint4 *>(py)), b = __ldcs(reinterpret_cast<const uint4 *>(pb)),
-                    c = __ldcs(reinterpret_cast<const uint4 *>(pr));
-        yw[0] = a.x, yw[1] = a.y, yw[2] = a.z, yw[3] = a.w;
-        bw[0] = b.x, bw[1] = b.y, bw[2] = b.z, bw[3] = b.w;
-        rw[0] = c.x, rw[1] = c.y, rw[2] = c.z, rw[3] = c.w;
-      } else {
-        yw[0] = __ldcs(reinterpret_cast<const unsigned int *>(py)), bw[0] = __ldcs(reinterpret_cast<const unsigned int *>(pb));
-        rw[0] = __ldcs(reinterpret_cast<const unsigned int *>(pr));
-      }
-#pragma unroll
-      for (int q = 0; q < V / 4; q++) {
+      if (live) {
         Rgb4 p;
-        ycc4(yw[q], bw[q], rw[q], p);
-        if (CH == 3) {  // R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3
-          ow[3 * q + 0] = pack_sat_u8x4(p.r[0], p.g[0], p.b[0], p.r[1]);
-          ow[3 * q + 1] = pack_sat_u8x4(p.g[1], p.b[1], p.r[2], p.g[2]);
-          ow[3 * q + 2] = pack_sat_u8x4(p.b[2], p.r[3], p.g[3], p.b[3]);
+        ycc4(*py, *pb, *pr, p);
+        const unsigned int px = pack_sat_u8x4(p.r[0], p.g[0], p.b[0], 255);
+        o[0] = (uint8_t)px, o[1] = (uint8_t)(px >> 8), o[2] = (uint8_t)(px >> 16);
+        if (CH == 4) o[3] = 0xff;
+      }
+    } else {
+      unsigned int yw[V / 4], bw[V / 4], rw[V / 4], ow[WPT];
+      if (live) {
+        if constexpr (V == 16) {
+          const uint4 a = __ldcs(reinterpret_cast<const uint4 *>(py)), b = __ldcs(reinterpret_cast<const uint4 *>(pb)),
+                      c = __ldcs(reinterpret_cast<const uint4 *>(pr));
+          yw[0] = a.x, yw[1] = a.y, yw[2] = a.z, yw[3] = a.w;
+          bw[0] = b.x, bw[1] = b.y, bw[2] = b.z, bw[3] = b.w;
+          rw[0] = c.x, rw[1] = c.y, rw[2] = c.z, rw[3] = c.w;
         } else {
+          yw[0] = __ldcs(reinterpret_cast<const unsigned int *>(py)), bw[0] = __ldcs(reinterpret_cast<const unsigned int *>(pb));
+          rw[0] = __ldcs(reinterpret_cast<const unsigned int *>(pr));
+        }
 #pragma unroll
-          for (int k = 0; k < 4; k++) ow[4 * q + k] = pack_sat_u8x4(p.r[k], p.g[k], p.b[k], 255);
+        for (int q = 0; q < V / 4; q++) {
+          Rgb4 p;
+          ycc4(yw[q], bw[q], rw[q], p);
+          if (CH == 3) {  // R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3
+            ow[3 * q + 0] = pack_sat_u8x4(p.r[0], p.g[0], p.b[0], p.r[1]);
+            ow[3 * q + 1] = pack_sat_u8x4(p.g[1], p.b[1], p.r[2], p.g[2]);
+            ow[3 * q + 2] = pack_sat_u8x4(p.b[2], p.r[3], p.g[3], p.b[3]);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) ow[4 * q + k] = pack_sat_u8x4(p.r[k], p.g[k], p.b[k], 255);
+          }
         }
       }
-      if constexpr (V == 16 || CH == 4) {
+      if constexpr (!STAGED) {
+        if (live) {
+          if constexpr (V == 16 || CH == 4) {
 #pragma unroll
-        for (int k = 0; k < V / 4 * CH / 4; k++)
-          __stcs(reinterpret_cast<uint4 *>(o) + k, make_uint4(ow[4 * k], ow[4 * k + 1], ow[4 * k + 2], ow[4 * k + 3]));
+            for (int k = 0; k < WPT / 4; k++)
+              __stcs(reinterpret_cast<uint4 *>(o) + k, make_uint4(ow[4 * k], ow[4 * k + 1], ow[4 * k + 2], ow[4 * k + 3]));
+          } else {
+#pragma unroll
+            for (int k = 0; k < 3; k++) __stcs(reinterpret_cast<unsigned int *>(o) + k, ow[k]);
+          }
+        }
       } else {
+        // unit k of lane L lives in slot L UPT + (k ^ swizzle(L)); the swizzle only matters for UPT == 4 (strides of 3 are
+        // conflict-free as they are): 128-bit units are served a quarter warp at a time, 32-bit units a warp at a time
+        unsigned int *stage = s_stage + (threadIdx.x >> 5) * (32 * WPT);
+        auto slot = [](int L, int k) { return L * UPT + (UPT == 4 ? (k ^ ((L >> (UW == 4 ? 1 : 3)) & 3)) : k); };
 #pragma unroll
-        for (int k = 0; k < 3; k++) __stcs(reinterpret_cast<unsigned int *>(o) + k, ow[k]);
+        for (int k = 0; k < UPT; k++) {
+          if constexpr (UW == 4) reinterpret_cast<uint4 *>(stage)[slot(lane, k)] = make_uint4(ow[4 * k], ow[4 * k + 1], ow[4 * k + 2], ow[4 * k + 3]);
+          else stage[slot(lane, k)] = ow[k];
+        }
+        __syncwarp();
+        const size_t ubase = (i - lane) * UPT, utotal = total * UPT;  // first unit of the warp's run, units in the whole output
+#pragma unroll
+        for (int j = 0; j < UPT; j++) {
+          const int g = j * 32 + lane, L = g / UPT, k = g - L * UPT;
+          if (ubase + g < utotal) {
+            if constexpr (UW == 4) __stcs(reinterpret_cast<uint4 *>(dst) + ubase + g, reinterpret_cast<const uint4 *>(stage)[slot(L, k)]);
+            else __stcs(reinterpret_cast<unsigned int *>(dst) + ubase + g, stage[slot(L, k)]);
+          }
+        }
+        __syncwarp();
       }
     }
   }
@@ -168,48 +207,79 @@ __device__ __forceinline__ unsigned int hi_pair(unsigned int t) { return __byte_
 template <int KIND>
 __global__ void __launch_bounds__(kStThreads)
 stencil3_kernel(const uint8_t *__restrict__ src, int row_stride, size_t frame_stride, int w, int h, int tiles_x, int tiles_y,
-                size_t n_tiles, int16_t *__restrict__ out, int word_ok) {
+                unsigned int n_tiles, int16_t *__restrict__ out, int word_ok) {
   __shared__ unsigned int s_tile[(kTileH + 2) * kPitchW];
+  constexpr int kRowsPerWarp = (kTileH + 2 + 7) / 8;  // staging: warp wid takes tile rows wid, wid + 8, ..: lane = interior word
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const bool store8 = (w % 4 == 0) && ((uintptr_t)out % 8 == 0);
-  for (size_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-    const size_t f = t / ((size_t)tiles_x * tiles_y);
-    const int rem = (int)(t - f * ((size_t)tiles_x * tiles_y)), ty = rem / tiles_x, tx = rem - ty * tiles_x;
-    const int x0 = tx * kTileW, y0 = ty * kTileH;
-    const uint8_t *img = src + f * frame_stride;
-    // staged word (r, k) holds image columns x0 - 4 + 4 k .. + 3 of image row y0 - 1 + r, clamped
-    for (int i = threadIdx.x; i < (kTileH + 2) * kPitchW; i += kStThreads) {
-      const int r = i / kPitchW, k = i - r * kPitchW;
-      int gy = y0 - 1 + r;
-      gy = gy < 0 ? 0 : (gy > h - 1 ? h - 1 : gy);
-      const uint8_t *row = img + (size_t)gy * row_stride;
-      const int gx = x0 - 4 + 4 * k;
-      unsigned int v;
-      if (word_ok && gx >= 0 && gx + 3 < w) {
-        v = __ldg(reinterpret_cast<const unsigned int *>(row + gx));
-      } else {
-        v = 0;
+  const unsigned int tiles_per_frame = (unsigned)(tiles_x * tiles_y);
+  struct Tile {
+    unsigned int f;
+    int x0, y0;
+  };
+  auto decode = [&](unsigned int t) {
+    Tile T;
+    T.f = t / tiles_per_frame;
+    const unsigned int rem = t - T.f * tiles_per_frame, ty = rem / (unsigned)tiles_x;
+    T.x0 = (int)(rem - ty * tiles_x) * kTileW, T.y0 = (int)ty * kTileH;
+    return T;
+  };
+  // The next tile's words are fetched into registers while the current one is computed from shared memory.
+  // Interior word (r, lane + 1) = image columns x0 + 4 lane .. + 3 of row clamp(y0 - 1 + r); the two halo words of a row
+  // only ever contribute one byte each: p(max(x0 - 1, 0)) as byte 3 of word 0 and p(min(x0 + 128, w - 1)) as byte 0 of word 33.
+  unsigned int regs[kRowsPerWarp], halo = 0;
+  auto fetch = [&](const Tile &T) {
+    const uint8_t *img = src + (size_t)T.f * frame_stride;
+    const int gx = T.x0 + 4 * lane;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          int c = gx + j;
-          c = c < 0 ? 0 : (c > w - 1 ? w - 1 : c);
-          v |= (unsigned int)__ldg(row + c) << (8 * j);
+    for (int j = 0; j < kRowsPerWarp; j++) {
+      const int r = wid + 8 * j;
+      unsigned int v = 0;
+      if (r < kTileH + 2 && gx <= w) {  // (a word that starts right of column w is never read by a live output)
+        int gy = T.y0 - 1 + r;
+        gy = gy < 0 ? 0 : (gy > h - 1 ? h - 1 : gy);
+        const uint8_t *row = img + (size_t)gy * row_stride;
+        if (word_ok && gx + 3 < w) {
+          v = __ldg(reinterpret_cast<const unsigned int *>(row + gx));
+        } else {
+#pragma unroll
+          for (int b = 0; b < 4; b++) v |= (unsigned int)__ldg(row + (gx + b > w - 1 ? w - 1 : gx + b)) << (8 * b);
         }
       }
-      s_tile[i] = v;
+      regs[j] = v;
     }
+    if (threadIdx.x < 2 * (kTileH + 2)) {
+      const int r = threadIdx.x >> 1, right = threadIdx.x & 1;
+      int gy = T.y0 - 1 + r;
+      gy = gy < 0 ? 0 : (gy > h - 1 ? h - 1 : gy);
+      int c = right ? T.x0 + kTileW : T.x0 - 1;
+      c = c < 0 ? 0 : (c > w - 1 ? w - 1 : c);
+      halo = __ldg(img + (size_t)gy * row_stride + c);
+    }
+  };
+  auto stage = [&]() {
+#pragma unroll
+    for (int j = 0; j < kRowsPerWarp; j++)
+      if (wid + 8 * j < kTileH + 2) s_tile[(wid + 8 * j) * kPitchW + lane + 1] = regs[j];
+    if (threadIdx.x < 2 * (kTileH + 2)) {
+      const int r = threadIdx.x >> 1, right = threadIdx.x & 1;
+      s_tile[r * kPitchW + (right ? kPitchW - 1 : 0)] = right ? halo : halo << 24;
+    }
+  };
+  unsigned int t = blockIdx.x;
+  if (t < n_tiles) fetch(decode(t));
+  for (; t < n_tiles; t += gridDim.x) {
+    const Tile T = decode(t);
+    stage();
     __syncthreads();
-    const int x = x0 + 4 * lane;
+    if (t + gridDim.x < n_tiles) fetch(decode(t + gridDim.x));
+    const int x = T.x0 + 4 * lane;
     if (x < w) {
       // window of staged rows: index 0 = the row above the output row, 1 = the output row, 2 = the row below
       unsigned int a[3], b[3], c[3];  // KIND 0: t pairs (lo, hi) are kept in a / b;  KIND 1, 2: the words left / at / right
-      auto fetch = [&](int r, unsigned int &L, unsigned int &C, unsigned int &R) {
-        const unsigned int *p = s_tile + r * kPitchW + lane;
-        L = p[0], C = p[1], R = p[2];
-      };
       auto prepare = [&](int r, int slot) {
-        unsigned int L, C, R;
-        fetch(r, L, C, R);
+        const unsigned int *p = s_tile + r * kPitchW + lane;
+        const unsigned int L = p[0], C = p[1], R = p[2];
         if (KIND == 0) {
           const unsigned int tt = __vabsdiffu4(__byte_perm(C, R, 0x4321), __byte_perm(L, C, 0x6543));  // |p(x+1) - p(x-1)| x 4
           a[slot] = lo_pair(tt), b[slot] = hi_pair(tt);
@@ -218,12 +288,12 @@ stencil3_kernel(const uint8_t *__restrict__ src, int row_stride, size_t frame_st
         }
       };
       const int r0 = wid * 8;  // first output row of this warp inside the tile
+      int16_t *o = out + ((size_t)T.f * h + (T.y0 + r0)) * (size_t)w + x;
       prepare(r0, 0);
       prepare(r0 + 1, 1);
 #pragma unroll
-      for (int rr = 0; rr < 8; rr++) {
+      for (int rr = 0; rr < 8; rr++, o += w) {
         prepare(r0 + rr + 2, 2);
-        const int yy = y0 + r0 + rr;
         unsigned int o_lo, o_hi;
         if (KIND == 0) {
           o_lo = (a[0] + a[2]) * 3u + a[1] * 10u, o_hi = (b[0] + b[2]) * 3u + b[1] * 10u;
@@ -239,8 +309,7 @@ stencil3_kernel(const uint8_t *__restrict__ src, int row_stride, size_t frame_st
           const int v0 = (int)(o_lo & 0xFFFFu) - 1024, v1 = (int)(o_lo >> 16) - 1024, v2 = (int)(o_hi & 0xFFFFu) - 1024, v3 = (int)(o_hi >> 16) - 1024;
           o_lo = __byte_perm((unsigned)v0, (unsigned)v1, 0x5410), o_hi = __byte_perm((unsigned)v2, (unsigned)v3, 0x5410);
         }
-        if (yy < h) {
-          int16_t *o = out + (f * h + yy) * (size_t)w + x;
+        if (T.y0 + r0 + rr < h) {
           if (store8 && x + 3 < w) {
             __stcs(reinterpret_cast<uint2 *>(o), make_uint2(o_lo, o_hi));
           } else {
@@ -254,7 +323,7 @@ stencil3_kernel(const uint8_t *__restrict__ src, int row_stride, size_t frame_st
         if (KIND != 0) c[0] = c[1], c[1] = c[2];
       }
     }
-    __syncthreads();  // the tile is reused by the next trip
+    __syncthreads();  // the tile is overwritten by the next trip
   }
 }
 
@@ -266,18 +335,21 @@ int launch_ycbcr_to_rgb(const uint8_t *y, int yrs, size_t yfs, const uint8_t *cb
     return w % a == 0 && yrs % a == 0 && crs % a == 0 && yfs % a == 0 && cfs % a == 0 && (uintptr_t)y % a == 0 && (uintptr_t)cb % a == 0 &&
            (uintptr_t)cr % a == 0 && (uintptr_t)dst % a == 0;
   };
-  // a 4-channel word store of four pixels needs 16-byte destination alignment: rows are 4 w bytes, so w % 4 == 0 gives it
-  const int v = aligned(16) ? 16 : (aligned(4) && (channels == 3 || (uintptr_t)dst % 16 == 0) ? 4 : 1);
+  const int v = aligned(16) ? 16 : (aligned(4) ? 4 : 1);
+  static const bool direct = getenv("B200_DMZ_FORMATS_DIRECT") != nullptr;  // experiment switch: per-lane strided stores
   const size_t items = (size_t)n * h * (w / v);
   size_t blocks = (items + 255) / 256;
   const size_t cap = (size_t)sm_count() * 8;  // grid-stride: 8 CTAs x 256 threads per SM
   blocks = blocks > cap ? cap : (blocks < 1 ? 1 : blocks);
-#define YCC(V, CH) ycbcr_to_rgb_kernel<V, CH><<<(unsigned)blocks, 256, 0, s>>>(y, yrs, yfs, cb, cr, crs, cfs, w, h, (size_t)n, dst)
-  if (channels == 3) {
-    if (v == 16) YCC(16, 3); else if (v == 4) YCC(4, 3); else YCC(1, 3);
-  } else {
-    if (v == 16) YCC(16, 4); else if (v == 4) YCC(4, 4); else YCC(1, 4);
-  }
+#define YCC(V, CH, ST) ycbcr_to_rgb_kernel<V, CH, ST><<<(unsigned)blocks, 256, 0, s>>>(y, yrs, yfs, cb, cr, crs, cfs, w, h, (size_t)n, dst)
+#define YCC_V(CH)                                                          \
+  do {                                                                     \
+    if (v == 16) { if (direct) YCC(16, CH, false); else YCC(16, CH, true); } \
+    else if (v == 4) { if (direct && (CH == 3 || (uintptr_t)dst % 16 == 0)) YCC(4, CH, false); else YCC(4, CH, true); } \
+    else YCC(1, CH, false);                                                \
+  } while (0)
+  if (channels == 3) YCC_V(3); else YCC_V(4);
+#undef YCC_V
 #undef YCC
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
@@ -293,12 +365,19 @@ int launch_rgba_to_r(const uint8_t *src, size_t n_px, uint8_t *dst, cudaStream_t
 
 int launch_stencil3(const uint8_t *src, int row_stride, size_t frame_stride, int w, int h, int n, int kind, int16_t *out, cudaStream_t s) {
   const int tiles_x = (w + kTileW - 1) / kTileW, tiles_y = (h + kTileH - 1) / kTileH;
-  const size_t n_tiles = (size_t)n * tiles_x * tiles_y;
   const int word_ok = ((uintptr_t)src % 4 == 0) && (row_stride % 4 == 0) && (frame_stride % 4 == 0);
-  const size_t cap = (size_t)sm_count() * 8;
-  const unsigned blocks = (unsigned)(n_tiles > cap ? cap : n_tiles);
-  if (kind == 0) stencil3_kernel<0><<<blocks, kStThreads, 0, s>>>(src, row_stride, frame_stride, w, h, tiles_x, tiles_y, n_tiles, out, word_ok);
-  else if (kind == 1) stencil3_kernel<1><<<blocks, kStThreads, 0, s>>>(src, row_stride, frame_stride, w, h, tiles_x, tiles_y, n_tiles, out, word_ok);
-  else stencil3_kernel<2><<<blocks, kStThreads, 0, s>>>(src, row_stride, frame_stride, w, h, tiles_x, tiles_y, n_tiles, out, word_ok);
-  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+  const size_t cap = (size_t)sm_count() * 8, per_frame = (size_t)tiles_x * tiles_y;
+  const size_t max_frames = ((size_t)1 << 30) / per_frame > 0 ? ((size_t)1 << 30) / per_frame : 1;  // tile indices stay 32-bit
+  int launches = 0;
+  for (size_t f0 = 0; f0 < (size_t)n; f0 += max_frames, launches++) {
+    const size_t cnt = (size_t)n - f0 < max_frames ? (size_t)n - f0 : max_frames;
+    const unsigned int n_tiles = (unsigned int)(cnt * per_frame);
+    const unsigned blocks = (unsigned)(n_tiles > cap ? cap : n_tiles);
+    const uint8_t *p = src + f0 * frame_stride;
+    int16_t *o = out + f0 * (size_t)w * h;
+    if (kind == 0) stencil3_kernel<0><<<blocks, kStThreads, 0, s>>>(p, row_stride, frame_stride, w, h, tiles_x, tiles_y, n_tiles, o, word_ok);
+    else if (kind == 1) stencil3_kernel<1><<<blocks, kStThreads, 0, s>>>(p, row_stride, frame_stride, w, h, tiles_x, tiles_y, n_tiles, o, word_ok);
+    else stencil3_kernel<2><<<blocks, kStThreads, 0, s>>>(p, row_stride, frame_stride, w, h, tiles_x, tiles_y, n_tiles, o, word_ok);
+  }
+  return cudaGetLastError() == cudaSuccess ? launches : -1;
 }
