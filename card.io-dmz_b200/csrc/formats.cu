@@ -208,20 +208,26 @@ template <int KIND>
 __global__ void __launch_bounds__(kStThreads)
 stencil3_kernel(const uint8_t *__restrict__ src, int row_stride, size_t frame_stride, int w, int h, int tiles_x, int tiles_y,
                 unsigned int n_tiles, int16_t *__restrict__ out, int word_ok) {
-  __shared__ unsigned int s_tile[(kTileH + 2) * kPitchW];
+  // two tile buffers: staging tile k + 1 may start while other warps still compute tile k, so one barrier per tile is enough
+  // (the barrier after staging k + 1 is only passed once every warp has finished computing k - 1, the buffer's last user)
+  __shared__ unsigned int s_tile[2][(kTileH + 2) * kPitchW];
   constexpr int kRowsPerWarp = (kTileH + 2 + 7) / 8;  // staging: warp wid takes tile rows wid, wid + 8, ..: lane = interior word
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const bool store8 = (w % 4 == 0) && ((uintptr_t)out % 8 == 0);
-  const unsigned int tiles_per_frame = (unsigned)(tiles_x * tiles_y);
+  // tile walk: (frame, tile row, tile column) advanced by the grid size without dividing again
   struct Tile {
     unsigned int f;
-    int x0, y0;
+    int ty, tx;
   };
-  auto decode = [&](unsigned int t) {
-    Tile T;
-    T.f = t / tiles_per_frame;
-    const unsigned int rem = t - T.f * tiles_per_frame, ty = rem / (unsigned)tiles_x;
-    T.x0 = (int)(rem - ty * tiles_x) * kTileW, T.y0 = (int)ty * kTileH;
+  const unsigned int tiles_per_frame = (unsigned)(tiles_x * tiles_y);
+  Tile step;
+  step.f = gridDim.x / tiles_per_frame;
+  step.ty = (int)((gridDim.x - step.f * tiles_per_frame) / (unsigned)tiles_x);
+  step.tx = (int)(gridDim.x - step.f * tiles_per_frame) - step.ty * tiles_x;
+  auto advance = [&](Tile T) {
+    T.f += step.f, T.ty += step.ty, T.tx += step.tx;
+    if (T.tx >= tiles_x) T.tx -= tiles_x, T.ty++;
+    if (T.ty >= tiles_y) T.ty -= tiles_y, T.f++;
     return T;
   };
   // The next tile's words are fetched into registers while the current one is computed from shared memory.
@@ -230,55 +236,68 @@ stencil3_kernel(const uint8_t *__restrict__ src, int row_stride, size_t frame_st
   unsigned int regs[kRowsPerWarp], halo = 0;
   auto fetch = [&](const Tile &T) {
     const uint8_t *img = src + (size_t)T.f * frame_stride;
-    const int gx = T.x0 + 4 * lane;
+    const int x0 = T.tx * kTileW, y0 = T.ty * kTileH, gx = x0 + 4 * lane;
+    if (word_ok && y0 > 0 && y0 + kTileH < h && x0 + kTileW <= w) {  // no clamping anywhere inside the tile (block-uniform)
+      const uint8_t *p = img + (size_t)(y0 - 1 + wid) * row_stride + gx;
 #pragma unroll
-    for (int j = 0; j < kRowsPerWarp; j++) {
-      const int r = wid + 8 * j;
-      unsigned int v = 0;
-      if (r < kTileH + 2 && gx <= w) {  // (a word that starts right of column w is never read by a live output)
-        int gy = T.y0 - 1 + r;
-        gy = gy < 0 ? 0 : (gy > h - 1 ? h - 1 : gy);
-        const uint8_t *row = img + (size_t)gy * row_stride;
-        if (word_ok && gx + 3 < w) {
-          v = __ldg(reinterpret_cast<const unsigned int *>(row + gx));
-        } else {
+      for (int j = 0; j < kRowsPerWarp; j++, p += 8 * (size_t)row_stride)
+        regs[j] = wid + 8 * j < kTileH + 2 ? __ldg(reinterpret_cast<const unsigned int *>(p)) : 0u;
+    } else {
 #pragma unroll
-          for (int b = 0; b < 4; b++) v |= (unsigned int)__ldg(row + (gx + b > w - 1 ? w - 1 : gx + b)) << (8 * b);
+      for (int j = 0; j < kRowsPerWarp; j++) {
+        const int r = wid + 8 * j;
+        unsigned int v = 0;
+        if (r < kTileH + 2 && gx <= w) {  // (a word that starts right of column w is never read by a live output)
+          int gy = y0 - 1 + r;
+          gy = gy < 0 ? 0 : (gy > h - 1 ? h - 1 : gy);
+          const uint8_t *row = img + (size_t)gy * row_stride;
+          if (word_ok && gx + 3 < w) {
+            v = __ldg(reinterpret_cast<const unsigned int *>(row + gx));
+          } else {
+#pragma unroll
+            for (int b = 0; b < 4; b++) v |= (unsigned int)__ldg(row + (gx + b > w - 1 ? w - 1 : gx + b)) << (8 * b);
+          }
         }
+        regs[j] = v;
       }
-      regs[j] = v;
     }
     if (threadIdx.x < 2 * (kTileH + 2)) {
       const int r = threadIdx.x >> 1, right = threadIdx.x & 1;
-      int gy = T.y0 - 1 + r;
+      int gy = y0 - 1 + r;
       gy = gy < 0 ? 0 : (gy > h - 1 ? h - 1 : gy);
-      int c = right ? T.x0 + kTileW : T.x0 - 1;
+      int c = right ? x0 + kTileW : x0 - 1;
       c = c < 0 ? 0 : (c > w - 1 ? w - 1 : c);
       halo = __ldg(img + (size_t)gy * row_stride + c);
     }
   };
-  auto stage = [&]() {
+  auto stage = [&](unsigned int *tile) {
 #pragma unroll
     for (int j = 0; j < kRowsPerWarp; j++)
-      if (wid + 8 * j < kTileH + 2) s_tile[(wid + 8 * j) * kPitchW + lane + 1] = regs[j];
+      if (wid + 8 * j < kTileH + 2) tile[(wid + 8 * j) * kPitchW + lane + 1] = regs[j];
     if (threadIdx.x < 2 * (kTileH + 2)) {
       const int r = threadIdx.x >> 1, right = threadIdx.x & 1;
-      s_tile[r * kPitchW + (right ? kPitchW - 1 : 0)] = right ? halo : halo << 24;
+      tile[r * kPitchW + (right ? kPitchW - 1 : 0)] = right ? halo : halo << 24;
     }
   };
   unsigned int t = blockIdx.x;
-  if (t < n_tiles) fetch(decode(t));
-  for (; t < n_tiles; t += gridDim.x) {
-    const Tile T = decode(t);
-    stage();
+  Tile cur;
+  cur.f = t / tiles_per_frame;
+  cur.ty = (int)((t - cur.f * tiles_per_frame) / (unsigned)tiles_x), cur.tx = (int)(t - cur.f * tiles_per_frame) - cur.ty * tiles_x;
+  if (t < n_tiles) fetch(cur);
+  for (int buf = 0; t < n_tiles; t += gridDim.x, buf ^= 1) {
+    unsigned int *tile = s_tile[buf];
+    stage(tile);
     __syncthreads();
-    if (t + gridDim.x < n_tiles) fetch(decode(t + gridDim.x));
-    const int x = T.x0 + 4 * lane;
-    if (x < w) {
+    const Tile nxt = advance(cur);
+    if (t + gridDim.x < n_tiles) fetch(nxt);
+    const int x0 = cur.tx * kTileW, y0 = cur.ty * kTileH, x = x0 + 4 * lane;
+    const int r0 = wid * 8;                    // first output row of this warp inside the tile
+    const int rows_live = h - (y0 + r0);       // rows of this warp that exist in the image (>= 8: all of them)
+    if (x < w && rows_live > 0) {
       // window of staged rows: index 0 = the row above the output row, 1 = the output row, 2 = the row below
       unsigned int a[3], b[3], c[3];  // KIND 0: t pairs (lo, hi) are kept in a / b;  KIND 1, 2: the words left / at / right
       auto prepare = [&](int r, int slot) {
-        const unsigned int *p = s_tile + r * kPitchW + lane;
+        const unsigned int *p = tile + r * kPitchW + lane;
         const unsigned int L = p[0], C = p[1], R = p[2];
         if (KIND == 0) {
           const unsigned int tt = __vabsdiffu4(__byte_perm(C, R, 0x4321), __byte_perm(L, C, 0x6543));  // |p(x+1) - p(x-1)| x 4
@@ -287,8 +306,8 @@ stencil3_kernel(const uint8_t *__restrict__ src, int row_stride, size_t frame_st
           a[slot] = L, b[slot] = C, c[slot] = R;
         }
       };
-      const int r0 = wid * 8;  // first output row of this warp inside the tile
-      int16_t *o = out + ((size_t)T.f * h + (T.y0 + r0)) * (size_t)w + x;
+      const bool wide = store8 && x + 3 < w;
+      int16_t *o = out + ((size_t)cur.f * h + (y0 + r0)) * (size_t)w + x;
       prepare(r0, 0);
       prepare(r0 + 1, 1);
 #pragma unroll
@@ -309,8 +328,8 @@ stencil3_kernel(const uint8_t *__restrict__ src, int row_stride, size_t frame_st
           const int v0 = (int)(o_lo & 0xFFFFu) - 1024, v1 = (int)(o_lo >> 16) - 1024, v2 = (int)(o_hi & 0xFFFFu) - 1024, v3 = (int)(o_hi >> 16) - 1024;
           o_lo = __byte_perm((unsigned)v0, (unsigned)v1, 0x5410), o_hi = __byte_perm((unsigned)v2, (unsigned)v3, 0x5410);
         }
-        if (T.y0 + r0 + rr < h) {
-          if (store8 && x + 3 < w) {
+        if (rr < rows_live) {
+          if (wide) {
             __stcs(reinterpret_cast<uint2 *>(o), make_uint2(o_lo, o_hi));
           } else {
             const unsigned int ww[2] = {o_lo, o_hi};
@@ -323,7 +342,7 @@ stencil3_kernel(const uint8_t *__restrict__ src, int row_stride, size_t frame_st
         if (KIND != 0) c[0] = c[1], c[1] = c[2];
       }
     }
-    __syncthreads();  // the tile is overwritten by the next trip
+    cur = nxt;
   }
 }
 
@@ -335,23 +354,50 @@ int launch_ycbcr_to_rgb(const uint8_t *y, int yrs, size_t yfs, const uint8_t *cb
     return w % a == 0 && yrs % a == 0 && crs % a == 0 && yfs % a == 0 && cfs % a == 0 && (uintptr_t)y % a == 0 && (uintptr_t)cb % a == 0 &&
            (uintptr_t)cr % a == 0 && (uintptr_t)dst % a == 0;
   };
-  const int v = aligned(16) ? 16 : (aligned(4) ? 4 : 1);
-  static const bool direct = getenv("B200_DMZ_FORMATS_DIRECT") != nullptr;  // experiment switch: per-lane strided stores
-  const size_t items = (size_t)n * h * (w / v);
-  size_t blocks = (items + 255) / 256;
-  const size_t cap = (size_t)sm_count() * 8;  // grid-stride: 8 CTAs x 256 threads per SM
-  blocks = blocks > cap ? cap : (blocks < 1 ? 1 : blocks);
-#define YCC(V, CH, ST) ycbcr_to_rgb_kernel<V, CH, ST><<<(unsigned)blocks, 256, 0, s>>>(y, yrs, yfs, cb, cr, crs, cfs, w, h, (size_t)n, dst)
-#define YCC_V(CH)                                                          \
-  do {                                                                     \
-    if (v == 16) { if (direct) YCC(16, CH, false); else YCC(16, CH, true); } \
-    else if (v == 4) { if (direct && (CH == 3 || (uintptr_t)dst % 16 == 0)) YCC(4, CH, false); else YCC(4, CH, true); } \
-    else YCC(1, CH, false);                                                \
+  static const bool direct = getenv("B200_DMZ_FORMATS_DIRECT") != nullptr;  // experiment switch: per-lane strided stores everywhere
+#define YCC(V, CH, ST, Y, CB, CR, YRS, YFS, CRS, CFS, W_, H_, N_, DST)                                                         \
+  do {                                                                                                                       \
+    const size_t items_ = (size_t)(N_) * (H_) * ((W_) / V);                                                                  \
+    size_t blocks_ = (items_ + 255) / 256;                                                                                   \
+    const size_t cap_ = (size_t)sm_count() * 8; /* grid-stride: 8 CTAs x 256 threads per SM */                               \
+    blocks_ = blocks_ > cap_ ? cap_ : (blocks_ < 1 ? 1 : blocks_);                                                           \
+    ycbcr_to_rgb_kernel<V, CH, ST><<<(unsigned)blocks_, 256, 0, s>>>(Y, YRS, YFS, CB, CR, CRS, CFS, W_, H_, (size_t)(N_), DST); \
+    launches++;                                                                                                              \
   } while (0)
-  if (channels == 3) YCC_V(3); else YCC_V(4);
-#undef YCC_V
+#define YCC_CH(V, ST, ...)                                                  \
+  do {                                                                      \
+    if (channels == 3) YCC(V, 3, ST, __VA_ARGS__); else YCC(V, 4, ST, __VA_ARGS__); \
+  } while (0)
+  int launches = 0;
+  const size_t plane = (size_t)w * h, total = plane * n;
+  const bool dense = yrs == w && crs == w && (n == 1 || (yfs == plane && cfs == plane));
+  const bool base16 = (uintptr_t)y % 16 == 0 && (uintptr_t)cb % 16 == 0 && (uintptr_t)cr % 16 == 0 && (uintptr_t)dst % 16 == 0;
+  if (dense && base16 && total >= 16) {
+    // Dense planes are one flat run of pixels whatever the width (the arithmetic does not look at coordinates): 16-pixel
+    // items over "rows" of 16 pixels, in slabs whose row count fits an int; the last total % 16 pixels go through the byte path.
+    const size_t main_px = total & ~(size_t)15, slab = (size_t)1 << 34;
+    for (size_t p0 = 0; p0 < main_px; p0 += slab) {
+      const size_t cnt = main_px - p0 < slab ? main_px - p0 : slab;
+      if (direct) YCC_CH(16, false, y + p0, cb + p0, cr + p0, 16, cnt, 16, cnt, 16, (int)(cnt / 16), 1, dst + p0 * channels);
+      else YCC_CH(16, true, y + p0, cb + p0, cr + p0, 16, cnt, 16, cnt, 16, (int)(cnt / 16), 1, dst + p0 * channels);
+    }
+    if (total > main_px) {
+      const int tail = (int)(total - main_px);
+      YCC_CH(1, false, y + main_px, cb + main_px, cr + main_px, tail, (size_t)tail, tail, (size_t)tail, tail, 1, 1, dst + main_px * channels);
+    }
+  } else if (aligned(16)) {
+    if (direct) YCC_CH(16, false, y, cb, cr, yrs, yfs, crs, cfs, w, h, n, dst);
+    else YCC_CH(16, true, y, cb, cr, yrs, yfs, crs, cfs, w, h, n, dst);
+  } else if (aligned(4)) {
+    // four pixels per item: the transposed stores cost more than they save here (measured: 3.4 vs 4.8 TB/s on 428-wide cards)
+    if (channels == 3 || (uintptr_t)dst % 16 == 0) YCC_CH(4, false, y, cb, cr, yrs, yfs, crs, cfs, w, h, n, dst);
+    else YCC_CH(4, true, y, cb, cr, yrs, yfs, crs, cfs, w, h, n, dst);
+  } else {
+    YCC_CH(1, false, y, cb, cr, yrs, yfs, crs, cfs, w, h, n, dst);
+  }
+#undef YCC_CH
 #undef YCC
-  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+  return cudaGetLastError() == cudaSuccess ? launches : -1;
 }
 
 int launch_rgba_to_r(const uint8_t *src, size_t n_px, uint8_t *dst, cudaStream_t s) {
