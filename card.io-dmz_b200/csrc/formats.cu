@@ -24,6 +24,15 @@ inline int sm_count() {
   return sms;
 }
 
+// Grid-stride kernels are launched with exactly the CTAs that can be resident (SMs x occupancy): a larger grid runs a
+// partial second wave on a mostly idle GPU (measured on the stencils: 1184 CTAs over 888 slots cost a third of the time).
+template <typename Kernel>
+inline size_t resident_ctas(Kernel kernel, int threads) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+  return (size_t)sm_count() * per_sm;
+}
+
 // ------------------------------------------------------------------------------------------------
 // YCbCr -> RGB(A).  Per pixel (convert.cpp:480-487), with sCb = Cb - 128, sCr = Cr - 128 as int8:
 //   B = sat8(Y + ((sCb * 29049                + 8192) >> 14))
@@ -359,7 +368,7 @@ int launch_ycbcr_to_rgb(const uint8_t *y, int yrs, size_t yfs, const uint8_t *cb
   do {                                                                                                                       \
     const size_t items_ = (size_t)(N_) * (H_) * ((W_) / V);                                                                  \
     size_t blocks_ = (items_ + 255) / 256;                                                                                   \
-    const size_t cap_ = (size_t)sm_count() * 8; /* grid-stride: 8 CTAs x 256 threads per SM */                               \
+    const size_t cap_ = resident_ctas(ycbcr_to_rgb_kernel<V, CH, ST>, 256);                                                  \
     blocks_ = blocks_ > cap_ ? cap_ : (blocks_ < 1 ? 1 : blocks_);                                                           \
     ycbcr_to_rgb_kernel<V, CH, ST><<<(unsigned)blocks_, 256, 0, s>>>(Y, YRS, YFS, CB, CR, CRS, CFS, W_, H_, (size_t)(N_), DST); \
     launches++;                                                                                                              \
@@ -403,7 +412,7 @@ int launch_ycbcr_to_rgb(const uint8_t *y, int yrs, size_t yfs, const uint8_t *cb
 int launch_rgba_to_r(const uint8_t *src, size_t n_px, uint8_t *dst, cudaStream_t s) {
   const int vec_ok = ((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 4 == 0);
   size_t blocks = ((n_px >> 4) + 255) / 256;  // a thread moves 16 pixels per step
-  const size_t cap = (size_t)sm_count() * 8;
+  const size_t cap = resident_ctas(rgba_to_r_kernel, 256);
   blocks = blocks > cap ? cap : (blocks < 1 ? 1 : blocks);
   rgba_to_r_kernel<<<(unsigned)blocks, 256, 0, s>>>(src, dst, n_px, vec_ok);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
@@ -412,7 +421,9 @@ int launch_rgba_to_r(const uint8_t *src, size_t n_px, uint8_t *dst, cudaStream_t
 int launch_stencil3(const uint8_t *src, int row_stride, size_t frame_stride, int w, int h, int n, int kind, int16_t *out, cudaStream_t s) {
   const int tiles_x = (w + kTileW - 1) / kTileW, tiles_y = (h + kTileH - 1) / kTileH;
   const int word_ok = ((uintptr_t)src % 4 == 0) && (row_stride % 4 == 0) && (frame_stride % 4 == 0);
-  const size_t cap = (size_t)sm_count() * 8, per_frame = (size_t)tiles_x * tiles_y;
+  const size_t cap = kind == 0 ? resident_ctas(stencil3_kernel<0>, kStThreads) : kind == 1 ? resident_ctas(stencil3_kernel<1>, kStThreads)
+                                                                                              : resident_ctas(stencil3_kernel<2>, kStThreads);
+  const size_t per_frame = (size_t)tiles_x * tiles_y;
   const size_t max_frames = ((size_t)1 << 30) / per_frame > 0 ? ((size_t)1 << 30) / per_frame : 1;  // tile indices stay 32-bit
   int launches = 0;
   for (size_t f0 = 0; f0 < (size_t)n; f0 += max_frames, launches++) {

@@ -14,8 +14,8 @@ PY
 }
 ( timeout 600 python bench.py --config formats --steps 5 --warmup 3 > gpurun_out/${tag}_formats.json ) 2> gpurun_out/${tag}_formats.err
 tail -3 gpurun_out/${tag}_formats.err; show gpurun_out/${tag}_formats.json
-( B200_DMZ_FORMATS_DIRECT=1 timeout 600 python bench.py --config formats --steps 5 --warmup 3 --no-e2e --no-cpu > gpurun_out/${tag}_formats_direct.json ) 2>> gpurun_out/${tag}_formats.err
-echo "== direct stores"; show gpurun_out/${tag}_formats_direct.json
+[ -n "$WITH_DIRECT" ] && ( B200_DMZ_FORMATS_DIRECT=1 timeout 600 python bench.py --config formats --steps 5 --warmup 3 --no-e2e --no-cpu > gpurun_out/${tag}_formats_direct.json ) 2>> gpurun_out/${tag}_formats.err
+[ -n "$WITH_DIRECT" ] && echo "== direct stores" && show gpurun_out/${tag}_formats_direct.json
 ( timeout 600 python bench.py --impl reference --config formats --steps 3 --warmup 1 > gpurun_out/${tag}_formats_ref.json ) 2>> gpurun_out/${tag}_formats.err
 if [ -z "$NO_NCU" ]; then
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:"ycbcr_to_rgb_kernel|rgba_to_r_kernel|stencil3_kernel" -c 7 \
