@@ -1,4 +1,4 @@
-// formats.cu -- the pixel-format steps either side of the detect -> warp -> OCR path (widening rows, DESIGN.md section 10):
+// formats.cu -- the pixel-format steps either side of the detect -> warp -> OCR path (widening rows, DESIGN.md section 11):
 //
 //   ycbcr_to_rgb_kernel   dmz_YCbCr_to_RGB            dmz.cpp:58-64 -> llcv_YCbCr2RGB_u8_c, cv/convert.cpp:449-504
 //   rgba_to_r_kernel      dmz_deinterleave_RGBA_to_R  dmz.cpp:66-109
@@ -76,7 +76,7 @@ __device__ __forceinline__ void ycc4(unsigned int yw, unsigned int cbw, unsigned
 // would be a strided store (every 32-byte sector written in halves by different instructions).  STAGED: the warp
 // transposes through shared memory (conflict-free slots, XOR-swizzled when a lane owns four units) and every store
 // instruction writes 128 / 512 contiguous bytes.  (Measured on B200, 8192 frames of 640x480: direct 5.6 TB/s,
-// staged -- see DESIGN.md section 10.)
+// staged -- see DESIGN.md section 11.)
 template <int V, int CH, bool STAGED>
 __global__ void __launch_bounds__(256)
 ycbcr_to_rgb_kernel(const uint8_t *__restrict__ y, int yrs, size_t yfs, const uint8_t *__restrict__ cb, const uint8_t *__restrict__ cr,

@@ -194,7 +194,7 @@ int b200_vseg_rows_batch(b200_ctx *ctx, const uint8_t *cards, int n, int mem, fl
 int b200_deinterleave_c2_batch(b200_ctx *ctx, const uint8_t *interleaved, int row_stride, size_t frame_stride, int width, int height,
                                int n, int mem, uint8_t *channel1, uint8_t *channel2);
 
-/* ---- pixel formats either side of the path (the widening after SURVEY 8f's four rows; DESIGN.md section 10) ----
+/* ---- pixel formats either side of the path (the widening after SURVEY 8f's four rows; DESIGN.md section 11) ----
  * dmz_YCbCr_to_RGB (dmz.h:72, dmz.cpp:58-64 -> llcv_YCbCr2RGB_u8_c, cv/convert.cpp:449-504): n triples of SAME-SIZED
  * u8 planes (the SDK converts the warped card: Cb / Cr come out of dmz_transform_card with upsample = true) into
  * interleaved R, G, B bytes, or R, G, B, 255 when channels == 4 (the reference keys that on dst->nChannels).

@@ -9,7 +9,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
-PAT = re.compile(r"\b(UTMALDG|UTMASTG|UTMAPF|UTCIMMA|UTCHMMA|UTCQMMA|LDTM|STTM|UTCBAR|UTCATOMSWS|UTCCP|SYNCS|LDGSTS|VIMNMX3?|FFMA2|REDUX)\b[\.\w]*")
+PAT = re.compile(r"\b(UTMALDG|UTMASTG|UTMAPF|UTCIMMA|UTCHMMA|UTCQMMA|LDTM|STTM|UTCBAR|UTCATOMSWS|UTCCP|SYNCS|LDGSTS|VIMNMX3?|FFMA2|REDUX|IDP|I2IP|VABSDIFF4)\b[\.\w]*")
 SHOW = ("UTMALDG", "UTCIMMA", "UTCHMMA", "LDTM", "UTCBAR", "UTCATOMSWS")
 out = ["# %s SASS evidence (cuobjdump -sass of the objects linked into card.io-dmz_b200/libb200dmz.so; sm_100a)\n" % tag,
        "Counts of the Blackwell / Hopper-class opcodes per kernel, then the instruction lines themselves.\n"]
