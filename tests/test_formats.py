@@ -110,3 +110,68 @@ def test_stencil3_exact(dmz, oracle, golden_formats):
             out = dmz.stencil3(img, kind)
             for k in range(n):
                 assert np.array_equal(out[k], oracle.stencil3(img[k], kind)), (n, h, w, kind, k)
+
+
+@pytest.mark.gpu
+def test_formats_strided_device_planes(dmz, oracle):
+    """Device pointers with padded rows / frames (B200_MEM_DEVICE): the row-wise 16-pixel, 4-pixel and byte paths of the
+    colour conversion (dense host planes always take the flat path) and the stencils' word / byte staging."""
+    import torch
+    from util import load_pkg
+    mem_device = load_pkg().MEM_DEVICE
+    rng = np.random.default_rng(12)
+    # (w, h, row stride, extra bytes between frames, byte offset of the base pointer)
+    shapes = [(64, 9, 80, 0, 0), (64, 9, 80, 160, 0), (60, 7, 64, 0, 0), (60, 7, 64, 64, 4), (61, 5, 70, 3, 0), (32, 4, 32, 16, 0), (48, 3, 48, 0, 1)]
+    for (w, h, rs, gap, off) in shapes:
+        n = 3
+        fs = rs * h + gap
+        host = [rng.integers(0, 256, off + n * fs + 16, dtype=np.uint8) for _ in range(3)]
+        dev = [torch.from_numpy(a).cuda() for a in host]
+        planes = [np.stack([a[off + k * fs: off + k * fs + rs * h].reshape(h, rs)[:, :w] for k in range(n)]) for a in host]
+        for ch in (3, 4):
+            out = torch.zeros(n * h * w * ch + 32, dtype=torch.uint8, device="cuda")
+            dmz._check(dmz.lib.b200_ycbcr_to_rgb_batch(dmz.ctx, dev[0].data_ptr() + off, rs, fs, dev[1].data_ptr() + off, dev[2].data_ptr() + off, rs, fs,
+                                                       w, h, n, ch, mem_device, out.data_ptr()))
+            got = out.cpu().numpy()
+            assert not got[n * h * w * ch:].any()
+            got = got[: n * h * w * ch].reshape(n, h, w, ch)
+            for k in range(n):
+                assert np.array_equal(got[k], oracle.ycbcr_to_rgb(planes[0][k], planes[1][k], planes[2][k], ch)), (w, h, rs, gap, off, ch, k)
+            if w % 4 == 0:  # a destination that is only 4-byte aligned (RGBA then takes the 4-pixel kernel's transposed stores)
+                out.zero_()
+                dmz._check(dmz.lib.b200_ycbcr_to_rgb_batch(dmz.ctx, dev[0].data_ptr() + off, rs, fs, dev[1].data_ptr() + off, dev[2].data_ptr() + off, rs, fs,
+                                                           w, h, n, ch, mem_device, out.data_ptr() + 4))
+                got4 = out.cpu().numpy()
+                assert not got4[:4].any() and not got4[4 + n * h * w * ch:].any()
+                assert np.array_equal(got4[4: 4 + n * h * w * ch].reshape(n, h, w, ch), got)
+        for kind in range(3):
+            out = torch.zeros(n * h * w + 16, dtype=torch.int16, device="cuda")
+            dmz._check(dmz.lib.b200_stencil3_batch(dmz.ctx, dev[0].data_ptr() + off, rs, fs, w, h, n, kind, mem_device, out.data_ptr()))
+            got = out.cpu().numpy()
+            assert not got[n * h * w:].any()
+            got = got[: n * h * w].reshape(n, h, w)
+            for k in range(n):
+                assert np.array_equal(got[k], oracle.stencil3(planes[0][k], kind)), (w, h, rs, gap, off, kind, k)
+    # larger strided frames: several tiles per frame, interior (unclamped) tiles included, rows padded to 704
+    w, h, rs, n = 640, 200, 704, 2
+    host = rng.integers(0, 256, n * rs * h, dtype=np.uint8)
+    dev = torch.from_numpy(host).cuda()
+    planes = host.reshape(n, h, rs)[:, :, :w]
+    for kind in range(3):
+        out = torch.zeros(n * h * w, dtype=torch.int16, device="cuda")
+        dmz._check(dmz.lib.b200_stencil3_batch(dmz.ctx, dev.data_ptr(), rs, rs * h, w, h, n, kind, mem_device, out.data_ptr()))
+        got = out.cpu().numpy().reshape(n, h, w)
+        for k in range(n):
+            assert np.array_equal(got[k], oracle.stencil3(np.ascontiguousarray(planes[k]), kind)), (kind, k)
+
+
+@pytest.mark.gpu
+def test_formats_bad_arguments(dmz):
+    y = np.zeros((1, 4, 4), np.uint8)
+    with pytest.raises(Exception):
+        dmz.ycbcr_to_rgb(y, y, y, channels=2)
+    with pytest.raises(Exception):
+        dmz.stencil3(y, 3)
+    out = np.zeros(16, np.uint8)
+    assert dmz.lib.b200_rgba_to_r_batch(dmz.ctx, None, 4, 0, out.ctypes.data) != 0
+    assert dmz.lib.b200_ycbcr_to_rgb_batch(dmz.ctx, y.ctypes.data, 3, 16, y.ctypes.data, y.ctypes.data, 4, 16, 4, 4, 1, 3, 0, out.ctypes.data) != 0  # row stride < width

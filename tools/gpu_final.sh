@@ -6,6 +6,9 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --fo
 ( timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -15 ) > gpurun_out/${tag}_tests.txt; tail -3 gpurun_out/${tag}_tests.txt
 ( timeout 900 python bench.py > gpurun_out/${tag}_bench.json ) 2> gpurun_out/${tag}_bench.err; tail -2 gpurun_out/${tag}_bench.err
 ( timeout 300 python bench.py --impl reference > gpurun_out/${tag}_bench_ref.json ) 2> gpurun_out/${tag}_bench_ref.err
+( timeout 600 python bench.py --config formats --steps 5 --warmup 3 > gpurun_out/${tag}_formats.json ) 2> gpurun_out/${tag}_formats.err
+( timeout 300 python bench.py --impl reference --config formats --steps 3 --warmup 1 > gpurun_out/${tag}_formats_ref.json ) 2>> gpurun_out/${tag}_formats.err
+bash tools/gpu_sanitize_formats.sh 2>&1 | tail -8
 ( timeout 600 python bench.py --config categorize > gpurun_out/${tag}_categorize.json ) 2> gpurun_out/${tag}_categorize.err
 ( timeout 900 python bench.py --config detect-sweep --steps 2 > gpurun_out/${tag}_detect_sweep.json ) 2> gpurun_out/${tag}_detect_sweep.err
 ( timeout 300 python tools/gpu_side_bench.py 262144 > gpurun_out/${tag}_side.json ) 2> gpurun_out/${tag}_side.err
