@@ -69,9 +69,10 @@ def build(force=False):
     if force or newer(lat, [lat_src, lib, os.path.join(ROOT, "include", "dmz_b200_compat.h")]):
         run(["g++", "-std=c++14", "-O2", "-I" + os.path.join(ROOT, "include"), lat_src, "-o", lat, "-L" + HERE, "-lb200dmz",
              "-Wl,-rpath,$ORIGIN/..", "-ldl"])
-    # device-side checks of the primitives (tools/microbench: tcgen05 kind::i8 against a host product; FFMA / FFMA2 rates)
+    # device-side checks of the primitives (tools/microbench: tcgen05 kind::i8 against a host product; FFMA / FFMA2 rates;
+    # h2d_pitched: what the host-buffer path's upload rectangle can reach over PCIe -- DMA, several streams, zero-copy, hybrids)
     mb = os.path.join(ROOT, "tools", "microbench")
-    for name, extra in (("umma_i8", ["-I" + CSRC]), ("ffma2", [])):
+    for name, extra in (("umma_i8", ["-I" + CSRC]), ("ffma2", []), ("h2d_pitched", ["-std=c++17"])):
         src, exe = os.path.join(mb, name + ".cu"), os.path.join(mb, name)
         if os.path.exists(src) and (force or newer(exe, [src, os.path.join(CSRC, "umma.cuh")])):
             run([nvcc] + ARCH + ["-O2", "-o", exe, src] + extra)
