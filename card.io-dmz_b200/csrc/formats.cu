@@ -213,6 +213,59 @@ constexpr int kTileW = 128, kTileH = 64, kStThreads = 256, kPitchW = kTileW / 4 
 __device__ __forceinline__ unsigned int lo_pair(unsigned int t) { return __byte_perm(t, 0u, 0x4140); }  // (t0, t1) as u16 x 2
 __device__ __forceinline__ unsigned int hi_pair(unsigned int t) { return __byte_perm(t, 0u, 0x4342); }  // (t2, t3)
 
+// Eight output rows x four pixels of one thread, from a sliding three-row window of the staged tile.  FAST: every row and
+// all four pixels exist and the 8-byte store is aligned -- a straight-line body (the generic one carries per-row and per-pixel
+// tests; keeping them out of this path halves the instructions of the kernel's hot loop).
+template <int KIND, bool FAST>
+__device__ __forceinline__ void stencil_band(const unsigned int *__restrict__ tile, int lane, int r0, int16_t *__restrict__ o, int w, int x,
+                                             int rows_live) {
+  // window of staged rows: index 0 = the row above the output row, 1 = the output row, 2 = the row below
+  unsigned int a[3], b[3], c[3];  // KIND 0: t pairs (lo, hi) are kept in a / b;  KIND 1, 2: the words left / at / right
+  auto prepare = [&](int r, int slot) {
+    const unsigned int *p = tile + r * kPitchW + lane;
+    const unsigned int L = p[0], C = p[1], R = p[2];
+    if (KIND == 0) {
+      const unsigned int tt = __vabsdiffu4(__byte_perm(C, R, 0x4321), __byte_perm(L, C, 0x6543));  // |p(x+1) - p(x-1)| x 4
+      a[slot] = lo_pair(tt), b[slot] = hi_pair(tt);
+    } else {
+      a[slot] = L, b[slot] = C, c[slot] = R;
+    }
+  };
+  const unsigned int row_bytes = 2u * (unsigned int)w;
+  prepare(r0, 0);
+  prepare(r0 + 1, 1);
+#pragma unroll
+  for (int rr = 0; rr < 8; rr++) {
+    prepare(r0 + rr + 2, 2);
+    unsigned int o_lo, o_hi;
+    if (KIND == 0) {
+      o_lo = (a[0] + a[2]) * 3u + a[1] * 10u, o_hi = (b[0] + b[2]) * 3u + b[1] * 10u;
+    } else if (KIND == 1) {
+      const unsigned int tL = __vabsdiffu4(a[2], a[0]), tC = __vabsdiffu4(b[2], b[0]), tR = __vabsdiffu4(c[2], c[0]);
+      const unsigned int tl = __byte_perm(tL, tC, 0x6543), tr = __byte_perm(tC, tR, 0x4321);  // t(x-1), t(x+1)
+      o_lo = (lo_pair(tl) + lo_pair(tr)) * 3u + lo_pair(tC) * 10u, o_hi = (hi_pair(tl) + hi_pair(tr)) * 3u + hi_pair(tC) * 10u;
+    } else {
+      const unsigned int ul = __byte_perm(a[0], b[0], 0x6543), ur = __byte_perm(b[0], c[0], 0x4321);  // row above: p(x-1), p(x+1)
+      const unsigned int dl = __byte_perm(a[2], b[2], 0x6543), dr = __byte_perm(b[2], c[2], 0x4321);  // row below
+      o_lo = lo_pair(ul) + lo_pair(dr) + 0x04000400u - lo_pair(ur) - lo_pair(dl);
+      o_hi = hi_pair(ul) + hi_pair(dr) + 0x04000400u - hi_pair(ur) - hi_pair(dl);
+      const int v0 = (int)(o_lo & 0xFFFFu) - 1024, v1 = (int)(o_lo >> 16) - 1024, v2 = (int)(o_hi & 0xFFFFu) - 1024, v3 = (int)(o_hi >> 16) - 1024;
+      o_lo = __byte_perm((unsigned)v0, (unsigned)v1, 0x5410), o_hi = __byte_perm((unsigned)v2, (unsigned)v3, 0x5410);
+    }
+    int16_t *orow = reinterpret_cast<int16_t *>(reinterpret_cast<char *>(o) + (unsigned int)rr * row_bytes);  // (one IMAD.WIDE per row)
+    if (FAST) {
+      __stcs(reinterpret_cast<uint2 *>(orow), make_uint2(o_lo, o_hi));
+    } else if (rr < rows_live) {
+      const unsigned int ww[2] = {o_lo, o_hi};
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        if (x + j < w) orow[j] = (int16_t)(ww[j >> 1] >> (16 * (j & 1)));
+    }
+    a[0] = a[1], a[1] = a[2], b[0] = b[1], b[1] = b[2];
+    if (KIND != 0) c[0] = c[1], c[1] = c[2];
+  }
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(kStThreads)
 stencil3_kernel(const uint8_t *__restrict__ src, int row_stride, size_t frame_stride, int w, int h, int tiles_x, int tiles_y,
@@ -303,53 +356,9 @@ stencil3_kernel(const uint8_t *__restrict__ src, int row_stride, size_t frame_st
     const int r0 = wid * 8;                    // first output row of this warp inside the tile
     const int rows_live = h - (y0 + r0);       // rows of this warp that exist in the image (>= 8: all of them)
     if (x < w && rows_live > 0) {
-      // window of staged rows: index 0 = the row above the output row, 1 = the output row, 2 = the row below
-      unsigned int a[3], b[3], c[3];  // KIND 0: t pairs (lo, hi) are kept in a / b;  KIND 1, 2: the words left / at / right
-      auto prepare = [&](int r, int slot) {
-        const unsigned int *p = tile + r * kPitchW + lane;
-        const unsigned int L = p[0], C = p[1], R = p[2];
-        if (KIND == 0) {
-          const unsigned int tt = __vabsdiffu4(__byte_perm(C, R, 0x4321), __byte_perm(L, C, 0x6543));  // |p(x+1) - p(x-1)| x 4
-          a[slot] = lo_pair(tt), b[slot] = hi_pair(tt);
-        } else {
-          a[slot] = L, b[slot] = C, c[slot] = R;
-        }
-      };
-      const bool wide = store8 && x + 3 < w;
       int16_t *o = out + ((size_t)cur.f * h + (y0 + r0)) * (size_t)w + x;
-      prepare(r0, 0);
-      prepare(r0 + 1, 1);
-#pragma unroll
-      for (int rr = 0; rr < 8; rr++, o += w) {
-        prepare(r0 + rr + 2, 2);
-        unsigned int o_lo, o_hi;
-        if (KIND == 0) {
-          o_lo = (a[0] + a[2]) * 3u + a[1] * 10u, o_hi = (b[0] + b[2]) * 3u + b[1] * 10u;
-        } else if (KIND == 1) {
-          const unsigned int tL = __vabsdiffu4(a[2], a[0]), tC = __vabsdiffu4(b[2], b[0]), tR = __vabsdiffu4(c[2], c[0]);
-          const unsigned int tl = __byte_perm(tL, tC, 0x6543), tr = __byte_perm(tC, tR, 0x4321);  // t(x-1), t(x+1)
-          o_lo = (lo_pair(tl) + lo_pair(tr)) * 3u + lo_pair(tC) * 10u, o_hi = (hi_pair(tl) + hi_pair(tr)) * 3u + hi_pair(tC) * 10u;
-        } else {
-          const unsigned int ul = __byte_perm(a[0], b[0], 0x6543), ur = __byte_perm(b[0], c[0], 0x4321);  // row above: p(x-1), p(x+1)
-          const unsigned int dl = __byte_perm(a[2], b[2], 0x6543), dr = __byte_perm(b[2], c[2], 0x4321);  // row below
-          o_lo = lo_pair(ul) + lo_pair(dr) + 0x04000400u - lo_pair(ur) - lo_pair(dl);
-          o_hi = hi_pair(ul) + hi_pair(dr) + 0x04000400u - hi_pair(ur) - hi_pair(dl);
-          const int v0 = (int)(o_lo & 0xFFFFu) - 1024, v1 = (int)(o_lo >> 16) - 1024, v2 = (int)(o_hi & 0xFFFFu) - 1024, v3 = (int)(o_hi >> 16) - 1024;
-          o_lo = __byte_perm((unsigned)v0, (unsigned)v1, 0x5410), o_hi = __byte_perm((unsigned)v2, (unsigned)v3, 0x5410);
-        }
-        if (rr < rows_live) {
-          if (wide) {
-            __stcs(reinterpret_cast<uint2 *>(o), make_uint2(o_lo, o_hi));
-          } else {
-            const unsigned int ww[2] = {o_lo, o_hi};
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-              if (x + j < w) o[j] = (int16_t)(ww[j >> 1] >> (16 * (j & 1)));
-          }
-        }
-        a[0] = a[1], a[1] = a[2], b[0] = b[1], b[1] = b[2];
-        if (KIND != 0) c[0] = c[1], c[1] = c[2];
-      }
+      if (store8 && x + 3 < w && rows_live >= 8) stencil_band<KIND, true>(tile, lane, r0, o, w, x, rows_live);
+      else stencil_band<KIND, false>(tile, lane, r0, o, w, x, rows_live);
     }
     cur = nxt;
   }
