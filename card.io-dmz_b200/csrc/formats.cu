@@ -218,14 +218,12 @@ __device__ __forceinline__ unsigned int hi_pair(unsigned int t) { return __byte_
 // tests; keeping them out of this path halves the instructions of the kernel's hot loop).
 template <int KIND, bool FAST>
 __device__ __forceinline__ void stencil_band(const unsigned int *__restrict__ tile, int lane, int r0, int16_t *__restrict__ o, int w, int x,
-                                             int rows_live, bool fix_left, bool fix_right) {
+                                             int rows_live) {
   // window of staged rows: index 0 = the row above the output row, 1 = the output row, 2 = the row below
   unsigned int a[3], b[3], c[3];  // KIND 0: t pairs (lo, hi) are kept in a / b;  KIND 1, 2: the words left / at / right
   auto prepare = [&](int r, int slot) {
     const unsigned int *p = tile + r * kPitchW + lane;
-    unsigned int L = p[0], C = p[1], R = p[2];
-    if (fix_left) L = C << 24;   // x == 0 on the asynchronous path: p(-1) := p(0)
-    if (fix_right) R = C >> 24;  // x + 4 == w there: p(w) := p(w - 1)
+    const unsigned int L = p[0], C = p[1], R = p[2];
     if (KIND == 0) {
       const unsigned int tt = __vabsdiffu4(__byte_perm(C, R, 0x4321), __byte_perm(L, C, 0x6543));  // |p(x+1) - p(x-1)| x 4
       a[slot] = lo_pair(tt), b[slot] = hi_pair(tt);
@@ -268,26 +266,16 @@ __device__ __forceinline__ void stencil_band(const unsigned int *__restrict__ ti
   }
 }
 
-__device__ __forceinline__ void cp_async4(unsigned int *smem_dst, const void *gmem_src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned int)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
-}
-
 template <int KIND>
 __global__ void __launch_bounds__(kStThreads)
 stencil3_kernel(const uint8_t *__restrict__ src, int row_stride, size_t frame_stride, int w, int h, int tiles_x, int tiles_y,
                 unsigned int n_tiles, int16_t *__restrict__ out, int word_ok) {
-  // Three tile buffers, filled two tiles ahead: a tile's compute is about as long as a DRAM round trip under load, so a
-  // distance of one tile leaves the loads exposed (measured: 18 % of the stall samples on the first use of the prefetched
-  // words).  Trip k: wait for this thread's copies of tile k, barrier (everybody's copies of k have landed and everybody is
-  // done with tile k - 1, whose buffer is the one filled next), start the fill of tile k + 2, compute tile k.
-  __shared__ __align__(16) unsigned int s_tile[3][(kTileH + 2) * kPitchW];
-  constexpr int kRowsPerWarp = (kTileH + 2 + 7) / 8;  // fill: warp wid takes tile rows wid, wid + 8, ..: lane = interior word
+  // two tile buffers: staging tile k + 1 may start while other warps still compute tile k, so one barrier per tile is enough
+  // (the barrier after staging k + 1 is only passed once every warp has finished computing k - 1, the buffer's last user)
+  __shared__ unsigned int s_tile[2][(kTileH + 2) * kPitchW];
+  constexpr int kRowsPerWarp = (kTileH + 2 + 7) / 8;  // staging: warp wid takes tile rows wid, wid + 8, ..: lane = interior word
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const bool store8 = (w % 4 == 0) && ((uintptr_t)out % 8 == 0);
-  // asynchronous fill (cp.async, 4 bytes each) needs aligned whole words everywhere: rows are clamped through the address, the
-  // column clamps at x = -1 and x = w are applied when the window is read (stencil_band's fix-ups).  Other shapes: plain
-  // loads with clamped bytes, stored to the same buffer at the same point of the trip.
-  const bool async_ok = word_ok && (w % 4 == 0);
   // tile walk: (frame, tile row, tile column) advanced by the grid size without dividing again
   struct Tile {
     unsigned int f;
@@ -304,84 +292,76 @@ stencil3_kernel(const uint8_t *__restrict__ src, int row_stride, size_t frame_st
     if (T.ty >= tiles_y) T.ty -= tiles_y, T.f++;
     return T;
   };
+  // The next tile's words are fetched into registers while the current one is computed from shared memory.
   // Interior word (r, lane + 1) = image columns x0 + 4 lane .. + 3 of row clamp(y0 - 1 + r); the two halo words of a row
-  // only ever contribute one byte each: p(x0 - 1) as byte 3 of word 0 and p(x0 + 128) as byte 0 of word 33.
-  auto fill = [&](const Tile &T, unsigned int *tile) {
+  // only ever contribute one byte each: p(max(x0 - 1, 0)) as byte 3 of word 0 and p(min(x0 + 128, w - 1)) as byte 0 of word 33.
+  unsigned int regs[kRowsPerWarp], halo = 0;
+  auto fetch = [&](const Tile &T) {
     const uint8_t *img = src + (size_t)T.f * frame_stride;
     const int x0 = T.tx * kTileW, y0 = T.ty * kTileH, gx = x0 + 4 * lane;
-    if (async_ok) {
+    if (word_ok && y0 > 0 && y0 + kTileH < h && x0 + kTileW <= w) {  // no clamping anywhere inside the tile (block-uniform)
+      const uint8_t *p = img + (size_t)(y0 - 1 + wid) * row_stride + gx;
 #pragma unroll
-      for (int j = 0; j < kRowsPerWarp; j++) {
-        const int r = wid + 8 * j;
-        if (r < kTileH + 2 && gx < w) {
-          int gy = y0 - 1 + r;
-          gy = gy < 0 ? 0 : (gy > h - 1 ? h - 1 : gy);
-          cp_async4(tile + r * kPitchW + lane + 1, img + (size_t)gy * row_stride + gx);
-        }
-      }
-      if (threadIdx.x < 2 * (kTileH + 2)) {
-        const int r = threadIdx.x >> 1, right = threadIdx.x & 1;
-        int gy = y0 - 1 + r;
-        gy = gy < 0 ? 0 : (gy > h - 1 ? h - 1 : gy);
-        const int c = right ? x0 + kTileW : x0 - 4;  // the whole aligned word that holds the halo byte
-        if (c >= 0 && c < w) cp_async4(tile + r * kPitchW + (right ? kPitchW - 1 : 0), img + (size_t)gy * row_stride + c);
-      }
+      for (int j = 0; j < kRowsPerWarp; j++, p += 8 * (size_t)row_stride)
+        regs[j] = wid + 8 * j < kTileH + 2 ? __ldg(reinterpret_cast<const unsigned int *>(p)) : 0u;
     } else {
 #pragma unroll
       for (int j = 0; j < kRowsPerWarp; j++) {
         const int r = wid + 8 * j;
+        unsigned int v = 0;
         if (r < kTileH + 2 && gx <= w) {  // (a word that starts right of column w is never read by a live output)
           int gy = y0 - 1 + r;
           gy = gy < 0 ? 0 : (gy > h - 1 ? h - 1 : gy);
           const uint8_t *row = img + (size_t)gy * row_stride;
-          unsigned int v = 0;
           if (word_ok && gx + 3 < w) {
             v = __ldg(reinterpret_cast<const unsigned int *>(row + gx));
           } else {
 #pragma unroll
             for (int b = 0; b < 4; b++) v |= (unsigned int)__ldg(row + (gx + b > w - 1 ? w - 1 : gx + b)) << (8 * b);
           }
-          tile[r * kPitchW + lane + 1] = v;
         }
-      }
-      if (threadIdx.x < 2 * (kTileH + 2)) {
-        const int r = threadIdx.x >> 1, right = threadIdx.x & 1;
-        int gy = y0 - 1 + r;
-        gy = gy < 0 ? 0 : (gy > h - 1 ? h - 1 : gy);
-        int c = right ? x0 + kTileW : x0 - 1;
-        c = c < 0 ? 0 : (c > w - 1 ? w - 1 : c);
-        const unsigned int v = __ldg(img + (size_t)gy * row_stride + c);
-        tile[r * kPitchW + (right ? kPitchW - 1 : 0)] = right ? v : v << 24;
+        regs[j] = v;
       }
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");  // (an empty group when nothing was copied: the counts stay in step)
+    if (threadIdx.x < 2 * (kTileH + 2)) {
+      const int r = threadIdx.x >> 1, right = threadIdx.x & 1;
+      int gy = y0 - 1 + r;
+      gy = gy < 0 ? 0 : (gy > h - 1 ? h - 1 : gy);
+      int c = right ? x0 + kTileW : x0 - 1;
+      c = c < 0 ? 0 : (c > w - 1 ? w - 1 : c);
+      halo = __ldg(img + (size_t)gy * row_stride + c);
+    }
+  };
+  auto stage = [&](unsigned int *tile) {
+#pragma unroll
+    for (int j = 0; j < kRowsPerWarp; j++)
+      if (wid + 8 * j < kTileH + 2) tile[(wid + 8 * j) * kPitchW + lane + 1] = regs[j];
+    if (threadIdx.x < 2 * (kTileH + 2)) {
+      const int r = threadIdx.x >> 1, right = threadIdx.x & 1;
+      tile[r * kPitchW + (right ? kPitchW - 1 : 0)] = right ? halo : halo << 24;
+    }
   };
   unsigned int t = blockIdx.x;
   Tile cur;
   cur.f = t / tiles_per_frame;
   cur.ty = (int)((t - cur.f * tiles_per_frame) / (unsigned)tiles_x), cur.tx = (int)(t - cur.f * tiles_per_frame) - cur.ty * tiles_x;
-  Tile nxt = advance(cur);
-  if (t < n_tiles) fill(cur, s_tile[0]); else asm volatile("cp.async.commit_group;" ::: "memory");
-  if (t + gridDim.x < n_tiles) fill(nxt, s_tile[1]); else asm volatile("cp.async.commit_group;" ::: "memory");
-  for (int buf = 0; t < n_tiles; t += gridDim.x, buf = buf == 2 ? 0 : buf + 1) {
-    asm volatile("cp.async.wait_group 1;" ::: "memory");  // this thread's copies of the current tile are done (the next tile's may fly)
+  if (t < n_tiles) fetch(cur);
+  for (int buf = 0; t < n_tiles; t += gridDim.x, buf ^= 1) {
+    unsigned int *tile = s_tile[buf];
+    stage(tile);
     __syncthreads();
-    const Tile nn = advance(nxt);
-    unsigned int *ahead = s_tile[buf == 0 ? 2 : buf - 1];  // (buf + 2) % 3: the buffer of tile k - 1
-    if (t + 2 * gridDim.x < n_tiles && t + 2 * gridDim.x >= t) fill(nn, ahead); else asm volatile("cp.async.commit_group;" ::: "memory");
-    const unsigned int *tile = s_tile[buf];
+    const Tile nxt = advance(cur);
+    if (t + gridDim.x < n_tiles) fetch(nxt);
     const int x0 = cur.tx * kTileW, y0 = cur.ty * kTileH, x = x0 + 4 * lane;
     const int r0 = wid * 8;                    // first output row of this warp inside the tile
     const int rows_live = h - (y0 + r0);       // rows of this warp that exist in the image (>= 8: all of them)
     if (x < w && rows_live > 0) {
       int16_t *o = out + ((size_t)cur.f * h + (y0 + r0)) * (size_t)w + x;
-      const bool fix_left = async_ok && x == 0, fix_right = async_ok && x + 4 == w;
-      if (store8 && x + 3 < w && rows_live >= 8) stencil_band<KIND, true>(tile, lane, r0, o, w, x, rows_live, fix_left, fix_right);
-      else stencil_band<KIND, false>(tile, lane, r0, o, w, x, rows_live, fix_left, fix_right);
+      if (store8 && x + 3 < w && rows_live >= 8) stencil_band<KIND, true>(tile, lane, r0, o, w, x, rows_live);
+      else stencil_band<KIND, false>(tile, lane, r0, o, w, x, rows_live);
     }
-    cur = nxt, nxt = nn;
+    cur = nxt;
   }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 }  // namespace
