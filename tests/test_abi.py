@@ -46,6 +46,16 @@ def test_exports_every_declared_c_symbol():
     assert not missing, missing
 
 
+def test_header_is_plain_c99_and_links(tmp_path):
+    """include/b200_dmz.h compiled by a strict C99 compiler, the caller linked with the library and run (host-side calls only)."""
+    exe = str(tmp_path / "c_abi_main")
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c_abi_main.c"), "-o", exe, "-L" + os.path.dirname(LIB), "-lb200dmz",
+                           "-Wl,-rpath," + os.path.dirname(LIB)])
+    out = subprocess.check_output([exe], text=True).split()
+    assert out[:3] == ["0", "0", "808"]  # not complete, no digits, sizeof(b200_frame_record)
+
+
 def test_exports_reference_cxx_entry_points():
     missing = set(REFERENCE_SYMBOLS) - exported()
     assert not missing, missing
