@@ -461,7 +461,8 @@ def pipeline_config(args):
                "fraction_of_host_h2d_ceiling": e2e_value / world * h2d_per_frame / 1e9 / ceiling,
                "note": "host frames are full 640x480 planes in pinned memory; the library uploads only the detection-region rectangle (+2 px) of each "
                        "(%d B per frame) and re-uploads a whole frame if its card quad reaches outside it; the ceiling is a contiguous pinned H2D copy "
-                       "run by all %d rank(s) at once on this host" % (int(h2d_per_frame), world),
+                       "run by all %d rank(s) at once on this host; the same link delivers 47.95 GB/s for this rectangle of 480-of-640-byte rows whatever "
+                       "moves it (pitched DMA on 1 / 2 / 4 streams, a zero-copy kernel, hybrids: profiles/r04_h2d_rectangle_microbench.txt)" % (int(h2d_per_frame), world),
                "digit_strings_gathered": dist is not None,
                "timing": "wall clock around the synchronous C-ABI calls (+ the gather), max over ranks", "rank0_cpu_binding": g.numa}
 
