@@ -222,7 +222,7 @@ void stencil_into(IplImage *src, IplImage *dst, int kind) {
   CtxCall call_guard(ctx);
   if (!ctx) return;
   const size_t plane = (size_t)vs.w * vs.h;
-  uint8_t *tmp = (uint8_t *)malloc(plane * 3);
+  uint8_t *tmp = (uint8_t *)malloc(plane * 3 + 2);  // the plane, one byte of padding when its size is odd, the int16 result
   pack_rows(vs, tmp);
   int16_t *dense = (int16_t *)(tmp + plane + (plane & 1));
   if (b200_stencil3_batch(ctx, tmp, vs.w, plane, vs.w, vs.h, 1, kind, B200_MEM_HOST, dense) == B200_OK)
